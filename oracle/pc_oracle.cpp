@@ -1,0 +1,1087 @@
+// pc_oracle.cpp -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE)
+//
+// A plain single-threaded C++ restatement of PolyChordLite's linear-mode nested
+// sampling algorithm, used ONLY as (a) the parity checker for the CUDA engine in
+// tests/, __graft_entry__.smoke() and (b) the timed CPU baseline in bench.py.
+// Nothing under polychordlite_b200/ may include, link or call this file.
+//
+// PARITY STATUS: "parity unpinned by the reference" -- the reference
+// (/root/reference, Fortran) cannot be compiled in this image (no gfortran) and its
+// own tests hold no numeric golden vectors (tests/test_run_pypolychord.py asserts
+// behaviour only).  This oracle is therefore pinned to (i) the analytic evidences the
+// built-in likelihoods are normalised to (likelihoods/examples/gaussian.f90:8-9,
+// rastrigin.f90:33), (ii) scipy/numpy for the numeric helpers (AS241, Cholesky,
+// logsumexp), (iii) a brute-force Monte-Carlo check of the evidence recurrences and
+// (iv) the published Philox4x32-10 known-answer vectors.  See tests/test_oracle_*.py.
+//
+// Reference sites restated here (all paths relative to /root/reference/src/polychord):
+//   nested_sampling.F90:140-405   driver, linear branch          -> Run::run()
+//   generate.F90:19-55            GenerateSeed                   -> Run::generate_seed()
+//   generate.F90:153-183,283-320  GenerateLivePoints (linear)    -> Run::generate_live_points()
+//   chordal_sampling.f90:7-92     SliceSampling                  -> Run::slice_sampling()
+//   chordal_sampling.f90:94-145   generate_nhats                 -> generate_nhats()
+//   chordal_sampling.f90:163-273  slice_sample                   -> Run::slice_sample()
+//   calculate.f90:6-50            calculate_point                -> Run::calculate_point()
+//   run_time_info.f90:211-296     update_evidence                -> Run::update_evidence()
+//   run_time_info.f90:601-641     calculate_covmats              -> Run::calculate_covmats()
+//   run_time_info.f90:652-678     calculate_logZ_estimate        -> Run::logZ_estimate()
+//   run_time_info.f90:683-709     live_logZ                      -> Run::live_logZ()
+//   run_time_info.f90:716-787     replace_point                  -> Run::replace_point()
+//   run_time_info.f90:789-817     delete_outermost_point         -> Run::delete_outermost_point()
+//   run_time_info.f90:820-877     clean_phantoms                 -> Run::clean_phantoms()
+//   run_time_info.f90:883-909     find_min_loglikelihoods        -> Run::find_min()
+//   run_time_info.f90:913-949     identify_cluster               -> Run::identify_cluster()
+//   random_utils.F90:381-437      random_orthonormal_basis/bases -> random_orthonormal_basis()
+//   random_utils.F90:505-532      shuffle_deck                   -> shuffle_deck()
+//   random_utils.F90:581-614      random_inverse_covmat          -> random_inverse_covmat()
+//   utils.F90:362-439             logsumexp/logaddexp/logincexp  -> same names
+//   utils.F90:621-649             calc_cholesky                  -> calc_cholesky()
+//   utils.F90:777-966             inv_normal_cdf (AS241 PPND16)  -> inv_normal_cdf()
+//   utils.F90:1028-1048           log_gauss                      -> loglike_corr_gaussian()
+//   array_utils.f90:396-458       add_point / delete_point       -> push_back / swap-with-last
+//   likelihoods/examples/{gaussian,rastrigin,random_gaussian}.f90
+//   priors.f90:40-55              uniform_htp                    -> Run::prior()
+//
+// The one thing that cannot be restated is the random stream: the reference draws
+// from libgfortran's random_number in program order (random_utils.F90:128).  The
+// oracle instead uses the counter-based stream spec shared with the CUDA engine
+// (DESIGN.md "RNG stream spec"): Philox4x32-10, key=(seed,tag), counter=(a,b,uid).
+//
+// Two scheduling modes:
+//   batch_K == 0 : REFERENCE MODE.  One death + one birth per iteration, seed drawn
+//                  from all live points, swap-with-last deletion: the faithful
+//                  restatement of nested_sampling.F90:239-374.  This is the CPU baseline.
+//   batch_K >= 1 : BATCHED-GENERATION MODE.  The K lowest points die together (evidence
+//                  updated sequentially with n, n-1, ... exactly as the reference's own
+//                  final kill-off nested_sampling.F90:381-384 does), K chains are seeded
+//                  from the n-K survivors at the contour of the K-th lowest, babies are
+//                  written into the vacated slots.  This is the schedule the GPU engine
+//                  runs; the oracle in this mode is the bit-for-bit (up to FP
+//                  re-association) checker for it.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include <limits>
+#include <numeric>
+#include <chrono>
+
+namespace {
+
+// ----------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  Written independently of the engine's copy;
+// both are pinned to the published known-answer vectors in tests.
+// ----------------------------------------------------------------------------------
+struct U4 { uint32_t v[4]; };
+
+inline U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)M0 * c0;
+        uint64_t p1 = (uint64_t)M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    return U4{{c0, c1, c2, c3}};
+}
+
+enum Tag : uint32_t { TAG_INIT = 1, TAG_SEED = 2, TAG_DIR = 3, TAG_SHUF = 4, TAG_SLICE = 5, TAG_POST = 6, TAG_LIKE = 7 };
+
+inline double u64_to_unit(uint64_t x) {
+    // 52 random bits + 1/2 ulp offset: strictly inside (0,1), exactly representable.
+    return ((double)(x >> 12) + 0.5) * (1.0 / 4503599627370496.0);
+}
+
+struct Rng {
+    uint32_t seed;
+    // first 64-bit lane of the Philox block
+    double uniform(uint32_t tag, uint64_t uid, uint32_t a, uint32_t b) const {
+        U4 o = philox4x32_10(a, b, (uint32_t)uid, (uint32_t)(uid >> 32), seed, tag);
+        return u64_to_unit((uint64_t)o.v[0] | ((uint64_t)o.v[1] << 32));
+    }
+    // both 64-bit lanes
+    void uniform2(uint32_t tag, uint64_t uid, uint32_t a, uint32_t b, double& u0, double& u1) const {
+        U4 o = philox4x32_10(a, b, (uint32_t)uid, (uint32_t)(uid >> 32), seed, tag);
+        u0 = u64_to_unit((uint64_t)o.v[0] | ((uint64_t)o.v[1] << 32));
+        u1 = u64_to_unit((uint64_t)o.v[2] | ((uint64_t)o.v[3] << 32));
+    }
+};
+
+// ----------------------------------------------------------------------------------
+// numeric helpers (utils.F90)
+// ----------------------------------------------------------------------------------
+const double LOG_TWO_PI = 1.8378770664093454835606594728112;
+const double HUGE_D = std::numeric_limits<double>::max();
+
+// AS241 PPND16 (Wichura 1988); utils.F90:806-966 uses the same published algorithm.
+double inv_normal_cdf(double p) {
+    static const double a[8] = {3.3871328727963666080, 1.3314166789178437745e+2, 1.9715909503065514427e+3,
+                                1.3731693765509461125e+4, 4.5921953931549871457e+4, 6.7265770927008700853e+4,
+                                3.3430575583588128105e+4, 2.5090809287301226727e+3};
+    static const double b[8] = {1.0, 4.2313330701600911252e+1, 6.8718700749205790830e+2, 5.3941960214247511077e+3,
+                                2.1213794301586595867e+4, 3.9307895800092710610e+4, 2.8729085735721942674e+4,
+                                5.2264952788528545610e+3};
+    static const double c[8] = {1.42343711074968357734, 4.63033784615654529590, 5.76949722146069140550,
+                                3.64784832476320460504, 1.27045825245236838258, 2.41780725177450611770e-1,
+                                2.27238449892691845833e-2, 7.74545014278341407640e-4};
+    static const double d[8] = {1.0, 2.05319162663775882187, 1.67638483018380384940, 6.89767334985100004550e-1,
+                                1.48103976427480074590e-1, 1.51986665636164571966e-2, 5.47593808499534494600e-4,
+                                1.05075007164441684324e-9};
+    static const double e[8] = {6.65790464350110377720, 5.46378491116411436990, 1.78482653991729133580,
+                                2.96560571828504891230e-1, 2.65321895265761230930e-2, 1.24266094738807843860e-3,
+                                2.71155556874348757815e-5, 2.01033439929228813265e-7};
+    static const double f[8] = {1.0, 5.99832206555887937690e-1, 1.36929880922735805310e-1, 1.48753612908506148525e-2,
+                                7.86869131145613259100e-4, 1.84631831751005468180e-5, 1.42151175831644588870e-7,
+                                2.04426310338993978564e-15};
+    auto poly = [](const double* co, double x) {
+        double v = 0.0;
+        for (int i = 7; i >= 0; --i) v = v * x + co[i];
+        return v;
+    };
+    if (p <= 0.0) return -HUGE_D;
+    if (p >= 1.0) return HUGE_D;
+    double q = p - 0.5;
+    if (std::fabs(q) <= 0.425) {
+        double r = 0.180625 - q * q;
+        return q * poly(a, r) / poly(b, r);
+    }
+    double r = (q < 0.0) ? p : 1.0 - p;
+    r = std::sqrt(-std::log(r));
+    double val;
+    if (r <= 5.0) {
+        r -= 1.6;
+        val = poly(c, r) / poly(d, r);
+    } else {
+        r -= 5.0;
+        val = poly(e, r) / poly(f, r);
+    }
+    return (q < 0.0) ? -val : val;
+}
+
+inline double logaddexp(double la, double lb) {
+    if (la > lb) return la + std::log(std::exp(lb - la) + 1.0);
+    return lb + std::log(std::exp(la - lb) + 1.0);
+}
+inline void logincexp(double& la, double lb) { la = logaddexp(la, lb); }
+inline void logincexp(double& la, double lb, double lc) {
+    la = logaddexp(la, lb);
+    la = logaddexp(la, lc);
+}
+double logsumexp(const double* v, size_t n) {
+    double m = v[0];
+    for (size_t i = 1; i < n; ++i) m = std::max(m, v[i]);
+    double s = 0.0;
+    for (size_t i = 0; i < n; ++i) s += std::exp(v[i] - m);
+    return m + std::log(s);
+}
+
+// utils.F90:621-649.  a, L column-major D x D.  Falls back to sqrt(trace)*I.
+void calc_cholesky(const double* a, double* L, int D) {
+    std::fill(L, L + (size_t)D * D, 0.0);
+    for (int i = 0; i < D; ++i) {
+        double s = 0.0;
+        for (int k = 0; k < i; ++k) s += L[i + (size_t)k * D] * L[i + (size_t)k * D];
+        double dii = a[i + (size_t)i * D] - s;
+        if (dii <= 0.0) {
+            double tr = 0.0;
+            for (int k = 0; k < D; ++k) tr += a[k + (size_t)k * D];
+            std::fill(L, L + (size_t)D * D, 0.0);
+            for (int k = 0; k < D; ++k) L[k + (size_t)k * D] = std::sqrt(tr);
+            return;
+        }
+        dii = std::sqrt(dii);
+        L[i + (size_t)i * D] = dii;
+        for (int j = i + 1; j < D; ++j) {
+            double t = 0.0;
+            for (int k = 0; k < i; ++k) t += L[i + (size_t)k * D] * L[j + (size_t)k * D];
+            L[j + (size_t)i * D] = (a[i + (size_t)j * D] - t) / dii;
+        }
+    }
+}
+
+// random_utils.F90:381-403 with random_direction (:276-298) and random_gaussian (:251-266).
+// basis is column-major D x D; Gaussian element (row r, column c) of basis number
+// `col0/D` comes from stream (tag, uid, a = col0 + c, b = r/2), lane r%2.
+void random_orthonormal_basis(const Rng& rng, uint32_t tag, uint64_t uid, int col0, int D, double* basis) {
+    for (int i = 0; i < D; ++i) {
+        double* v = basis + (size_t)i * D;
+        for (int r = 0; r < D; r += 2) {
+            double u0, u1;
+            rng.uniform2(tag, uid, (uint32_t)(col0 + i), (uint32_t)(r / 2), u0, u1);
+            v[r] = inv_normal_cdf(u0);
+            if (r + 1 < D) v[r + 1] = inv_normal_cdf(u1);
+        }
+        // random_direction: normalise the Gaussian vector first
+        double n2 = 0.0;
+        for (int r = 0; r < D; ++r) n2 += v[r] * v[r];
+        double inv = std::sqrt(n2);
+        for (int r = 0; r < D; ++r) v[r] /= inv;
+        // Gram-Schmidt against the earlier vectors, each projection on the updated vector
+        for (int j = 0; j < i; ++j) {
+            const double* q = basis + (size_t)j * D;
+            double dot = 0.0;
+            for (int r = 0; r < D; ++r) dot += v[r] * q[r];
+            for (int r = 0; r < D; ++r) v[r] -= dot * q[r];
+        }
+        double m2 = 0.0;
+        for (int r = 0; r < D; ++r) m2 += v[r] * v[r];
+        double m = std::sqrt(m2);
+        for (int r = 0; r < D; ++r) v[r] /= m;
+    }
+}
+
+// random_utils.F90:505-532 on deck[1..n-1] (deck[0] stays), draws from TAG_SHUF.
+void shuffle_deck_tail(const Rng& rng, uint64_t uid, std::vector<int>& deck) {
+    int n = (int)deck.size() - 1;  // size of deck(2:)
+    for (int i = n; i >= 1; --i) {
+        double u = rng.uniform(TAG_SHUF, uid, (uint32_t)i, 0);
+        int j = (int)std::ceil(u * i);
+        if (j < 1) j = 1;
+        std::swap(deck[i], deck[j]);  // deck(2:)(i) == deck[i] zero-based
+    }
+}
+
+struct Likelihood {
+    int kind = 0;  // 0 gaussian, 1 rastrigin, 2 correlated gaussian, 3 host callback
+    std::vector<double> mu, sigma;       // kind 0
+    std::vector<double> invcov;          // kind 2, column-major D x D (symmetric)
+    double logdet = 0.0;                 // kind 2
+    double (*cb)(double*, int, double*, int) = nullptr;  // kind 3
+    // loop invariants of gaussian.f90 hoisted out of the call (the values are identical to
+    // recomputing them per call as the Fortran source is written; this only keeps the timed
+    // CPU baseline from being slower than an optimising Fortran compiler would make it)
+    double gauss_norm = 0.0, Vn = 0.0, log_rast = 0.0;
+};
+
+struct Prior {
+    int kind = 0;  // 0 uniform box (priors.f90:40-55), 1 host callback
+    std::vector<double> lo, hi;
+    void (*cb)(double*, double*, int) = nullptr;
+};
+
+}  // namespace
+
+extern "C" {
+
+struct oracle_settings {
+    int nDims, nDerived, nlive, num_repeats, nprior, nfail;
+    int do_clustering;
+    double precision_criterion, logzero;
+    int max_ndead;
+    double boost_posterior;
+    int posteriors, equals, cluster_posteriors;
+    double compression_factor;
+    int seed;
+    int batch_K;  // 0 = reference mode, >=1 batched generations
+};
+
+struct oracle_result {
+    double logZ, logZerr;     // calculate_logZ_estimate
+    double logZ_raw, logZ2_raw;  // RTI%logZ, RTI%logZ2
+    long long ndead, nlike, nchains, ngenerations, nupdates, nfailures;
+    long long nslices, nphantoms_final;
+    double seconds;
+};
+
+typedef void (*oracle_dumper_t)(int ndead, int nlive, int npars, double* live, double* dead, double* logweights,
+                                double logZ, double logZerr);
+}
+
+namespace {
+
+struct Cluster {
+    std::vector<double> live;     // T x nlive, point-major
+    std::vector<double> phantom;  // T x nphantom
+    std::vector<double> stack_l;  // pos_l of the posterior stack since the last update (deaths of this cluster)
+    int nlive = 0, nphantom = 0;
+    double logZp, logXp, logZXp, logZp2, logZpXp;
+    double logLp;
+    int imin = -1;
+    std::vector<double> covmat, cholesky;  // column-major D x D
+};
+
+struct Run {
+    oracle_settings S;
+    Likelihood like;
+    Prior pri;
+    Rng rng;
+    int D, P, T, R;
+    int h0, p0, d0, b0, l0;
+
+    std::vector<double> sc_R, sc_L, sc_cube, sc_theta;  // scratch (no heap traffic in the hot loop)
+    std::vector<Cluster> cl;
+    std::vector<double> logXpXq;  // ncluster x ncluster
+    double logZ, logZ2, logX_last_update;
+    std::vector<double> dead;  // T x ndead
+    std::vector<double> logweights;
+    long long ndead = 0, nlike = 0, nchains = 0, ngen = 0, nupdates = 0, nfail_total = 0, nslices = 0;
+    oracle_dumper_t dumper = nullptr;
+
+    void init_layout() {
+        D = S.nDims; P = S.nDerived; T = 2 * D + P + 2; R = S.num_repeats;
+        h0 = 0; p0 = D; d0 = 2 * D; b0 = 2 * D + P; l0 = b0 + 1;  // settings.f90:163-182 (zero-based)
+        rng.seed = (uint32_t)S.seed;
+    }
+
+    // ---- prior + likelihood (calculate.f90:6-50) ----
+    void prior(const double* cube, double* theta) {
+        if (pri.kind == 0) {
+            for (int i = 0; i < D; ++i) theta[i] = pri.lo[i] + (pri.hi[i] - pri.lo[i]) * cube[i];
+        } else {
+            std::vector<double> c(cube, cube + D);
+            pri.cb(c.data(), theta, D);
+        }
+    }
+    double loglikelihood(const double* theta, double* phi) {
+        switch (like.kind) {
+            case 0: {  // gaussian.f90:12-41
+                double norm = like.gauss_norm, chi = 0.0, r2 = 0.0;
+                for (int i = 0; i < D; ++i) {
+                    double z = (theta[i] - like.mu[i]) / like.sigma[i];
+                    chi += z * z;
+                    r2 += (theta[i] - like.mu[i]) * (theta[i] - like.mu[i]);
+                }
+                if (P >= 1) phi[0] = std::sqrt(r2);
+                if (P >= 2) {
+                    // log( r^D * Vn(D) ), Vn = pi^(D/2) / Gamma(1 + D/2)   (utils.F90:754-760)
+                    phi[1] = std::log(std::pow(phi[0], (double)D) * like.Vn);
+                }
+                for (int i = 2; i < P; ++i) phi[i] = 0.0;
+                return -norm - chi / 2.0;
+            }
+            case 1: {  // rastrigin.f90:20-35
+                const double TwoPi = 8.0 * std::atan(1.0);
+                double s = 0.0;
+                for (int i = 0; i < D; ++i)
+                    s += like.log_rast + theta[i] * theta[i] - 10.0 * std::cos(TwoPi * theta[i]);
+                for (int i = 0; i < P; ++i) phi[i] = 0.0;
+                return -s;
+            }
+            case 2: {  // utils.F90:1028-1048
+                double q = 0.0;
+                for (int r = 0; r < D; ++r) {
+                    double y = 0.0;
+                    for (int c = 0; c < D; ++c) y += like.invcov[r + (size_t)c * D] * (theta[c] - like.mu[c]);
+                    q += (theta[r] - like.mu[r]) * y;
+                }
+                for (int i = 0; i < P; ++i) phi[i] = 0.0;
+                return -(D * LOG_TWO_PI + like.logdet) / 2.0 - q / 2.0;
+            }
+            default: {
+                std::vector<double> th(theta, theta + D);
+                return like.cb(th.data(), D, phi, P);
+            }
+        }
+    }
+    void calculate_point(double* point, long long& n) {
+        const double* cube = point + h0;
+        bool out = false;
+        for (int i = 0; i < D; ++i) out = out || cube[i] < 0.0 || cube[i] > 1.0;
+        double logL;
+        double* theta = point + p0;
+        double* phi = point + d0;
+        if (out) {
+            for (int i = 0; i < D; ++i) theta[i] = 0.0;
+            logL = S.logzero;
+        } else {
+            prior(cube, theta);
+            logL = loglikelihood(theta, phi);
+        }
+        if (logL > S.logzero) n += 1;
+        point[l0] = logL;
+    }
+
+    // ---- chordal_sampling.f90 ----
+    // generate_nhats for a single grade (grade_dims = [nDims]).
+    void generate_nhats(uint64_t uid, std::vector<double>& nhats) {
+        nhats.assign((size_t)D * R, 0.0);
+        std::vector<double> raw((size_t)D * R), basis((size_t)D * D);
+        int lower = 0;
+        // random_orthonormal_bases: full bases while upper_index < num_nhats, then one more, truncated
+        while (lower + D < R) {
+            random_orthonormal_basis(rng, TAG_DIR, uid, lower, D, basis.data());
+            std::copy(basis.begin(), basis.end(), raw.begin() + (size_t)lower * D);
+            lower += D;
+        }
+        random_orthonormal_basis(rng, TAG_DIR, uid, lower, D, basis.data());
+        std::copy(basis.begin(), basis.begin() + (size_t)(R - lower) * D, raw.begin() + (size_t)lower * D);
+        std::vector<int> deck(R);
+        std::iota(deck.begin(), deck.end(), 0);
+        shuffle_deck_tail(rng, uid, deck);
+        for (int i = 0; i < R; ++i)
+            std::copy(raw.begin() + (size_t)deck[i] * D, raw.begin() + (size_t)(deck[i] + 1) * D, nhats.begin() + (size_t)i * D);
+    }
+
+    // slice_sample, chordal_sampling.f90:163-273
+    void slice_sample(double logL, const double* nhat, const double* x0, double w, uint64_t uid, int step,
+                      double* baby, long long& n) {
+        sc_R.assign(T, 0.0); sc_L.assign(T, 0.0);
+        std::vector<double>&Rp = sc_R, &Lp = sc_L;
+        std::fill(baby, baby + T, 0.0);
+        double u0 = rng.uniform(TAG_SLICE, uid, (uint32_t)step, 0);
+        for (int i = 0; i < D; ++i) {
+            Lp[h0 + i] = x0[h0 + i] - u0 * w * nhat[i];
+            Rp[h0 + i] = x0[h0 + i] + (1.0 - u0) * w * nhat[i];
+        }
+        calculate_point(Rp.data(), n);
+        calculate_point(Lp.data(), n);
+        int i_step = 0;
+        while (Rp[l0] >= logL && Rp[l0] > S.logzero) {
+            i_step++;
+            for (int i = 0; i < D; ++i) Rp[h0 + i] = x0[h0 + i] + nhat[i] * w * i_step;
+            calculate_point(Rp.data(), n);
+        }
+        i_step = 0;
+        while (Lp[l0] >= logL && Lp[l0] > S.logzero) {
+            i_step++;
+            for (int i = 0; i < D; ++i) Lp[h0 + i] = x0[h0 + i] - nhat[i] * w * i_step;
+            calculate_point(Lp.data(), n);
+        }
+        for (i_step = 0; i_step <= 100; ++i_step) {
+            double dL2 = 0.0, dR2 = 0.0;
+            for (int i = 0; i < D; ++i) {
+                dL2 += (x0[h0 + i] - Lp[h0 + i]) * (x0[h0 + i] - Lp[h0 + i]);
+                dR2 += (x0[h0 + i] - Rp[h0 + i]) * (x0[h0 + i] - Rp[h0 + i]);
+            }
+            double x0Ld = std::sqrt(dL2), x0Rd = std::sqrt(dR2);
+            double u = rng.uniform(TAG_SLICE, uid, (uint32_t)step, (uint32_t)(1 + i_step));
+            double t = u * (x0Rd + x0Ld) - x0Ld;
+            for (int i = 0; i < D; ++i) baby[h0 + i] = x0[h0 + i] + t * nhat[i];
+            calculate_point(baby, n);
+            if (baby[l0] < logL || baby[l0] <= S.logzero) {
+                double dot = 0.0;
+                for (int i = 0; i < D; ++i) dot += (baby[h0 + i] - x0[h0 + i]) * nhat[i];
+                if (dot > 0.0) std::copy(baby, baby + T, Rp.begin());
+                else std::copy(baby, baby + T, Lp.begin());
+            } else {
+                return;
+            }
+        }
+        baby[l0] = S.logzero;  // "Non deterministic loglikelihood"
+    }
+
+    // SliceSampling, chordal_sampling.f90:7-92.  babies: T x R point-major.
+    void slice_sampling(double logL, const double* seed_point, const double* cholesky, uint64_t uid,
+                        std::vector<double>& babies, long long& n) {
+        std::vector<double> nhats;
+        generate_nhats(uid, nhats);
+        // nhats = matmul(cholesky, nhats)
+        std::vector<double> wh((size_t)D * R);
+        for (int c = 0; c < R; ++c)
+            for (int r = 0; r < D; ++r) {
+                double s = 0.0;
+                for (int k = 0; k < D; ++k) s += cholesky[r + (size_t)k * D] * nhats[k + (size_t)c * D];
+                wh[r + (size_t)c * D] = s;
+            }
+        babies.assign((size_t)T * R, 0.0);
+        std::vector<double> prev(seed_point, seed_point + T), nhat(D);
+        for (int i = 0; i < R; ++i) {
+            double w2 = 0.0;
+            for (int r = 0; r < D; ++r) w2 += wh[r + (size_t)i * D] * wh[r + (size_t)i * D];
+            double w = std::sqrt(w2);
+            for (int r = 0; r < D; ++r) nhat[r] = wh[r + (size_t)i * D] / w;
+            w *= 3.0;
+            double* baby = babies.data() + (size_t)i * T;
+            slice_sample(logL, nhat.data(), prev.data(), w, uid, i, baby, n);
+            std::copy(baby, baby + T, prev.begin());
+            nslices++;
+        }
+    }
+
+    // ---- run_time_info.f90 ----
+    void initialise() {
+        cl.assign(1, Cluster());
+        Cluster& c = cl[0];
+        c.logZp = c.logZXp = c.logZp2 = c.logZpXp = S.logzero;
+        c.logXp = 0.0;
+        c.logLp = S.logzero;
+        c.covmat.assign((size_t)D * D, 0.0);
+        c.cholesky.assign((size_t)D * D, 0.0);
+        for (int i = 0; i < D; ++i) c.covmat[i + (size_t)i * D] = c.cholesky[i + (size_t)i * D] = 1.0;
+        logXpXq.assign(1, 0.0);
+        logZ = logZ2 = S.logzero;
+        logX_last_update = 0.0;
+    }
+    double& XX(int p, int q) { return logXpXq[(size_t)p * cl.size() + q]; }
+
+    // update_evidence, run_time_info.f90:211-296
+    double update_evidence(int p) {
+        Cluster& c = cl[p];
+        const double log2 = std::log(2.0);
+        double logL = c.logLp;
+        double lognp = std::log(c.nlive + 0.0), lognp1 = std::log(c.nlive + 1.0), lognp2 = std::log(c.nlive + 2.0);
+        double logweight = c.logXp - lognp1;
+        logincexp(logZ, c.logXp + logL - lognp1);
+        logincexp(c.logZp, c.logXp + logL - lognp1);
+        c.logXp = c.logXp + lognp - lognp1;
+        logincexp(logZ2, log2 + c.logZXp + logL - lognp1, log2 + XX(p, p) + 2 * logL - lognp1 - lognp2);
+        c.logZXp = c.logZXp + lognp - lognp1;
+        logincexp(c.logZXp, XX(p, p) + logL + lognp - lognp1 - lognp2);
+        for (int q = 0; q < (int)cl.size(); ++q)
+            if (q != p) logincexp(cl[q].logZXp, XX(p, q) + logL - lognp1);
+        logincexp(c.logZp2, log2 + c.logZpXp + logL - lognp1, log2 + XX(p, p) + 2 * logL - lognp1 - lognp2);
+        c.logZpXp = c.logZpXp + lognp - lognp1;
+        logincexp(c.logZpXp, XX(p, p) + logL + lognp - lognp1 - lognp2);
+        XX(p, p) = XX(p, p) + lognp - lognp2;
+        for (int q = 0; q < (int)cl.size(); ++q)
+            if (q != p) {
+                XX(p, q) += lognp - lognp1;
+                XX(q, p) += lognp - lognp1;
+            }
+        return logweight;
+    }
+
+    void find_min() {
+        for (auto& c : cl) {
+            c.imin = -1;
+            double best = 0.0;
+            for (int i = 0; i < c.nlive; ++i) {
+                double l = c.live[(size_t)i * T + l0];
+                if (c.imin < 0 || l < best) { best = l; c.imin = i; }  // minloc: first minimum
+            }
+            c.logLp = (c.imin < 0) ? HUGE_D : best;
+        }
+    }
+    int min_cluster() {
+        int p = 0;
+        for (int q = 1; q < (int)cl.size(); ++q)
+            if (cl[q].logLp < cl[p].logLp) p = q;
+        return p;
+    }
+    double sum_logX() {
+        std::vector<double> v;
+        for (auto& c : cl) v.push_back(c.logXp);
+        return logsumexp(v.data(), v.size());
+    }
+    int total_live() {
+        int n = 0;
+        for (auto& c : cl) n += c.nlive;
+        return n;
+    }
+    void push_dead(const double* rec, double logw) {
+        dead.insert(dead.end(), rec, rec + T);
+        logweights.push_back(logw);
+        ndead++;
+    }
+
+    // delete_outermost_point, run_time_info.f90:789-817 (swap-with-last deletion)
+    void delete_outermost_point() {
+        int p = min_cluster();
+        Cluster& c = cl[p];
+        double logw = update_evidence(p);
+        std::vector<double> rec(c.live.begin() + (size_t)c.imin * T, c.live.begin() + (size_t)(c.imin + 1) * T);
+        std::copy(c.live.begin() + (size_t)(c.nlive - 1) * T, c.live.begin() + (size_t)c.nlive * T,
+                  c.live.begin() + (size_t)c.imin * T);
+        c.nlive--;
+        c.live.resize((size_t)c.nlive * T);
+        find_min();
+        push_dead(rec.data(), logw);
+        c.stack_l.push_back(rec[l0]);
+    }
+
+    int identify_cluster(const double* point) {
+        if (cl.size() == 1) return 0;
+        double best = HUGE_D;
+        int which = 0;
+        for (int p = 0; p < (int)cl.size(); ++p)
+            for (int i = 0; i < cl[p].nlive; ++i) {
+                double d2 = 0.0;
+                const double* q = &cl[p].live[(size_t)i * T + h0];
+                for (int k = 0; k < D; ++k) d2 += (point[h0 + k] - q[k]) * (point[h0 + k] - q[k]);
+                if (d2 < best) { best = d2; which = p; }
+            }
+        return which;
+    }
+
+    // replace_point, run_time_info.f90:716-787 (constant nlive schedule)
+    bool replace_point(const std::vector<double>& babies, int cluster_add) {
+        double logL = cl[0].logLp;
+        for (auto& c : cl) logL = std::min(logL, c.logLp);
+        for (int i = 0; i < R - 1; ++i) {
+            const double* pt = babies.data() + (size_t)i * T;
+            if (pt[l0] > logL && identify_cluster(pt) == cluster_add) {
+                Cluster& c = cl[cluster_add];
+                c.phantom.insert(c.phantom.end(), pt, pt + T);
+                c.nphantom++;
+            }
+        }
+        const double* pt = babies.data() + (size_t)(R - 1) * T;
+        bool replaced = false;
+        if (pt[l0] > logL) {
+            if (identify_cluster(pt) == cluster_add) {
+                int nlive = S.nlive;
+                if (total_live() >= std::max(nlive, 1)) {
+                    delete_outermost_point();
+                    replaced = true;
+                }
+                if (total_live() < nlive) {
+                    Cluster& c = cl[cluster_add];
+                    c.live.insert(c.live.end(), pt, pt + T);
+                    c.nlive++;
+                    find_min();
+                }
+            }
+        } else {
+            push_dead(pt, S.logzero);
+        }
+        return replaced;
+    }
+
+    // clean_phantoms, run_time_info.f90:820-877: a phantom is dropped as soon as some death
+    // of its cluster since the last update has a larger logL.  (Posterior conversion: see
+    // DESIGN.md "next" row f1 -- the oracle only needs the deletion for the covariance.)
+    void clean_phantoms() {
+        for (auto& c : cl) {
+            if (c.stack_l.empty()) continue;
+            double lmax = *std::max_element(c.stack_l.begin(), c.stack_l.end());
+            int i = 0;
+            while (i < c.nphantom) {
+                if (lmax > c.phantom[(size_t)i * T + l0]) {
+                    std::copy(c.phantom.begin() + (size_t)(c.nphantom - 1) * T, c.phantom.begin() + (size_t)c.nphantom * T,
+                              c.phantom.begin() + (size_t)i * T);
+                    c.nphantom--;
+                } else {
+                    ++i;
+                }
+            }
+            c.phantom.resize((size_t)c.nphantom * T);
+            c.stack_l.clear();
+        }
+    }
+    // batched mode keeps the phantom pool in birth order (stable compaction) so that the
+    // covariance sums run over the same sequence as the GPU engine's pool.
+    void clean_phantoms_stable() {
+        for (auto& c : cl) {
+            if (c.stack_l.empty()) continue;
+            double lmax = *std::max_element(c.stack_l.begin(), c.stack_l.end());
+            int w = 0;
+            for (int i = 0; i < c.nphantom; ++i) {
+                if (!(lmax > c.phantom[(size_t)i * T + l0])) {
+                    if (w != i)
+                        std::copy(c.phantom.begin() + (size_t)i * T, c.phantom.begin() + (size_t)(i + 1) * T,
+                                  c.phantom.begin() + (size_t)w * T);
+                    ++w;
+                }
+            }
+            c.nphantom = w;
+            c.phantom.resize((size_t)w * T);
+            c.stack_l.clear();
+        }
+    }
+
+    // calculate_covmats, run_time_info.f90:601-641
+    void calculate_covmats() {
+        for (auto& c : cl) {
+            int N = c.nlive + c.nphantom;
+            if (N == 0) continue;
+            std::vector<double> mean(D, 0.0);
+            for (int i = 0; i < c.nlive; ++i)
+                for (int k = 0; k < D; ++k) mean[k] += c.live[(size_t)i * T + h0 + k];
+            std::vector<double> mp(D, 0.0);
+            for (int i = 0; i < c.nphantom; ++i)
+                for (int k = 0; k < D; ++k) mp[k] += c.phantom[(size_t)i * T + h0 + k];
+            for (int k = 0; k < D; ++k) mean[k] = (mean[k] + mp[k]) / N;
+            std::vector<double> cov((size_t)D * D, 0.0), covp((size_t)D * D, 0.0), dv(D);
+            for (int i = 0; i < c.nlive; ++i) {
+                for (int k = 0; k < D; ++k) dv[k] = c.live[(size_t)i * T + h0 + k] - mean[k];
+                for (int b = 0; b < D; ++b)
+                    for (int a = 0; a < D; ++a) cov[a + (size_t)b * D] += dv[a] * dv[b];
+            }
+            for (int i = 0; i < c.nphantom; ++i) {
+                for (int k = 0; k < D; ++k) dv[k] = c.phantom[(size_t)i * T + h0 + k] - mean[k];
+                for (int b = 0; b < D; ++b)
+                    for (int a = 0; a < D; ++a) covp[a + (size_t)b * D] += dv[a] * dv[b];
+            }
+            for (size_t k = 0; k < cov.size(); ++k) c.covmat[k] = (cov[k] + covp[k]) / N;
+            calc_cholesky(c.covmat.data(), c.cholesky.data(), D);
+        }
+    }
+
+    double live_logZ() {
+        double r = S.logzero;
+        std::vector<double> ll;
+        for (auto& c : cl) {
+            if (c.nlive > 0) {
+                ll.resize(c.nlive);
+                for (int i = 0; i < c.nlive; ++i) ll[i] = c.live[(size_t)i * T + l0];
+                logincexp(r, logsumexp(ll.data(), ll.size()) - std::log(c.nlive + 0.0) + c.logXp);
+            }
+        }
+        return r;
+    }
+    bool more_samples_needed() {
+        if (S.max_ndead == 0) return false;
+        if (S.max_ndead > 0 && ndead >= S.max_ndead) return false;
+        if (S.precision_criterion > 0 && live_logZ() < std::log(S.precision_criterion) + logZ) return false;
+        return true;
+    }
+    void logZ_estimate(double& lz, double& var) {
+        lz = std::max(-HUGE_D, 2 * logZ - 0.5 * logZ2);
+        var = logZ2 - 2 * logZ;
+    }
+
+    // dump, nested_sampling.F90:546-590
+    void dump() {
+        if (!dumper) return;
+        int npars = D + P + 2;
+        int nl = total_live();
+        std::vector<double> live_o((size_t)npars * std::max(nl, 1)), dead_o((size_t)npars * std::max<long long>(ndead, 1)),
+            lw(std::max<long long>(ndead, 1));
+        auto pack = [&](const double* rec, double* out) {
+            for (int k = 0; k < D; ++k) out[k] = rec[p0 + k];
+            for (int k = 0; k < P; ++k) out[D + k] = rec[d0 + k];
+            out[D + P] = rec[b0];
+            out[D + P + 1] = rec[l0];
+        };
+        for (long long i = 0; i < ndead; ++i) {
+            pack(&dead[(size_t)i * T], &dead_o[(size_t)i * npars]);
+            lw[i] = logweights[i] + dead[(size_t)i * T + l0];
+        }
+        if (ndead > 0) {
+            double lse = logsumexp(lw.data(), (size_t)ndead);
+            for (long long i = 0; i < ndead; ++i) lw[i] -= lse;
+        }
+        int o = 0;
+        for (auto& c : cl)
+            for (int i = 0; i < c.nlive; ++i) pack(&c.live[(size_t)i * T], &live_o[(size_t)(o++) * npars]);
+        double lz, var;
+        logZ_estimate(lz, var);
+        dumper((int)ndead, nl, npars, live_o.data(), dead_o.data(), lw.data(), lz, std::sqrt(var));
+    }
+
+    // GenerateLivePoints linear, generate.F90:153-183
+    void generate_live_points() {
+        initialise();
+        int nprior = S.nprior <= 0 ? S.nlive : S.nprior;
+        Cluster& c = cl[0];
+        std::vector<double> pt(T);
+        uint64_t attempt = 0;
+        while (c.nlive < nprior) {
+            std::fill(pt.begin(), pt.end(), 0.0);
+            for (int k = 0; k < D; ++k) pt[h0 + k] = rng.uniform(TAG_INIT, attempt, (uint32_t)k, 0);
+            attempt++;
+            calculate_point(pt.data(), nlike);
+            pt[b0] = S.logzero;
+            if (pt[l0] > S.logzero) {
+                c.live.insert(c.live.end(), pt.begin(), pt.end());
+                c.nlive++;
+            }
+        }
+        find_min();
+    }
+
+    void do_update() {
+        logX_last_update = sum_logX();
+        if (S.batch_K > 0) clean_phantoms_stable(); else clean_phantoms();
+        dump();
+        nupdates++;
+        calculate_covmats();
+    }
+
+    // ---- reference-mode main loop, nested_sampling.F90:239-374 ----
+    void run_reference() {
+        int nfail = S.nfail <= 0 ? S.nlive : S.nfail;
+        int failures = 0;
+        std::vector<double> babies;
+        while (more_samples_needed() && failures <= nfail) {
+            // GenerateSeed (generate.F90:19-55), single cluster or volume-weighted choice
+            uint64_t uid = (uint64_t)nchains;
+            int p = 0;
+            if (cl.size() > 1) {
+                std::vector<double> probs(cl.size());
+                double lse = sum_logX();
+                for (size_t q = 0; q < cl.size(); ++q) probs[q] = std::exp(cl[q].logXp - lse);
+                double norm = 0.0;
+                for (double v : probs) norm += v;
+                double rnd = rng.uniform(TAG_SEED, uid, 1, 0), cdf = 0.0;
+                p = (int)cl.size() - 1;
+                for (size_t q = 0; q < cl.size(); ++q) {
+                    cdf += probs[q] / norm;
+                    if (rnd < cdf) { p = (int)q; break; }
+                }
+            }
+            double u = rng.uniform(TAG_SEED, uid, 0, 0);
+            int choice = (int)std::ceil(u * cl[p].nlive);
+            if (choice < 1) choice = 1;
+            std::vector<double> seed(cl[p].live.begin() + (size_t)(choice - 1) * T, cl[p].live.begin() + (size_t)choice * T);
+            double logL = cl[p].logLp;
+            slice_sampling(logL, seed.data(), cl[p].cholesky.data(), uid, babies, nlike);
+            for (int i = 0; i < R; ++i) babies[(size_t)i * T + b0] = logL;
+            nchains++;
+            ngen++;
+            if (replace_point(babies, p)) failures = 0;
+            else { failures++; nfail_total++; }
+            if (sum_logX() <= logX_last_update + std::log(S.compression_factor)) do_update();
+        }
+    }
+
+    // ---- batched-generation main loop (the GPU engine's schedule) ----
+    void run_batched() {
+        Cluster& c = cl[0];
+        const int n = c.nlive;
+        std::vector<int> order(n);
+        std::vector<double> babies, rec(T);
+        while (more_samples_needed()) {
+            int K = std::min(S.batch_K, n - 1);
+            if (S.max_ndead > 0) K = (int)std::min<long long>(K, S.max_ndead - ndead);
+            if (K < 1) break;
+            // rank by (logL, slot)
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+                return c.live[(size_t)a * T + l0] < c.live[(size_t)b * T + l0];
+            });
+            double Lstar = c.live[(size_t)order[K - 1] * T + l0];
+            // K sequential deaths with n, n-1, ... live points (cf. nested_sampling.F90:381-384)
+            int nlive_save = c.nlive;
+            for (int k = 0; k < K; ++k) {
+                const double* r = &c.live[(size_t)order[k] * T];
+                c.logLp = r[l0];
+                double logw = update_evidence(0);
+                push_dead(r, logw);
+                c.stack_l.push_back(r[l0]);
+                c.nlive--;
+            }
+            c.nlive = nlive_save;
+            // K chains seeded from the n-K survivors, all at contour Lstar
+            int m = n - K;
+            std::vector<double> newpts((size_t)K * T);
+            for (int k = 0; k < K; ++k) {
+                uint64_t uid = (uint64_t)nchains + k;
+                double u = rng.uniform(TAG_SEED, uid, 0, 0);
+                int choice = (int)std::ceil(u * m);
+                if (choice < 1) choice = 1;
+                const double* seed = &c.live[(size_t)order[K + choice - 1] * T];
+                slice_sampling(Lstar, seed, c.cholesky.data(), uid, babies, nlike);
+                for (int i = 0; i < R; ++i) babies[(size_t)i * T + b0] = Lstar;
+                for (int i = 0; i < R - 1; ++i) {
+                    const double* pt = babies.data() + (size_t)i * T;
+                    if (pt[l0] > Lstar) {
+                        c.phantom.insert(c.phantom.end(), pt, pt + T);
+                        c.nphantom++;
+                    }
+                }
+                const double* last = babies.data() + (size_t)(R - 1) * T;
+                if (!(last[l0] > Lstar)) nfail_total++;
+                std::copy(last, last + T, newpts.begin() + (size_t)k * T);
+            }
+            for (int k = 0; k < K; ++k)
+                std::copy(newpts.begin() + (size_t)k * T, newpts.begin() + (size_t)(k + 1) * T, c.live.begin() + (size_t)order[k] * T);
+            nchains += K;
+            ngen++;
+            find_min();
+            if (sum_logX() <= logX_last_update + std::log(S.compression_factor)) do_update();
+        }
+    }
+
+    void final_killoff() {
+        if (S.batch_K > 0) {
+            // same order as the engine: ascending (logL, slot)
+            Cluster& c = cl[0];
+            int n = c.nlive;
+            std::vector<int> order(n);
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+                return c.live[(size_t)a * T + l0] < c.live[(size_t)b * T + l0];
+            });
+            for (int k = 0; k < n; ++k) {
+                const double* r = &c.live[(size_t)order[k] * T];
+                c.logLp = r[l0];
+                double logw = update_evidence(0);
+                push_dead(r, logw);
+                c.nlive--;
+            }
+            c.live.clear();
+        } else {
+            while (total_live() > 0) delete_outermost_point();
+        }
+    }
+
+    void run(oracle_result* out) {
+        auto t0 = std::chrono::steady_clock::now();
+        init_layout();
+        generate_live_points();
+        // nprior > nlive: trim (nested_sampling.F90:201-203)
+        while (cl[0].nlive > S.nlive) delete_outermost_point();
+        if (S.batch_K > 0) run_batched(); else run_reference();
+        final_killoff();
+        dump();
+        auto t1 = std::chrono::steady_clock::now();
+        double lz, var;
+        logZ_estimate(lz, var);
+        out->logZ = lz; out->logZerr = std::sqrt(var);
+        out->logZ_raw = logZ; out->logZ2_raw = logZ2;
+        out->ndead = ndead; out->nlike = nlike; out->nchains = nchains; out->ngenerations = ngen;
+        out->nupdates = nupdates; out->nfailures = nfail_total; out->nslices = nslices;
+        long long nph = 0;
+        for (auto& c : cl) nph += c.nphantom;
+        out->nphantoms_final = nph;
+        out->seconds = std::chrono::duration<double>(t1 - t0).count();
+    }
+};
+
+void setup_like_prior(Run& run, int like_kind, const double* like_params, int n_like_params, const double* prior_lo,
+                      const double* prior_hi, double (*ll_cb)(double*, int, double*, int),
+                      void (*prior_cb)(double*, double*, int)) {
+    int D = run.S.nDims;
+    run.like.kind = like_kind;
+    run.like.log_rast = std::log(4991.21750);
+    run.like.Vn = std::pow(std::sqrt(M_PI), (double)D) / std::tgamma(1.0 + D / 2.0);
+    if (like_kind == 0) {
+        run.like.mu.assign(D, 0.5);
+        run.like.sigma.assign(D, 0.1);
+        if (like_params && n_like_params >= 2 * D) {
+            run.like.mu.assign(like_params, like_params + D);
+            run.like.sigma.assign(like_params + D, like_params + 2 * D);
+        } else if (like_params && n_like_params == 2) {
+            run.like.mu.assign(D, like_params[0]);
+            run.like.sigma.assign(D, like_params[1]);
+        }
+        run.like.gauss_norm = 0.0;
+        for (int i = 0; i < D; ++i) run.like.gauss_norm += std::log(run.like.sigma[i]) + LOG_TWO_PI / 2.0;
+    } else if (like_kind == 2) {
+        // params: mu[D], invcov[D*D] column-major, logdet
+        run.like.mu.assign(like_params, like_params + D);
+        run.like.invcov.assign(like_params + D, like_params + D + (size_t)D * D);
+        run.like.logdet = like_params[D + (size_t)D * D];
+    } else if (like_kind == 3) {
+        run.like.cb = ll_cb;
+    }
+    if (prior_cb) {
+        run.pri.kind = 1;
+        run.pri.cb = prior_cb;
+    } else {
+        run.pri.kind = 0;
+        run.pri.lo.assign(D, 0.0);
+        run.pri.hi.assign(D, 1.0);
+        if (prior_lo && prior_hi) {
+            run.pri.lo.assign(prior_lo, prior_lo + D);
+            run.pri.hi.assign(prior_hi, prior_hi + D);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// Full nested-sampling run.  like_kind: 0 gaussian (params: mu[D],sigma[D] or {mu,sigma} or none),
+// 1 rastrigin, 2 correlated gaussian (params: mu[D], invcov[D*D], logdet), 3 host callback.
+int oracle_run(const oracle_settings* s, int like_kind, const double* like_params, int n_like_params,
+               const double* prior_lo, const double* prior_hi, double (*ll_cb)(double*, int, double*, int),
+               void (*prior_cb)(double*, double*, int), oracle_dumper_t dumper, oracle_result* out) {
+    Run run;
+    run.S = *s;
+    run.dumper = dumper;
+    setup_like_prior(run, like_kind, like_params, n_like_params, prior_lo, prior_hi, ll_cb, prior_cb);
+    run.run(out);
+    return 0;
+}
+
+// One chain (SliceSampling) from a given seed record: the per-chain parity probe.
+// seed_point: T doubles; cholesky: D*D column-major; babies out: R*T doubles (b0 set to logL).
+int oracle_slice_chain(const oracle_settings* s, int like_kind, const double* like_params, int n_like_params,
+                       const double* prior_lo, const double* prior_hi, const double* seed_point,
+                       const double* cholesky, double logL, unsigned long long uid, double* babies_out,
+                       long long* nlike_out) {
+    Run run;
+    run.S = *s;
+    setup_like_prior(run, like_kind, like_params, n_like_params, prior_lo, prior_hi, nullptr, nullptr);
+    run.init_layout();
+    std::vector<double> babies;
+    long long n = 0;
+    run.slice_sampling(logL, seed_point, cholesky, uid, babies, n);
+    for (int i = 0; i < run.R; ++i) babies[(size_t)i * run.T + run.b0] = logL;
+    std::copy(babies.begin(), babies.end(), babies_out);
+    *nlike_out = n;
+    return 0;
+}
+
+// Whitening-free direction set of one chain (D x R column-major), after the shuffle.
+int oracle_generate_nhats(const oracle_settings* s, unsigned long long uid, double* nhats_out) {
+    Run run;
+    run.S = *s;
+    run.init_layout();
+    std::vector<double> nh;
+    run.generate_nhats(uid, nh);
+    std::copy(nh.begin(), nh.end(), nhats_out);
+    return 0;
+}
+
+// Evaluate prior+likelihood for npts cube points (records of T doubles, cube in [0,D)).
+int oracle_calculate_points(const oracle_settings* s, int like_kind, const double* like_params, int n_like_params,
+                            const double* prior_lo, const double* prior_hi, double* records, int npts) {
+    Run run;
+    run.S = *s;
+    setup_like_prior(run, like_kind, like_params, n_like_params, prior_lo, prior_hi, nullptr, nullptr);
+    run.init_layout();
+    long long n = 0;
+    for (int i = 0; i < npts; ++i) run.calculate_point(records + (size_t)i * run.T, n);
+    return (int)n;
+}
+
+void oracle_philox4x32_10(const unsigned* ctr, const unsigned* key, unsigned* out) {
+    U4 o = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    for (int i = 0; i < 4; ++i) out[i] = o.v[i];
+}
+double oracle_uniform(unsigned seed, unsigned tag, unsigned long long uid, unsigned a, unsigned b) {
+    Rng r{seed};
+    return r.uniform(tag, uid, a, b);
+}
+double oracle_inv_normal_cdf(double p) { return inv_normal_cdf(p); }
+double oracle_logaddexp(double a, double b) { return logaddexp(a, b); }
+double oracle_logsumexp(const double* v, int n) { return logsumexp(v, (size_t)n); }
+void oracle_calc_cholesky(const double* a, double* L, int D) { calc_cholesky(a, L, D); }
+
+// Apply `ndeaths` consecutive single-cluster evidence updates with the given logL values
+// and starting live count n0 (decreasing by `dec` per death: 0 = constant nlive, 1 = kill-off).
+// state = {logZ, logZ2, logXp, logZXp, logZp, logZp2, logZpXp, logXpXp}; logweights_out[ndeaths].
+void oracle_evidence_sequence(double* state, const double* logLs, int ndeaths, int n0, int dec, double logzero,
+                              double* logweights_out) {
+    Run run;
+    std::memset(&run.S, 0, sizeof(run.S));
+    run.S.logzero = logzero;
+    run.S.nDims = 1;
+    run.init_layout();
+    run.initialise();
+    Cluster& c = run.cl[0];
+    run.logZ = state[0]; run.logZ2 = state[1]; c.logXp = state[2]; c.logZXp = state[3];
+    c.logZp = state[4]; c.logZp2 = state[5]; c.logZpXp = state[6]; run.XX(0, 0) = state[7];
+    int n = n0;
+    for (int i = 0; i < ndeaths; ++i) {
+        c.nlive = n;
+        c.logLp = logLs[i];
+        logweights_out[i] = run.update_evidence(0);
+        n -= dec;
+    }
+    state[0] = run.logZ; state[1] = run.logZ2; state[2] = c.logXp; state[3] = c.logZXp;
+    state[4] = c.logZp; state[5] = c.logZp2; state[6] = c.logZpXp; state[7] = run.XX(0, 0);
+}
+
+// random_inverse_covmat (random_utils.F90:581-614): Haar basis from stream TAG_LIKE.
+// out: invcov[D*D] column-major, then logdet.  sigma is passed by the caller (the reference
+// uses the single-precision literal 0.1, random_gaussian.f90:5).
+void oracle_random_inverse_covmat(unsigned seed, int D, double sigma, double* invcov, double* logdet) {
+    Rng rng{seed};
+    std::vector<double> Q((size_t)D * D), ev(D);
+    random_orthonormal_basis(rng, TAG_LIKE, 0, 0, D, Q.data());
+    double ld = 0.0;
+    for (int j = 0; j < D; ++j) {
+        ev[j] = sigma * std::pow(1e-2, (double)j / (D - 1.0));
+        ld += std::log(ev[j]);
+    }
+    for (int r = 0; r < D; ++r)
+        for (int c = 0; c < D; ++c) {
+            double s = 0.0;
+            for (int j = 0; j < D; ++j) s += Q[r + (size_t)j * D] * (1.0 / (ev[j] * ev[j])) * Q[c + (size_t)j * D];
+            invcov[r + (size_t)c * D] = s;
+        }
+    *logdet = 2.0 * ld;
+}
+
+}  // extern "C"

@@ -1,0 +1,186 @@
+"""ctypes binding of the CPU oracle (oracle/pc_oracle.cpp).
+
+Test infrastructure only: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package
+polychordlite_b200 never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+ORACLE_DIR = ROOT / "oracle"
+LIB_PATH = ORACLE_DIR / "_build" / "liboracle.so"
+
+
+class OracleSettings(C.Structure):
+    _fields_ = [
+        ("nDims", C.c_int), ("nDerived", C.c_int), ("nlive", C.c_int), ("num_repeats", C.c_int),
+        ("nprior", C.c_int), ("nfail", C.c_int), ("do_clustering", C.c_int),
+        ("precision_criterion", C.c_double), ("logzero", C.c_double), ("max_ndead", C.c_int),
+        ("boost_posterior", C.c_double), ("posteriors", C.c_int), ("equals", C.c_int),
+        ("cluster_posteriors", C.c_int), ("compression_factor", C.c_double), ("seed", C.c_int),
+        ("batch_K", C.c_int),
+    ]
+
+
+class OracleResult(C.Structure):
+    _fields_ = [
+        ("logZ", C.c_double), ("logZerr", C.c_double), ("logZ_raw", C.c_double), ("logZ2_raw", C.c_double),
+        ("ndead", C.c_longlong), ("nlike", C.c_longlong), ("nchains", C.c_longlong),
+        ("ngenerations", C.c_longlong), ("nupdates", C.c_longlong), ("nfailures", C.c_longlong),
+        ("nslices", C.c_longlong), ("nphantoms_final", C.c_longlong), ("seconds", C.c_double),
+    ]
+
+
+LL_CB = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int)
+PRIOR_CB = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int)
+DUMPER_CB = C.CFUNCTYPE(None, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                        C.POINTER(C.c_double), C.c_double, C.c_double)
+
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", str(ORACLE_DIR)], check=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        src = ORACLE_DIR / "pc_oracle.cpp"
+        if not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+            build()
+        _lib = C.CDLL(str(LIB_PATH))
+        _lib.oracle_uniform.restype = C.c_double
+        _lib.oracle_uniform.argtypes = [C.c_uint, C.c_uint, C.c_ulonglong, C.c_uint, C.c_uint]
+        _lib.oracle_inv_normal_cdf.restype = C.c_double
+        _lib.oracle_inv_normal_cdf.argtypes = [C.c_double]
+        _lib.oracle_logaddexp.restype = C.c_double
+        _lib.oracle_logaddexp.argtypes = [C.c_double, C.c_double]
+        _lib.oracle_logsumexp.restype = C.c_double
+    return _lib
+
+
+def _dptr(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def make_settings(nDims, nDerived=0, nlive=500, num_repeats=None, nprior=-1, nfail=-1, do_clustering=False,
+                  precision_criterion=1e-3, logzero=-1e30, max_ndead=-1, boost_posterior=0.0, posteriors=False,
+                  equals=False, cluster_posteriors=False, compression_factor=np.exp(-1), seed=0, batch_K=0):
+    s = OracleSettings()
+    s.nDims, s.nDerived, s.nlive = nDims, nDerived, nlive
+    s.num_repeats = 5 * nDims if num_repeats is None else num_repeats
+    s.nprior, s.nfail, s.do_clustering = nprior, nfail, int(do_clustering)
+    s.precision_criterion, s.logzero, s.max_ndead = precision_criterion, logzero, max_ndead
+    s.boost_posterior, s.posteriors, s.equals = boost_posterior, int(posteriors), int(equals)
+    s.cluster_posteriors, s.compression_factor = int(cluster_posteriors), compression_factor
+    s.seed, s.batch_K = seed, batch_K
+    return s
+
+
+LIKE_KINDS = {"gaussian": 0, "rastrigin": 1, "corr_gaussian": 2, "callback": 3}
+
+
+def run(settings, like="gaussian", like_params=None, prior_lo=None, prior_hi=None, ll_cb=None, prior_cb=None,
+        want_dump=False):
+    """Full run.  Returns (OracleResult, dumps) with dumps a list of dicts when want_dump."""
+    L = lib()
+    lp = None if like_params is None else np.ascontiguousarray(like_params, dtype=np.float64)
+    lo = None if prior_lo is None else np.ascontiguousarray(prior_lo, dtype=np.float64)
+    hi = None if prior_hi is None else np.ascontiguousarray(prior_hi, dtype=np.float64)
+    dumps = []
+
+    def _dump(ndead, nlive, npars, live, dead, lw, logZ, logZerr):
+        dumps.append(dict(
+            live=np.ctypeslib.as_array(live, shape=(max(nlive, 1), npars))[:nlive].copy(),
+            dead=np.ctypeslib.as_array(dead, shape=(max(ndead, 1), npars))[:ndead].copy(),
+            logweights=np.ctypeslib.as_array(lw, shape=(max(ndead, 1),))[:ndead].copy(),
+            logZ=logZ, logZerr=logZerr))
+
+    dcb = DUMPER_CB(_dump) if want_dump else C.cast(None, DUMPER_CB)
+    res = OracleResult()
+    L.oracle_run(C.byref(settings), LIKE_KINDS[like], _dptr(lp), 0 if lp is None else lp.size, _dptr(lo), _dptr(hi),
+                 ll_cb if ll_cb is not None else C.cast(None, LL_CB),
+                 prior_cb if prior_cb is not None else C.cast(None, PRIOR_CB), dcb, C.byref(res))
+    return res, dumps
+
+
+def slice_chain(settings, seed_point, cholesky, logL, uid, like="gaussian", like_params=None, prior_lo=None,
+                prior_hi=None):
+    L = lib()
+    D, P, R = settings.nDims, settings.nDerived, settings.num_repeats
+    T = 2 * D + P + 2
+    lp = None if like_params is None else np.ascontiguousarray(like_params, dtype=np.float64)
+    lo = None if prior_lo is None else np.ascontiguousarray(prior_lo, dtype=np.float64)
+    hi = None if prior_hi is None else np.ascontiguousarray(prior_hi, dtype=np.float64)
+    sp = np.ascontiguousarray(seed_point, dtype=np.float64)
+    ch = np.asfortranarray(cholesky, dtype=np.float64)
+    babies = np.zeros((R, T))
+    n = C.c_longlong(0)
+    L.oracle_slice_chain(C.byref(settings), LIKE_KINDS[like], _dptr(lp), 0 if lp is None else lp.size, _dptr(lo),
+                         _dptr(hi), _dptr(sp), ch.ctypes.data_as(C.POINTER(C.c_double)), C.c_double(logL),
+                         C.c_ulonglong(uid), _dptr(babies), C.byref(n))
+    return babies, n.value
+
+
+def generate_nhats(settings, uid):
+    L = lib()
+    out = np.zeros((settings.num_repeats, settings.nDims))
+    L.oracle_generate_nhats(C.byref(settings), C.c_ulonglong(uid), _dptr(out))
+    return out  # row i = direction i
+
+
+def calculate_points(settings, cubes, like="gaussian", like_params=None, prior_lo=None, prior_hi=None):
+    L = lib()
+    D, P = settings.nDims, settings.nDerived
+    T = 2 * D + P + 2
+    cubes = np.atleast_2d(np.asarray(cubes, dtype=np.float64))
+    rec = np.zeros((cubes.shape[0], T))
+    rec[:, :D] = cubes
+    lp = None if like_params is None else np.ascontiguousarray(like_params, dtype=np.float64)
+    lo = None if prior_lo is None else np.ascontiguousarray(prior_lo, dtype=np.float64)
+    hi = None if prior_hi is None else np.ascontiguousarray(prior_hi, dtype=np.float64)
+    n = L.oracle_calculate_points(C.byref(settings), LIKE_KINDS[like], _dptr(lp), 0 if lp is None else lp.size,
+                                  _dptr(lo), _dptr(hi), _dptr(rec), rec.shape[0])
+    return rec, n
+
+
+def philox(ctr, key):
+    L = lib()
+    c = (C.c_uint * 4)(*ctr)
+    k = (C.c_uint * 2)(*key)
+    o = (C.c_uint * 4)()
+    L.oracle_philox4x32_10(c, k, o)
+    return [int(x) for x in o]
+
+
+def calc_cholesky(a):
+    L = lib()
+    a = np.asfortranarray(a, dtype=np.float64)
+    out = np.zeros_like(a, order="F")
+    L.oracle_calc_cholesky(a.ctypes.data_as(C.POINTER(C.c_double)), out.ctypes.data_as(C.POINTER(C.c_double)),
+                           a.shape[0])
+    return np.array(out)
+
+
+def evidence_sequence(state, logLs, n0, dec, logzero=-1e30):
+    L = lib()
+    st = np.array(state, dtype=np.float64)
+    ll = np.ascontiguousarray(logLs, dtype=np.float64)
+    lw = np.zeros(ll.size)
+    L.oracle_evidence_sequence(_dptr(st), _dptr(ll), ll.size, n0, dec, C.c_double(logzero), _dptr(lw))
+    return st, lw
+
+
+def random_inverse_covmat(seed, D, sigma):
+    L = lib()
+    inv = np.zeros((D, D), order="F")
+    ld = C.c_double(0)
+    L.oracle_random_inverse_covmat(C.c_uint(seed), D, C.c_double(sigma), inv.ctypes.data_as(C.POINTER(C.c_double)),
+                                   C.byref(ld))
+    return np.array(inv), ld.value
