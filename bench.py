@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- likelihood evals/sec + wall-time-to-logZ on BASELINE.json's metric config.
+
+A "step" is ONE complete nested-sampling run of the workload (BASELINE config[1]: 20-D Gaussian,
+nlive=1000, num_repeats=40, nDerived=2, precision_criterion=1e-3) from live-point generation to
+the final kill-off.  evals = the reference's nlike counter (calculate.f90:44).
+
+  value     evals/s with everything resident on the device: pc_run(), no dumper, timed with the
+            CUDA events the engine records around its persistent-kernel launches.
+  e2e       the same metric through the reference-facing C ABI, polychord_c_interface(), with a
+            dumper callback that receives HOST arrays (live/dead/logweights) at every update and
+            at the end; host wall time, every host<->device copy inside the timed region.
+  roofline  persistent run kernel: algorithmic bytes (8T+8D per slice step, 16T per
+            chain, 8D^2 per generation) / CUDA-event kernel time vs MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the CPU oracle (oracle/pc_oracle.cpp, reference schedule, 1 thread) on the box's host.
+
+`--impl reference` times the CPU restatement of the reference's linear-mode algorithm (the Fortran
+reference cannot be built in this image: no gfortran/MPI) on the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+WORKLOADS = {
+    # name: (nDims, nDerived, nlive, num_repeats, like, prior box)
+    "gaussian20_nlive1000_R40": dict(nDims=20, nDerived=2, nlive=1000, num_repeats=40, like="gaussian", box=None),
+    "gaussian20_nlive500_R40": dict(nDims=20, nDerived=2, nlive=500, num_repeats=40, like="gaussian", box=None),
+    "rastrigin10_nlive2000_R50": dict(nDims=10, nDerived=0, nlive=2000, num_repeats=50, like="rastrigin", box=5.12),
+    "gaussian20_nlive8000_R40": dict(nDims=20, nDerived=2, nlive=8000, num_repeats=40, like="gaussian", box=None),
+}
+METRIC = "likelihood_evals_per_sec"
+UNIT = "evals/s"
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        self.index = index
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def run_reference(args):
+    """The reference's CPU path (restated: oracle, reference schedule batch_K=0), one thread."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    import oracle_lib as O
+    w = WORKLOADS[args.workload]
+    kw = dict(prior_lo=[-w["box"]] * w["nDims"], prior_hi=[w["box"]] * w["nDims"]) if w["box"] else {}
+
+    def one(seed):
+        s = O.make_settings(w["nDims"], w["nDerived"], nlive=w["nlive"], num_repeats=w["num_repeats"], seed=seed,
+                            batch_K=0)
+        t0 = time.perf_counter()
+        r, _ = O.run(s, like=w["like"], **kw)
+        return r, time.perf_counter() - t0
+
+    for i in range(args.warmup):
+        one(1000 + i)
+    tot_e, tot_t, lz = 0, 0.0, []
+    for i in range(args.steps):
+        r, t = one(i)
+        tot_e += r.nlike; tot_t += t; lz.append(r.logZ)
+    v = tot_e / tot_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, **{k: w[k] for k in ("nDims", "nDerived", "nlive", "num_repeats")},
+                   "precision_criterion": 1e-3, "schedule": "reference: one death + one birth per iteration"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{args.steps} complete runs (seeds 0..{args.steps - 1}) of the workload, "
+                                   "oracle/pc_oracle.cpp reference schedule, 1 host thread; the Fortran reference "
+                                   "cannot be built here (no gfortran/MPI) and its linear mode is single-threaded"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_time_to_logZ_s": tot_t / args.steps, "logZ_mean": sum(lz) / len(lz),
+        "host_cores": os.cpu_count(),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="gaussian20_nlive1000_R40", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch-fraction", type=float, default=None)
+    ap.add_argument("--warps-per-cta", type=int, default=None)
+    ap.add_argument("--ensemble", type=int, default=32, help="replicas for the extra ensemble-throughput figure (0=skip)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    from polychordlite_b200 import _capi as capi
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available() or capi.device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    capi.set_option("device", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.batch_fraction is not None:
+        capi.set_option("batch_fraction", args.batch_fraction)
+    if args.warps_per_cta is not None:
+        capi.set_option("warps_per_cta", args.warps_per_cta)
+
+    w = WORKLOADS[args.workload]
+    D, P, n, R = w["nDims"], w["nDerived"], w["nlive"], w["num_repeats"]
+    T = 2 * D + P + 2
+    box = dict(prior_lo=[-w["box"]] * D, prior_hi=[w["box"]] * D) if w["box"] else {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def settings(seed):
+        return capi.make_settings(D, P, nlive=n, num_repeats=R, seed=seed)
+
+    def step_device(seed):
+        flush.zero_()
+        torch.cuda.synchronize()
+        info, _ = capi.run(settings(seed), like=w["like"], **box)
+        return info
+
+    # ---- the reference-facing call with host buffers -----------------------------------------
+    L = capi.lib()
+    like_fn = {"gaussian": L.pc_gaussian_loglikelihood, "rastrigin": L.pc_rastrigin_loglikelihood}[w["like"]]
+    prior_fn = L.pc_uniform_prior if w["box"] else L.pc_unit_prior
+    if w["box"]:
+        pp = np.array(box["prior_lo"] + box["prior_hi"], dtype=np.float64)
+        L.pc_register_device_prior(C.cast(prior_fn, capi.PRIOR_CB), 0, pp.ctypes.data_as(C.POINTER(C.c_double)), pp.size)
+    sink = {"rows": 0, "logZ": None, "calls": 0}
+
+    def _dumper(ndead, nlive, npars, live, dead, lw, logZ, logZerr):
+        # touch the host arrays like a consumer would (pypolychord's dumper wraps them in numpy)
+        d = np.ctypeslib.as_array(dead, shape=(max(ndead, 1), npars))
+        sink["rows"] = ndead
+        sink["last_logL"] = float(d[ndead - 1, npars - 1]) if ndead else None
+        sink["logZ"] = logZ
+        sink["calls"] += 1
+
+    dcb = capi.DUMPER_CB(_dumper)
+    grade_frac = (C.c_double * 1)(1.0)
+    grade_dims = (C.c_int * 1)(D)
+    comm = C.c_int(0)
+    L.polychord_c_interface.restype = None
+    L.polychord_c_interface.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_bool, C.c_int, C.c_double,
+        C.c_double, C.c_int, C.c_double] + [C.c_bool] * 11 + [C.c_double, C.c_bool, C.c_int, C.c_int, C.c_char_p,
+                                                                C.c_char_p, C.c_int, C.POINTER(C.c_double),
+                                                                C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_double),
+                                                                C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
+
+    def step_e2e(seed):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        L.polychord_c_interface(C.cast(like_fn, C.c_void_p), C.cast(prior_fn, C.c_void_p), C.cast(dcb, C.c_void_p),
+                                n, R, -1, -1, False, 0, 1e-3, -1e30, -1, 0.0,
+                                False, False, False, False, False, False, False, False, False, False, False,
+                                float(np.exp(-1)), True, D, P, b"chains", b"bench", 1, grade_frac, grade_dims, 0, None,
+                                None, seed, C.byref(comm))
+        t = time.perf_counter() - t0
+        return capi.last_run_info(), t
+
+    # ---- warm-up --------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        step_device(10_000 + i + 100 * rank)
+        step_e2e(20_000 + i + 100 * rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- timed region 1: device-resident ------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    evals = launches = 0
+    dev_ms, wall, algo_bytes, logZs, ndead = 0.0, 0.0, 0, [], 0
+    t_region = time.perf_counter()
+    for i in range(args.steps):
+        t0 = time.perf_counter()
+        info = step_device(i + 1000 * rank)
+        wall += time.perf_counter() - t0
+        evals += info.nlike; dev_ms += info.device_ms; launches += info.kernel_launches
+        algo_bytes += info.algorithmic_bytes; logZs.append(info.logZ); ndead += info.ndead
+    barrier()
+    t_region = time.perf_counter() - t_region
+    # ---- timed region 2: end to end through polychord_c_interface ----------------------------
+    e_evals, e_t, h2d, d2h, e_launch = 0, 0.0, 0, 0, 0
+    barrier()
+    for i in range(args.steps):
+        info, t = step_e2e(i + 1000 * rank)
+        e_evals += info.nlike; e_t += t; h2d += info.h2d_bytes; d2h += info.d2h_bytes; e_launch += info.kernel_launches
+    barrier()
+    clocks = sampler.stop()
+
+    # ---- extra: ensemble throughput (the GPU filled with independent replicas) ----------------
+    ens = None
+    if args.ensemble > 0 and world == 1:
+        try:
+            capi.run_ensemble(settings(0), list(range(5000, 5000 + args.ensemble)), like=w["like"], **box)
+            flush.zero_(); torch.cuda.synchronize()
+            infos = capi.run_ensemble(settings(0), list(range(args.ensemble)), like=w["like"], **box)
+            ee = sum(i.nlike for i in infos)
+            eb = sum(i.algorithmic_bytes for i in infos)
+            ms = infos[0].device_ms
+            lz = [i.logZ for i in infos]
+            ens = {"replicas": args.ensemble, "value": ee / (ms * 1e-3), "unit": UNIT, "device_ms": ms,
+                   "logZ_mean": float(np.mean(lz)), "logZ_sem": float(np.std(lz, ddof=1) / np.sqrt(len(lz))),
+                   "hbm_achieved_gbs": eb / (ms * 1e-3) / 1e9, "ctas_per_run": infos[0].ctas_per_run}
+        except RuntimeError as ex:  # e.g. too many replicas for one launch
+            ens = {"error": str(ex)}
+
+    # ---- reduce over ranks ------------------------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([dev_ms, e_t, wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms_max, e_t_max, wall_max = t.tolist()
+        c = torch.tensor([evals, e_evals, launches + e_launch, algo_bytes], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        evals_all, e_evals_all, launches_all, algo_all = c.tolist()
+    else:
+        dev_ms_max, e_t_max, wall_max = dev_ms, e_t, wall
+        evals_all, e_evals_all, launches_all, algo_all = evals, e_evals, launches + e_launch, algo_bytes
+
+    if rank == 0:
+        peak, which = peaks()
+        achieved = (algo_bytes / (dev_ms * 1e-3)) / 1e9
+        value = evals_all / (dev_ms_max * 1e-3)
+        cpu = None
+        if not args.no_cpu_baseline:
+            import oracle_lib as O
+            kw = dict(prior_lo=box["prior_lo"], prior_hi=box["prior_hi"]) if box else {}
+            ce, ct = 0, 0.0
+            nruns = 3
+            for sd in range(nruns):
+                t0 = time.perf_counter()
+                r, _ = O.run(O.make_settings(D, P, nlive=n, num_repeats=R, seed=sd, batch_K=0), like=w["like"], **kw)
+                ct += time.perf_counter() - t0; ce += r.nlike
+            cpu = {"value": ce / ct, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"{nruns} complete runs of the workload (seeds 0..{nruns - 1}), oracle reference schedule "
+                             f"(1 death/iteration), 1 host thread of {os.cpu_count()}; {ct:.1f} s of CPU work",
+                   "wall_time_to_logZ_s": ct / nruns}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "nDims": D, "nDerived": P, "nlive": n, "num_repeats": R,
+                       "precision_criterion": 1e-3, "batch_K": int(info.batch_K), "ctas_per_run": int(info.ctas_per_run),
+                       "warps_per_cta": int(info.warps_per_cta), "step": "one complete nested-sampling run",
+                       "l2": "flushed (256 MiB memset) before every step",
+                       "multi_gpu": "independent replica runs per rank (no data-path collective)" if world > 1 else "n/a"},
+            "wall_time_to_logZ_s": dev_ms / args.steps * 1e-3, "wall_ms_per_step_host": 1e3 * wall_max / args.steps,
+            "logZ_mean": float(np.mean(logZs)), "logZ_sem": float(np.std(logZs, ddof=1) / np.sqrt(len(logZs))) if len(logZs) > 1 else None,
+            "ndead_per_step": ndead / args.steps, "evals_per_step": evals / args.steps,
+            "e2e": {"value": e_evals_all / e_t_max, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
+                    "d2h_bytes_per_step": d2h / args.steps, "api": "polychord_c_interface + dumper (host arrays)",
+                    "ms_per_step": 1e3 * e_t_max / args.steps, "dumper_calls": sink["calls"]},
+            "gpu_launches": int(launches_all),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": which, "kernel": "pc_run_kernel<1>",
+                         "note": "latency-bound persistent kernel; one run occupies ctas_per_run of 148 SMs; "
+                                 "see 'ensemble' for the GPU filled with independent replicas"},
+            "cpu_baseline": cpu, "clocks": clocks, "ensemble": ens, "region_wall_s": t_region,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

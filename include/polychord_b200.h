@@ -1,0 +1,190 @@
+/* polychord_b200.h -- C ABI of the B200-native nested-sampling engine (libchord.so).
+ *
+ * Two groups of entry points:
+ *
+ *  (1) The drop-in boundary: the exact symbols the reference's libchord.so exports and
+ *      its C++ facade / CPython shim bind (reference: src/polychord/interfaces.h:2-56,
+ *      Fortran side src/polychord/interfaces.F90:285-324 and :496-497).  A caller that
+ *      was linked against the reference library relinks against this one unchanged.
+ *
+ *  (2) Additive pc_* entry points.  The reference ABI only carries host function
+ *      pointers, so the engine cannot see that a callback is "the built-in Gaussian".
+ *      pc_register_device_likelihood()/pc_register_device_prior() bind a host pointer to
+ *      a device-resident analytic form; polychord_c_interface() looks the pointer up by
+ *      identity and runs the whole sampling loop on the GPU.  Unregistered callbacks take
+ *      the lock-step host-callback path.  The remaining pc_* calls expose results
+ *      (the reference entry returns nothing: interfaces.F90:129 drops output_info),
+ *      engine options, and the kernel-level probes the parity tests drive.
+ *
+ * All pointers are plain host pointers owned by the caller unless stated otherwise; no
+ * torch / CUDA types appear in any signature (streams are passed as void*).
+ */
+#ifndef POLYCHORD_B200_H
+#define POLYCHORD_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------
+ * (1) Drop-in boundary
+ * ---------------------------------------------------------------------------------- */
+
+typedef double (*pc_loglikelihood_t)(double* theta, int nDims, double* phi, int nDerived);
+typedef void (*pc_prior_t)(double* cube, double* theta, int nDims);
+typedef void (*pc_dumper_t)(int ndead, int nlive, int npars, double* live, double* dead, double* logweights,
+                            double logZ, double logZerr);
+
+/* Replaces the Fortran bind(c) entry src/polychord/interfaces.F90:285-436, declared for C
+ * callers at src/polychord/interfaces.h:2-45 and called from src/polychord/c_interface.cpp:73-112.
+ * Argument order, by-value/by-pointer convention and the `int& comm` (pointer) last argument
+ * are identical.  bool arguments are C++ `bool` in the reference declaration; this header
+ * spells them `unsigned char` for C callers (same size and calling convention on x86-64 SysV).
+ * Fatal configuration errors follow the reference convention (abort.F90:19-29): a banner on
+ * stderr and exit(1) -- unless PC_ERRORS=return is set, in which case the call returns and
+ * pc_last_run_info().status carries the code. */
+#ifdef __cplusplus
+typedef bool pc_bool;
+#else
+typedef unsigned char pc_bool;
+#endif
+
+void polychord_c_interface(
+    pc_loglikelihood_t loglikelihood, pc_prior_t prior, pc_dumper_t dumper,
+    int nlive, int num_repeats, int nprior, int nfail, pc_bool do_clustering, int feedback,
+    double precision_criterion, double logzero, int max_ndead, double boost_posterior,
+    pc_bool posteriors, pc_bool equals, pc_bool cluster_posteriors, pc_bool write_resume,
+    pc_bool write_paramnames, pc_bool read_resume, pc_bool write_stats, pc_bool write_live,
+    pc_bool write_dead, pc_bool write_prior, pc_bool maximise, double compression_factor,
+    pc_bool synchronous, int nDims, int nDerived, char* base_dir, char* file_root, int nGrade,
+    double* grade_frac, int* grade_dims, int n_nlives, double* loglikes, int* nlives, int seed,
+    int* comm);
+
+/* Replaces src/polychord/interfaces.F90:496-519 (decl. interfaces.h:47-56).  The .ini driver
+ * path is outside the hot-path scope ("next" row f4): the symbol exists so
+ * that the reference facade links, and reports "unsupported" through the error convention. */
+void polychord_c_interface_ini(pc_loglikelihood_t loglikelihood, void (*setup_loglikelihood)(void),
+                               char* inifile, int* comm);
+
+/* ------------------------------------------------------------------------------------
+ * (2) Additive engine API
+ * ---------------------------------------------------------------------------------- */
+
+/* Analytic forms with a device implementation (likelihoods/examples/*.f90). */
+enum pc_like_kind {
+    PC_LIKE_GAUSSIAN = 0,      /* gaussian.f90:12-41; params: mu[D], sigma[D] (or {mu,sigma}, or none = 0.5/0.1) */
+    PC_LIKE_RASTRIGIN = 1,     /* rastrigin.f90:20-35; no params */
+    PC_LIKE_CORR_GAUSSIAN = 2, /* random_gaussian.f90 / utils.F90:1028-1048; params: mu[D], invcov[D*D] col-major, logdet */
+    PC_LIKE_HOST = 3           /* arbitrary host callback (lock-step path) */
+};
+enum pc_prior_kind {
+    PC_PRIOR_UNIFORM = 0, /* priors.f90:40-55 uniform_htp; params: lo[D], hi[D] (none = unit cube) */
+    PC_PRIOR_HOST = 1
+};
+
+/* Bind a host callback pointer to a device-resident analytic form.  Later calls of
+ * polychord_c_interface() with the same pointer run fully on the GPU.  params are copied.
+ * Returns 0 on success. */
+int pc_register_device_likelihood(pc_loglikelihood_t host_fn, int kind, const double* params, int nparams);
+int pc_register_device_prior(pc_prior_t host_fn, int kind, const double* params, int nparams);
+void pc_clear_registrations(void);
+
+/* Ready-made host callbacks with the reference's callback signature; each is pre-registered
+ * with its device form, so `polychord_c_interface(pc_gaussian_loglikelihood, pc_unit_prior, ...)`
+ * is the GPU fast path.  Their parameters are set with pc_register_device_* on these pointers. */
+double pc_gaussian_loglikelihood(double* theta, int nDims, double* phi, int nDerived);
+double pc_rastrigin_loglikelihood(double* theta, int nDims, double* phi, int nDerived);
+double pc_corr_gaussian_loglikelihood(double* theta, int nDims, double* phi, int nDerived);
+void pc_unit_prior(double* cube, double* theta, int nDims);    /* theta = cube (c_interface.cpp:210) */
+void pc_uniform_prior(double* cube, double* theta, int nDims); /* theta = lo + (hi-lo)*cube */
+
+/* Engine options (name/value); unknown names return -1.
+ *   "batch_fraction"  K = max(1, round(nlive*value)) lowest points die per generation (default 0.25)
+ *   "batch_K"         absolute K (overrides batch_fraction when > 0)
+ *   "device"          CUDA device ordinal
+ *   "warps_per_cta"   chain warps per CTA (default: chosen from the shared-memory budget)
+ *   "max_ctas"        cap on the CTAs of one run (default 0 = one warp per chain)
+ *   "errors_return"   1: configuration errors return instead of exit(1)
+ *   "nh_global"       1: keep the direction scratch in global memory even when it fits in shared memory
+ *   "cap_dead0", "cap_ph0"  initial capacity (records) of the dead / phantom pools; 0 = automatic.
+ *                     The pools grow on demand either way (the kernel exits, the host reallocates, relaunches).
+ */
+int pc_set_option(const char* name, double value);
+double pc_get_option(const char* name);
+/* CUDA stream (cudaStream_t passed as void*) all engine work is enqueued on; NULL = default stream. */
+void pc_set_stream(void* cuda_stream);
+
+typedef struct pc_run_info {
+    int status;               /* 0 ok; <0 error code */
+    double logZ, logZerr;     /* run_time_info.f90:652-678 estimate */
+    double logZ_raw, logZ2_raw;
+    long long ndead, nlike, nchains, ngenerations, nupdates, nfailures, nslices;
+    long long nphantoms_final;
+    int batch_K, warps_per_cta, ctas_per_run, kernel_launches;
+    double device_ms;         /* sum of CUDA-event durations of the engine's kernels */
+    double wall_ms;           /* entry to return of the call */
+    long long h2d_bytes, d2h_bytes;
+    long long algorithmic_bytes; /* 8T+8D per slice, 8T per chain, 8D^2 per generation */
+} pc_run_info;
+
+/* Results of the most recent polychord_c_interface()/pc_run() in this process. */
+int pc_last_run_info(pc_run_info* out);
+
+typedef struct pc_settings {
+    int nDims, nDerived, nlive, num_repeats, nprior, nfail;
+    int do_clustering, feedback;
+    double precision_criterion, logzero;
+    int max_ndead;
+    double boost_posterior;
+    int posteriors, equals, cluster_posteriors;
+    double compression_factor;
+    int seed;
+} pc_settings;
+
+/* One run with explicit device forms (what polychord_c_interface dispatches to).
+ * dumper may be NULL.  prior_params: lo[D],hi[D] or NULL. */
+int pc_run(const pc_settings* s, int like_kind, const double* like_params, int n_like_params,
+           const double* prior_params, int n_prior_params, pc_dumper_t dumper, pc_run_info* out);
+
+/* nruns independent runs (seeds[i]) advanced concurrently by ONE persistent kernel, each run
+ * owning its own group of CTAs.  out[nruns].  dead/logweight arrays are not returned. */
+int pc_run_ensemble(const pc_settings* s, int like_kind, const double* like_params, int n_like_params,
+                    const double* prior_params, int n_prior_params, int nruns, const int* seeds,
+                    pc_run_info* out);
+
+/* ---- kernel-level probes (parity tests call these through the same library) ---- */
+
+/* SliceSampling for nchains chains (chordal_sampling.f90:7-92): chain c starts from
+ * seed_points[c*T..] with contour logL[c], RNG stream uid[c]; cholesky is D*D column-major.
+ * babies_out: nchains*R*T doubles (b0 = logL); nlike_out[nchains]. */
+int pc_slice_chains(const pc_settings* s, int like_kind, const double* like_params, int n_like_params,
+                    const double* prior_params, int n_prior_params, int nchains, const double* seed_points,
+                    const double* cholesky, const double* logL, const unsigned long long* uid,
+                    double* babies_out, long long* nlike_out);
+
+/* calculate_point (calculate.f90:6-50) for npts records of T doubles (cube filled in). Returns nlike. */
+int pc_calculate_points(const pc_settings* s, int like_kind, const double* like_params, int n_like_params,
+                        const double* prior_params, int n_prior_params, double* records, int npts);
+
+/* RNG stream probe: Philox4x32-10 block and the uniform derived from it, computed on the device. */
+int pc_device_philox(const unsigned* ctr, const unsigned* key, unsigned* out4);
+int pc_device_uniforms(unsigned seed, unsigned tag, unsigned long long uid, unsigned a0, unsigned b, int n,
+                       double* out);
+int pc_device_inv_normal_cdf(const double* p, int n, double* out);
+
+/* Directions of one chain in use order (chordal_sampling.f90:94-145): out[i*nDims + r], i < num_repeats. */
+int pc_device_directions(int nDims, int num_repeats, unsigned seed, unsigned long long uid, double* out);
+/* Evidence recurrences (run_time_info.f90:211-296) for `count` deaths with live counts n_start, n_start-1, ...;
+ * state = {logZ, logZ2, logX, logZX, logXX} (single cluster), updated in place; logw_out[count]. */
+int pc_device_evidence(double* state, const double* logLs, int count, int n_start, double* logw_out);
+/* calc_cholesky (utils.F90:621-649), column-major D x D; returns 1 when the identity fallback was taken. */
+int pc_device_cholesky(const double* a, int D, double* L_out);
+
+/* Number of CUDA devices visible; <=0 means the engine cannot run (no CPU fallback exists). */
+int pc_device_count(void);
+const char* pc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLYCHORD_B200_H */

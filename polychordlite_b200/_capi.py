@@ -1,0 +1,245 @@
+"""ctypes binding of libchord.so -- the C ABI declared in include/polychord_b200.h.
+
+Nothing here computes: every call goes into the CUDA library.  If the library is missing the
+import fails loudly (there is no CPU fallback by design).
+"""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "lib" / "libchord.so"
+
+LL_CB = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int)
+PRIOR_CB = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int)
+DUMPER_CB = C.CFUNCTYPE(None, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                        C.POINTER(C.c_double), C.c_double, C.c_double)
+
+LIKE_KINDS = {"gaussian": 0, "rastrigin": 1, "corr_gaussian": 2}
+
+# every symbol include/polychord_b200.h declares
+EXPORTS = [
+    "polychord_c_interface", "polychord_c_interface_ini",
+    "pc_register_device_likelihood", "pc_register_device_prior", "pc_clear_registrations",
+    "pc_gaussian_loglikelihood", "pc_rastrigin_loglikelihood", "pc_corr_gaussian_loglikelihood",
+    "pc_unit_prior", "pc_uniform_prior", "pc_set_option", "pc_get_option", "pc_set_stream",
+    "pc_last_run_info", "pc_run", "pc_run_ensemble", "pc_slice_chains", "pc_calculate_points",
+    "pc_device_philox", "pc_device_uniforms", "pc_device_inv_normal_cdf", "pc_device_directions",
+    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version",
+]
+
+
+class Settings(C.Structure):
+    _fields_ = [
+        ("nDims", C.c_int), ("nDerived", C.c_int), ("nlive", C.c_int), ("num_repeats", C.c_int),
+        ("nprior", C.c_int), ("nfail", C.c_int), ("do_clustering", C.c_int), ("feedback", C.c_int),
+        ("precision_criterion", C.c_double), ("logzero", C.c_double), ("max_ndead", C.c_int),
+        ("boost_posterior", C.c_double), ("posteriors", C.c_int), ("equals", C.c_int),
+        ("cluster_posteriors", C.c_int), ("compression_factor", C.c_double), ("seed", C.c_int),
+    ]
+
+
+class RunInfo(C.Structure):
+    _fields_ = [
+        ("status", C.c_int), ("logZ", C.c_double), ("logZerr", C.c_double), ("logZ_raw", C.c_double),
+        ("logZ2_raw", C.c_double), ("ndead", C.c_longlong), ("nlike", C.c_longlong), ("nchains", C.c_longlong),
+        ("ngenerations", C.c_longlong), ("nupdates", C.c_longlong), ("nfailures", C.c_longlong),
+        ("nslices", C.c_longlong), ("nphantoms_final", C.c_longlong), ("batch_K", C.c_int),
+        ("warps_per_cta", C.c_int), ("ctas_per_run", C.c_int), ("kernel_launches", C.c_int),
+        ("device_ms", C.c_double), ("wall_ms", C.c_double), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong),
+        ("algorithmic_bytes", C.c_longlong),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    """Load libchord.so (raises if it has not been built: there is no fallback path)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -m polychordlite_b200._build` "
+                              "(the engine has no CPU fallback)")
+        L = C.CDLL(str(LIB_PATH), mode=C.RTLD_GLOBAL)
+        L.pc_version.restype = C.c_char_p
+        L.pc_get_option.restype = C.c_double
+        L.pc_set_option.argtypes = [C.c_char_p, C.c_double]
+        L.pc_get_option.argtypes = [C.c_char_p]
+        L.pc_set_stream.argtypes = [C.c_void_p]
+        for name in ("pc_gaussian_loglikelihood", "pc_rastrigin_loglikelihood", "pc_corr_gaussian_loglikelihood"):
+            getattr(L, name).restype = C.c_double
+        _lib = L
+    return _lib
+
+
+def _dptr(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _arr(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64).ravel()
+
+
+def make_settings(nDims, nDerived=0, nlive=500, num_repeats=None, nprior=-1, nfail=-1, do_clustering=False, feedback=0,
+                  precision_criterion=1e-3, logzero=-1e30, max_ndead=-1, boost_posterior=0.0, posteriors=False,
+                  equals=False, cluster_posteriors=False, compression_factor=np.exp(-1), seed=0):
+    s = Settings()
+    s.nDims, s.nDerived, s.nlive = nDims, nDerived, nlive
+    s.num_repeats = 5 * nDims if num_repeats is None else num_repeats
+    s.nprior, s.nfail, s.do_clustering, s.feedback = nprior, nfail, int(do_clustering), feedback
+    s.precision_criterion, s.logzero, s.max_ndead = precision_criterion, logzero, max_ndead
+    s.boost_posterior, s.posteriors, s.equals = boost_posterior, int(posteriors), int(equals)
+    s.cluster_posteriors, s.compression_factor, s.seed = int(cluster_posteriors), compression_factor, seed
+    return s
+
+
+def set_option(name, value):
+    if lib().pc_set_option(name.encode(), float(value)) != 0:
+        raise KeyError(name)
+
+
+def get_option(name):
+    return lib().pc_get_option(name.encode())
+
+
+def device_count():
+    return lib().pc_device_count()
+
+
+def _prior_params(lo, hi):
+    if lo is None or hi is None:
+        return None
+    return np.concatenate([_arr(lo), _arr(hi)])
+
+
+def run(settings, like="gaussian", like_params=None, prior_lo=None, prior_hi=None, want_dump=False):
+    """One device run (pc_run).  Returns (RunInfo, dumps)."""
+    L = lib()
+    lp, pp = _arr(like_params), _prior_params(prior_lo, prior_hi)
+    dumps = []
+
+    def _dump(ndead, nlive, npars, live, dead, lw, logZ, logZerr):
+        dumps.append(dict(
+            live=np.ctypeslib.as_array(live, shape=(max(nlive, 1), npars))[:nlive].copy(),
+            dead=np.ctypeslib.as_array(dead, shape=(max(ndead, 1), npars))[:ndead].copy(),
+            logweights=np.ctypeslib.as_array(lw, shape=(max(ndead, 1),))[:ndead].copy(),
+            logZ=logZ, logZerr=logZerr))
+
+    dcb = DUMPER_CB(_dump) if want_dump else C.cast(None, DUMPER_CB)
+    info = RunInfo()
+    rc = L.pc_run(C.byref(settings), LIKE_KINDS[like], _dptr(lp), 0 if lp is None else lp.size, _dptr(pp),
+                  0 if pp is None else pp.size, dcb, C.byref(info))
+    if rc != 0:
+        raise RuntimeError(f"pc_run failed with status {rc}")
+    return info, dumps
+
+
+def run_ensemble(settings, seeds, like="gaussian", like_params=None, prior_lo=None, prior_hi=None):
+    L = lib()
+    lp, pp = _arr(like_params), _prior_params(prior_lo, prior_hi)
+    seeds = np.ascontiguousarray(seeds, dtype=np.int32)
+    infos = (RunInfo * len(seeds))()
+    rc = L.pc_run_ensemble(C.byref(settings), LIKE_KINDS[like], _dptr(lp), 0 if lp is None else lp.size, _dptr(pp),
+                           0 if pp is None else pp.size, len(seeds), seeds.ctypes.data_as(C.POINTER(C.c_int)), infos)
+    if rc != 0:
+        raise RuntimeError(f"pc_run_ensemble failed with status {rc}")
+    return list(infos)
+
+
+def slice_chains(settings, seed_points, cholesky, logL, uid, like="gaussian", like_params=None, prior_lo=None,
+                 prior_hi=None):
+    L = lib()
+    D, P, R = settings.nDims, settings.nDerived, settings.num_repeats
+    T = 2 * D + P + 2
+    sp = np.ascontiguousarray(seed_points, dtype=np.float64).reshape(-1, T)
+    nch = sp.shape[0]
+    ch = np.asfortranarray(cholesky, dtype=np.float64)
+    ll = np.ascontiguousarray(np.broadcast_to(np.asarray(logL, dtype=np.float64), (nch,)))
+    ui = np.ascontiguousarray(uid, dtype=np.uint64)
+    lp, pp = _arr(like_params), _prior_params(prior_lo, prior_hi)
+    babies = np.zeros((nch, R, T))
+    nlike = np.zeros(nch, dtype=np.int64)
+    rc = L.pc_slice_chains(C.byref(settings), LIKE_KINDS[like], _dptr(lp), 0 if lp is None else lp.size, _dptr(pp),
+                           0 if pp is None else pp.size, nch, _dptr(sp), ch.ctypes.data_as(C.POINTER(C.c_double)),
+                           _dptr(ll), ui.ctypes.data_as(C.POINTER(C.c_ulonglong)), _dptr(babies),
+                           nlike.ctypes.data_as(C.POINTER(C.c_longlong)))
+    if rc != 0:
+        raise RuntimeError(f"pc_slice_chains failed with status {rc}")
+    return babies, nlike
+
+
+def calculate_points(settings, cubes, like="gaussian", like_params=None, prior_lo=None, prior_hi=None):
+    L = lib()
+    D, P = settings.nDims, settings.nDerived
+    T = 2 * D + P + 2
+    cubes = np.atleast_2d(np.asarray(cubes, dtype=np.float64))
+    rec = np.zeros((cubes.shape[0], T))
+    rec[:, :D] = cubes
+    lp, pp = _arr(like_params), _prior_params(prior_lo, prior_hi)
+    n = L.pc_calculate_points(C.byref(settings), LIKE_KINDS[like], _dptr(lp), 0 if lp is None else lp.size, _dptr(pp),
+                              0 if pp is None else pp.size, _dptr(rec), rec.shape[0])
+    if n < 0:
+        raise RuntimeError(f"pc_calculate_points failed with status {n}")
+    return rec, n
+
+
+def device_philox(ctr, key):
+    c = (C.c_uint * 4)(*ctr)
+    k = (C.c_uint * 2)(*key)
+    o = (C.c_uint * 4)()
+    if lib().pc_device_philox(c, k, o) != 0:
+        raise RuntimeError("pc_device_philox failed")
+    return [int(x) for x in o]
+
+
+def device_uniforms(seed, tag, uid, a0, b, n):
+    out = np.zeros(n)
+    if lib().pc_device_uniforms(C.c_uint(seed), C.c_uint(tag), C.c_ulonglong(uid), C.c_uint(a0), C.c_uint(b), n,
+                                _dptr(out)) != 0:
+        raise RuntimeError("pc_device_uniforms failed")
+    return out
+
+
+def device_inv_normal_cdf(p):
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    out = np.zeros_like(p)
+    if lib().pc_device_inv_normal_cdf(_dptr(p), p.size, _dptr(out)) != 0:
+        raise RuntimeError("pc_device_inv_normal_cdf failed")
+    return out
+
+
+def device_directions(nDims, num_repeats, seed, uid):
+    out = np.zeros((num_repeats, nDims))
+    if lib().pc_device_directions(nDims, num_repeats, C.c_uint(seed), C.c_ulonglong(uid), _dptr(out)) != 0:
+        raise RuntimeError("pc_device_directions failed")
+    return out
+
+
+def device_evidence(state, logLs, n_start):
+    st = np.array(state, dtype=np.float64)
+    ll = np.ascontiguousarray(logLs, dtype=np.float64)
+    lw = np.zeros(ll.size)
+    if lib().pc_device_evidence(_dptr(st), _dptr(ll), ll.size, n_start, _dptr(lw)) != 0:
+        raise RuntimeError("pc_device_evidence failed")
+    return st, lw
+
+
+def device_cholesky(a):
+    a = np.asfortranarray(a, dtype=np.float64)
+    out = np.zeros_like(a, order="F")
+    fb = lib().pc_device_cholesky(a.ctypes.data_as(C.POINTER(C.c_double)), a.shape[0],
+                                  out.ctypes.data_as(C.POINTER(C.c_double)))
+    if fb < 0:
+        raise RuntimeError("pc_device_cholesky failed")
+    return np.array(out), fb
+
+
+def last_run_info():
+    info = RunInfo()
+    lib().pc_last_run_info(C.byref(info))
+    return info

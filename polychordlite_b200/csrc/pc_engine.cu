@@ -1,0 +1,889 @@
+// pc_engine.cu -- host side of the B200 nested-sampling engine and its C ABI (libchord.so).
+//
+// Boundary replaced: src/polychord/interfaces.F90:285-436 (polychord_c_interface) and the
+// Fortran core behind it (nested_sampling.F90:15-510).  See include/polychord_b200.h.
+// There is NO CPU fallback: without a CUDA device every compute entry point fails loudly.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/polychord_b200.h"
+#include "pc_run_kernel.cuh"
+
+namespace pc {
+
+#define PC_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            throw std::runtime_error(std::string("polychord_b200: CUDA error: ") + cudaGetErrorString(e_) + \
+                                     " at " + __FILE__ + ":" + std::to_string(__LINE__));              \
+    } while (0)
+
+template <class V>
+struct DevArr {  // RAII device buffer (exception-transparent: callbacks may throw through the engine)
+    V* p = nullptr;
+    size_t n = 0;
+    DevArr() {}
+    explicit DevArr(size_t n_) { alloc(n_); }
+    DevArr(const DevArr&) = delete;
+    DevArr& operator=(const DevArr&) = delete;
+    DevArr(DevArr&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevArr& operator=(DevArr&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~DevArr() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void alloc(size_t n_) { release(); n = n_; if (n) PC_CUDA(cudaMalloc(&p, n * sizeof(V))); }
+    void zero(cudaStream_t s) { if (n) PC_CUDA(cudaMemsetAsync(p, 0, n * sizeof(V), s)); }
+    void upload(const V* h, size_t cnt, cudaStream_t s) { PC_CUDA(cudaMemcpyAsync(p, h, cnt * sizeof(V), cudaMemcpyHostToDevice, s)); }
+    void download(V* h, size_t cnt, cudaStream_t s, size_t off = 0) const { PC_CUDA(cudaMemcpyAsync(h, p + off, cnt * sizeof(V), cudaMemcpyDeviceToHost, s)); }
+    // grow keeping the first `keep` elements
+    void grow(size_t n_, size_t keep, cudaStream_t s) {
+        V* q = nullptr;
+        PC_CUDA(cudaMalloc(&q, n_ * sizeof(V)));
+        if (keep) PC_CUDA(cudaMemcpyAsync(q, p, keep * sizeof(V), cudaMemcpyDeviceToDevice, s));
+        PC_CUDA(cudaStreamSynchronize(s));
+        if (p) cudaFree(p);
+        p = q; n = n_;
+    }
+};
+
+struct Options {
+    double batch_fraction = 0.25;
+    int batch_K = 0;
+    int device = 0;
+    int warps_per_cta = 8;
+    int max_ctas = 0;
+    int errors_return = 0;
+    int nh_global = 0;  // force the direction scratch into global memory (testing)
+    long long cap_dead0 = 0, cap_ph0 = 0;  // initial pool capacities in records (0 = automatic)
+};
+static Options g_opt;
+static cudaStream_t g_stream = nullptr;
+static pc_run_info g_last;
+static std::mutex g_mu;
+
+struct ModelSpec {
+    int like_kind = 0;
+    std::vector<double> like_params;   // raw API params
+    std::vector<double> prior_params;  // lo[D], hi[D] or empty
+};
+
+struct DevModel {
+    DevArr<double> like, prior;
+    double gauss_norm = 0, Vn = 0, log_rast = 0, corr_const = 0;
+};
+
+static const double LOG_TWO_PI = 1.8378770664093454835606594728112;
+
+static void build_dev_model(const pc_settings& s, const ModelSpec& ms, DevModel& dm, cudaStream_t st) {
+    const int D = s.nDims;
+    std::vector<double> lp;
+    dm.log_rast = std::log(4991.21750);                                                    // rastrigin.f90:33
+    dm.Vn = std::pow(std::sqrt(M_PI), (double)D) / std::tgamma(1.0 + D / 2.0);           // utils.F90:754-760
+    if (ms.like_kind == PC_LIKE_GAUSSIAN) {
+        std::vector<double> mu(D, 0.5), sg(D, 0.1);                                        // gaussian.f90:20-21
+        const auto& q = ms.like_params;
+        if ((int)q.size() >= 2 * D) { mu.assign(q.begin(), q.begin() + D); sg.assign(q.begin() + D, q.begin() + 2 * D); }
+        else if (q.size() == 2) { mu.assign(D, q[0]); sg.assign(D, q[1]); }
+        else if (!q.empty()) throw std::invalid_argument("polychord_b200: gaussian likelihood wants 0, 2 or 2*nDims params");
+        dm.gauss_norm = 0.0;
+        for (int i = 0; i < D; ++i) dm.gauss_norm += std::log(sg[i]) + LOG_TWO_PI / 2.0;
+        lp = mu;
+        for (int i = 0; i < D; ++i) lp.push_back(1.0 / sg[i]);
+    } else if (ms.like_kind == PC_LIKE_CORR_GAUSSIAN) {
+        if ((int)ms.like_params.size() != D + D * D + 1)
+            throw std::invalid_argument("polychord_b200: correlated gaussian wants mu[D], invcov[D*D], logdet");
+        lp.assign(ms.like_params.begin(), ms.like_params.begin() + D + D * D);
+        dm.corr_const = -(D * LOG_TWO_PI + ms.like_params[D + D * D]) / 2.0;              // utils.F90:1040-1046
+    } else if (ms.like_kind != PC_LIKE_RASTRIGIN) {
+        throw std::invalid_argument("polychord_b200: unknown device likelihood kind");
+    }
+    if (lp.empty()) lp.push_back(0.0);
+    dm.like.alloc(lp.size());
+    dm.like.upload(lp.data(), lp.size(), st);
+    std::vector<double> pr(2 * D);
+    for (int i = 0; i < D; ++i) { pr[i] = 0.0; pr[D + i] = 1.0; }
+    if ((int)ms.prior_params.size() == 2 * D)
+        for (int i = 0; i < D; ++i) { pr[i] = ms.prior_params[i]; pr[D + i] = ms.prior_params[D + i] - ms.prior_params[i]; }
+    else if (!ms.prior_params.empty())
+        throw std::invalid_argument("polychord_b200: uniform prior wants lo[D], hi[D]");
+    dm.prior.alloc(pr.size());
+    dm.prior.upload(pr.data(), pr.size(), st);
+    PC_CUDA(cudaStreamSynchronize(st));
+}
+
+struct Layout {
+    KParams kp;
+    size_t smem = 0;
+    int npl = 1;
+    int W = 8;
+};
+
+static int device_check() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        throw std::runtime_error("polychord_b200: no CUDA device available -- this engine has no CPU fallback");
+    PC_CUDA(cudaSetDevice(g_opt.device));
+    return n;
+}
+
+static Layout make_layout(const pc_settings& s, const ModelSpec& ms, const DevModel& dm, int W) {
+    Layout L;
+    KParams& k = L.kp;
+    std::memset(&k, 0, sizeof(k));
+    const int D = s.nDims, P = s.nDerived, R = s.num_repeats;
+    if (D < 1 || D > 128) throw std::invalid_argument("polychord_b200: nDims must be in 1..128");
+    if (R < 1) throw std::invalid_argument("polychord_b200: num_repeats must be >= 1");  // settings.f90:216
+    if (s.nlive < 2) throw std::invalid_argument("polychord_b200: nlive must be >= 2");
+    k.D = D; k.P = P; k.T = 2 * D + P + 2; k.R = R; k.n = s.nlive;
+    k.LD = D | 1;
+    k.like_kind = ms.like_kind;
+    k.use_prec = s.precision_criterion > 0.0;
+    k.max_ndead = s.max_ndead;
+    k.logzero = s.logzero;
+    k.log_prec = k.use_prec ? std::log(s.precision_criterion) : 0.0;
+    k.log_comp = std::log(s.compression_factor);
+    k.gauss_norm = dm.gauss_norm; k.Vn = dm.Vn; k.log_rast = dm.log_rast; k.corr_const = dm.corr_const;
+    k.like_params = dm.like.p;
+    k.prior_params = dm.prior.p;
+    k.warps_per_cta = W;
+    k.ntri = D * (D + 1) / 2;
+    k.cov_passes = (k.ntri + COV_ACC * 32 - 1) / (COV_ACC * 32);
+    k.partial_stride = 1 + D + k.cov_passes * COV_ACC * 32;
+    L.npl = (D + 31) / 32;
+    L.W = W;
+    const int nlp = ms.like_kind == PC_LIKE_GAUSSIAN ? 2 * D : (ms.like_kind == PC_LIKE_CORR_GAUSSIAN ? D + D * D : 0);
+    const int Dpad = (D + 1) & ~1;
+    size_t off = (size_t)D * D * 8;
+    k.off_like = (int)off;
+    off += (size_t)((nlp + 1) & ~1) * 8;
+    off += 64 * sizeof(int);  // s_cnt
+    k.off_warp = (int)off;
+    size_t base_warp = (size_t)(2 * Dpad + ((R + 1) & ~1)) * 8;
+    size_t nh_bytes = (size_t)R * k.LD * 8;
+    size_t cov_bytes = (size_t)(Dpad + COV_ACC * 32) * 8;
+    int np2 = 1;
+    while (np2 < s.nlive) np2 <<= 1;
+    size_t sort_bytes = 64 * 8 + (size_t)np2 * 12;
+    const size_t budget = 200 * 1024;
+    bool in_smem = !g_opt.nh_global && (off + (size_t)W * std::max(base_warp + nh_bytes, cov_bytes) <= budget);
+    k.nh_in_smem = in_smem ? 1 : 0;
+    size_t wb = std::max(base_warp + (in_smem ? nh_bytes : 0), cov_bytes);
+    wb = (wb + 15) & ~(size_t)15;
+    k.warp_bytes = (int)wb;
+    L.smem = off + std::max((size_t)W * wb, sort_bytes);
+    if (L.smem > 227 * 1024) throw std::invalid_argument("polychord_b200: nlive too large for the shared-memory sort");
+    return L;
+}
+
+template <int NPL>
+static void set_smem_attr(size_t smem) {
+    PC_CUDA(cudaFuncSetAttribute(pc_run_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PC_CUDA(cudaFuncSetAttribute(pc_slice_chains_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PC_CUDA(cudaFuncSetAttribute(pc_calculate_points_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+}
+static void set_smem(int npl, size_t smem) {
+    switch (npl) {
+        case 1: set_smem_attr<1>(smem); break;
+        case 2: set_smem_attr<2>(smem); break;
+        case 3: set_smem_attr<3>(smem); break;
+        default: set_smem_attr<4>(smem); break;
+    }
+}
+static const void* run_kernel_ptr(int npl) {
+    switch (npl) {
+        case 1: return (const void*)pc_run_kernel<1>;
+        case 2: return (const void*)pc_run_kernel<2>;
+        case 3: return (const void*)pc_run_kernel<3>;
+        default: return (const void*)pc_run_kernel<4>;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// One ensemble of runs advanced by the persistent kernel.
+// ------------------------------------------------------------------------------------------
+struct HostRun {
+    DevArr<DevRun> st;
+    DevArr<double> live, dead, logw, ph0, ph1, chol, cov, partial, nh;
+    DevArr<int> order;
+    DevArr<long long> pcount;
+    RunBuf buf;
+    DevRun host_st;
+    // dumper mirror
+    std::vector<double> dead_rows;   // packed (ndead, npars)
+    std::vector<double> dead_logw, dead_logL;
+    long long mirrored = 0;
+};
+
+struct Engine {
+    pc_settings S;
+    ModelSpec ms;
+    DevModel dm;
+    Layout L;
+    cudaStream_t stream;
+    int nruns = 0, G = 1;
+    std::vector<HostRun> runs;
+    DevArr<RunBuf> d_bufs;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double device_ms = 0;
+    int launches = 0;
+    long long h2d = 0, d2h = 0;
+
+    ~Engine() {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+    }
+
+    void setup(const pc_settings& s, const ModelSpec& m, int nruns_, const int* seeds) {
+        device_check();
+        S = s; ms = m; nruns = nruns_;
+        stream = g_stream;
+        if (S.nprior > 0 && S.nprior != S.nlive)
+            throw std::invalid_argument("polychord_b200: nprior != nlive is not supported by the device path yet");
+        build_dev_model(S, ms, dm, stream);
+        int W = std::max(1, std::min(8, g_opt.warps_per_cta));
+        L = make_layout(S, ms, dm, W);
+        set_smem(L.npl, L.smem);
+        KParams& k = L.kp;
+        int K = g_opt.batch_K > 0 ? g_opt.batch_K : (int)std::lround(S.nlive * g_opt.batch_fraction);
+        K = std::max(1, std::min(K, S.nlive - 1));
+        k.batch_K = K;
+        // CTAs per run: one warp per chain unless capped by residency
+        int dev = 0, sms = 0, per_sm = 0;
+        PC_CUDA(cudaGetDevice(&dev));
+        PC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        PC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&per_sm, run_kernel_ptr(L.npl), W * 32, L.smem, 0));
+        if (per_sm < 1) throw std::runtime_error("polychord_b200: run kernel does not fit on an SM");
+        long long capacity = (long long)sms * per_sm;
+        G = (K + W - 1) / W;
+        if (g_opt.max_ctas > 0) G = std::min(G, g_opt.max_ctas);
+        G = (int)std::max(1LL, std::min<long long>(G, capacity / nruns));
+        if ((long long)G * nruns > capacity) throw std::invalid_argument("polychord_b200: too many concurrent runs for one launch");
+        k.ctas_per_run = G;
+        PC_CUDA(cudaEventCreate(&ev0));
+        PC_CUDA(cudaEventCreate(&ev1));
+
+        const int T = k.T, D = k.D, R = k.R, n = k.n;
+        runs.resize(nruns);
+        std::vector<RunBuf> hb(nruns);
+        for (int r = 0; r < nruns; ++r) {
+            HostRun& h = runs[r];
+            long long cap_dead = S.max_ndead > 0 ? (long long)S.max_ndead + 2LL * n + K : 40LL * n + K;
+            long long cap_ph = std::max<long long>(3LL * n * (R - 1) + (long long)K * (R - 1), n);
+            if (g_opt.cap_dead0 > 0) cap_dead = std::max<long long>(g_opt.cap_dead0, 2LL * n + K);
+            if (g_opt.cap_ph0 > 0) cap_ph = std::max<long long>(g_opt.cap_ph0, std::max<long long>((long long)K * (R - 1), n));
+            h.st.alloc(1); h.st.zero(stream);
+            h.live.alloc((size_t)n * T); h.live.zero(stream);
+            h.order.alloc(n);
+            h.dead.alloc((size_t)cap_dead * T);
+            h.logw.alloc(cap_dead);
+            h.ph0.alloc((size_t)cap_ph * T);
+            h.ph1.alloc((size_t)cap_ph * T);
+            h.chol.alloc((size_t)D * D); h.cov.alloc((size_t)D * D);
+            h.partial.alloc((size_t)G * k.partial_stride);
+            h.pcount.alloc(G); h.pcount.zero(stream);
+            if (!k.nh_in_smem) h.nh.alloc((size_t)G * W * R * k.LD);
+            RunBuf& b = h.buf;
+            std::memset(&b, 0, sizeof(b));
+            b.st = h.st.p; b.live = h.live.p; b.order = h.order.p; b.dead = h.dead.p; b.logw = h.logw.p;
+            b.ph[0] = h.ph0.p; b.ph[1] = h.ph1.p; b.chol = h.chol.p; b.cov = h.cov.p; b.partial = h.partial.p;
+            b.pcount = h.pcount.p; b.nh = h.nh.p; b.cap_dead = cap_dead; b.cap_ph = cap_ph;
+            b.seed = (unsigned)seeds[r];
+            hb[r] = b;
+        }
+        d_bufs.alloc(nruns);
+        d_bufs.upload(hb.data(), nruns, stream);
+        h2d += (long long)nruns * sizeof(RunBuf);
+        k.runs = d_bufs.p;
+        PC_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    void upload_bufs() {
+        std::vector<RunBuf> hb(nruns);
+        for (int r = 0; r < nruns; ++r) hb[r] = runs[r].buf;
+        d_bufs.upload(hb.data(), nruns, stream);
+        h2d += (long long)nruns * sizeof(RunBuf);
+        PC_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    void launch() {
+        KParams kp = L.kp;
+        void* args[] = {&kp};
+        PC_CUDA(cudaEventRecord(ev0, stream));
+        PC_CUDA(cudaLaunchCooperativeKernel(run_kernel_ptr(L.npl), dim3(G * nruns), dim3(L.W * 32), args, L.smem, stream));
+        PC_CUDA(cudaEventRecord(ev1, stream));
+        PC_CUDA(cudaEventSynchronize(ev1));
+        float ms = 0;
+        PC_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        device_ms += ms;
+        ++launches;
+        for (int r = 0; r < nruns; ++r) {
+            runs[r].st.download(&runs[r].host_st, 1, stream);
+            d2h += sizeof(DevRun);
+        }
+        PC_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    // dump, nested_sampling.F90:546-590: rows [theta, phi, birth, logL]; normalised posterior log-weights
+    void dump(int r, pc_dumper_t dumper, bool final_dump) {
+        HostRun& h = runs[r];
+        const KParams& k = L.kp;
+        const int T = k.T, D = k.D, P = k.P, n = k.n, npars = D + P + 2;
+        const long long ndead = h.host_st.ndead;
+        const long long fresh = ndead - h.mirrored;
+        if (fresh > 0) {
+            std::vector<double> rec((size_t)fresh * T), lw(fresh);
+            h.dead.download(rec.data(), (size_t)fresh * T, stream, (size_t)h.mirrored * T);
+            h.logw.download(lw.data(), fresh, stream, h.mirrored);
+            PC_CUDA(cudaStreamSynchronize(stream));
+            d2h += fresh * (T + 1) * 8;
+            h.dead_rows.resize((size_t)ndead * npars);
+            h.dead_logw.resize(ndead);
+            for (long long i = 0; i < fresh; ++i) {
+                const double* s = &rec[(size_t)i * T];
+                double* o = &h.dead_rows[(size_t)(h.mirrored + i) * npars];
+                for (int c = 0; c < D; ++c) o[c] = s[D + c];
+                for (int c = 0; c < P; ++c) o[D + c] = s[2 * D + c];
+                o[D + P] = s[2 * D + P];
+                o[D + P + 1] = s[2 * D + P + 1];
+                h.dead_logw[h.mirrored + i] = lw[i] + s[T - 1];
+            }
+            h.mirrored = ndead;
+        }
+        int nl = final_dump ? 0 : n;
+        std::vector<double> live_rows((size_t)std::max(nl, 1) * npars);
+        if (nl > 0) {
+            std::vector<double> rec((size_t)n * T);
+            h.live.download(rec.data(), (size_t)n * T, stream);
+            PC_CUDA(cudaStreamSynchronize(stream));
+            d2h += (long long)n * T * 8;
+            for (int i = 0; i < n; ++i) {
+                const double* s = &rec[(size_t)i * T];
+                double* o = &live_rows[(size_t)i * npars];
+                for (int c = 0; c < D; ++c) o[c] = s[D + c];
+                for (int c = 0; c < P; ++c) o[D + c] = s[2 * D + c];
+                o[D + P] = s[2 * D + P];
+                o[D + P + 1] = s[2 * D + P + 1];
+            }
+        }
+        std::vector<double> lw(std::max<long long>(ndead, 1));
+        if (ndead > 0) {
+            double m = *std::max_element(h.dead_logw.begin(), h.dead_logw.end());
+            double sum = 0.0;
+            for (long long i = 0; i < ndead; ++i) sum += std::exp(h.dead_logw[i] - m);
+            double lse = m + std::log(sum);
+            for (long long i = 0; i < ndead; ++i) lw[i] = h.dead_logw[i] - lse;
+        }
+        double lz = std::max(-std::numeric_limits<double>::max(), 2 * h.host_st.logZ - 0.5 * h.host_st.logZ2);
+        double var = h.host_st.logZ2 - 2 * h.host_st.logZ;
+        std::vector<double> dummy(npars, 0.0);
+        dumper((int)ndead, nl, npars, live_rows.data(), ndead > 0 ? h.dead_rows.data() : dummy.data(), lw.data(), lz,
+               std::sqrt(var));
+    }
+
+    void grow(int r, int status) {
+        HostRun& h = runs[r];
+        const KParams& k = L.kp;
+        if (status == ST_NEED_DEAD) {
+            long long nc = h.buf.cap_dead * 2 + k.n + k.batch_K;
+            h.dead.grow((size_t)nc * k.T, (size_t)h.host_st.ndead * k.T, stream);
+            h.logw.grow(nc, h.host_st.ndead, stream);
+            h.buf.dead = h.dead.p; h.buf.logw = h.logw.p; h.buf.cap_dead = nc;
+        } else {
+            long long nc = h.buf.cap_ph * 2;
+            int cur = h.host_st.cur_pool;
+            DevArr<double>& a = cur == 0 ? h.ph0 : h.ph1;
+            DevArr<double>& b = cur == 0 ? h.ph1 : h.ph0;
+            a.grow((size_t)nc * k.T, (size_t)h.host_st.nphantom * k.T, stream);
+            b.alloc((size_t)nc * k.T);
+            h.buf.ph[0] = h.ph0.p; h.buf.ph[1] = h.ph1.p; h.buf.cap_ph = nc;
+        }
+    }
+
+    void run(pc_dumper_t dumper, pc_run_info* out) {
+        auto t0 = std::chrono::steady_clock::now();
+        L.kp.want_dump = (dumper != nullptr && nruns == 1) ? 1 : 0;
+        for (;;) {
+            launch();
+            bool all_done = true, regrow = false;
+            for (int r = 0; r < nruns; ++r) {
+                int stt = runs[r].host_st.status;
+                if (stt == ST_ERROR) throw std::runtime_error("polychord_b200: could not generate live points (likelihood <= logzero everywhere?)");
+                if (stt == ST_NEED_DEAD || stt == ST_NEED_PHANTOM) { grow(r, stt); regrow = true; }
+                if (stt == ST_DUMP && dumper) dump(r, dumper, false);
+                if (stt != ST_DONE) all_done = false;
+            }
+            if (regrow) upload_bufs();
+            if (all_done) break;
+        }
+        if (dumper)
+            for (int r = 0; r < nruns; ++r) dump(r, dumper, true);
+        auto t1 = std::chrono::steady_clock::now();
+        const KParams& k = L.kp;
+        for (int r = 0; r < nruns; ++r) {
+            const DevRun& s = runs[r].host_st;
+            pc_run_info& o = out[r];
+            std::memset(&o, 0, sizeof(o));
+            o.status = 0;
+            o.logZ = std::max(-std::numeric_limits<double>::max(), 2 * s.logZ - 0.5 * s.logZ2);  // run_time_info.f90:663-664
+            o.logZerr = std::sqrt(s.logZ2 - 2 * s.logZ);
+            o.logZ_raw = s.logZ; o.logZ2_raw = s.logZ2;
+            o.ndead = s.ndead; o.nlike = s.nlike; o.nchains = s.nchains; o.ngenerations = s.ngen;
+            o.nupdates = s.nupdates; o.nfailures = s.nfail; o.nslices = s.nslices; o.nphantoms_final = s.nphantom;
+            o.batch_K = k.batch_K; o.warps_per_cta = L.W; o.ctas_per_run = G; o.kernel_launches = launches;
+            o.device_ms = device_ms;
+            o.wall_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+            o.h2d_bytes = h2d; o.d2h_bytes = d2h;
+            // 8T+8D per slice step, 8T per chain (seed read) + 8T (dead record), 8D^2 per generation
+            o.algorithmic_bytes = s.nslices * (8LL * k.T + 8LL * k.D) + s.nchains * 16LL * k.T + s.ngen * 8LL * k.D * k.D;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// registry: host callback pointer -> device form
+// ------------------------------------------------------------------------------------------
+struct LikeReg { int kind; std::vector<double> params; };
+struct PriorReg { int kind; std::vector<double> params; };
+static std::map<void*, LikeReg>& like_registry() { static std::map<void*, LikeReg> m; return m; }
+static std::map<void*, PriorReg>& prior_registry() { static std::map<void*, PriorReg> m; return m; }
+
+static int fail(int code, const std::string& msg) {
+    std::fprintf(stderr, "\n polychord_b200: %s\n", msg.c_str());
+    g_last.status = code;
+    if (!g_opt.errors_return && !std::getenv("PC_ERRORS_RETURN")) std::exit(1);  // abort.F90:19-29 convention
+    return code;
+}
+
+}  // namespace pc
+
+using namespace pc;
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+int pc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+const char* pc_version(void) { return "polychordlite_b200 0.1.0 (PolyChordLite 1.22.2 API)"; }
+
+int pc_set_option(const char* name, double value) {
+    std::string s(name);
+    if (s == "batch_fraction") g_opt.batch_fraction = value;
+    else if (s == "batch_K") g_opt.batch_K = (int)value;
+    else if (s == "device") g_opt.device = (int)value;
+    else if (s == "warps_per_cta") g_opt.warps_per_cta = (int)value;
+    else if (s == "max_ctas") g_opt.max_ctas = (int)value;
+    else if (s == "errors_return") g_opt.errors_return = (int)value;
+    else if (s == "nh_global") g_opt.nh_global = (int)value;
+    else if (s == "cap_dead0") g_opt.cap_dead0 = (long long)value;
+    else if (s == "cap_ph0") g_opt.cap_ph0 = (long long)value;
+    else return -1;
+    return 0;
+}
+double pc_get_option(const char* name) {
+    std::string s(name);
+    if (s == "batch_fraction") return g_opt.batch_fraction;
+    if (s == "batch_K") return g_opt.batch_K;
+    if (s == "device") return g_opt.device;
+    if (s == "warps_per_cta") return g_opt.warps_per_cta;
+    if (s == "max_ctas") return g_opt.max_ctas;
+    if (s == "errors_return") return g_opt.errors_return;
+    if (s == "nh_global") return g_opt.nh_global;
+    if (s == "cap_dead0") return (double)g_opt.cap_dead0;
+    if (s == "cap_ph0") return (double)g_opt.cap_ph0;
+    return NAN;
+}
+void pc_set_stream(void* cuda_stream) { g_stream = (cudaStream_t)cuda_stream; }
+
+int pc_last_run_info(pc_run_info* out) {
+    *out = g_last;
+    return g_last.status;
+}
+
+int pc_register_device_likelihood(pc_loglikelihood_t fn, int kind, const double* params, int nparams) {
+    if (!fn || kind < 0 || kind > PC_LIKE_CORR_GAUSSIAN) return -1;
+    like_registry()[(void*)fn] = LikeReg{kind, std::vector<double>(params, params + (params ? nparams : 0))};
+    return 0;
+}
+int pc_register_device_prior(pc_prior_t fn, int kind, const double* params, int nparams) {
+    if (!fn || kind != PC_PRIOR_UNIFORM) return -1;
+    prior_registry()[(void*)fn] = PriorReg{kind, std::vector<double>(params, params + (params ? nparams : 0))};
+    return 0;
+}
+void pc_clear_registrations(void) {
+    like_registry().clear();
+    prior_registry().clear();
+}
+
+// ---- ready-made host callbacks (also usable by CPU-side callers; they evaluate the same formulas) ----
+static std::vector<double>& reg_params(void* fn) {
+    static std::vector<double> empty;
+    auto it = like_registry().find(fn);
+    return it == like_registry().end() ? empty : it->second.params;
+}
+double pc_gaussian_loglikelihood(double* theta, int nDims, double* phi, int nDerived) {
+    const std::vector<double>& q = reg_params((void*)pc_gaussian_loglikelihood);
+    double norm = 0, chi = 0, r2 = 0;
+    for (int i = 0; i < nDims; ++i) {
+        double mu = 0.5, sg = 0.1;
+        if ((int)q.size() >= 2 * nDims) { mu = q[i]; sg = q[nDims + i]; } else if (q.size() == 2) { mu = q[0]; sg = q[1]; }
+        norm += std::log(sg) + LOG_TWO_PI / 2.0;
+        chi += (theta[i] - mu) / sg * ((theta[i] - mu) / sg);
+        r2 += (theta[i] - mu) * (theta[i] - mu);
+    }
+    if (nDerived >= 1) phi[0] = std::sqrt(r2);
+    if (nDerived >= 2) phi[1] = std::log(std::pow(phi[0], (double)nDims) * std::pow(std::sqrt(M_PI), (double)nDims) / std::tgamma(1.0 + nDims / 2.0));
+    for (int i = 2; i < nDerived; ++i) phi[i] = 0.0;
+    return -norm - chi / 2.0;
+}
+double pc_rastrigin_loglikelihood(double* theta, int nDims, double* phi, int nDerived) {
+    double s = 0;
+    for (int i = 0; i < nDims; ++i) s += std::log(4991.21750) + theta[i] * theta[i] - 10.0 * std::cos(2.0 * M_PI * theta[i]);
+    for (int i = 0; i < nDerived; ++i) phi[i] = 0.0;
+    return -s;
+}
+double pc_corr_gaussian_loglikelihood(double* theta, int nDims, double* phi, int nDerived) {
+    const std::vector<double>& q = reg_params((void*)pc_corr_gaussian_loglikelihood);
+    const int D = nDims;
+    for (int i = 0; i < nDerived; ++i) phi[i] = 0.0;
+    if ((int)q.size() != D + D * D + 1) return -1e30;
+    double s = 0;
+    for (int r = 0; r < D; ++r) {
+        double y = 0;
+        for (int c = 0; c < D; ++c) y += q[D + r + (size_t)c * D] * (theta[c] - q[c]);
+        s += (theta[r] - q[r]) * y;
+    }
+    return -(D * LOG_TWO_PI + q[D + D * D]) / 2.0 - s / 2.0;
+}
+void pc_unit_prior(double* cube, double* theta, int nDims) {
+    for (int i = 0; i < nDims; ++i) theta[i] = cube[i];
+}
+void pc_uniform_prior(double* cube, double* theta, int nDims) {
+    auto it = prior_registry().find((void*)pc_uniform_prior);
+    for (int i = 0; i < nDims; ++i) {
+        double lo = 0, hi = 1;
+        if (it != prior_registry().end() && (int)it->second.params.size() == 2 * nDims) { lo = it->second.params[i]; hi = it->second.params[nDims + i]; }
+        theta[i] = lo + (hi - lo) * cube[i];
+    }
+}
+
+static int run_common(const pc_settings* s, const ModelSpec& ms, int nruns, const int* seeds, pc_dumper_t dumper,
+                      pc_run_info* out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    Engine e;
+    e.setup(*s, ms, nruns, seeds);
+    e.run(dumper, out);
+    g_last = out[0];
+    return 0;
+}
+
+int pc_run(const pc_settings* s, int like_kind, const double* like_params, int n_like_params, const double* prior_params,
+           int n_prior_params, pc_dumper_t dumper, pc_run_info* out) {
+    try {
+        ModelSpec ms;
+        ms.like_kind = like_kind;
+        if (like_params) ms.like_params.assign(like_params, like_params + n_like_params);
+        if (prior_params) ms.prior_params.assign(prior_params, prior_params + n_prior_params);
+        int seed = s->seed;
+        return run_common(s, ms, 1, &seed, dumper, out);
+    } catch (const std::invalid_argument& ex) {
+        return fail(-2, ex.what());
+    } catch (const std::runtime_error& ex) {
+        return fail(-3, ex.what());
+    }
+}
+
+int pc_run_ensemble(const pc_settings* s, int like_kind, const double* like_params, int n_like_params,
+                    const double* prior_params, int n_prior_params, int nruns, const int* seeds, pc_run_info* out) {
+    try {
+        ModelSpec ms;
+        ms.like_kind = like_kind;
+        if (like_params) ms.like_params.assign(like_params, like_params + n_like_params);
+        if (prior_params) ms.prior_params.assign(prior_params, prior_params + n_prior_params);
+        return run_common(s, ms, nruns, seeds, nullptr, out);
+    } catch (const std::invalid_argument& ex) {
+        return fail(-2, ex.what());
+    } catch (const std::runtime_error& ex) {
+        return fail(-3, ex.what());
+    }
+}
+
+// ---- probes -------------------------------------------------------------------------------
+struct ProbeCtx {
+    DevModel dm;
+    Layout L;
+    ModelSpec ms;
+};
+static void probe_setup(ProbeCtx& c, const pc_settings* s, int like_kind, const double* lp, int nlp, const double* pp,
+                        int npp) {
+    device_check();
+    c.ms.like_kind = like_kind;
+    if (lp) c.ms.like_params.assign(lp, lp + nlp);
+    if (pp) c.ms.prior_params.assign(pp, pp + npp);
+    build_dev_model(*s, c.ms, c.dm, g_stream);
+    c.L = make_layout(*s, c.ms, c.dm, std::max(1, std::min(8, g_opt.warps_per_cta)));
+    set_smem(c.L.npl, c.L.smem);
+}
+
+int pc_slice_chains(const pc_settings* s, int like_kind, const double* like_params, int n_like_params,
+                    const double* prior_params, int n_prior_params, int nchains, const double* seed_points,
+                    const double* cholesky, const double* logL, const unsigned long long* uid, double* babies_out,
+                    long long* nlike_out) {
+    try {
+        ProbeCtx c;
+        probe_setup(c, s, like_kind, like_params, n_like_params, prior_params, n_prior_params);
+        const KParams& k = c.L.kp;
+        cudaStream_t st = g_stream;
+        DevArr<double> d_seed((size_t)nchains * k.T), d_chol((size_t)k.D * k.D), d_logL(nchains),
+            d_babies((size_t)nchains * k.R * k.T), d_nh;
+        DevArr<unsigned long long> d_uid(nchains);
+        DevArr<long long> d_nlike(nchains);
+        d_seed.upload(seed_points, (size_t)nchains * k.T, st);
+        d_chol.upload(cholesky, (size_t)k.D * k.D, st);
+        d_logL.upload(logL, nchains, st);
+        d_uid.upload(uid, nchains, st);
+        d_babies.zero(st);
+        int W = c.L.W;
+        int blocks = std::min(1024, (nchains + W - 1) / W);
+        if (!k.nh_in_smem) d_nh.alloc((size_t)blocks * W * k.R * k.LD);
+        KParams kp = k;
+        unsigned seed = (unsigned)s->seed;
+#define LAUNCH_SC(N)                                                                                                 \
+    pc_slice_chains_kernel<N><<<blocks, W * 32, c.L.smem, st>>>(kp, nchains, d_seed.p, d_chol.p, d_logL.p, d_uid.p, \
+                                                                 seed, d_babies.p, d_nlike.p, d_nh.p)
+        switch (c.L.npl) { case 1: LAUNCH_SC(1); break; case 2: LAUNCH_SC(2); break; case 3: LAUNCH_SC(3); break; default: LAUNCH_SC(4); }
+#undef LAUNCH_SC
+        PC_CUDA(cudaGetLastError());
+        d_babies.download(babies_out, (size_t)nchains * k.R * k.T, st);
+        d_nlike.download(nlike_out, nchains, st);
+        PC_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(-3, ex.what());
+    }
+}
+
+int pc_calculate_points(const pc_settings* s, int like_kind, const double* like_params, int n_like_params,
+                        const double* prior_params, int n_prior_params, double* records, int npts) {
+    try {
+        ProbeCtx c;
+        probe_setup(c, s, like_kind, like_params, n_like_params, prior_params, n_prior_params);
+        const KParams& k = c.L.kp;
+        cudaStream_t st = g_stream;
+        DevArr<double> d_rec((size_t)npts * k.T);
+        DevArr<int> d_n(1);
+        d_rec.upload(records, (size_t)npts * k.T, st);
+        d_n.zero(st);
+        int W = c.L.W;
+        int blocks = std::max(1, std::min(1024, (npts + W - 1) / W));
+        KParams kp = k;
+#define LAUNCH_CP(N) pc_calculate_points_kernel<N><<<blocks, W * 32, c.L.smem, st>>>(kp, d_rec.p, npts, d_n.p)
+        switch (c.L.npl) { case 1: LAUNCH_CP(1); break; case 2: LAUNCH_CP(2); break; case 3: LAUNCH_CP(3); break; default: LAUNCH_CP(4); }
+#undef LAUNCH_CP
+        PC_CUDA(cudaGetLastError());
+        int n = 0;
+        d_rec.download(records, (size_t)npts * k.T, st);
+        d_n.download(&n, 1, st);
+        PC_CUDA(cudaStreamSynchronize(st));
+        return n;
+    } catch (const std::exception& ex) {
+        return fail(-3, ex.what());
+    }
+}
+
+int pc_device_directions(int nDims, int num_repeats, unsigned seed, unsigned long long uid, double* out) {
+    try {
+        device_check();
+        const int D = nDims, R = num_repeats, LD = D | 1;
+        cudaStream_t st = g_stream;
+        DevArr<double> d_nh((size_t)R * LD), d_out((size_t)R * D);
+        size_t smem = (size_t)(((D + 1) & ~1) + R + 2) * 8;
+        int npl = (D + 31) / 32;
+        switch (npl) {
+            case 1: pc_directions_kernel<1><<<1, 32, smem, st>>>(D, R, LD, seed, uid, d_nh.p, d_out.p); break;
+            case 2: pc_directions_kernel<2><<<1, 32, smem, st>>>(D, R, LD, seed, uid, d_nh.p, d_out.p); break;
+            case 3: pc_directions_kernel<3><<<1, 32, smem, st>>>(D, R, LD, seed, uid, d_nh.p, d_out.p); break;
+            default: pc_directions_kernel<4><<<1, 32, smem, st>>>(D, R, LD, seed, uid, d_nh.p, d_out.p); break;
+        }
+        PC_CUDA(cudaGetLastError());
+        d_out.download(out, (size_t)R * D, st);
+        PC_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(-3, ex.what());
+    }
+}
+
+int pc_device_philox(const unsigned* ctr, const unsigned* key, unsigned* out4) {
+    try {
+        device_check();
+        DevArr<unsigned> c(4), k(2), o(4);
+        c.upload(ctr, 4, g_stream); k.upload(key, 2, g_stream);
+        pc_philox_kernel<<<1, 1, 0, g_stream>>>(c.p, k.p, o.p);
+        PC_CUDA(cudaGetLastError());
+        o.download(out4, 4, g_stream);
+        PC_CUDA(cudaStreamSynchronize(g_stream));
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(-3, ex.what());
+    }
+}
+int pc_device_uniforms(unsigned seed, unsigned tag, unsigned long long uid, unsigned a0, unsigned b, int n, double* out) {
+    try {
+        device_check();
+        DevArr<double> o(n);
+        pc_uniforms_kernel<<<(n + 255) / 256, 256, 0, g_stream>>>(seed, tag, uid, a0, b, n, o.p);
+        PC_CUDA(cudaGetLastError());
+        o.download(out, n, g_stream);
+        PC_CUDA(cudaStreamSynchronize(g_stream));
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(-3, ex.what());
+    }
+}
+int pc_device_inv_normal_cdf(const double* p, int n, double* out) {
+    try {
+        device_check();
+        DevArr<double> i(n), o(n);
+        i.upload(p, n, g_stream);
+        pc_inv_normal_kernel<<<(n + 255) / 256, 256, 0, g_stream>>>(i.p, n, o.p);
+        PC_CUDA(cudaGetLastError());
+        o.download(out, n, g_stream);
+        PC_CUDA(cudaStreamSynchronize(g_stream));
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(-3, ex.what());
+    }
+}
+// state = {logZ, logZ2, logX, logZX, logXX}; deaths with live counts n_start, n_start-1, ...
+int pc_device_evidence(double* state, const double* logLs, int count, int n_start, double* logw_out) {
+    try {
+        device_check();
+        DevRun h;
+        std::memset(&h, 0, sizeof(h));
+        h.logZ = state[0]; h.logZ2 = state[1]; h.logX = state[2]; h.logZX = state[3]; h.logXX = state[4];
+        DevArr<DevRun> st(1);
+        DevArr<double> l(count), w(count);
+        st.upload(&h, 1, g_stream);
+        l.upload(logLs, count, g_stream);
+        size_t smem = (size_t)(64 + count) * 8;
+        PC_CUDA(cudaFuncSetAttribute(pc_evidence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        pc_evidence_kernel<<<1, 256, smem, g_stream>>>(st.p, l.p, count, n_start, w.p);
+        PC_CUDA(cudaGetLastError());
+        st.download(&h, 1, g_stream);
+        w.download(logw_out, count, g_stream);
+        PC_CUDA(cudaStreamSynchronize(g_stream));
+        state[0] = h.logZ; state[1] = h.logZ2; state[2] = h.logX; state[3] = h.logZX; state[4] = h.logXX;
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(-3, ex.what());
+    }
+}
+int pc_device_cholesky(const double* a, int D, double* L_out) {
+    try {
+        device_check();
+        DevArr<double> da((size_t)D * D), dl((size_t)D * D);
+        DevArr<int> fb(1);
+        da.upload(a, (size_t)D * D, g_stream);
+        pc_cholesky_kernel<<<1, 32, 0, g_stream>>>(da.p, dl.p, D, fb.p);
+        PC_CUDA(cudaGetLastError());
+        int f = 0;
+        dl.download(L_out, (size_t)D * D, g_stream);
+        fb.download(&f, 1, g_stream);
+        PC_CUDA(cudaStreamSynchronize(g_stream));
+        return f;
+    } catch (const std::exception& ex) {
+        return fail(-3, ex.what());
+    }
+}
+
+// ==========================================================================================
+// Drop-in boundary
+// ==========================================================================================
+void polychord_c_interface(pc_loglikelihood_t loglikelihood, pc_prior_t prior, pc_dumper_t dumper, int nlive,
+                           int num_repeats, int nprior, int nfail, pc_bool do_clustering, int feedback,
+                           double precision_criterion, double logzero, int max_ndead, double boost_posterior,
+                           pc_bool posteriors, pc_bool equals, pc_bool cluster_posteriors, pc_bool write_resume,
+                           pc_bool write_paramnames, pc_bool read_resume, pc_bool write_stats, pc_bool write_live,
+                           pc_bool write_dead, pc_bool write_prior, pc_bool maximise, double compression_factor,
+                           pc_bool synchronous, int nDims, int nDerived, char* base_dir, char* file_root, int nGrade,
+                           double* grade_frac, int* grade_dims, int n_nlives, double* loglikes, int* nlives, int seed,
+                           int* comm) {
+    (void)write_resume; (void)write_paramnames; (void)read_resume; (void)write_stats; (void)write_live; (void)write_dead;
+    (void)write_prior; (void)maximise; (void)synchronous; (void)base_dir; (void)file_root; (void)grade_frac;
+    (void)loglikes; (void)nlives; (void)comm; (void)nfail; (void)do_clustering;
+    std::memset(&g_last, 0, sizeof(g_last));
+    pc_settings s;
+    std::memset(&s, 0, sizeof(s));
+    s.nDims = nDims; s.nDerived = nDerived; s.nlive = nlive; s.num_repeats = num_repeats; s.nprior = nprior; s.nfail = nfail;
+    s.do_clustering = do_clustering; s.feedback = feedback; s.precision_criterion = precision_criterion; s.logzero = logzero;
+    s.max_ndead = max_ndead; s.boost_posterior = boost_posterior; s.posteriors = posteriors; s.equals = equals;
+    s.cluster_posteriors = cluster_posteriors; s.compression_factor = compression_factor;
+    if (seed < 0) {  // random_utils.F90:60-75: seed from the system clock
+        seed = (int)(std::chrono::high_resolution_clock::now().time_since_epoch().count() & 0x7fffffff);
+    }
+    s.seed = seed;
+    if (nGrade != 1 || (grade_dims && grade_dims[0] != nDims)) {
+        fail(-4, "fast/slow parameter grades (nGrade > 1) are not supported by the B200 engine yet");
+        return;
+    }
+    if (n_nlives > 0) {
+        fail(-4, "dynamic nlive schedules (nlives/loglikes) are not supported by the B200 engine yet");
+        return;
+    }
+    auto li = like_registry().find((void*)loglikelihood);
+    auto pi = prior_registry().find((void*)prior);
+    ModelSpec ms;
+    bool have_like = true, have_prior = true;
+    if (li != like_registry().end()) { ms.like_kind = li->second.kind; ms.like_params = li->second.params; }
+    else if (loglikelihood == pc_gaussian_loglikelihood) ms.like_kind = PC_LIKE_GAUSSIAN;
+    else if (loglikelihood == pc_rastrigin_loglikelihood) ms.like_kind = PC_LIKE_RASTRIGIN;
+    else have_like = false;
+    if (pi != prior_registry().end()) ms.prior_params = pi->second.params;
+    else if (prior == pc_unit_prior || prior == pc_uniform_prior) {}
+    else have_prior = false;
+    if (!have_like || !have_prior) {
+        fail(-5, "the loglikelihood/prior callbacks are not registered with a device form "
+                 "(pc_register_device_likelihood / pc_register_device_prior); the generic host-callback path is not built yet");
+        return;
+    }
+    pc_run_info info;
+    try {
+        run_common(&s, ms, 1, &seed, dumper, &info);
+    } catch (const std::invalid_argument& ex) {
+        fail(-2, ex.what());
+        return;
+    } catch (const std::runtime_error& ex) {
+        fail(-3, ex.what());
+        return;
+    }
+    if (feedback >= 1) {
+        std::printf(" log(Z) = %12.5f +/- %8.5f   ndead = %lld  nlike = %lld  [B200 engine: K=%d, %d launches, %.2f ms]\n",
+                    info.logZ, info.logZerr, info.ndead, info.nlike, info.batch_K, info.kernel_launches, info.device_ms);
+        std::fflush(stdout);
+    }
+}
+
+void polychord_c_interface_ini(pc_loglikelihood_t loglikelihood, void (*setup_loglikelihood)(void), char* inifile,
+                               int* comm) {
+    (void)loglikelihood; (void)setup_loglikelihood; (void)inifile; (void)comm;
+    fail(-6, "polychord_c_interface_ini: the .ini driver path is outside the B200 engine's scope (SURVEY.md section 8 row f4)");
+}
+
+}  // extern "C"

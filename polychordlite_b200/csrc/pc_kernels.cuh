@@ -1,0 +1,562 @@
+// pc_kernels.cuh -- the sm_100a kernels of the nested-sampling engine.
+//
+// One PERSISTENT kernel (pc_run_kernel) advances whole nested-sampling runs on the device.
+// Each run owns a group of CTAs; inside a group every warp owns one slice-sampling chain at
+// a time (reference: src/polychord/chordal_sampling.f90:7-92 SliceSampling), the nDims-long
+// point lives in registers (lane r <-> dimension r, r+32, ...), directions are staged in
+// shared memory, and every likelihood evaluation ends in a warp-shuffle reduction whose
+// result drives the step-out / shrink decisions (chordal_sampling.f90:163-273).
+//
+// A generation (the batched form of one iteration of nested_sampling.F90:239-374):
+//   phase S (CTA 0 of the group)  termination test (run_time_info.f90:683-709), bitonic sort of
+//                                 (logL, slot), K lowest die: evidence recurrences
+//                                 (run_time_info.f90:211-296) as block-wide log-space scans
+//   phase C (all warps)           chain k: GenerateSeed (generate.F90:19-55) from the survivors,
+//                                 directions (random_utils.F90:381-437 + chordal_sampling.f90:94-145),
+//                                 Cholesky whitening (:73), R slice steps; babies stream to the
+//                                 phantom pool, the last baby replaces the dead slot
+//   phase U (all warps, at the    clean_phantoms (run_time_info.f90:820-877) as a stable
+//            update cadence)      compaction fused with calculate_covmats (:601-641); CTA 0
+//                                 finishes with calc_cholesky (utils.F90:621-649)
+// Groups synchronise with their own global-memory barrier, so many independent runs
+// (an ensemble) advance concurrently inside one launch.
+#pragma once
+#include "pc_device.cuh"
+
+namespace pc {
+
+enum Status : int { ST_RUNNING = 0, ST_DONE = 1, ST_NEED_DEAD = 2, ST_NEED_PHANTOM = 3, ST_DUMP = 4, ST_ERROR = -1 };
+enum LikeKind : int { LIKE_GAUSSIAN = 0, LIKE_RASTRIGIN = 1, LIKE_CORR = 2 };
+
+constexpr double NEG_BIG = -1e300;  // log(0) stand-in that survives additions without NaN
+constexpr int COV_ACC = 20;         // covariance accumulators per lane and pass
+
+// Mutable per-run scalars (device global memory; the host reads them between launches).
+struct DevRun {
+    double logZ, logZ2, logX, logZX, logXX;  // single-cluster evidence state (log space)
+    double logX_last_update;
+    double Lstar;     // contour of the generation in flight
+    double cov_N;     // points that entered the last covariance
+    long long ndead, nlike, nchains, ngen, nupdates, nfail, nslices;
+    long long nphantom;       // records in the current phantom pool
+    long long ndead_base;     // ndead before the generation in flight
+    long long nph_base;       // nphantom before the generation in flight
+    long long nchains_base;
+    long long init_attempts;
+    int cur_pool;
+    int K;
+    int do_update;
+    int update_pending;  // phase U ran, CTA 0 still has to finish covariance/Cholesky
+    int status;
+    int initialised;
+    int init_need;
+    int chol_fallback;   // number of calc_cholesky identity fallbacks
+    unsigned int bar;    // group barrier (monotonic)
+    unsigned int pad;
+};
+
+struct RunBuf {
+    DevRun* st;
+    double* live;      // n x T records
+    int* order;        // n slots sorted by (logL, slot)
+    double* dead;      // cap_dead x T
+    double* logw;      // cap_dead
+    double* ph[2];     // phantom pools (ping-pong), cap_ph x T each
+    double* chol;      // D x D column-major
+    double* cov;       // D x D column-major
+    double* partial;   // per CTA: [0]=count, [1..D]=sum x, then ntri covariance partials
+    long long* pcount; // per CTA survivor counts
+    double* nh;        // global direction scratch (used when the directions do not fit in smem)
+    long long cap_dead, cap_ph;
+    unsigned int seed;
+    int pad;
+};
+
+struct KParams {
+    int D, P, T, R, n, batch_K, LD;
+    int like_kind;
+    int use_prec, max_ndead;
+    int ctas_per_run, warps_per_cta;
+    int nh_in_smem, want_dump;
+    int ntri, cov_passes, partial_stride;
+    int off_like, off_warp, warp_bytes;  // shared-memory byte offsets
+    double logzero, log_prec, log_comp;
+    double gauss_norm, Vn, log_rast, corr_const;
+    const double* like_params;   // gaussian: mu[D], 1/sigma[D]; corr: mu[D], invcov[D*D]
+    const double* prior_params;  // lo[D], hi-lo[D]
+    RunBuf* runs;
+};
+
+// ------------------------------------------------------------------------------------------
+// group barrier (same fence / atomic / fence pattern cooperative groups uses for grid.sync)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void group_sync(unsigned int* bar, unsigned int G) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int t = atomicAdd(bar, 1u);
+        unsigned int target = (t / G + 1u) * G;
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// block-wide helpers for phase S (deterministic: fixed combination order)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* sc) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) sc[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < nw; ++i) t += sc[i];
+    __syncthreads();
+    return t;
+}
+__device__ __forceinline__ double block_max(double v, double* sc) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_max(v);
+    if (lane == 0) sc[w] = v;
+    __syncthreads();
+    double t = sc[0];
+    for (int i = 1; i < nw; ++i) t = fmax(t, sc[i]);
+    __syncthreads();
+    return t;
+}
+// log( exp(init) + sum_threads exp(v) )
+__device__ __forceinline__ double block_lse(double v, double init, double* sc) {
+    double m = fmax(block_max(v, sc), init);
+    double s = block_sum(exp(v - m), sc) + exp(init - m);
+    return m + log(s);
+}
+// exclusive prefix sum; *total receives the block total
+__device__ __forceinline__ double block_exscan_sum(double v, double* total, double* sc) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) sc[w] = inc;
+    double ex = __shfl_up_sync(FULL, inc, 1);
+    if (lane == 0) ex = 0.0;
+    __syncthreads();
+    double pre = 0.0, tot = 0.0;
+    for (int i = 0; i < nw; ++i) {
+        if (i < w) pre += sc[i];
+        tot += sc[i];
+    }
+    __syncthreads();
+    *total = tot;
+    return pre + ex;
+}
+// exclusive scan of affine maps x -> logaddexp(x + a, b), applied in thread order.
+__device__ __forceinline__ void affine_combine(double& a, double& b, double ea, double eb) {
+    // (ea,eb) earlier, (a,b) later:  x -> logaddexp(logaddexp(x+ea, eb) + a, b)
+    b = logaddexp(eb + a, b);
+    a = ea + a;
+}
+__device__ __forceinline__ void block_exscan_affine(double a, double b, double& exa, double& exb, double& tota,
+                                                    double& totb, double* sc) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double ia = a, ib = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double pa = __shfl_up_sync(FULL, ia, o), pb = __shfl_up_sync(FULL, ib, o);
+        if (lane >= o) affine_combine(ia, ib, pa, pb);
+    }
+    if (lane == 31) { sc[2 * w] = ia; sc[2 * w + 1] = ib; }
+    double pa = __shfl_up_sync(FULL, ia, 1), pb = __shfl_up_sync(FULL, ib, 1);
+    if (lane == 0) { pa = 0.0; pb = NEG_BIG; }
+    __syncthreads();
+    double wa = 0.0, wb = NEG_BIG, ta = 0.0, tb = NEG_BIG;
+    for (int i = 0; i < nw; ++i) {
+        double ca = sc[2 * i], cb = sc[2 * i + 1];
+        if (i < w) { double xa = ca, xb = cb; affine_combine(xa, xb, wa, wb); wa = xa; wb = xb; }
+        { double xa = ca, xb = cb; affine_combine(xa, xb, ta, tb); ta = xa; tb = xb; }
+    }
+    __syncthreads();
+    // exclusive = (warps before) then (lanes before)
+    affine_combine(pa, pb, wa, wb);
+    exa = pa; exb = pb; tota = ta; totb = tb;
+}
+
+// bitonic sort of (key, val) ascending by key then val; np2 a power of two
+__device__ inline void block_sort(double* key, int* val, int np2) {
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    double ka = key[i], kb = key[ixj];
+                    int va = val[i], vb = val[ixj];
+                    bool gt = (ka > kb) || (ka == kb && va > vb);
+                    bool up = ((i & k) == 0);
+                    if (gt == up) { key[i] = kb; key[ixj] = ka; val[i] = vb; val[ixj] = va; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Evidence recurrences for `count` consecutive deaths with live counts n_start, n_start-1, ...
+// (run_time_info.f90:211-296 applied as in the final kill-off nested_sampling.F90:381-384).
+// X and XX are prefix sums, ZX a first-order linear recurrence (affine scan), Z and Z2
+// log-sum-exp reductions.  skey: ascending logL of the dying points (shared memory).
+// ------------------------------------------------------------------------------------------
+__device__ inline void evidence_deaths(DevRun* st, const double* skey, int count, int n_start, double* logw_out,
+                                       double* sc) {
+    const double LOG2 = 0.69314718055994530942;
+    double lX = st->logX, lXX = st->logXX, lZX = st->logZX, lZ = st->logZ, lZ2 = st->logZ2;
+    __syncthreads();
+    for (int base = 0; base < count; base += blockDim.x) {
+        int j = base + threadIdx.x;
+        bool act = j < count;
+        double nj = (double)(n_start - (act ? j : 0));
+        double l0n = log(nj), l1 = log(nj + 1.0), l2 = log(nj + 2.0);
+        double dx = act ? l0n - l1 : 0.0, dxx = act ? l0n - l2 : 0.0;
+        double totx, totxx;
+        double lXb = lX + block_exscan_sum(dx, &totx, sc);
+        double lXXb = lXX + block_exscan_sum(dxx, &totxx, sc);
+        double L = act ? skey[j] : 0.0;
+        double a = dx, b = act ? lXXb + L + l0n - l1 - l2 : NEG_BIG;
+        double exa, exb, tota, totb;
+        block_exscan_affine(a, b, exa, exb, tota, totb, sc);
+        double ZXb = logaddexp(lZX + exa, exb);
+        double tZ = act ? lXb + L - l1 : NEG_BIG;
+        double tZ2 = act ? logaddexp(LOG2 + ZXb + L - l1, LOG2 + lXXb + 2.0 * L - l1 - l2) : NEG_BIG;
+        if (act) logw_out[j] = lXb - l1;
+        lZ = block_lse(tZ, lZ, sc);
+        lZ2 = block_lse(tZ2, lZ2, sc);
+        lZX = logaddexp(lZX + tota, totb);
+        lX += totx;
+        lXX += totxx;
+    }
+    if (threadIdx.x == 0) { st->logX = lX; st->logXX = lXX; st->logZX = lZX; st->logZ = lZ; st->logZ2 = lZ2; }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-lane view of the model: lane holds dimensions lane, lane+32, ...
+// ------------------------------------------------------------------------------------------
+template <int NPL>
+struct Model {
+    double mu[NPL], isig[NPL], lo[NPL], wid[NPL];
+    bool valid[NPL];
+    int D, P, kind, lane;
+    double logzero, gauss_norm, Vn, log_rast, corr_const;
+    const double* invcov;  // shared memory, D x D column-major (corr only)
+    double* dvec;          // per-warp shared scratch, D doubles
+
+    __device__ void init(const KParams& p, const double* s_like, double* warp_dvec) {
+        D = p.D; P = p.P; kind = p.like_kind; lane = threadIdx.x & 31;
+        logzero = p.logzero; gauss_norm = p.gauss_norm; Vn = p.Vn; log_rast = p.log_rast; corr_const = p.corr_const;
+        invcov = s_like + D;
+        dvec = warp_dvec;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            int r = lane + 32 * j;
+            valid[j] = r < D;
+            lo[j] = valid[j] ? p.prior_params[r] : 0.0;
+            wid[j] = valid[j] ? p.prior_params[D + r] : 0.0;
+            mu[j] = 0.0; isig[j] = 0.0;
+            if (valid[j] && kind != LIKE_RASTRIGIN) mu[j] = s_like[r];
+            if (valid[j] && kind == LIKE_GAUSSIAN) isig[j] = s_like[D + r];
+        }
+    }
+
+    // calculate_point (calculate.f90:6-50): in-cube test, uniform prior (priors.f90:40-55) and
+    // log-likelihood.  Warp-collective; the result is identical on every lane.
+    __device__ __forceinline__ double eval(const double (&x)[NPL], double (&theta)[NPL]) const {
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) ok = ok && (!valid[j] || (x[j] >= 0.0 && x[j] <= 1.0));
+        if (!__all_sync(FULL, ok)) {
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) theta[j] = 0.0;
+            return logzero;
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) theta[j] = lo[j] + wid[j] * x[j];
+        if (kind == LIKE_GAUSSIAN) {  // likelihoods/examples/gaussian.f90:12-41
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) {
+                double z = (theta[j] - mu[j]) * isig[j];
+                acc += valid[j] ? z * z : 0.0;
+            }
+            return -gauss_norm - warp_sum(acc) / 2.0;
+        } else if (kind == LIKE_RASTRIGIN) {  // likelihoods/examples/rastrigin.f90:20-35
+            const double TwoPi = 6.283185307179586476925286766559;
+#pragma unroll
+            for (int j = 0; j < NPL; ++j)
+                acc += valid[j] ? log_rast + theta[j] * theta[j] - 10.0 * cos(TwoPi * theta[j]) : 0.0;
+            return -warp_sum(acc);
+        } else {  // utils.F90:1028-1048 log_gauss with a dense inverse covariance
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < NPL; ++j)
+                if (valid[j]) dvec[lane + 32 * j] = theta[j] - mu[j];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) {
+                if (valid[j]) {
+                    int r = lane + 32 * j;
+                    double y = 0.0;
+                    for (int c = 0; c < D; ++c) y += invcov[r + c * D] * dvec[c];
+                    acc += (theta[j] - mu[j]) * y;
+                }
+            }
+            return corr_const - warp_sum(acc) / 2.0;
+        }
+    }
+
+    // derived parameters of the accepted point (gaussian.f90:37-40); lane 0 writes them
+    __device__ __forceinline__ void derived(const double (&theta)[NPL], double* phi_out) const {
+        if (P <= 0) return;
+        if (kind == LIKE_GAUSSIAN) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) acc += valid[j] ? (theta[j] - mu[j]) * (theta[j] - mu[j]) : 0.0;
+            double r = sqrt(warp_sum(acc));
+            if (lane == 0) {
+                phi_out[0] = r;
+                if (P >= 2) phi_out[1] = log(pow(r, (double)D) * Vn);
+                for (int i = 2; i < P; ++i) phi_out[i] = 0.0;
+            }
+        } else if (lane == 0) {
+            for (int i = 0; i < P; ++i) phi_out[i] = 0.0;
+        }
+    }
+
+    // full record [cube | theta | phi | birth | logL] (settings.f90:163-182)
+    __device__ __forceinline__ void write_record(double* rec, const double (&x)[NPL], const double (&theta)[NPL],
+                                                 double birth, double logL) const {
+#pragma unroll
+        for (int j = 0; j < NPL; ++j)
+            if (valid[j]) {
+                rec[lane + 32 * j] = x[j];
+                rec[D + lane + 32 * j] = theta[j];
+            }
+        derived(theta, rec + 2 * D);
+        if (lane == 0) {
+            rec[2 * D + P] = birth;
+            rec[2 * D + P + 1] = logL;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Directions of one chain: ceil(R/D) Haar-random orthonormal bases by Gram-Schmidt on Gaussian
+// vectors (random_utils.F90:381-437), then a Fisher-Yates shuffle of columns 2..R
+// (chordal_sampling.f90:133-136, random_utils.F90:505-532) kept as an index deck.
+// nh: R columns with leading dimension LD (odd, bank-conflict free); deck/jd: R ints; dots: D doubles.
+// ------------------------------------------------------------------------------------------
+template <int NPL>
+__device__ inline void gen_directions(int D, int R, int LD, unsigned seed, unsigned long long uid, double* nh, int* deck,
+                                      int* jd, double* dots) {
+    const int lane = threadIdx.x & 31;
+    for (int col0 = 0; col0 < R; col0 += D) {
+        const int m = min(D, R - col0);
+        for (int i = 0; i < m; ++i) {
+            const int col = col0 + i;
+            double* vp = nh + (size_t)col * LD;
+            double v[NPL];
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) {
+                int r = lane + 32 * j;
+                v[j] = 0.0;
+                if (r < D) {
+                    double u0, u1;
+                    uniform2(seed, TAG_DIR, uid, (unsigned)col, (unsigned)(r >> 1), u0, u1);
+                    v[j] = inv_normal_cdf((r & 1) ? u1 : u0);
+                }
+                acc += v[j] * v[j];
+            }
+            double nrm = sqrt(warp_sum(acc));
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) {
+                v[j] /= nrm;
+                if (lane + 32 * j < D) vp[lane + 32 * j] = v[j];
+            }
+            __syncwarp();
+            // projections on the earlier vectors of this basis: lane jj owns <v, q_jj>
+            for (int jj = lane; jj < i; jj += 32) {
+                const double* q = nh + (size_t)(col0 + jj) * LD;
+                double d = 0.0;
+                for (int r = 0; r < D; ++r) d += vp[r] * q[r];
+                dots[jj] = d;
+            }
+            __syncwarp();
+            acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) {
+                int r = lane + 32 * j;
+                if (r < D) {
+                    double t = v[j];
+                    for (int jj = 0; jj < i; ++jj) t -= dots[jj] * nh[(size_t)(col0 + jj) * LD + r];
+                    v[j] = t;
+                } else {
+                    v[j] = 0.0;
+                }
+                acc += v[j] * v[j];
+            }
+            nrm = sqrt(warp_sum(acc));
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < NPL; ++j)
+                if (lane + 32 * j < D) vp[lane + 32 * j] = v[j] / nrm;
+            __syncwarp();
+        }
+    }
+    for (int i = lane; i < R; i += 32) {
+        deck[i] = i;
+        int j = 0;
+        if (i >= 1) {
+            double u = uniform(seed, TAG_SHUF, uid, (unsigned)i, 0u);
+            j = (int)ceil(u * (double)i);
+            if (j < 1) j = 1;
+        }
+        jd[i] = j;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (int i = R - 1; i >= 1; --i) {
+            int j = jd[i];
+            int t = deck[i]; deck[i] = deck[j]; deck[j] = t;
+        }
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// One chain: R slice steps from x (chordal_sampling.f90:7-92 and :163-273).
+// babies 0..R-2 go to ph_base + i*T, the last one to last_dst.  Returns the final logL.
+// ------------------------------------------------------------------------------------------
+template <int NPL>
+__device__ inline double run_chain(const KParams& p, const Model<NPL>& M, unsigned seed, unsigned long long uid,
+                                   double (&x)[NPL], double Lstar, const double* s_chol, double* nh, int* deck, int* jd,
+                                   double* dots, double* ph_base, double* last_dst, unsigned long long& nlike) {
+    const int D = p.D, R = p.R, LD = p.LD, T = p.T, lane = threadIdx.x & 31;
+    const double logzero = p.logzero;
+    gen_directions<NPL>(D, R, LD, seed, uid, nh, deck, jd, dots);
+    double logL_cur = logzero;
+    for (int i = 0; i < R; ++i) {
+        const double* q = nh + (size_t)deck[i] * LD;
+        // nhats = matmul(cholesky, nhats)  (chordal_sampling.f90:73); w = 3*|nhat| (:80-82)
+        double nhat[NPL], acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            int r = lane + 32 * j;
+            double s = 0.0;
+            if (r < D)
+                for (int k = 0; k < D; ++k) s += s_chol[r + k * D] * q[k];
+            nhat[j] = s;
+            acc += s * s;
+        }
+        double w = sqrt(warp_sum(acc));
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) nhat[j] /= w;
+        w *= 3.0;
+
+        // ---- slice_sample (chordal_sampling.f90:163-273), bounds kept as distances dL, dR >= 0 ----
+        double u0 = uniform(seed, TAG_SLICE, uid, (unsigned)i, 0u);
+        double dL = u0 * w, dR = (1.0 - u0) * w;
+        double y[NPL], th[NPL];
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) y[j] = x[j] + dR * nhat[j];
+        double lR = M.eval(y, th);
+        if (lR > logzero) ++nlike;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) y[j] = x[j] - dL * nhat[j];
+        double lL = M.eval(y, th);
+        if (lL > logzero) ++nlike;
+        int istep = 0;
+        while (lR >= Lstar && lR > logzero) {  // step out (:223-227)
+            ++istep;
+            dR = w * (double)istep;
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) y[j] = x[j] + dR * nhat[j];
+            lR = M.eval(y, th);
+            if (lR > logzero) ++nlike;
+        }
+        istep = 0;
+        while (lL >= Lstar && lL > logzero) {  // (:232-236)
+            ++istep;
+            dL = w * (double)istep;
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) y[j] = x[j] - dL * nhat[j];
+            lL = M.eval(y, th);
+            if (lL > logzero) ++nlike;
+        }
+        double lnew = logzero;
+        bool accepted = false;
+        for (int s = 0; s <= 100; ++s) {  // shrink (:240-266)
+            double u = uniform(seed, TAG_SLICE, uid, (unsigned)i, (unsigned)(1 + s));
+            double t = u * (dR + dL) - dL;
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) y[j] = x[j] + t * nhat[j];
+            lnew = M.eval(y, th);
+            if (lnew > logzero) ++nlike;
+            if (lnew < Lstar || lnew <= logzero) {
+                if (t > 0.0) dR = t; else dL = -t;
+            } else {
+                accepted = true;
+                break;
+            }
+        }
+        if (!accepted) lnew = logzero;  // "Non deterministic loglikelihood" (:268-271)
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) x[j] = y[j];  // next start = this baby even if it failed (:88)
+        double* dst = (i == R - 1) ? last_dst : ph_base + (size_t)i * T;
+        M.write_record(dst, y, th, Lstar, lnew);
+        logL_cur = lnew;
+    }
+    return logL_cur;
+}
+
+// ------------------------------------------------------------------------------------------
+// Cholesky with the reference's fallback (utils.F90:621-649), one warp, column-major in smem/global.
+// ------------------------------------------------------------------------------------------
+__device__ inline int warp_cholesky(const double* a, double* L, int D) {
+    const int lane = threadIdx.x & 31;
+    for (int e = lane; e < D * D; e += 32) L[e] = 0.0;
+    __syncwarp();
+    int fallback = 0;
+    for (int i = 0; i < D; ++i) {
+        double s = 0.0;
+        for (int k = 0; k < i; ++k) s += L[i + k * D] * L[i + k * D];
+        double dii = a[i + i * D] - s;
+        if (dii <= 0.0) { fallback = 1; break; }
+        dii = sqrt(dii);
+        __syncwarp();
+        if (lane == 0) L[i + i * D] = dii;
+        for (int j = i + 1 + lane; j < D; j += 32) {
+            double t = 0.0;
+            for (int k = 0; k < i; ++k) t += L[i + k * D] * L[j + k * D];
+            L[j + i * D] = (a[i + j * D] - t) / dii;
+        }
+        __syncwarp();
+    }
+    if (fallback) {
+        double tr = 0.0;
+        for (int k = 0; k < D; ++k) tr += a[k + k * D];
+        __syncwarp();
+        for (int e = lane; e < D * D; e += 32) L[e] = 0.0;
+        __syncwarp();
+        for (int k = lane; k < D; k += 32) L[k + k * D] = sqrt(tr);
+        __syncwarp();
+    }
+    return fallback;
+}
+
+}  // namespace pc

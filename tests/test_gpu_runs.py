@@ -1,0 +1,169 @@
+"""GPU parity, whole runs: the persistent kernel against the oracle's batched-generation mode on
+identical seeds, the analytic evidences, and the reference's behavioural contracts."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).parent / "golden"
+ANALYTIC = json.loads((GOLDEN / "analytic.json").read_text())
+
+
+def both(gpu, oracle, like="gaussian", extra=None, **kw):
+    extra = extra or {}
+    K = kw.pop("batch_K")
+    so = oracle.make_settings(batch_K=K, **kw)
+    sg = gpu.make_settings(**kw)
+    gpu.set_option("batch_K", K)
+    try:
+        gi, gd = gpu.run(sg, like=like, want_dump=True, **extra)
+    finally:
+        gpu.set_option("batch_K", 0)
+    oi, od = oracle.run(so, like=like, want_dump=True, **extra)
+    return gi, gd, oi, od
+
+
+@pytest.mark.parametrize("kw", [
+    dict(nDims=4, nDerived=1, nlive=64, num_repeats=8, seed=0, batch_K=16),
+    dict(nDims=20, nDerived=2, nlive=200, num_repeats=40, seed=1, batch_K=50),
+    dict(nDims=20, nDerived=2, nlive=1000, num_repeats=40, seed=2, batch_K=250),   # BASELINE config 2
+    dict(nDims=6, nDerived=0, nlive=100, num_repeats=12, seed=3, batch_K=99),      # K = nlive-1
+    dict(nDims=6, nDerived=0, nlive=100, num_repeats=12, seed=3, batch_K=1),       # one death per generation
+    dict(nDims=3, nDerived=0, nlive=50, num_repeats=1, seed=4, batch_K=10),        # no phantoms at all
+])
+def test_run_matches_oracle_batched_mode(gpu, oracle, kw):
+    """Same seeds, same schedule -> same decisions: identical death/eval/update counts, and logZ,
+    dead points and weights equal within 1e-7 (FP re-association; see DESIGN.md 'Parity')."""
+    gi, gd, oi, od = both(gpu, oracle, **dict(kw))
+    assert (gi.ndead, gi.nlike, gi.nchains, gi.ngenerations, gi.nupdates, gi.nfailures) == \
+           (oi.ndead, oi.nlike, oi.nchains, oi.ngenerations, oi.nupdates, oi.nfailures)
+    assert gi.nphantoms_final == oi.nphantoms_final
+    assert abs(gi.logZ - oi.logZ) < 1e-7 and abs(gi.logZerr - oi.logZerr) < 1e-7
+    assert len(gd) == len(od)
+    for a, b in zip(gd, od):
+        assert a["dead"].shape == b["dead"].shape and a["live"].shape == b["live"].shape
+        assert np.allclose(a["dead"], b["dead"], rtol=0, atol=1e-6)
+        assert np.allclose(a["logweights"], b["logweights"], rtol=0, atol=1e-6)
+        assert abs(a["logZ"] - b["logZ"]) < 1e-7
+        # live rows: the oracle holds them in slot order too
+        assert np.allclose(a["live"], b["live"], rtol=0, atol=1e-6)
+
+
+def test_run_matches_golden_fixture(gpu):
+    g = json.loads((GOLDEN / "oracle_golden.json").read_text())
+    for case in g["runs"]:
+        if case["batch_K"] == 0:
+            continue
+        sg = gpu.make_settings(case["D"], case["P"], nlive=case["nlive"], num_repeats=case["R"], seed=case["seed"])
+        gpu.set_option("batch_K", case["batch_K"])
+        try:
+            gi, _ = gpu.run(sg)
+        finally:
+            gpu.set_option("batch_K", 0)
+        assert gi.ndead == case["ndead"] and gi.nlike == case["nlike"] and gi.nupdates == case["nupdates"]
+        assert abs(gi.logZ - case["logZ"]) < 1e-7
+
+
+def test_rastrigin_and_box_prior_run_matches_oracle(gpu, oracle):
+    D = 4
+    extra = dict(prior_lo=[-5.12] * D, prior_hi=[5.12] * D)
+    gi, gd, oi, od = both(gpu, oracle, like="rastrigin", extra=extra, nDims=D, nDerived=0, nlive=200,
+                          num_repeats=12, seed=6, batch_K=50)
+    assert (gi.ndead, gi.nlike, gi.nupdates) == (oi.ndead, oi.nlike, oi.nupdates)
+    assert abs(gi.logZ - oi.logZ) < 1e-7
+
+
+def test_corr_gaussian_run_matches_oracle(gpu, oracle):
+    D = 12
+    inv, logdet = oracle.random_inverse_covmat(4, D, float(np.float32(0.1)))
+    extra = dict(like_params=np.concatenate([np.full(D, 0.5), inv.ravel(order="F"), [logdet]]))
+    gi, gd, oi, od = both(gpu, oracle, like="corr_gaussian", extra=extra, nDims=D, nDerived=0, nlive=150,
+                          num_repeats=24, seed=8, batch_K=40)
+    assert (gi.ndead, gi.nlike, gi.nupdates) == (oi.ndead, oi.nlike, oi.nupdates)
+    assert abs(gi.logZ - oi.logZ) < 1e-6
+
+
+def test_ensemble_logZ_gaussian20_nlive1000_matches_analytic(gpu):
+    """BASELINE config 2 at full size: 20-D Gaussian, nlive=1000, num_repeats=40.  Single-run scatter
+    (sqrt(H/nlive)=0.133) exceeds the north star's +-0.1, so parity is an ensemble statement:
+    the mean over 32 seeds (s.e. ~0.024) must sit within 0.1 of the analytic logZ."""
+    s = gpu.make_settings(20, 2, nlive=1000, num_repeats=40)
+    infos = gpu.run_ensemble(s, list(range(32)))
+    z = np.array([i.logZ for i in infos])
+    se = z.std(ddof=1) / np.sqrt(z.size)
+    assert abs(z.mean() - ANALYTIC["gaussian20_unit_cube"]["logZ"]) < 0.1
+    assert abs(z.mean() - ANALYTIC["gaussian20_unit_cube"]["logZ"]) < 4 * se
+    assert 0.08 < z.std(ddof=1) < 0.22
+    assert all(i.nfailures == 0 for i in infos)
+    e = np.mean([i.nlike / i.nslices for i in infos])
+    assert 3.5 < e < 7.0
+
+
+def test_ensemble_member_equals_single_run(gpu):
+    """A run inside an ensemble launch is bit-identical to the same seed run alone."""
+    s = gpu.make_settings(8, 1, nlive=100, num_repeats=16, seed=5)
+    single, _ = gpu.run(s)
+    infos = gpu.run_ensemble(s, [3, 5, 9])
+    assert infos[1].logZ == single.logZ and infos[1].nlike == single.nlike and infos[1].ndead == single.ndead
+    assert infos[0].logZ != infos[1].logZ
+
+
+def test_seed_determinism_and_nDerived_independence(gpu):
+    """tests/test_run_pypolychord.py:77-119 of the reference, on the device path."""
+    a, da = gpu.run(gpu.make_settings(4, 1, nlive=100, num_repeats=12, seed=2), want_dump=True)
+    b, db = gpu.run(gpu.make_settings(4, 1, nlive=100, num_repeats=12, seed=2), want_dump=True)
+    c, dc = gpu.run(gpu.make_settings(4, 0, nlive=100, num_repeats=12, seed=2), want_dump=True)
+    d, _ = gpu.run(gpu.make_settings(4, 1, nlive=100, num_repeats=12, seed=3))
+    assert a.logZ == b.logZ and a.nlike == b.nlike
+    assert np.array_equal(da[-1]["dead"], db[-1]["dead"]) and np.array_equal(da[-1]["logweights"], db[-1]["logweights"])
+    assert a.logZ == c.logZ and np.array_equal(da[-1]["dead"][:, :4], dc[-1]["dead"][:, :4])
+    assert a.logZ != d.logZ
+
+
+def test_posterior_moments_and_dumper_contract(gpu):
+    D = 20
+    s = gpu.make_settings(D, 2, nlive=1000, num_repeats=40, seed=4)
+    info, dumps = gpu.run(s, want_dump=True)
+    assert len(dumps) == info.nupdates + 1
+    last = dumps[-1]
+    assert last["live"].shape[0] == 0 and last["dead"].shape == (info.ndead, D + 4)
+    w = np.exp(last["logweights"])
+    assert np.isclose(w.sum(), 1.0, rtol=1e-10)
+    theta = last["dead"][:, :D]
+    mean = (w[:, None] * theta).sum(0)
+    sd = np.sqrt((w[:, None] * (theta - mean) ** 2).sum(0))
+    assert np.all(np.abs(mean - 0.5) < 0.02) and np.all(np.abs(sd - 0.1) < 0.015)
+    assert np.all(np.diff(last["dead"][:, -1]) >= 0)
+    assert np.all(last["dead"][:, -2] <= last["dead"][:, -1])
+    assert dumps[0]["live"].shape == (1000, D + 4)
+
+
+def test_max_ndead(gpu, oracle):
+    s = gpu.make_settings(4, 0, nlive=50, num_repeats=8, max_ndead=95, seed=1)
+    gpu.set_option("batch_K", 10)
+    try:
+        r, _ = gpu.run(s)
+        r0, _ = gpu.run(gpu.make_settings(4, 0, nlive=50, num_repeats=8, max_ndead=0, seed=1))
+    finally:
+        gpu.set_option("batch_K", 0)
+    assert r.ndead == 145 and r.nchains == 95
+    assert r0.ndead == 50 and r0.nchains == 0 and r0.nlike == 50
+    o, _ = oracle.run(oracle.make_settings(4, 0, nlive=50, num_repeats=8, max_ndead=95, seed=1, batch_K=10))
+    assert abs(o.logZ - r.logZ) < 1e-8
+
+
+def test_capacity_growth_paths(gpu):
+    """Dead/phantom pools grow by relaunching the persistent kernel; results must not change."""
+    s = gpu.make_settings(3, 0, nlive=40, num_repeats=6, seed=7)
+    a, _ = gpu.run(s)
+    gpu.set_option("cap_dead0", 1)
+    gpu.set_option("cap_ph0", 1)
+    try:
+        b, _ = gpu.run(s)
+    finally:
+        gpu.set_option("cap_dead0", 0)
+        gpu.set_option("cap_ph0", 0)
+    assert b.kernel_launches > a.kernel_launches
+    assert a.logZ == b.logZ and a.nlike == b.nlike and a.ndead == b.ndead
