@@ -320,9 +320,9 @@ struct Model {
     }
 
     // derived parameters of the accepted point (gaussian.f90:37-40); lane 0 writes them
-    __device__ __forceinline__ void derived(const double (&theta)[NPL], double* phi_out) const {
+    __device__ __forceinline__ void derived(const double (&theta)[NPL], double* phi_out, bool incube) const {
         if (P <= 0) return;
-        if (kind == LIKE_GAUSSIAN) {
+        if (kind == LIKE_GAUSSIAN && incube) {
             double acc = 0.0;
 #pragma unroll
             for (int j = 0; j < NPL; ++j) acc += valid[j] ? (theta[j] - mu[j]) * (theta[j] - mu[j]) : 0.0;
@@ -346,7 +346,10 @@ struct Model {
                 rec[lane + 32 * j] = x[j];
                 rec[D + lane + 32 * j] = theta[j];
             }
-        derived(theta, rec + 2 * D);
+        bool ok = true;  // out-of-cube points never reach the likelihood (calculate.f90:36-39): phi = 0
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) ok = ok && (!valid[j] || (x[j] >= 0.0 && x[j] <= 1.0));
+        derived(theta, rec + 2 * D, __all_sync(FULL, ok));
         if (lane == 0) {
             rec[2 * D + P] = birth;
             rec[2 * D + P + 1] = logL;
