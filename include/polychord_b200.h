@@ -125,6 +125,11 @@ typedef struct pc_run_info {
     double wall_ms;           /* entry to return of the call */
     long long h2d_bytes, d2h_bytes;
     long long algorithmic_bytes; /* 8T+8D per slice, 8T per chain, 8D^2 per generation */
+    /* where the run kernel's time went, from SM clock counters (ms at the device's nominal SM clock):
+     * [0] CTA 0 waiting for the chains, [1] phase S (select/evidence), [2] covariance+Cholesky finish,
+     * [3] phase U (phantom compaction + covariance), [4..6] one representative chain warp: direction
+     * preparation left on the critical path, whitening, slice steps; [7] whole kernel */
+    double phase_ms[8];
 } pc_run_info;
 
 /* Results of the most recent polychord_c_interface()/pc_run() in this process. */

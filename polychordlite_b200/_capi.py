@@ -48,11 +48,14 @@ class RunInfo(C.Structure):
         ("nslices", C.c_longlong), ("nphantoms_final", C.c_longlong), ("batch_K", C.c_int),
         ("warps_per_cta", C.c_int), ("ctas_per_run", C.c_int), ("kernel_launches", C.c_int),
         ("device_ms", C.c_double), ("wall_ms", C.c_double), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong),
-        ("algorithmic_bytes", C.c_longlong),
+        ("algorithmic_bytes", C.c_longlong), ("phase_ms", C.c_double * 8),
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["phase_ms"] = dict(zip(("wait_chains", "phase_S", "finish_update", "phase_U", "prep", "whiten", "slices",
+                                  "kernel"), list(self.phase_ms)))
+        return d
 
 
 _lib = None

@@ -1,0 +1,528 @@
+// pc_chain.cuh -- one slice-sampling chain on one warp (the hot path).
+//
+// Reference: src/polychord/chordal_sampling.f90:7-92 (SliceSampling), :94-145 (generate_nhats),
+// :163-273 (slice_sample); random_utils.F90:381-437 (orthonormal bases), :505-532 (shuffle_deck);
+// calculate.f90:6-50 (calculate_point); likelihoods/examples/{gaussian,rastrigin,random_gaussian}.f90.
+//
+// Warp organisation.  The 32 lanes of a warp form NPT = 32/G "point groups" of G lanes.  Every
+// group holds the chain's current point x and the slice direction nhat in registers (lane `sub`
+// of a group owns dimensions sub, sub+G, ...; DPL = ceil(D/G) values per lane), so one warp
+// instruction stream evaluates NPT different trial points x + t_p * nhat at once and a
+// log2(G)-stage shuffle reduction finishes each group's likelihood.  The trial points of a slice
+// step are known before their likelihoods are: the bracket ends, the step-out multiples and --
+// because a rejected shrink candidate moves a bound to its own position -- the whole sequence of
+// shrink candidates under the hypothesis "all earlier ones were rejected".  A round therefore
+// evaluates [R0, L0, candidate 1..NPT-2] speculatively, a ballot collects the accept bits, and
+// the sequential decisions of slice_sample are replayed on the bit mask.  The result (accepted
+// point, bounds, and the nlike count of the evaluations the sequential algorithm would have
+// made) is identical to the sequential algorithm's; speculative evaluations it would not have
+// made are simply not counted.
+//
+// Everything random is counter-addressed (pc_device.cuh), so the directions, the shuffle deck and
+// the slice uniforms of a chain depend only on (seed, uid): prep_chain() can run before the
+// chain's generation starts (the run kernel overlaps it with the generation barrier).
+#pragma once
+#include "pc_device.cuh"
+
+namespace pc {
+
+enum LikeKind : int { LIKE_GAUSSIAN = 0, LIKE_RASTRIGIN = 1, LIKE_CORR = 2 };
+
+constexpr int NU = 9;  // uniforms staged per slice step: u0 and the first 8 shrink draws (two shrink rounds)
+
+// What the chain code needs from the run configuration.
+struct ChainParams {
+    int D, P, T, R, LD;
+    int like_kind;
+    double logzero;
+    double gauss_norm, Vn, log_rast, corr_const;
+};
+
+// Per-warp scratch (shared memory; nh may live in global memory when R*D is large).
+struct ChainScratch {
+    double* nh;    // R columns, leading dimension LD (odd): raw orthonormal basis, then whitened unit directions
+    double* wts;   // R: initial bracket width w = 3*|L q| of each column
+    double* uni;   // R x NU slice uniforms
+    double* dots;  // 4 x Dpad Gram-Schmidt projections
+    double* dvec;  // NPT x Dpad (correlated Gaussian only)
+    int* deck;     // R: column used by slice i
+    int* jd;       // R: Fisher-Yates picks
+};
+
+__host__ __device__ inline size_t chain_scratch_bytes(int D, int R, int LD, bool nh_in_smem, int like_kind, int npt) {
+    const int Dpad = (D + 1) & ~1;
+    size_t b = 0;
+    if (nh_in_smem) b += (size_t)R * LD * 8;
+    b += (size_t)R * 8;                 // wts
+    b += (size_t)R * NU * 8;            // uni
+    b += (size_t)4 * Dpad * 8;          // dots
+    if (like_kind == LIKE_CORR) b += (size_t)npt * Dpad * 8;
+    b += (size_t)((2 * R + 1) & ~1) * 4;  // deck + jd
+    return (b + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ ChainScratch chain_scratch(unsigned char* base, int D, int R, int LD, bool nh_in_smem,
+                                                      int like_kind, int npt, double* nh_global) {
+    ChainScratch cs;
+    const int Dpad = (D + 1) & ~1;
+    double* d = (double*)base;
+    if (nh_in_smem) { cs.nh = d; d += (size_t)R * LD; } else cs.nh = nh_global;
+    cs.wts = d; d += R;
+    cs.uni = d; d += (size_t)R * NU;
+    cs.dots = d; d += 4 * Dpad;
+    cs.dvec = d;
+    if (like_kind == LIKE_CORR) d += (size_t)npt * Dpad;
+    cs.deck = (int*)d;
+    cs.jd = cs.deck + R;
+    return cs;
+}
+
+// ------------------------------------------------------------------------------------------
+// Model: prior + likelihood as seen by one lane of a point group.
+// Padding lanes (dimension index >= D) carry x = nhat = 0, lo = wid = mu = isig = 0, so they sit inside
+// the cube and add exact zeros to the Gaussian sums: the hot path needs no validity predicates.
+// ------------------------------------------------------------------------------------------
+template <int G, int DPL>
+struct Model {
+    static constexpr int NPT = 32 / G;
+    static constexpr unsigned GMASK = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+    double mu[DPL], isig[DPL], lo[DPL], wid[DPL];
+    int D, P, kind, lane, grp, sub, Dpad;
+    double logzero, gauss_norm, Vn, log_rast, corr_const;
+    const double* s_mu;    // shared memory: mu[D] (Gaussian kinds)
+    const double* invcov;  // shared memory, D x D column-major (corr only)
+    double* dvec;          // this group's D-vector scratch (corr only)
+
+    __device__ __forceinline__ int dim(int k) const { return sub + k * G; }
+    __device__ __forceinline__ bool valid(int k) const { return sub + k * G < D; }
+
+    __device__ void init(const ChainParams& p, const double* s_like, const double* prior_params, double* warp_dvec) {
+        D = p.D; P = p.P; kind = p.like_kind; lane = threadIdx.x & 31; grp = lane / G; sub = lane % G;
+        Dpad = (D + 1) & ~1;
+        logzero = p.logzero; gauss_norm = p.gauss_norm; Vn = p.Vn; log_rast = p.log_rast; corr_const = p.corr_const;
+        s_mu = s_like;
+        invcov = s_like + D;
+        dvec = warp_dvec + (size_t)grp * Dpad;
+#pragma unroll
+        for (int k = 0; k < DPL; ++k) {
+            const int r = dim(k);
+            const bool v = r < D;
+            lo[k] = v ? prior_params[r] : 0.0;
+            wid[k] = v ? prior_params[D + r] : 0.0;
+            mu[k] = 0.0; isig[k] = 0.0;
+            if (v && kind != LIKE_RASTRIGIN) mu[k] = s_like[r];
+            if (v && kind == LIKE_GAUSSIAN) isig[k] = s_like[D + r];
+        }
+    }
+
+    // sum over the G lanes of a point group; every lane of the group receives the total
+    __device__ __forceinline__ double group_sum(double v) const {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        return v;
+    }
+
+    // calculate_point (calculate.f90:6-50) for this group's trial point y: in-cube test, uniform prior
+    // (priors.f90:40-55), log-likelihood.  Warp-collective; each group gets its own result.
+    __device__ __forceinline__ double eval(const double (&y)[DPL], double (&theta)[DPL]) const {
+        double mn = y[0], mx = y[0];
+#pragma unroll
+        for (int k = 1; k < DPL; ++k) { mn = fmin(mn, y[k]); mx = fmax(mx, y[k]); }
+        const unsigned bal = __ballot_sync(FULL, mn >= 0.0 && mx <= 1.0);
+        const bool incube = ((bal >> (grp * G)) & GMASK) == GMASK;
+#pragma unroll
+        for (int k = 0; k < DPL; ++k) theta[k] = fma(wid[k], y[k], lo[k]);
+        double logL;
+        if (kind == LIKE_GAUSSIAN) {  // likelihoods/examples/gaussian.f90:12-41
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < DPL; ++k) {
+                const double z = (theta[k] - mu[k]) * isig[k];
+                if (k & 1) a1 = fma(z, z, a1); else a0 = fma(z, z, a0);
+            }
+            logL = -gauss_norm - group_sum(a0 + a1) / 2.0;
+        } else if (kind == LIKE_RASTRIGIN) {  // likelihoods/examples/rastrigin.f90:20-35
+            const double TwoPi = 6.283185307179586476925286766559;
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < DPL; ++k)
+                acc += valid(k) ? log_rast + theta[k] * theta[k] - 10.0 * cos(TwoPi * theta[k]) : 0.0;
+            logL = -group_sum(acc);
+        } else {  // utils.F90:1028-1048 log_gauss with a dense inverse covariance
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < DPL; ++k)
+                if (valid(k)) dvec[dim(k)] = theta[k] - mu[k];
+            __syncwarp();
+            double yk[DPL];
+#pragma unroll
+            for (int k = 0; k < DPL; ++k) yk[k] = 0.0;
+            for (int c = 0; c < D; ++c) {
+                const double dc = dvec[c];
+                const double* col = invcov + (size_t)c * D;
+#pragma unroll
+                for (int k = 0; k < DPL; ++k)
+                    if (valid(k)) yk[k] += col[dim(k)] * dc;
+            }
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < DPL; ++k) acc += valid(k) ? (theta[k] - mu[k]) * yk[k] : 0.0;
+            logL = corr_const - group_sum(acc) / 2.0;
+        }
+        if (!incube) {  // calculate.f90:36-39: theta = 0, logL = logzero, the likelihood is not called
+#pragma unroll
+            for (int k = 0; k < DPL; ++k) theta[k] = 0.0;
+            logL = logzero;
+        }
+        return logL;
+    }
+
+    // Record [cube | theta | phi | birth | logL] (settings.f90:163-182), written by point group `g`.
+    // The derived parameters phi are filled in afterwards by finish_derived.
+    __device__ __forceinline__ void write_record(double* rec, int g, const double (&y)[DPL], const double (&theta)[DPL],
+                                                 double birth, double logL) const {
+        if (grp == g) {
+#pragma unroll
+            for (int k = 0; k < DPL; ++k)
+                if (valid(k)) {
+                    rec[dim(k)] = y[k];
+                    rec[D + dim(k)] = theta[k];
+                }
+            if (sub == 0) {
+                rec[2 * D + P] = birth;
+                rec[2 * D + P + 1] = logL;
+            }
+        }
+    }
+
+    // Derived parameters of a finished record, one lane per record.  gaussian.f90:37-40:
+    // phi1 = |theta-mu|, phi2 = log(phi1^D * Vn(D)); other likelihoods have none (zeros).  Points outside the
+    // cube never reach the likelihood (calculate.f90:36-39): zeros (check_cube is set where such records occur).
+    __device__ __forceinline__ void finish_derived(double* rec, bool check_cube) const {
+        if (P <= 0) return;
+        bool gauss = (kind == LIKE_GAUSSIAN);
+        if (gauss && check_cube)
+            for (int d = 0; d < D; ++d) {
+                const double c = __ldcg(rec + d);
+                if (!(c >= 0.0 && c <= 1.0)) gauss = false;
+            }
+        double r = 0.0;
+        if (gauss) {
+            double r2 = 0.0;
+            for (int d = 0; d < D; ++d) {
+                const double dl = __ldcg(rec + D + d) - s_mu[d];
+                r2 += dl * dl;
+            }
+            r = sqrt(r2);
+        }
+        rec[2 * D] = r;
+        if (P >= 2) rec[2 * D + 1] = gauss ? log(pow(r, (double)D) * Vn) : 0.0;
+        for (int i = 2; i < P; ++i) rec[2 * D + i] = 0.0;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// prep_chain: everything of a chain that depends only on (seed, uid).
+//   nh   <- ceil(R/D) Haar-random orthonormal bases (Gram-Schmidt on Gaussian vectors,
+//           random_utils.F90:381-437), column c at nh + c*LD
+//   deck <- Fisher-Yates shuffle of columns 1..R-1 (chordal_sampling.f90:133-136, random_utils.F90:505-532)
+//   uni  <- slice uniforms: uni[i*NU + 0] = u0 of slice i, uni[i*NU + 1 + s] = shrink draw s
+// ------------------------------------------------------------------------------------------
+__device__ inline void prep_chain(int D, int R, int LD, unsigned seed, unsigned long long uid, const ChainScratch& cs) {
+    const int lane = threadIdx.x & 31;
+    double* nh = cs.nh;
+    // (a) Gaussian deviates, two per Philox block (inv_normal_cdf = AS241, utils.F90:777-966)
+    const int H = (D + 1) >> 1;
+    for (int e = lane; e < R * H; e += 32) {
+        const int col = e / H, hp = e - col * H;
+        double u0, u1;
+        uniform2(seed, TAG_DIR, uid, (unsigned)col, (unsigned)hp, u0, u1);
+        double* vp = nh + (size_t)col * LD + 2 * hp;
+        vp[0] = inv_normal_cdf(u0);
+        if (2 * hp + 1 < D) vp[1] = inv_normal_cdf(u1);
+    }
+    // (c) shuffle picks and (d) slice uniforms are independent of (a)/(b): issue them here so their
+    //     integer work overlaps the FP64 work above
+    for (int i = lane; i < R; i += 32) {
+        int j = 0;
+        if (i >= 1) {
+            const double u = uniform(seed, TAG_SHUF, uid, (unsigned)i, 0u);
+            j = (int)ceil(u * (double)i);
+            if (j < 1) j = 1;
+        }
+        cs.jd[i] = j;
+    }
+    for (int e = lane; e < R * NU; e += 32) {
+        const int i = e / NU, s = e - i * NU;
+        cs.uni[e] = uniform(seed, TAG_SLICE, uid, (unsigned)i, (unsigned)s);
+    }
+    __syncwarp();
+    // (b) Gram-Schmidt, B bases at a time on LB = 32/B lanes each.  Classical form: all projections of
+    //     vector i on q_0..q_{i-1} are taken from the raw vector, then subtracted together.
+    const int nb = (R + D - 1) / D;
+    const int B = nb >= 4 ? 4 : (nb >= 2 ? 2 : 1);
+    const int LB = 32 / B;
+    const int sl = lane % LB, bslot = lane / LB;
+    const int Dpad = (D + 1) & ~1;
+    double* dots = cs.dots + (size_t)bslot * Dpad;
+    for (int b0 = 0; b0 < nb; b0 += B) {
+        const int basis = b0 + bslot;
+        const int col0 = basis * D;
+        const int m = (basis < nb) ? min(D, R - col0) : 0;    // vectors of my basis that are used
+        const int mmax = min(D, R - b0 * D);                  // trip count of the round (first basis is the longest)
+        for (int i = 0; i < mmax; ++i) {
+            const bool act = i < m;
+            double* vp = nh + (size_t)(col0 + i) * LD;
+            if (act) {
+                for (int jj = sl; jj < i; jj += LB) {
+                    const double* q = nh + (size_t)(col0 + jj) * LD;
+                    double d0 = 0.0, d1 = 0.0;
+                    int r = 0;
+                    for (; r + 1 < D; r += 2) { d0 += vp[r] * q[r]; d1 += vp[r + 1] * q[r + 1]; }
+                    if (r < D) d0 += vp[r] * q[r];
+                    dots[jj] = d0 + d1;
+                }
+            }
+            __syncwarp();
+            double acc = 0.0;
+            if (act) {
+                for (int r = sl; r < D; r += LB) {
+                    double t0 = vp[r], t1 = 0.0;
+                    int jj = 0;
+                    for (; jj + 1 < i; jj += 2) {
+                        t0 -= dots[jj] * nh[(size_t)(col0 + jj) * LD + r];
+                        t1 -= dots[jj + 1] * nh[(size_t)(col0 + jj + 1) * LD + r];
+                    }
+                    if (jj < i) t0 -= dots[jj] * nh[(size_t)(col0 + jj) * LD + r];
+                    const double t = t0 + t1;
+                    vp[r] = t;
+                    acc += t * t;
+                }
+            }
+            for (int o = LB >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+            if (act) {
+                const double inv = 1.0 / sqrt(acc);
+                for (int r = sl; r < D; r += LB) vp[r] *= inv;
+            }
+            __syncwarp();
+        }
+    }
+    // (c) the shuffled deck.  The swaps run i = R-1 .. 1 (swap deck[i], deck[jd[i]]); the element that ends
+    //     at position p is found by walking the swaps backwards from p.
+    for (int p = lane; p < R; p += 32) {
+        int pos = p;
+        for (int i = 1; i < R; ++i) {
+            const int j = cs.jd[i];
+            pos = (pos == i) ? j : ((pos == j) ? i : pos);
+        }
+        cs.deck[p] = pos;
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// whiten_chain: nhats = matmul(cholesky, nhats) (chordal_sampling.f90:73), w = 3*|nhat|, nhat /= |nhat|
+// (:80-82) for all R columns, in place.  chol: D x D column-major LOWER-triangular factor.
+// ------------------------------------------------------------------------------------------
+__device__ inline void whiten_chain(int D, int R, int LD, const double* chol, const ChainScratch& cs) {
+    const int lane = threadIdx.x & 31;
+    double* nh = cs.nh;
+    const int total = R * D;
+    for (int e0 = 0; e0 < total; e0 += 32) {
+        const int e = e0 + lane;
+        double s0 = 0.0, s1 = 0.0;
+        int col = 0, r = 0;
+        if (e < total) {
+            col = e / D;
+            r = D - 1 - (e - col * D);  // rows descend so that an in-place write never precedes a read
+            const double* q = nh + (size_t)col * LD;
+            int k = 0;
+            for (; k + 1 <= r; k += 2) {
+                s0 += chol[r + (size_t)k * D] * q[k];
+                s1 += chol[r + (size_t)(k + 1) * D] * q[k + 1];
+            }
+            if (k <= r) s0 += chol[r + (size_t)k * D] * q[k];
+        }
+        __syncwarp();
+        if (e < total) nh[(size_t)col * LD + r] = s0 + s1;
+        __syncwarp();
+    }
+    for (int col = lane; col < R; col += 32) {
+        const double* q = nh + (size_t)col * LD;
+        double s = 0.0;
+        for (int r = 0; r < D; ++r) s += q[r] * q[r];
+        const double w0 = sqrt(s);
+        cs.wts[col] = w0;
+    }
+    __syncwarp();
+    for (int e = lane; e < total; e += 32) {
+        const int col = e / D, r = e - col * D;
+        nh[(size_t)col * LD + r] /= cs.wts[col];
+    }
+    __syncwarp();
+    for (int col = lane; col < R; col += 32) cs.wts[col] *= 3.0;
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// slice_chain: R slice steps from x (chordal_sampling.f90:75-90 calling slice_sample :163-273).
+// Babies 0..R-2 go to ph_base + i*T, the last one to last_dst.  Returns the final logL.
+//
+// A slice step is two speculative rounds in the common case:
+//   bracket round   the NPT point groups evaluate the right end R0 and the step-out multiples w, 2w, ...
+//                   (groups 0..NS-1) and the left end L0 and -w, -2w, ... (groups NS..2NS-1) at once; the
+//                   first point of each side that is outside the contour closes the bracket (:213-236)
+//   shrink round    groups 0..NC-1 evaluate the next NC shrink draws, each placed under the hypothesis that
+//                   the earlier ones were rejected (a rejected draw becomes the bound on its side, :254-262,
+//                   so the positions do not depend on the likelihoods); the first accepted one is the baby
+// nlike counts exactly the evaluations the sequential algorithm makes (calculate.f90:44).
+// ------------------------------------------------------------------------------------------
+template <int G, int DPL>
+__device__ inline double slice_chain(const ChainParams& p, const Model<G, DPL>& M, unsigned seed, unsigned long long uid,
+                                     double (&x)[DPL], double Lstar, const ChainScratch& cs, double* ph_base,
+                                     double* last_dst, unsigned long long& nlike) {
+    constexpr int NPT = 32 / G;
+    constexpr int LOG2G = (G == 1) ? 0 : (G == 2) ? 1 : (G == 4) ? 2 : (G == 8) ? 3 : (G == 16) ? 4 : 5;
+    constexpr int NS = NPT / 2;                 // bracket points per side and round
+    constexpr int SIDE = 16;                    // ballot bits per side (NS * G)
+    constexpr int NC = NPT < 4 ? NPT : 4;       // shrink candidates per round
+    const int R = p.R, LD = p.LD, T = p.T;
+    const int lane = threadIdx.x & 31, grp = lane >> LOG2G;
+    const int myc = grp < NC ? grp : NC - 1;    // shrink candidate evaluated by this group
+    const double logzero = p.logzero;
+    double logL_cur = logzero;
+
+    // ballot bits of groups 0..g-1 (the G lanes of a group always vote alike)
+    auto lanes_below = [](int g) -> unsigned {
+        const int nb = g << LOG2G;
+        return nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
+    };
+
+    for (int i = 0; i < R; ++i) {
+        const int c = cs.deck[i];
+        const double* q = cs.nh + (size_t)c * LD;
+        double nh[DPL];
+#pragma unroll
+        for (int k = 0; k < DPL; ++k) nh[k] = M.valid(k) ? q[M.dim(k)] : 0.0;
+        const double w = cs.wts[c];
+        const double* ui = cs.uni + (size_t)i * NU;
+        const double u0 = ui[0];
+        double dL = u0 * w, dR = (1.0 - u0) * w;  // bracket [x - dL*nhat, x + dR*nhat] (:213-215)
+
+        double y[DPL], th[DPL], l;
+        auto eval_t = [&](double tt) -> double {  // this group's point x + tt*nhat
+#pragma unroll
+            for (int k = 0; k < DPL; ++k) y[k] = fma(tt, nh[k], x[k]);
+            return M.eval(y, th);
+        };
+
+        // ---------------- bracket (:213-236) ----------------
+        if (NPT >= 2) {
+            const int side = grp / NS, idx = grp - side * NS;
+            {
+                const double mult = (idx == 0) ? (side ? dL : dR) : w * (double)idx;
+                l = eval_t(side ? -mult : mult);
+            }
+            const unsigned in_raw = __ballot_sync(FULL, l >= Lstar && l > logzero);
+            const unsigned cnt_raw = __ballot_sync(FULL, l > logzero);
+            const unsigned smask = (NS * G >= 32) ? 0xffffffffu : ((1u << (NS * G)) - 1u);
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd) {
+                const unsigned inb = (in_raw >> (sd * SIDE)) & smask, cnb = (cnt_raw >> (sd * SIDE)) & smask;
+                const unsigned out = ~inb & smask;
+                if (out) {  // the first point outside the contour closes this side
+                    const int g = (__ffs(out) - 1) >> LOG2G;
+                    nlike += __popc(cnb & lanes_below(g + 1)) >> LOG2G;
+                    if (g > 0) { if (sd) dL = w * (double)g; else dR = w * (double)g; }
+                } else {    // all NS points inside: keep stepping this side, NPT multiples at a time (:223-227)
+                    nlike += NS;
+                    for (int base = NS;; base += NPT) {
+                        const double mult = w * (double)(base + grp);
+                        l = eval_t(sd ? -mult : mult);
+                        const unsigned ib = __ballot_sync(FULL, l >= Lstar && l > logzero);
+                        const unsigned cb = __ballot_sync(FULL, l > logzero);
+                        if (~ib) {
+                            const int g = (__ffs(~ib) - 1) >> LOG2G;
+                            nlike += __popc(cb & lanes_below(g + 1)) >> LOG2G;
+                            if (sd) dL = w * (double)(base + g); else dR = w * (double)(base + g);
+                            break;
+                        }
+                        nlike += NPT;
+                    }
+                }
+            }
+        } else {  // a single point group: the sequential form
+            double lR = eval_t(dR);
+            if (lR > logzero) ++nlike;
+            double lL = eval_t(-dL);
+            if (lL > logzero) ++nlike;
+            for (int is = 1; lR >= Lstar && lR > logzero; ++is) {
+                dR = w * (double)is;
+                lR = eval_t(dR);
+                if (lR > logzero) ++nlike;
+            }
+            for (int is = 1; lL >= Lstar && lL > logzero; ++is) {
+                dL = w * (double)is;
+                lL = eval_t(-dL);
+                if (lL > logzero) ++nlike;
+            }
+        }
+        // ---------------- shrink (:240-266) ----------------
+        // bounds as signed positions a < 0 < b and their distance wd = dR + dL, exactly the quantities of
+        // baby = x0 + (u*(x0Rd + x0Ld) - x0Ld)*nhat (:247)
+        double a = -dL, b = dR, wd = dR + dL;
+        double t_acc = 0.0, l_acc = logzero;
+        int g_acc = 0, s_done = 0;
+        bool accepted = false;
+        while (!accepted && s_done < 101) {
+            double tmine = 0.0;
+#pragma unroll
+            for (int cnd = 0; cnd < NC; ++cnd) {
+                const int sidx = 1 + s_done + cnd;
+                const double u = (sidx < NU) ? ui[sidx] : uniform(seed, TAG_SLICE, uid, (unsigned)i, (unsigned)sidx);
+                const double tc = fma(u, wd, a);
+                if (cnd == myc) tmine = tc;
+                const bool pos = tc > 0.0;  // sign of (baby - x0).nhat picks the bound to move (:254)
+                wd = pos ? tc - a : b - tc;
+                a = pos ? a : tc;
+                b = pos ? tc : b;
+            }
+            l = eval_t(tmine);
+            const unsigned in_raw = __ballot_sync(FULL, l >= Lstar && l > logzero);
+            const unsigned cnt_raw = __ballot_sync(FULL, l > logzero);
+            const int ncand = min(NC, 101 - s_done);  // at most 101 draws per slice (:240)
+            const unsigned cmask = lanes_below(ncand);
+            const unsigned hit = in_raw & cmask;
+            if (hit) {
+                g_acc = (__ffs(hit) - 1) >> LOG2G;
+                nlike += __popc(cnt_raw & lanes_below(g_acc + 1)) >> LOG2G;
+                l_acc = __shfl_sync(FULL, l, g_acc << LOG2G);
+                accepted = true;
+            } else {
+                nlike += __popc(cnt_raw & cmask) >> LOG2G;
+                g_acc = ncand - 1;  // the last draw: kept if the slice gives up (:268-271)
+                s_done += ncand;
+            }
+            t_acc = __shfl_sync(FULL, tmine, g_acc << LOG2G);
+        }
+        // "Non deterministic loglikelihood" (:268-271): after 101 rejected draws the last trial point is kept
+        // with logL = logzero.
+        const double lnew = accepted ? l_acc : logzero;
+        // The accepting group's registers hold the baby (cube, theta): it writes the record.  Every group
+        // moves to the same point with the same fma, so the chain state stays replicated bit for bit.
+        double* dst = (i == R - 1) ? last_dst : ph_base + (size_t)i * T;
+        M.write_record(dst, g_acc, y, th, Lstar, lnew);
+#pragma unroll
+        for (int k = 0; k < DPL; ++k) x[k] = fma(t_acc, nh[k], x[k]);  // next start = this baby even if it failed (:88)
+        logL_cur = lnew;
+    }
+    __syncwarp();
+    // derived parameters of the R babies, one lane per record
+    if (p.P > 0) {
+        for (int i = lane; i < R; i += 32) M.finish_derived((i == R - 1) ? last_dst : ph_base + (size_t)i * T, false);
+        __syncwarp();
+    }
+    return logL_cur;
+}
+
+}  // namespace pc

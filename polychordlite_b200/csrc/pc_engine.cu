@@ -18,7 +18,8 @@
 #include <vector>
 
 #include "../../include/polychord_b200.h"
-#include "pc_run_kernel.cuh"
+#include "pc_probes.cuh"
+#include "pc_shapes.h"
 
 namespace pc {
 
@@ -125,7 +126,7 @@ static void build_dev_model(const pc_settings& s, const ModelSpec& ms, DevModel&
 struct Layout {
     KParams kp;
     size_t smem = 0;
-    int npl = 1;
+    ShapeFns fn;
     int W = 8;
 };
 
@@ -138,7 +139,28 @@ static int device_check() {
     return n;
 }
 
+// (G, DPL): G lanes share one trial point, DPL dimensions per lane; G*DPL >= nDims
+static ShapeFns pick_shape(int D) {
+    if (D <= 8) return shape_fns_4_2();
+    if (D <= 16) return shape_fns_4_4();
+    if (D <= 20) return shape_fns_4_5();
+    if (D <= 32) return shape_fns_4_8();
+    if (D <= 64) return shape_fns_8_8();
+    return shape_fns_16_8();
+}
+
+static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const DevModel& dm, int W);
+
+// the largest warp count per CTA (<= the requested one) whose scratch fits in shared memory
 static Layout make_layout(const pc_settings& s, const ModelSpec& ms, const DevModel& dm, int W) {
+    for (;; --W) {
+        Layout L = make_layout_w(s, ms, dm, W);
+        if (L.smem <= 227 * 1024) return L;
+        if (W == 1) throw std::invalid_argument("polychord_b200: the run does not fit in shared memory (nlive too large for the in-kernel sort, or nDims*nDims too large)");
+    }
+}
+
+static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const DevModel& dm, int W) {
     Layout L;
     KParams& k = L.kp;
     std::memset(&k, 0, sizeof(k));
@@ -146,22 +168,24 @@ static Layout make_layout(const pc_settings& s, const ModelSpec& ms, const DevMo
     if (D < 1 || D > 128) throw std::invalid_argument("polychord_b200: nDims must be in 1..128");
     if (R < 1) throw std::invalid_argument("polychord_b200: num_repeats must be >= 1");  // settings.f90:216
     if (s.nlive < 2) throw std::invalid_argument("polychord_b200: nlive must be >= 2");
-    k.D = D; k.P = P; k.T = 2 * D + P + 2; k.R = R; k.n = s.nlive;
-    k.LD = D | 1;
-    k.like_kind = ms.like_kind;
+    L.fn = pick_shape(D);
+    const int npt = 32 / L.fn.G;
+    k.cp.D = D; k.cp.P = P; k.cp.T = 2 * D + P + 2; k.cp.R = R;
+    k.cp.LD = D | 1;
+    k.cp.like_kind = ms.like_kind;
+    k.cp.logzero = s.logzero;
+    k.cp.gauss_norm = dm.gauss_norm; k.cp.Vn = dm.Vn; k.cp.log_rast = dm.log_rast; k.cp.corr_const = dm.corr_const;
+    k.n = s.nlive;
     k.use_prec = s.precision_criterion > 0.0;
     k.max_ndead = s.max_ndead;
-    k.logzero = s.logzero;
     k.log_prec = k.use_prec ? std::log(s.precision_criterion) : 0.0;
     k.log_comp = std::log(s.compression_factor);
-    k.gauss_norm = dm.gauss_norm; k.Vn = dm.Vn; k.log_rast = dm.log_rast; k.corr_const = dm.corr_const;
     k.like_params = dm.like.p;
     k.prior_params = dm.prior.p;
     k.warps_per_cta = W;
     k.ntri = D * (D + 1) / 2;
     k.cov_passes = (k.ntri + COV_ACC * 32 - 1) / (COV_ACC * 32);
     k.partial_stride = 1 + D + k.cov_passes * COV_ACC * 32;
-    L.npl = (D + 31) / 32;
     L.W = W;
     const int nlp = ms.like_kind == PC_LIKE_GAUSSIAN ? 2 * D : (ms.like_kind == PC_LIKE_CORR_GAUSSIAN ? D + D * D : 0);
     const int Dpad = (D + 1) & ~1;
@@ -170,44 +194,25 @@ static Layout make_layout(const pc_settings& s, const ModelSpec& ms, const DevMo
     off += (size_t)((nlp + 1) & ~1) * 8;
     off += 64 * sizeof(int);  // s_cnt
     k.off_warp = (int)off;
-    size_t base_warp = (size_t)(2 * Dpad + ((R + 1) & ~1)) * 8;
-    size_t nh_bytes = (size_t)R * k.LD * 8;
-    size_t cov_bytes = (size_t)(Dpad + COV_ACC * 32) * 8;
+    const size_t cov_bytes = (size_t)(2 * Dpad + COV_ACC * 32) * 8;
     int np2 = 1;
     while (np2 < s.nlive) np2 <<= 1;
-    size_t sort_bytes = 64 * 8 + (size_t)np2 * 12;
+    const size_t sort_bytes = 64 * 8 + (size_t)np2 * 12;
     const size_t budget = 200 * 1024;
-    bool in_smem = !g_opt.nh_global && (off + (size_t)W * std::max(base_warp + nh_bytes, cov_bytes) <= budget);
+    const size_t with_nh = chain_scratch_bytes(D, R, k.cp.LD, true, ms.like_kind, npt);
+    const bool in_smem = !g_opt.nh_global && (off + (size_t)W * std::max(with_nh, cov_bytes) <= budget);
     k.nh_in_smem = in_smem ? 1 : 0;
-    size_t wb = std::max(base_warp + (in_smem ? nh_bytes : 0), cov_bytes);
+    size_t wb = std::max(chain_scratch_bytes(D, R, k.cp.LD, in_smem, ms.like_kind, npt), cov_bytes);
     wb = (wb + 15) & ~(size_t)15;
     k.warp_bytes = (int)wb;
     L.smem = off + std::max((size_t)W * wb, sort_bytes);
-    if (L.smem > 227 * 1024) throw std::invalid_argument("polychord_b200: nlive too large for the shared-memory sort");
     return L;
 }
 
-template <int NPL>
-static void set_smem_attr(size_t smem) {
-    PC_CUDA(cudaFuncSetAttribute(pc_run_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PC_CUDA(cudaFuncSetAttribute(pc_slice_chains_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PC_CUDA(cudaFuncSetAttribute(pc_calculate_points_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-}
-static void set_smem(int npl, size_t smem) {
-    switch (npl) {
-        case 1: set_smem_attr<1>(smem); break;
-        case 2: set_smem_attr<2>(smem); break;
-        case 3: set_smem_attr<3>(smem); break;
-        default: set_smem_attr<4>(smem); break;
-    }
-}
-static const void* run_kernel_ptr(int npl) {
-    switch (npl) {
-        case 1: return (const void*)pc_run_kernel<1>;
-        case 2: return (const void*)pc_run_kernel<2>;
-        case 3: return (const void*)pc_run_kernel<3>;
-        default: return (const void*)pc_run_kernel<4>;
-    }
+static void set_smem(const ShapeFns& fn, size_t smem) {
+    PC_CUDA(cudaFuncSetAttribute(fn.run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PC_CUDA(cudaFuncSetAttribute(fn.slice, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PC_CUDA(cudaFuncSetAttribute(fn.calc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -254,7 +259,8 @@ struct Engine {
         build_dev_model(S, ms, dm, stream);
         int W = std::max(1, std::min(8, g_opt.warps_per_cta));
         L = make_layout(S, ms, dm, W);
-        set_smem(L.npl, L.smem);
+        W = L.W;
+        set_smem(L.fn, L.smem);
         KParams& k = L.kp;
         int K = g_opt.batch_K > 0 ? g_opt.batch_K : (int)std::lround(S.nlive * g_opt.batch_fraction);
         K = std::max(1, std::min(K, S.nlive - 1));
@@ -263,18 +269,21 @@ struct Engine {
         int dev = 0, sms = 0, per_sm = 0;
         PC_CUDA(cudaGetDevice(&dev));
         PC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        PC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&per_sm, run_kernel_ptr(L.npl), W * 32, L.smem, 0));
+        PC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&per_sm, L.fn.run, W * 32, L.smem, 0));
         if (per_sm < 1) throw std::runtime_error("polychord_b200: run kernel does not fit on an SM");
         long long capacity = (long long)sms * per_sm;
-        G = (K + W - 1) / W;
+        // A run alone on the device spreads its chains one per CTA (a chain warp then has an SM sub-partition
+        // to itself) and leaves CTA 0 to the bookkeeping; an ensemble packs W chains per CTA.
+        G = K + 1;
         if (g_opt.max_ctas > 0) G = std::min(G, g_opt.max_ctas);
         G = (int)std::max(1LL, std::min<long long>(G, capacity / nruns));
         if ((long long)G * nruns > capacity) throw std::invalid_argument("polychord_b200: too many concurrent runs for one launch");
         k.ctas_per_run = G;
+        k.chain_cta0 = (G >= 8) ? 1 : 0;
         PC_CUDA(cudaEventCreate(&ev0));
         PC_CUDA(cudaEventCreate(&ev1));
 
-        const int T = k.T, D = k.D, R = k.R, n = k.n;
+        const int T = k.cp.T, D = k.cp.D, R = k.cp.R, n = k.n;
         runs.resize(nruns);
         std::vector<RunBuf> hb(nruns);
         for (int r = 0; r < nruns; ++r) {
@@ -293,7 +302,7 @@ struct Engine {
             h.chol.alloc((size_t)D * D); h.cov.alloc((size_t)D * D);
             h.partial.alloc((size_t)G * k.partial_stride);
             h.pcount.alloc(G); h.pcount.zero(stream);
-            if (!k.nh_in_smem) h.nh.alloc((size_t)G * W * R * k.LD);
+            if (!k.nh_in_smem) h.nh.alloc((size_t)G * W * R * k.cp.LD);
             RunBuf& b = h.buf;
             std::memset(&b, 0, sizeof(b));
             b.st = h.st.p; b.live = h.live.p; b.order = h.order.p; b.dead = h.dead.p; b.logw = h.logw.p;
@@ -321,7 +330,7 @@ struct Engine {
         KParams kp = L.kp;
         void* args[] = {&kp};
         PC_CUDA(cudaEventRecord(ev0, stream));
-        PC_CUDA(cudaLaunchCooperativeKernel(run_kernel_ptr(L.npl), dim3(G * nruns), dim3(L.W * 32), args, L.smem, stream));
+        PC_CUDA(cudaLaunchCooperativeKernel(L.fn.run, dim3(G * nruns), dim3(L.W * 32), args, L.smem, stream));
         PC_CUDA(cudaEventRecord(ev1, stream));
         PC_CUDA(cudaEventSynchronize(ev1));
         float ms = 0;
@@ -339,7 +348,7 @@ struct Engine {
     void dump(int r, pc_dumper_t dumper, bool final_dump) {
         HostRun& h = runs[r];
         const KParams& k = L.kp;
-        const int T = k.T, D = k.D, P = k.P, n = k.n, npars = D + P + 2;
+        const int T = k.cp.T, D = k.cp.D, P = k.cp.P, n = k.n, npars = D + P + 2;
         const long long ndead = h.host_st.ndead;
         const long long fresh = ndead - h.mirrored;
         if (fresh > 0) {
@@ -397,7 +406,7 @@ struct Engine {
         const KParams& k = L.kp;
         if (status == ST_NEED_DEAD) {
             long long nc = h.buf.cap_dead * 2 + k.n + k.batch_K;
-            h.dead.grow((size_t)nc * k.T, (size_t)h.host_st.ndead * k.T, stream);
+            h.dead.grow((size_t)nc * k.cp.T, (size_t)h.host_st.ndead * k.cp.T, stream);
             h.logw.grow(nc, h.host_st.ndead, stream);
             h.buf.dead = h.dead.p; h.buf.logw = h.logw.p; h.buf.cap_dead = nc;
         } else {
@@ -405,8 +414,8 @@ struct Engine {
             int cur = h.host_st.cur_pool;
             DevArr<double>& a = cur == 0 ? h.ph0 : h.ph1;
             DevArr<double>& b = cur == 0 ? h.ph1 : h.ph0;
-            a.grow((size_t)nc * k.T, (size_t)h.host_st.nphantom * k.T, stream);
-            b.alloc((size_t)nc * k.T);
+            a.grow((size_t)nc * k.cp.T, (size_t)h.host_st.nphantom * k.cp.T, stream);
+            b.alloc((size_t)nc * k.cp.T);
             h.buf.ph[0] = h.ph0.p; h.buf.ph[1] = h.ph1.p; h.buf.cap_ph = nc;
         }
     }
@@ -446,7 +455,14 @@ struct Engine {
             o.wall_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
             o.h2d_bytes = h2d; o.d2h_bytes = d2h;
             // 8T+8D per slice step, 8T per chain (seed read) + 8T (dead record), 8D^2 per generation
-            o.algorithmic_bytes = s.nslices * (8LL * k.T + 8LL * k.D) + s.nchains * 16LL * k.T + s.ngen * 8LL * k.D * k.D;
+            {
+                int khz = 0, dev = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+                const long long cyc[8] = {s.cyc_wait, s.cyc_S, s.cyc_fin, s.cyc_U, s.cyc_prep, s.cyc_white, s.cyc_slice, s.cyc_total};
+                for (int i = 0; i < 8; ++i) o.phase_ms[i] = khz > 0 ? (double)cyc[i] / (double)khz : 0.0;
+            }
+            o.algorithmic_bytes = s.nslices * (8LL * k.cp.T + 8LL * k.cp.D) + s.nchains * 16LL * k.cp.T + s.ngen * 8LL * k.cp.D * k.cp.D;
         }
     }
 };
@@ -638,7 +654,7 @@ static void probe_setup(ProbeCtx& c, const pc_settings* s, int like_kind, const 
     if (pp) c.ms.prior_params.assign(pp, pp + npp);
     build_dev_model(*s, c.ms, c.dm, g_stream);
     c.L = make_layout(*s, c.ms, c.dm, std::max(1, std::min(8, g_opt.warps_per_cta)));
-    set_smem(c.L.npl, c.L.smem);
+    set_smem(c.L.fn, c.L.smem);
 }
 
 int pc_slice_chains(const pc_settings* s, int like_kind, const double* like_params, int n_like_params,
@@ -650,27 +666,29 @@ int pc_slice_chains(const pc_settings* s, int like_kind, const double* like_para
         probe_setup(c, s, like_kind, like_params, n_like_params, prior_params, n_prior_params);
         const KParams& k = c.L.kp;
         cudaStream_t st = g_stream;
-        DevArr<double> d_seed((size_t)nchains * k.T), d_chol((size_t)k.D * k.D), d_logL(nchains),
-            d_babies((size_t)nchains * k.R * k.T), d_nh;
+        const int T = k.cp.T, D = k.cp.D, R = k.cp.R;
+        DevArr<double> d_seed((size_t)nchains * T), d_chol((size_t)D * D), d_logL(nchains),
+            d_babies((size_t)nchains * R * T), d_nh;
         DevArr<unsigned long long> d_uid(nchains);
         DevArr<long long> d_nlike(nchains);
-        d_seed.upload(seed_points, (size_t)nchains * k.T, st);
-        d_chol.upload(cholesky, (size_t)k.D * k.D, st);
+        d_seed.upload(seed_points, (size_t)nchains * T, st);
+        d_chol.upload(cholesky, (size_t)D * D, st);
         d_logL.upload(logL, nchains, st);
         d_uid.upload(uid, nchains, st);
         d_babies.zero(st);
         int W = c.L.W;
         int blocks = std::min(1024, (nchains + W - 1) / W);
-        if (!k.nh_in_smem) d_nh.alloc((size_t)blocks * W * k.R * k.LD);
+        if (!k.nh_in_smem) d_nh.alloc((size_t)blocks * W * R * k.cp.LD);
         KParams kp = k;
         unsigned seed = (unsigned)s->seed;
-#define LAUNCH_SC(N)                                                                                                 \
-    pc_slice_chains_kernel<N><<<blocks, W * 32, c.L.smem, st>>>(kp, nchains, d_seed.p, d_chol.p, d_logL.p, d_uid.p, \
-                                                                 seed, d_babies.p, d_nlike.p, d_nh.p)
-        switch (c.L.npl) { case 1: LAUNCH_SC(1); break; case 2: LAUNCH_SC(2); break; case 3: LAUNCH_SC(3); break; default: LAUNCH_SC(4); }
-#undef LAUNCH_SC
+        const double *a_seed = d_seed.p, *a_chol = d_chol.p, *a_logL = d_logL.p;
+        const unsigned long long* a_uid = d_uid.p;
+        double *a_babies = d_babies.p, *a_nh = d_nh.p;
+        long long* a_nlike = d_nlike.p;
+        void* args[] = {&kp, &nchains, &a_seed, &a_chol, &a_logL, &a_uid, &seed, &a_babies, &a_nlike, &a_nh};
+        PC_CUDA(cudaLaunchKernel(c.L.fn.slice, dim3(blocks), dim3(W * 32), args, c.L.smem, st));
         PC_CUDA(cudaGetLastError());
-        d_babies.download(babies_out, (size_t)nchains * k.R * k.T, st);
+        d_babies.download(babies_out, (size_t)nchains * R * T, st);
         d_nlike.download(nlike_out, nchains, st);
         PC_CUDA(cudaStreamSynchronize(st));
         return 0;
@@ -686,19 +704,22 @@ int pc_calculate_points(const pc_settings* s, int like_kind, const double* like_
         probe_setup(c, s, like_kind, like_params, n_like_params, prior_params, n_prior_params);
         const KParams& k = c.L.kp;
         cudaStream_t st = g_stream;
-        DevArr<double> d_rec((size_t)npts * k.T);
+        const int T = k.cp.T;
+        DevArr<double> d_rec((size_t)npts * T);
         DevArr<int> d_n(1);
-        d_rec.upload(records, (size_t)npts * k.T, st);
+        d_rec.upload(records, (size_t)npts * T, st);
         d_n.zero(st);
         int W = c.L.W;
-        int blocks = std::max(1, std::min(1024, (npts + W - 1) / W));
+        const int npt = 32 / c.L.fn.G;
+        int blocks = std::max(1, std::min(1024, (npts + W * npt - 1) / (W * npt)));
         KParams kp = k;
-#define LAUNCH_CP(N) pc_calculate_points_kernel<N><<<blocks, W * 32, c.L.smem, st>>>(kp, d_rec.p, npts, d_n.p)
-        switch (c.L.npl) { case 1: LAUNCH_CP(1); break; case 2: LAUNCH_CP(2); break; case 3: LAUNCH_CP(3); break; default: LAUNCH_CP(4); }
-#undef LAUNCH_CP
+        double* a_rec = d_rec.p;
+        int* a_n = d_n.p;
+        void* args[] = {&kp, &a_rec, &npts, &a_n};
+        PC_CUDA(cudaLaunchKernel(c.L.fn.calc, dim3(blocks), dim3(W * 32), args, c.L.smem, st));
         PC_CUDA(cudaGetLastError());
         int n = 0;
-        d_rec.download(records, (size_t)npts * k.T, st);
+        d_rec.download(records, (size_t)npts * T, st);
         d_n.download(&n, 1, st);
         PC_CUDA(cudaStreamSynchronize(st));
         return n;
@@ -713,14 +734,9 @@ int pc_device_directions(int nDims, int num_repeats, unsigned seed, unsigned lon
         const int D = nDims, R = num_repeats, LD = D | 1;
         cudaStream_t st = g_stream;
         DevArr<double> d_nh((size_t)R * LD), d_out((size_t)R * D);
-        size_t smem = (size_t)(((D + 1) & ~1) + R + 2) * 8;
-        int npl = (D + 31) / 32;
-        switch (npl) {
-            case 1: pc_directions_kernel<1><<<1, 32, smem, st>>>(D, R, LD, seed, uid, d_nh.p, d_out.p); break;
-            case 2: pc_directions_kernel<2><<<1, 32, smem, st>>>(D, R, LD, seed, uid, d_nh.p, d_out.p); break;
-            case 3: pc_directions_kernel<3><<<1, 32, smem, st>>>(D, R, LD, seed, uid, d_nh.p, d_out.p); break;
-            default: pc_directions_kernel<4><<<1, 32, smem, st>>>(D, R, LD, seed, uid, d_nh.p, d_out.p); break;
-        }
+        size_t smem = chain_scratch_bytes(D, R, LD, false, LIKE_GAUSSIAN, 1);
+        PC_CUDA(cudaFuncSetAttribute(pc_directions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        pc_directions_kernel<<<1, 32, smem, st>>>(D, R, LD, seed, uid, d_nh.p, d_out.p);
         PC_CUDA(cudaGetLastError());
         d_out.download(out, (size_t)R * D, st);
         PC_CUDA(cudaStreamSynchronize(st));

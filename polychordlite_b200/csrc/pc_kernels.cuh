@@ -21,12 +21,11 @@
 // Groups synchronise with their own global-memory barrier, so many independent runs
 // (an ensemble) advance concurrently inside one launch.
 #pragma once
-#include "pc_device.cuh"
+#include "pc_chain.cuh"
 
 namespace pc {
 
 enum Status : int { ST_RUNNING = 0, ST_DONE = 1, ST_NEED_DEAD = 2, ST_NEED_PHANTOM = 3, ST_DUMP = 4, ST_ERROR = -1 };
-enum LikeKind : int { LIKE_GAUSSIAN = 0, LIKE_RASTRIGIN = 1, LIKE_CORR = 2 };
 
 constexpr double NEG_BIG = -1e300;  // log(0) stand-in that survives additions without NaN
 constexpr int COV_ACC = 20;         // covariance accumulators per lane and pass
@@ -51,8 +50,10 @@ struct DevRun {
     int initialised;
     int init_need;
     int chol_fallback;   // number of calc_cholesky identity fallbacks
-    unsigned int bar;    // group barrier (monotonic)
-    unsigned int pad;
+    // SM-clock cycle counters of the phases (thread 0 of CTA 0; chain phases: warp 0 of the first chain CTA)
+    long long cyc_wait, cyc_S, cyc_fin, cyc_U, cyc_prep, cyc_white, cyc_slice, cyc_total;
+    unsigned int bar;    // group barrier, one arrival per CTA (monotonic)
+    unsigned int wbar;   // chains-done barrier, one arrival per warp (monotonic)
 };
 
 struct RunBuf {
@@ -73,15 +74,15 @@ struct RunBuf {
 };
 
 struct KParams {
-    int D, P, T, R, n, batch_K, LD;
-    int like_kind;
+    ChainParams cp;              // D, P, T, R, LD, likelihood constants
+    int n, batch_K;
     int use_prec, max_ndead;
     int ctas_per_run, warps_per_cta;
+    int chain_cta0;              // first CTA of a run's group that runs chains (1: CTA 0 only keeps the books)
     int nh_in_smem, want_dump;
     int ntri, cov_passes, partial_stride;
     int off_like, off_warp, warp_bytes;  // shared-memory byte offsets
-    double logzero, log_prec, log_comp;
-    double gauss_norm, Vn, log_rast, corr_const;
+    double log_prec, log_comp;
     const double* like_params;   // gaussian: mu[D], 1/sigma[D]; corr: mu[D], invcov[D*D]
     const double* prior_params;  // lo[D], hi-lo[D]
     RunBuf* runs;
@@ -99,10 +100,33 @@ __device__ __forceinline__ void group_sync(unsigned int* bar, unsigned int G) {
         unsigned int v;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-        } while (v < target);
+        } while ((int)(v - target) < 0);
         __threadfence();
     }
     __syncthreads();
+}
+
+// Per-warp split barrier: a warp arrives as soon as its own chains are written, does other work
+// (prep of its next chain), and only the warps that need everybody's results wait.
+__device__ __forceinline__ unsigned int warp_arrive(unsigned int* wbar, unsigned int GW) {
+    __syncwarp();
+    unsigned int target = 0;
+    if ((threadIdx.x & 31) == 0) {
+        __threadfence();
+        unsigned int t = atomicAdd(wbar, 1u);
+        target = (t / GW + 1u) * GW;
+    }
+    return __shfl_sync(FULL, target, 0);
+}
+__device__ __forceinline__ void warp_wait(unsigned int* wbar, unsigned int target) {
+    if ((threadIdx.x & 31) == 0) {
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(wbar) : "memory");
+        } while ((int)(v - target) < 0);
+        __threadfence();
+    }
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -242,289 +266,6 @@ __device__ inline void evidence_deaths(DevRun* st, const double* skey, int count
     }
     if (threadIdx.x == 0) { st->logX = lX; st->logXX = lXX; st->logZX = lZX; st->logZ = lZ; st->logZ2 = lZ2; }
     __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------------
-// Per-lane view of the model: lane holds dimensions lane, lane+32, ...
-// ------------------------------------------------------------------------------------------
-template <int NPL>
-struct Model {
-    double mu[NPL], isig[NPL], lo[NPL], wid[NPL];
-    bool valid[NPL];
-    int D, P, kind, lane;
-    double logzero, gauss_norm, Vn, log_rast, corr_const;
-    const double* invcov;  // shared memory, D x D column-major (corr only)
-    double* dvec;          // per-warp shared scratch, D doubles
-
-    __device__ void init(const KParams& p, const double* s_like, double* warp_dvec) {
-        D = p.D; P = p.P; kind = p.like_kind; lane = threadIdx.x & 31;
-        logzero = p.logzero; gauss_norm = p.gauss_norm; Vn = p.Vn; log_rast = p.log_rast; corr_const = p.corr_const;
-        invcov = s_like + D;
-        dvec = warp_dvec;
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) {
-            int r = lane + 32 * j;
-            valid[j] = r < D;
-            lo[j] = valid[j] ? p.prior_params[r] : 0.0;
-            wid[j] = valid[j] ? p.prior_params[D + r] : 0.0;
-            mu[j] = 0.0; isig[j] = 0.0;
-            if (valid[j] && kind != LIKE_RASTRIGIN) mu[j] = s_like[r];
-            if (valid[j] && kind == LIKE_GAUSSIAN) isig[j] = s_like[D + r];
-        }
-    }
-
-    // calculate_point (calculate.f90:6-50): in-cube test, uniform prior (priors.f90:40-55) and
-    // log-likelihood.  Warp-collective; the result is identical on every lane.
-    __device__ __forceinline__ double eval(const double (&x)[NPL], double (&theta)[NPL]) const {
-        bool ok = true;
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) ok = ok && (!valid[j] || (x[j] >= 0.0 && x[j] <= 1.0));
-        if (!__all_sync(FULL, ok)) {
-#pragma unroll
-            for (int j = 0; j < NPL; ++j) theta[j] = 0.0;
-            return logzero;
-        }
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) theta[j] = lo[j] + wid[j] * x[j];
-        if (kind == LIKE_GAUSSIAN) {  // likelihoods/examples/gaussian.f90:12-41
-#pragma unroll
-            for (int j = 0; j < NPL; ++j) {
-                double z = (theta[j] - mu[j]) * isig[j];
-                acc += valid[j] ? z * z : 0.0;
-            }
-            return -gauss_norm - warp_sum(acc) / 2.0;
-        } else if (kind == LIKE_RASTRIGIN) {  // likelihoods/examples/rastrigin.f90:20-35
-            const double TwoPi = 6.283185307179586476925286766559;
-#pragma unroll
-            for (int j = 0; j < NPL; ++j)
-                acc += valid[j] ? log_rast + theta[j] * theta[j] - 10.0 * cos(TwoPi * theta[j]) : 0.0;
-            return -warp_sum(acc);
-        } else {  // utils.F90:1028-1048 log_gauss with a dense inverse covariance
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < NPL; ++j)
-                if (valid[j]) dvec[lane + 32 * j] = theta[j] - mu[j];
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < NPL; ++j) {
-                if (valid[j]) {
-                    int r = lane + 32 * j;
-                    double y = 0.0;
-                    for (int c = 0; c < D; ++c) y += invcov[r + c * D] * dvec[c];
-                    acc += (theta[j] - mu[j]) * y;
-                }
-            }
-            return corr_const - warp_sum(acc) / 2.0;
-        }
-    }
-
-    // derived parameters of the accepted point (gaussian.f90:37-40); lane 0 writes them
-    __device__ __forceinline__ void derived(const double (&theta)[NPL], double* phi_out, bool incube) const {
-        if (P <= 0) return;
-        if (kind == LIKE_GAUSSIAN && incube) {
-            double acc = 0.0;
-#pragma unroll
-            for (int j = 0; j < NPL; ++j) acc += valid[j] ? (theta[j] - mu[j]) * (theta[j] - mu[j]) : 0.0;
-            double r = sqrt(warp_sum(acc));
-            if (lane == 0) {
-                phi_out[0] = r;
-                if (P >= 2) phi_out[1] = log(pow(r, (double)D) * Vn);
-                for (int i = 2; i < P; ++i) phi_out[i] = 0.0;
-            }
-        } else if (lane == 0) {
-            for (int i = 0; i < P; ++i) phi_out[i] = 0.0;
-        }
-    }
-
-    // full record [cube | theta | phi | birth | logL] (settings.f90:163-182)
-    __device__ __forceinline__ void write_record(double* rec, const double (&x)[NPL], const double (&theta)[NPL],
-                                                 double birth, double logL) const {
-#pragma unroll
-        for (int j = 0; j < NPL; ++j)
-            if (valid[j]) {
-                rec[lane + 32 * j] = x[j];
-                rec[D + lane + 32 * j] = theta[j];
-            }
-        bool ok = true;  // out-of-cube points never reach the likelihood (calculate.f90:36-39): phi = 0
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) ok = ok && (!valid[j] || (x[j] >= 0.0 && x[j] <= 1.0));
-        derived(theta, rec + 2 * D, __all_sync(FULL, ok));
-        if (lane == 0) {
-            rec[2 * D + P] = birth;
-            rec[2 * D + P + 1] = logL;
-        }
-    }
-};
-
-// ------------------------------------------------------------------------------------------
-// Directions of one chain: ceil(R/D) Haar-random orthonormal bases by Gram-Schmidt on Gaussian
-// vectors (random_utils.F90:381-437), then a Fisher-Yates shuffle of columns 2..R
-// (chordal_sampling.f90:133-136, random_utils.F90:505-532) kept as an index deck.
-// nh: R columns with leading dimension LD (odd, bank-conflict free); deck/jd: R ints; dots: D doubles.
-// ------------------------------------------------------------------------------------------
-template <int NPL>
-__device__ inline void gen_directions(int D, int R, int LD, unsigned seed, unsigned long long uid, double* nh, int* deck,
-                                      int* jd, double* dots) {
-    const int lane = threadIdx.x & 31;
-    for (int col0 = 0; col0 < R; col0 += D) {
-        const int m = min(D, R - col0);
-        for (int i = 0; i < m; ++i) {
-            const int col = col0 + i;
-            double* vp = nh + (size_t)col * LD;
-            double v[NPL];
-            double acc = 0.0;
-#pragma unroll
-            for (int j = 0; j < NPL; ++j) {
-                int r = lane + 32 * j;
-                v[j] = 0.0;
-                if (r < D) {
-                    double u0, u1;
-                    uniform2(seed, TAG_DIR, uid, (unsigned)col, (unsigned)(r >> 1), u0, u1);
-                    v[j] = inv_normal_cdf((r & 1) ? u1 : u0);
-                }
-                acc += v[j] * v[j];
-            }
-            double nrm = sqrt(warp_sum(acc));
-#pragma unroll
-            for (int j = 0; j < NPL; ++j) {
-                v[j] /= nrm;
-                if (lane + 32 * j < D) vp[lane + 32 * j] = v[j];
-            }
-            __syncwarp();
-            // projections on the earlier vectors of this basis: lane jj owns <v, q_jj>
-            for (int jj = lane; jj < i; jj += 32) {
-                const double* q = nh + (size_t)(col0 + jj) * LD;
-                double d = 0.0;
-                for (int r = 0; r < D; ++r) d += vp[r] * q[r];
-                dots[jj] = d;
-            }
-            __syncwarp();
-            acc = 0.0;
-#pragma unroll
-            for (int j = 0; j < NPL; ++j) {
-                int r = lane + 32 * j;
-                if (r < D) {
-                    double t = v[j];
-                    for (int jj = 0; jj < i; ++jj) t -= dots[jj] * nh[(size_t)(col0 + jj) * LD + r];
-                    v[j] = t;
-                } else {
-                    v[j] = 0.0;
-                }
-                acc += v[j] * v[j];
-            }
-            nrm = sqrt(warp_sum(acc));
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < NPL; ++j)
-                if (lane + 32 * j < D) vp[lane + 32 * j] = v[j] / nrm;
-            __syncwarp();
-        }
-    }
-    for (int i = lane; i < R; i += 32) {
-        deck[i] = i;
-        int j = 0;
-        if (i >= 1) {
-            double u = uniform(seed, TAG_SHUF, uid, (unsigned)i, 0u);
-            j = (int)ceil(u * (double)i);
-            if (j < 1) j = 1;
-        }
-        jd[i] = j;
-    }
-    __syncwarp();
-    if (lane == 0) {
-        for (int i = R - 1; i >= 1; --i) {
-            int j = jd[i];
-            int t = deck[i]; deck[i] = deck[j]; deck[j] = t;
-        }
-    }
-    __syncwarp();
-}
-
-// ------------------------------------------------------------------------------------------
-// One chain: R slice steps from x (chordal_sampling.f90:7-92 and :163-273).
-// babies 0..R-2 go to ph_base + i*T, the last one to last_dst.  Returns the final logL.
-// ------------------------------------------------------------------------------------------
-template <int NPL>
-__device__ inline double run_chain(const KParams& p, const Model<NPL>& M, unsigned seed, unsigned long long uid,
-                                   double (&x)[NPL], double Lstar, const double* s_chol, double* nh, int* deck, int* jd,
-                                   double* dots, double* ph_base, double* last_dst, unsigned long long& nlike) {
-    const int D = p.D, R = p.R, LD = p.LD, T = p.T, lane = threadIdx.x & 31;
-    const double logzero = p.logzero;
-    gen_directions<NPL>(D, R, LD, seed, uid, nh, deck, jd, dots);
-    double logL_cur = logzero;
-    for (int i = 0; i < R; ++i) {
-        const double* q = nh + (size_t)deck[i] * LD;
-        // nhats = matmul(cholesky, nhats)  (chordal_sampling.f90:73); w = 3*|nhat| (:80-82)
-        double nhat[NPL], acc = 0.0;
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) {
-            int r = lane + 32 * j;
-            double s = 0.0;
-            if (r < D)
-                for (int k = 0; k < D; ++k) s += s_chol[r + k * D] * q[k];
-            nhat[j] = s;
-            acc += s * s;
-        }
-        double w = sqrt(warp_sum(acc));
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) nhat[j] /= w;
-        w *= 3.0;
-
-        // ---- slice_sample (chordal_sampling.f90:163-273), bounds kept as distances dL, dR >= 0 ----
-        double u0 = uniform(seed, TAG_SLICE, uid, (unsigned)i, 0u);
-        double dL = u0 * w, dR = (1.0 - u0) * w;
-        double y[NPL], th[NPL];
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) y[j] = x[j] + dR * nhat[j];
-        double lR = M.eval(y, th);
-        if (lR > logzero) ++nlike;
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) y[j] = x[j] - dL * nhat[j];
-        double lL = M.eval(y, th);
-        if (lL > logzero) ++nlike;
-        int istep = 0;
-        while (lR >= Lstar && lR > logzero) {  // step out (:223-227)
-            ++istep;
-            dR = w * (double)istep;
-#pragma unroll
-            for (int j = 0; j < NPL; ++j) y[j] = x[j] + dR * nhat[j];
-            lR = M.eval(y, th);
-            if (lR > logzero) ++nlike;
-        }
-        istep = 0;
-        while (lL >= Lstar && lL > logzero) {  // (:232-236)
-            ++istep;
-            dL = w * (double)istep;
-#pragma unroll
-            for (int j = 0; j < NPL; ++j) y[j] = x[j] - dL * nhat[j];
-            lL = M.eval(y, th);
-            if (lL > logzero) ++nlike;
-        }
-        double lnew = logzero;
-        bool accepted = false;
-        for (int s = 0; s <= 100; ++s) {  // shrink (:240-266)
-            double u = uniform(seed, TAG_SLICE, uid, (unsigned)i, (unsigned)(1 + s));
-            double t = u * (dR + dL) - dL;
-#pragma unroll
-            for (int j = 0; j < NPL; ++j) y[j] = x[j] + t * nhat[j];
-            lnew = M.eval(y, th);
-            if (lnew > logzero) ++nlike;
-            if (lnew < Lstar || lnew <= logzero) {
-                if (t > 0.0) dR = t; else dL = -t;
-            } else {
-                accepted = true;
-                break;
-            }
-        }
-        if (!accepted) lnew = logzero;  // "Non deterministic loglikelihood" (:268-271)
-#pragma unroll
-        for (int j = 0; j < NPL; ++j) x[j] = y[j];  // next start = this baby even if it failed (:88)
-        double* dst = (i == R - 1) ? last_dst : ph_base + (size_t)i * T;
-        M.write_record(dst, y, th, Lstar, lnew);
-        logL_cur = lnew;
-    }
-    return logL_cur;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1,0 +1,44 @@
+// pc_probes.cuh -- small non-templated probe kernels (parity tests drive them through the C ABI).
+#pragma once
+#include "pc_kernels.cuh"
+
+namespace pc {
+
+// directions of one chain in use order, before whitening: out[i*D + r]
+__global__ void pc_directions_kernel(int D, int R, int LD, unsigned seed, unsigned long long uid, double* nh_global,
+                                     double* out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const ChainScratch cs = chain_scratch(smem, D, R, LD, false, LIKE_GAUSSIAN, 1, nh_global);
+    prep_chain(D, R, LD, seed, uid, cs);
+    for (int i = 0; i < R; ++i)
+        for (int r = threadIdx.x; r < D; r += 32) out[(size_t)i * D + r] = nh_global[(size_t)cs.deck[i] * LD + r];
+}
+
+__global__ void pc_philox_kernel(const unsigned* ctr, const unsigned* key, unsigned* out) {
+    u4 o = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = o.w;
+}
+__global__ void pc_uniforms_kernel(unsigned seed, unsigned tag, unsigned long long uid, unsigned a0, unsigned b, int n,
+                                   double* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = uniform(seed, tag, uid, a0 + (unsigned)i, b);
+}
+__global__ void pc_inv_normal_kernel(const double* pin, int n, double* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = inv_normal_cdf(pin[i]);
+}
+// evidence recurrences for an explicit death sequence (parity probe for evidence_deaths)
+__global__ void pc_evidence_kernel(DevRun* st, const double* logLs, int count, int n_start, double* logw_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double* sc = (double*)smem;
+    double* skey = sc + 64;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) skey[i] = logLs[i];
+    __syncthreads();
+    evidence_deaths(st, skey, count, n_start, logw_out, sc);
+}
+__global__ void pc_cholesky_kernel(const double* a, double* L, int D, int* fb) {
+    int f = warp_cholesky(a, L, D);
+    if (threadIdx.x == 0) *fb = f;
+}
+
+}  // namespace pc

@@ -7,34 +7,15 @@ namespace pc {
 template <class V>
 __device__ __forceinline__ V vload(const V* p) { return *(const volatile V*)p; }
 
-struct WarpScratch {
-    double* nh;    // R x LD (smem or global)
-    double* dots;  // Dpad
-    double* dvec;  // Dpad
-    int* deck;     // R
-    int* jd;       // R
-};
-
-__device__ __forceinline__ WarpScratch warp_scratch(const KParams& p, unsigned char* s_warp, double* nh_global) {
-    WarpScratch ws;
-    const int Dpad = (p.D + 1) & ~1;
-    double* d = (double*)s_warp;
-    ws.dots = d; d += Dpad;
-    ws.dvec = d; d += Dpad;
-    ws.deck = (int*)d; ws.jd = ws.deck + p.R;
-    d += (p.R + 1) & ~1;  // 2*R ints = R doubles, rounded to even
-    ws.nh = p.nh_in_smem ? d : nh_global;
-    return ws;
-}
-
 // ---------------------------------------------------------------- initial live points (K1)
 // GenerateLivePoints, generate.F90:153-183: attempt a draws cube = U(TAG_INIT, a, dim), accepted
-// (in attempt order) when logL > logzero.
-template <int NPL>
-__device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st, const Model<NPL>& M, int cta, int G,
-                                  double* sc) {
-    const int tid = threadIdx.x, lane = tid & 31, W = blockDim.x >> 5, gw = cta * W + (tid >> 5), GW = G * W;
-    const int D = p.D, T = p.T, n = p.n;
+// (in attempt order) when logL > logzero.  One attempt per point group.
+template <int G, int DPL>
+__device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st, const Model<G, DPL>& M, int cta,
+                                  int NG, double* sc) {
+    constexpr int NPT = 32 / G;
+    const int tid = threadIdx.x, W = blockDim.x >> 5, gw = cta * W + (tid >> 5), GW = NG * W;
+    const int D = p.cp.D, T = p.cp.T, n = p.n;
     if (cta == 0) {
         for (int e = tid; e < D * D; e += blockDim.x) {
             double v = (e % D == e / D) ? 1.0 : 0.0;  // run_time_info.f90:193-194
@@ -42,36 +23,38 @@ __device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st
             rb.cov[e] = v;
         }
         if (tid == 0) {
-            st->logZ = st->logZ2 = st->logZX = p.logzero;  // run_time_info.f90:165-175
+            st->logZ = st->logZ2 = st->logZX = p.cp.logzero;  // run_time_info.f90:165-175
             st->logX = st->logXX = 0.0;
             st->logX_last_update = 0.0;
             st->init_need = n;
             st->init_attempts = 0;
         }
     }
-    group_sync(&st->bar, G);
+    group_sync(&st->bar, NG);
     double* staging = rb.ph[1];
     for (;;) {
         const int need = vload(&st->init_need);
         if (need == 0) break;
         const long long a0 = vload(&st->init_attempts);
-        for (int j = gw; j < need; j += GW) {
-            double x[NPL], th[NPL];
+        for (int j0 = gw * NPT; j0 < need; j0 += GW * NPT) {
+            const int j = j0 + M.grp;
+            double x[DPL], th[DPL];
 #pragma unroll
-            for (int q = 0; q < NPL; ++q) {
-                int r = lane + 32 * q;
-                x[q] = (r < D) ? uniform(rb.seed, TAG_INIT, (unsigned long long)(a0 + j), (unsigned)r, 0u) : 0.0;
-            }
-            double l = M.eval(x, th);
-            M.write_record(staging + (size_t)j * T, x, th, p.logzero, l);
+            for (int k = 0; k < DPL; ++k)
+                x[k] = M.valid(k) ? uniform(rb.seed, TAG_INIT, (unsigned long long)(a0 + j), (unsigned)M.dim(k), 0u) : 0.0;
+            const double l = M.eval(x, th);
+            double* rec = staging + (size_t)min(j, need - 1) * T;
+            M.write_record(rec, (j < need) ? M.grp : -1, x, th, p.cp.logzero, l);
+            __syncwarp();
+            if (j < need && M.sub == 0) M.finish_derived(rec, true);
         }
-        group_sync(&st->bar, G);
+        group_sync(&st->bar, NG);
         if (cta == 0) {
             const int have = n - need;
             int run = 0;
             for (int base = 0; base < need; base += blockDim.x) {
                 int j = base + tid;
-                bool ok = j < need && __ldcg(staging + (size_t)j * T + T - 1) > p.logzero;
+                bool ok = j < need && __ldcg(staging + (size_t)j * T + T - 1) > p.cp.logzero;
                 double tot;
                 int pos = (int)block_exscan_sum(ok ? 1.0 : 0.0, &tot, sc);
                 if (ok) {
@@ -88,7 +71,7 @@ __device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st
                 if (a0 > 1000LL * n + 1000000LL) { st->init_need = 0; st->status = ST_ERROR; }
             }
         }
-        group_sync(&st->bar, G);
+        group_sync(&st->bar, NG);
     }
     if (cta == 0 && tid == 0) st->initialised = 1;
 }
@@ -96,7 +79,7 @@ __device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st
 // ---------------------------------------------------------------- phase S (CTA 0)
 __device__ inline void phase_S(const KParams& p, const RunBuf& rb, DevRun* st, double* sc, double* skey, int* sval,
                                int np2) {
-    const int tid = threadIdx.x, n = p.n, T = p.T;
+    const int tid = threadIdx.x, n = p.n, T = p.cp.T;
     for (int i = tid; i < np2; i += blockDim.x) {
         skey[i] = (i < n) ? __ldcg(rb.live + (size_t)i * T + T - 1) : INFINITY;
         sval[i] = i;
@@ -121,7 +104,7 @@ __device__ inline void phase_S(const KParams& p, const RunBuf& rb, DevRun* st, d
     if (K < 1) more = false;
     if (more) {
         if (ndead + K + n > rb.cap_dead) { if (tid == 0) st->status = ST_NEED_DEAD; return; }
-        if (st->nphantom + (long long)K * (p.R - 1) > rb.cap_ph) { if (tid == 0) st->status = ST_NEED_PHANTOM; return; }
+        if (st->nphantom + (long long)K * (p.cp.R - 1) > rb.cap_ph) { if (tid == 0) st->status = ST_NEED_PHANTOM; return; }
     } else if (ndead + n > rb.cap_dead) {
         if (tid == 0) st->status = ST_NEED_DEAD;
         return;
@@ -144,53 +127,45 @@ __device__ inline void phase_S(const KParams& p, const RunBuf& rb, DevRun* st, d
         st->ndead_base = ndead;
         st->ndead = ndead + K;
         st->nph_base = st->nphantom;
-        st->nphantom += (long long)K * (p.R - 1);
+        st->nphantom += (long long)K * (p.cp.R - 1);
         st->nchains_base = st->nchains;
         st->nchains += K;
         st->ngen += 1;
-        st->nslices += (long long)K * p.R;
+        st->nslices += (long long)K * p.cp.R;
         st->do_update = (st->logX <= st->logX_last_update + p.log_comp) ? 1 : 0;  // nested_sampling.F90:321
         st->status = ST_RUNNING;
     }
 }
 
 // ---------------------------------------------------------------- phase U, pass 1: survivor counts + sum x
-template <int NPL>
-__device__ inline void phase_U1(const KParams& p, const RunBuf& rb, DevRun* st, int cta, int G, unsigned char* smem_warp0,
+__device__ inline void phase_U1(const KParams& p, const RunBuf& rb, DevRun* st, int cta, int NG, unsigned char* smem_warp0,
                                 int warp_bytes) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
-    const int D = p.D, T = p.T, n = p.n;
+    const int D = p.cp.D, T = p.cp.T, n = p.n;
     const long long total = vload(&st->nphantom);
     const double Lstar = vload(&st->Lstar);
     const double* src = rb.ph[vload(&st->cur_pool)];
-    const long long chunk = (total + G - 1) / G, c0 = min(total, cta * chunk), c1 = min(total, c0 + chunk);
-    const int lchunk = (n + G - 1) / G, l0 = min(n, cta * lchunk), l1 = min(n, l0 + lchunk);
-    double sx[NPL];
-#pragma unroll
-    for (int j = 0; j < NPL; ++j) sx[j] = 0.0;
+    const long long chunk = (total + NG - 1) / NG, c0 = min(total, cta * chunk), c1 = min(total, c0 + chunk);
+    const int lchunk = (n + NG - 1) / NG, l0 = min(n, cta * lchunk), l1 = min(n, l0 + lchunk);
+    double* mine = (double*)(smem_warp0 + (size_t)warp * warp_bytes);  // [0]=count, [1..D]=sum x
+    __syncthreads();
+    for (int e = lane; e < D + 1; e += 32) mine[e] = 0.0;
+    __syncwarp();
     double cnt = 0.0;
+    // lane r accumulates dimension r, r+32, ... in shared memory (this warp's private slice)
     for (long long rec = c0 + warp; rec < c1; rec += W) {
         const double* r = src + (size_t)rec * T;
         double l = __ldcg(r + T - 1);
         if (!(Lstar > l)) {  // clean_phantoms keeps it (run_time_info.f90:842-875)
             cnt += 1.0;
-#pragma unroll
-            for (int j = 0; j < NPL; ++j)
-                if (lane + 32 * j < D) sx[j] += __ldcg(r + lane + 32 * j);
+            for (int e = lane; e < D; e += 32) mine[1 + e] += __ldcg(r + e);
         }
     }
     for (int rec = l0 + warp; rec < l1; rec += W) {
         const double* r = rb.live + (size_t)rec * T;
-#pragma unroll
-        for (int j = 0; j < NPL; ++j)
-            if (lane + 32 * j < D) sx[j] += __ldcg(r + lane + 32 * j);
+        for (int e = lane; e < D; e += 32) mine[1 + e] += __ldcg(r + e);
     }
-    __syncthreads();
-    double* mine = (double*)(smem_warp0 + (size_t)warp * warp_bytes);
     if (lane == 0) mine[0] = cnt;
-#pragma unroll
-    for (int j = 0; j < NPL; ++j)
-        if (lane + 32 * j < D) mine[1 + lane + 32 * j] = sx[j];
     __syncthreads();
     double* out = rb.partial + (size_t)cta * p.partial_stride;
     for (int e = tid; e < D + 1; e += blockDim.x) {
@@ -203,35 +178,35 @@ __device__ inline void phase_U1(const KParams& p, const RunBuf& rb, DevRun* st, 
 }
 
 // ---------------------------------------------------------------- phase U, pass 2: stable compaction + centred outer products
-template <int NPL>
-__device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, int cta, int G, unsigned char* smem_warp0,
+__device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, int cta, int NG, unsigned char* smem_warp0,
                                 int warp_bytes, int* s_cnt) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
-    const int D = p.D, T = p.T, n = p.n, ntri = p.ntri;
+    const int D = p.cp.D, T = p.cp.T, n = p.n, ntri = p.ntri;
+    const int Dpad = (D + 1) & ~1;
     const long long total = vload(&st->nphantom);
     const double Lstar = vload(&st->Lstar);
     const int pool = vload(&st->cur_pool);
     const double* src = rb.ph[pool];
     double* dst = rb.ph[pool ^ 1];
-    const long long chunk = (total + G - 1) / G, c0 = min(total, cta * chunk), c1 = min(total, c0 + chunk);
-    const int lchunk = (n + G - 1) / G, l0 = min(n, cta * lchunk), l1 = min(n, l0 + lchunk);
+    const long long chunk = (total + NG - 1) / NG, c0 = min(total, cta * chunk), c1 = min(total, c0 + chunk);
+    const int lchunk = (n + NG - 1) / NG, l0 = min(n, cta * lchunk), l1 = min(n, l0 + lchunk);
     long long base = 0, tot = 0;
-    for (int g = 0; g < G; ++g) {
+    for (int g = 0; g < NG; ++g) {
         long long c = vload(&rb.pcount[g]);
         if (g < cta) base += c;
         tot += c;
     }
     const double N = (double)(n + tot);
-    double mean[NPL];
-#pragma unroll
-    for (int j = 0; j < NPL; ++j) {
+    double* mine = (double*)(smem_warp0 + (size_t)warp * warp_bytes);  // [0..Dpad) mean, [Dpad..2Dpad) dv, then COV_ACC*32 partials
+    double* s_mean = mine;
+    double* s_dv = mine + Dpad;
+    __syncthreads();
+    for (int e = lane; e < D; e += 32) {
         double s = 0.0;
-        if (lane + 32 * j < D)
-            for (int g = 0; g < G; ++g) s += vload(&rb.partial[(size_t)g * p.partial_stride + 1 + lane + 32 * j]);
-        mean[j] = s / N;
+        for (int g = 0; g < NG; ++g) s += vload(&rb.partial[(size_t)g * p.partial_stride + 1 + e]);
+        s_mean[e] = s / N;
     }
-    double* mine = (double*)(smem_warp0 + (size_t)warp * warp_bytes);  // [0..D) dv, then COV_ACC*32 partials
-    double* s_dv = mine;
+    __syncwarp();
     for (int pass = 0; pass < p.cov_passes; ++pass) {
         double acc[COV_ACC];
         int ab[COV_ACC];
@@ -250,9 +225,7 @@ __device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, 
         }
         auto accumulate = [&](const double* r) {
             __syncwarp();
-#pragma unroll
-            for (int j = 0; j < NPL; ++j)
-                if (lane + 32 * j < D) s_dv[lane + 32 * j] = __ldcg(r + lane + 32 * j) - mean[j];
+            for (int e = lane; e < D; e += 32) s_dv[e] = __ldcg(r + e) - s_mean[e];
             __syncwarp();
 #pragma unroll
             for (int a = 0; a < COV_ACC; ++a)
@@ -290,7 +263,7 @@ __device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, 
         for (int rec = l0 + warp; rec < l1; rec += W) accumulate(rb.live + (size_t)rec * T);
         // combine the warps of this CTA in warp order
         __syncthreads();
-        double* pacc = mine + ((D + 1) & ~1);
+        double* pacc = mine + 2 * Dpad;
 #pragma unroll
         for (int a = 0; a < COV_ACC; ++a) pacc[a * 32 + lane] = acc[a];
         __syncthreads();
@@ -299,7 +272,7 @@ __device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, 
             if (pass * COV_ACC * 32 + e < ntri) {
                 double s = 0.0;
                 for (int w = 0; w < W; ++w)
-                    s += ((double*)(smem_warp0 + (size_t)w * warp_bytes))[((D + 1) & ~1) + e];
+                    s += ((double*)(smem_warp0 + (size_t)w * warp_bytes))[2 * Dpad + e];
                 out[e] = s;
             }
         }
@@ -308,10 +281,10 @@ __device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, 
 }
 
 // ---------------------------------------------------------------- update finalisation (CTA 0)
-__device__ inline void finish_update(const KParams& p, const RunBuf& rb, DevRun* st, int G) {
-    const int tid = threadIdx.x, D = p.D, ntri = p.ntri;
+__device__ inline void finish_update(const KParams& p, const RunBuf& rb, DevRun* st, int NG) {
+    const int tid = threadIdx.x, D = p.cp.D, ntri = p.ntri;
     long long tot = 0;
-    for (int g = 0; g < G; ++g) tot += vload(&rb.pcount[g]);
+    for (int g = 0; g < NG; ++g) tot += vload(&rb.pcount[g]);
     const double N = (double)(p.n + tot);
     for (int idx = tid; idx < ntri; idx += blockDim.x) {
         int ai = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
@@ -319,7 +292,7 @@ __device__ inline void finish_update(const KParams& p, const RunBuf& rb, DevRun*
         while ((ai + 1) * (ai + 2) / 2 <= idx) ++ai;
         int bi = idx - ai * (ai + 1) / 2;
         double s = 0.0;
-        for (int g = 0; g < G; ++g) s += vload(&rb.partial[(size_t)g * p.partial_stride + 1 + D + idx]);
+        for (int g = 0; g < NG; ++g) s += vload(&rb.partial[(size_t)g * p.partial_stride + 1 + D + idx]);
         s /= N;  // calculate_covmats divides by N, not N-1 (run_time_info.f90:601-641)
         rb.cov[ai + bi * D] = s;
         rb.cov[bi + ai * D] = s;
@@ -341,16 +314,25 @@ __device__ inline void finish_update(const KParams& p, const RunBuf& rb, DevRun*
 }
 
 // ---------------------------------------------------------------- the persistent run kernel
-template <int NPL>
+//
+// One generation, seen from a warp (NG = CTAs of the run's group, GW = NG * warps):
+//   [CTA 0]   wait until every warp arrived (wbar) -> finish a pending update -> phase S -> group barrier B
+//   [others]  chains -> arrive (wbar) -> prepare the directions of the NEXT generation's chain -> barrier B
+// so the counter-addressed direction/uniform preparation of a chain overlaps the bookkeeping of CTA 0
+// and the wait for the slowest chain.  Generations at the update cadence insert phase U (all CTAs)
+// between the arrival and the bookkeeping.
+template <int G, int DPL>
 __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int G = p.ctas_per_run;
-    const int run = blockIdx.x / G, cta = blockIdx.x % G;
+    constexpr int NPT = 32 / G;
+    const int NG = p.ctas_per_run;
+    const int run = blockIdx.x / NG, cta = blockIdx.x % NG;
     const RunBuf rb = p.runs[run];
     DevRun* st = rb.st;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
-    const int gw = cta * W + warp, GW = G * W;
-    const int D = p.D, T = p.T, n = p.n, R = p.R;
+    const int gw = cta * W + warp, GW = NG * W;
+    const int D = p.cp.D, T = p.cp.T, n = p.n, R = p.cp.R, LD = p.cp.LD;
+    const int c0 = p.chain_cta0, Gc = NG - c0;
 
     double* s_chol = (double*)smem;
     double* s_like = (double*)(smem + p.off_like);
@@ -364,176 +346,206 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
     double* skey = sc + 64;
     int* sval = (int*)(skey + np2);
 
-    const int nlp = (p.like_kind == LIKE_GAUSSIAN) ? 2 * D : (p.like_kind == LIKE_CORR ? D + D * D : 0);
+    const int nlp = (p.cp.like_kind == LIKE_GAUSSIAN) ? 2 * D : (p.cp.like_kind == LIKE_CORR ? D + D * D : 0);
     for (int e = tid; e < nlp; e += blockDim.x) s_like[e] = p.like_params[e];
     __syncthreads();
 
-    WarpScratch ws = warp_scratch(p, s_warp, rb.nh ? rb.nh + (size_t)gw * R * p.LD : nullptr);
-    Model<NPL> M;
-    M.init(p, s_like, ws.dvec);
+    const ChainScratch cs = chain_scratch(s_warp, D, R, LD, p.nh_in_smem != 0, p.cp.like_kind, NPT,
+                                          rb.nh ? rb.nh + (size_t)gw * R * LD : nullptr);
+    Model<G, DPL> M;
+    M.init(p.cp, s_like, p.prior_params, cs.dvec);
 
-    if (!vload(&st->initialised)) init_phase<NPL>(p, rb, st, M, cta, G, sc);
+    if (!vload(&st->initialised)) init_phase<G, DPL>(p, rb, st, M, cta, NG, sc);
 
+    // chain whose directions currently sit in this warp's scratch (~0 = none), and whether they are whitened
+    unsigned long long prep_uid = ~0ull;
+    bool prep_white = false;
+    unsigned int wtarget = 0;
+    bool have_wtarget = false;
+
+    const bool timer = (tid == 0) && (cta == 0);          // bookkeeping phases
+    const bool ctimer = (tid == 0) && (cta == c0);         // chain phases of one representative warp
+    const long long t_start = clock64();
     for (;;) {
         if (cta == 0) {
+            long long t0 = clock64();
+            if (have_wtarget) warp_wait(&st->wbar, wtarget);  // every chain of the previous generation is written
+            __syncthreads();
+            long long t1 = clock64();
             bool dump_exit = false;
             if (st->update_pending) {
-                finish_update(p, rb, st, G);
+                finish_update(p, rb, st, NG);
                 dump_exit = p.want_dump != 0;
             }
+            long long t2 = clock64();
             if (dump_exit) {
                 if (tid == 0) st->status = ST_DUMP;
             } else if (vload(&st->status) != ST_ERROR) {
                 phase_S(p, rb, st, sc, skey, sval, np2);
             }
+            __syncthreads();
+            if (timer) {
+                long long t3 = clock64();
+                st->cyc_wait += t1 - t0; st->cyc_fin += t2 - t1; st->cyc_S += t3 - t2; 
+            }
+            prep_uid = ~0ull;  // phase S overlays this CTA's chain scratch
         }
-        group_sync(&st->bar, G);
-        if (vload(&st->status) != ST_RUNNING) return;
+        group_sync(&st->bar, NG);
+        if (vload(&st->status) != ST_RUNNING) {
+            if (timer) st->cyc_total += clock64() - t_start;
+            return;
+        }
 
-        // ---------------- phase C: one chain per warp ----------------
+        // ---------------- phase C: chains, one warp each ----------------
         const int K = vload(&st->K);
         const double Lstar = vload(&st->Lstar);
         const long long ndead_base = vload(&st->ndead_base), nph_base = vload(&st->nph_base);
         const long long nchains_base = vload(&st->nchains_base);
+        const int do_update = vload(&st->do_update);
         double* pool = rb.ph[vload(&st->cur_pool)];
         for (int e = tid; e < D * D; e += blockDim.x) s_chol[e] = __ldcg(rb.chol + e);
         __syncthreads();
         unsigned long long nlike = 0, nfail = 0;
         const int m = n - K;
-        for (int k = gw; k < K; k += GW) {
-            const unsigned long long uid = (unsigned long long)(nchains_base + k);
-            double u = uniform(rb.seed, TAG_SEED, uid, 0u, 0u);  // GenerateSeed, generate.F90:19-55
-            int choice = (int)ceil(u * (double)m);
-            choice = max(1, min(m, choice));
-            const int src = __ldcg(rb.order + K + choice - 1);
-            const int dslot = __ldcg(rb.order + k);
-            double x[NPL];
+        if (cta >= c0) {
+            for (int li = warp;; li += W) {
+                const int k = (cta - c0) + Gc * li;
+                if (k >= K) break;
+                const unsigned long long uid = (unsigned long long)(nchains_base + k);
+                double u = uniform(rb.seed, TAG_SEED, uid, 0u, 0u);  // GenerateSeed, generate.F90:19-55
+                int choice = (int)ceil(u * (double)m);
+                choice = max(1, min(m, choice));
+                const int src = __ldcg(rb.order + K + choice - 1);
+                const int dslot = __ldcg(rb.order + k);
+                double x[DPL];
 #pragma unroll
-            for (int j = 0; j < NPL; ++j) x[j] = (lane + 32 * j < D) ? __ldcg(rb.live + (size_t)src * T + lane + 32 * j) : 0.0;
-            // the dying point moves to the dead list before its slot is reused (run_time_info.f90:789-817)
-            for (int e = lane; e < T; e += 32)
-                rb.dead[(size_t)(ndead_base + k) * T + e] = __ldcg(rb.live + (size_t)dslot * T + e);
-            __syncwarp();
-            double lfin = run_chain<NPL>(p, M, rb.seed, uid, x, Lstar, s_chol, ws.nh, ws.deck, ws.jd, ws.dots,
-                                         pool + (size_t)(nph_base + (long long)k * (R - 1)) * T,
-                                         rb.live + (size_t)dslot * T, nlike);
-            if (!(lfin > Lstar)) ++nfail;
+                for (int j = 0; j < DPL; ++j) x[j] = M.valid(j) ? __ldcg(rb.live + (size_t)src * T + M.dim(j)) : 0.0;
+                // the dying point moves to the dead list before its slot is reused (run_time_info.f90:789-817)
+                for (int e = lane; e < T; e += 32)
+                    rb.dead[(size_t)(ndead_base + k) * T + e] = __ldcg(rb.live + (size_t)dslot * T + e);
+                long long tc0 = clock64();
+                if (prep_uid != uid) {
+                    prep_chain(D, R, LD, rb.seed, uid, cs);
+                    prep_white = false;
+                }
+                long long tc1 = clock64();
+                if (!prep_white) whiten_chain(D, R, LD, s_chol, cs);
+                prep_uid = ~0ull;
+                long long tc2 = clock64();
+                double lfin = slice_chain<G, DPL>(p.cp, M, rb.seed, uid, x, Lstar, cs,
+                                                  pool + (size_t)(nph_base + (long long)k * (R - 1)) * T,
+                                                  rb.live + (size_t)dslot * T, nlike);
+                if (ctimer) {
+                    long long tc3 = clock64();
+                    st->cyc_prep += tc1 - tc0; st->cyc_white += tc2 - tc1; st->cyc_slice += tc3 - tc2;
+                }
+                if (!(lfin > Lstar)) ++nfail;
+            }
         }
         if (lane == 0) {
             if (nlike) atomicAdd((unsigned long long*)&st->nlike, nlike);
             if (nfail) atomicAdd((unsigned long long*)&st->nfail, nfail);
         }
-        if (vload(&st->do_update)) {
-            group_sync(&st->bar, G);
-            phase_U1<NPL>(p, rb, st, cta, G, s_warp0, p.warp_bytes);
-            group_sync(&st->bar, G);
-            phase_U2<NPL>(p, rb, st, cta, G, s_warp0, p.warp_bytes, s_cnt);
+        wtarget = warp_arrive(&st->wbar, GW);
+        have_wtarget = true;
+        // the first chain this warp will run in the next generation (if the run goes on with the same K)
+        const int knext = (cta - c0) + Gc * warp;
+        const bool will_chain = cta >= c0 && cta != 0 && knext < p.batch_K;
+        if (do_update) {
+            long long tu0 = clock64();
+            warp_wait(&st->wbar, wtarget);
+            long long tu1 = clock64();
+            phase_U1(p, rb, st, cta, NG, s_warp0, p.warp_bytes);
+            group_sync(&st->bar, NG);
+            phase_U2(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt);
             if (cta == 0 && tid == 0) st->update_pending = 1;
+            group_sync(&st->bar, NG);
+            if (timer) { st->cyc_wait += tu1 - tu0; st->cyc_U += clock64() - tu1; }
+            have_wtarget = false;
+            if (will_chain) {  // the Cholesky factor is about to change: whiten after the barrier
+                prep_uid = (unsigned long long)(nchains_base + K + knext);
+                prep_chain(D, R, LD, rb.seed, prep_uid, cs);
+                prep_white = false;
+            }
+        } else if (will_chain) {
+            prep_uid = (unsigned long long)(nchains_base + K + knext);
+            prep_chain(D, R, LD, rb.seed, prep_uid, cs);
+            whiten_chain(D, R, LD, s_chol, cs);
+            prep_white = true;
         }
-        group_sync(&st->bar, G);
     }
 }
 
 // ---------------------------------------------------------------- probes
 // SliceSampling for explicit (seed point, contour, uid) triples; one warp per chain.
-template <int NPL>
+template <int G, int DPL>
 __global__ void __launch_bounds__(256, 1) pc_slice_chains_kernel(const __grid_constant__ KParams p, int nchains,
                                                                  const double* seed_points, const double* chol,
                                                                  const double* logL, const unsigned long long* uid,
                                                                  unsigned seed, double* babies, long long* nlike_out,
                                                                  double* nh_global) {
     extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NPT = 32 / G;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
-    const int D = p.D, T = p.T, R = p.R;
+    const int D = p.cp.D, T = p.cp.T, R = p.cp.R, LD = p.cp.LD;
     double* s_chol = (double*)smem;
     double* s_like = (double*)(smem + p.off_like);
     unsigned char* s_warp = smem + p.off_warp + (size_t)warp * p.warp_bytes;
-    const int nlp = (p.like_kind == LIKE_GAUSSIAN) ? 2 * D : (p.like_kind == LIKE_CORR ? D + D * D : 0);
+    const int nlp = (p.cp.like_kind == LIKE_GAUSSIAN) ? 2 * D : (p.cp.like_kind == LIKE_CORR ? D + D * D : 0);
     for (int e = tid; e < nlp; e += blockDim.x) s_like[e] = p.like_params[e];
     for (int e = tid; e < D * D; e += blockDim.x) s_chol[e] = chol[e];
     __syncthreads();
     const int gw = blockIdx.x * W + warp;
-    WarpScratch ws = warp_scratch(p, s_warp, nh_global ? nh_global + (size_t)gw * R * p.LD : nullptr);
-    Model<NPL> M;
-    M.init(p, s_like, ws.dvec);
+    const ChainScratch cs = chain_scratch(s_warp, D, R, LD, p.nh_in_smem != 0, p.cp.like_kind, NPT,
+                                          nh_global ? nh_global + (size_t)gw * R * LD : nullptr);
+    Model<G, DPL> M;
+    M.init(p.cp, s_like, p.prior_params, cs.dvec);
     for (int c = gw; c < nchains; c += gridDim.x * W) {
-        double x[NPL];
+        double x[DPL];
 #pragma unroll
-        for (int j = 0; j < NPL; ++j) x[j] = (lane + 32 * j < D) ? seed_points[(size_t)c * T + lane + 32 * j] : 0.0;
+        for (int j = 0; j < DPL; ++j) x[j] = M.valid(j) ? seed_points[(size_t)c * T + M.dim(j)] : 0.0;
         unsigned long long nl = 0;
         double* out = babies + (size_t)c * R * T;
-        run_chain<NPL>(p, M, seed, uid[c], x, logL[c], s_chol, ws.nh, ws.deck, ws.jd, ws.dots, out,
-                       out + (size_t)(R - 1) * T, nl);
+        prep_chain(D, R, LD, seed, uid[c], cs);
+        whiten_chain(D, R, LD, s_chol, cs);
+        slice_chain<G, DPL>(p.cp, M, seed, uid[c], x, logL[c], cs, out, out + (size_t)(R - 1) * T, nl);
         if (lane == 0) nlike_out[c] = (long long)nl;
     }
 }
 
-template <int NPL>
+template <int G, int DPL>
 __global__ void pc_calculate_points_kernel(const __grid_constant__ KParams p, double* records, int npts, int* nlike) {
     extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NPT = 32 / G;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
-    const int D = p.D, T = p.T;
+    const int D = p.cp.D, T = p.cp.T, R = p.cp.R, LD = p.cp.LD;
     double* s_like = (double*)(smem + p.off_like);
     unsigned char* s_warp = smem + p.off_warp + (size_t)warp * p.warp_bytes;
-    const int nlp = (p.like_kind == LIKE_GAUSSIAN) ? 2 * D : (p.like_kind == LIKE_CORR ? D + D * D : 0);
+    const int nlp = (p.cp.like_kind == LIKE_GAUSSIAN) ? 2 * D : (p.cp.like_kind == LIKE_CORR ? D + D * D : 0);
     for (int e = tid; e < nlp; e += blockDim.x) s_like[e] = p.like_params[e];
     __syncthreads();
-    WarpScratch ws = warp_scratch(p, s_warp, nullptr);
-    Model<NPL> M;
-    M.init(p, s_like, ws.dvec);
+    const ChainScratch cs = chain_scratch(s_warp, D, R, LD, p.nh_in_smem != 0, p.cp.like_kind, NPT, nullptr);
+    Model<G, DPL> M;
+    M.init(p.cp, s_like, p.prior_params, cs.dvec);
     int cnt = 0;
-    for (int c = blockIdx.x * W + warp; c < npts; c += gridDim.x * W) {
-        double* rec = records + (size_t)c * T;
-        double x[NPL], th[NPL];
+    for (int c0 = (blockIdx.x * W + warp) * NPT; c0 < npts; c0 += gridDim.x * W * NPT) {
+        const int c = c0 + M.grp;
+        double* rec = records + (size_t)min(c, npts - 1) * T;
+        double x[DPL], th[DPL];
 #pragma unroll
-        for (int j = 0; j < NPL; ++j) x[j] = (lane + 32 * j < D) ? rec[lane + 32 * j] : 0.0;
-        double l = M.eval(x, th);
-        double birth = rec[T - 2];
+        for (int j = 0; j < DPL; ++j) x[j] = M.valid(j) ? rec[M.dim(j)] : 0.0;
+        const double l = M.eval(x, th);
+        const double birth = rec[T - 2];
         __syncwarp();
-        M.write_record(rec, x, th, birth, l);
-        if (l > p.logzero) ++cnt;
+        M.write_record(rec, (c < npts) ? M.grp : -1, x, th, birth, l);
+        __syncwarp();
+        if (c < npts && M.sub == 0) {
+            M.finish_derived(rec, true);
+            if (l > p.cp.logzero) ++cnt;
+        }
     }
+    cnt = warp_sum_int(cnt);
     if (lane == 0 && cnt) atomicAdd(nlike, cnt);
-}
-
-// directions of one chain, de-shuffled into use order: out[i*D + r]
-template <int NPL>
-__global__ void pc_directions_kernel(int D, int R, int LD, unsigned seed, unsigned long long uid, double* nh_global,
-                                     double* out) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    double* dots = (double*)smem;
-    int* deck = (int*)(dots + ((D + 1) & ~1));
-    int* jd = deck + R;
-    gen_directions<NPL>(D, R, LD, seed, uid, nh_global, deck, jd, dots);
-    for (int i = 0; i < R; ++i)
-        for (int r = threadIdx.x; r < D; r += 32) out[(size_t)i * D + r] = nh_global[(size_t)deck[i] * LD + r];
-}
-
-__global__ void pc_philox_kernel(const unsigned* ctr, const unsigned* key, unsigned* out) {
-    u4 o = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
-    out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = o.w;
-}
-__global__ void pc_uniforms_kernel(unsigned seed, unsigned tag, unsigned long long uid, unsigned a0, unsigned b, int n,
-                                   double* out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = uniform(seed, tag, uid, a0 + (unsigned)i, b);
-}
-__global__ void pc_inv_normal_kernel(const double* pin, int n, double* out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = inv_normal_cdf(pin[i]);
-}
-// evidence recurrences for an explicit death sequence (parity probe for evidence_deaths)
-__global__ void pc_evidence_kernel(DevRun* st, const double* logLs, int count, int n_start, double* logw_out) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    double* sc = (double*)smem;
-    double* skey = sc + 64;
-    for (int i = threadIdx.x; i < count; i += blockDim.x) skey[i] = logLs[i];
-    __syncthreads();
-    evidence_deaths(st, skey, count, n_start, logw_out, sc);
-}
-__global__ void pc_cholesky_kernel(const double* a, double* L, int D, int* fb) {
-    int f = warp_cholesky(a, L, D);
-    if (threadIdx.x == 0) *fb = f;
 }
 
 }  // namespace pc

@@ -62,7 +62,9 @@ def test_chains_match_oracle(gpu, oracle, like, D, P, R, chol_kind):
     bad = []
     for c in range(nchains):
         want, nl = oracle.slice_chain(s, rec[c], chol, float(logL[c]), int(uid[c]), like=like, **kw)
-        if nl != nlike[c] or not np.allclose(babies[c], want, rtol=0, atol=ATOL):
+        # Rastrigin's gradient (up to 20*pi*10.24 per unit of cube) amplifies the O(eps) differences more
+        atol = 1e-6 if like == "rastrigin" else ATOL
+        if nl != nlike[c] or not np.allclose(babies[c], want, rtol=0, atol=atol):
             bad.append((c, nl, int(nlike[c]), float(np.abs(babies[c] - want).max())))
         # every baby is inside the contour and carries it as its birth contour
         assert np.all(babies[c][:, -1] >= logL[c])
