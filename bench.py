@@ -203,10 +203,15 @@ def main():
     sink = {"rows": 0, "logZ": None, "calls": 0}
 
     def _dumper(ndead, nlive, npars, live, dead, lw, logZ, logZerr):
-        # touch the host arrays like a consumer would (pypolychord's dumper wraps them in numpy)
-        d = np.ctypeslib.as_array(dead, shape=(max(ndead, 1), npars))
+        # wrap the host arrays without copying, like pypolychord's shim does (PyArray_SimpleNewFromData,
+        # _pypolychord.cpp:88-94), and touch them
+        if ndead:
+            d = np.frombuffer((C.c_double * (ndead * npars)).from_address(C.addressof(dead.contents)),
+                              dtype=np.float64).reshape(ndead, npars)
+            w = np.frombuffer((C.c_double * ndead).from_address(C.addressof(lw.contents)), dtype=np.float64)
+            sink["last_logL"] = float(d[ndead - 1, npars - 1])
+            sink["last_logw"] = float(w[ndead - 1])
         sink["rows"] = ndead
-        sink["last_logL"] = float(d[ndead - 1, npars - 1]) if ndead else None
         sink["logZ"] = logZ
         sink["calls"] += 1
 

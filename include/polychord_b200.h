@@ -113,6 +113,9 @@ int pc_set_option(const char* name, double value);
 double pc_get_option(const char* name);
 /* CUDA stream (cudaStream_t passed as void*) all engine work is enqueued on; NULL = default stream. */
 void pc_set_stream(void* cuda_stream);
+/* The engine keeps the device buffers of finished runs for the next run (cudaMalloc/cudaFree cost
+ * milliseconds); this returns the cached blocks to the driver. */
+void pc_release_memory(void);
 
 typedef struct pc_run_info {
     int status;               /* 0 ok; <0 error code */

@@ -23,7 +23,7 @@ EXPORTS = [
     "polychord_c_interface", "polychord_c_interface_ini",
     "pc_register_device_likelihood", "pc_register_device_prior", "pc_clear_registrations",
     "pc_gaussian_loglikelihood", "pc_rastrigin_loglikelihood", "pc_corr_gaussian_loglikelihood",
-    "pc_unit_prior", "pc_uniform_prior", "pc_set_option", "pc_get_option", "pc_set_stream",
+    "pc_unit_prior", "pc_uniform_prior", "pc_set_option", "pc_get_option", "pc_set_stream", "pc_release_memory",
     "pc_last_run_info", "pc_run", "pc_run_ensemble", "pc_slice_chains", "pc_calculate_points",
     "pc_device_philox", "pc_device_uniforms", "pc_device_inv_normal_cdf", "pc_device_directions",
     "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version",

@@ -124,12 +124,12 @@ struct Model {
 
     // calculate_point (calculate.f90:6-50) for this group's trial point y: in-cube test, uniform prior
     // (priors.f90:40-55), log-likelihood.  Warp-collective; each group gets its own result.
-    __device__ __forceinline__ double eval(const double (&y)[DPL], double (&theta)[DPL]) const {
-        double mn = y[0], mx = y[0];
+    __device__ __forceinline__ double eval(const double (&y)[DPL], double (&theta)[DPL], bool& incube) const {
+        bool ok = true;
 #pragma unroll
-        for (int k = 1; k < DPL; ++k) { mn = fmin(mn, y[k]); mx = fmax(mx, y[k]); }
-        const unsigned bal = __ballot_sync(FULL, mn >= 0.0 && mx <= 1.0);
-        const bool incube = ((bal >> (grp * G)) & GMASK) == GMASK;
+        for (int k = 0; k < DPL; ++k) ok = ok && (y[k] >= 0.0) && (y[k] <= 1.0);
+        const unsigned bal = __ballot_sync(FULL, ok);
+        incube = ((bal >> (grp * G)) & GMASK) == GMASK;
 #pragma unroll
         for (int k = 0; k < DPL; ++k) theta[k] = fma(wid[k], y[k], lo[k]);
         double logL;
@@ -169,24 +169,21 @@ struct Model {
             for (int k = 0; k < DPL; ++k) acc += valid(k) ? (theta[k] - mu[k]) * yk[k] : 0.0;
             logL = corr_const - group_sum(acc) / 2.0;
         }
-        if (!incube) {  // calculate.f90:36-39: theta = 0, logL = logzero, the likelihood is not called
-#pragma unroll
-            for (int k = 0; k < DPL; ++k) theta[k] = 0.0;
-            logL = logzero;
-        }
-        return logL;
+        // calculate.f90:36-39: outside the cube logL = logzero and the likelihood is not called (callers
+        // that keep such a record zero its theta, see write_record)
+        return incube ? logL : logzero;
     }
 
     // Record [cube | theta | phi | birth | logL] (settings.f90:163-182), written by point group `g`.
     // The derived parameters phi are filled in afterwards by finish_derived.
     __device__ __forceinline__ void write_record(double* rec, int g, const double (&y)[DPL], const double (&theta)[DPL],
-                                                 double birth, double logL) const {
+                                                 double birth, double logL, bool incube = true) const {
         if (grp == g) {
 #pragma unroll
             for (int k = 0; k < DPL; ++k)
                 if (valid(k)) {
                     rec[dim(k)] = y[k];
-                    rec[D + dim(k)] = theta[k];
+                    rec[D + dim(k)] = incube ? theta[k] : 0.0;
                 }
             if (sub == 0) {
                 rec[2 * D + P] = birth;
@@ -240,6 +237,10 @@ __device__ inline void prep_chain(int D, int R, int LD, unsigned seed, unsigned 
         double* vp = nh + (size_t)col * LD + 2 * hp;
         vp[0] = inv_normal_cdf(u0);
         if (2 * hp + 1 < D) vp[1] = inv_normal_cdf(u1);
+    }
+    for (int e = lane; e < R * (LD - D); e += 32) {  // zero padding of every column (entries D..LD-1)
+        const int col = e / (LD - D), r = D + e - col * (LD - D);
+        nh[(size_t)col * LD + r] = 0.0;
     }
     // (c) shuffle picks and (d) slice uniforms are independent of (a)/(b): issue them here so their
     //     integer work overlaps the FP64 work above
@@ -327,40 +328,53 @@ __device__ inline void prep_chain(int D, int R, int LD, unsigned seed, unsigned 
 __device__ inline void whiten_chain(int D, int R, int LD, const double* chol, const ChainScratch& cs) {
     const int lane = threadIdx.x & 31;
     double* nh = cs.nh;
-    const int total = R * D;
-    for (int e0 = 0; e0 < total; e0 += 32) {
-        const int e = e0 + lane;
-        double s0 = 0.0, s1 = 0.0;
-        int col = 0, r = 0;
-        if (e < total) {
-            col = e / D;
-            r = D - 1 - (e - col * D);  // rows descend so that an in-place write never precedes a read
-            const double* q = nh + (size_t)col * LD;
-            int k = 0;
-            for (; k + 1 <= r; k += 2) {
-                s0 += chol[r + (size_t)k * D] * q[k];
-                s1 += chol[r + (size_t)(k + 1) * D] * q[k + 1];
+    // Half-warp h takes column 2j+h; its lane r' computes rows r', r'+16, ... (row r needs q[0..r]).  All reads
+    // of an iteration precede its writes, and columns are independent, so the product is formed in place.
+    const int h = lane >> 4, rp = lane & 15;
+    constexpr int MAXROWS = 8;  // D <= 128
+    for (int c0 = 0; c0 < R; c0 += 2) {
+        const int col = c0 + h;
+        double out[MAXROWS];
+        const double* q = nh + (size_t)col * LD;
+        if (col < R) {
+#pragma unroll
+            for (int m = 0; m < MAXROWS; ++m) {
+                const int r = rp + 16 * m;
+                if (r < D) {
+                    const double* lrow = chol + r;
+                    double s0 = 0.0, s1 = 0.0;
+                    int k = 0;
+                    for (; k + 1 <= r; k += 2) {
+                        s0 = fma(lrow[(size_t)k * D], q[k], s0);
+                        s1 = fma(lrow[(size_t)(k + 1) * D], q[k + 1], s1);
+                    }
+                    if (k <= r) s0 = fma(lrow[(size_t)k * D], q[k], s0);
+                    out[m] = s0 + s1;
+                }
             }
-            if (k <= r) s0 += chol[r + (size_t)k * D] * q[k];
         }
         __syncwarp();
-        if (e < total) nh[(size_t)col * LD + r] = s0 + s1;
+        if (col < R) {
+#pragma unroll
+            for (int m = 0; m < MAXROWS; ++m) {
+                const int r = rp + 16 * m;
+                if (r < D) nh[(size_t)col * LD + r] = out[m];
+            }
+        }
         __syncwarp();
     }
+    // w = 3*|nhat|, nhat /= |nhat| (:80-82): one lane per column
     for (int col = lane; col < R; col += 32) {
-        const double* q = nh + (size_t)col * LD;
-        double s = 0.0;
-        for (int r = 0; r < D; ++r) s += q[r] * q[r];
-        const double w0 = sqrt(s);
-        cs.wts[col] = w0;
+        double* q = nh + (size_t)col * LD;
+        double s0 = 0.0, s1 = 0.0;
+        int r = 0;
+        for (; r + 1 < D; r += 2) { s0 = fma(q[r], q[r], s0); s1 = fma(q[r + 1], q[r + 1], s1); }
+        if (r < D) s0 = fma(q[r], q[r], s0);
+        const double w0 = sqrt(s0 + s1);
+        const double inv = 1.0 / w0;
+        for (r = 0; r < D; ++r) q[r] *= inv;
+        cs.wts[col] = 3.0 * w0;
     }
-    __syncwarp();
-    for (int e = lane; e < total; e += 32) {
-        const int col = e / D, r = e - col * D;
-        nh[(size_t)col * LD + r] /= cs.wts[col];
-    }
-    __syncwarp();
-    for (int col = lane; col < R; col += 32) cs.wts[col] *= 3.0;
     __syncwarp();
 }
 
@@ -394,8 +408,7 @@ __device__ inline double slice_chain(const ChainParams& p, const Model<G, DPL>& 
 
     // ballot bits of groups 0..g-1 (the G lanes of a group always vote alike)
     auto lanes_below = [](int g) -> unsigned {
-        const int nb = g << LOG2G;
-        return nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
+        return g > 0 ? (0xffffffffu >> (32 - (g << LOG2G))) : 0u;
     };
 
     for (int i = 0; i < R; ++i) {
@@ -403,17 +416,18 @@ __device__ inline double slice_chain(const ChainParams& p, const Model<G, DPL>& 
         const double* q = cs.nh + (size_t)c * LD;
         double nh[DPL];
 #pragma unroll
-        for (int k = 0; k < DPL; ++k) nh[k] = M.valid(k) ? q[M.dim(k)] : 0.0;
+        for (int k = 0; k < DPL; ++k) nh[k] = q[M.dim(k)];  // columns are zero-padded to G*DPL entries
         const double w = cs.wts[c];
         const double* ui = cs.uni + (size_t)i * NU;
         const double u0 = ui[0];
         double dL = u0 * w, dR = (1.0 - u0) * w;  // bracket [x - dL*nhat, x + dR*nhat] (:213-215)
 
         double y[DPL], th[DPL], l;
+        bool inc;
         auto eval_t = [&](double tt) -> double {  // this group's point x + tt*nhat
 #pragma unroll
             for (int k = 0; k < DPL; ++k) y[k] = fma(tt, nh[k], x[k]);
-            return M.eval(y, th);
+            return M.eval(y, th, inc);
         };
 
         // ---------------- bracket (:213-236) ----------------
@@ -511,7 +525,7 @@ __device__ inline double slice_chain(const ChainParams& p, const Model<G, DPL>& 
         // The accepting group's registers hold the baby (cube, theta): it writes the record.  Every group
         // moves to the same point with the same fma, so the chain state stays replicated bit for bit.
         double* dst = (i == R - 1) ? last_dst : ph_base + (size_t)i * T;
-        M.write_record(dst, g_acc, y, th, Lstar, lnew);
+        M.write_record(dst, g_acc, y, th, Lstar, lnew, inc);
 #pragma unroll
         for (int k = 0; k < DPL; ++k) x[k] = fma(t_acc, nh[k], x[k]);  // next start = this baby even if it failed (:88)
         logL_cur = lnew;

@@ -31,6 +31,64 @@ namespace pc {
                                      " at " + __FILE__ + ":" + std::to_string(__LINE__));              \
     } while (0)
 
+// Caching device allocator: cudaMalloc/cudaFree cost milliseconds and synchronise the device, and a
+// sampler is typically called many times with the same shapes, so freed blocks are kept (per device,
+// per exact size) and handed out again.  pc_release_memory() returns them to the driver.
+struct DevicePool {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void*> free_blocks;
+    std::map<void*, std::pair<int, size_t>> live_blocks;
+    void* get(size_t bytes) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        bytes = (bytes + 255) & ~(size_t)255;
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = free_blocks.find({dev, bytes});
+        void* p = nullptr;
+        if (it != free_blocks.end()) { p = it->second; free_blocks.erase(it); }
+        else {
+            cudaError_t e = cudaMalloc(&p, bytes);
+            if (e != cudaSuccess) {  // give cached blocks back and retry once
+                for (auto& kv : free_blocks) cudaFree(kv.second);
+                free_blocks.clear();
+                e = cudaMalloc(&p, bytes);
+            }
+            if (e != cudaSuccess)
+                throw std::runtime_error(std::string("polychord_b200: cudaMalloc failed: ") + cudaGetErrorString(e));
+        }
+        live_blocks[p] = {dev, bytes};
+        return p;
+    }
+    void put(void* p) {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = live_blocks.find(p);
+        if (it == live_blocks.end()) return;
+        free_blocks.insert({it->second, p});
+        live_blocks.erase(it);
+    }
+    void trim() {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto& kv : free_blocks) cudaFree(kv.second);
+        free_blocks.clear();
+    }
+};
+static DevicePool& pool() { static DevicePool* p = new DevicePool; return *p; }  // leaked on purpose: outlives the CUDA context teardown
+
+// Pinned host staging buffer that grows on demand and is reused between runs.
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void* need(size_t bytes) {
+        if (bytes > cap) {
+            if (p) cudaFreeHost(p);
+            cap = std::max(bytes, cap * 2);
+            PC_CUDA(cudaHostAlloc(&p, cap, cudaHostAllocDefault));
+        }
+        return p;
+    }
+};
+static PinnedBuf g_pin_dead, g_pin_live, g_pin_misc;
+
 template <class V>
 struct DevArr {  // RAII device buffer (exception-transparent: callbacks may throw through the engine)
     V* p = nullptr;
@@ -42,18 +100,17 @@ struct DevArr {  // RAII device buffer (exception-transparent: callbacks may thr
     DevArr(DevArr&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
     DevArr& operator=(DevArr&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
     ~DevArr() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
-    void alloc(size_t n_) { release(); n = n_; if (n) PC_CUDA(cudaMalloc(&p, n * sizeof(V))); }
+    void release() { if (p) pool().put(p); p = nullptr; n = 0; }
+    void alloc(size_t n_) { release(); n = n_; if (n) p = (V*)pool().get(n * sizeof(V)); }
     void zero(cudaStream_t s) { if (n) PC_CUDA(cudaMemsetAsync(p, 0, n * sizeof(V), s)); }
     void upload(const V* h, size_t cnt, cudaStream_t s) { PC_CUDA(cudaMemcpyAsync(p, h, cnt * sizeof(V), cudaMemcpyHostToDevice, s)); }
     void download(V* h, size_t cnt, cudaStream_t s, size_t off = 0) const { PC_CUDA(cudaMemcpyAsync(h, p + off, cnt * sizeof(V), cudaMemcpyDeviceToHost, s)); }
     // grow keeping the first `keep` elements
     void grow(size_t n_, size_t keep, cudaStream_t s) {
-        V* q = nullptr;
-        PC_CUDA(cudaMalloc(&q, n_ * sizeof(V)));
+        V* q = (V*)pool().get(n_ * sizeof(V));
         if (keep) PC_CUDA(cudaMemcpyAsync(q, p, keep * sizeof(V), cudaMemcpyDeviceToDevice, s));
         PC_CUDA(cudaStreamSynchronize(s));
-        if (p) cudaFree(p);
+        if (p) pool().put(p);
         p = q; n = n_;
     }
 };
@@ -171,7 +228,7 @@ static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const Dev
     L.fn = pick_shape(D);
     const int npt = 32 / L.fn.G;
     k.cp.D = D; k.cp.P = P; k.cp.T = 2 * D + P + 2; k.cp.R = R;
-    k.cp.LD = D | 1;
+    k.cp.LD = (L.fn.G * L.fn.DPL) | 1;  // odd (bank-conflict free), zero-padded to the lanes' G*DPL dimensions
     k.cp.like_kind = ms.like_kind;
     k.cp.logzero = s.logzero;
     k.cp.gauss_norm = dm.gauss_norm; k.cp.Vn = dm.Vn; k.cp.log_rast = dm.log_rast; k.cp.corr_const = dm.corr_const;
@@ -351,40 +408,41 @@ struct Engine {
         const int T = k.cp.T, D = k.cp.D, P = k.cp.P, n = k.n, npars = D + P + 2;
         const long long ndead = h.host_st.ndead;
         const long long fresh = ndead - h.mirrored;
+        const int nl = final_dump ? 0 : n;
+        // one batch of async copies into pinned staging, one synchronisation
+        double* sd = fresh > 0 ? (double*)g_pin_dead.need((size_t)fresh * (T + 1) * 8) : nullptr;
+        double* sl = nl > 0 ? (double*)g_pin_live.need((size_t)n * T * 8) : nullptr;
         if (fresh > 0) {
-            std::vector<double> rec((size_t)fresh * T), lw(fresh);
-            h.dead.download(rec.data(), (size_t)fresh * T, stream, (size_t)h.mirrored * T);
-            h.logw.download(lw.data(), fresh, stream, h.mirrored);
-            PC_CUDA(cudaStreamSynchronize(stream));
+            h.dead.download(sd, (size_t)fresh * T, stream, (size_t)h.mirrored * T);
+            h.logw.download(sd + (size_t)fresh * T, fresh, stream, h.mirrored);
             d2h += fresh * (T + 1) * 8;
+        }
+        if (nl > 0) {
+            h.live.download(sl, (size_t)n * T, stream);
+            d2h += (long long)n * T * 8;
+        }
+        PC_CUDA(cudaStreamSynchronize(stream));
+        if (fresh > 0) {
+            const double* lwp = sd + (size_t)fresh * T;
             h.dead_rows.resize((size_t)ndead * npars);
             h.dead_logw.resize(ndead);
             for (long long i = 0; i < fresh; ++i) {
-                const double* s = &rec[(size_t)i * T];
+                const double* s = sd + (size_t)i * T;
                 double* o = &h.dead_rows[(size_t)(h.mirrored + i) * npars];
-                for (int c = 0; c < D; ++c) o[c] = s[D + c];
-                for (int c = 0; c < P; ++c) o[D + c] = s[2 * D + c];
+                std::memcpy(o, s + D, (size_t)(D + P) * sizeof(double));  // theta, phi
                 o[D + P] = s[2 * D + P];
                 o[D + P + 1] = s[2 * D + P + 1];
-                h.dead_logw[h.mirrored + i] = lw[i] + s[T - 1];
+                h.dead_logw[h.mirrored + i] = lwp[i] + s[T - 1];
             }
             h.mirrored = ndead;
         }
-        int nl = final_dump ? 0 : n;
         std::vector<double> live_rows((size_t)std::max(nl, 1) * npars);
-        if (nl > 0) {
-            std::vector<double> rec((size_t)n * T);
-            h.live.download(rec.data(), (size_t)n * T, stream);
-            PC_CUDA(cudaStreamSynchronize(stream));
-            d2h += (long long)n * T * 8;
-            for (int i = 0; i < n; ++i) {
-                const double* s = &rec[(size_t)i * T];
-                double* o = &live_rows[(size_t)i * npars];
-                for (int c = 0; c < D; ++c) o[c] = s[D + c];
-                for (int c = 0; c < P; ++c) o[D + c] = s[2 * D + c];
-                o[D + P] = s[2 * D + P];
-                o[D + P + 1] = s[2 * D + P + 1];
-            }
+        for (int i = 0; i < nl; ++i) {
+            const double* s = sl + (size_t)i * T;
+            double* o = &live_rows[(size_t)i * npars];
+            std::memcpy(o, s + D, (size_t)(D + P) * sizeof(double));
+            o[D + P] = s[2 * D + P];
+            o[D + P + 1] = s[2 * D + P + 1];
         }
         std::vector<double> lw(std::max<long long>(ndead, 1));
         if (ndead > 0) {
@@ -526,6 +584,7 @@ double pc_get_option(const char* name) {
     return NAN;
 }
 void pc_set_stream(void* cuda_stream) { g_stream = (cudaStream_t)cuda_stream; }
+void pc_release_memory(void) { pool().trim(); }
 
 int pc_last_run_info(pc_run_info* out) {
     *out = g_last;
@@ -602,9 +661,12 @@ void pc_uniform_prior(double* cube, double* theta, int nDims) {
 static int run_common(const pc_settings* s, const ModelSpec& ms, int nruns, const int* seeds, pc_dumper_t dumper,
                       pc_run_info* out) {
     std::lock_guard<std::mutex> lk(g_mu);
+    auto t0 = std::chrono::steady_clock::now();
     Engine e;
     e.setup(*s, ms, nruns, seeds);
     e.run(dumper, out);
+    const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    for (int r = 0; r < nruns; ++r) out[r].wall_ms = wall;  // entry to return, set-up included
     g_last = out[0];
     return 0;
 }

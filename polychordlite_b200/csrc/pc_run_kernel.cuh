@@ -42,9 +42,10 @@ __device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st
 #pragma unroll
             for (int k = 0; k < DPL; ++k)
                 x[k] = M.valid(k) ? uniform(rb.seed, TAG_INIT, (unsigned long long)(a0 + j), (unsigned)M.dim(k), 0u) : 0.0;
-            const double l = M.eval(x, th);
+            bool inc;
+            const double l = M.eval(x, th, inc);
             double* rec = staging + (size_t)min(j, need - 1) * T;
-            M.write_record(rec, (j < need) ? M.grp : -1, x, th, p.cp.logzero, l);
+            M.write_record(rec, (j < need) ? M.grp : -1, x, th, p.cp.logzero, l, inc);
             __syncwarp();
             if (j < need && M.sub == 0) M.finish_derived(rec, true);
         }
@@ -138,6 +139,9 @@ __device__ inline void phase_S(const KParams& p, const RunBuf& rb, DevRun* st, d
 }
 
 // ---------------------------------------------------------------- phase U, pass 1: survivor counts + sum x
+// clean_phantoms (run_time_info.f90:820-877) keeps a phantom unless the contour has passed it.  Each warp
+// takes 32 consecutive records per step: the lanes test the 32 logL values, then the kept records are added
+// four at a time (loads issued together), lane r holding the running sum of dimension r, r+32, ...
 __device__ inline void phase_U1(const KParams& p, const RunBuf& rb, DevRun* st, int cta, int NG, unsigned char* smem_warp0,
                                 int warp_bytes) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
@@ -149,23 +153,45 @@ __device__ inline void phase_U1(const KParams& p, const RunBuf& rb, DevRun* st, 
     const int lchunk = (n + NG - 1) / NG, l0 = min(n, cta * lchunk), l1 = min(n, l0 + lchunk);
     double* mine = (double*)(smem_warp0 + (size_t)warp * warp_bytes);  // [0]=count, [1..D]=sum x
     __syncthreads();
-    for (int e = lane; e < D + 1; e += 32) mine[e] = 0.0;
-    __syncwarp();
+    double sx[4] = {0.0, 0.0, 0.0, 0.0};  // D <= 128
     double cnt = 0.0;
-    // lane r accumulates dimension r, r+32, ... in shared memory (this warp's private slice)
-    for (long long rec = c0 + warp; rec < c1; rec += W) {
-        const double* r = src + (size_t)rec * T;
-        double l = __ldcg(r + T - 1);
-        if (!(Lstar > l)) {  // clean_phantoms keeps it (run_time_info.f90:842-875)
-            cnt += 1.0;
-            for (int e = lane; e < D; e += 32) mine[1 + e] += __ldcg(r + e);
+    auto add4 = [&](const double* r0, const double* r1, const double* r2, const double* r3) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = lane + 32 * j;
+            if (e < D) {
+                const double v0 = r0 ? __ldcg(r0 + e) : 0.0, v1 = r1 ? __ldcg(r1 + e) : 0.0;
+                const double v2 = r2 ? __ldcg(r2 + e) : 0.0, v3 = r3 ? __ldcg(r3 + e) : 0.0;
+                if (r0) sx[j] += v0;
+                if (r1) sx[j] += v1;
+                if (r2) sx[j] += v2;
+                if (r3) sx[j] += v3;
+            }
+        }
+    };
+    for (long long tile = c0 + (long long)warp * 32; tile < c1; tile += (long long)W * 32) {
+        const long long rec = tile + lane;
+        const bool keep = rec < c1 && !(Lstar > __ldcg(src + (size_t)rec * T + T - 1));
+        unsigned rem = __ballot_sync(FULL, keep);
+        cnt += (double)__popc(rem);
+        while (rem) {
+            const double* r[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (rem) { const int b = __ffs(rem) - 1; rem &= rem - 1; r[j] = src + (size_t)(tile + b) * T; }
+                else r[j] = nullptr;
+            }
+            add4(r[0], r[1], r[2], r[3]);
         }
     }
-    for (int rec = l0 + warp; rec < l1; rec += W) {
-        const double* r = rb.live + (size_t)rec * T;
-        for (int e = lane; e < D; e += 32) mine[1 + e] += __ldcg(r + e);
+    for (int rec = l0 + warp * 4; rec < l1; rec += W * 4) {
+        const double* b = rb.live + (size_t)rec * T;
+        add4(b, rec + 1 < l1 ? b + T : nullptr, rec + 2 < l1 ? b + 2 * T : nullptr, rec + 3 < l1 ? b + 3 * T : nullptr);
     }
     if (lane == 0) mine[0] = cnt;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (lane + 32 * j < D) mine[1 + lane + 32 * j] = sx[j];
     __syncthreads();
     double* out = rb.partial + (size_t)cta * p.partial_stride;
     for (int e = tid; e < D + 1; e += blockDim.x) {
@@ -190,23 +216,35 @@ __device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, 
     double* dst = rb.ph[pool ^ 1];
     const long long chunk = (total + NG - 1) / NG, c0 = min(total, cta * chunk), c1 = min(total, c0 + chunk);
     const int lchunk = (n + NG - 1) / NG, l0 = min(n, cta * lchunk), l1 = min(n, l0 + lchunk);
-    long long base = 0, tot = 0;
-    for (int g = 0; g < NG; ++g) {
-        long long c = vload(&rb.pcount[g]);
-        if (g < cta) base += c;
-        tot += c;
-    }
-    const double N = (double)(n + tot);
-    double* mine = (double*)(smem_warp0 + (size_t)warp * warp_bytes);  // [0..Dpad) mean, [Dpad..2Dpad) dv, then COV_ACC*32 partials
-    double* s_mean = mine;
+    double* mine = (double*)(smem_warp0 + (size_t)warp * warp_bytes);  // [0..Dpad) mean (warp 0's copy is used), [Dpad..2Dpad) dv, then COV_ACC*32 partials
+    double* s_mean = (double*)smem_warp0;
     double* s_dv = mine + Dpad;
+    long long* s_base = (long long*)(s_cnt + 16);  // [0] survivors in CTAs before this one, [1] all survivors
     __syncthreads();
-    for (int e = lane; e < D; e += 32) {
+    if (warp == 0) {
+        long long before = 0, all = 0;
+        for (int g = lane; g < NG; g += 32) {
+            const long long c = __ldcg(rb.pcount + g);
+            all += c;
+            if (g < cta) before += c;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            before += __shfl_xor_sync(FULL, before, o);
+            all += __shfl_xor_sync(FULL, all, o);
+        }
+        if (lane == 0) { s_base[0] = before; s_base[1] = all; }
+    }
+    __syncthreads();
+    const long long base = s_base[0], tot = s_base[1];
+    const double N = (double)(n + tot);
+    for (int e = tid; e < D; e += blockDim.x) {  // the mean, summed over the CTAs in CTA order
         double s = 0.0;
-        for (int g = 0; g < NG; ++g) s += vload(&rb.partial[(size_t)g * p.partial_stride + 1 + e]);
+#pragma unroll 8
+        for (int g = 0; g < NG; ++g) s += __ldcg(rb.partial + (size_t)g * p.partial_stride + 1 + e);
         s_mean[e] = s / N;
     }
-    __syncwarp();
+    __syncthreads();
     for (int pass = 0; pass < p.cov_passes; ++pass) {
         double acc[COV_ACC];
         int ab[COV_ACC];
@@ -284,7 +322,8 @@ __device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, 
 __device__ inline void finish_update(const KParams& p, const RunBuf& rb, DevRun* st, int NG) {
     const int tid = threadIdx.x, D = p.cp.D, ntri = p.ntri;
     long long tot = 0;
-    for (int g = 0; g < NG; ++g) tot += vload(&rb.pcount[g]);
+#pragma unroll 8
+    for (int g = 0; g < NG; ++g) tot += __ldcg(rb.pcount + g);
     const double N = (double)(p.n + tot);
     for (int idx = tid; idx < ntri; idx += blockDim.x) {
         int ai = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
@@ -292,7 +331,8 @@ __device__ inline void finish_update(const KParams& p, const RunBuf& rb, DevRun*
         while ((ai + 1) * (ai + 2) / 2 <= idx) ++ai;
         int bi = idx - ai * (ai + 1) / 2;
         double s = 0.0;
-        for (int g = 0; g < NG; ++g) s += vload(&rb.partial[(size_t)g * p.partial_stride + 1 + D + idx]);
+#pragma unroll 8
+        for (int g = 0; g < NG; ++g) s += __ldcg(rb.partial + (size_t)g * p.partial_stride + 1 + D + idx);
         s /= N;  // calculate_covmats divides by N, not N-1 (run_time_info.f90:601-641)
         rb.cov[ai + bi * D] = s;
         rb.cov[bi + ai * D] = s;
@@ -534,10 +574,11 @@ __global__ void pc_calculate_points_kernel(const __grid_constant__ KParams p, do
         double x[DPL], th[DPL];
 #pragma unroll
         for (int j = 0; j < DPL; ++j) x[j] = M.valid(j) ? rec[M.dim(j)] : 0.0;
-        const double l = M.eval(x, th);
+        bool inc;
+        const double l = M.eval(x, th, inc);
         const double birth = rec[T - 2];
         __syncwarp();
-        M.write_record(rec, (c < npts) ? M.grp : -1, x, th, birth, l);
+        M.write_record(rec, (c < npts) ? M.grp : -1, x, th, birth, l, inc);
         __syncwarp();
         if (c < npts && M.sub == 0) {
             M.finish_derived(rec, true);
