@@ -106,6 +106,8 @@ void pc_uniform_prior(double* cube, double* theta, int nDims); /* theta = lo + (
  *   "max_ctas"        cap on the CTAs of one run (default 0 = one warp per chain)
  *   "errors_return"   1: configuration errors return instead of exit(1)
  *   "nh_global"       1: keep the direction scratch in global memory even when it fits in shared memory
+ *   "no_pairing"      1: do not use helper warps for the direction preparation (a run alone on the device
+ *                     normally pairs every chain warp with a helper warp)
  *   "cap_dead0", "cap_ph0"  initial capacity (records) of the dead / phantom pools; 0 = automatic.
  *                     The pools grow on demand either way (the kernel exits, the host reallocates, relaunches).
  */

@@ -87,7 +87,7 @@ struct PinnedBuf {
         return p;
     }
 };
-static PinnedBuf g_pin_dead, g_pin_live, g_pin_misc;
+static PinnedBuf g_pin_dead, g_pin_live;
 
 template <class V>
 struct DevArr {  // RAII device buffer (exception-transparent: callbacks may throw through the engine)
@@ -123,6 +123,7 @@ struct Options {
     int max_ctas = 0;
     int errors_return = 0;
     int nh_global = 0;  // force the direction scratch into global memory (testing)
+    int no_pairing = 0; // keep the helper-warp preparation off (testing)
     long long cap_dead0 = 0, cap_ph0 = 0;  // initial pool capacities in records (0 = automatic)
 };
 static Options g_opt;
@@ -252,9 +253,10 @@ static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const Dev
     off += 64 * sizeof(int);  // s_cnt
     k.off_warp = (int)off;
     const size_t cov_bytes = (size_t)(2 * Dpad + COV_ACC * 32) * 8;
-    int np2 = 1;
-    while (np2 < s.nlive) np2 <<= 1;
-    const size_t sort_bytes = 64 * 8 + (size_t)np2 * 12;
+    int K = g_opt.batch_K > 0 ? g_opt.batch_K : (int)std::lround(s.nlive * g_opt.batch_fraction);
+    K = std::max(1, std::min(K, s.nlive - 1));
+    k.batch_K = K;
+    const size_t sort_bytes = std::max(smem_S_bytes(s.nlive, K), (size_t)64 * 8 + (size_t)D * D * 8);  // phase S, or the covariance in finish_update
     const size_t budget = 200 * 1024;
     const size_t with_nh = chain_scratch_bytes(D, R, k.cp.LD, true, ms.like_kind, npt);
     const bool in_smem = !g_opt.nh_global && (off + (size_t)W * std::max(with_nh, cov_bytes) <= budget);
@@ -319,9 +321,7 @@ struct Engine {
         W = L.W;
         set_smem(L.fn, L.smem);
         KParams& k = L.kp;
-        int K = g_opt.batch_K > 0 ? g_opt.batch_K : (int)std::lround(S.nlive * g_opt.batch_fraction);
-        K = std::max(1, std::min(K, S.nlive - 1));
-        k.batch_K = K;
+        const int K = k.batch_K;
         // CTAs per run: one warp per chain unless capped by residency
         int dev = 0, sms = 0, per_sm = 0;
         PC_CUDA(cudaGetDevice(&dev));
@@ -337,6 +337,7 @@ struct Engine {
         if ((long long)G * nruns > capacity) throw std::invalid_argument("polychord_b200: too many concurrent runs for one launch");
         k.ctas_per_run = G;
         k.chain_cta0 = (G >= 8) ? 1 : 0;
+        k.paired = (k.chain_cta0 == 1 && W >= 2 && (W % 2) == 0 && !g_opt.no_pairing) ? 1 : 0;
         PC_CUDA(cudaEventCreate(&ev0));
         PC_CUDA(cudaEventCreate(&ev1));
 
@@ -351,14 +352,14 @@ struct Engine {
             if (g_opt.cap_ph0 > 0) cap_ph = std::max<long long>(g_opt.cap_ph0, std::max<long long>((long long)K * (R - 1), n));
             h.st.alloc(1); h.st.zero(stream);
             h.live.alloc((size_t)n * T); h.live.zero(stream);
-            h.order.alloc(n);
+            h.order.alloc(2 * (size_t)n);
             h.dead.alloc((size_t)cap_dead * T);
             h.logw.alloc(cap_dead);
             h.ph0.alloc((size_t)cap_ph * T);
             h.ph1.alloc((size_t)cap_ph * T);
             h.chol.alloc((size_t)D * D); h.cov.alloc((size_t)D * D);
             h.partial.alloc((size_t)G * k.partial_stride);
-            h.pcount.alloc(G); h.pcount.zero(stream);
+            h.pcount.alloc((size_t)cap_ph / U_TILE + 2); h.pcount.zero(stream);
             if (!k.nh_in_smem) h.nh.alloc((size_t)G * W * R * k.cp.LD);
             RunBuf& b = h.buf;
             std::memset(&b, 0, sizeof(b));
@@ -474,6 +475,8 @@ struct Engine {
             DevArr<double>& b = cur == 0 ? h.ph1 : h.ph0;
             a.grow((size_t)nc * k.cp.T, (size_t)h.host_st.nphantom * k.cp.T, stream);
             b.alloc((size_t)nc * k.cp.T);
+            h.pcount.alloc((size_t)nc / U_TILE + 2);
+            h.buf.pcount = h.pcount.p;
             h.buf.ph[0] = h.ph0.p; h.buf.ph[1] = h.ph1.p; h.buf.cap_ph = nc;
         }
     }
@@ -520,6 +523,12 @@ struct Engine {
                 const long long cyc[8] = {s.cyc_wait, s.cyc_S, s.cyc_fin, s.cyc_U, s.cyc_prep, s.cyc_white, s.cyc_slice, s.cyc_total};
                 for (int i = 0; i < 8; ++i) o.phase_ms[i] = khz > 0 ? (double)cyc[i] / (double)khz : 0.0;
             }
+            if (std::getenv("PC_DEBUG")) {
+                int khz = 1; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+                std::fprintf(stderr, "[pc dbg ms]");
+                for (int i = 0; i < 8; ++i) std::fprintf(stderr, " %.3f", (double)s.dbg[i] / khz);
+                std::fprintf(stderr, "\n");
+            }
             o.algorithmic_bytes = s.nslices * (8LL * k.cp.T + 8LL * k.cp.D) + s.nchains * 16LL * k.cp.T + s.ngen * 8LL * k.cp.D * k.cp.D;
         }
     }
@@ -565,6 +574,7 @@ int pc_set_option(const char* name, double value) {
     else if (s == "max_ctas") g_opt.max_ctas = (int)value;
     else if (s == "errors_return") g_opt.errors_return = (int)value;
     else if (s == "nh_global") g_opt.nh_global = (int)value;
+    else if (s == "no_pairing") g_opt.no_pairing = (int)value;
     else if (s == "cap_dead0") g_opt.cap_dead0 = (long long)value;
     else if (s == "cap_ph0") g_opt.cap_ph0 = (long long)value;
     else return -1;
@@ -579,6 +589,7 @@ double pc_get_option(const char* name) {
     if (s == "max_ctas") return g_opt.max_ctas;
     if (s == "errors_return") return g_opt.errors_return;
     if (s == "nh_global") return g_opt.nh_global;
+    if (s == "no_pairing") return g_opt.no_pairing;
     if (s == "cap_dead0") return (double)g_opt.cap_dead0;
     if (s == "cap_ph0") return (double)g_opt.cap_ph0;
     return NAN;

@@ -29,6 +29,7 @@ enum Status : int { ST_RUNNING = 0, ST_DONE = 1, ST_NEED_DEAD = 2, ST_NEED_PHANT
 
 constexpr double NEG_BIG = -1e300;  // log(0) stand-in that survives additions without NaN
 constexpr int COV_ACC = 20;         // covariance accumulators per lane and pass
+constexpr int U_TILE = 256;         // records per phantom tile of phase U (= threads per CTA)
 
 // Mutable per-run scalars (device global memory; the host reads them between launches).
 struct DevRun {
@@ -38,6 +39,7 @@ struct DevRun {
     double cov_N;     // points that entered the last covariance
     long long ndead, nlike, nchains, ngen, nupdates, nfail, nslices;
     long long nphantom;       // records in the current phantom pool
+    long long ph_kept;        // survivors counted by the last phase U
     long long ndead_base;     // ndead before the generation in flight
     long long nph_base;       // nphantom before the generation in flight
     long long nchains_base;
@@ -50,8 +52,11 @@ struct DevRun {
     int initialised;
     int init_need;
     int chol_fallback;   // number of calc_cholesky identity fallbacks
+    int order_valid;     // rb.order + order_off holds the live slots sorted by (logL, slot) as of the last phase S
+    int order_off;       // 0 or n: which half of rb.order is current
     // SM-clock cycle counters of the phases (thread 0 of CTA 0; chain phases: warp 0 of the first chain CTA)
     long long cyc_wait, cyc_S, cyc_fin, cyc_U, cyc_prep, cyc_white, cyc_slice, cyc_total;
+    long long dbg[8];    // scratch cycle counters for profiling experiments (printed when PC_DEBUG is set)
     unsigned int bar;    // group barrier, one arrival per CTA (monotonic)
     unsigned int wbar;   // chains-done barrier, one arrival per warp (monotonic)
 };
@@ -59,14 +64,14 @@ struct DevRun {
 struct RunBuf {
     DevRun* st;
     double* live;      // n x T records
-    int* order;        // n slots sorted by (logL, slot)
+    int* order;        // 2 x n: live slots sorted by (logL, slot), ping-pong (DevRun::order_off)
     double* dead;      // cap_dead x T
     double* logw;      // cap_dead
     double* ph[2];     // phantom pools (ping-pong), cap_ph x T each
     double* chol;      // D x D column-major
     double* cov;       // D x D column-major
     double* partial;   // per CTA: [0]=count, [1..D]=sum x, then ntri covariance partials
-    long long* pcount; // per CTA survivor counts
+    long long* pcount; // survivor count of each phantom tile (phase U)
     double* nh;        // global direction scratch (used when the directions do not fit in smem)
     long long cap_dead, cap_ph;
     unsigned int seed;
@@ -79,6 +84,7 @@ struct KParams {
     int use_prec, max_ndead;
     int ctas_per_run, warps_per_cta;
     int chain_cta0;              // first CTA of a run's group that runs chains (1: CTA 0 only keeps the books)
+    int paired;                  // 1: warps w >= W/2 prepare the chains of warp w - W/2 (a run alone on the device)
     int nh_in_smem, want_dump;
     int ntri, cov_passes, partial_stride;
     int off_like, off_warp, warp_bytes;  // shared-memory byte offsets
@@ -87,6 +93,33 @@ struct KParams {
     const double* prior_params;  // lo[D], hi-lo[D]
     RunBuf* runs;
 };
+
+// shared-memory layout of phase S (CTA 0)
+struct SmemS {
+    double* sc;     // 64 doubles of reduction scratch
+    double* akey;   // n: keys of the survivors in order (merge path) / np2: all keys (full sort)
+    double* bkey;   // npB: keys of the new babies
+    int* bval;      // npB (merge) / np2 (full sort: slot of every key)
+    double* kkey;   // batch_K (+pad): the K lowest keys in order -> evidence
+};
+__host__ __device__ inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+__host__ __device__ inline size_t smem_S_bytes(int n, int batch_K) {
+    const int np2 = next_pow2(n), npB = next_pow2(batch_K);
+    size_t full = (size_t)np2 * 12;
+    size_t merge = (size_t)n * 8 + (size_t)npB * 12;
+    return 64 * 8 + (full > merge ? full : merge) + (size_t)((batch_K + 1) & ~1) * 8 + 16;
+}
+__device__ inline SmemS smem_S(unsigned char* base, int n, int batch_K) {
+    SmemS m;
+    const int np2 = next_pow2(n), npB = next_pow2(batch_K);
+    size_t full = (size_t)np2 * 12, merge = (size_t)n * 8 + (size_t)npB * 12;
+    m.sc = (double*)base;
+    m.akey = m.sc + 64;
+    m.kkey = (double*)(base + 64 * 8 + (((full > merge ? full : merge) + 7) & ~(size_t)7));
+    m.bkey = m.akey + n;           // merge layout
+    m.bval = (int*)(m.bkey + npB);
+    return m;
+}
 
 // ------------------------------------------------------------------------------------------
 // group barrier (same fence / atomic / fence pattern cooperative groups uses for grid.sync)

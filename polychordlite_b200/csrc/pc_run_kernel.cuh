@@ -78,53 +78,145 @@ __device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st
 }
 
 // ---------------------------------------------------------------- phase S (CTA 0)
-__device__ inline void phase_S(const KParams& p, const RunBuf& rb, DevRun* st, double* sc, double* skey, int* sval,
-                               int np2) {
-    const int tid = threadIdx.x, n = p.n, T = p.cp.T;
-    for (int i = tid; i < np2; i += blockDim.x) {
-        skey[i] = (i < n) ? __ldcg(rb.live + (size_t)i * T + T - 1) : INFINITY;
-        sval[i] = i;
+// S1 (on the critical path of a generation): termination test (live_logZ, run_time_info.f90:683-709, against
+// precision_criterion, nested_sampling.F90:538), the order of the live points by (logL, slot), the K lowest die:
+// contour, bases, update decision.  The order is maintained incrementally: the n-K survivors of the previous
+// generation are still sorted, so only the K new babies are sorted (bitonic, shared memory) and the two lists
+// are merged by rank (binary searches).  The first generation sorts everything.
+// S2 (off the critical path when CTA 0 only keeps the books): the evidence recurrences of the K deaths.
+// log X after `count` deaths from n_start live points: the same chunked sum evidence_deaths forms
+__device__ inline double logX_after(double lX, int count, int n_start, double* sc) {
+    for (int base = 0; base < count; base += blockDim.x) {
+        const int j = base + threadIdx.x;
+        const bool act = j < count;
+        const double nj = (double)(n_start - (act ? j : 0));
+        const double dx = act ? log(nj) - log(nj + 1.0) : 0.0;
+        double totx;
+        block_exscan_sum(dx, &totx, sc);
+        lX += totx;
+    }
+    return lX;
+}
+
+// returns true when the evidence of the K deaths is still to be accumulated (S2)
+__device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, const SmemS& sm) {
+    const int tid = threadIdx.x, n = p.n, T = p.cp.T, nthr = blockDim.x;
+    double* sc = sm.sc;
+    long long q0 = clock64();
+    const long long ndead = st->ndead;
+    const int Kp = st->K;
+    const bool merge = st->order_valid != 0 && Kp > 0 && Kp < n;
+    const int* oldo = rb.order + st->order_off;
+    int* newo = rb.order + (st->order_off ? 0 : n);
+    const int m = n - Kp, npB = next_pow2(p.batch_K), np2 = next_pow2(n);
+    if (merge) {
+        for (int i = tid; i < m; i += nthr) sm.akey[i] = __ldcg(rb.live + (size_t)__ldcg(oldo + Kp + i) * T + T - 1);
+        for (int j = tid; j < npB; j += nthr) {
+            const int slot = j < Kp ? __ldcg(oldo + j) : 0x7fffffff;
+            sm.bval[j] = slot;
+            sm.bkey[j] = j < Kp ? __ldcg(rb.live + (size_t)slot * T + T - 1) : INFINITY;
+        }
+    } else {
+        for (int i = tid; i < np2; i += nthr) {
+            sm.akey[i] = (i < n) ? __ldcg(rb.live + (size_t)i * T + T - 1) : INFINITY;
+            ((int*)(sm.akey + np2))[i] = i;
+        }
     }
     __syncthreads();
-    const long long ndead = st->ndead;
+    long long q1 = clock64();
+    // every live key once, whichever layout: index i < m in akey, the rest in bkey (merge) / all in akey
+    auto key_at = [&](int i) -> double { return merge ? (i < m ? sm.akey[i] : sm.bkey[i - m]) : sm.akey[i]; };
     bool more = true;
     if (p.max_ndead == 0) more = false;
     else if (p.max_ndead > 0 && ndead >= p.max_ndead) more = false;
-    else if (p.use_prec) {  // live_logZ (run_time_info.f90:683-709) vs precision_criterion (nested_sampling.F90:538)
-        double m = -INFINITY;
-        for (int i = tid; i < n; i += blockDim.x) m = fmax(m, skey[i]);
-        m = block_max(m, sc);
+    else if (p.use_prec) {
+        double mx = -INFINITY;
+        for (int i = tid; i < n; i += nthr) mx = fmax(mx, key_at(i));
+        mx = block_max(mx, sc);
         double s = 0.0;
-        for (int i = tid; i < n; i += blockDim.x) s += exp(skey[i] - m);
+        for (int i = tid; i < n; i += nthr) s += exp(key_at(i) - mx);
         s = block_sum(s, sc);
-        double lz = m + log(s) - log((double)n) + st->logX;
+        double lz = mx + log(s) - log((double)n) + st->logX;
         if (lz < p.log_prec + st->logZ) more = false;
     }
     int K = min(p.batch_K, n - 1);
     if (p.max_ndead > 0) K = (int)min((long long)K, (long long)p.max_ndead - ndead);
     if (K < 1) more = false;
     if (more) {
-        if (ndead + K + n > rb.cap_dead) { if (tid == 0) st->status = ST_NEED_DEAD; return; }
-        if (st->nphantom + (long long)K * (p.cp.R - 1) > rb.cap_ph) { if (tid == 0) st->status = ST_NEED_PHANTOM; return; }
+        if (ndead + K + n > rb.cap_dead) { if (tid == 0) st->status = ST_NEED_DEAD; return false; }
+        if (st->nphantom + (long long)K * (p.cp.R - 1) > rb.cap_ph) { if (tid == 0) st->status = ST_NEED_PHANTOM; return false; }
     } else if (ndead + n > rb.cap_dead) {
         if (tid == 0) st->status = ST_NEED_DEAD;
-        return;
+        return false;
     }
-    block_sort(skey, sval, np2);
-    for (int i = tid; i < n; i += blockDim.x) rb.order[i] = sval[i];
-    if (!more) {  // final kill-off, nested_sampling.F90:381-384
-        evidence_deaths(st, skey, n, n, rb.logw + ndead, sc);
-        for (size_t e = tid; e < (size_t)n * T; e += blockDim.x) {
-            size_t i = e / T, c = e % T;
-            rb.dead[(size_t)(ndead + i) * T + c] = __ldcg(rb.live + (size_t)sval[i] * T + c);
+    long long q2 = clock64();
+    if (merge && more) {
+        block_sort(sm.bkey, sm.bval, npB);
+        // rank of a survivor = its index + number of babies before it; rank of a baby = its index + number of
+        // survivors before it ((key, slot) pairs are distinct, so the merged order is the sorted order)
+        for (int i = tid; i < m; i += nthr) {
+            const double ka = sm.akey[i];
+            const int va = __ldcg(oldo + Kp + i);
+            int lo = 0, hi = Kp;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const double kb = sm.bkey[mid];
+                if (kb < ka || (kb == ka && sm.bval[mid] < va)) lo = mid + 1; else hi = mid;
+            }
+            const int rank = i + lo;
+            newo[rank] = va;
+            if (rank < K) sm.kkey[rank] = ka;
         }
-        if (tid == 0) { st->ndead = ndead + n; st->K = 0; st->status = ST_DONE; }
-        return;
+        for (int j = tid; j < Kp; j += nthr) {
+            const double kb = sm.bkey[j];
+            const int vb = sm.bval[j];
+            int lo = 0, hi = m;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const double ka = sm.akey[mid];
+                bool less = ka < kb;
+                if (ka == kb) less = __ldcg(oldo + Kp + mid) < vb;
+                if (less) lo = mid + 1; else hi = mid;
+            }
+            const int rank = j + lo;
+            newo[rank] = vb;
+            if (rank < K) sm.kkey[rank] = kb;
+        }
+        __syncthreads();
+    } else {
+        // full sort: first generation and the final kill-off (which needs every key in order)
+        double* skey = sm.akey;
+        int* sval = (int*)(sm.akey + np2);
+        if (merge) {  // !more on the merge layout: rebuild the flat layout
+            __syncthreads();
+            for (int i = tid; i < np2; i += nthr) {
+                skey[i] = (i < n) ? __ldcg(rb.live + (size_t)i * T + T - 1) : INFINITY;
+                sval[i] = i;
+            }
+            __syncthreads();
+        }
+        block_sort(skey, sval, np2);
+        for (int i = tid; i < n; i += nthr) newo[i] = sval[i];
+        if (!more) {  // final kill-off, nested_sampling.F90:381-384
+            evidence_deaths(st, skey, n, n, rb.logw + ndead, sc);
+            for (size_t e = tid; e < (size_t)n * T; e += nthr) {
+                size_t i = e / T, c = e % T;
+                rb.dead[(size_t)(ndead + i) * T + c] = __ldcg(rb.live + (size_t)sval[i] * T + c);
+            }
+            if (tid == 0) { st->ndead = ndead + n; st->K = 0; st->status = ST_DONE; }
+            return false;
+        }
+        __syncthreads();
+        for (int i = tid; i < K; i += nthr) sm.kkey[i] = skey[i];
+        __syncthreads();
     }
-    evidence_deaths(st, skey, K, n, rb.logw + ndead, sc);
+    long long q3 = clock64();
+    const double lX_new = logX_after(st->logX, K, n, sc);
     if (tid == 0) {
         st->K = K;
-        st->Lstar = skey[K - 1];
+        st->Lstar = sm.kkey[K - 1];
+        st->order_off = (int)(newo - rb.order);
+        st->order_valid = 1;
         st->ndead_base = ndead;
         st->ndead = ndead + K;
         st->nph_base = st->nphantom;
@@ -133,28 +225,43 @@ __device__ inline void phase_S(const KParams& p, const RunBuf& rb, DevRun* st, d
         st->nchains += K;
         st->ngen += 1;
         st->nslices += (long long)K * p.cp.R;
-        st->do_update = (st->logX <= st->logX_last_update + p.log_comp) ? 1 : 0;  // nested_sampling.F90:321
+        st->do_update = (lX_new <= st->logX_last_update + p.log_comp) ? 1 : 0;  // nested_sampling.F90:321
         st->status = ST_RUNNING;
+        long long q4 = clock64();
+        st->dbg[0] += q1 - q0; st->dbg[1] += q2 - q1; st->dbg[2] += q3 - q2; st->dbg[3] += q4 - q3;
     }
+    return true;
 }
 
-// ---------------------------------------------------------------- phase U, pass 1: survivor counts + sum x
-// clean_phantoms (run_time_info.f90:820-877) keeps a phantom unless the contour has passed it.  Each warp
-// takes 32 consecutive records per step: the lanes test the 32 logL values, then the kept records are added
-// four at a time (loads issued together), lane r holding the running sum of dimension r, r+32, ...
+// S2: update_evidence (run_time_info.f90:211-296) for the K deaths of the generation just published
+__device__ inline void phase_S2(const KParams& p, const RunBuf& rb, DevRun* st, const SmemS& sm) {
+    long long q0 = clock64();
+    const int K = st->K;
+    evidence_deaths(st, sm.kkey, K, p.n, rb.logw + st->ndead_base, sm.sc);
+    if (threadIdx.x == 0) st->dbg[4] += clock64() - q0;
+}
+
+// ---------------------------------------------------------------- phase U
+// clean_phantoms (run_time_info.f90:820-877) + calculate_covmats (:601-641) at the update cadence.
+// The phantom pool is cut into tiles of blockDim.x records dealt round-robin to the CTAs of the run (old
+// phantoms are mostly dead, new ones mostly alive: contiguous chunks would be badly balanced).
+//   pass 1  per tile: survivor count (rb.pcount[tile]); per CTA: sum of the survivors' and its live points' x
+//   pass 2  per tile: stable compaction into the other pool at the tile's prefix offset, fused with the centred
+//           outer products; per CTA partial covariance.  CTA 0 finishes (finish_update).
+// Lane r of a warp owns dimension r, r+32, ... of the running sums; kept records are loaded four at a time.
+
 __device__ inline void phase_U1(const KParams& p, const RunBuf& rb, DevRun* st, int cta, int NG, unsigned char* smem_warp0,
-                                int warp_bytes) {
+                                int warp_bytes, int* s_cnt) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
     const int D = p.cp.D, T = p.cp.T, n = p.n;
     const long long total = vload(&st->nphantom);
     const double Lstar = vload(&st->Lstar);
     const double* src = rb.ph[vload(&st->cur_pool)];
-    const long long chunk = (total + NG - 1) / NG, c0 = min(total, cta * chunk), c1 = min(total, c0 + chunk);
+    const long long ntiles = (total + U_TILE - 1) / U_TILE;
     const int lchunk = (n + NG - 1) / NG, l0 = min(n, cta * lchunk), l1 = min(n, l0 + lchunk);
-    double* mine = (double*)(smem_warp0 + (size_t)warp * warp_bytes);  // [0]=count, [1..D]=sum x
+    double* mine = (double*)(smem_warp0 + (size_t)warp * warp_bytes);  // [0..D) = sum x of this warp
     __syncthreads();
     double sx[4] = {0.0, 0.0, 0.0, 0.0};  // D <= 128
-    double cnt = 0.0;
     auto add4 = [&](const double* r0, const double* r1, const double* r2, const double* r3) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -169,41 +276,45 @@ __device__ inline void phase_U1(const KParams& p, const RunBuf& rb, DevRun* st, 
             }
         }
     };
-    for (long long tile = c0 + (long long)warp * 32; tile < c1; tile += (long long)W * 32) {
-        const long long rec = tile + lane;
-        const bool keep = rec < c1 && !(Lstar > __ldcg(src + (size_t)rec * T + T - 1));
+    for (long long t = cta; t < ntiles; t += NG) {
+        const long long tile = t * U_TILE, rec = tile + tid;
+        const bool keep = rec < total && !(Lstar > __ldcg(src + (size_t)rec * T + T - 1));
         unsigned rem = __ballot_sync(FULL, keep);
-        cnt += (double)__popc(rem);
+        if (lane == 0) s_cnt[warp] = __popc(rem);
         while (rem) {
             const double* r[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (rem) { const int b = __ffs(rem) - 1; rem &= rem - 1; r[j] = src + (size_t)(tile + b) * T; }
+                if (rem) { const int b = __ffs(rem) - 1; rem &= rem - 1; r[j] = src + (size_t)(tile + warp * 32 + b) * T; }
                 else r[j] = nullptr;
             }
             add4(r[0], r[1], r[2], r[3]);
         }
+        __syncthreads();
+        if (tid == 0) {
+            int c = 0;
+            for (int w = 0; w < W; ++w) c += s_cnt[w];
+            rb.pcount[t] = c;
+        }
+        __syncthreads();
     }
     for (int rec = l0 + warp * 4; rec < l1; rec += W * 4) {
         const double* b = rb.live + (size_t)rec * T;
         add4(b, rec + 1 < l1 ? b + T : nullptr, rec + 2 < l1 ? b + 2 * T : nullptr, rec + 3 < l1 ? b + 3 * T : nullptr);
     }
-    if (lane == 0) mine[0] = cnt;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-        if (lane + 32 * j < D) mine[1 + lane + 32 * j] = sx[j];
+        if (lane + 32 * j < D) mine[lane + 32 * j] = sx[j];
     __syncthreads();
     double* out = rb.partial + (size_t)cta * p.partial_stride;
-    for (int e = tid; e < D + 1; e += blockDim.x) {
+    for (int e = tid; e < D; e += blockDim.x) {
         double s = 0.0;
         for (int w = 0; w < W; ++w) s += ((double*)(smem_warp0 + (size_t)w * warp_bytes))[e];
-        out[e] = s;
-        if (e == 0) rb.pcount[cta] = (long long)s;
+        out[1 + e] = s;
     }
     __syncthreads();
 }
 
-// ---------------------------------------------------------------- phase U, pass 2: stable compaction + centred outer products
 __device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, int cta, int NG, unsigned char* smem_warp0,
                                 int warp_bytes, int* s_cnt) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
@@ -214,29 +325,29 @@ __device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, 
     const int pool = vload(&st->cur_pool);
     const double* src = rb.ph[pool];
     double* dst = rb.ph[pool ^ 1];
-    const long long chunk = (total + NG - 1) / NG, c0 = min(total, cta * chunk), c1 = min(total, c0 + chunk);
+    const long long ntiles = (total + U_TILE - 1) / U_TILE;
     const int lchunk = (n + NG - 1) / NG, l0 = min(n, cta * lchunk), l1 = min(n, l0 + lchunk);
     double* mine = (double*)(smem_warp0 + (size_t)warp * warp_bytes);  // [0..Dpad) mean (warp 0's copy is used), [Dpad..2Dpad) dv, then COV_ACC*32 partials
     double* s_mean = (double*)smem_warp0;
     double* s_dv = mine + Dpad;
-    long long* s_base = (long long*)(s_cnt + 16);  // [0] survivors in CTAs before this one, [1] all survivors
+    long long* s_base = (long long*)(s_cnt + 16);  // [0] survivors in the tiles before this CTA's first tile, [1] all survivors
     __syncthreads();
-    if (warp == 0) {
-        long long before = 0, all = 0;
-        for (int g = lane; g < NG; g += 32) {
-            const long long c = __ldcg(rb.pcount + g);
-            all += c;
-            if (g < cta) before += c;
-        }
+    // survivors before tile `upto` (exclusive) starting from tile `from`: one warp, coalesced
+    auto count_range = [&](long long from, long long upto) -> long long {
+        long long c = 0;
+        for (long long g = from + lane; g < upto; g += 32) c += __ldcg(rb.pcount + g);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            before += __shfl_xor_sync(FULL, before, o);
-            all += __shfl_xor_sync(FULL, all, o);
-        }
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+        return c;
+    };
+    if (warp == 0) {
+        const long long before = count_range(0, min((long long)cta, ntiles));
+        const long long all = before + count_range(min((long long)cta, ntiles), ntiles);
         if (lane == 0) { s_base[0] = before; s_base[1] = all; }
     }
     __syncthreads();
-    const long long base = s_base[0], tot = s_base[1];
+    long long base = s_base[0];
+    const long long tot = s_base[1];
     const double N = (double)(n + tot);
     for (int e = tid; e < D; e += blockDim.x) {  // the mean, summed over the CTAs in CTA order
         double s = 0.0;
@@ -244,6 +355,7 @@ __device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, 
         for (int g = 0; g < NG; ++g) s += __ldcg(rb.partial + (size_t)g * p.partial_stride + 1 + e);
         s_mean[e] = s / N;
     }
+    if (cta == 0 && tid == 0) st->ph_kept = tot;
     __syncthreads();
     for (int pass = 0; pass < p.cov_passes; ++pass) {
         double acc[COV_ACC];
@@ -261,44 +373,78 @@ __device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, 
             }
             ab[a] = (idx < ntri) ? ((ai << 16) | bi) : -1;
         }
-        auto accumulate = [&](const double* r) {
+        // centred coordinates of one record -> this warp's dv, then the lane's outer-product entries
+        auto accumulate = [&](const double (&v)[4]) {
             __syncwarp();
-            for (int e = lane; e < D; e += 32) s_dv[e] = __ldcg(r + e) - s_mean[e];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (lane + 32 * j < D) s_dv[lane + 32 * j] = v[j] - s_mean[lane + 32 * j];
             __syncwarp();
 #pragma unroll
             for (int a = 0; a < COV_ACC; ++a)
                 if (ab[a] >= 0) acc[a] += s_dv[ab[a] >> 16] * s_dv[ab[a] & 0xffff];
         };
-        long long run = 0;
-        for (long long tile = c0; tile < c1; tile += blockDim.x) {
-            long long rec = tile + tid;
-            bool keep = rec < c1 && !(Lstar > __ldcg(src + (size_t)rec * T + T - 1));
-            unsigned bal = __ballot_sync(FULL, keep);
+        auto load_x = [&](const double* r, double (&v)[4]) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = (lane + 32 * j < D) ? __ldcg(r + lane + 32 * j) : 0.0;
+        };
+        long long tbase = base;
+        for (long long t = cta; t < ntiles; t += NG) {
+            const long long tile = t * U_TILE, rec = tile + tid;
+            const bool keep = rec < total && !(Lstar > __ldcg(src + (size_t)rec * T + T - 1));
+            const unsigned bal = __ballot_sync(FULL, keep);
             __syncthreads();
             if (lane == 0) s_cnt[warp] = __popc(bal);
             __syncthreads();
-            int woff = 0, ttot = 0;
-            for (int w = 0; w < W; ++w) {
-                int c = s_cnt[w];
-                if (w < warp) woff += c;
-                ttot += c;
-            }
-            unsigned rem = bal;
-            int kk = 0;
-            while (rem) {
-                int b = __ffs(rem) - 1;
-                rem &= rem - 1;
-                const double* r = src + (size_t)(tile + warp * 32 + b) * T;
-                if (pass == 0) {
-                    double* d = dst + (size_t)(base + run + woff + kk) * T;
-                    for (int e = lane; e < T; e += 32) d[e] = __ldcg(r + e);
+            int woff = 0;
+            for (int w = 0; w < warp; ++w) woff += s_cnt[w];
+            if (pass == 0) {  // stable compaction: survivor number woff+kk of the tile goes to tbase+woff+kk
+                unsigned rem = bal;
+                int kk = 0;
+                while (rem) {
+                    const int b0 = __ffs(rem) - 1; rem &= rem - 1;
+                    const int b1 = rem ? __ffs(rem) - 1 : -1; if (rem) rem &= rem - 1;
+                    const double* r0 = src + (size_t)(tile + warp * 32 + b0) * T;
+                    const double* r1 = src + (size_t)(tile + warp * 32 + max(b1, 0)) * T;
+                    double* d0 = dst + (size_t)(tbase + woff + kk) * T;
+                    for (int e = lane; e < T; e += 32) {
+                        const double v0 = __ldcg(r0 + e), v1 = __ldcg(r1 + e);
+                        d0[e] = v0;
+                        if (b1 >= 0) d0[T + e] = v1;
+                    }
+                    kk += (b1 >= 0) ? 2 : 1;
                 }
-                accumulate(r);
-                ++kk;
             }
-            run += ttot;
+            {   // outer products, the next record's coordinates in flight while the current one is accumulated
+                unsigned rem = bal;
+                double cur[4], nxt[4];
+                if (rem) { const int b = __ffs(rem) - 1; rem &= rem - 1; load_x(src + (size_t)(tile + warp * 32 + b) * T, cur); }
+                bool have = bal != 0;
+                while (have) {
+                    const bool more = rem != 0;
+                    if (more) { const int b = __ffs(rem) - 1; rem &= rem - 1; load_x(src + (size_t)(tile + warp * 32 + b) * T, nxt); }
+                    accumulate(cur);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+                    have = more;
+                }
+            }
+            // offset of this CTA's next tile
+            if (t + NG < ntiles) {
+                __syncthreads();
+                if (warp == 0) {
+                    const long long c = count_range(t, t + NG);
+                    if (lane == 0) s_base[0] = tbase + c;
+                }
+                __syncthreads();
+                tbase = s_base[0];
+            }
         }
-        for (int rec = l0 + warp; rec < l1; rec += W) accumulate(rb.live + (size_t)rec * T);
+        for (int rec = l0 + warp; rec < l1; rec += W) {
+            double v[4];
+            load_x(rb.live + (size_t)rec * T, v);
+            accumulate(v);
+        }
         // combine the warps of this CTA in warp order
         __syncthreads();
         double* pacc = mine + 2 * Dpad;
@@ -319,11 +465,9 @@ __device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, 
 }
 
 // ---------------------------------------------------------------- update finalisation (CTA 0)
-__device__ inline void finish_update(const KParams& p, const RunBuf& rb, DevRun* st, int NG) {
+__device__ inline void finish_update(const KParams& p, const RunBuf& rb, DevRun* st, int NG, double* s_cov, double* s_L) {
     const int tid = threadIdx.x, D = p.cp.D, ntri = p.ntri;
-    long long tot = 0;
-#pragma unroll 8
-    for (int g = 0; g < NG; ++g) tot += __ldcg(rb.pcount + g);
+    const long long tot = st->ph_kept;
     const double N = (double)(p.n + tot);
     for (int idx = tid; idx < ntri; idx += blockDim.x) {
         int ai = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
@@ -334,21 +478,22 @@ __device__ inline void finish_update(const KParams& p, const RunBuf& rb, DevRun*
 #pragma unroll 8
         for (int g = 0; g < NG; ++g) s += __ldcg(rb.partial + (size_t)g * p.partial_stride + 1 + D + idx);
         s /= N;  // calculate_covmats divides by N, not N-1 (run_time_info.f90:601-641)
-        rb.cov[ai + bi * D] = s;
-        rb.cov[bi + ai * D] = s;
+        s_cov[ai + bi * D] = s;
+        s_cov[bi + ai * D] = s;
     }
     __syncthreads();
-    if (tid < 32) {
-        int fb = warp_cholesky(rb.cov, rb.chol, D);
-        if (tid == 0) {
-            st->chol_fallback += fb;
-            st->cov_N = N;
-            st->nphantom = tot;
-            st->cur_pool ^= 1;
-            st->nupdates += 1;
-            st->logX_last_update = st->logX;
-            st->update_pending = 0;
-        }
+    int fb = 0;
+    if (tid < 32) fb = warp_cholesky(s_cov, s_L, D);  // calc_cholesky (utils.F90:621-649) in shared memory
+    __syncthreads();
+    for (int e = tid; e < D * D; e += blockDim.x) { rb.cov[e] = s_cov[e]; rb.chol[e] = s_L[e]; }
+    if (tid == 0) {
+        st->chol_fallback += fb;
+        st->cov_N = N;
+        st->nphantom = tot;
+        st->cur_pool ^= 1;
+        st->nupdates += 1;
+        st->logX_last_update = st->logX;
+        st->update_pending = 0;
     }
     __syncthreads();
 }
@@ -379,12 +524,9 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
     unsigned char* s_warp0 = smem + p.off_warp;
     unsigned char* s_warp = s_warp0 + (size_t)warp * p.warp_bytes;
     // CTA-wide scratch of phase S overlays the per-warp area
-    double* sc = (double*)s_warp0;           // 64 doubles
+    const SmemS smS = smem_S(s_warp0, n, p.batch_K);
+    double* sc = smS.sc;
     int* s_cnt = (int*)(smem + p.off_warp - 64 * (int)sizeof(int));
-    int np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    double* skey = sc + 64;
-    int* sval = (int*)(skey + np2);
 
     const int nlp = (p.cp.like_kind == LIKE_GAUSSIAN) ? 2 * D : (p.cp.like_kind == LIKE_CORR ? D + D * D : 0);
     for (int e = tid; e < nlp; e += blockDim.x) s_like[e] = p.like_params[e];
@@ -402,6 +544,8 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
     bool prep_white = false;
     unsigned int wtarget = 0;
     bool have_wtarget = false;
+    unsigned pair_seq = 0;  // paired mode: chains this warp pair has run since the launch (buffer parity)
+    bool s2_due = false;  // CTA 0: the evidence of the generation in flight is still to be accumulated
 
     const bool timer = (tid == 0) && (cta == 0);          // bookkeeping phases
     const bool ctimer = (tid == 0) && (cta == c0);         // chain phases of one representative warp
@@ -414,15 +558,18 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
             long long t1 = clock64();
             bool dump_exit = false;
             if (st->update_pending) {
-                finish_update(p, rb, st, NG);
+                finish_update(p, rb, st, NG, smS.akey, s_chol);
                 dump_exit = p.want_dump != 0;
             }
             long long t2 = clock64();
+            bool evidence_due = false;
             if (dump_exit) {
                 if (tid == 0) st->status = ST_DUMP;
             } else if (vload(&st->status) != ST_ERROR) {
-                phase_S(p, rb, st, sc, skey, sval, np2);
+                evidence_due = phase_S1(p, rb, st, smS);
+                if (evidence_due && c0 == 0) { __syncthreads(); phase_S2(p, rb, st, smS); evidence_due = false; }
             }
+            s2_due = evidence_due;
             __syncthreads();
             if (timer) {
                 long long t3 = clock64();
@@ -435,6 +582,10 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
             if (timer) st->cyc_total += clock64() - t_start;
             return;
         }
+        if (cta == 0 && s2_due) {  // the chains are running: the evidence bookkeeping is off their critical path
+            phase_S2(p, rb, st, smS);
+            s2_due = false;
+        }
 
         // ---------------- phase C: chains, one warp each ----------------
         const int K = vload(&st->K);
@@ -442,12 +593,62 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
         const long long ndead_base = vload(&st->ndead_base), nph_base = vload(&st->nph_base);
         const long long nchains_base = vload(&st->nchains_base);
         const int do_update = vload(&st->do_update);
+        const int* order = rb.order + vload(&st->order_off);
         double* pool = rb.ph[vload(&st->cur_pool)];
         for (int e = tid; e < D * D; e += blockDim.x) s_chol[e] = __ldcg(rb.chol + e);
         __syncthreads();
         unsigned long long nlike = 0, nfail = 0;
         const int m = n - K;
-        if (cta >= c0) {
+        int knext = -1;  // first chain this warp prepares for the next generation
+        if (p.paired) {
+            // Warps w < W/2 run chains, warp w + W/2 is the helper of warp w: it prepares (directions, deck,
+            // uniforms, whitening) the pair's next chain into the other of the pair's two scratch buffers
+            // while the chain warp is slicing, so preparation leaves the critical path.
+            const int HW = W >> 1, pair = warp % HW;
+            const bool helper = warp >= HW;
+            int nmine = 0;
+            if (cta >= c0)
+                for (int li = pair; (cta - c0) + Gc * li < K; li += HW) ++nmine;
+            auto buf = [&](unsigned sq) -> ChainScratch {
+                const int region = pair + HW * (int)(sq & 1u);
+                return chain_scratch(s_warp0 + (size_t)region * p.warp_bytes, D, R, LD, p.nh_in_smem != 0, p.cp.like_kind,
+                                     NPT, rb.nh ? rb.nh + ((size_t)cta * W + region) * R * LD : nullptr);
+            };
+            for (int j = 0; j < nmine; ++j) {
+                const int k = (cta - c0) + Gc * (pair + HW * j);
+                const unsigned long long uid = (unsigned long long)(nchains_base + k);
+                const ChainScratch b = buf(pair_seq + j);
+                if (helper) {
+                    long long th0 = clock64();
+                    if (prep_uid != uid) { prep_chain(D, R, LD, rb.seed, uid, b); prep_white = false; }
+                    if (!prep_white) whiten_chain(D, R, LD, s_chol, b);
+                    prep_uid = ~0ull;
+                    if (lane == 0 && cta == c0 && pair == 0) st->cyc_prep += clock64() - th0;
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");  // hand-over of the buffer
+                if (!helper) {
+                    double u = uniform(rb.seed, TAG_SEED, uid, 0u, 0u);  // GenerateSeed, generate.F90:19-55
+                    int choice = (int)ceil(u * (double)m);
+                    choice = max(1, min(m, choice));
+                    const int src = __ldcg(order + K + choice - 1);
+                    const int dslot = __ldcg(order + k);
+                    double x[DPL];
+#pragma unroll
+                    for (int jj = 0; jj < DPL; ++jj) x[jj] = M.valid(jj) ? __ldcg(rb.live + (size_t)src * T + M.dim(jj)) : 0.0;
+                    // the dying point moves to the dead list before its slot is reused (run_time_info.f90:789-817)
+                    for (int e = lane; e < T; e += 32)
+                        rb.dead[(size_t)(ndead_base + k) * T + e] = __ldcg(rb.live + (size_t)dslot * T + e);
+                    long long tc2 = clock64();
+                    double lfin = slice_chain<G, DPL>(p.cp, M, rb.seed, uid, x, Lstar, b,
+                                                      pool + (size_t)(nph_base + (long long)k * (R - 1)) * T,
+                                                      rb.live + (size_t)dslot * T, nlike);
+                    if (ctimer) st->cyc_slice += clock64() - tc2;
+                    if (!(lfin > Lstar)) ++nfail;
+                }
+            }
+            pair_seq += (unsigned)nmine;
+            if (helper && cta >= c0 && (cta - c0) + Gc * pair < p.batch_K) knext = (cta - c0) + Gc * pair;
+        } else if (cta >= c0) {
             for (int li = warp;; li += W) {
                 const int k = (cta - c0) + Gc * li;
                 if (k >= K) break;
@@ -455,8 +656,8 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                 double u = uniform(rb.seed, TAG_SEED, uid, 0u, 0u);  // GenerateSeed, generate.F90:19-55
                 int choice = (int)ceil(u * (double)m);
                 choice = max(1, min(m, choice));
-                const int src = __ldcg(rb.order + K + choice - 1);
-                const int dslot = __ldcg(rb.order + k);
+                const int src = __ldcg(order + K + choice - 1);
+                const int dslot = __ldcg(order + k);
                 double x[DPL];
 #pragma unroll
                 for (int j = 0; j < DPL; ++j) x[j] = M.valid(j) ? __ldcg(rb.live + (size_t)src * T + M.dim(j)) : 0.0;
@@ -481,6 +682,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                 }
                 if (!(lfin > Lstar)) ++nfail;
             }
+            if (cta != 0 && (cta - c0) + Gc * warp < p.batch_K) knext = (cta - c0) + Gc * warp;
         }
         if (lane == 0) {
             if (nlike) atomicAdd((unsigned long long*)&st->nlike, nlike);
@@ -488,29 +690,38 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
         }
         wtarget = warp_arrive(&st->wbar, GW);
         have_wtarget = true;
-        // the first chain this warp will run in the next generation (if the run goes on with the same K)
-        const int knext = (cta - c0) + Gc * warp;
-        const bool will_chain = cta >= c0 && cta != 0 && knext < p.batch_K;
+        // the scratch the next generation's first chain of this warp (pair) will use
+        const bool will_chain = knext >= 0;
+        const ChainScratch csn = p.paired ? chain_scratch(s_warp0 + (size_t)((warp % (W >> 1)) + (W >> 1) * (int)(pair_seq & 1u)) * p.warp_bytes,
+                                                          D, R, LD, p.nh_in_smem != 0, p.cp.like_kind, NPT,
+                                                          rb.nh ? rb.nh + ((size_t)cta * W + (warp % (W >> 1)) + (W >> 1) * (int)(pair_seq & 1u)) * R * LD : nullptr)
+                                          : cs;
         if (do_update) {
             long long tu0 = clock64();
             warp_wait(&st->wbar, wtarget);
             long long tu1 = clock64();
-            phase_U1(p, rb, st, cta, NG, s_warp0, p.warp_bytes);
+            phase_U1(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt);
+            long long tu2 = clock64();
             group_sync(&st->bar, NG);
+            long long tu3 = clock64();
             phase_U2(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt);
+            long long tu4 = clock64();
             if (cta == 0 && tid == 0) st->update_pending = 1;
             group_sync(&st->bar, NG);
-            if (timer) { st->cyc_wait += tu1 - tu0; st->cyc_U += clock64() - tu1; }
+            if (timer) {
+                st->cyc_wait += tu1 - tu0; st->cyc_U += clock64() - tu1;
+                st->dbg[5] += tu2 - tu1; st->dbg[6] += tu3 - tu2; st->dbg[7] += tu4 - tu3;
+            }
             have_wtarget = false;
             if (will_chain) {  // the Cholesky factor is about to change: whiten after the barrier
                 prep_uid = (unsigned long long)(nchains_base + K + knext);
-                prep_chain(D, R, LD, rb.seed, prep_uid, cs);
+                prep_chain(D, R, LD, rb.seed, prep_uid, csn);
                 prep_white = false;
             }
         } else if (will_chain) {
             prep_uid = (unsigned long long)(nchains_base + K + knext);
-            prep_chain(D, R, LD, rb.seed, prep_uid, cs);
-            whiten_chain(D, R, LD, s_chol, cs);
+            prep_chain(D, R, LD, rb.seed, prep_uid, csn);
+            whiten_chain(D, R, LD, s_chol, csn);
             prep_white = true;
         }
     }
