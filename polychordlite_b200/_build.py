@@ -16,7 +16,7 @@ LIB = LIBDIR / "libchord.so"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "--threads", "4",
+    "-Xcompiler", "-fPIC", "-shared", "--threads", "8",
 ]
 
 

@@ -82,12 +82,13 @@ __device__ __forceinline__ ChainScratch chain_scratch(unsigned char* base, int D
 // Padding lanes (dimension index >= D) carry x = nhat = 0, lo = wid = mu = isig = 0, so they sit inside
 // the cube and add exact zeros to the Gaussian sums: the hot path needs no validity predicates.
 // ------------------------------------------------------------------------------------------
-template <int G, int DPL>
+template <int G, int DPL, int KIND>
 struct Model {
     static constexpr int NPT = 32 / G;
     static constexpr unsigned GMASK = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
     double mu[DPL], isig[DPL], lo[DPL], wid[DPL];
-    int D, P, kind, lane, grp, sub, Dpad;
+    static constexpr int kind = KIND;
+    int D, P, lane, grp, sub, Dpad;
     double logzero, gauss_norm, Vn, log_rast, corr_const;
     const double* s_mu;    // shared memory: mu[D] (Gaussian kinds)
     const double* invcov;  // shared memory, D x D column-major (corr only)
@@ -97,7 +98,7 @@ struct Model {
     __device__ __forceinline__ bool valid(int k) const { return sub + k * G < D; }
 
     __device__ void init(const ChainParams& p, const double* s_like, const double* prior_params, double* warp_dvec) {
-        D = p.D; P = p.P; kind = p.like_kind; lane = threadIdx.x & 31; grp = lane / G; sub = lane % G;
+        D = p.D; P = p.P; lane = threadIdx.x & 31; grp = lane / G; sub = lane % G;
         Dpad = (D + 1) & ~1;
         logzero = p.logzero; gauss_norm = p.gauss_norm; Vn = p.Vn; log_rast = p.log_rast; corr_const = p.corr_const;
         s_mu = s_like;
@@ -133,7 +134,7 @@ struct Model {
 #pragma unroll
         for (int k = 0; k < DPL; ++k) theta[k] = fma(wid[k], y[k], lo[k]);
         double logL;
-        if (kind == LIKE_GAUSSIAN) {  // likelihoods/examples/gaussian.f90:12-41
+        if constexpr (KIND == LIKE_GAUSSIAN) {  // likelihoods/examples/gaussian.f90:12-41
             double a0 = 0.0, a1 = 0.0;
 #pragma unroll
             for (int k = 0; k < DPL; ++k) {
@@ -141,7 +142,7 @@ struct Model {
                 if (k & 1) a1 = fma(z, z, a1); else a0 = fma(z, z, a0);
             }
             logL = -gauss_norm - group_sum(a0 + a1) / 2.0;
-        } else if (kind == LIKE_RASTRIGIN) {  // likelihoods/examples/rastrigin.f90:20-35
+        } else if constexpr (KIND == LIKE_RASTRIGIN) {  // likelihoods/examples/rastrigin.f90:20-35
             const double TwoPi = 6.283185307179586476925286766559;
             double acc = 0.0;
 #pragma unroll
@@ -378,6 +379,11 @@ __device__ inline void whiten_chain(int D, int R, int LD, const double* chol, co
     __syncwarp();
 }
 
+// shrink draws beyond the staged ones (rare): kept out of line so the slice loop stays small in the I-cache
+static __device__ __noinline__ double slow_uniform(unsigned seed, unsigned long long uid, unsigned i, unsigned sidx) {
+    return uniform(seed, TAG_SLICE, uid, i, sidx);
+}
+
 // ------------------------------------------------------------------------------------------
 // slice_chain: R slice steps from x (chordal_sampling.f90:75-90 calling slice_sample :163-273).
 // Babies 0..R-2 go to ph_base + i*T, the last one to last_dst.  Returns the final logL.
@@ -390,51 +396,123 @@ __device__ inline void whiten_chain(int D, int R, int LD, const double* chol, co
 //                   the earlier ones were rejected (a rejected draw becomes the bound on its side, :254-262,
 //                   so the positions do not depend on the likelihoods); the first accepted one is the baby
 // nlike counts exactly the evaluations the sequential algorithm makes (calculate.f90:44).
+//
+// The chain is bound by the latency of dependent FP64 operations (~20 cycles each on sm_100), so along a chord
+// the likelihood argument is kept in chord form: with theta - mu = t*nW + xs (nW = nhat*width,
+// xs = x*width + lo - mu, both formed once per slice) an evaluation at offset t starts with ONE fma per
+// dimension; the cube test y = t*nhat + x runs beside it, and theta itself is only formed for the accepted point.
 // ------------------------------------------------------------------------------------------
-template <int G, int DPL>
-__device__ inline double slice_chain(const ChainParams& p, const Model<G, DPL>& M, unsigned seed, unsigned long long uid,
+template <int G, int DPL, int KIND>
+__device__ inline double slice_chain(const ChainParams& p, const Model<G, DPL, KIND>& M, unsigned seed, unsigned long long uid,
                                      double (&x)[DPL], double Lstar, const ChainScratch& cs, double* ph_base,
-                                     double* last_dst, unsigned long long& nlike) {
+                                     double* last_dst, unsigned long long& nlike, long long* tim = nullptr) {
     constexpr int NPT = 32 / G;
     constexpr int LOG2G = (G == 1) ? 0 : (G == 2) ? 1 : (G == 4) ? 2 : (G == 8) ? 3 : (G == 16) ? 4 : 5;
     constexpr int NS = NPT / 2;                 // bracket points per side and round
     constexpr int SIDE = 16;                    // ballot bits per side (NS * G)
     constexpr int NC = NPT < 4 ? NPT : 4;       // shrink candidates per round
-    const int R = p.R, LD = p.LD, T = p.T;
+    const int R = p.R, LD = p.LD, T = p.T, D = p.D;
     const int lane = threadIdx.x & 31, grp = lane >> LOG2G;
     const int myc = grp < NC ? grp : NC - 1;    // shrink candidate evaluated by this group
+    const int side = NS > 0 ? grp / (NS > 0 ? NS : 1) : 0, idx = grp - side * NS;
+    const double fidx = (double)idx;
     const double logzero = p.logzero;
+    const unsigned gmask = Model<G, DPL, KIND>::GMASK << (grp << LOG2G);
     double logL_cur = logzero;
+    long long tq0 = clock64();
 
     // ballot bits of groups 0..g-1 (the G lanes of a group always vote alike)
-    auto lanes_below = [](int g) -> unsigned {
-        return g > 0 ? (0xffffffffu >> (32 - (g << LOG2G))) : 0u;
-    };
+    auto lanes_below = [](int g) -> unsigned { return g > 0 ? (0xffffffffu >> (32 - (g << LOG2G))) : 0u; };
+
+    // per-dimension constants of the chord form
+    double wdt[DPL], shf[DPL];  // width, lo - mu
+#pragma unroll
+    for (int k = 0; k < DPL; ++k) { wdt[k] = M.wid[k]; shf[k] = M.lo[k] - M.mu[k]; }
 
     for (int i = 0; i < R; ++i) {
         const int c = cs.deck[i];
         const double* q = cs.nh + (size_t)c * LD;
-        double nh[DPL];
+        double nh[DPL], nW[DPL], xs[DPL];
 #pragma unroll
         for (int k = 0; k < DPL; ++k) nh[k] = q[M.dim(k)];  // columns are zero-padded to G*DPL entries
         const double w = cs.wts[c];
         const double* ui = cs.uni + (size_t)i * NU;
         const double u0 = ui[0];
         double dL = u0 * w, dR = (1.0 - u0) * w;  // bracket [x - dL*nhat, x + dR*nhat] (:213-215)
-
-        double y[DPL], th[DPL], l;
-        bool inc;
-        auto eval_t = [&](double tt) -> double {  // this group's point x + tt*nhat
+        if constexpr (KIND == LIKE_GAUSSIAN) {
 #pragma unroll
-            for (int k = 0; k < DPL; ++k) y[k] = fma(tt, nh[k], x[k]);
-            return M.eval(y, th, inc);
+            for (int k = 0; k < DPL; ++k) {  // z = (theta - mu)/sigma = t*nW + xs
+                nW[k] = nh[k] * wdt[k] * M.isig[k];
+                xs[k] = fma(x[k], wdt[k], shf[k]) * M.isig[k];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < DPL; ++k) {  // theta - mu = t*nW + xs
+                nW[k] = nh[k] * wdt[k];
+                xs[k] = fma(x[k], wdt[k], shf[k]);
+            }
+        }
+
+        double y[DPL];
+        // log-likelihood of this group's point x + tt*nhat (calculate_point, calculate.f90:6-50)
+        auto eval_t = [&](double tt) -> double {
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < DPL; ++k) {
+                y[k] = fma(tt, nh[k], x[k]);
+                ok = ok && (y[k] >= 0.0) && (y[k] <= 1.0);
+            }
+            const unsigned bal = __ballot_sync(FULL, ok);
+            double logL;
+            if constexpr (KIND == LIKE_GAUSSIAN) {  // gaussian.f90:12-41
+                double z[DPL];
+#pragma unroll
+                for (int k = 0; k < DPL; ++k) z[k] = fma(tt, nW[k], xs[k]);
+                double a0 = z[0] * z[0], a1 = 0.0;
+                if (DPL > 1) a1 = z[1] * z[1];
+#pragma unroll
+                for (int k = 2; k < DPL; ++k) { if (k & 1) a1 = fma(z[k], z[k], a1); else a0 = fma(z[k], z[k], a0); }
+                logL = fma(M.group_sum(a0 + a1), -0.5, -M.gauss_norm);
+            } else if constexpr (KIND == LIKE_RASTRIGIN) {  // rastrigin.f90:20-35 (mu = 0)
+                const double TwoPi = 6.283185307179586476925286766559;
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < DPL; ++k) {
+                    const double th = fma(tt, nW[k], xs[k]);
+                    acc += M.valid(k) ? M.log_rast + th * th - 10.0 * cos(TwoPi * th) : 0.0;
+                }
+                logL = -M.group_sum(acc);
+            } else {  // utils.F90:1028-1048 log_gauss with a dense inverse covariance
+                double d[DPL], yk[DPL];
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < DPL; ++k) {
+                    d[k] = fma(tt, nW[k], xs[k]);
+                    yk[k] = 0.0;
+                    if (M.valid(k)) M.dvec[M.dim(k)] = d[k];
+                }
+                __syncwarp();
+                for (int cc = 0; cc < D; ++cc) {
+                    const double dc = M.dvec[cc];
+                    const double* col = M.invcov + (size_t)cc * D;
+#pragma unroll
+                    for (int k = 0; k < DPL; ++k)
+                        if (M.valid(k)) yk[k] = fma(col[M.dim(k)], dc, yk[k]);
+                }
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < DPL; ++k) acc += M.valid(k) ? d[k] * yk[k] : 0.0;
+                logL = M.corr_const - M.group_sum(acc) / 2.0;
+            }
+            return ((bal & gmask) == gmask) ? logL : logzero;  // outside the cube the likelihood is not called
         };
 
+        double l;
         // ---------------- bracket (:213-236) ----------------
         if (NPT >= 2) {
-            const int side = grp / NS, idx = grp - side * NS;
+            const double wm = w * fidx;  // this group's step-out multiple
             {
-                const double mult = (idx == 0) ? (side ? dL : dR) : w * (double)idx;
+                const double mult = (idx == 0) ? (side ? dL : dR) : wm;
                 l = eval_t(side ? -mult : mult);
             }
             const unsigned in_raw = __ballot_sync(FULL, l >= Lstar && l > logzero);
@@ -447,8 +525,11 @@ __device__ inline double slice_chain(const ChainParams& p, const Model<G, DPL>& 
                 if (out) {  // the first point outside the contour closes this side
                     const int g = (__ffs(out) - 1) >> LOG2G;
                     nlike += __popc(cnb & lanes_below(g + 1)) >> LOG2G;
-                    if (g > 0) { if (sd) dL = w * (double)g; else dR = w * (double)g; }
-                } else {    // all NS points inside: keep stepping this side, NPT multiples at a time (:223-227)
+                    if (g > 0) {  // the bound is the multiple group g of this side evaluated
+                        const double wg = __shfl_sync(FULL, wm, (sd * NS + g) << LOG2G);
+                        if (sd) dL = wg; else dR = wg;
+                    }
+                } else [[unlikely]] {    // all NS points inside: keep stepping this side, NPT multiples at a time (:223-227)
                     nlike += NS;
                     for (int base = NS;; base += NPT) {
                         const double mult = w * (double)(base + grp);
@@ -493,11 +574,16 @@ __device__ inline double slice_chain(const ChainParams& p, const Model<G, DPL>& 
 #pragma unroll
             for (int cnd = 0; cnd < NC; ++cnd) {
                 const int sidx = 1 + s_done + cnd;
-                const double u = (sidx < NU) ? ui[sidx] : uniform(seed, TAG_SLICE, uid, (unsigned)i, (unsigned)sidx);
+                double u;
+                if (__builtin_expect(sidx < NU, 1)) u = ui[sidx];
+                else u = slow_uniform(seed, uid, (unsigned)i, (unsigned)sidx);
                 const double tc = fma(u, wd, a);
                 if (cnd == myc) tmine = tc;
-                const bool pos = tc > 0.0;  // sign of (baby - x0).nhat picks the bound to move (:254)
-                wd = pos ? tc - a : b - tc;
+                // sign of (baby - x0).nhat picks the bound to move (:254); the sign is read from the high word
+                // (tc > 0 for every positive normal double), both new widths are formed beside the test
+                const bool pos = __double2hiint(tc) > 0;
+                const double wpos = tc - a, wneg = b - tc;
+                wd = pos ? wpos : wneg;
                 a = pos ? a : tc;
                 b = pos ? tc : b;
             }
@@ -522,20 +608,38 @@ __device__ inline double slice_chain(const ChainParams& p, const Model<G, DPL>& 
         // "Non deterministic loglikelihood" (:268-271): after 101 rejected draws the last trial point is kept
         // with logL = logzero.
         const double lnew = accepted ? l_acc : logzero;
-        // The accepting group's registers hold the baby (cube, theta): it writes the record.  Every group
-        // moves to the same point with the same fma, so the chain state stays replicated bit for bit.
+        // The accepting group's registers hold the baby's cube coordinates: it writes the record (theta is
+        // formed here, priors.f90:40-55).  Every group moves to the same point with the same fma, so the chain
+        // state stays replicated bit for bit.
         double* dst = (i == R - 1) ? last_dst : ph_base + (size_t)i * T;
-        M.write_record(dst, g_acc, y, th, Lstar, lnew, inc);
+        if (grp == g_acc) {
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < DPL; ++k) ok = ok && (y[k] >= 0.0) && (y[k] <= 1.0);
+            const bool inc = __all_sync(gmask, ok);
+#pragma unroll
+            for (int k = 0; k < DPL; ++k)
+                if (M.valid(k)) {
+                    dst[M.dim(k)] = y[k];
+                    dst[D + M.dim(k)] = inc ? fma(wdt[k], y[k], M.lo[k]) : 0.0;
+                }
+            if (M.sub == 0) {
+                dst[2 * D + p.P] = Lstar;
+                dst[2 * D + p.P + 1] = lnew;
+            }
+        }
 #pragma unroll
         for (int k = 0; k < DPL; ++k) x[k] = fma(t_acc, nh[k], x[k]);  // next start = this baby even if it failed (:88)
         logL_cur = lnew;
     }
     __syncwarp();
+    long long tq1 = clock64();
     // derived parameters of the R babies, one lane per record
     if (p.P > 0) {
         for (int i = lane; i < R; i += 32) M.finish_derived((i == R - 1) ? last_dst : ph_base + (size_t)i * T, false);
         __syncwarp();
     }
+    if (tim && lane == 0) { tim[0] += tq1 - tq0; tim[1] += clock64() - tq1; }
     return logL_cur;
 }
 

@@ -13,6 +13,7 @@
 #include <limits>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -88,6 +89,15 @@ struct PinnedBuf {
     }
 };
 static PinnedBuf g_pin_dead, g_pin_live;
+static HostCtl* g_ctl = nullptr;          // mapped pinned control block of the asynchronous dumper hand-over
+static cudaStream_t g_copy_stream = nullptr;
+static HostCtl* host_ctl() {
+    if (!g_ctl) {
+        PC_CUDA(cudaHostAlloc((void**)&g_ctl, sizeof(HostCtl), cudaHostAllocMapped | cudaHostAllocPortable));
+        PC_CUDA(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+    }
+    return g_ctl;
+}
 
 template <class V>
 struct DevArr {  // RAII device buffer (exception-transparent: callbacks may throw through the engine)
@@ -198,13 +208,17 @@ static int device_check() {
 }
 
 // (G, DPL): G lanes share one trial point, DPL dimensions per lane; G*DPL >= nDims
-static ShapeFns pick_shape(int D) {
-    if (D <= 8) return shape_fns_4_2();
-    if (D <= 16) return shape_fns_4_4();
-    if (D <= 20) return shape_fns_4_5();
-    if (D <= 32) return shape_fns_4_8();
-    if (D <= 64) return shape_fns_8_8();
-    return shape_fns_16_8();
+static ShapeFns pick_shape(int D, int kind) {
+#define PC_SHAPE(G, DPL)                                                                                     \
+    return kind == PC_LIKE_GAUSSIAN ? shape_fns_##G##_##DPL##_0()                                           \
+                                    : (kind == PC_LIKE_RASTRIGIN ? shape_fns_##G##_##DPL##_1() : shape_fns_##G##_##DPL##_2())
+    if (D <= 8) { PC_SHAPE(4, 2); }
+    if (D <= 16) { PC_SHAPE(4, 4); }
+    if (D <= 20) { PC_SHAPE(4, 5); }
+    if (D <= 32) { PC_SHAPE(4, 8); }
+    if (D <= 64) { PC_SHAPE(8, 8); }
+    PC_SHAPE(16, 8);
+#undef PC_SHAPE
 }
 
 static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const DevModel& dm, int W);
@@ -226,7 +240,7 @@ static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const Dev
     if (D < 1 || D > 128) throw std::invalid_argument("polychord_b200: nDims must be in 1..128");
     if (R < 1) throw std::invalid_argument("polychord_b200: num_repeats must be >= 1");  // settings.f90:216
     if (s.nlive < 2) throw std::invalid_argument("polychord_b200: nlive must be >= 2");
-    L.fn = pick_shape(D);
+    L.fn = pick_shape(D, ms.like_kind);
     const int npt = 32 / L.fn.G;
     k.cp.D = D; k.cp.P = P; k.cp.T = 2 * D + P + 2; k.cp.R = R;
     k.cp.LD = (L.fn.G * L.fn.DPL) | 1;  // odd (bank-conflict free), zero-padded to the lanes' G*DPL dimensions
@@ -279,7 +293,7 @@ static void set_smem(const ShapeFns& fn, size_t smem) {
 // ------------------------------------------------------------------------------------------
 struct HostRun {
     DevArr<DevRun> st;
-    DevArr<double> live, dead, logw, ph0, ph1, chol, cov, partial, nh;
+    DevArr<double> live, live_snap, dead, logw, ph0, ph1, chol, cov, partial, nh;
     DevArr<int> order;
     DevArr<long long> pcount;
     RunBuf buf;
@@ -363,7 +377,7 @@ struct Engine {
             if (!k.nh_in_smem) h.nh.alloc((size_t)G * W * R * k.cp.LD);
             RunBuf& b = h.buf;
             std::memset(&b, 0, sizeof(b));
-            b.st = h.st.p; b.live = h.live.p; b.order = h.order.p; b.dead = h.dead.p; b.logw = h.logw.p;
+            b.st = h.st.p; b.live = h.live.p; b.live_snap = nullptr; b.ctl = nullptr; b.order = h.order.p; b.dead = h.dead.p; b.logw = h.logw.p;
             b.ph[0] = h.ph0.p; b.ph[1] = h.ph1.p; b.chol = h.chol.p; b.cov = h.cov.p; b.partial = h.partial.p;
             b.pcount = h.pcount.p; b.nh = h.nh.p; b.cap_dead = cap_dead; b.cap_ph = cap_ph;
             b.seed = (unsigned)seeds[r];
@@ -384,12 +398,14 @@ struct Engine {
         PC_CUDA(cudaStreamSynchronize(stream));
     }
 
-    void launch() {
+    void launch_async() {
         KParams kp = L.kp;
         void* args[] = {&kp};
         PC_CUDA(cudaEventRecord(ev0, stream));
         PC_CUDA(cudaLaunchCooperativeKernel(L.fn.run, dim3(G * nruns), dim3(L.W * 32), args, L.smem, stream));
         PC_CUDA(cudaEventRecord(ev1, stream));
+    }
+    void launch_finish() {
         PC_CUDA(cudaEventSynchronize(ev1));
         float ms = 0;
         PC_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
@@ -403,26 +419,28 @@ struct Engine {
     }
 
     // dump, nested_sampling.F90:546-590: rows [theta, phi, birth, logL]; normalised posterior log-weights
-    void dump(int r, pc_dumper_t dumper, bool final_dump) {
+    // state: {ndead, logZ, logZ2}; live_src: device records of the live points to report (null: none);
+    // cs: the stream the copies are enqueued on (the copy stream while the run kernel is still sampling)
+    void dump(int r, pc_dumper_t dumper, long long ndead, double logZ_raw, double logZ2_raw, const double* live_src,
+              cudaStream_t cs) {
         HostRun& h = runs[r];
         const KParams& k = L.kp;
         const int T = k.cp.T, D = k.cp.D, P = k.cp.P, n = k.n, npars = D + P + 2;
-        const long long ndead = h.host_st.ndead;
         const long long fresh = ndead - h.mirrored;
-        const int nl = final_dump ? 0 : n;
+        const int nl = live_src ? n : 0;
         // one batch of async copies into pinned staging, one synchronisation
         double* sd = fresh > 0 ? (double*)g_pin_dead.need((size_t)fresh * (T + 1) * 8) : nullptr;
         double* sl = nl > 0 ? (double*)g_pin_live.need((size_t)n * T * 8) : nullptr;
         if (fresh > 0) {
-            h.dead.download(sd, (size_t)fresh * T, stream, (size_t)h.mirrored * T);
-            h.logw.download(sd + (size_t)fresh * T, fresh, stream, h.mirrored);
+            h.dead.download(sd, (size_t)fresh * T, cs, (size_t)h.mirrored * T);
+            h.logw.download(sd + (size_t)fresh * T, fresh, cs, h.mirrored);
             d2h += fresh * (T + 1) * 8;
         }
         if (nl > 0) {
-            h.live.download(sl, (size_t)n * T, stream);
+            PC_CUDA(cudaMemcpyAsync(sl, live_src, (size_t)n * T * 8, cudaMemcpyDeviceToHost, cs));
             d2h += (long long)n * T * 8;
         }
-        PC_CUDA(cudaStreamSynchronize(stream));
+        PC_CUDA(cudaStreamSynchronize(cs));
         if (fresh > 0) {
             const double* lwp = sd + (size_t)fresh * T;
             h.dead_rows.resize((size_t)ndead * npars);
@@ -453,8 +471,8 @@ struct Engine {
             double lse = m + std::log(sum);
             for (long long i = 0; i < ndead; ++i) lw[i] = h.dead_logw[i] - lse;
         }
-        double lz = std::max(-std::numeric_limits<double>::max(), 2 * h.host_st.logZ - 0.5 * h.host_st.logZ2);
-        double var = h.host_st.logZ2 - 2 * h.host_st.logZ;
+        double lz = std::max(-std::numeric_limits<double>::max(), 2 * logZ_raw - 0.5 * logZ2_raw);
+        double var = logZ2_raw - 2 * logZ_raw;
         std::vector<double> dummy(npars, 0.0);
         dumper((int)ndead, nl, npars, live_rows.data(), ndead > 0 ? h.dead_rows.data() : dummy.data(), lw.data(), lz,
                std::sqrt(var));
@@ -483,22 +501,62 @@ struct Engine {
 
     void run(pc_dumper_t dumper, pc_run_info* out) {
         auto t0 = std::chrono::steady_clock::now();
-        L.kp.want_dump = (dumper != nullptr && nruns == 1) ? 1 : 0;
+        volatile HostCtl* ctl = nullptr;
+        unsigned long long handled = 0;
+        if (dumper != nullptr && nruns == 1) {  // asynchronous dumper hand-over
+            HostCtl* c = host_ctl();
+            std::memset(c, 0, sizeof(*c));
+            ctl = c;
+            HostRun& h = runs[0];
+            h.live_snap.alloc((size_t)L.kp.n * L.kp.cp.T);
+            h.buf.live_snap = h.live_snap.p;
+            HostCtl* dctl = nullptr;
+            PC_CUDA(cudaHostGetDevicePointer((void**)&dctl, c, 0));
+            h.buf.ctl = dctl;
+            upload_bufs();
+        }
+        L.kp.want_dump = ctl ? 1 : 0;
+        auto service = [&]() {  // hand one published dump to the user's dumper
+            const long long nd = ctl->ndead;
+            const double lz = ctl->logZ, lz2 = ctl->logZ2;
+            dump(0, dumper, nd, lz, lz2, runs[0].live_snap.p, g_copy_stream);
+            ++handled;
+            ctl->ack_seq = handled;
+        };
         for (;;) {
-            launch();
+            if (ctl) {  // size the pinned staging now: (re)allocating pinned memory synchronises with the running kernel
+                g_pin_dead.need((size_t)runs[0].buf.cap_dead * (L.kp.cp.T + 1) * 8);
+                g_pin_live.need((size_t)L.kp.n * L.kp.cp.T * 8);
+            }
+            launch_async();
+            if (ctl) {
+                try {
+                    while (cudaEventQuery(ev1) == cudaErrorNotReady) {
+                        if (ctl->dump_seq > handled) service();
+                        else std::this_thread::yield();
+                    }
+                    while (ctl->dump_seq > handled) service();
+                } catch (...) {  // the dumper threw (e.g. a Python exception): release the kernel, then unwind
+                    ctl->abort = 1;
+                    cudaEventSynchronize(ev1);
+                    throw;
+                }
+            }
+            launch_finish();
             bool all_done = true, regrow = false;
             for (int r = 0; r < nruns; ++r) {
                 int stt = runs[r].host_st.status;
                 if (stt == ST_ERROR) throw std::runtime_error("polychord_b200: could not generate live points (likelihood <= logzero everywhere?)");
+                if (stt == ST_DUMP) throw std::runtime_error("polychord_b200: run aborted");
                 if (stt == ST_NEED_DEAD || stt == ST_NEED_PHANTOM) { grow(r, stt); regrow = true; }
-                if (stt == ST_DUMP && dumper) dump(r, dumper, false);
                 if (stt != ST_DONE) all_done = false;
             }
             if (regrow) upload_bufs();
             if (all_done) break;
         }
-        if (dumper)
-            for (int r = 0; r < nruns; ++r) dump(r, dumper, true);
+        if (dumper)  // the final call: every point is dead (nested_sampling.F90:392)
+            for (int r = 0; r < nruns; ++r)
+                dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, nullptr, stream);
         auto t1 = std::chrono::steady_clock::now();
         const KParams& k = L.kp;
         for (int r = 0; r < nruns; ++r) {
@@ -675,7 +733,11 @@ static int run_common(const pc_settings* s, const ModelSpec& ms, int nruns, cons
     auto t0 = std::chrono::steady_clock::now();
     Engine e;
     e.setup(*s, ms, nruns, seeds);
+    auto t1 = std::chrono::steady_clock::now();
     e.run(dumper, out);
+    if (std::getenv("PC_DEBUG"))
+        std::fprintf(stderr, "[pc dbg] setup %.3f ms, run %.3f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
     const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     for (int r = 0; r < nruns; ++r) out[r].wall_ms = wall;  // entry to return, set-up included
     g_last = out[0];

@@ -61,9 +61,23 @@ struct DevRun {
     unsigned int wbar;   // chains-done barrier, one arrival per warp (monotonic)
 };
 
+// Control block in mapped pinned host memory: the run kernel publishes a dump (run state + a snapshot of the
+// live points) at every update and keeps sampling; the host thread that called the engine picks it up, copies
+// the new dead rows on a second stream and calls the user's dumper.  One dump may be outstanding.
+struct HostCtl {
+    unsigned long long dump_seq;   // device -> host: dumps published
+    unsigned long long ack_seq;    // host -> device: dumps consumed (the live snapshot may be overwritten)
+    long long ndead;               // state at the published dump
+    double logZ, logZ2;
+    int abort;                     // host -> device: stop waiting (the dumper threw)
+    int pad;
+};
+
 struct RunBuf {
     DevRun* st;
     double* live;      // n x T records
+    double* live_snap; // n x T: copy of the live points at the last published dump
+    HostCtl* ctl;      // mapped host memory, or null (no dumper)
     int* order;        // 2 x n: live slots sorted by (logL, slot), ping-pong (DevRun::order_off)
     double* dead;      // cap_dead x T
     double* logw;      // cap_dead

@@ -10,8 +10,8 @@ __device__ __forceinline__ V vload(const V* p) { return *(const volatile V*)p; }
 // ---------------------------------------------------------------- initial live points (K1)
 // GenerateLivePoints, generate.F90:153-183: attempt a draws cube = U(TAG_INIT, a, dim), accepted
 // (in attempt order) when logL > logzero.  One attempt per point group.
-template <int G, int DPL>
-__device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st, const Model<G, DPL>& M, int cta,
+template <int G, int DPL, int KIND>
+__device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st, const Model<G, DPL, KIND>& M, int cta,
                                   int NG, double* sc) {
     constexpr int NPT = 32 / G;
     const int tid = threadIdx.x, W = blockDim.x >> 5, gw = cta * W + (tid >> 5), GW = NG * W;
@@ -228,7 +228,7 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
         st->do_update = (lX_new <= st->logX_last_update + p.log_comp) ? 1 : 0;  // nested_sampling.F90:321
         st->status = ST_RUNNING;
         long long q4 = clock64();
-        st->dbg[0] += q1 - q0; st->dbg[1] += q2 - q1; st->dbg[2] += q3 - q2; st->dbg[3] += q4 - q3;
+        
     }
     return true;
 }
@@ -238,7 +238,7 @@ __device__ inline void phase_S2(const KParams& p, const RunBuf& rb, DevRun* st, 
     long long q0 = clock64();
     const int K = st->K;
     evidence_deaths(st, sm.kkey, K, p.n, rb.logw + st->ndead_base, sm.sc);
-    if (threadIdx.x == 0) st->dbg[4] += clock64() - q0;
+    
 }
 
 // ---------------------------------------------------------------- phase U
@@ -498,6 +498,36 @@ __device__ inline void finish_update(const KParams& p, const RunBuf& rb, DevRun*
     __syncthreads();
 }
 
+// ---------------------------------------------------------------- dump hand-over (CTA 0)
+// dump (nested_sampling.F90:546-590) is called at every update (:335).  The kernel does not stop for it: it
+// waits until the host has consumed the previous dump, snapshots the live points, publishes the state through
+// the mapped control block and goes on.  Returns true when the host asked to abort.
+__device__ inline bool publish_dump(const KParams& p, const RunBuf& rb, DevRun* st) {
+    __shared__ int s_abort;
+    volatile HostCtl* ctl = rb.ctl;
+    if (threadIdx.x == 0) {
+        const unsigned long long seq = ctl->dump_seq;
+        int ab = 0;
+        while (ctl->ack_seq < seq && !(ab = ctl->abort)) __nanosleep(200);
+        s_abort = ab;
+    }
+    __syncthreads();
+    if (s_abort) return true;
+    const size_t nd = (size_t)p.n * p.cp.T;
+    for (size_t e = threadIdx.x; e < nd; e += blockDim.x) rb.live_snap[e] = __ldcg(rb.live + e);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ctl->ndead = st->ndead;
+        ctl->logZ = st->logZ;
+        ctl->logZ2 = st->logZ2;
+        __threadfence_system();
+        ctl->dump_seq = ctl->dump_seq + 1;
+        __threadfence_system();
+    }
+    __syncthreads();
+    return false;
+}
+
 // ---------------------------------------------------------------- the persistent run kernel
 //
 // One generation, seen from a warp (NG = CTAs of the run's group, GW = NG * warps):
@@ -506,7 +536,7 @@ __device__ inline void finish_update(const KParams& p, const RunBuf& rb, DevRun*
 // so the counter-addressed direction/uniform preparation of a chain overlaps the bookkeeping of CTA 0
 // and the wait for the slowest chain.  Generations at the update cadence insert phase U (all CTAs)
 // between the arrival and the bookkeeping.
-template <int G, int DPL>
+template <int G, int DPL, int KIND>
 __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NPT = 32 / G;
@@ -534,10 +564,10 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
 
     const ChainScratch cs = chain_scratch(s_warp, D, R, LD, p.nh_in_smem != 0, p.cp.like_kind, NPT,
                                           rb.nh ? rb.nh + (size_t)gw * R * LD : nullptr);
-    Model<G, DPL> M;
+    Model<G, DPL, KIND> M;
     M.init(p.cp, s_like, p.prior_params, cs.dvec);
 
-    if (!vload(&st->initialised)) init_phase<G, DPL>(p, rb, st, M, cta, NG, sc);
+    if (!vload(&st->initialised)) init_phase<G, DPL, KIND>(p, rb, st, M, cta, NG, sc);
 
     // chain whose directions currently sit in this warp's scratch (~0 = none), and whether they are whitened
     unsigned long long prep_uid = ~0ull;
@@ -559,7 +589,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
             bool dump_exit = false;
             if (st->update_pending) {
                 finish_update(p, rb, st, NG, smS.akey, s_chol);
-                dump_exit = p.want_dump != 0;
+                if (rb.ctl) dump_exit = publish_dump(p, rb, st);
             }
             long long t2 = clock64();
             bool evidence_due = false;
@@ -639,9 +669,10 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                     for (int e = lane; e < T; e += 32)
                         rb.dead[(size_t)(ndead_base + k) * T + e] = __ldcg(rb.live + (size_t)dslot * T + e);
                     long long tc2 = clock64();
-                    double lfin = slice_chain<G, DPL>(p.cp, M, rb.seed, uid, x, Lstar, b,
+                    double lfin = slice_chain<G, DPL, KIND>(p.cp, M, rb.seed, uid, x, Lstar, b,
                                                       pool + (size_t)(nph_base + (long long)k * (R - 1)) * T,
-                                                      rb.live + (size_t)dslot * T, nlike);
+                                                      rb.live + (size_t)dslot * T, nlike,
+                                                      (cta == c0 && warp == 0) ? st->dbg : nullptr);
                     if (ctimer) st->cyc_slice += clock64() - tc2;
                     if (!(lfin > Lstar)) ++nfail;
                 }
@@ -673,7 +704,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                 if (!prep_white) whiten_chain(D, R, LD, s_chol, cs);
                 prep_uid = ~0ull;
                 long long tc2 = clock64();
-                double lfin = slice_chain<G, DPL>(p.cp, M, rb.seed, uid, x, Lstar, cs,
+                double lfin = slice_chain<G, DPL, KIND>(p.cp, M, rb.seed, uid, x, Lstar, cs,
                                                   pool + (size_t)(nph_base + (long long)k * (R - 1)) * T,
                                                   rb.live + (size_t)dslot * T, nlike);
                 if (ctimer) {
@@ -710,7 +741,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
             group_sync(&st->bar, NG);
             if (timer) {
                 st->cyc_wait += tu1 - tu0; st->cyc_U += clock64() - tu1;
-                st->dbg[5] += tu2 - tu1; st->dbg[6] += tu3 - tu2; st->dbg[7] += tu4 - tu3;
+                
             }
             have_wtarget = false;
             if (will_chain) {  // the Cholesky factor is about to change: whiten after the barrier
@@ -729,7 +760,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
 
 // ---------------------------------------------------------------- probes
 // SliceSampling for explicit (seed point, contour, uid) triples; one warp per chain.
-template <int G, int DPL>
+template <int G, int DPL, int KIND>
 __global__ void __launch_bounds__(256, 1) pc_slice_chains_kernel(const __grid_constant__ KParams p, int nchains,
                                                                  const double* seed_points, const double* chol,
                                                                  const double* logL, const unsigned long long* uid,
@@ -749,7 +780,7 @@ __global__ void __launch_bounds__(256, 1) pc_slice_chains_kernel(const __grid_co
     const int gw = blockIdx.x * W + warp;
     const ChainScratch cs = chain_scratch(s_warp, D, R, LD, p.nh_in_smem != 0, p.cp.like_kind, NPT,
                                           nh_global ? nh_global + (size_t)gw * R * LD : nullptr);
-    Model<G, DPL> M;
+    Model<G, DPL, KIND> M;
     M.init(p.cp, s_like, p.prior_params, cs.dvec);
     for (int c = gw; c < nchains; c += gridDim.x * W) {
         double x[DPL];
@@ -759,12 +790,12 @@ __global__ void __launch_bounds__(256, 1) pc_slice_chains_kernel(const __grid_co
         double* out = babies + (size_t)c * R * T;
         prep_chain(D, R, LD, seed, uid[c], cs);
         whiten_chain(D, R, LD, s_chol, cs);
-        slice_chain<G, DPL>(p.cp, M, seed, uid[c], x, logL[c], cs, out, out + (size_t)(R - 1) * T, nl);
+        slice_chain<G, DPL, KIND>(p.cp, M, seed, uid[c], x, logL[c], cs, out, out + (size_t)(R - 1) * T, nl);
         if (lane == 0) nlike_out[c] = (long long)nl;
     }
 }
 
-template <int G, int DPL>
+template <int G, int DPL, int KIND>
 __global__ void pc_calculate_points_kernel(const __grid_constant__ KParams p, double* records, int npts, int* nlike) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NPT = 32 / G;
@@ -776,7 +807,7 @@ __global__ void pc_calculate_points_kernel(const __grid_constant__ KParams p, do
     for (int e = tid; e < nlp; e += blockDim.x) s_like[e] = p.like_params[e];
     __syncthreads();
     const ChainScratch cs = chain_scratch(s_warp, D, R, LD, p.nh_in_smem != 0, p.cp.like_kind, NPT, nullptr);
-    Model<G, DPL> M;
+    Model<G, DPL, KIND> M;
     M.init(p.cp, s_like, p.prior_params, cs.dvec);
     int cnt = 0;
     for (int c0 = (blockIdx.x * W + warp) * NPT; c0 < npts; c0 += gridDim.x * W * NPT) {

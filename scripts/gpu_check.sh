@@ -8,15 +8,15 @@ nproc > gpurun_out/host.txt; lscpu | grep -E 'Model name|^CPU\(s\)' >> gpurun_ou
 for stage in "$@"; do
 case $stage in
 tests)
-  timeout -s KILL 900 python -m pytest tests -m gpu -q -x --timeout 600 2>&1 | tail -60 > gpurun_out/pytest_gpu.log
+  timeout -s KILL 300 python -m pytest tests -m gpu -q -x --timeout 120 2>&1 | tail -60 > gpurun_out/pytest_gpu.log
   tail -25 gpurun_out/pytest_gpu.log ;;
 tests_all)
-  timeout -s KILL 1200 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -150 > gpurun_out/pytest_gpu.log
+  timeout -s KILL 400 python -m pytest tests -m gpu -q --timeout 120 2>&1 | tail -150 > gpurun_out/pytest_gpu.log
   tail -60 gpurun_out/pytest_gpu.log ;;
 smoke)
-  timeout -s KILL 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -5 gpurun_out/smoke.log ;;
+  timeout -s KILL 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -5 gpurun_out/smoke.log ;;
 bench)
-  timeout -s KILL 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err ;;
+  timeout -s KILL 300 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err ;;
 bench_ref)
   timeout -s KILL 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json ;;
 ncu_list)
