@@ -338,7 +338,7 @@ def main():
                     "ms_per_step": 1e3 * e_t_max / args.steps, "dumper_calls": sink["calls"]},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": which, "kernel": "pc_run_kernel<1>",
+                         "traffic": None, "peak_source": which, "kernel": "pc_run_kernel<4,5,0>",
                          "note": "latency-bound persistent kernel; one run occupies ctas_per_run of 148 SMs; "
                                  "see 'ensemble' for the GPU filled with independent replicas"},
             "cpu_baseline": cpu, "clocks": clocks, "ensemble": ens, "region_wall_s": t_region,

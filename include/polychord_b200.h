@@ -106,6 +106,10 @@ void pc_uniform_prior(double* cube, double* theta, int nDims); /* theta = lo + (
  *   "max_ctas"        cap on the CTAs of one run (default 0 = one warp per chain)
  *   "errors_return"   1: configuration errors return instead of exit(1)
  *   "nh_global"       1: keep the direction scratch in global memory even when it fits in shared memory
+ *   "sync_dump"       1: the run kernel exits at every update, the host calls the dumper and relaunches
+ *                     (also: environment PC_SYNC_DUMP).  Default 0: dumps are handed to the host through a
+ *                     mapped control block while the kernel keeps sampling.  Needed under profilers that
+ *                     serialise kernel launches (the host cannot acknowledge a dump from inside the launch call).
  *   "no_pairing"      1: do not use helper warps for the direction preparation (a run alone on the device
  *                     normally pairs every chain warp with a helper warp)
  *   "cap_dead0", "cap_ph0"  initial capacity (records) of the dead / phantom pools; 0 = automatic.

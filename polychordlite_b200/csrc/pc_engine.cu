@@ -134,6 +134,7 @@ struct Options {
     int errors_return = 0;
     int nh_global = 0;  // force the direction scratch into global memory (testing)
     int no_pairing = 0; // keep the helper-warp preparation off (testing)
+    int sync_dump = 0;  // the kernel exits at every update for the dumper instead of handing dumps over while running
     long long cap_dead0 = 0, cap_ph0 = 0;  // initial pool capacities in records (0 = automatic)
 };
 static Options g_opt;
@@ -503,7 +504,8 @@ struct Engine {
         auto t0 = std::chrono::steady_clock::now();
         volatile HostCtl* ctl = nullptr;
         unsigned long long handled = 0;
-        if (dumper != nullptr && nruns == 1) {  // asynchronous dumper hand-over
+        const bool sync_dump = g_opt.sync_dump || std::getenv("PC_SYNC_DUMP");
+        if (dumper != nullptr && nruns == 1 && !sync_dump) {  // asynchronous dumper hand-over
             HostCtl* c = host_ctl();
             std::memset(c, 0, sizeof(*c));
             ctl = c;
@@ -515,7 +517,7 @@ struct Engine {
             h.buf.ctl = dctl;
             upload_bufs();
         }
-        L.kp.want_dump = ctl ? 1 : 0;
+        L.kp.want_dump = (dumper != nullptr && nruns == 1) ? 1 : 0;
         auto service = [&]() {  // hand one published dump to the user's dumper
             const long long nd = ctl->ndead;
             const double lz = ctl->logZ, lz2 = ctl->logZ2;
@@ -547,7 +549,9 @@ struct Engine {
             for (int r = 0; r < nruns; ++r) {
                 int stt = runs[r].host_st.status;
                 if (stt == ST_ERROR) throw std::runtime_error("polychord_b200: could not generate live points (likelihood <= logzero everywhere?)");
-                if (stt == ST_DUMP) throw std::runtime_error("polychord_b200: run aborted");
+                if (stt == ST_DUMP && ctl) throw std::runtime_error("polychord_b200: run aborted");
+                if (stt == ST_DUMP)  // sync_dump: the kernel left at the update, dump and relaunch
+                    dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, runs[r].live.p, stream);
                 if (stt == ST_NEED_DEAD || stt == ST_NEED_PHANTOM) { grow(r, stt); regrow = true; }
                 if (stt != ST_DONE) all_done = false;
             }
@@ -633,6 +637,7 @@ int pc_set_option(const char* name, double value) {
     else if (s == "errors_return") g_opt.errors_return = (int)value;
     else if (s == "nh_global") g_opt.nh_global = (int)value;
     else if (s == "no_pairing") g_opt.no_pairing = (int)value;
+    else if (s == "sync_dump") g_opt.sync_dump = (int)value;
     else if (s == "cap_dead0") g_opt.cap_dead0 = (long long)value;
     else if (s == "cap_ph0") g_opt.cap_ph0 = (long long)value;
     else return -1;
@@ -648,6 +653,7 @@ double pc_get_option(const char* name) {
     if (s == "errors_return") return g_opt.errors_return;
     if (s == "nh_global") return g_opt.nh_global;
     if (s == "no_pairing") return g_opt.no_pairing;
+    if (s == "sync_dump") return g_opt.sync_dump;
     if (s == "cap_dead0") return (double)g_opt.cap_dead0;
     if (s == "cap_ph0") return (double)g_opt.cap_ph0;
     return NAN;

@@ -589,7 +589,8 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
             bool dump_exit = false;
             if (st->update_pending) {
                 finish_update(p, rb, st, NG, smS.akey, s_chol);
-                if (rb.ctl) dump_exit = publish_dump(p, rb, st);
+                if (rb.ctl) dump_exit = publish_dump(p, rb, st);   // the kernel keeps running
+                else if (p.want_dump) dump_exit = true;              // "sync_dump": leave, the host dumps and relaunches
             }
             long long t2 = clock64();
             bool evidence_due = false;

@@ -20,11 +20,13 @@ bench)
 bench_ref)
   timeout -s KILL 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json ;;
 ncu_list)
-  timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+  PC_SYNC_DUMP=1 timeout -s KILL 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 1 --ensemble 0 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1; tail -3 gpurun_out/ncu_list.log ;;
 ncu_full)
-  timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:pc_run_kernel -c 2 -f -o gpurun_out/prof \
-      python bench.py --steps 1 --warmup 0 --ensemble 0 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log ;;
+  # only the first launch (the device-resident run): a launch that hands dumps to the host cannot be replayed
+  # by ncu (the replay passes run inside the intercepted launch call, the host never gets to acknowledge)
+  timeout -s KILL 240 ncu --set full --clock-control none --import-source on -k regex:pc_run_kernel -c 1 -f -o gpurun_out/prof \
+      python scripts/one_run.py > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log ;;
 *) bash -c "$stage" ;;
 esac
 done
