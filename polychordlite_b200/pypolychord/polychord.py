@@ -1,0 +1,160 @@
+"""run() / run_polychord(): the reference's Python entry points (pypolychord/polychord.py:16 and :221)
+on top of the B200 engine's C ABI.
+
+Differences from the reference, all forced by scope:
+  * the loglikelihood must have a device form (`pypolychord.builtin.*`) and the prior must be the default
+    unit-cube prior or a `UniformPrior`; arbitrary Python callables need the generic host-callback path
+    (row f2, not built yet) and raise NotImplementedError with that explanation;
+  * no files are written yet (row f1); the return value is an in-memory `NestedSamplesLite` built from the
+    final dumper call instead of `anesthetic.read_chains(...)`.
+Everything else -- keyword names, defaults, TypeError on unknown keywords, ValueError when grade_dims does
+not sum to nDims, creation of base_dir/cluster_dir, the paramnames file, the dumper signature -- follows the
+reference line by line (polychord.py:520-595).
+"""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from .. import _capi
+from . import builtin as _builtin
+from .output import NestedSamplesLite, make_paramnames_file
+from .priors import UniformPrior
+
+
+def default_prior(cube):
+    return cube.copy()
+
+
+def default_dumper(live, dead, logweights, logZ, logZerr):
+    pass
+
+
+_ARGTYPES = ([C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_bool, C.c_int, C.c_double,
+              C.c_double, C.c_int, C.c_double] + [C.c_bool] * 11 +
+             [C.c_double, C.c_bool, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_double),
+              C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)])
+
+
+def _view(ptr, shape):
+    """zero-copy float64 view of engine-owned memory (what the reference's shim does with
+    PyArray_SimpleNewFromData, _pypolychord.cpp:88-94)"""
+    n = int(np.prod(shape))
+    if n == 0:
+        return np.zeros(shape)
+    buf = (C.c_double * n).from_address(C.addressof(ptr.contents))
+    return np.frombuffer(buf, dtype=np.float64).reshape(shape)
+
+
+def run(loglikelihood, nDims, **kwargs):
+    paramnames = kwargs.pop('paramnames', None)
+    default_kwargs = {
+        'nDerived': 0, 'prior': default_prior, 'dumper': default_dumper, 'nlive': nDims * 25,
+        'num_repeats': nDims * 5, 'nprior': -1, 'nfail': -1, 'do_clustering': True, 'feedback': 1,
+        'precision_criterion': 0.001, 'logzero': -1e30, 'max_ndead': -1, 'boost_posterior': 0.0,
+        'posteriors': True, 'equals': True, 'cluster_posteriors': True, 'write_resume': True,
+        'write_paramnames': False, 'read_resume': True, 'write_stats': True, 'write_live': True,
+        'write_dead': True, 'write_prior': True, 'maximise': False, 'compression_factor': np.exp(-1),
+        'synchronous': True, 'base_dir': 'chains', 'file_root': 'test', 'cluster_dir': 'clusters',
+        'grade_dims': [nDims], 'nlives': {}, 'seed': -1,
+    }
+    default_kwargs['grade_frac'] = ([1.0] * len(default_kwargs['grade_dims']) if 'grade_dims' not in kwargs
+                                    else [1.0] * len(kwargs['grade_dims']))
+    if not kwargs.keys() <= default_kwargs.keys():
+        raise TypeError(f"{__name__} got unknown keyword arguments: {kwargs.keys() - default_kwargs.keys()}")
+    default_kwargs.update(kwargs)
+    kwargs = default_kwargs
+
+    (Path(kwargs['base_dir']) / kwargs['cluster_dir']).mkdir(parents=True, exist_ok=True)
+    if paramnames is not None:
+        make_paramnames_file(paramnames, Path(kwargs['base_dir']) / (kwargs['file_root'] + ".paramnames"))
+
+    kwargs['grade_dims'] = [int(d) for d in list(kwargs['grade_dims'])]
+    if sum(kwargs['grade_dims']) != nDims:
+        raise ValueError(f"grade_dims ({sum(kwargs['grade_dims'])}) must sum to nDims ({nDims})")
+    kwargs['nlives'] = {float(logL): int(nlive) for logL, nlive in kwargs['nlives'].items()}
+
+    L = _capi.lib()
+    nDerived = int(kwargs['nDerived'])
+    # ---- loglikelihood / prior -> device forms --------------------------------------------------
+    if not isinstance(loglikelihood, _builtin._DeviceLikelihood):
+        raise NotImplementedError(
+            "this engine runs the sampling loop on the GPU and needs a likelihood with a device form "
+            "(polychordlite_b200.pypolychord.builtin.Gaussian / Rastrigin / CorrelatedGaussian, or "
+            "pc_register_device_likelihood from C); the generic host-callback path for arbitrary Python "
+            "callables is not built yet (SURVEY.md section 8 row f2)")
+    like_fn = loglikelihood.register(nDims)
+    prior = kwargs['prior']
+    if prior is default_prior:
+        prior_fn = C.cast(L.pc_unit_prior, _capi.PRIOR_CB)
+    elif isinstance(prior, UniformPrior) and getattr(prior, 'device_params', None) is not None:
+        prior_fn = C.cast(L.pc_uniform_prior, _capi.PRIOR_CB)
+        pp = np.ascontiguousarray(prior.device_params(nDims), dtype=np.float64)
+        if L.pc_register_device_prior(prior_fn, 0, pp.ctypes.data_as(C.POINTER(C.c_double)), pp.size) != 0:
+            raise RuntimeError("pc_register_device_prior failed")
+    else:
+        raise NotImplementedError(
+            "only the unit-cube default prior and UniformPrior have a device form; other priors need the "
+            "generic host-callback path (SURVEY.md section 8 row f2, not built yet)")
+
+    # ---- dumper: the user's callable plus the in-memory result ------------------------------------
+    last = {}
+    user_dumper = kwargs['dumper']
+
+    def _dumper(ndead, nlive, npars, live, dead, logweights, logZ, logZerr):
+        lv, dd, lw = _view(live, (nlive, npars)), _view(dead, (ndead, npars)), _view(logweights, (ndead,))
+        if nlive == 0:  # the final call: every point is dead (nested_sampling.F90:392)
+            last.update(dead=dd.copy(), logweights=lw.copy(), logZ=logZ, logZerr=logZerr)
+        user_dumper(lv, dd, lw, logZ, logZerr)
+
+    dcb = _capi.DUMPER_CB(_dumper)
+    ngrade = len(kwargs['grade_dims'])
+    grade_frac = (C.c_double * ngrade)(*[float(f) for f in kwargs['grade_frac']])
+    grade_dims = (C.c_int * ngrade)(*kwargs['grade_dims'])
+    nl = sorted(kwargs['nlives'].items())
+    loglikes = (C.c_double * max(len(nl), 1))(*[k for k, _ in nl])
+    nlives = (C.c_int * max(len(nl), 1))(*[v for _, v in nl])
+    comm = C.c_int(0)
+    L.polychord_c_interface.restype = None
+    L.polychord_c_interface.argtypes = _ARGTYPES
+    # the reference convention for fatal configuration errors is a banner and exit(1) (abort.F90:19-29);
+    # under Python report them as exceptions instead
+    old_err = _capi.get_option("errors_return")
+    _capi.set_option("errors_return", 1)
+    try:
+        _call(L, like_fn, prior_fn, dcb, kwargs, nDims, nDerived, ngrade, grade_frac, grade_dims, nl, loglikes,
+              nlives, comm)
+    finally:
+        _capi.set_option("errors_return", old_err)
+    info = _capi.last_run_info()
+    if info.status != 0 or not last:
+        raise RuntimeError(f"polychord_c_interface failed (status {info.status}); see the message on stderr")
+    return NestedSamplesLite(last['dead'], last['logweights'], last['logZ'], last['logZerr'], nDims, nDerived,
+                             info=info.as_dict())
+
+
+def _call(L, like_fn, prior_fn, dcb, kwargs, nDims, nDerived, ngrade, grade_frac, grade_dims, nl, loglikes, nlives,
+          comm):
+    L.polychord_c_interface(
+        C.cast(like_fn, C.c_void_p), C.cast(prior_fn, C.c_void_p), C.cast(dcb, C.c_void_p),
+        int(kwargs['nlive']), int(kwargs['num_repeats']), int(kwargs['nprior']), int(kwargs['nfail']),
+        bool(kwargs['do_clustering']), int(kwargs['feedback']), float(kwargs['precision_criterion']),
+        float(kwargs['logzero']), int(kwargs['max_ndead']), float(kwargs['boost_posterior']),
+        bool(kwargs['posteriors']), bool(kwargs['equals']), bool(kwargs['cluster_posteriors']),
+        bool(kwargs['write_resume']), bool(kwargs['write_paramnames']), bool(kwargs['read_resume']),
+        bool(kwargs['write_stats']), bool(kwargs['write_live']), bool(kwargs['write_dead']),
+        bool(kwargs['write_prior']), bool(kwargs['maximise']), float(kwargs['compression_factor']),
+        bool(kwargs['synchronous']), int(nDims), nDerived, str(kwargs['base_dir']).encode(),
+        str(kwargs['file_root']).encode(), ngrade, grade_frac, grade_dims, len(nl), loglikes, nlives,
+        int(kwargs['seed']), C.byref(comm))
+
+
+def run_polychord(loglikelihood, nDims, nDerived, settings, prior=default_prior, dumper=default_dumper):
+    """Legacy entry point (polychord.py:16): settings object instead of keywords."""
+    kw = {k: getattr(settings, k) for k in (
+        'nlive', 'num_repeats', 'nprior', 'nfail', 'do_clustering', 'feedback', 'precision_criterion', 'logzero',
+        'max_ndead', 'boost_posterior', 'posteriors', 'equals', 'cluster_posteriors', 'write_resume',
+        'write_paramnames', 'read_resume', 'write_stats', 'write_live', 'write_dead', 'write_prior', 'maximise',
+        'compression_factor', 'synchronous', 'base_dir', 'file_root', 'grade_dims', 'nlives', 'seed')}
+    kw['grade_frac'] = settings.grade_frac
+    return run(loglikelihood, nDims, nDerived=nDerived, prior=prior, dumper=dumper, **kw)

@@ -69,3 +69,23 @@ def test_no_device_means_loud_failure(capi):
         pass
     finally:
         capi.set_option("errors_return", 0)
+
+
+def test_reference_facade_links_against_this_library(capi, tmp_path):
+    """the reference's own C++ facade (src/polychord/c_interface.cpp) compiled from
+    where it lies and linked against this repository's libchord.so with no undefined symbols: the two
+    extern "C" entry points are the whole link-time contract.  Needs /root/reference (this container only)."""
+    import shutil
+    import subprocess
+    ref = Path("/root/reference/src/polychord")
+    if not (ref / "c_interface.cpp").exists() or shutil.which("g++") is None:
+        import pytest
+        pytest.skip("reference sources or g++ not available")
+    out = tmp_path / "libfacade.so"
+    cmd = ["g++", "-std=c++11", "-shared", "-fPIC", "-I", str(ref), str(ref / "c_interface.cpp"),
+           "-L", str(capi.LIB_PATH.parent), "-lchord", "-Wl,--no-undefined", "-Wl,-rpath," + str(capi.LIB_PATH.parent),
+           "-o", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    nm = subprocess.run(["nm", "-D", "--undefined-only", str(out)], capture_output=True, text=True).stdout
+    assert "polychord_c_interface" in nm and "polychord_c_interface_ini" in nm

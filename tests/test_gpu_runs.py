@@ -167,3 +167,19 @@ def test_capacity_growth_paths(gpu):
         gpu.set_option("cap_ph0", 0)
     assert b.kernel_launches > a.kernel_launches
     assert a.logZ == b.logZ and a.nlike == b.nlike and a.ndead == b.ndead
+
+
+def test_reference_cpp_facade_drives_the_engine(gpu):
+    """oracle/_ref/ref_driver: the REFERENCE'S OWN C++ facade (Settings + run_polychord, c_interface.cpp compiled
+    from the reference tree by oracle/Makefile) linked against this library -- the drop-in boundary exercised
+    from the reference's side.  The 20-D Gaussian's logZ must come back within 5 sigma of the analytic value."""
+    import subprocess
+    from pathlib import Path
+    exe = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "ref_driver"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/ref_driver not built (needs the reference tree at build time)")
+    r = subprocess.run([str(exe), "20", "500", "3"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    logZ, logZerr, ndead, nlive_last, ndumps = r.stdout.split()[-5:]
+    assert abs(float(logZ) - ANALYTIC["gaussian20_unit_cube"]["logZ"]) < 5 * float(logZerr)
+    assert int(ndead) > 5000 and int(nlive_last) == 0 and int(ndumps) > 5
