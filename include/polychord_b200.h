@@ -123,6 +123,21 @@ void pc_set_stream(void* cuda_stream);
  * milliseconds); this returns the cached blocks to the driver. */
 void pc_release_memory(void);
 
+struct pc_settings;
+/* Sharded run over the GPUs of one box, one process per GPU (replaces the reference's MPI administrator /
+ * worker scheme, src/polychord/mpi_utils.F90 and nested_sampling.F90:262-303,420-500).  Every rank calls
+ *   pc_mgpu_create(settings, world, handle)     allocates this rank's exchange block, returns its 64-byte CUDA IPC handle
+ *   [the caller all-gathers the handles, e.g. with torch.distributed]
+ *   pc_mgpu_attach(rank, world, handles)         maps every peer's block (handles: world x 64 bytes, rank order)
+ * and then the same pc_run()/polychord_c_interface() call with identical settings and seed.  The ranks keep the
+ * run state replicated, deal the chains of a generation k % world and exchange the new live points and the
+ * covariance statistics through the mapped blocks over NVLink inside the persistent kernel.  nlike in
+ * pc_run_info counts this rank's evaluations (sum over ranks for the run's total); everything else is identical
+ * on every rank.  The dumper is honoured on every rank that passes one. */
+int pc_mgpu_create(const struct pc_settings* s, int world, unsigned char* handle64);
+int pc_mgpu_attach(int rank, int world, const unsigned char* handles);
+int pc_mgpu_destroy(void);
+
 typedef struct pc_run_info {
     int status;               /* 0 ok; <0 error code */
     double logZ, logZerr;     /* run_time_info.f90:652-678 estimate */

@@ -23,7 +23,7 @@ EXPORTS = [
     "polychord_c_interface", "polychord_c_interface_ini",
     "pc_register_device_likelihood", "pc_register_device_prior", "pc_clear_registrations",
     "pc_gaussian_loglikelihood", "pc_rastrigin_loglikelihood", "pc_corr_gaussian_loglikelihood",
-    "pc_unit_prior", "pc_uniform_prior", "pc_set_option", "pc_get_option", "pc_set_stream", "pc_release_memory",
+    "pc_unit_prior", "pc_uniform_prior", "pc_set_option", "pc_get_option", "pc_set_stream", "pc_release_memory", "pc_mgpu_create", "pc_mgpu_attach", "pc_mgpu_destroy",
     "pc_last_run_info", "pc_run", "pc_run_ensemble", "pc_slice_chains", "pc_calculate_points",
     "pc_device_philox", "pc_device_uniforms", "pc_device_inv_normal_cdf", "pc_device_directions",
     "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version",
@@ -240,6 +240,24 @@ def device_cholesky(a):
     if fb < 0:
         raise RuntimeError("pc_device_cholesky failed")
     return np.array(out), fb
+
+
+def mgpu_create(settings, world):
+    """This rank's exchange block for a sharded run; returns its 64-byte CUDA IPC handle."""
+    h = (C.c_ubyte * 64)()
+    if lib().pc_mgpu_create(C.byref(settings), int(world), h) != 0:
+        raise RuntimeError("pc_mgpu_create failed")
+    return bytes(h)
+
+
+def mgpu_attach(rank, world, handles):
+    buf = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+    if lib().pc_mgpu_attach(int(rank), int(world), buf) != 0:
+        raise RuntimeError("pc_mgpu_attach failed")
+
+
+def mgpu_destroy():
+    lib().pc_mgpu_destroy()
 
 
 def last_run_info():

@@ -99,6 +99,23 @@ static HostCtl* host_ctl() {
     return g_ctl;
 }
 
+// Sharded run across the GPUs of one box (one process per GPU): the exchange block of every rank, mapped
+// into this process through CUDA IPC.  Layout of a block: [barrier counter, 256 B][incoming last babies,
+// 2 x batch_K x T doubles][statistics slots, world x xstride doubles].
+struct MgpuCtx {
+    int rank = 0, world = 0;
+    void* local = nullptr;
+    void* peer[MAX_RANKS] = {nullptr};
+    size_t bytes = 0;
+    int batch_K = 0, T = 0, D = 0;
+    unsigned long long epoch = 0;  // cross-GPU barriers passed so far (the counters are never reset)
+};
+static MgpuCtx g_mgpu;
+static size_t mgpu_xstride(int D) { return (size_t)((2 + D + D * (D + 1) / 2 + 1) & ~1); }
+static size_t mgpu_block_bytes(int batch_K, int T, int D, int world) {
+    return 256 + (size_t)2 * batch_K * T * 8 + (size_t)world * mgpu_xstride(D) * 8;
+}
+
 template <class V>
 struct DevArr {  // RAII device buffer (exception-transparent: callbacks may throw through the engine)
     V* p = nullptr;
@@ -294,7 +311,7 @@ static void set_smem(const ShapeFns& fn, size_t smem) {
 // ------------------------------------------------------------------------------------------
 struct HostRun {
     DevArr<DevRun> st;
-    DevArr<double> live, live_snap, dead, logw, ph0, ph1, chol, cov, partial, nh;
+    DevArr<double> live, live_snap, dead, logw, ph0, ph1, chol, cov, partial, nh, gsum;
     DevArr<int> order;
     DevArr<long long> pcount;
     RunBuf buf;
@@ -346,7 +363,20 @@ struct Engine {
         long long capacity = (long long)sms * per_sm;
         // A run alone on the device spreads its chains one per CTA (a chain warp then has an SM sub-partition
         // to itself) and leaves CTA 0 to the bookkeeping; an ensemble packs W chains per CTA.
-        G = K + 1;
+        const bool sharded = g_mgpu.world > 1;
+        if (sharded) {
+            if (nruns != 1) throw std::invalid_argument("polychord_b200: a sharded run cannot be part of an ensemble");
+            if (g_mgpu.batch_K != K || g_mgpu.T != k.cp.T || g_mgpu.D != k.cp.D)
+                throw std::invalid_argument("polychord_b200: pc_mgpu_create was called with different settings than this run");
+            k.sh.rank = g_mgpu.rank; k.sh.world = g_mgpu.world; k.sh.xstride = (long long)mgpu_xstride(k.cp.D);
+            for (int q = 0; q < g_mgpu.world; ++q) {
+                unsigned char* b = (unsigned char*)g_mgpu.peer[q];
+                k.sh.xbar[q] = (unsigned int*)b;
+                k.sh.xin[q] = (double*)(b + 256);
+                k.sh.xpart[q] = (double*)(b + 256 + (size_t)2 * K * k.cp.T * 8);
+            }
+        }
+        G = (sharded ? (K + g_mgpu.world - 1) / g_mgpu.world : K) + 1;
         if (g_opt.max_ctas > 0) G = std::min(G, g_opt.max_ctas);
         G = (int)std::max(1LL, std::min<long long>(G, capacity / nruns));
         if ((long long)G * nruns > capacity) throw std::invalid_argument("polychord_b200: too many concurrent runs for one launch");
@@ -373,6 +403,7 @@ struct Engine {
             h.ph0.alloc((size_t)cap_ph * T);
             h.ph1.alloc((size_t)cap_ph * T);
             h.chol.alloc((size_t)D * D); h.cov.alloc((size_t)D * D);
+            h.gsum.alloc((size_t)D + 4);
             h.partial.alloc((size_t)G * k.partial_stride);
             h.pcount.alloc((size_t)cap_ph / U_TILE + 2); h.pcount.zero(stream);
             if (!k.nh_in_smem) h.nh.alloc((size_t)G * W * R * k.cp.LD);
@@ -380,7 +411,9 @@ struct Engine {
             std::memset(&b, 0, sizeof(b));
             b.st = h.st.p; b.live = h.live.p; b.live_snap = nullptr; b.ctl = nullptr; b.order = h.order.p; b.dead = h.dead.p; b.logw = h.logw.p;
             b.ph[0] = h.ph0.p; b.ph[1] = h.ph1.p; b.chol = h.chol.p; b.cov = h.cov.p; b.partial = h.partial.p;
-            b.pcount = h.pcount.p; b.nh = h.nh.p; b.cap_dead = cap_dead; b.cap_ph = cap_ph;
+            b.pcount = h.pcount.p; b.nh = h.nh.p; b.cap_dead = cap_dead; b.cap_ph = cap_ph; b.gsum = h.gsum.p;
+            if (sharded)  // continue the cross-GPU barrier count of earlier runs (the counters are monotonic)
+                PC_CUDA(cudaMemcpyAsync(&h.st.p->xepoch, &g_mgpu.epoch, sizeof(g_mgpu.epoch), cudaMemcpyHostToDevice, stream));
             b.seed = (unsigned)seeds[r];
             hb[r] = b;
         }
@@ -558,6 +591,7 @@ struct Engine {
             if (regrow) upload_bufs();
             if (all_done) break;
         }
+        if (g_mgpu.world > 1) g_mgpu.epoch = runs[0].host_st.xepoch;
         if (dumper)  // the final call: every point is dead (nested_sampling.F90:392)
             for (int r = 0; r < nruns; ++r)
                 dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, nullptr, stream);
@@ -660,6 +694,53 @@ double pc_get_option(const char* name) {
 }
 void pc_set_stream(void* cuda_stream) { g_stream = (cudaStream_t)cuda_stream; }
 void pc_release_memory(void) { pool().trim(); }
+
+// ---- sharded run over the GPUs of one box ---------------------------------------------------------
+int pc_mgpu_create(const pc_settings* s, int world, unsigned char* handle64) {
+    try {
+        device_check();
+        if (world < 2 || world > MAX_RANKS) throw std::invalid_argument("polychord_b200: world must be 2..8");
+        if (g_mgpu.local) throw std::invalid_argument("polychord_b200: pc_mgpu_create called twice (pc_mgpu_destroy first)");
+        int K = g_opt.batch_K > 0 ? g_opt.batch_K : (int)std::lround(s->nlive * g_opt.batch_fraction);
+        K = std::max(1, std::min(K, s->nlive - 1));
+        const int T = 2 * s->nDims + s->nDerived + 2;
+        g_mgpu.bytes = mgpu_block_bytes(K, T, s->nDims, world);
+        g_mgpu.batch_K = K; g_mgpu.T = T; g_mgpu.D = s->nDims; g_mgpu.world = 0; g_mgpu.epoch = 0;
+        PC_CUDA(cudaMalloc(&g_mgpu.local, g_mgpu.bytes));  // not from the pool: the block is exported through CUDA IPC
+        PC_CUDA(cudaMemset(g_mgpu.local, 0, g_mgpu.bytes));
+        PC_CUDA(cudaDeviceSynchronize());
+        cudaIpcMemHandle_t h;
+        PC_CUDA(cudaIpcGetMemHandle(&h, g_mgpu.local));
+        static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+        std::memcpy(handle64, &h, 64);
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(-7, ex.what());
+    }
+}
+int pc_mgpu_attach(int rank, int world, const unsigned char* handles) {
+    try {
+        if (!g_mgpu.local) throw std::invalid_argument("polychord_b200: pc_mgpu_attach before pc_mgpu_create");
+        if (rank < 0 || rank >= world || world > MAX_RANKS) throw std::invalid_argument("polychord_b200: bad rank/world");
+        for (int q = 0; q < world; ++q) {
+            if (q == rank) { g_mgpu.peer[q] = g_mgpu.local; continue; }
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, handles + (size_t)q * 64, 64);
+            PC_CUDA(cudaIpcOpenMemHandle(&g_mgpu.peer[q], h, cudaIpcMemLazyEnablePeerAccess));
+        }
+        g_mgpu.rank = rank; g_mgpu.world = world;
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(-7, ex.what());
+    }
+}
+int pc_mgpu_destroy(void) {
+    for (int q = 0; q < g_mgpu.world; ++q)
+        if (q != g_mgpu.rank && g_mgpu.peer[q]) cudaIpcCloseMemHandle(g_mgpu.peer[q]);
+    if (g_mgpu.local) cudaFree(g_mgpu.local);
+    g_mgpu = MgpuCtx();
+    return 0;
+}
 
 int pc_last_run_info(pc_run_info* out) {
     *out = g_last;

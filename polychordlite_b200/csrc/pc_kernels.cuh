@@ -39,7 +39,9 @@ struct DevRun {
     double cov_N;     // points that entered the last covariance
     long long ndead, nlike, nchains, ngen, nupdates, nfail, nslices;
     long long nphantom;       // records in the current phantom pool
-    long long ph_kept;        // survivors counted by the last phase U
+    long long ph_kept;        // survivors counted by the last phase U (this rank's pool)
+    long long nph_glob;       // sharded run: phantoms of all ranks (replicated arithmetic, used for the capacity test)
+    unsigned long long xepoch; // sharded run: cross-GPU barriers passed
     long long ndead_base;     // ndead before the generation in flight
     long long nph_base;       // nphantom before the generation in flight
     long long nchains_base;
@@ -85,6 +87,7 @@ struct RunBuf {
     double* chol;      // D x D column-major
     double* cov;       // D x D column-major
     double* partial;   // per CTA: [0]=count, [1..D]=sum x, then ntri covariance partials
+    double* gsum;      // [0] survivors of all ranks, [1] unused, [2..2+D) sum x over live + all phantoms
     long long* pcount; // survivor count of each phantom tile (phase U)
     double* nh;        // global direction scratch (used when the directions do not fit in smem)
     long long cap_dead, cap_ph;
@@ -92,8 +95,26 @@ struct RunBuf {
     int pad;
 };
 
+// Sharded run: one process per GPU, every rank keeps the whole run state and does
+// the (deterministic) bookkeeping redundantly, the chains of a generation are dealt k % world, and the ranks
+// exchange through peer-mapped memory over NVLink inside the persistent kernel:
+//   xin    the last baby of every chain is stored into every rank's incoming buffer (2 x batch_K x T, by
+//          generation parity) and scattered into the replicated live array after a cross-GPU barrier;
+//   xpart  the covariance statistics (count, sum x | centred outer products) of each rank's phantoms are
+//          all-reduced by storing them into every rank's slot and summing in rank order;
+//   xbar   one monotonic counter per rank: a barrier adds `world` to each of them.
+constexpr int MAX_RANKS = 8;
+struct Shard {
+    int rank, world;
+    long long xstride;                 // doubles per rank slot in xpart
+    unsigned int* xbar[MAX_RANKS];
+    double* xin[MAX_RANKS];
+    double* xpart[MAX_RANKS];
+};
+
 struct KParams {
     ChainParams cp;              // D, P, T, R, LD, likelihood constants
+    Shard sh;                    // sh.world <= 1: a run on one GPU
     int n, batch_K;
     int use_prec, max_ndead;
     int ctas_per_run, warps_per_cta;
@@ -151,6 +172,24 @@ __device__ __forceinline__ void group_sync(unsigned int* bar, unsigned int G) {
         __threadfence();
     }
     __syncthreads();
+}
+
+// Cross-GPU barrier of a sharded run, called by ONE thread per rank: publish everything written so far
+// (system scope), add one to every rank's counter, wait until this rank's counter shows `world` arrivals for
+// the new epoch.  Returns false on time-out (a peer died): the caller stops the run.
+__device__ inline bool xgpu_barrier(const Shard& sh, DevRun* st) {
+    const unsigned long long epoch = ++st->xepoch;
+    __threadfence_system();
+    for (int q = 0; q < sh.world; ++q) atomicAdd_system(sh.xbar[q], 1u);
+    const unsigned int target = (unsigned int)(epoch * (unsigned long long)sh.world);
+    const long long t0 = clock64();
+    unsigned int v;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(sh.xbar[sh.rank]) : "memory");
+        if (clock64() - t0 > 60000000000LL) return false;  // ~30 s
+    } while ((int)(v - target) < 0);
+    __threadfence_system();
+    return true;
 }
 
 // Per-warp split barrier: a warp arrives as soon as its own chains are written, does other work

@@ -66,7 +66,7 @@ __device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st
                 run += (int)tot;
             }
             if (tid == 0) {
-                st->nlike += run;
+                if (p.sh.rank == 0) st->nlike += run;  // a sharded run generates the live points on every rank, counts them once
                 st->init_need = need - run;
                 st->init_attempts = a0 + need;
                 if (a0 > 1000LL * n + 1000000LL) { st->init_need = 0; st->status = ST_ERROR; }
@@ -144,7 +144,9 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
     if (K < 1) more = false;
     if (more) {
         if (ndead + K + n > rb.cap_dead) { if (tid == 0) st->status = ST_NEED_DEAD; return false; }
-        if (st->nphantom + (long long)K * (p.cp.R - 1) > rb.cap_ph) { if (tid == 0) st->status = ST_NEED_PHANTOM; return false; }
+        // sharded run: the decision must be the same on every rank, so it is taken on the phantoms of all ranks
+        const long long nph_test = p.sh.world > 1 ? st->nph_glob : st->nphantom;
+        if (nph_test + (long long)K * (p.cp.R - 1) > rb.cap_ph) { if (tid == 0) st->status = ST_NEED_PHANTOM; return false; }
     } else if (ndead + n > rb.cap_dead) {
         if (tid == 0) st->status = ST_NEED_DEAD;
         return false;
@@ -220,7 +222,9 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
         st->ndead_base = ndead;
         st->ndead = ndead + K;
         st->nph_base = st->nphantom;
-        st->nphantom += (long long)K * (p.cp.R - 1);
+        const int Kloc = p.sh.world > 1 ? (K - p.sh.rank + p.sh.world - 1) / p.sh.world : K;  // chains of this rank
+        st->nphantom += (long long)Kloc * (p.cp.R - 1);
+        st->nph_glob += (long long)K * (p.cp.R - 1);
         st->nchains_base = st->nchains;
         st->nchains += K;
         st->ngen += 1;
@@ -298,7 +302,7 @@ __device__ inline void phase_U1(const KParams& p, const RunBuf& rb, DevRun* st, 
         }
         __syncthreads();
     }
-    for (int rec = l0 + warp * 4; rec < l1; rec += W * 4) {
+    for (int rec = l0 + warp * 4; rec < l1 && p.sh.rank == 0; rec += W * 4) {  // the live points are replicated: rank 0 counts them
         const double* b = rb.live + (size_t)rec * T;
         add4(b, rec + 1 < l1 ? b + T : nullptr, rec + 2 < l1 ? b + 2 * T : nullptr, rec + 3 < l1 ? b + 3 * T : nullptr);
     }
@@ -313,6 +317,52 @@ __device__ inline void phase_U1(const KParams& p, const RunBuf& rb, DevRun* st, 
         out[1 + e] = s;
     }
     __syncthreads();
+}
+
+// Between the passes (CTA 0): survivors and sum x of this rank from the per-CTA partials, all-reduced over the
+// ranks of a sharded run in rank order, into rb.gsum.  Returns false when a peer does not answer.
+__device__ inline bool reduce_stats(const KParams& p, const RunBuf& rb, DevRun* st, int NG, double* s_tmp) {
+    const int tid = threadIdx.x, D = p.cp.D;
+    const long long total = vload(&st->nphantom);
+    const long long ntiles = (total + U_TILE - 1) / U_TILE;
+    __shared__ int s_ok;
+    double cnt = 0.0;
+    for (long long g = tid; g < ntiles; g += blockDim.x) cnt += (double)__ldcg(rb.pcount + g);
+    cnt = block_sum(cnt, s_tmp);  // exact: integers
+    for (int e = tid; e < D; e += blockDim.x) {
+        double s = 0.0;
+#pragma unroll 8
+        for (int g = 0; g < NG; ++g) s += __ldcg(rb.partial + (size_t)g * p.partial_stride + 1 + e);
+        s_tmp[64 + e] = s;
+    }
+    __syncthreads();
+    if (p.sh.world > 1) {
+        for (int q = 0; q < p.sh.world; ++q) {
+            double* slot = p.sh.xpart[q] + (size_t)p.sh.rank * p.sh.xstride;
+            if (tid == 0) slot[0] = cnt;
+            for (int e = tid; e < D; e += blockDim.x) slot[2 + e] = s_tmp[64 + e];
+        }
+        __syncthreads();
+        if (tid == 0) s_ok = xgpu_barrier(p.sh, st) ? 1 : 0;
+        __syncthreads();
+        if (!s_ok) return false;
+        const double* mine = p.sh.xpart[p.sh.rank];
+        if (tid == 0) {
+            double c = 0.0;
+            for (int r = 0; r < p.sh.world; ++r) c += __ldcg(mine + (size_t)r * p.sh.xstride);
+            rb.gsum[0] = c;
+        }
+        for (int e = tid; e < D; e += blockDim.x) {
+            double s = 0.0;
+            for (int r = 0; r < p.sh.world; ++r) s += __ldcg(mine + (size_t)r * p.sh.xstride + 2 + e);
+            rb.gsum[2 + e] = s;
+        }
+    } else {
+        if (tid == 0) rb.gsum[0] = cnt;
+        for (int e = tid; e < D; e += blockDim.x) rb.gsum[2 + e] = s_tmp[64 + e];
+    }
+    __syncthreads();
+    return true;
 }
 
 __device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, int cta, int NG, unsigned char* smem_warp0,
@@ -348,13 +398,8 @@ __device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, 
     __syncthreads();
     long long base = s_base[0];
     const long long tot = s_base[1];
-    const double N = (double)(n + tot);
-    for (int e = tid; e < D; e += blockDim.x) {  // the mean, summed over the CTAs in CTA order
-        double s = 0.0;
-#pragma unroll 8
-        for (int g = 0; g < NG; ++g) s += __ldcg(rb.partial + (size_t)g * p.partial_stride + 1 + e);
-        s_mean[e] = s / N;
-    }
+    const double N = (double)n + __ldcg(rb.gsum);  // live points + the surviving phantoms of all ranks
+    for (int e = tid; e < D; e += blockDim.x) s_mean[e] = __ldcg(rb.gsum + 2 + e) / N;
     if (cta == 0 && tid == 0) st->ph_kept = tot;
     __syncthreads();
     for (int pass = 0; pass < p.cov_passes; ++pass) {
@@ -440,7 +485,7 @@ __device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, 
                 tbase = s_base[0];
             }
         }
-        for (int rec = l0 + warp; rec < l1; rec += W) {
+        for (int rec = l0 + warp; rec < l1 && p.sh.rank == 0; rec += W) {
             double v[4];
             load_x(rb.live + (size_t)rec * T, v);
             accumulate(v);
@@ -465,23 +510,49 @@ __device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, 
 }
 
 // ---------------------------------------------------------------- update finalisation (CTA 0)
-__device__ inline void finish_update(const KParams& p, const RunBuf& rb, DevRun* st, int NG, double* s_cov, double* s_L) {
+__device__ inline bool finish_update(const KParams& p, const RunBuf& rb, DevRun* st, int NG, double* s_cov, double* s_L) {
     const int tid = threadIdx.x, D = p.cp.D, ntri = p.ntri;
     const long long tot = st->ph_kept;
-    const double N = (double)(p.n + tot);
-    for (int idx = tid; idx < ntri; idx += blockDim.x) {
-        int ai = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+    const double Nglob = __ldcg(rb.gsum);
+    const double N = (double)p.n + Nglob;
+    __shared__ int s_ok;
+    auto unpack = [](int idx, int& ai, int& bi) {
+        ai = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
         while (ai * (ai + 1) / 2 > idx) --ai;
         while ((ai + 1) * (ai + 2) / 2 <= idx) ++ai;
-        int bi = idx - ai * (ai + 1) / 2;
+        bi = idx - ai * (ai + 1) / 2;
+    };
+    for (int idx = tid; idx < ntri; idx += blockDim.x) {  // this rank's outer products, CTA order
         double s = 0.0;
 #pragma unroll 8
         for (int g = 0; g < NG; ++g) s += __ldcg(rb.partial + (size_t)g * p.partial_stride + 1 + D + idx);
-        s /= N;  // calculate_covmats divides by N, not N-1 (run_time_info.f90:601-641)
-        s_cov[ai + bi * D] = s;
-        s_cov[bi + ai * D] = s;
+        if (p.sh.world > 1) {
+            for (int q = 0; q < p.sh.world; ++q) p.sh.xpart[q][(size_t)p.sh.rank * p.sh.xstride + 2 + D + idx] = s;
+        } else {
+            int ai, bi;
+            unpack(idx, ai, bi);
+            s /= N;  // calculate_covmats divides by N, not N-1 (run_time_info.f90:601-641)
+            s_cov[ai + bi * D] = s;
+            s_cov[bi + ai * D] = s;
+        }
     }
     __syncthreads();
+    if (p.sh.world > 1) {
+        if (tid == 0) s_ok = xgpu_barrier(p.sh, st) ? 1 : 0;
+        __syncthreads();
+        if (!s_ok) return false;
+        const double* mine = p.sh.xpart[p.sh.rank];
+        for (int idx = tid; idx < ntri; idx += blockDim.x) {
+            double s = 0.0;
+            for (int r = 0; r < p.sh.world; ++r) s += __ldcg(mine + (size_t)r * p.sh.xstride + 2 + D + idx);
+            int ai, bi;
+            unpack(idx, ai, bi);
+            s /= N;
+            s_cov[ai + bi * D] = s;
+            s_cov[bi + ai * D] = s;
+        }
+        __syncthreads();
+    }
     int fb = 0;
     if (tid < 32) fb = warp_cholesky(s_cov, s_L, D);  // calc_cholesky (utils.F90:621-649) in shared memory
     __syncthreads();
@@ -490,10 +561,42 @@ __device__ inline void finish_update(const KParams& p, const RunBuf& rb, DevRun*
         st->chol_fallback += fb;
         st->cov_N = N;
         st->nphantom = tot;
+        st->nph_glob = (long long)Nglob;
         st->cur_pool ^= 1;
         st->nupdates += 1;
         st->logX_last_update = st->logX;
         st->update_pending = 0;
+    }
+    __syncthreads();
+    return true;
+}
+
+// ---------------------------------------------------------------- sharded run: last-baby exchange
+// A chain warp stores its last baby (already in this rank's incoming buffer) into every peer's incoming buffer.
+__device__ inline void shard_publish(const KParams& p, const double* rec, int k, int parity) {
+    const int lane = threadIdx.x & 31, T = p.cp.T;
+    __syncwarp();
+    for (int q = 0; q < p.sh.world; ++q) {
+        if (q == p.sh.rank) continue;
+        double* dst = p.sh.xin[q] + ((size_t)parity * p.batch_K + k) * T;
+        for (int e = lane; e < T; e += 32) dst[e] = __ldcg(rec + e);
+    }
+    __threadfence_system();
+}
+// CTA 0, after this rank's chains are done: cross-GPU barrier, then the K last babies of all ranks are copied
+// from the incoming buffer into the vacated live slots (the same on every rank).
+__device__ inline void shard_scatter(const KParams& p, const RunBuf& rb, DevRun* st) {
+    __shared__ int s_ok;
+    const int tid = threadIdx.x, T = p.cp.T;
+    if (tid == 0) s_ok = xgpu_barrier(p.sh, st) ? 1 : 0;
+    __syncthreads();
+    if (!s_ok) { if (tid == 0) st->status = ST_ERROR; __syncthreads(); return; }
+    const int K = st->K;
+    const int* ord = rb.order + st->order_off;
+    const double* in = p.sh.xin[p.sh.rank] + (size_t)(st->ngen & 1) * p.batch_K * T;
+    for (int e = tid; e < K * T; e += blockDim.x) {
+        const int k = e / T, c = e - k * T;
+        rb.live[(size_t)__ldcg(ord + k) * T + c] = __ldcg(in + e);
     }
     __syncthreads();
 }
@@ -575,6 +678,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
     unsigned int wtarget = 0;
     bool have_wtarget = false;
     unsigned pair_seq = 0;  // paired mode: chains this warp pair has run since the launch (buffer parity)
+    bool scatter_due = false;  // sharded run: the last babies of the generation are still in the incoming buffer
     bool s2_due = false;  // CTA 0: the evidence of the generation in flight is still to be accumulated
 
     const bool timer = (tid == 0) && (cta == 0);          // bookkeeping phases
@@ -585,10 +689,15 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
             long long t0 = clock64();
             if (have_wtarget) warp_wait(&st->wbar, wtarget);  // every chain of the previous generation is written
             __syncthreads();
+            if (scatter_due) {  // sharded run: every rank's last babies -> the replicated live array
+                shard_scatter(p, rb, st);
+                scatter_due = false;
+            }
             long long t1 = clock64();
             bool dump_exit = false;
             if (st->update_pending) {
-                finish_update(p, rb, st, NG, smS.akey, s_chol);
+                if (!finish_update(p, rb, st, NG, smS.akey, s_chol) && tid == 0) st->status = ST_ERROR;
+                __syncthreads();
                 if (rb.ctl) dump_exit = publish_dump(p, rb, st);   // the kernel keeps running
                 else if (p.want_dump) dump_exit = true;              // "sync_dump": leave, the host dumps and relaunches
             }
@@ -617,6 +726,17 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
             phase_S2(p, rb, st, smS);
             s2_due = false;
         }
+        const bool sharded = p.sh.world > 1;
+        const int xw = sharded ? p.sh.world : 1, xr = sharded ? p.sh.rank : 0;
+        if (sharded && cta == 0) {  // the dying points move to the (replicated) dead list (run_time_info.f90:789-817)
+            const int K_ = vload(&st->K);
+            const long long nb = vload(&st->ndead_base);
+            const int* ord = rb.order + vload(&st->order_off);
+            for (int e = tid; e < K_ * T; e += blockDim.x) {
+                const int k = e / T, c = e - k * T;
+                rb.dead[(size_t)(nb + k) * T + c] = __ldcg(rb.live + (size_t)__ldcg(ord + k) * T + c);
+            }
+        }
 
         // ---------------- phase C: chains, one warp each ----------------
         const int K = vload(&st->K);
@@ -630,6 +750,9 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
         __syncthreads();
         unsigned long long nlike = 0, nfail = 0;
         const int m = n - K;
+        // sharded run: the last babies go to the incoming buffers (by generation parity) instead of the live slots
+        const int xpar = (int)(vload(&st->ngen) & 1);
+        double* xin_mine = sharded ? p.sh.xin[xr] + (size_t)xpar * p.batch_K * T : nullptr;
         int knext = -1;  // first chain this warp prepares for the next generation
         if (p.paired) {
             // Warps w < W/2 run chains, warp w + W/2 is the helper of warp w: it prepares (directions, deck,
@@ -639,14 +762,15 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
             const bool helper = warp >= HW;
             int nmine = 0;
             if (cta >= c0)
-                for (int li = pair; (cta - c0) + Gc * li < K; li += HW) ++nmine;
+                for (int li = pair; ((cta - c0) + Gc * li) * xw + xr < K; li += HW) ++nmine;
             auto buf = [&](unsigned sq) -> ChainScratch {
                 const int region = pair + HW * (int)(sq & 1u);
                 return chain_scratch(s_warp0 + (size_t)region * p.warp_bytes, D, R, LD, p.nh_in_smem != 0, p.cp.like_kind,
                                      NPT, rb.nh ? rb.nh + ((size_t)cta * W + region) * R * LD : nullptr);
             };
             for (int j = 0; j < nmine; ++j) {
-                const int k = (cta - c0) + Gc * (pair + HW * j);
+                const int cl = (cta - c0) + Gc * (pair + HW * j);  // chain ordinal on this rank
+                const int k = cl * xw + xr;                        // chain of the generation (dealt k % world)
                 const unsigned long long uid = (unsigned long long)(nchains_base + k);
                 const ChainScratch b = buf(pair_seq + j);
                 if (helper) {
@@ -667,22 +791,25 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
 #pragma unroll
                     for (int jj = 0; jj < DPL; ++jj) x[jj] = M.valid(jj) ? __ldcg(rb.live + (size_t)src * T + M.dim(jj)) : 0.0;
                     // the dying point moves to the dead list before its slot is reused (run_time_info.f90:789-817)
-                    for (int e = lane; e < T; e += 32)
-                        rb.dead[(size_t)(ndead_base + k) * T + e] = __ldcg(rb.live + (size_t)dslot * T + e);
+                    if (!sharded)
+                        for (int e = lane; e < T; e += 32)
+                            rb.dead[(size_t)(ndead_base + k) * T + e] = __ldcg(rb.live + (size_t)dslot * T + e);
+                    double* last = sharded ? xin_mine + (size_t)k * T : rb.live + (size_t)dslot * T;
                     long long tc2 = clock64();
                     double lfin = slice_chain<G, DPL, KIND>(p.cp, M, rb.seed, uid, x, Lstar, b,
-                                                      pool + (size_t)(nph_base + (long long)k * (R - 1)) * T,
-                                                      rb.live + (size_t)dslot * T, nlike,
+                                                      pool + (size_t)(nph_base + (long long)cl * (R - 1)) * T, last, nlike,
                                                       (cta == c0 && warp == 0) ? st->dbg : nullptr);
+                    if (sharded) shard_publish(p, last, k, xpar);
                     if (ctimer) st->cyc_slice += clock64() - tc2;
                     if (!(lfin > Lstar)) ++nfail;
                 }
             }
             pair_seq += (unsigned)nmine;
-            if (helper && cta >= c0 && (cta - c0) + Gc * pair < p.batch_K) knext = (cta - c0) + Gc * pair;
+            if (helper && cta >= c0 && ((cta - c0) + Gc * pair) * xw + xr < p.batch_K) knext = ((cta - c0) + Gc * pair) * xw + xr;
         } else if (cta >= c0) {
             for (int li = warp;; li += W) {
-                const int k = (cta - c0) + Gc * li;
+                const int cl = (cta - c0) + Gc * li;
+                const int k = cl * xw + xr;
                 if (k >= K) break;
                 const unsigned long long uid = (unsigned long long)(nchains_base + k);
                 double u = uniform(rb.seed, TAG_SEED, uid, 0u, 0u);  // GenerateSeed, generate.F90:19-55
@@ -694,8 +821,10 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < DPL; ++j) x[j] = M.valid(j) ? __ldcg(rb.live + (size_t)src * T + M.dim(j)) : 0.0;
                 // the dying point moves to the dead list before its slot is reused (run_time_info.f90:789-817)
-                for (int e = lane; e < T; e += 32)
-                    rb.dead[(size_t)(ndead_base + k) * T + e] = __ldcg(rb.live + (size_t)dslot * T + e);
+                if (!sharded)
+                    for (int e = lane; e < T; e += 32)
+                        rb.dead[(size_t)(ndead_base + k) * T + e] = __ldcg(rb.live + (size_t)dslot * T + e);
+                double* last = sharded ? xin_mine + (size_t)k * T : rb.live + (size_t)dslot * T;
                 long long tc0 = clock64();
                 if (prep_uid != uid) {
                     prep_chain(D, R, LD, rb.seed, uid, cs);
@@ -706,15 +835,15 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                 prep_uid = ~0ull;
                 long long tc2 = clock64();
                 double lfin = slice_chain<G, DPL, KIND>(p.cp, M, rb.seed, uid, x, Lstar, cs,
-                                                  pool + (size_t)(nph_base + (long long)k * (R - 1)) * T,
-                                                  rb.live + (size_t)dslot * T, nlike);
+                                                  pool + (size_t)(nph_base + (long long)cl * (R - 1)) * T, last, nlike);
+                if (sharded) shard_publish(p, last, k, xpar);
                 if (ctimer) {
                     long long tc3 = clock64();
                     st->cyc_prep += tc1 - tc0; st->cyc_white += tc2 - tc1; st->cyc_slice += tc3 - tc2;
                 }
                 if (!(lfin > Lstar)) ++nfail;
             }
-            if (cta != 0 && (cta - c0) + Gc * warp < p.batch_K) knext = (cta - c0) + Gc * warp;
+            if (cta != 0 && ((cta - c0) + Gc * warp) * xw + xr < p.batch_K) knext = ((cta - c0) + Gc * warp) * xw + xr;
         }
         if (lane == 0) {
             if (nlike) atomicAdd((unsigned long long*)&st->nlike, nlike);
@@ -722,6 +851,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
         }
         wtarget = warp_arrive(&st->wbar, GW);
         have_wtarget = true;
+        scatter_due = sharded;
         // the scratch the next generation's first chain of this warp (pair) will use
         const bool will_chain = knext >= 0;
         const ChainScratch csn = p.paired ? chain_scratch(s_warp0 + (size_t)((warp % (W >> 1)) + (W >> 1) * (int)(pair_seq & 1u)) * p.warp_bytes,
@@ -732,18 +862,19 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
             long long tu0 = clock64();
             warp_wait(&st->wbar, wtarget);
             long long tu1 = clock64();
+            if (sharded) {  // the covariance is over the live points including this generation's babies
+                if (cta == 0) { __syncthreads(); shard_scatter(p, rb, st); }
+                scatter_due = false;
+                group_sync(&st->bar, NG);
+            }
             phase_U1(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt);
-            long long tu2 = clock64();
             group_sync(&st->bar, NG);
-            long long tu3 = clock64();
+            if (cta == 0 && !reduce_stats(p, rb, st, NG, sc) && tid == 0) st->status = ST_ERROR;
+            group_sync(&st->bar, NG);
             phase_U2(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt);
-            long long tu4 = clock64();
             if (cta == 0 && tid == 0) st->update_pending = 1;
             group_sync(&st->bar, NG);
-            if (timer) {
-                st->cyc_wait += tu1 - tu0; st->cyc_U += clock64() - tu1;
-                
-            }
+            if (timer) { st->cyc_wait += tu1 - tu0; st->cyc_U += clock64() - tu1; }
             have_wtarget = false;
             if (will_chain) {  // the Cholesky factor is about to change: whiten after the barrier
                 prep_uid = (unsigned long long)(nchains_base + K + knext);
