@@ -157,6 +157,9 @@ def main():
     ap.add_argument("--warps-per-cta", type=int, default=None)
     ap.add_argument("--ensemble", type=int, default=32, help="replicas for the extra ensemble-throughput figure (0=skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicas", action="store_true",
+                    help="N>1: N independent runs of the workload (one per GPU, no exchange) instead of ONE run "
+                         "sharded over the GPUs with nlive scaled by N")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -180,6 +183,12 @@ def main():
 
     w = WORKLOADS[args.workload]
     D, P, n, R = w["nDims"], w["nDerived"], w["nlive"], w["num_repeats"]
+    # N > 1 (weak scaling, BASELINE config 5's shape): ONE run with nlive*N live points sharded over the N GPUs --
+    # every rank runs 1/N of each generation's chains, the new live points and the covariance statistics are
+    # exchanged over NVLink inside the persistent kernel (polychordlite_b200/mgpu.py)
+    sharded = world > 1 and not args.replicas
+    if sharded:
+        n = n * world
     T = 2 * D + P + 2
     box = dict(prior_lo=[-w["box"]] * D, prior_hi=[w["box"]] * D) if w["box"] else {}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -187,9 +196,15 @@ def main():
     def settings(seed):
         return capi.make_settings(D, P, nlive=n, num_repeats=R, seed=seed)
 
+    if sharded:
+        from polychordlite_b200 import mgpu
+        mgpu.attach(settings(0))
+
     def step_device(seed):
         flush.zero_()
         torch.cuda.synchronize()
+        if sharded:
+            dist.barrier()
         info, _ = capi.run(settings(seed), like=w["like"], **box)
         return info
 
@@ -230,8 +245,12 @@ def main():
     def step_e2e(seed):
         flush.zero_()
         torch.cuda.synchronize()
+        if sharded:
+            dist.barrier()
         t0 = time.perf_counter()
-        L.polychord_c_interface(C.cast(like_fn, C.c_void_p), C.cast(prior_fn, C.c_void_p), C.cast(dcb, C.c_void_p),
+        # sharded run: every rank makes the call (like the ranks of an MPI run), rank 0 carries the dumper
+        L.polychord_c_interface(C.cast(like_fn, C.c_void_p), C.cast(prior_fn, C.c_void_p),
+                                C.cast(dcb, C.c_void_p) if (rank == 0 or not sharded) else None,
                                 n, R, -1, -1, False, 0, 1e-3, -1e30, -1, 0.0,
                                 False, False, False, False, False, False, False, False, False, False, False,
                                 float(np.exp(-1)), True, D, P, b"chains", b"bench", 1, grade_frac, grade_dims, 0, None,
@@ -240,9 +259,10 @@ def main():
         return capi.last_run_info(), t
 
     # ---- warm-up --------------------------------------------------------------------------------
+    roff = 0 if sharded else 1  # a sharded run needs the same seed on every rank, replicas need different ones
     for i in range(args.warmup):
-        step_device(10_000 + i + 100 * rank)
-        step_e2e(20_000 + i + 100 * rank)
+        step_device(10_000 + i + 100 * rank * roff)
+        step_e2e(20_000 + i + 100 * rank * roff)
 
     def barrier():
         torch.cuda.synchronize()
@@ -259,7 +279,8 @@ def main():
     t_region = time.perf_counter()
     for i in range(args.steps):
         t0 = time.perf_counter()
-        info = step_device(i + 1000 * rank)
+        info = step_device(i + 1000 * rank * roff)
+        info_dev = info
         wall += time.perf_counter() - t0
         evals += info.nlike; dev_ms += info.device_ms; launches += info.kernel_launches
         algo_bytes += info.algorithmic_bytes; logZs.append(info.logZ); ndead += info.ndead
@@ -269,7 +290,7 @@ def main():
     e_evals, e_t, h2d, d2h, e_launch = 0, 0.0, 0, 0, 0
     barrier()
     for i in range(args.steps):
-        info, t = step_e2e(i + 1000 * rank)
+        info, t = step_e2e(i + 1000 * rank * roff)
         e_evals += info.nlike; e_t += t; h2d += info.h2d_bytes; d2h += info.d2h_bytes; e_launch += info.kernel_launches
     barrier()
     clocks = sampler.stop()
@@ -296,19 +317,20 @@ def main():
         t = torch.tensor([dev_ms, e_t, wall], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms_max, e_t_max, wall_max = t.tolist()
-        c = torch.tensor([evals, e_evals, launches + e_launch, algo_bytes], dtype=torch.float64, device="cuda")
+        c = torch.tensor([evals, e_evals, launches + e_launch, algo_bytes, h2d, d2h], dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        evals_all, e_evals_all, launches_all, algo_all = c.tolist()
+        evals_all, e_evals_all, launches_all, algo_all, h2d, d2h = c.tolist()
     else:
         dev_ms_max, e_t_max, wall_max = dev_ms, e_t, wall
         evals_all, e_evals_all, launches_all, algo_all = evals, e_evals, launches + e_launch, algo_bytes
 
     if rank == 0:
         peak, which = peaks()
-        achieved = (algo_bytes / (dev_ms * 1e-3)) / 1e9
+        # rank 0's kernel: a sharded run's counters are replicated, each rank moves 1/world of the algorithmic bytes
+        achieved = (algo_bytes / (world if sharded else 1) / (dev_ms * 1e-3)) / 1e9
         value = evals_all / (dev_ms_max * 1e-3)
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             import oracle_lib as O
             kw = dict(prior_lo=box["prior_lo"], prior_hi=box["prior_hi"]) if box else {}
             ce, ct = 0, 0.0
@@ -325,18 +347,23 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "nDims": D, "nDerived": P, "nlive": n, "num_repeats": R,
+            "config": {"workload": args.workload + (f"_x{world}_sharded" if sharded else ""), "nDims": D, "nDerived": P,
+                       "nlive": n, "num_repeats": R,
                        "precision_criterion": 1e-3, "batch_K": int(info.batch_K), "ctas_per_run": int(info.ctas_per_run),
                        "warps_per_cta": int(info.warps_per_cta), "step": "one complete nested-sampling run",
                        "l2": "flushed (256 MiB memset) before every step",
-                       "multi_gpu": "independent replica runs per rank (no data-path collective)" if world > 1 else "n/a"},
+                       "multi_gpu": ("n/a" if world == 1 else
+                                     "independent replica runs per rank (no data-path collective)" if not sharded else
+                                     f"ONE run, nlive={n} sharded over {world} GPUs: chains dealt k % world, last babies and "
+                                     "covariance statistics exchanged over NVLink peer memory inside the persistent kernel")},
             "wall_time_to_logZ_s": dev_ms / args.steps * 1e-3, "wall_ms_per_step_host": 1e3 * wall_max / args.steps,
             "logZ_mean": float(np.mean(logZs)), "logZ_sem": float(np.std(logZs, ddof=1) / np.sqrt(len(logZs))) if len(logZs) > 1 else None,
-            "ndead_per_step": ndead / args.steps, "evals_per_step": evals / args.steps,
+            "ndead_per_step": ndead / args.steps, "evals_per_step": (evals_all if sharded else evals) / args.steps,
             "e2e": {"value": e_evals_all / e_t_max, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
                     "d2h_bytes_per_step": d2h / args.steps, "api": "polychord_c_interface + dumper (host arrays)",
                     "ms_per_step": 1e3 * e_t_max / args.steps, "dumper_calls": sink["calls"]},
             "gpu_launches": int(launches_all),
+            "phase_ms_last_step": {k: round(v, 3) for k, v in info_dev.as_dict()["phase_ms"].items()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": which, "kernel": "pc_run_kernel<4,5,0>",
                          "note": "latency-bound persistent kernel; one run occupies ctas_per_run of 148 SMs; "
@@ -344,6 +371,8 @@ def main():
             "cpu_baseline": cpu, "clocks": clocks, "ensemble": ens, "region_wall_s": t_region,
         }
         print(json.dumps(line), flush=True)
+    if sharded:
+        mgpu.detach()
     if world > 1:
         dist.destroy_process_group()
 
