@@ -51,17 +51,44 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).
+
+    Sampled in-process through NVML (the library nvidia-smi itself reads): a looping `nvidia-smi -lms`
+    child holds driver locks for milliseconds at a time and was measured to stretch the host side of a
+    17 ms run to 20-115 ms, i.e. it perturbs exactly the end-to-end number it is supposed to vouch for.
+    Falls back to the nvidia-smi loop when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None, period_s=0.02):
+        self.index, self.uuid, self.period = index, uuid, period_s
         self.proc = None
-        self.index = index
         self.lines = []
+        self.samples = []   # (sm_mhz, reasons bitmask)
+        self.nv = None
+        self.stop_flag = threading.Event()
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    u = self.uuid if str(self.uuid).startswith("GPU-") else "GPU-" + str(self.uuid)
+                    h = nv.nvmlDeviceGetHandleByUUID(u.encode() if hasattr(u, "encode") else u)
+                except Exception:
+                    h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.nv, self.h = nv, h
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -70,11 +97,43 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((mhz, rs))
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nv is not None:
+            self.stop_flag.set()
+            self.t.join(timeout=2)
+            nv = self.nv
+            names = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("hw_thermal_slowdown", 0x40),
+                     ("sw_thermal_slowdown", 0x20), ("hw_power_brake_slowdown", 0x80))
+            reasons = set()
+            for _, rs in self.samples:
+                for name, bit in names:
+                    if rs & bit:
+                        reasons.add(name)
+            sm = [m for m, _ in self.samples]
+            try:
+                nv.nvmlShutdown()
+            except Exception:
+                pass
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(reasons), "samples": len(sm), "source": "nvml, in-process, every 20 ms"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -96,7 +155,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def dist_env():
@@ -271,7 +330,11 @@ def main():
             torch.cuda.synchronize()
 
     # ---- timed region 1: device-resident ------------------------------------------------------
-    sampler = ClockSampler(local)
+    try:
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local, uuid=uuid)
     sampler.start()
     barrier()
     evals = launches = 0

@@ -89,6 +89,24 @@ struct PinnedBuf {
     }
 };
 static PinnedBuf g_pin_dead, g_pin_live;
+// Host mirror of the dead points handed to the dumper (rows [theta, phi, birth, logL], posterior log-weights).
+// Kept between runs: a sampler is called again and again with the same shapes, and fresh pages cost more
+// than the copies.
+struct DumpMirror {
+    std::vector<double> rows, logw, lw, live_rows;
+};
+static DumpMirror g_mirror;
+static int sm_clock_khz() {  // cudaDevAttrClockRate is a slow driver query (milliseconds): ask once per device
+    static std::map<int, int> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto it = cache.find(dev);
+    if (it != cache.end()) return it->second;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+    cache[dev] = khz;
+    return khz;
+}
 static HostCtl* g_ctl = nullptr;          // mapped pinned control block of the asynchronous dumper hand-over
 static cudaStream_t g_copy_stream = nullptr;
 static HostCtl* host_ctl() {
@@ -155,6 +173,7 @@ struct Options {
     long long cap_dead0 = 0, cap_ph0 = 0;  // initial pool capacities in records (0 = automatic)
 };
 static Options g_opt;
+static double g_dbg_dump[4];  // PC_DEBUG: ms spent in copies, row packing, weight normalisation, the user's dumper
 static cudaStream_t g_stream = nullptr;
 static pc_run_info g_last;
 static std::mutex g_mu;
@@ -274,8 +293,9 @@ static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const Dev
     k.prior_params = dm.prior.p;
     k.warps_per_cta = W;
     k.ntri = D * (D + 1) / 2;
-    k.cov_passes = (k.ntri + COV_ACC * 32 - 1) / (COV_ACC * 32);
-    k.partial_stride = 1 + D + k.cov_passes * COV_ACC * 32;
+    const int Dp8 = (D + 1 + 7) & ~7, nt8 = Dp8 / 8;  // phase U: augmented coordinate rows in 8-wide tiles (pc_run_kernel.cuh)
+    k.cov_passes = (nt8 * (nt8 + 1) / 2 + COV_TPP - 1) / COV_TPP;
+    k.partial_stride = 1 + D + k.ntri;
     L.W = W;
     const int nlp = ms.like_kind == PC_LIKE_GAUSSIAN ? 2 * D : (ms.like_kind == PC_LIKE_CORR_GAUSSIAN ? D + D * D : 0);
     const int Dpad = (D + 1) & ~1;
@@ -284,11 +304,13 @@ static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const Dev
     off += (size_t)((nlp + 1) & ~1) * 8;
     off += 64 * sizeof(int);  // s_cnt
     k.off_warp = (int)off;
-    const size_t cov_bytes = (size_t)(2 * Dpad + COV_ACC * 32) * 8;
+    // phase U: pivot + a staged batch of augmented rows per warp; all warps' areas together hold the CTA's moment matrix
+    const size_t cov_bytes = std::max((size_t)(Dpad + U_BATCH * (Dp8 + 4)) * 8,
+                                      ((size_t)(Dpad + Dp8 * Dp8) * 8 + W - 1) / W);
     int K = g_opt.batch_K > 0 ? g_opt.batch_K : (int)std::lround(s.nlive * g_opt.batch_fraction);
     K = std::max(1, std::min(K, s.nlive - 1));
     k.batch_K = K;
-    const size_t sort_bytes = std::max(smem_S_bytes(s.nlive, K), (size_t)64 * 8 + (size_t)D * D * 8);  // phase S, or the covariance in finish_update
+    const size_t sort_bytes = std::max(smem_S_bytes(s.nlive, K), (size_t)64 * 8 + (size_t)(D * D + Dpad) * 8);  // phase S, or the covariance (+ mean shift) in finish_update
     const size_t budget = 200 * 1024;
     const size_t with_nh = chain_scratch_bytes(D, R, k.cp.LD, true, ms.like_kind, npt);
     const bool in_smem = !g_opt.nh_global && (off + (size_t)W * std::max(with_nh, cov_bytes) <= budget);
@@ -317,9 +339,8 @@ struct HostRun {
     RunBuf buf;
     DevRun host_st;
     // dumper mirror
-    std::vector<double> dead_rows;   // packed (ndead, npars)
-    std::vector<double> dead_logw, dead_logL;
     long long mirrored = 0;
+    double lse_max = -std::numeric_limits<double>::infinity(), lse_sum = 0.0;  // running logsumexp of logw + logL
 };
 
 struct Engine {
@@ -342,16 +363,27 @@ struct Engine {
     }
 
     void setup(const pc_settings& s, const ModelSpec& m, int nruns_, const int* seeds) {
+        const bool dbg = std::getenv("PC_DEBUG") != nullptr;
+        auto tm0 = std::chrono::steady_clock::now();
+        auto mark = [&](const char* what) {
+            if (!dbg) return;
+            auto t = std::chrono::steady_clock::now();
+            std::fprintf(stderr, "[pc dbg setup] %s %.3f ms\n", what, std::chrono::duration<double, std::milli>(t - tm0).count());
+            tm0 = t;
+        };
         device_check();
+        mark("device_check");
         S = s; ms = m; nruns = nruns_;
         stream = g_stream;
         if (S.nprior > 0 && S.nprior != S.nlive)
             throw std::invalid_argument("polychord_b200: nprior != nlive is not supported by the device path yet");
         build_dev_model(S, ms, dm, stream);
+        mark("build_dev_model");
         int W = std::max(1, std::min(8, g_opt.warps_per_cta));
         L = make_layout(S, ms, dm, W);
         W = L.W;
         set_smem(L.fn, L.smem);
+        mark("layout+set_smem");
         KParams& k = L.kp;
         const int K = k.batch_K;
         // CTAs per run: one warp per chain unless capped by residency
@@ -385,6 +417,7 @@ struct Engine {
         k.paired = (k.chain_cta0 == 1 && W >= 2 && (W % 2) == 0 && !g_opt.no_pairing) ? 1 : 0;
         PC_CUDA(cudaEventCreate(&ev0));
         PC_CUDA(cudaEventCreate(&ev1));
+        mark("occupancy+events");
 
         const int T = k.cp.T, D = k.cp.D, R = k.cp.R, n = k.n;
         runs.resize(nruns);
@@ -403,7 +436,7 @@ struct Engine {
             h.ph0.alloc((size_t)cap_ph * T);
             h.ph1.alloc((size_t)cap_ph * T);
             h.chol.alloc((size_t)D * D); h.cov.alloc((size_t)D * D);
-            h.gsum.alloc((size_t)D + 4);
+            h.gsum.alloc((size_t)2 * D + 4);
             h.partial.alloc((size_t)G * k.partial_stride);
             h.pcount.alloc((size_t)cap_ph / U_TILE + 2); h.pcount.zero(stream);
             if (!k.nh_in_smem) h.nh.alloc((size_t)G * W * R * k.cp.LD);
@@ -417,11 +450,13 @@ struct Engine {
             b.seed = (unsigned)seeds[r];
             hb[r] = b;
         }
+        mark("allocs");
         d_bufs.alloc(nruns);
         d_bufs.upload(hb.data(), nruns, stream);
         h2d += (long long)nruns * sizeof(RunBuf);
         k.runs = d_bufs.p;
         PC_CUDA(cudaStreamSynchronize(stream));
+        mark("upload+sync");
     }
 
     void upload_bufs() {
@@ -462,6 +497,12 @@ struct Engine {
         const int T = k.cp.T, D = k.cp.D, P = k.cp.P, n = k.n, npars = D + P + 2;
         const long long fresh = ndead - h.mirrored;
         const int nl = live_src ? n : 0;
+        auto td0 = std::chrono::steady_clock::now();
+        auto lap = [&](int slot) {
+            auto t = std::chrono::steady_clock::now();
+            g_dbg_dump[slot] += std::chrono::duration<double, std::milli>(t - td0).count();
+            td0 = t;
+        };
         // one batch of async copies into pinned staging, one synchronisation
         double* sd = fresh > 0 ? (double*)g_pin_dead.need((size_t)fresh * (T + 1) * 8) : nullptr;
         double* sl = nl > 0 ? (double*)g_pin_live.need((size_t)n * T * 8) : nullptr;
@@ -475,21 +516,32 @@ struct Engine {
             d2h += (long long)n * T * 8;
         }
         PC_CUDA(cudaStreamSynchronize(cs));
+        lap(0);
+        DumpMirror& mr = g_mirror;
+        if (mr.rows.size() < (size_t)ndead * npars) mr.rows.resize(std::max((size_t)ndead * npars, mr.rows.size() * 2));
+        if (mr.logw.size() < (size_t)ndead) { mr.logw.resize(std::max((size_t)ndead, mr.logw.size() * 2)); mr.lw.resize(mr.logw.size()); }
         if (fresh > 0) {
             const double* lwp = sd + (size_t)fresh * T;
-            h.dead_rows.resize((size_t)ndead * npars);
-            h.dead_logw.resize(ndead);
+            double mx = h.lse_max;
             for (long long i = 0; i < fresh; ++i) {
                 const double* s = sd + (size_t)i * T;
-                double* o = &h.dead_rows[(size_t)(h.mirrored + i) * npars];
+                double* o = &mr.rows[(size_t)(h.mirrored + i) * npars];
                 std::memcpy(o, s + D, (size_t)(D + P) * sizeof(double));  // theta, phi
                 o[D + P] = s[2 * D + P];
                 o[D + P + 1] = s[2 * D + P + 1];
-                h.dead_logw[h.mirrored + i] = lwp[i] + s[T - 1];
+                const double v = lwp[i] + s[T - 1];
+                mr.logw[h.mirrored + i] = v;
+                mx = std::max(mx, v);
             }
+            // running logsumexp of the posterior log-weights: only the fresh terms are exponentiated
+            double sum = (h.lse_sum > 0.0) ? h.lse_sum * std::exp(h.lse_max - mx) : 0.0;
+            if (mx > -std::numeric_limits<double>::infinity())
+                for (long long i = 0; i < fresh; ++i) sum += std::exp(mr.logw[h.mirrored + i] - mx);
+            h.lse_max = mx; h.lse_sum = sum;
             h.mirrored = ndead;
         }
-        std::vector<double> live_rows((size_t)std::max(nl, 1) * npars);
+        if (mr.live_rows.size() < (size_t)std::max(nl, 1) * npars) mr.live_rows.resize((size_t)std::max(nl, 1) * npars);
+        std::vector<double>& live_rows = mr.live_rows;
         for (int i = 0; i < nl; ++i) {
             const double* s = sl + (size_t)i * T;
             double* o = &live_rows[(size_t)i * npars];
@@ -497,19 +549,22 @@ struct Engine {
             o[D + P] = s[2 * D + P];
             o[D + P + 1] = s[2 * D + P + 1];
         }
-        std::vector<double> lw(std::max<long long>(ndead, 1));
-        if (ndead > 0) {
-            double m = *std::max_element(h.dead_logw.begin(), h.dead_logw.end());
-            double sum = 0.0;
-            for (long long i = 0; i < ndead; ++i) sum += std::exp(h.dead_logw[i] - m);
-            double lse = m + std::log(sum);
-            for (long long i = 0; i < ndead; ++i) lw[i] = h.dead_logw[i] - lse;
+        lap(1);
+        std::vector<double>& lw = mr.lw;
+        if (lw.empty()) lw.resize(1);
+        if (ndead > 0) {  // normalised posterior log-weights (nested_sampling.F90:574-575)
+            const double lse = h.lse_max + std::log(h.lse_sum);
+            const double* src = mr.logw.data();
+            double* dst = lw.data();
+            for (long long i = 0; i < ndead; ++i) dst[i] = src[i] - lse;
         }
         double lz = std::max(-std::numeric_limits<double>::max(), 2 * logZ_raw - 0.5 * logZ2_raw);
         double var = logZ2_raw - 2 * logZ_raw;
         std::vector<double> dummy(npars, 0.0);
-        dumper((int)ndead, nl, npars, live_rows.data(), ndead > 0 ? h.dead_rows.data() : dummy.data(), lw.data(), lz,
+        lap(2);
+        dumper((int)ndead, nl, npars, live_rows.data(), ndead > 0 ? mr.rows.data() : dummy.data(), lw.data(), lz,
                std::sqrt(var));
+        lap(3);
     }
 
     void grow(int r, int status) {
@@ -551,19 +606,24 @@ struct Engine {
             upload_bufs();
         }
         L.kp.want_dump = (dumper != nullptr && nruns == 1) ? 1 : 0;
+        double dbg_service_ms = 0, dbg_launch_ms = 0, dbg_finish_ms = 0, dbg_final_ms = 0;
+        auto now = [] { return std::chrono::steady_clock::now(); };
+        auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
         auto service = [&]() {  // hand one published dump to the user's dumper
+            auto ts = now();
             const long long nd = ctl->ndead;
             const double lz = ctl->logZ, lz2 = ctl->logZ2;
             dump(0, dumper, nd, lz, lz2, runs[0].live_snap.p, g_copy_stream);
             ++handled;
             ctl->ack_seq = handled;
+            dbg_service_ms += ms_since(ts);
         };
         for (;;) {
             if (ctl) {  // size the pinned staging now: (re)allocating pinned memory synchronises with the running kernel
                 g_pin_dead.need((size_t)runs[0].buf.cap_dead * (L.kp.cp.T + 1) * 8);
                 g_pin_live.need((size_t)L.kp.n * L.kp.cp.T * 8);
             }
-            launch_async();
+            { auto tl = now(); launch_async(); dbg_launch_ms += ms_since(tl); }
             if (ctl) {
                 try {
                     while (cudaEventQuery(ev1) == cudaErrorNotReady) {
@@ -577,7 +637,7 @@ struct Engine {
                     throw;
                 }
             }
-            launch_finish();
+            { auto tf = now(); launch_finish(); dbg_finish_ms += ms_since(tf); }
             bool all_done = true, regrow = false;
             for (int r = 0; r < nruns; ++r) {
                 int stt = runs[r].host_st.status;
@@ -592,9 +652,19 @@ struct Engine {
             if (all_done) break;
         }
         if (g_mgpu.world > 1) g_mgpu.epoch = runs[0].host_st.xepoch;
+        auto tfin = now();
         if (dumper)  // the final call: every point is dead (nested_sampling.F90:392)
             for (int r = 0; r < nruns; ++r)
                 dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, nullptr, stream);
+        dbg_final_ms = ms_since(tfin);
+        if (std::getenv("PC_DEBUG")) {
+            std::fprintf(stderr, "[pc dbg dump] copies %.3f ms, rows %.3f ms, weights %.3f ms, user dumper %.3f ms\n", g_dbg_dump[0],
+                         g_dbg_dump[1], g_dbg_dump[2], g_dbg_dump[3]);
+            g_dbg_dump[0] = g_dbg_dump[1] = g_dbg_dump[2] = g_dbg_dump[3] = 0;
+        }
+        if (std::getenv("PC_DEBUG"))
+            std::fprintf(stderr, "[pc dbg run] launch %.3f ms, dumps served %llu in %.3f ms, finish(wait+download) %.3f ms, final dump %.3f ms\n",
+                         dbg_launch_ms, handled, dbg_service_ms, dbg_finish_ms, dbg_final_ms);
         auto t1 = std::chrono::steady_clock::now();
         const KParams& k = L.kp;
         for (int r = 0; r < nruns; ++r) {
@@ -613,16 +683,14 @@ struct Engine {
             o.h2d_bytes = h2d; o.d2h_bytes = d2h;
             // 8T+8D per slice step, 8T per chain (seed read) + 8T (dead record), 8D^2 per generation
             {
-                int khz = 0, dev = 0;
-                cudaGetDevice(&dev);
-                cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+                const int khz = sm_clock_khz();
                 const long long cyc[8] = {s.cyc_wait, s.cyc_S, s.cyc_fin, s.cyc_U, s.cyc_prep, s.cyc_white, s.cyc_slice, s.cyc_total};
                 for (int i = 0; i < 8; ++i) o.phase_ms[i] = khz > 0 ? (double)cyc[i] / (double)khz : 0.0;
             }
             if (std::getenv("PC_DEBUG")) {
-                int khz = 1; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+                const int khz = std::max(1, sm_clock_khz());
                 std::fprintf(stderr, "[pc dbg ms]");
-                for (int i = 0; i < 8; ++i) std::fprintf(stderr, " %.3f", (double)s.dbg[i] / khz);
+                for (int i = 0; i < 16; ++i) std::fprintf(stderr, " %.3f", (double)s.dbg[i] / khz);
                 std::fprintf(stderr, "\n");
             }
             o.algorithmic_bytes = s.nslices * (8LL * k.cp.T + 8LL * k.cp.D) + s.nchains * 16LL * k.cp.T + s.ngen * 8LL * k.cp.D * k.cp.D;

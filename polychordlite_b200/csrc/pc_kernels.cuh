@@ -28,8 +28,9 @@ namespace pc {
 enum Status : int { ST_RUNNING = 0, ST_DONE = 1, ST_NEED_DEAD = 2, ST_NEED_PHANTOM = 3, ST_DUMP = 4, ST_ERROR = -1 };
 
 constexpr double NEG_BIG = -1e300;  // log(0) stand-in that survives additions without NaN
-constexpr int COV_ACC = 20;         // covariance accumulators per lane and pass
+constexpr int COV_TPP = 10;         // 8x8 tiles of the moment matrix a warp accumulates per pass of phase U (2 registers each)
 constexpr int U_TILE = 256;         // records per phantom tile of phase U (= threads per CTA)
+constexpr int U_BATCH = 8;          // records a warp of phase U keeps in flight
 
 // Mutable per-run scalars (device global memory; the host reads them between launches).
 struct DevRun {
@@ -58,7 +59,7 @@ struct DevRun {
     int order_off;       // 0 or n: which half of rb.order is current
     // SM-clock cycle counters of the phases (thread 0 of CTA 0; chain phases: warp 0 of the first chain CTA)
     long long cyc_wait, cyc_S, cyc_fin, cyc_U, cyc_prep, cyc_white, cyc_slice, cyc_total;
-    long long dbg[8];    // scratch cycle counters for profiling experiments (printed when PC_DEBUG is set)
+    long long dbg[16];    // scratch cycle counters for profiling experiments (printed when PC_DEBUG is set)
     unsigned int bar;    // group barrier, one arrival per CTA (monotonic)
     unsigned int wbar;   // chains-done barrier, one arrival per warp (monotonic)
 };
@@ -87,7 +88,7 @@ struct RunBuf {
     double* chol;      // D x D column-major
     double* cov;       // D x D column-major
     double* partial;   // per CTA: [0]=count, [1..D]=sum x, then ntri covariance partials
-    double* gsum;      // [0] survivors of all ranks, [1] unused, [2..2+D) sum x over live + all phantoms
+    double* gsum;      // [0] surviving phantoms of all ranks, [2..2+D) mean of live + phantom cube coordinates, [2+D..2+2D) pivot of the next update
     long long* pcount; // survivor count of each phantom tile (phase U)
     double* nh;        // global direction scratch (used when the directions do not fit in smem)
     long long cap_dead, cap_ph;

@@ -22,6 +22,7 @@ __device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st
             rb.chol[e] = v;
             rb.cov[e] = v;
         }
+        for (int e = tid; e < D; e += blockDim.x) rb.gsum[2 + D + e] = 0.5;  // first pivot of the covariance moments: the cube centre
         if (tid == 0) {
             st->logZ = st->logZ2 = st->logZX = p.cp.logzero;  // run_time_info.f90:165-175
             st->logX = st->logXX = 0.0;
@@ -232,7 +233,7 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
         st->do_update = (lX_new <= st->logX_last_update + p.log_comp) ? 1 : 0;  // nested_sampling.F90:321
         st->status = ST_RUNNING;
         long long q4 = clock64();
-        
+        st->dbg[6] += q1 - q0; st->dbg[7] += q2 - q1; st->dbg[8] += q3 - q2; st->dbg[9] += q4 - q3;
     }
     return true;
 }
@@ -249,138 +250,75 @@ __device__ inline void phase_S2(const KParams& p, const RunBuf& rb, DevRun* st, 
 // clean_phantoms (run_time_info.f90:820-877) + calculate_covmats (:601-641) at the update cadence.
 // The phantom pool is cut into tiles of blockDim.x records dealt round-robin to the CTAs of the run (old
 // phantoms are mostly dead, new ones mostly alive: contiguous chunks would be badly balanced).
-//   pass 1  per tile: survivor count (rb.pcount[tile]); per CTA: sum of the survivors' and its live points' x
-//   pass 2  per tile: stable compaction into the other pool at the tile's prefix offset, fused with the centred
-//           outer products; per CTA partial covariance.  CTA 0 finishes (finish_update).
-// Lane r of a warp owns dimension r, r+32, ... of the running sums; kept records are loaded four at a time.
+//   pass A  per tile: survivor count (rb.pcount[tile]); only the logL column is read
+//   pass B  per tile: stable compaction into the other pool at the tile's prefix offset, fused with the first
+//           and second moments of the survivors' (and this CTA's share of the live points') cube coordinates
+//           about a pivot c -- the mean of the previous update (the cube centre at first) -- so the data is
+//           read once:  cov = S2/N - d d^T with d = S1/N, mean = c + d.  |d| is a small fraction of the
+//           spread (the mean moves little between updates), so nothing cancels.
+//   CTA 0 finishes (finish_update): partials in CTA order, all-reduce over the ranks of a sharded run,
+//   calc_cholesky.
+// Lane r of a warp owns dimension r, r+32, ... of S1 and COV_ACC entries of the packed triangle of S2.
 
-__device__ inline void phase_U1(const KParams& p, const RunBuf& rb, DevRun* st, int cta, int NG, unsigned char* smem_warp0,
-                                int warp_bytes, int* s_cnt) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
-    const int D = p.cp.D, T = p.cp.T, n = p.n;
+__device__ inline void phase_UA(const KParams& p, const RunBuf& rb, DevRun* st, int cta, int NG) {
+    const int tid = threadIdx.x, T = p.cp.T;
     const long long total = vload(&st->nphantom);
     const double Lstar = vload(&st->Lstar);
     const double* src = rb.ph[vload(&st->cur_pool)];
     const long long ntiles = (total + U_TILE - 1) / U_TILE;
-    const int lchunk = (n + NG - 1) / NG, l0 = min(n, cta * lchunk), l1 = min(n, l0 + lchunk);
-    double* mine = (double*)(smem_warp0 + (size_t)warp * warp_bytes);  // [0..D) = sum x of this warp
-    __syncthreads();
-    double sx[4] = {0.0, 0.0, 0.0, 0.0};  // D <= 128
-    auto add4 = [&](const double* r0, const double* r1, const double* r2, const double* r3) {
+    // keys of up to four tiles in flight before the first count
+    for (long long t0 = cta; t0 < ntiles; t0 += 4LL * NG) {
+        bool keep[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int e = lane + 32 * j;
-            if (e < D) {
-                const double v0 = r0 ? __ldcg(r0 + e) : 0.0, v1 = r1 ? __ldcg(r1 + e) : 0.0;
-                const double v2 = r2 ? __ldcg(r2 + e) : 0.0, v3 = r3 ? __ldcg(r3 + e) : 0.0;
-                if (r0) sx[j] += v0;
-                if (r1) sx[j] += v1;
-                if (r2) sx[j] += v2;
-                if (r3) sx[j] += v3;
+            const long long t = t0 + (long long)j * NG, rec = t * U_TILE + tid;
+            keep[j] = t < ntiles && rec < total && !(Lstar > __ldcg(src + (size_t)rec * T + T - 1));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long t = t0 + (long long)j * NG;
+            if (t < ntiles) {  // uniform over the CTA
+                const int c = __syncthreads_count(keep[j]);
+                if (tid == 0) rb.pcount[t] = c;
             }
         }
-    };
-    for (long long t = cta; t < ntiles; t += NG) {
-        const long long tile = t * U_TILE, rec = tile + tid;
-        const bool keep = rec < total && !(Lstar > __ldcg(src + (size_t)rec * T + T - 1));
-        unsigned rem = __ballot_sync(FULL, keep);
-        if (lane == 0) s_cnt[warp] = __popc(rem);
-        while (rem) {
-            const double* r[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (rem) { const int b = __ffs(rem) - 1; rem &= rem - 1; r[j] = src + (size_t)(tile + warp * 32 + b) * T; }
-                else r[j] = nullptr;
-            }
-            add4(r[0], r[1], r[2], r[3]);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int c = 0;
-            for (int w = 0; w < W; ++w) c += s_cnt[w];
-            rb.pcount[t] = c;
-        }
-        __syncthreads();
     }
-    for (int rec = l0 + warp * 4; rec < l1 && p.sh.rank == 0; rec += W * 4) {  // the live points are replicated: rank 0 counts them
-        const double* b = rb.live + (size_t)rec * T;
-        add4(b, rec + 1 < l1 ? b + T : nullptr, rec + 2 < l1 ? b + 2 * T : nullptr, rec + 3 < l1 ? b + 3 * T : nullptr);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (lane + 32 * j < D) mine[lane + 32 * j] = sx[j];
-    __syncthreads();
-    double* out = rb.partial + (size_t)cta * p.partial_stride;
-    for (int e = tid; e < D; e += blockDim.x) {
-        double s = 0.0;
-        for (int w = 0; w < W; ++w) s += ((double*)(smem_warp0 + (size_t)w * warp_bytes))[e];
-        out[1 + e] = s;
-    }
-    __syncthreads();
 }
 
-// Between the passes (CTA 0): survivors and sum x of this rank from the per-CTA partials, all-reduced over the
-// ranks of a sharded run in rank order, into rb.gsum.  Returns false when a peer does not answer.
-__device__ inline bool reduce_stats(const KParams& p, const RunBuf& rb, DevRun* st, int NG, double* s_tmp) {
-    const int tid = threadIdx.x, D = p.cp.D;
-    const long long total = vload(&st->nphantom);
-    const long long ntiles = (total + U_TILE - 1) / U_TILE;
-    __shared__ int s_ok;
-    double cnt = 0.0;
-    for (long long g = tid; g < ntiles; g += blockDim.x) cnt += (double)__ldcg(rb.pcount + g);
-    cnt = block_sum(cnt, s_tmp);  // exact: integers
-    for (int e = tid; e < D; e += blockDim.x) {
-        double s = 0.0;
-#pragma unroll 8
-        for (int g = 0; g < NG; ++g) s += __ldcg(rb.partial + (size_t)g * p.partial_stride + 1 + e);
-        s_tmp[64 + e] = s;
-    }
-    __syncthreads();
-    if (p.sh.world > 1) {
-        for (int q = 0; q < p.sh.world; ++q) {
-            double* slot = p.sh.xpart[q] + (size_t)p.sh.rank * p.sh.xstride;
-            if (tid == 0) slot[0] = cnt;
-            for (int e = tid; e < D; e += blockDim.x) slot[2 + e] = s_tmp[64 + e];
-        }
-        __syncthreads();
-        if (tid == 0) s_ok = xgpu_barrier(p.sh, st) ? 1 : 0;
-        __syncthreads();
-        if (!s_ok) return false;
-        const double* mine = p.sh.xpart[p.sh.rank];
-        if (tid == 0) {
-            double c = 0.0;
-            for (int r = 0; r < p.sh.world; ++r) c += __ldcg(mine + (size_t)r * p.sh.xstride);
-            rb.gsum[0] = c;
-        }
-        for (int e = tid; e < D; e += blockDim.x) {
-            double s = 0.0;
-            for (int r = 0; r < p.sh.world; ++r) s += __ldcg(mine + (size_t)r * p.sh.xstride + 2 + e);
-            rb.gsum[2 + e] = s;
-        }
-    } else {
-        if (tid == 0) rb.gsum[0] = cnt;
-        for (int e = tid; e < D; e += blockDim.x) rb.gsum[2 + e] = s_tmp[64 + e];
-    }
-    __syncthreads();
-    return true;
+// D(8x8) += A(8x4) * B(4x8) on the FP64 tensor cores (DMMA).  Lane l holds A[l/4][l%4], B[l%4][l/4] and
+// C[l/4][2*(l%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-__device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, int cta, int NG, unsigned char* smem_warp0,
+// Pass B.  The moments are one matrix product: with the augmented, pivot-shifted coordinate rows
+// z = [x - c, 1, 0...] (Dp8 = 8*ceil((D+1)/8) entries) of the kept records, M = sum z z^T holds S2 in its leading
+// D x D block, S1 in column D and the record count at (D, D).  A warp stages U_BATCH = 8 records (two k-steps of
+// the m8n8k4 FP64 tensor-core MMA) in shared memory and multiplies the 8x8 tiles of the upper triangle of M,
+// COV_TPP tiles per pass over the data (one pass up to D = 31).
+__device__ inline void phase_UB(const KParams& p, const RunBuf& rb, DevRun* st, int cta, int NG, unsigned char* smem_warp0,
                                 int warp_bytes, int* s_cnt) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
-    const int D = p.cp.D, T = p.cp.T, n = p.n, ntri = p.ntri;
+    const int D = p.cp.D, T = p.cp.T, n = p.n;
     const int Dpad = (D + 1) & ~1;
+    const int Dp8 = (D + 1 + 7) & ~7, SX = Dp8 + 4;   // row stride of the staged batch: SX mod 16 in {4, 12}, conflict-free fragments
+    const int nt = Dp8 >> 3, ntl = nt * (nt + 1) / 2;  // 8-wide dimension tiles, tiles of the upper triangle
     const long long total = vload(&st->nphantom);
     const double Lstar = vload(&st->Lstar);
     const int pool = vload(&st->cur_pool);
-    const double* src = rb.ph[pool];
-    double* dst = rb.ph[pool ^ 1];
+    const double* __restrict__ src = rb.ph[pool];
+    double* __restrict__ dst = rb.ph[pool ^ 1];
     const long long ntiles = (total + U_TILE - 1) / U_TILE;
     const int lchunk = (n + NG - 1) / NG, l0 = min(n, cta * lchunk), l1 = min(n, l0 + lchunk);
-    double* mine = (double*)(smem_warp0 + (size_t)warp * warp_bytes);  // [0..Dpad) mean (warp 0's copy is used), [Dpad..2Dpad) dv, then COV_ACC*32 partials
-    double* s_mean = (double*)smem_warp0;
-    double* s_dv = mine + Dpad;
+    // per warp: [0..Dpad) pivot (warp 0's copy is used) | U_BATCH x SX staged rows.  After a pass the whole per-warp
+    // area (behind the pivot) is reused as the CTA's Dp8 x Dp8 matrix the warps add their tiles to, in warp order.
+    double* s_piv = (double*)smem_warp0;
+    double* s_x = (double*)(smem_warp0 + (size_t)warp * warp_bytes) + Dpad;
+    double* s_M = (double*)smem_warp0 + Dpad;
     long long* s_base = (long long*)(s_cnt + 16);  // [0] survivors in the tiles before this CTA's first tile, [1] all survivors
+    const bool tmr = (cta == 0 && tid == 0);
+    const long long z0 = clock64();
     __syncthreads();
     // survivors before tile `upto` (exclusive) starting from tile `from`: one warp, coalesced
     auto count_range = [&](long long from, long long upto) -> long long {
@@ -395,87 +333,99 @@ __device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, 
         const long long all = before + count_range(min((long long)cta, ntiles), ntiles);
         if (lane == 0) { s_base[0] = before; s_base[1] = all; }
     }
+    for (int e = tid; e < D; e += blockDim.x) s_piv[e] = __ldcg(rb.gsum + 2 + D + e);
     __syncthreads();
-    long long base = s_base[0];
-    const long long tot = s_base[1];
-    const double N = (double)n + __ldcg(rb.gsum);  // live points + the surviving phantoms of all ranks
-    for (int e = tid; e < D; e += blockDim.x) s_mean[e] = __ldcg(rb.gsum + 2 + e) / N;
-    if (cta == 0 && tid == 0) st->ph_kept = tot;
-    __syncthreads();
+    const long long base = s_base[0];
+    if (cta == 0 && tid == 0) st->ph_kept = s_base[1];
+    const int JT = (T + 31) >> 5, JD = (D + 31) >> 5;  // 32-wide column chunks of a record / of its cube coordinates
+    const int fr = lane >> 2, fk = lane & 3;           // fragment row (dimension within a tile) and k index (record within a k-step)
+    double* outp = rb.partial + (size_t)cta * p.partial_stride;
     for (int pass = 0; pass < p.cov_passes; ++pass) {
-        double acc[COV_ACC];
-        int ab[COV_ACC];
+        double c0[COV_TPP], c1[COV_TPP];
+        int tl[COV_TPP];  // (ti << 8) | tj of the pass's tiles, -1 beyond the last
 #pragma unroll
-        for (int a = 0; a < COV_ACC; ++a) {
-            acc[a] = 0.0;
-            int idx = (pass * COV_ACC + a) * 32 + lane;
-            int ai = 0, bi = 0;
-            if (idx < ntri) {
-                ai = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
-                while (ai * (ai + 1) / 2 > idx) --ai;
-                while ((ai + 1) * (ai + 2) / 2 <= idx) ++ai;
-                bi = idx - ai * (ai + 1) / 2;
-            }
-            ab[a] = (idx < ntri) ? ((ai << 16) | bi) : -1;
+        for (int q = 0; q < COV_TPP; ++q) {
+            c0[q] = c1[q] = 0.0;
+            const int idx = pass * COV_TPP + q;
+            int tj = 0;
+            while ((tj + 1) * (tj + 2) / 2 <= idx) ++tj;  // tiles ordered (0,0) (0,1) (1,1) (0,2) ...
+            const int ti = idx - tj * (tj + 1) / 2;
+            tl[q] = idx < ntl ? ((ti << 8) | tj) : -1;
         }
-        // centred coordinates of one record -> this warp's dv, then the lane's outer-product entries
-        auto accumulate = [&](const double (&v)[4]) {
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (lane + 32 * j < D) s_dv[lane + 32 * j] = v[j] - s_mean[lane + 32 * j];
-            __syncwarp();
-#pragma unroll
-            for (int a = 0; a < COV_ACC; ++a)
-                if (ab[a] >= 0) acc[a] += s_dv[ab[a] >> 16] * s_dv[ab[a] & 0xffff];
-        };
-        auto load_x = [&](const double* r, double (&v)[4]) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = (lane + 32 * j < D) ? __ldcg(r + lane + 32 * j) : 0.0;
-        };
+        for (int e = lane; e < U_BATCH * SX; e += 32) s_x[e] = 0.0;  // the padding columns stay zero
+        __syncwarp();
+        // The CTA's work items: its phantom tiles (t = cta, cta + NG, ...), then its share of the live points cut
+        // into pseudo-tiles of U_TILE records (never copied).  A warp takes the kept records of its 32-record
+        // segment in batches of U_BATCH: all loads of a batch are issued before the first use.  Pass 0 copies
+        // the phantom records to their place in the other pool (stable compaction).
         long long tbase = base;
-        for (long long t = cta; t < ntiles; t += NG) {
-            const long long tile = t * U_TILE, rec = tile + tid;
-            const bool keep = rec < total && !(Lstar > __ldcg(src + (size_t)rec * T + T - 1));
+        const long long z1 = clock64();
+        if (tmr) st->dbg[12] += z1 - z0;
+        const long long my_tiles = (ntiles > cta) ? (ntiles - cta + NG - 1) / NG : 0;
+        const int my_live = (p.sh.rank == 0) ? (l1 - l0) : 0;  // the live points are replicated: rank 0 counts them
+        const long long my_items = my_tiles + (my_live + U_TILE - 1) / U_TILE;
+        for (long long it = 0; it < my_items; ++it) {
+            const bool is_ph = it < my_tiles;
+            const long long t = cta + it * NG;
+            const double* __restrict__ rbase;   // record 0 of this warp's segment
+            bool keep;
+            if (is_ph) {
+                const long long tile = t * U_TILE, rec = tile + tid;
+                keep = rec < total && !(Lstar > __ldcg(src + (size_t)rec * T + T - 1));
+                rbase = src + (size_t)(tile + warp * 32) * T;
+            } else {
+                const int lrec = l0 + (int)(it - my_tiles) * U_TILE + tid;
+                keep = lrec < l1;
+                rbase = rb.live + (size_t)(l0 + (int)(it - my_tiles) * U_TILE + warp * 32) * T;
+            }
             const unsigned bal = __ballot_sync(FULL, keep);
-            __syncthreads();
-            if (lane == 0) s_cnt[warp] = __popc(bal);
-            __syncthreads();
             int woff = 0;
-            for (int w = 0; w < warp; ++w) woff += s_cnt[w];
-            if (pass == 0) {  // stable compaction: survivor number woff+kk of the tile goes to tbase+woff+kk
-                unsigned rem = bal;
-                int kk = 0;
-                while (rem) {
-                    const int b0 = __ffs(rem) - 1; rem &= rem - 1;
-                    const int b1 = rem ? __ffs(rem) - 1 : -1; if (rem) rem &= rem - 1;
-                    const double* r0 = src + (size_t)(tile + warp * 32 + b0) * T;
-                    const double* r1 = src + (size_t)(tile + warp * 32 + max(b1, 0)) * T;
-                    double* d0 = dst + (size_t)(tbase + woff + kk) * T;
-                    for (int e = lane; e < T; e += 32) {
-                        const double v0 = __ldcg(r0 + e), v1 = __ldcg(r1 + e);
-                        d0[e] = v0;
-                        if (b1 >= 0) d0[T + e] = v1;
-                    }
-                    kk += (b1 >= 0) ? 2 : 1;
-                }
+            const bool copy = is_ph && pass == 0;
+            if (copy) {  // survivor number woff+kk of the tile goes to tbase+woff+kk
+                __syncthreads();
+                if (lane == 0) s_cnt[warp] = __popc(bal);
+                __syncthreads();
+                for (int w = 0; w < warp; ++w) woff += s_cnt[w];
             }
-            {   // outer products, the next record's coordinates in flight while the current one is accumulated
-                unsigned rem = bal;
-                double cur[4], nxt[4];
-                if (rem) { const int b = __ffs(rem) - 1; rem &= rem - 1; load_x(src + (size_t)(tile + warp * 32 + b) * T, cur); }
-                bool have = bal != 0;
-                while (have) {
-                    const bool more = rem != 0;
-                    if (more) { const int b = __ffs(rem) - 1; rem &= rem - 1; load_x(src + (size_t)(tile + warp * 32 + b) * T, nxt); }
-                    accumulate(cur);
+            const int jmax = copy ? JT : JD;
+            unsigned rem = bal;
+            int kk = 0;
+            while (rem) {
+                const double* rp[U_BATCH];
+                int nb = 0;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
-                    have = more;
+                for (int b2 = 0; b2 < U_BATCH; ++b2) {
+                    rp[b2] = rbase;
+                    if (rem) { const int bit = __ffs(rem) - 1; rem &= rem - 1; rp[b2] = rbase + (size_t)bit * T; ++nb; }
                 }
+                double* out = dst + (size_t)(tbase + woff + kk) * T;
+                __syncwarp();
+                for (int j = 0; j < jmax; ++j) {
+                    const int e = lane + 32 * j;
+                    double v[U_BATCH];
+#pragma unroll
+                    for (int b2 = 0; b2 < U_BATCH; ++b2) v[b2] = (b2 < nb && e < T) ? __ldcg(rp[b2] + e) : 0.0;
+                    const double pv = e < D ? s_piv[e] : 0.0;
+#pragma unroll
+                    for (int b2 = 0; b2 < U_BATCH; ++b2) {
+                        if (copy && b2 < nb && e < T) out[(size_t)b2 * T + e] = v[b2];
+                        // rows beyond the batch are zero; column D carries the 1 of the augmented row
+                        if (e <= D) s_x[b2 * SX + e] = b2 < nb ? (e < D ? v[b2] - pv : 1.0) : 0.0;
+                    }
+                }
+                if ((D & 31) == 0 && lane < U_BATCH) s_x[lane * SX + D] = lane < nb ? 1.0 : 0.0;  // column D starts a chunk the loop above did not reach
+                __syncwarp();
+#pragma unroll
+                for (int ks = 0; ks < U_BATCH / 4; ++ks) {
+                    const double* row = s_x + (4 * ks + fk) * SX + fr;
+#pragma unroll
+                    for (int q = 0; q < COV_TPP; ++q)
+                        if (tl[q] >= 0) dmma884(c0[q], c1[q], row[(tl[q] >> 8) << 3], row[(tl[q] & 0xff) << 3]);
+                }
+                kk += nb;
             }
-            // offset of this CTA's next tile
-            if (t + NG < ntiles) {
+            // offset of this CTA's next phantom tile
+            if (copy && t + NG < ntiles) {
                 __syncthreads();
                 if (warp == 0) {
                     const long long c = count_range(t, t + NG);
@@ -485,27 +435,39 @@ __device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, 
                 tbase = s_base[0];
             }
         }
-        for (int rec = l0 + warp; rec < l1 && p.sh.rank == 0; rec += W) {
-            double v[4];
-            load_x(rb.live + (size_t)rec * T, v);
-            accumulate(v);
-        }
-        // combine the warps of this CTA in warp order
+        const long long z3 = clock64();
+        if (tmr) st->dbg[13] += z3 - z1;
+        // the warps add their tiles to the CTA's matrix in warp order (deterministic), then the pass's entries go
+        // to this CTA's partial: [0] count, [1..1+D) S1, then the packed triangle of S2 (entry (a <= b) at b(b+1)/2 + a)
         __syncthreads();
-        double* pacc = mine + 2 * Dpad;
+        for (int e = tid; e < Dp8 * Dp8; e += blockDim.x) s_M[e] = 0.0;
+        __syncthreads();
+        for (int w = 0; w < W; ++w) {
+            if (warp == w) {
 #pragma unroll
-        for (int a = 0; a < COV_ACC; ++a) pacc[a * 32 + lane] = acc[a];
-        __syncthreads();
-        double* out = rb.partial + (size_t)cta * p.partial_stride + 1 + D + (size_t)pass * COV_ACC * 32;
-        for (int e = tid; e < COV_ACC * 32; e += blockDim.x) {
-            if (pass * COV_ACC * 32 + e < ntri) {
-                double s = 0.0;
-                for (int w = 0; w < W; ++w)
-                    s += ((double*)(smem_warp0 + (size_t)w * warp_bytes))[2 * Dpad + e];
-                out[e] = s;
+                for (int q = 0; q < COV_TPP; ++q)
+                    if (tl[q] >= 0) {
+                        const int a2 = ((tl[q] >> 8) << 3) + fr, b2 = ((tl[q] & 0xff) << 3) + 2 * fk;
+                        s_M[a2 * Dp8 + b2] += c0[q];
+                        s_M[a2 * Dp8 + b2 + 1] += c1[q];
+                    }
             }
+            __syncthreads();
+        }
+        for (int e = tid; e < COV_TPP * 64; e += blockDim.x) {
+            const int idx = pass * COV_TPP + (e >> 6);
+            if (idx >= ntl) continue;
+            int tj = 0;
+            while ((tj + 1) * (tj + 2) / 2 <= idx) ++tj;
+            const int ti = idx - tj * (tj + 1) / 2;
+            const int a2 = (ti << 3) + ((e >> 3) & 7), b2 = (tj << 3) + (e & 7);
+            if (a2 > b2 || b2 > D) continue;
+            const double v = s_M[a2 * Dp8 + b2];
+            if (b2 == D) outp[a2 == D ? 0 : 1 + a2] = v;
+            else outp[1 + D + b2 * (b2 + 1) / 2 + a2] = v;
         }
         __syncthreads();
+        if (tmr) st->dbg[15] += clock64() - z3;
     }
 }
 
@@ -513,51 +475,78 @@ __device__ inline void phase_U2(const KParams& p, const RunBuf& rb, DevRun* st, 
 __device__ inline bool finish_update(const KParams& p, const RunBuf& rb, DevRun* st, int NG, double* s_cov, double* s_L) {
     const int tid = threadIdx.x, D = p.cp.D, ntri = p.ntri;
     const long long tot = st->ph_kept;
-    const double Nglob = __ldcg(rb.gsum);
-    const double N = (double)p.n + Nglob;
     __shared__ int s_ok;
+    __shared__ double s_N;
     auto unpack = [](int idx, int& ai, int& bi) {
         ai = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
         while (ai * (ai + 1) / 2 > idx) --ai;
         while ((ai + 1) * (ai + 2) / 2 <= idx) ++ai;
         bi = idx - ai * (ai + 1) / 2;
     };
-    for (int idx = tid; idx < ntri; idx += blockDim.x) {  // this rank's outer products, CTA order
+    // scratch until the matrix is formed: the packed triangle of S2 in s_L, d = S1/N behind the matrix in s_cov
+    double* s_S2 = s_L;             // ntri <= D*D
+    double* s_d = s_cov + D * D;    // D (the layout reserves it, make_layout_w)
+    // this rank's moments: S1 and S2 partials summed in CTA order (coalesced over the entries, 8 CTAs in flight)
+    for (int e = tid; e < D + ntri; e += blockDim.x) {
         double s = 0.0;
-#pragma unroll 8
-        for (int g = 0; g < NG; ++g) s += __ldcg(rb.partial + (size_t)g * p.partial_stride + 1 + D + idx);
-        if (p.sh.world > 1) {
-            for (int q = 0; q < p.sh.world; ++q) p.sh.xpart[q][(size_t)p.sh.rank * p.sh.xstride + 2 + D + idx] = s;
-        } else {
-            int ai, bi;
-            unpack(idx, ai, bi);
-            s /= N;  // calculate_covmats divides by N, not N-1 (run_time_info.f90:601-641)
-            s_cov[ai + bi * D] = s;
-            s_cov[bi + ai * D] = s;
+        for (int g0 = 0; g0 < NG; g0 += 32) {  // 32 partials in flight, added in CTA order
+            double v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (g0 + j < NG) ? __ldcg(rb.partial + (size_t)(g0 + j) * p.partial_stride + 1 + e) : 0.0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s += v[j];
         }
+        if (p.sh.world > 1) {
+            for (int q = 0; q < p.sh.world; ++q) p.sh.xpart[q][(size_t)p.sh.rank * p.sh.xstride + 2 + e] = s;
+        } else if (e < D) s_d[e] = s; else s_S2[e - D] = s;
     }
-    __syncthreads();
+    double Nglob = (double)tot;  // surviving phantoms of all ranks
     if (p.sh.world > 1) {
+        if (tid == 0)
+            for (int q = 0; q < p.sh.world; ++q) p.sh.xpart[q][(size_t)p.sh.rank * p.sh.xstride] = (double)tot;
+        __syncthreads();
         if (tid == 0) s_ok = xgpu_barrier(p.sh, st) ? 1 : 0;
         __syncthreads();
         if (!s_ok) return false;
         const double* mine = p.sh.xpart[p.sh.rank];
-        for (int idx = tid; idx < ntri; idx += blockDim.x) {
+        for (int e = tid; e < D + ntri; e += blockDim.x) {
             double s = 0.0;
-            for (int r = 0; r < p.sh.world; ++r) s += __ldcg(mine + (size_t)r * p.sh.xstride + 2 + D + idx);
-            int ai, bi;
-            unpack(idx, ai, bi);
-            s /= N;
-            s_cov[ai + bi * D] = s;
-            s_cov[bi + ai * D] = s;
+            for (int r = 0; r < p.sh.world; ++r) s += __ldcg(mine + (size_t)r * p.sh.xstride + 2 + e);
+            if (e < D) s_d[e] = s; else s_S2[e - D] = s;
+        }
+        if (tid == 0) {
+            double c = 0.0;
+            for (int r = 0; r < p.sh.world; ++r) c += __ldcg(mine + (size_t)r * p.sh.xstride);
+            s_N = c;
         }
         __syncthreads();
+        Nglob = s_N;
     }
+    __syncthreads();
+    const double N = (double)p.n + Nglob;
+    for (int e = tid; e < D; e += blockDim.x) {
+        const double d = s_d[e] / N;
+        s_d[e] = d;
+        const double mean = __ldcg(rb.gsum + 2 + D + e) + d;
+        rb.gsum[2 + e] = mean;       // the mean of live + phantom cube coordinates
+        rb.gsum[2 + D + e] = mean;   // ... is the pivot of the next update
+    }
+    __syncthreads();
+    // cov = S2/N - d d^T (calculate_covmats divides by N, not N-1: run_time_info.f90:601-641)
+    for (int idx = tid; idx < ntri; idx += blockDim.x) {
+        int ai, bi;
+        unpack(idx, ai, bi);
+        const double v = s_S2[idx] / N - s_d[ai] * s_d[bi];
+        s_cov[ai + bi * D] = v;
+        s_cov[bi + ai * D] = v;
+    }
+    __syncthreads();
     int fb = 0;
     if (tid < 32) fb = warp_cholesky(s_cov, s_L, D);  // calc_cholesky (utils.F90:621-649) in shared memory
     __syncthreads();
     for (int e = tid; e < D * D; e += blockDim.x) { rb.cov[e] = s_cov[e]; rb.chol[e] = s_L[e]; }
     if (tid == 0) {
+        rb.gsum[0] = Nglob;
         st->chol_fallback += fb;
         st->cov_N = N;
         st->nphantom = tot;
@@ -717,7 +706,10 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
             }
             prep_uid = ~0ull;  // phase S overlays this CTA's chain scratch
         }
+        const long long tg0 = clock64();
         group_sync(&st->bar, NG);
+        const long long tg1 = clock64();
+        if (ctimer) st->dbg[10] += tg1 - tg0;
         if (vload(&st->status) != ST_RUNNING) {
             if (timer) st->cyc_total += clock64() - t_start;
             return;
@@ -796,6 +788,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                             rb.dead[(size_t)(ndead_base + k) * T + e] = __ldcg(rb.live + (size_t)dslot * T + e);
                     double* last = sharded ? xin_mine + (size_t)k * T : rb.live + (size_t)dslot * T;
                     long long tc2 = clock64();
+                    if (ctimer && j == 0) st->dbg[11] += tc2 - tg1;
                     double lfin = slice_chain<G, DPL, KIND>(p.cp, M, rb.seed, uid, x, Lstar, b,
                                                       pool + (size_t)(nph_base + (long long)cl * (R - 1)) * T, last, nlike,
                                                       (cta == c0 && warp == 0) ? st->dbg : nullptr);
@@ -867,14 +860,23 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                 scatter_due = false;
                 group_sync(&st->bar, NG);
             }
-            phase_U1(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt);
+            long long ua0 = clock64();
+            phase_UA(p, rb, st, cta, NG);
+            long long ua1 = clock64();
             group_sync(&st->bar, NG);
-            if (cta == 0 && !reduce_stats(p, rb, st, NG, sc) && tid == 0) st->status = ST_ERROR;
-            group_sync(&st->bar, NG);
-            phase_U2(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt);
+            long long ua2 = clock64();
+            phase_UB(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt);
+            long long ua3 = clock64();
+#ifdef PC_EXPERIMENT_UB_TWICE
+            __syncthreads();
+            phase_UB(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt);
+            if (timer) st->dbg[12] += clock64() - ua3;
+            ua3 = clock64();
+#endif
+            if (timer) { st->dbg[2] += ua1 - ua0; st->dbg[3] += ua2 - ua1; st->dbg[4] += ua3 - ua2; st->dbg[5] -= ua3; }
             if (cta == 0 && tid == 0) st->update_pending = 1;
             group_sync(&st->bar, NG);
-            if (timer) { st->cyc_wait += tu1 - tu0; st->cyc_U += clock64() - tu1; }
+            if (timer) { st->cyc_wait += tu1 - tu0; st->cyc_U += clock64() - tu1; st->dbg[5] += clock64(); }
             have_wtarget = false;
             if (will_chain) {  // the Cholesky factor is about to change: whiten after the barrier
                 prep_uid = (unsigned long long)(nchains_base + K + knext);
