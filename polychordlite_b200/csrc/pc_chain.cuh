@@ -324,57 +324,59 @@ __device__ inline void prep_chain(int D, int R, int LD, unsigned seed, unsigned 
 
 // ------------------------------------------------------------------------------------------
 // whiten_chain: nhats = matmul(cholesky, nhats) (chordal_sampling.f90:73), w = 3*|nhat|, nhat /= |nhat|
-// (:80-82) for all R columns, in place.  chol: D x D column-major LOWER-triangular factor.
+// (:80-82) for all R columns, in place.  chol: D x D column-major LOWER-triangular factor (zeros above).
+//
+// The product runs on the FP64 tensor cores: for a block of 8 columns the warp accumulates the 8-row tiles of
+// L * Q with m8n8k4 DMMAs (tiles of L above the diagonal are skipped), so each lane ends up with two columns'
+// entries of rows fr, fr+8, ...; the column norms are finished with three shuffles and the normalised columns
+// are written back over the raw ones (every read of a column block precedes its writes).
+// MAXMT = 8-row tiles the instantiation can hold (>= ceil(D/8)).
 // ------------------------------------------------------------------------------------------
+template <int MAXMT>
 __device__ inline void whiten_chain(int D, int R, int LD, const double* chol, const ChainScratch& cs) {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, fr = lane >> 2, fk = lane & 3;
     double* nh = cs.nh;
-    // Half-warp h takes column 2j+h; its lane r' computes rows r', r'+16, ... (row r needs q[0..r]).  All reads
-    // of an iteration precede its writes, and columns are independent, so the product is formed in place.
-    const int h = lane >> 4, rp = lane & 15;
-    constexpr int MAXROWS = 8;  // D <= 128
-    for (int c0 = 0; c0 < R; c0 += 2) {
-        const int col = c0 + h;
-        double out[MAXROWS];
-        const double* q = nh + (size_t)col * LD;
-        if (col < R) {
+    const int MT = (D + 7) >> 3, KT = (D + 3) >> 2;
+    for (int c0 = 0; c0 < R; c0 += 8) {
+        double acc0[MAXMT], acc1[MAXMT];
 #pragma unroll
-            for (int m = 0; m < MAXROWS; ++m) {
-                const int r = rp + 16 * m;
-                if (r < D) {
-                    const double* lrow = chol + r;
-                    double s0 = 0.0, s1 = 0.0;
-                    int k = 0;
-                    for (; k + 1 <= r; k += 2) {
-                        s0 = fma(lrow[(size_t)k * D], q[k], s0);
-                        s1 = fma(lrow[(size_t)(k + 1) * D], q[k + 1], s1);
-                    }
-                    if (k <= r) s0 = fma(lrow[(size_t)k * D], q[k], s0);
-                    out[m] = s0 + s1;
+        for (int mt = 0; mt < MAXMT; ++mt) acc0[mt] = acc1[mt] = 0.0;
+        const int cb = c0 + fr;  // the column this lane feeds into the B fragments
+        const double* qcol = nh + (size_t)min(cb, R - 1) * LD;
+        for (int kt = 0; kt < KT; ++kt) {
+            const int k = 4 * kt + fk;
+            const double bq = (k < D && cb < R) ? qcol[k] : 0.0;
+#pragma unroll
+            for (int mt = 0; mt < MAXMT; ++mt) {
+                if (mt < MT && 8 * mt + 7 >= 4 * kt) {  // warp-uniform: the tile touches the lower triangle
+                    const int r = 8 * mt + fr;
+                    const double al = (r < D && k <= r) ? chol[r + (size_t)k * D] : 0.0;
+                    dmma884(acc0[mt], acc1[mt], al, bq);
                 }
             }
         }
-        __syncwarp();
-        if (col < R) {
+        // this lane holds rows 8*mt + fr of columns c0 + 2*fk + {0, 1}
+        double n0 = 0.0, n1 = 0.0;
 #pragma unroll
-            for (int m = 0; m < MAXROWS; ++m) {
-                const int r = rp + 16 * m;
-                if (r < D) nh[(size_t)col * LD + r] = out[m];
+        for (int mt = 0; mt < MAXMT; ++mt) { n0 = fma(acc0[mt], acc0[mt], n0); n1 = fma(acc1[mt], acc1[mt], n1); }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) { n0 += __shfl_xor_sync(FULL, n0, o); n1 += __shfl_xor_sync(FULL, n1, o); }
+        const double w0 = sqrt(n0), w1 = sqrt(n1);
+        const double i0 = 1.0 / w0, i1 = 1.0 / w1;
+        const int ca = c0 + 2 * fk;
+        __syncwarp();  // every lane has read its B fragments of this column block
+#pragma unroll
+        for (int mt = 0; mt < MAXMT; ++mt) {
+            const int r = 8 * mt + fr;
+            if (mt < MT && r < D) {
+                if (ca < R) nh[(size_t)ca * LD + r] = acc0[mt] * i0;
+                if (ca + 1 < R) nh[(size_t)(ca + 1) * LD + r] = acc1[mt] * i1;
             }
         }
-        __syncwarp();
-    }
-    // w = 3*|nhat|, nhat /= |nhat| (:80-82): one lane per column
-    for (int col = lane; col < R; col += 32) {
-        double* q = nh + (size_t)col * LD;
-        double s0 = 0.0, s1 = 0.0;
-        int r = 0;
-        for (; r + 1 < D; r += 2) { s0 = fma(q[r], q[r], s0); s1 = fma(q[r + 1], q[r + 1], s1); }
-        if (r < D) s0 = fma(q[r], q[r], s0);
-        const double w0 = sqrt(s0 + s1);
-        const double inv = 1.0 / w0;
-        for (r = 0; r < D; ++r) q[r] *= inv;
-        cs.wts[col] = 3.0 * w0;
+        if (fr == 0) {
+            if (ca < R) cs.wts[ca] = 3.0 * w0;
+            if (ca + 1 < R) cs.wts[ca + 1] = 3.0 * w1;
+        }
     }
     __syncwarp();
 }
@@ -405,7 +407,8 @@ static __device__ __noinline__ double slow_uniform(unsigned seed, unsigned long 
 template <int G, int DPL, int KIND>
 __device__ inline double slice_chain(const ChainParams& p, const Model<G, DPL, KIND>& M, unsigned seed, unsigned long long uid,
                                      double (&x)[DPL], double Lstar, const ChainScratch& cs, double* ph_base,
-                                     double* last_dst, unsigned long long& nlike, long long* tim = nullptr) {
+                                     double* last_dst, unsigned long long& nlike, long long* tim = nullptr,
+                                     bool derive_all = true) {
     constexpr int NPT = 32 / G;
     constexpr int LOG2G = (G == 1) ? 0 : (G == 2) ? 1 : (G == 4) ? 2 : (G == 8) ? 3 : (G == 16) ? 4 : 5;
     constexpr int NS = NPT / 2;                 // bracket points per side and round
@@ -634,9 +637,16 @@ __device__ inline double slice_chain(const ChainParams& p, const Model<G, DPL, K
     }
     __syncwarp();
     long long tq1 = clock64();
-    // derived parameters of the R babies, one lane per record
+    // derived parameters, one lane per record.  Inside a run only the last baby needs them: it becomes a live
+    // point and later a dead one (what the dumper and the output files report); babies 0..R-2 are phantoms, which
+    // only ever contribute their cube coordinates (covariance) and logL (cleaning) -- their phi slots are left
+    // unset.  The chain probe (derive_all) fills them for all R babies, as the reference's SliceSampling returns them.
     if (p.P > 0) {
-        for (int i = lane; i < R; i += 32) M.finish_derived((i == R - 1) ? last_dst : ph_base + (size_t)i * T, false);
+        if (derive_all) {
+            for (int i = lane; i < R; i += 32) M.finish_derived((i == R - 1) ? last_dst : ph_base + (size_t)i * T, false);
+        } else if (lane == 0) {
+            M.finish_derived(last_dst, false);
+        }
         __syncwarp();
     }
     if (tim && lane == 0) { tim[0] += tq1 - tq0; tim[1] += clock64() - tq1; }

@@ -145,6 +145,12 @@ __device__ __forceinline__ int warp_sum_int(int v) {
 __device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }
 __device__ __forceinline__ int ldcg(const int* p) { return __ldcg(p); }
 __device__ __forceinline__ long long ldcg(const long long* p) { return __ldcg(p); }
+// D(8x8) += A(8x4) * B(4x8) on the FP64 tensor cores (DMMA).  Lane l holds A[l/4][l%4], B[l%4][l/4] and
+// C[l/4][2*(l%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 #endif
 
 }  // namespace pc

@@ -285,13 +285,6 @@ __device__ inline void phase_UA(const KParams& p, const RunBuf& rb, DevRun* st, 
     }
 }
 
-// D(8x8) += A(8x4) * B(4x8) on the FP64 tensor cores (DMMA).  Lane l holds A[l/4][l%4], B[l%4][l/4] and
-// C[l/4][2*(l%4) + {0,1}].
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
 // Pass B.  The moments are one matrix product: with the augmented, pivot-shifted coordinate rows
 // z = [x - c, 1, 0...] (Dp8 = 8*ceil((D+1)/8) entries) of the kept records, M = sum z z^T holds S2 in its leading
 // D x D block, S1 in column D and the record count at (D, D).  A warp stages U_BATCH = 8 records (two k-steps of
@@ -768,7 +761,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                 if (helper) {
                     long long th0 = clock64();
                     if (prep_uid != uid) { prep_chain(D, R, LD, rb.seed, uid, b); prep_white = false; }
-                    if (!prep_white) whiten_chain(D, R, LD, s_chol, b);
+                    if (!prep_white) whiten_chain<(G * DPL + 7) / 8>(D, R, LD, s_chol, b);
                     prep_uid = ~0ull;
                     if (lane == 0 && cta == c0 && pair == 0) st->cyc_prep += clock64() - th0;
                 }
@@ -791,7 +784,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                     if (ctimer && j == 0) st->dbg[11] += tc2 - tg1;
                     double lfin = slice_chain<G, DPL, KIND>(p.cp, M, rb.seed, uid, x, Lstar, b,
                                                       pool + (size_t)(nph_base + (long long)cl * (R - 1)) * T, last, nlike,
-                                                      (cta == c0 && warp == 0) ? st->dbg : nullptr);
+                                                      (cta == c0 && warp == 0) ? st->dbg : nullptr, false);
                     if (sharded) shard_publish(p, last, k, xpar);
                     if (ctimer) st->cyc_slice += clock64() - tc2;
                     if (!(lfin > Lstar)) ++nfail;
@@ -824,11 +817,11 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                     prep_white = false;
                 }
                 long long tc1 = clock64();
-                if (!prep_white) whiten_chain(D, R, LD, s_chol, cs);
+                if (!prep_white) whiten_chain<(G * DPL + 7) / 8>(D, R, LD, s_chol, cs);
                 prep_uid = ~0ull;
                 long long tc2 = clock64();
                 double lfin = slice_chain<G, DPL, KIND>(p.cp, M, rb.seed, uid, x, Lstar, cs,
-                                                  pool + (size_t)(nph_base + (long long)cl * (R - 1)) * T, last, nlike);
+                                                  pool + (size_t)(nph_base + (long long)cl * (R - 1)) * T, last, nlike, nullptr, false);
                 if (sharded) shard_publish(p, last, k, xpar);
                 if (ctimer) {
                     long long tc3 = clock64();
@@ -886,7 +879,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
         } else if (will_chain) {
             prep_uid = (unsigned long long)(nchains_base + K + knext);
             prep_chain(D, R, LD, rb.seed, prep_uid, csn);
-            whiten_chain(D, R, LD, s_chol, csn);
+            whiten_chain<(G * DPL + 7) / 8>(D, R, LD, s_chol, csn);
             prep_white = true;
         }
     }
@@ -923,7 +916,7 @@ __global__ void __launch_bounds__(256, 1) pc_slice_chains_kernel(const __grid_co
         unsigned long long nl = 0;
         double* out = babies + (size_t)c * R * T;
         prep_chain(D, R, LD, seed, uid[c], cs);
-        whiten_chain(D, R, LD, s_chol, cs);
+        whiten_chain<(G * DPL + 7) / 8>(D, R, LD, s_chol, cs);
         slice_chain<G, DPL, KIND>(p.cp, M, seed, uid[c], x, logL[c], cs, out, out + (size_t)(R - 1) * T, nl);
         if (lane == 0) nlike_out[c] = (long long)nl;
     }
