@@ -119,6 +119,10 @@ int pc_set_option(const char* name, double value);
 double pc_get_option(const char* name);
 /* CUDA stream (cudaStream_t passed as void*) all engine work is enqueued on; NULL = default stream. */
 void pc_set_stream(void* cuda_stream);
+/* Callable from inside a host callback (loglikelihood / prior / dumper): the run in flight stops at the next round
+ * of the host-callback path and polychord_c_interface reports status -3.  Language bindings whose callbacks cannot
+ * unwind through C frames (ctypes, cgo, JNI) use it to turn a callback exception into a prompt return. */
+void pc_request_abort(void);
 /* The engine keeps the device buffers of finished runs for the next run (cudaMalloc/cudaFree cost
  * milliseconds); this returns the cached blocks to the driver. */
 void pc_release_memory(void);
@@ -208,6 +212,19 @@ int pc_device_directions(int nDims, int num_repeats, unsigned seed, unsigned lon
 int pc_device_evidence(double* state, const double* logLs, int count, int n_start, double* logw_out);
 /* calc_cholesky (utils.F90:621-649), column-major D x D; returns 1 when the identity fallback was taken. */
 int pc_device_cholesky(const double* a, int D, double* L_out);
+
+/* ---- output files in the reference's formats (replaces src/polychord/read_write.F90:479-716, 809-961) ----
+ * polychord_c_interface() writes them itself when its write_* / posteriors / equals flags are set:
+ *   <root>.stats, <root>_dead.txt, <root>_dead-birth.txt, <root>_phys_live.txt, <root>_phys_live-birth.txt,
+ *   <root>.txt (weighted posterior), <root>_equal_weights.txt, <root>.prior_info
+ * with every number in Fortran's E24.15E3 edit descriptor (utils.F90:19).  The two entry points below are host-only
+ * (no device needed): the formatter, and the writer driven with explicit arrays.
+ * flags: 1 stats, 2 live, 4 dead, 8 prior_info, 16 weighted posterior, 32 equally weighted posterior.
+ * dead_rows / live_rows: rows [theta(nDims), phi(nDerived), birth contour, logL]; dead_logw[i] = log weight + logL. */
+void pc_format_e24(double value, char* out25);
+int pc_write_files(const char* base_dir, const char* file_root, int flags, int nDims, int nDerived, long long ndead,
+                   const double* dead_rows, const double* dead_logw, int nlive, const double* live_rows, double logZ,
+                   double logZerr, long long nlike, int num_repeats, double compression_factor, unsigned seed);
 
 /* Number of CUDA devices visible; <=0 means the engine cannot run (no CPU fallback exists). */
 int pc_device_count(void);

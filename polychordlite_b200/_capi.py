@@ -26,7 +26,7 @@ EXPORTS = [
     "pc_unit_prior", "pc_uniform_prior", "pc_set_option", "pc_get_option", "pc_set_stream", "pc_release_memory", "pc_mgpu_create", "pc_mgpu_attach", "pc_mgpu_destroy",
     "pc_last_run_info", "pc_run", "pc_run_ensemble", "pc_slice_chains", "pc_calculate_points",
     "pc_device_philox", "pc_device_uniforms", "pc_device_inv_normal_cdf", "pc_device_directions",
-    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version",
+    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort",
 ]
 
 
@@ -264,3 +264,35 @@ def last_run_info():
     info = RunInfo()
     lib().pc_last_run_info(C.byref(info))
     return info
+
+
+# ---- output files (host only) ----------------------------------------------------------------------
+FILE_FLAGS = {"stats": 1, "live": 2, "dead": 4, "prior": 8, "posteriors": 16, "equals": 32}
+
+
+def format_e24(value):
+    """Fortran E24.15E3 rendering of a double (utils.F90:19), as the engine writes every number."""
+    buf = C.create_string_buffer(25)
+    L = lib()
+    L.pc_format_e24.argtypes = [C.c_double, C.c_char_p]
+    L.pc_format_e24.restype = None
+    L.pc_format_e24(float(value), buf)
+    return buf.value.decode()
+
+
+def write_files(base_dir, file_root, nDims, nDerived, dead_rows, dead_logw, live_rows, logZ, logZerr, nlike,
+                num_repeats, compression_factor=float(np.exp(-1)), seed=0, flags=("stats", "live", "dead", "posteriors",
+                                                                                  "equals")):
+    """pc_write_files: the engine's file writer driven with explicit arrays (no device needed)."""
+    L = lib()
+    dead_rows = np.ascontiguousarray(dead_rows, dtype=np.float64).reshape(-1, nDims + nDerived + 2)
+    live_rows = np.ascontiguousarray(live_rows, dtype=np.float64).reshape(-1, nDims + nDerived + 2)
+    dead_logw = np.ascontiguousarray(dead_logw, dtype=np.float64)
+    L.pc_write_files.restype = C.c_int
+    L.pc_write_files.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_double, C.c_double,
+                                 C.c_longlong, C.c_int, C.c_double, C.c_uint]
+    fl = sum(FILE_FLAGS[f] for f in flags)
+    return L.pc_write_files(str(base_dir).encode(), str(file_root).encode(), fl, nDims, nDerived, dead_rows.shape[0],
+                            _dptr(dead_rows), _dptr(dead_logw), live_rows.shape[0], _dptr(live_rows), float(logZ),
+                            float(logZerr), int(nlike), int(num_repeats), float(compression_factor), int(seed))

@@ -20,6 +20,8 @@
 
 #include "../../include/polychord_b200.h"
 #include "pc_probes.cuh"
+#include "pc_files.h"
+#include "pc_hostchain.cuh"
 #include "pc_shapes.h"
 
 namespace pc {
@@ -173,6 +175,11 @@ struct Options {
     long long cap_dead0 = 0, cap_ph0 = 0;  // initial pool capacities in records (0 = automatic)
 };
 static Options g_opt;
+static volatile int g_abort = 0;                  // pc_request_abort(): a host callback asks the run in flight to stop
+static pc_loglikelihood_t g_host_ll = nullptr;   // host-callback run in flight (PC_LIKE_HOST)
+static pc_prior_t g_host_prior = nullptr;
+static FileOpts g_files;    // output files of the run in flight (set by polychord_c_interface / pc_set_output)
+static FileState g_fstate;
 static double g_dbg_dump[4];  // PC_DEBUG: ms spent in copies, row packing, weight normalisation, the user's dumper
 static cudaStream_t g_stream = nullptr;
 static pc_run_info g_last;
@@ -196,7 +203,9 @@ static void build_dev_model(const pc_settings& s, const ModelSpec& ms, DevModel&
     std::vector<double> lp;
     dm.log_rast = std::log(4991.21750);                                                    // rastrigin.f90:33
     dm.Vn = std::pow(std::sqrt(M_PI), (double)D) / std::tgamma(1.0 + D / 2.0);           // utils.F90:754-760
-    if (ms.like_kind == PC_LIKE_GAUSSIAN) {
+    if (ms.like_kind == PC_LIKE_HOST) {
+        lp.assign(2 * D, 1.0);  // never evaluated: the run kernel leaves before its chain phase (pc_hostchain.cuh)
+    } else if (ms.like_kind == PC_LIKE_GAUSSIAN) {
         std::vector<double> mu(D, 0.5), sg(D, 0.1);                                        // gaussian.f90:20-21
         const auto& q = ms.like_params;
         if ((int)q.size() >= 2 * D) { mu.assign(q.begin(), q.begin() + D); sg.assign(q.begin() + D, q.begin() + 2 * D); }
@@ -277,11 +286,12 @@ static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const Dev
     if (D < 1 || D > 128) throw std::invalid_argument("polychord_b200: nDims must be in 1..128");
     if (R < 1) throw std::invalid_argument("polychord_b200: num_repeats must be >= 1");  // settings.f90:216
     if (s.nlive < 2) throw std::invalid_argument("polychord_b200: nlive must be >= 2");
-    L.fn = pick_shape(D, ms.like_kind);
+    L.fn = pick_shape(D, ms.like_kind == PC_LIKE_HOST ? PC_LIKE_GAUSSIAN : ms.like_kind);
+    k.host_like = ms.like_kind == PC_LIKE_HOST ? 1 : 0;
     const int npt = 32 / L.fn.G;
     k.cp.D = D; k.cp.P = P; k.cp.T = 2 * D + P + 2; k.cp.R = R;
     k.cp.LD = (L.fn.G * L.fn.DPL) | 1;  // odd (bank-conflict free), zero-padded to the lanes' G*DPL dimensions
-    k.cp.like_kind = ms.like_kind;
+    k.cp.like_kind = ms.like_kind == PC_LIKE_HOST ? PC_LIKE_GAUSSIAN : ms.like_kind;
     k.cp.logzero = s.logzero;
     k.cp.gauss_norm = dm.gauss_norm; k.cp.Vn = dm.Vn; k.cp.log_rast = dm.log_rast; k.cp.corr_const = dm.corr_const;
     k.n = s.nlive;
@@ -297,7 +307,7 @@ static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const Dev
     k.cov_passes = (nt8 * (nt8 + 1) / 2 + COV_TPP - 1) / COV_TPP;
     k.partial_stride = 1 + D + k.ntri;
     L.W = W;
-    const int nlp = ms.like_kind == PC_LIKE_GAUSSIAN ? 2 * D : (ms.like_kind == PC_LIKE_CORR_GAUSSIAN ? D + D * D : 0);
+    const int nlp = (ms.like_kind == PC_LIKE_GAUSSIAN || ms.like_kind == PC_LIKE_HOST) ? 2 * D : (ms.like_kind == PC_LIKE_CORR_GAUSSIAN ? D + D * D : 0);
     const int Dpad = (D + 1) & ~1;
     size_t off = (size_t)D * D * 8;
     k.off_like = (int)off;
@@ -353,6 +363,13 @@ struct Engine {
     std::vector<HostRun> runs;
     DevArr<RunBuf> d_bufs;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // host-callback runs (pc_hostchain.cuh)
+    bool host_like = false;
+    DevArr<unsigned char> hc_scratch;
+    DevArr<double> hc_x;
+    DevArr<HcChain> hc_ch;
+    double *hc_out = nullptr, *hc_in = nullptr;   // mapped pinned host memory
+    long long hc_rounds = 0;
     double device_ms = 0;
     int launches = 0;
     long long h2d = 0, d2h = 0;
@@ -360,6 +377,107 @@ struct Engine {
     ~Engine() {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (hc_out) cudaFreeHost(hc_out);
+        if (hc_in) cudaFreeHost(hc_in);
+    }
+
+    // GenerateLivePoints (generate.F90:153-183) with host callbacks: attempt a draws cube = U(TAG_INIT, a, dim) --
+    // the same counter-addressed numbers the device path uses -- and is kept when logL > logzero.
+    void host_generate_live_points() {
+        const KParams& k = L.kp;
+        const int D = k.cp.D, P = k.cp.P, T = k.cp.T, n = k.n;
+        std::vector<double> live((size_t)n * T, 0.0), cube(D), theta(D), phi(std::max(P, 1));
+        DevRun h0;
+        std::memset(&h0, 0, sizeof(h0));
+        int have = 0;
+        long long a = 0, nl = 0;
+        const unsigned seed = runs[0].buf.seed;
+        while (have < n) {
+            if (a > 1000LL * n + 1000000LL) throw std::runtime_error("polychord_b200: could not generate live points (likelihood <= logzero everywhere?)");
+            for (int d = 0; d < D; ++d) cube[d] = uniform(seed, TAG_INIT, (unsigned long long)a, (unsigned)d, 0u);
+            ++a;
+            std::vector<double> c2(cube);
+            std::fill(phi.begin(), phi.end(), 0.0);
+            g_host_prior(c2.data(), theta.data(), D);
+            const double logL = g_host_ll(theta.data(), D, phi.data(), P);
+            if (!(logL > S.logzero)) continue;
+            ++nl;
+            double* rec = &live[(size_t)have * T];
+            std::copy(cube.begin(), cube.end(), rec);
+            std::copy(theta.begin(), theta.end(), rec + D);
+            for (int i = 0; i < P; ++i) rec[2 * D + i] = phi[i];
+            rec[2 * D + P] = S.logzero;  // born from the prior
+            rec[2 * D + P + 1] = logL;
+            ++have;
+        }
+        h0.nlike = nl;
+        h0.init_attempts = a;
+        runs[0].live.upload(live.data(), live.size(), stream);
+        runs[0].st.upload(&h0, 1, stream);
+        h2d += (long long)live.size() * 8;
+        PC_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    // The chains of one generation in lock step: every round the device emits one trial point per running chain
+    // and the calling thread makes the prior + likelihood calls (calculate_point, calculate.f90:6-50).
+    void host_chains() {
+        const KParams& k = L.kp;
+        const int D = k.cp.D, P = k.cp.P, K = runs[0].host_st.K;
+        HcParams hp;
+        std::memset(&hp, 0, sizeof(hp));
+        hp.D = D; hp.P = P; hp.T = k.cp.T; hp.R = k.cp.R; hp.LD = k.cp.LD; hp.n = k.n; hp.K = K;
+        hp.logzero = S.logzero; hp.seed = runs[0].buf.seed; hp.rb = runs[0].buf;
+        hp.scratch_bytes = chain_scratch_bytes(D, k.cp.R, k.cp.LD, true, LIKE_GAUSSIAN, 1);
+        if (!hc_out) {
+            const size_t Kmax = (size_t)k.batch_K;
+            hc_scratch.alloc(Kmax * hp.scratch_bytes);
+            hc_x.alloc(Kmax * k.cp.LD);
+            hc_ch.alloc(Kmax);
+            PC_CUDA(cudaHostAlloc((void**)&hc_out, Kmax * (D + 2) * 8, cudaHostAllocMapped));
+            PC_CUDA(cudaHostAlloc((void**)&hc_in, Kmax * (D + P + 1) * 8, cudaHostAllocMapped));
+        }
+        hp.scratch = hc_scratch.p; hp.x = hc_x.p; hp.ch = hc_ch.p;
+        double *d_out = nullptr, *d_in = nullptr;
+        PC_CUDA(cudaHostGetDevicePointer((void**)&d_out, hc_out, 0));
+        PC_CUDA(cudaHostGetDevicePointer((void**)&d_in, hc_in, 0));
+        hp.out = d_out; hp.in = d_in;
+        const int W = 4, blocks = (K + W - 1) / W;
+        hc_begin_kernel<<<blocks, W * 32, 0, stream>>>(hp);
+        PC_CUDA(cudaGetLastError());
+        std::vector<double> cube(D), theta(D), phi(std::max(P, 1));
+        long long nl = 0;
+        for (;;) {
+            PC_CUDA(cudaStreamSynchronize(stream));
+            int active = 0;
+            for (int c = 0; c < K; ++c) {
+                const double* o = hc_out + (size_t)c * (D + 2);
+                if (o[D + 1] == 0.0) continue;
+                ++active;
+                double* in = hc_in + (size_t)c * (D + P + 1);
+                if (o[D] != 0.0) {
+                    std::copy(o, o + D, cube.begin());
+                    std::fill(phi.begin(), phi.end(), 0.0);
+                    g_host_prior(cube.data(), theta.data(), D);
+                    const double logL = g_host_ll(theta.data(), D, phi.data(), P);
+                    if (logL > S.logzero) ++nl;  // calculate.f90:44
+                    std::copy(theta.begin(), theta.end(), in);
+                    for (int i = 0; i < P; ++i) in[D + i] = phi[i];
+                    in[D + P] = logL;
+                } else {  // outside the cube the callbacks are not called (calculate.f90:36-39)
+                    std::fill(in, in + D + P, 0.0);
+                    in[D + P] = S.logzero;
+                }
+            }
+            if (active == 0) break;
+            if (g_abort) throw std::runtime_error("polychord_b200: run aborted by a host callback (pc_request_abort)");
+            hc_step_kernel<<<blocks, W * 32, 0, stream>>>(hp);
+            PC_CUDA(cudaGetLastError());
+            ++hc_rounds;
+            launches += 1;
+        }
+        hc_finish_kernel<<<1, 1, 0, stream>>>(runs[0].st.p, nl, 1);
+        PC_CUDA(cudaGetLastError());
+        launches += 2;
     }
 
     void setup(const pc_settings& s, const ModelSpec& m, int nruns_, const int* seeds) {
@@ -377,6 +495,10 @@ struct Engine {
         stream = g_stream;
         if (S.nprior > 0 && S.nprior != S.nlive)
             throw std::invalid_argument("polychord_b200: nprior != nlive is not supported by the device path yet");
+        host_like = ms.like_kind == PC_LIKE_HOST;
+        if (host_like && (nruns != 1 || g_mgpu.world > 1))
+            throw std::invalid_argument("polychord_b200: host-callback likelihoods run one run on one GPU");
+        if (host_like && (!g_host_ll || !g_host_prior)) throw std::invalid_argument("polychord_b200: host callbacks missing");
         build_dev_model(S, ms, dm, stream);
         mark("build_dev_model");
         int W = std::max(1, std::min(8, g_opt.warps_per_cta));
@@ -491,7 +613,7 @@ struct Engine {
     // state: {ndead, logZ, logZ2}; live_src: device records of the live points to report (null: none);
     // cs: the stream the copies are enqueued on (the copy stream while the run kernel is still sampling)
     void dump(int r, pc_dumper_t dumper, long long ndead, double logZ_raw, double logZ2_raw, const double* live_src,
-              cudaStream_t cs) {
+              cudaStream_t cs, long long nlike_now = 0, bool final_call = false) {
         HostRun& h = runs[r];
         const KParams& k = L.kp;
         const int T = k.cp.T, D = k.cp.D, P = k.cp.P, n = k.n, npars = D + P + 2;
@@ -562,9 +684,13 @@ struct Engine {
         double var = logZ2_raw - 2 * logZ_raw;
         std::vector<double> dummy(npars, 0.0);
         lap(2);
-        dumper((int)ndead, nl, npars, live_rows.data(), ndead > 0 ? mr.rows.data() : dummy.data(), lw.data(), lz,
-               std::sqrt(var));
+        if (dumper)
+            dumper((int)ndead, nl, npars, live_rows.data(), ndead > 0 ? mr.rows.data() : dummy.data(), lw.data(), lz,
+                   std::sqrt(var));
         lap(3);
+        if (g_files.enabled && r == 0)  // read_write.F90: the files are rewritten at every update and at the end
+            write_run_files(g_files, g_fstate, D, P, ndead, mr.rows.data(), mr.logw.data(), nl, live_rows.data(), lz,
+                            std::sqrt(std::fabs(var)), nlike_now, final_call);
     }
 
     void grow(int r, int status) {
@@ -592,8 +718,11 @@ struct Engine {
         auto t0 = std::chrono::steady_clock::now();
         volatile HostCtl* ctl = nullptr;
         unsigned long long handled = 0;
-        const bool sync_dump = g_opt.sync_dump || std::getenv("PC_SYNC_DUMP");
-        if (dumper != nullptr && nruns == 1 && !sync_dump) {  // asynchronous dumper hand-over
+        const bool sync_dump = g_opt.sync_dump || std::getenv("PC_SYNC_DUMP") || host_like;  // a host-callback run returns to the host every generation anyway
+        if (host_like) host_generate_live_points();
+        const bool want_files = g_files.enabled && nruns == 1;
+        const bool dumping = (dumper != nullptr || want_files) && nruns == 1;
+        if (dumping && !sync_dump) {  // asynchronous dumper hand-over
             HostCtl* c = host_ctl();
             std::memset(c, 0, sizeof(*c));
             ctl = c;
@@ -605,7 +734,7 @@ struct Engine {
             h.buf.ctl = dctl;
             upload_bufs();
         }
-        L.kp.want_dump = (dumper != nullptr && nruns == 1) ? 1 : 0;
+        L.kp.want_dump = dumping ? 1 : 0;
         double dbg_service_ms = 0, dbg_launch_ms = 0, dbg_finish_ms = 0, dbg_final_ms = 0;
         auto now = [] { return std::chrono::steady_clock::now(); };
         auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
@@ -613,7 +742,7 @@ struct Engine {
             auto ts = now();
             const long long nd = ctl->ndead;
             const double lz = ctl->logZ, lz2 = ctl->logZ2;
-            dump(0, dumper, nd, lz, lz2, runs[0].live_snap.p, g_copy_stream);
+            dump(0, dumper, nd, lz, lz2, runs[0].live_snap.p, g_copy_stream, ctl->nlike);
             ++handled;
             ctl->ack_seq = handled;
             dbg_service_ms += ms_since(ts);
@@ -644,7 +773,9 @@ struct Engine {
                 if (stt == ST_ERROR) throw std::runtime_error("polychord_b200: could not generate live points (likelihood <= logzero everywhere?)");
                 if (stt == ST_DUMP && ctl) throw std::runtime_error("polychord_b200: run aborted");
                 if (stt == ST_DUMP)  // sync_dump: the kernel left at the update, dump and relaunch
-                    dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, runs[r].live.p, stream);
+                    dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, runs[r].live.p, stream,
+                         runs[r].host_st.nlike);
+                if (stt == ST_HOSTCHAINS) host_chains();
                 if (stt == ST_NEED_DEAD || stt == ST_NEED_PHANTOM) { grow(r, stt); regrow = true; }
                 if (stt != ST_DONE) all_done = false;
             }
@@ -653,9 +784,11 @@ struct Engine {
         }
         if (g_mgpu.world > 1) g_mgpu.epoch = runs[0].host_st.xepoch;
         auto tfin = now();
-        if (dumper)  // the final call: every point is dead (nested_sampling.F90:392)
+        if (dumping)  // the final call: every point is dead (nested_sampling.F90:392)
             for (int r = 0; r < nruns; ++r)
-                dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, nullptr, stream);
+                dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, nullptr, stream,
+                     runs[r].host_st.nlike, true);
+        if (want_files) write_prior_info(g_files, L.kp.n, runs[0].host_st.init_attempts);
         dbg_final_ms = ms_since(tfin);
         if (std::getenv("PC_DEBUG")) {
             std::fprintf(stderr, "[pc dbg dump] copies %.3f ms, rows %.3f ms, weights %.3f ms, user dumper %.3f ms\n", g_dbg_dump[0],
@@ -761,6 +894,7 @@ double pc_get_option(const char* name) {
     return NAN;
 }
 void pc_set_stream(void* cuda_stream) { g_stream = (cudaStream_t)cuda_stream; }
+void pc_request_abort(void) { g_abort = 1; }
 void pc_release_memory(void) { pool().trim(); }
 
 // ---- sharded run over the GPUs of one box ---------------------------------------------------------
@@ -1119,6 +1253,25 @@ int pc_device_cholesky(const double* a, int D, double* L_out) {
     }
 }
 
+// ---- output files (host only; no device needed) -------------------------------------------------
+void pc_format_e24(double v, char* out25) { format_e24(v, out25); }
+int pc_write_files(const char* base_dir, const char* file_root, int flags, int nDims, int nDerived, long long ndead,
+                   const double* dead_rows, const double* dead_logw, int nlive, const double* live_rows, double logZ,
+                   double logZerr, long long nlike, int num_repeats, double compression_factor, unsigned seed) {
+    try {
+        FileOpts o;
+        o.enabled = true;
+        o.base_dir = base_dir; o.file_root = file_root;
+        o.write_stats = flags & 1; o.write_live = flags & 2; o.write_dead = flags & 4; o.write_prior = flags & 8;
+        o.posteriors = flags & 16; o.equals = flags & 32;
+        o.num_repeats = num_repeats; o.compression_factor = compression_factor; o.seed = seed;
+        FileState st;
+        return write_run_files(o, st, nDims, nDerived, ndead, dead_rows, dead_logw, nlive, live_rows, logZ, logZerr, nlike, true);
+    } catch (const std::exception& ex) {
+        return fail(-1, ex.what());
+    }
+}
+
 // ==========================================================================================
 // Drop-in boundary
 // ==========================================================================================
@@ -1131,10 +1284,10 @@ void polychord_c_interface(pc_loglikelihood_t loglikelihood, pc_prior_t prior, p
                            pc_bool synchronous, int nDims, int nDerived, char* base_dir, char* file_root, int nGrade,
                            double* grade_frac, int* grade_dims, int n_nlives, double* loglikes, int* nlives, int seed,
                            int* comm) {
-    (void)write_resume; (void)write_paramnames; (void)read_resume; (void)write_stats; (void)write_live; (void)write_dead;
-    (void)write_prior; (void)maximise; (void)synchronous; (void)base_dir; (void)file_root; (void)grade_frac;
+    (void)write_resume; (void)write_paramnames; (void)read_resume; (void)maximise; (void)synchronous; (void)grade_frac;
     (void)loglikes; (void)nlives; (void)comm; (void)nfail; (void)do_clustering;
     std::memset(&g_last, 0, sizeof(g_last));
+    g_abort = 0;
     pc_settings s;
     std::memset(&s, 0, sizeof(s));
     s.nDims = nDims; s.nDerived = nDerived; s.nlive = nlive; s.num_repeats = num_repeats; s.nprior = nprior; s.nfail = nfail;
@@ -1164,11 +1317,39 @@ void polychord_c_interface(pc_loglikelihood_t loglikelihood, pc_prior_t prior, p
     if (pi != prior_registry().end()) ms.prior_params = pi->second.params;
     else if (prior == pc_unit_prior || prior == pc_uniform_prior) {}
     else have_prior = false;
+    struct HostGuard {  // callbacks may throw through the engine (e.g. a Python exception): always clear
+        ~HostGuard() { g_host_ll = nullptr; g_host_prior = nullptr; }
+    } host_guard;
     if (!have_like || !have_prior) {
-        fail(-5, "the loglikelihood/prior callbacks are not registered with a device form "
-                 "(pc_register_device_likelihood / pc_register_device_prior); the generic host-callback path is not built yet");
-        return;
+        // a callback without a device form: the generic path -- the slice state machines stay on the device, the
+        // calling thread makes the prior + likelihood calls in lock step (pc_hostchain.cuh)
+        if (!loglikelihood || !prior) { fail(-5, "loglikelihood and prior callbacks must not be NULL"); return; }
+        ms = ModelSpec();
+        ms.like_kind = PC_LIKE_HOST;
+        g_host_ll = loglikelihood;
+        g_host_prior = prior;
     }
+    // output files (read_write.F90); the reference halts when base_dir is missing (read_write.F90:28-38)
+    FileOpts fo;
+    fo.write_stats = write_stats; fo.write_live = write_live; fo.write_dead = write_dead; fo.write_prior = write_prior;
+    fo.posteriors = posteriors; fo.equals = equals;
+    fo.enabled = write_stats || write_live || write_dead || write_prior || posteriors || equals;
+    fo.base_dir = base_dir ? std::string(base_dir) : std::string(".");   // read up to the first NUL only (utils.F90:787-801)
+    fo.file_root = file_root ? std::string(file_root) : std::string("test");
+    fo.compression_factor = compression_factor; fo.num_repeats = num_repeats; fo.seed = (unsigned)seed; fo.logzero = logzero;
+    if (fo.enabled) {
+        FILE* probe = std::fopen((fo.base_dir + "/.pc_probe").c_str(), "w");
+        if (!probe) {
+            fail(-1, "base_dir '" + fo.base_dir + "' does not exist or is not writable (the reference halts here too: read_write.F90:28-38)");
+            return;
+        }
+        std::fclose(probe);
+        std::remove((fo.base_dir + "/.pc_probe").c_str());
+    }
+    struct FilesGuard {  // exception-transparent: a throwing dumper must not leave the next run writing files
+        FilesGuard(const FileOpts& o) { g_files = o; g_fstate = FileState(); }
+        ~FilesGuard() { g_files.enabled = false; }
+    } files_guard(fo);
     pc_run_info info;
     try {
         run_common(&s, ms, 1, &seed, dumper, &info);

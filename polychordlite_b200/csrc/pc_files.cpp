@@ -1,0 +1,257 @@
+// pc_files.cpp -- output files in the reference's formats (see pc_files.h).  Host-only.
+#include "pc_files.h"
+
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+#include <vector>
+
+#include "pc_device.cuh"  // the counter-based uniform stream (equally weighted posterior thinning)
+
+namespace pc {
+
+// Fortran E24.15E3: right-justified in 24 columns, "0.ddddddddddddddd" mantissa in [0.1, 1), exponent letter, sign
+// and three exponent digits (utils.F90:19, DB_FMT).  The 15 significant digits are the ones "%.14E" produces,
+// shifted by one place.
+void format_e24(double v, char* out) {
+    std::memset(out, ' ', 24);
+    out[24] = 0;
+    if (std::isnan(v)) { std::memcpy(out + 21, "NaN", 3); return; }
+    if (std::isinf(v)) {
+        if (v > 0) std::memcpy(out + 16, "Infinity", 8); else std::memcpy(out + 15, "-Infinity", 9);
+        return;
+    }
+    char buf[40];
+    auto res = std::to_chars(buf, buf + sizeof(buf), std::fabs(v), std::chars_format::scientific, 14);
+    *res.ptr = 0;  // d.dddddddddddddde[+-]XX[X]
+    const char* e = std::strchr(buf, 'e');
+    int ex = std::atoi(e + 1);
+    if (v != 0.0) ex += 1;
+    // [0] blank, [1] sign, "0." at 2-3, the 15 digits at 4..18, 'E' at 19, exponent sign at 20, three digits at 21..23
+    out[1] = std::signbit(v) ? '-' : ' ';
+    out[2] = '0';
+    out[3] = '.';
+    out[4] = buf[0];
+    std::memcpy(out + 5, buf + 2, 14);
+    out[19] = 'E';
+    out[20] = ex < 0 ? '-' : '+';
+    const int ax = ex < 0 ? -ex : ex;
+    out[21] = (char)('0' + (ax / 100) % 10);
+    out[22] = (char)('0' + (ax / 10) % 10);
+    out[23] = (char)('0' + ax % 10);
+}
+
+namespace {
+
+struct Out {
+    FILE* f;
+    std::vector<char> big;  // stdio buffer of this file (must outlive the stream)
+    explicit Out(const std::string& path) : f(std::fopen(path.c_str(), "w")), big(1 << 20) {
+        if (!f) throw std::runtime_error("polychord_b200: cannot open " + path + " for writing");
+        std::setvbuf(f, big.data(), _IOFBF, big.size());
+    }
+    Out(const Out&) = delete;
+    Out& operator=(const Out&) = delete;
+    ~Out() { if (f) std::fclose(f); }
+    void num(double v) { char b[25]; format_e24(v, b); std::fwrite(b, 1, 24, f); }
+    void nl() { std::fputc('\n', f); }
+    void line(const char* s) { std::fputs(s, f); std::fputc('\n', f); }
+};
+
+std::string root_of(const FileOpts& o) { return o.base_dir + "/" + o.file_root; }
+
+double host_logaddexp(double a, double b) {
+    if (a < b) std::swap(a, b);
+    if (b == -std::numeric_limits<double>::infinity()) return a;
+    return a + std::log1p(std::exp(b - a));
+}
+
+}  // namespace
+
+void write_prior_info(const FileOpts& o, long long nprior, long long ndiscarded) {
+    if (!o.enabled || !o.write_prior) return;
+    FILE* f = std::fopen((root_of(o) + ".prior_info").c_str(), "a");
+    if (!f) throw std::runtime_error("polychord_b200: cannot open " + root_of(o) + ".prior_info");
+    std::fprintf(f, "nprior = %12lld\n", nprior);
+    std::fprintf(f, "ndiscarded = %12lld\n", ndiscarded);
+    std::fclose(f);
+}
+
+int write_run_files(const FileOpts& o, FileState& st, int D, int P, long long ndead, const double* dead_rows,
+                    const double* dead_logw, int nlive, const double* live_rows, double logZ, double logZerr,
+                    long long nlike, bool final_call) {
+    if (!o.enabled) return 0;
+    const auto now = std::chrono::steady_clock::now();
+    if (!final_call && st.written && std::chrono::duration<double>(now - st.last).count() < o.min_interval_s) return 0;
+    const int npars = D + P + 2, np = D + P;
+    const std::string root = root_of(o);
+    int files = 0;
+
+    if (o.write_dead) {  // write_dead_points, read_write.F90:679-716
+        {
+            Out w(root + "_dead.txt");
+            for (long long i = 0; i < ndead; ++i) {
+                const double* r = dead_rows + (size_t)i * npars;
+                w.num(r[np + 1]);
+                for (int k = 0; k < np; ++k) w.num(r[k]);
+                w.nl();
+            }
+        }
+        {
+            Out w(root + "_dead-birth.txt");
+            for (long long i = 0; i < ndead; ++i) {
+                const double* r = dead_rows + (size_t)i * npars;
+                for (int k = 0; k < np; ++k) w.num(r[k]);
+                w.num(r[np + 1]);
+                w.num(r[np]);
+                w.nl();
+            }
+        }
+        files += 2;
+    }
+    if (o.write_live) {  // write_phys_live_points, read_write.F90:621-677
+        Out a(root + "_phys_live.txt"), b(root + "_phys_live-birth.txt");
+        for (int i = 0; i < nlive; ++i) {
+            const double* r = live_rows + (size_t)i * npars;
+            for (int k = 0; k < np; ++k) { a.num(r[k]); b.num(r[k]); }
+            a.num(r[np + 1]); a.nl();
+            b.num(r[np + 1]); b.num(r[np]); b.nl();
+        }
+        files += 2;
+    }
+
+    // posterior weights: log w_i + log L_i relative to the largest one (maximum weight 1.0, read_write.F90:565-566)
+    double wmax = -std::numeric_limits<double>::infinity();
+    for (long long i = 0; i < ndead; ++i) wmax = std::max(wmax, dead_logw[i]);
+    long long nposterior = 0, nequals = 0;
+    if (o.posteriors || o.equals || o.write_stats) {
+        for (long long i = 0; i < ndead; ++i) {
+            const double wgt = std::exp(dead_logw[i] - wmax);
+            if (wgt > 0.0) ++nposterior;
+        }
+    }
+    if (o.posteriors) {  // <root>.txt: weight, -2 logL, theta, phi (written to _temp, then renamed: read_write.F90:600-611)
+        const std::string tmp = root + "_temp.txt";
+        {
+            Out w(tmp);
+            for (long long i = 0; i < ndead; ++i) {
+                const double wgt = std::exp(dead_logw[i] - wmax);
+                if (!(wgt > 0.0)) continue;
+                const double* r = dead_rows + (size_t)i * npars;
+                w.num(wgt);
+                w.num(-2.0 * r[np + 1]);
+                for (int k = 0; k < np; ++k) w.num(r[k]);
+                w.nl();
+            }
+        }
+        std::rename(tmp.c_str(), (root + ".txt").c_str());
+        ++files;
+    }
+    if (o.equals || o.write_stats) {
+        // equally weighted posterior: point i is kept with probability w_i / w_max (the net effect of the
+        // reference's incremental thinning in update_posteriors, run_time_info.f90:955-1066); the draw is
+        // addressed by the point's index, so successive rewrites agree on the points they share
+        const std::string tmp = root + "_equal_weights_temp.txt";
+        std::vector<long long> keep;
+        for (long long i = 0; i < ndead; ++i) {
+            const double u = uniform(o.seed, TAG_POST, (uint64_t)i, 0u, 0u);
+            if (u < std::exp(dead_logw[i] - wmax)) keep.push_back(i);
+        }
+        nequals = (long long)keep.size();
+        if (o.equals) {
+            {
+                Out w(tmp);
+                for (long long i : keep) {
+                    const double* r = dead_rows + (size_t)i * npars;
+                    w.num(1.0);
+                    w.num(-2.0 * r[np + 1]);
+                    for (int k = 0; k < np; ++k) w.num(r[k]);
+                    w.nl();
+                }
+            }
+            std::rename(tmp.c_str(), (root + "_equal_weights.txt").c_str());
+            ++files;
+        }
+    }
+
+    if (o.write_stats) {  // write_stats_file, read_write.F90:809-910 (one cluster: evidence is kept globally)
+        Out w(root + ".stats");
+        char a[25], b[25];
+        w.line("Evidence estimates:");
+        w.line("===================");
+        w.line("  - The evidence Z is a log-normally distributed, with location and scale parameters mu and sigma.");
+        w.line("  - We denote this as log(Z) = mu +/- sigma.");
+        w.line("");
+        w.line("Global evidence:");
+        w.line("----------------");
+        w.line("");
+        format_e24(logZ, a); format_e24(logZerr, b);
+        std::fprintf(w.f, "log(Z)       = %s +/- %s\n", a, b);
+        w.line("");
+        w.line("");
+        w.line("Local evidences:");
+        w.line("----------------");
+        w.line("");
+        if (nlive > 0) std::fprintf(w.f, "log(Z_1)     = %s +/- %s (Still Active)\n", a, b);
+        else std::fprintf(w.f, "log(Z_1)     = %s +/- %s\n", a, b);
+        w.line("");
+        w.line("");
+        w.line("Run-time information:");
+        w.line("---------------------");
+        w.line("");
+        std::fprintf(w.f, " ncluster:   %8d /%8d\n", nlive > 0 ? 1 : 0, 1);
+        std::fprintf(w.f, " nposterior: %8lld\n", nposterior);
+        std::fprintf(w.f, " nequals:    %8lld\n", nequals);
+        std::fprintf(w.f, " ndead:      %8lld\n", ndead);
+        std::fprintf(w.f, " nlive:      %8d\n", nlive);
+        if (nlike < 100000000LL) std::fprintf(w.f, " nlike:      %8lld\n", nlike);
+        else std::fprintf(w.f, " nlike:      ********\n");  // Fortran I8 overflow
+        const double since = (double)(nlike - st.nlike_last);
+        if (nlive > 0) {
+            const double update_files = -(double)nlive * std::log(o.compression_factor);
+            std::fprintf(w.f, " <nlike>:    %8.2f   (%8.2f per slice )\n", since / update_files,
+                         since / ((double)o.num_repeats * update_files));
+        } else {
+            std::fprintf(w.f, " <nlike>:    %8.2f   (%8.2f per slice )\n", 0.0, 0.0);
+        }
+        if (o.posteriors) {  // weighted mean / variance, streaming log-space updates (read_write.F90:912-961)
+            w.line("");
+            w.line("");
+            w.line("Dim No.       Mean        Sigma");
+            std::vector<double> mu(np, 0.0), mu_old(np), logS(np, o.logzero);
+            double logwsum = o.logzero;
+            for (long long i = 0; i < ndead; ++i) {
+                if (!(std::exp(dead_logw[i] - wmax) > 0.0)) continue;
+                const double* x = dead_rows + (size_t)i * npars;
+                const double lw = dead_logw[i];
+                mu_old = mu;
+                logwsum = host_logaddexp(logwsum, lw);
+                const double f = std::exp(lw - logwsum);
+                bool all_pos = true;
+                for (int k = 0; k < np; ++k) {
+                    mu[k] = mu_old[k] + f * (x[k] - mu_old[k]);
+                    all_pos = all_pos && (x[k] - mu_old[k]) * (x[k] - mu[k]) > 0.0;
+                }
+                if (all_pos)
+                    for (int k = 0; k < np; ++k) logS[k] = host_logaddexp(logS[k], lw + std::log((x[k] - mu_old[k]) * (x[k] - mu[k])));
+            }
+            for (int k = 0; k < np; ++k) {
+                if (k == D) w.line("-------------------------------");
+                format_e24(mu[k], a);
+                format_e24(std::sqrt(std::exp(logS[k] - logwsum)), b);
+                std::fprintf(w.f, "%3d%s +/- %s\n", k + 1, a, b);
+            }
+            if (np == D) w.line("-------------------------------");
+        }
+        ++files;
+        st.nlike_last = nlike;
+    }
+    st.written = true;
+    st.last = std::chrono::steady_clock::now();
+    return files;
+}
+
+}  // namespace pc

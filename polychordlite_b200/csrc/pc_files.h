@@ -1,0 +1,45 @@
+// pc_files.h -- the run's output files in the reference's on-disk formats.
+//
+// Replaces src/polychord/read_write.F90: write_stats_file (:809-910), write_dead_points (:679-716),
+// write_phys_live_points (:621-677), write_posterior_file (:479-612, global files) and the prior_info lines of
+// generate.F90:274-279.  Numbers are written in Fortran's E24.15E3 edit descriptor (utils.F90:19), which is what
+// anesthetic / getdist / pypolychord.output.PolyChordOutput parse.  Host-only code: the engine hands it the same
+// host arrays the dumper receives.
+#pragma once
+#include <chrono>
+#include <string>
+
+namespace pc {
+
+struct FileOpts {
+    bool enabled = false;  // any write_* flag set
+    std::string base_dir, file_root;
+    bool write_stats = false, write_live = false, write_dead = false, write_prior = false;
+    bool posteriors = false, equals = false;
+    double compression_factor = 0.36787944117144233;
+    int num_repeats = 1;
+    unsigned seed = 0;
+    double logzero = -1e30;
+    double min_interval_s = 0.5;  // intermediate (per-update) rewrites are rate-limited; the final write always happens
+};
+
+struct FileState {
+    long long nlike_last = 0;  // likelihood calls at the previous stats write (the file reports calls since then)
+    bool written = false;
+    std::chrono::steady_clock::time_point last;
+};
+
+// value in Fortran E24.15E3 form, 24 characters, no terminator needed by callers (out must hold 25 bytes)
+void format_e24(double v, char* out);
+
+// Writes every requested file under base_dir.  dead_rows/live_rows: rows [theta(D), phi(P), birth, logL];
+// dead_logw[i] = log-weight + logL of dead point i (unnormalised posterior log-weight).
+// Returns the number of files written; throws std::runtime_error when a file cannot be opened.
+int write_run_files(const FileOpts& o, FileState& st, int D, int P, long long ndead, const double* dead_rows,
+                    const double* dead_logw, int nlive, const double* live_rows, double logZ, double logZerr,
+                    long long nlike, bool final_call);
+
+// generate.F90:274-279
+void write_prior_info(const FileOpts& o, long long nprior, long long ndiscarded);
+
+}  // namespace pc

@@ -25,7 +25,7 @@
 
 namespace pc {
 
-enum Status : int { ST_RUNNING = 0, ST_DONE = 1, ST_NEED_DEAD = 2, ST_NEED_PHANTOM = 3, ST_DUMP = 4, ST_ERROR = -1 };
+enum Status : int { ST_RUNNING = 0, ST_DONE = 1, ST_NEED_DEAD = 2, ST_NEED_PHANTOM = 3, ST_DUMP = 4, ST_HOSTCHAINS = 5, ST_ERROR = -1 };
 
 constexpr double NEG_BIG = -1e300;  // log(0) stand-in that survives additions without NaN
 constexpr int COV_TPP = 10;         // 8x8 tiles of the moment matrix a warp accumulates per pass of phase U (2 registers each)
@@ -57,6 +57,8 @@ struct DevRun {
     int chol_fallback;   // number of calc_cholesky identity fallbacks
     int order_valid;     // rb.order + order_off holds the live slots sorted by (logL, slot) as of the last phase S
     int order_off;       // 0 or n: which half of rb.order is current
+    int host_resume;     // host-callback runs: the chains of the generation in flight were run by the host loop
+    int pad0;
     // SM-clock cycle counters of the phases (thread 0 of CTA 0; chain phases: warp 0 of the first chain CTA)
     long long cyc_wait, cyc_S, cyc_fin, cyc_U, cyc_prep, cyc_white, cyc_slice, cyc_total;
     long long dbg[16];    // scratch cycle counters for profiling experiments (printed when PC_DEBUG is set)
@@ -71,6 +73,7 @@ struct HostCtl {
     unsigned long long dump_seq;   // device -> host: dumps published
     unsigned long long ack_seq;    // host -> device: dumps consumed (the live snapshot may be overwritten)
     long long ndead;               // state at the published dump
+    long long nlike;
     double logZ, logZ2;
     int abort;                     // host -> device: stop waiting (the dumper threw)
     int pad;
@@ -122,6 +125,7 @@ struct KParams {
     int chain_cta0;              // first CTA of a run's group that runs chains (1: CTA 0 only keeps the books)
     int paired;                  // 1: warps w >= W/2 prepare the chains of warp w - W/2 (a run alone on the device)
     int nh_in_smem, want_dump;
+    int host_like;               // 1: likelihood/prior are host callbacks -- the kernel leaves before the chain phase (pc_hostchain.cuh)
     int ntri, cov_passes, partial_stride;
     int off_like, off_warp, warp_bytes;  // shared-memory byte offsets
     double log_prec, log_comp;

@@ -27,8 +27,8 @@ __device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st
             st->logZ = st->logZ2 = st->logZX = p.cp.logzero;  // run_time_info.f90:165-175
             st->logX = st->logXX = 0.0;
             st->logX_last_update = 0.0;
-            st->init_need = n;
-            st->init_attempts = 0;
+            st->init_need = p.host_like ? 0 : n;   // host-callback runs: the host evaluated and uploaded the live points
+            if (!p.host_like) st->init_attempts = 0;
         }
     }
     group_sync(&st->bar, NG);
@@ -603,6 +603,7 @@ __device__ inline bool publish_dump(const KParams& p, const RunBuf& rb, DevRun* 
     __syncthreads();
     if (threadIdx.x == 0) {
         ctl->ndead = st->ndead;
+        ctl->nlike = st->nlike;
         ctl->logZ = st->logZ;
         ctl->logZ2 = st->logZ2;
         __threadfence_system();
@@ -663,6 +664,20 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
     bool scatter_due = false;  // sharded run: the last babies of the generation are still in the incoming buffer
     bool s2_due = false;  // CTA 0: the evidence of the generation in flight is still to be accumulated
 
+    if (p.host_like && vload(&st->host_resume)) {
+        // host-callback run: the host loop ran the chains of the generation in flight; finish the generation
+        // (phase U at the update cadence) exactly where the chain phase would have left it
+        if (vload(&st->do_update)) {
+            phase_UA(p, rb, st, cta, NG);
+            group_sync(&st->bar, NG);
+            phase_UB(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt);
+            if (cta == 0 && tid == 0) st->update_pending = 1;
+        }
+        group_sync(&st->bar, NG);
+        if (cta == 0 && tid == 0) st->host_resume = 0;
+        group_sync(&st->bar, NG);
+    }
+
     const bool timer = (tid == 0) && (cta == 0);          // bookkeeping phases
     const bool ctimer = (tid == 0) && (cta == c0);         // chain phases of one representative warp
     const long long t_start = clock64();
@@ -710,6 +725,13 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
         if (cta == 0 && s2_due) {  // the chains are running: the evidence bookkeeping is off their critical path
             phase_S2(p, rb, st, smS);
             s2_due = false;
+        }
+        if (p.host_like) {  // the chains of this generation belong to the host loop (pc_hostchain.cuh)
+            if (cta == 0) {
+                __syncthreads();
+                if (tid == 0) st->status = ST_HOSTCHAINS;
+            }
+            return;
         }
         const bool sharded = p.sh.world > 1;
         const int xw = sharded ? p.sh.world : 1, xr = sharded ? p.sh.rank : 0;

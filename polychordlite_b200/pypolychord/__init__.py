@@ -12,7 +12,7 @@ C ABI (`polychord_c_interface`, include/polychord_b200.h) instead of the Fortran
 """
 from .polychord import run, run_polychord, default_prior, default_dumper  # noqa: F401
 from .settings import PolyChordSettings  # noqa: F401
-from .output import NestedSamplesLite  # noqa: F401
+from .output import NestedSamplesLite, PolyChordOutput  # noqa: F401
 from . import priors, builtin  # noqa: F401
 
 __version__ = "1.22.2+b200"

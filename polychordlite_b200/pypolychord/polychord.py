@@ -2,11 +2,12 @@
 on top of the B200 engine's C ABI.
 
 Differences from the reference, all forced by scope:
-  * the loglikelihood must have a device form (`pypolychord.builtin.*`) and the prior must be the default
-    unit-cube prior or a `UniformPrior`; arbitrary Python callables need the generic host-callback path
-    (row f2, not built yet) and raise NotImplementedError with that explanation;
-  * no files are written yet (row f1); the return value is an in-memory `NestedSamplesLite` built from the
-    final dumper call instead of `anesthetic.read_chains(...)`.
+  * likelihoods with a device form (`pypolychord.builtin.*`) with the default unit-cube prior or a `UniformPrior`
+    run the whole sampling loop on the GPU; any other Python callable (likelihood or prior) takes the engine's
+    host-callback path (row f2): the chains advance in lock step on the device and call back once per trial point;
+  * anesthetic is not installed in this image: `run()` returns `anesthetic.read_chains(...)` when it can be
+    imported and an in-memory `NestedSamplesLite` built from the final dumper call otherwise; `run_polychord()`
+    returns a `PolyChordOutput` parsed from the `<root>.stats` file the engine wrote (row f1).
 Everything else -- keyword names, defaults, TypeError on unknown keywords, ValueError when grade_dims does
 not sum to nDims, creation of base_dir/cluster_dir, the paramnames file, the dumper signature -- follows the
 reference line by line (polychord.py:520-595).
@@ -18,7 +19,7 @@ import numpy as np
 
 from .. import _capi
 from . import builtin as _builtin
-from .output import NestedSamplesLite, make_paramnames_file
+from .output import NestedSamplesLite, PolyChordOutput, make_paramnames_file
 from .priors import UniformPrior
 
 
@@ -60,10 +61,12 @@ def run(loglikelihood, nDims, **kwargs):
     }
     default_kwargs['grade_frac'] = ([1.0] * len(default_kwargs['grade_dims']) if 'grade_dims' not in kwargs
                                     else [1.0] * len(kwargs['grade_dims']))
+    legacy = kwargs.pop('_legacy_output', False)
     if not kwargs.keys() <= default_kwargs.keys():
         raise TypeError(f"{__name__} got unknown keyword arguments: {kwargs.keys() - default_kwargs.keys()}")
     default_kwargs.update(kwargs)
     kwargs = default_kwargs
+    kwargs['_legacy_output'] = legacy
 
     (Path(kwargs['base_dir']) / kwargs['cluster_dir']).mkdir(parents=True, exist_ok=True)
     if paramnames is not None:
@@ -77,13 +80,40 @@ def run(loglikelihood, nDims, **kwargs):
     L = _capi.lib()
     nDerived = int(kwargs['nDerived'])
     # ---- loglikelihood / prior -> device forms --------------------------------------------------
-    if not isinstance(loglikelihood, _builtin._DeviceLikelihood):
-        raise NotImplementedError(
-            "this engine runs the sampling loop on the GPU and needs a likelihood with a device form "
-            "(polychordlite_b200.pypolychord.builtin.Gaussian / Rastrigin / CorrelatedGaussian, or "
-            "pc_register_device_likelihood from C); the generic host-callback path for arbitrary Python "
-            "callables is not built yet (SURVEY.md section 8 row f2)")
-    like_fn = loglikelihood.register(nDims)
+    pending = []   # exception raised inside a callback: ctypes cannot unwind through the C frames, so it is kept,
+                   # the engine is asked to stop (pc_request_abort) and the exception is re-raised after the call
+    keep = []      # ctypes callback objects must outlive the run
+    L.pc_request_abort.restype = None
+
+    def _guard(fn, fallback):
+        def wrapped(*a):
+            if pending:
+                return fallback
+            try:
+                return fn(*a)
+            except BaseException as ex:  # noqa: BLE001 -- re-raised below
+                pending.append(ex)
+                L.pc_request_abort()
+                return fallback
+        return wrapped
+
+    if isinstance(loglikelihood, _builtin._DeviceLikelihood):
+        like_fn = loglikelihood.register(nDims)
+    else:
+        # polychord.py:581-587 wrap_loglikelihood: the callable returns logL or (logL, phi); theta is read-only
+        def _ll(theta_p, nd, phi_p, nder):
+            theta = _view(theta_p, (nd,))
+            theta.flags.writeable = False
+            res = loglikelihood(theta)
+            if isinstance(res, tuple):
+                logL, phi = res
+                if nder:
+                    _view(phi_p, (nder,))[:] = phi
+            else:
+                logL = res
+            return float(logL)
+        like_fn = _capi.LL_CB(_guard(_ll, float(kwargs['logzero'])))
+        keep.append(like_fn)
     prior = kwargs['prior']
     if prior is default_prior:
         prior_fn = C.cast(L.pc_unit_prior, _capi.PRIOR_CB)
@@ -93,9 +123,13 @@ def run(loglikelihood, nDims, **kwargs):
         if L.pc_register_device_prior(prior_fn, 0, pp.ctypes.data_as(C.POINTER(C.c_double)), pp.size) != 0:
             raise RuntimeError("pc_register_device_prior failed")
     else:
-        raise NotImplementedError(
-            "only the unit-cube default prior and UniformPrior have a device form; other priors need the "
-            "generic host-callback path (SURVEY.md section 8 row f2, not built yet)")
+        # polychord.py:589-590 wrap_prior: theta[:] = prior(cube)
+        def _prior(cube_p, theta_p, nd):
+            cube = _view(cube_p, (nd,))
+            cube.flags.writeable = False
+            _view(theta_p, (nd,))[:] = prior(cube)
+        prior_fn = _capi.PRIOR_CB(_guard(_prior, None))
+        keep.append(prior_fn)
 
     # ---- dumper: the user's callable plus the in-memory result ------------------------------------
     last = {}
@@ -107,7 +141,7 @@ def run(loglikelihood, nDims, **kwargs):
             last.update(dead=dd.copy(), logweights=lw.copy(), logZ=logZ, logZerr=logZerr)
         user_dumper(lv, dd, lw, logZ, logZerr)
 
-    dcb = _capi.DUMPER_CB(_dumper)
+    dcb = _capi.DUMPER_CB(_guard(_dumper, None))
     ngrade = len(kwargs['grade_dims'])
     grade_frac = (C.c_double * ngrade)(*[float(f) for f in kwargs['grade_frac']])
     grade_dims = (C.c_int * ngrade)(*kwargs['grade_dims'])
@@ -126,11 +160,22 @@ def run(loglikelihood, nDims, **kwargs):
               nlives, comm)
     finally:
         _capi.set_option("errors_return", old_err)
+    if pending:
+        raise pending[0]
     info = _capi.last_run_info()
     if info.status != 0 or not last:
         raise RuntimeError(f"polychord_c_interface failed (status {info.status}); see the message on stderr")
-    return NestedSamplesLite(last['dead'], last['logweights'], last['logZ'], last['logZerr'], nDims, nDerived,
+    lite = NestedSamplesLite(last['dead'], last['logweights'], last['logZ'], last['logZerr'], nDims, nDerived,
                              info=info.as_dict())
+    if kwargs.get('_legacy_output'):
+        return lite
+    try:  # polychord.py:639-646: the chains as anesthetic reads them from the files the engine wrote
+        import anesthetic
+        if kwargs['write_dead']:
+            return anesthetic.read_chains(str(Path(kwargs['base_dir']) / kwargs['file_root']))
+    except ImportError:
+        pass
+    return lite
 
 
 def _call(L, like_fn, prior_fn, dcb, kwargs, nDims, nDerived, ngrade, grade_frac, grade_dims, nl, loglikes, nlives,
@@ -157,4 +202,9 @@ def run_polychord(loglikelihood, nDims, nDerived, settings, prior=default_prior,
         'write_paramnames', 'read_resume', 'write_stats', 'write_live', 'write_dead', 'write_prior', 'maximise',
         'compression_factor', 'synchronous', 'base_dir', 'file_root', 'grade_dims', 'nlives', 'seed')}
     kw['grade_frac'] = settings.grade_frac
-    return run(loglikelihood, nDims, nDerived=nDerived, prior=prior, dumper=dumper, **kw)
+    lite = run(loglikelihood, nDims, nDerived=nDerived, prior=prior, dumper=dumper, _legacy_output=True, **kw)
+    if settings.write_stats:  # polychord.py:218: PolyChordOutput(base_dir, file_root), parsed from <root>.stats
+        out = PolyChordOutput(settings.base_dir, settings.file_root)
+        out.samples = lite
+        return out
+    return lite

@@ -36,9 +36,11 @@ def test_grade_dims_must_sum_to_nDims(tmp_path):
 
 def test_run_creates_directories_and_paramnames(tmp_path):
     base = tmp_path / "chains"
-    with pytest.raises(NotImplementedError):  # raised after the reference's own preamble has run
-        pypolychord.run(lambda theta: 0.0, nDims, base_dir=str(base), file_root="t",
-                        paramnames=[("a", "\\alpha"), ("b", "\\beta")])
+    try:  # without a device the engine refuses to run (no CPU fallback) -- after the reference's own preamble has run
+        pypolychord.run(lambda theta: -float(np.sum(theta ** 2)), nDims, base_dir=str(base), file_root="t", nlive=20,
+                        num_repeats=4, feedback=0, paramnames=[("a", "\\alpha"), ("b", "\\beta")])
+    except RuntimeError:
+        pass
     assert (base / "clusters").is_dir()
     assert (base / "t.paramnames").read_text().splitlines() == ["a   \\alpha", "b   \\beta"]
 
@@ -114,3 +116,36 @@ def test_legacy_run_polychord(gpu, tmp_path):
 def test_unsupported_configuration_raises(gpu, tmp_path):
     with pytest.raises(RuntimeError):
         pypolychord.run(Gaussian(), nDims, base_dir=str(tmp_path), grade_dims=[1, 3], **KW)   # fast/slow grades
+
+
+@pytest.mark.gpu
+def test_output_files_and_PolyChordOutput(gpu, tmp_path):
+    """run_polychord() returns a PolyChordOutput parsed from <root>.stats
+    (polychord.py:218, output.py:57-99) and the engine writes the files anesthetic/getdist read."""
+    s = PolyChordSettings(nDims, 1, nlive=200, num_repeats=12, feedback=0, do_clustering=False, write_resume=False,
+                          read_resume=False, base_dir=str(tmp_path), file_root="f1", seed=3)
+    seen = {}
+
+    def dumper(live, dead, logweights, logZ, logZerr):
+        seen.update(ndead=dead.shape[0], last=dead[-1].copy(), logZ=logZ)
+
+    out = pypolychord.run_polychord(Gaussian(mu=0.0, sigma=0.1, nDerived=1), nDims, 1, s, UniformPrior(-1, 1), dumper)
+    assert isinstance(out, pypolychord.PolyChordOutput)
+    assert out.ndead == seen["ndead"] and out.nlive == 0 and out.ncluster == 1
+    assert abs(out.logZ - seen["logZ"]) < 1e-12 and abs(out.logZ - (-4 * np.log(2))) < 0.5
+    assert out.nlike == out.samples.info["nlike"]
+    db = out.dead_birth()                                   # theta, phi, logL, birth
+    assert db.shape == (out.ndead, nDims + 1 + 2)
+    assert np.allclose(db[-1, :nDims + 1], seen["last"][:nDims + 1], rtol=1e-14)
+    assert np.all(np.diff(db[:, -2]) >= 0)                  # dead points leave in order of logL
+    assert np.all(db[:, -1] <= db[:, -2])                   # born below where they died
+    w = out.weighted_posterior()
+    assert np.isclose(w[:, 0].max(), 1.0) and out.nposterior == w.shape[0]
+    mean = (w[:, 0] / w[:, 0].sum()) @ w[:, 2:2 + nDims]
+    assert np.all(np.abs(mean) < 0.03)                      # the posterior is N(0, 0.1^2)
+    assert np.allclose(out.means[:nDims], mean, atol=1e-9)
+    assert out.equal_weights().shape[0] == out.nequals > 50
+    assert (tmp_path / "f1.prior_info").read_text().split()[:3] == ["nprior", "=", "200"]
+    assert (tmp_path / "f1_phys_live.txt").exists()
+    out.make_paramnames_files([("p%i" % i, "\\theta_%i" % i) for i in range(nDims)] + [("r*", "r")])
+    assert len((tmp_path / "f1.paramnames").read_text().splitlines()) == nDims + 1
