@@ -205,6 +205,101 @@ void calc_cholesky(const double* a, double* L, int D) {
     }
 }
 
+// ----------------------------------------------------------------------------------
+// clustering.f90 (KNN_clustering module) restated.  Indices are zero-based.
+// ----------------------------------------------------------------------------------
+// Squared distance of two cube points.  calculate_similarity_matrix (calculate.f90:94-109) forms
+// |vi|^2 + |vj|^2 - 2 vi.vj with matmul; the difference form below is the same number up to rounding and is
+// the form the engine's kernel uses, accumulated with fused multiply-adds in dimension order so that both sides
+// produce bit-identical distances (the k-nearest-neighbour ORDER must not depend on who computed it).
+inline double dist2(const double* a, const double* b, int D) {
+    double s = 0.0;
+    for (int k = 0; k < D; ++k) { double d = a[k] - b[k]; s = std::fma(d, d, s); }
+    return s;
+}
+std::vector<double> similarity_matrix(const std::vector<const double*>& pts, int D) {
+    const int m = (int)pts.size();
+    std::vector<double> sim((size_t)m * m);
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) sim[(size_t)i * m + j] = dist2(pts[i], pts[j], D);
+    return sim;
+}
+// compute_knn (clustering.f90:134-174): for each point the k nearest (itself included), by insertion: a new
+// distance goes in front of the first stored distance that is strictly larger, so equal distances keep index order.
+std::vector<int> compute_knn(const std::vector<double>& sim, int m, int k) {
+    std::vector<int> knn((size_t)m * k, -1);
+    std::vector<double> d2(k);
+    for (int i = 0; i < m; ++i) {
+        std::fill(d2.begin(), d2.end(), HUGE_D);
+        int* row = &knn[(size_t)i * k];
+        for (int j = 0; j < m; ++j) {
+            const double v = sim[(size_t)i * m + j];
+            int pos = -1;
+            for (int t = 0; t < k; ++t) if (d2[t] > v) { pos = t; break; }
+            if (pos < 0) continue;
+            for (int t = k - 1; t > pos; --t) { d2[t] = d2[t - 1]; row[t] = row[t - 1]; }
+            d2[pos] = v; row[pos] = j;
+        }
+    }
+    return knn;
+}
+// relabel (utils.F90:713-749): labels in order of first appearance; returns their number
+int relabel(std::vector<int>& c) {
+    std::vector<int> mapping;
+    for (int v : c) if (std::find(mapping.begin(), mapping.end(), v) == mapping.end()) mapping.push_back(v);
+    for (int& v : c) v = (int)(std::find(mapping.begin(), mapping.end(), v) - mapping.begin());
+    return (int)mapping.size();
+}
+// do_clustering_k (clustering.f90:100-130) on the first n entries of every neighbour list, with
+// neighbours (:178-188): i ~ j when the head of one list appears in the other
+std::vector<int> do_clustering_k(const std::vector<int>& knn, int m, int k, int n) {
+    std::vector<int> c(m);
+    std::iota(c.begin(), c.end(), 0);
+    auto has = [&](int i, int v) { for (int t = 0; t < n; ++t) if (knn[(size_t)i * k + t] == v) return true; return false; };
+    for (int i = 0; i < m; ++i)
+        for (int j = i + 1; j < m; ++j)
+            if (c[i] != c[j] && (has(i, knn[(size_t)j * k]) || has(j, knn[(size_t)i * k]))) {
+                const int ci = c[i], cj = c[j], lo = std::min(ci, cj);
+                for (int& v : c) if (v == ci || v == cj) v = lo;
+            }
+    return c;
+}
+// NN_clustering (clustering.f90:15-97).  `do n=2,k` fixes its trip count at entry, so the "expand k" branch
+// (:64-67) never extends the search: k = min(m, 10) throughout.
+std::vector<int> NN_clustering(const std::vector<double>& sim, int m, int& num_clusters) {
+    std::vector<int> cl(m, 0);
+    num_clusters = 1;
+    if (m < 2) return cl;
+    const int k = std::min(m, 10);
+    const std::vector<int> knn = compute_knn(sim, m, k);
+    std::vector<int> old(m);
+    std::iota(old.begin(), old.end(), 0);
+    for (int n = 2; n <= k; ++n) {
+        cl = do_clustering_k(knn, m, k, n);
+        num_clusters = relabel(cl);
+        if (num_clusters == 1) return cl;
+        if (cl == old) break;
+        old = cl;
+    }
+    if (num_clusters > 1) {  // search within the clusters found (:78-95)
+        int ic = 0;
+        while (ic < num_clusters) {
+            std::vector<int> pts;
+            for (int j = 0; j < m; ++j) if (cl[j] == ic) pts.push_back(j);
+            const int mm = (int)pts.size();
+            std::vector<double> sub((size_t)mm * mm);
+            for (int a = 0; a < mm; ++a)
+                for (int b = 0; b < mm; ++b) sub[(size_t)a * mm + b] = sim[(size_t)pts[a] * m + pts[b]];
+            int nnew = 1;
+            const std::vector<int> subl = NN_clustering(sub, mm, nnew);
+            for (int a = 0; a < mm; ++a) cl[pts[a]] = num_clusters + subl[a];
+            if (nnew == 1) ++ic;
+            num_clusters = relabel(cl);
+        }
+    }
+    return cl;
+}
+
 // random_utils.F90:381-403 with random_direction (:276-298) and random_gaussian (:251-266).
 // basis is column-major D x D; Gaussian element (row r, column c) of basis number
 // `col0/D` comes from stream (tag, uid, a = col0 + c, b = r/2), lane r%2.
@@ -287,6 +382,7 @@ struct oracle_result {
     long long ndead, nlike, nchains, ngenerations, nupdates, nfailures;
     long long nslices, nphantoms_final;
     double seconds;
+    long long ncluster, nsplits;  // clusters at the end of the sampling loop; splits (reference mode) / labels (batched mode)
 };
 
 typedef void (*oracle_dumper_t)(int ndead, int nlive, int npars, double* live, double* dead, double* logweights,
@@ -661,14 +757,17 @@ struct Run {
             if (c.stack_l.empty()) continue;
             double lmax = *std::max_element(c.stack_l.begin(), c.stack_l.end());
             int w = 0;
+            const bool lbl = (int)phlab.size() == c.nphantom && &c == &cl[0];
             for (int i = 0; i < c.nphantom; ++i) {
                 if (!(lmax > c.phantom[(size_t)i * T + l0])) {
                     if (w != i)
                         std::copy(c.phantom.begin() + (size_t)i * T, c.phantom.begin() + (size_t)(i + 1) * T,
                                   c.phantom.begin() + (size_t)w * T);
+                    if (lbl) phlab[w] = phlab[i];
                     ++w;
                 }
             }
+            if (lbl) phlab.resize(w);
             c.nphantom = w;
             c.phantom.resize((size_t)w * T);
             c.stack_l.clear();
@@ -700,6 +799,169 @@ struct Run {
             }
             for (size_t k = 0; k < cov.size(); ++k) c.covmat[k] = (cov[k] + covp[k]) / N;
             calc_cholesky(c.covmat.data(), c.cholesky.data(), D);
+        }
+    }
+
+    // ---- clusters, reference mode: add_cluster / delete_cluster / do_clustering -----------------
+    int ncluster_dead = 0;
+    std::vector<double> logZp_dead, logZp2_dead;
+
+    // delete_cluster, run_time_info.f90:507-598: the first cluster without live points leaves the active arrays
+    bool delete_cluster() {
+        int p = -1;
+        for (int q = 0; q < (int)cl.size(); ++q) if (cl[q].nlive == 0) { p = q; break; }
+        if (p < 0) return false;
+        const int nc = (int)cl.size();
+        logZp_dead.push_back(cl[p].logZp);
+        logZp2_dead.push_back(cl[p].logZp2);
+        ++ncluster_dead;
+        std::vector<double> xx((size_t)(nc - 1) * (nc - 1));
+        for (int a = 0, ia = 0; a < nc; ++a) {
+            if (a == p) continue;
+            for (int b = 0, ib = 0; b < nc; ++b) {
+                if (b == p) continue;
+                xx[(size_t)ia * (nc - 1) + ib] = logXpXq[(size_t)a * nc + b];
+                ++ib;
+            }
+            ++ia;
+        }
+        cl.erase(cl.begin() + p);
+        logXpXq.swap(xx);
+        return true;
+    }
+
+    // add_cluster, run_time_info.f90:303-505: cluster p splits into num pieces appended after the surviving ones
+    void add_cluster(int p, const std::vector<int>& labels, int num) {
+        const int nc_old = (int)cl.size();
+        const Cluster old = cl[p];
+        std::vector<Cluster> before = cl;                       // old_phantom: every cluster's phantoms, old order
+        std::vector<int> keep;                                  // old_save
+        for (int q = 0; q < nc_old; ++q) if (q != p) keep.push_back(q);
+        const int nold = (int)keep.size(), nc = nold + num;
+        std::vector<double> xpq(nold);
+        for (int a = 0; a < nold; ++a) xpq[a] = logXpXq[(size_t)p * nc_old + keep[a]];
+        const double xpp = logXpXq[(size_t)p * nc_old + p];
+        std::vector<double> xx((size_t)nc * nc, 0.0);
+        for (int a = 0; a < nold; ++a)
+            for (int b = 0; b < nold; ++b) xx[(size_t)a * nc + b] = logXpXq[(size_t)keep[a] * nc_old + keep[b]];
+        std::vector<Cluster> ncl;
+        for (int q : keep) ncl.push_back(cl[q]);
+        for (int i = 0; i < num; ++i) {
+            Cluster c;
+            c.logLp = S.logzero;
+            c.covmat.assign((size_t)D * D, 0.0);
+            c.cholesky.assign((size_t)D * D, 0.0);
+            for (int d = 0; d < D; ++d) c.covmat[d + (size_t)d * D] = c.cholesky[d + (size_t)d * D] = 1.0;
+            ncl.push_back(c);
+        }
+        for (int i = 0; i < old.nlive; ++i) {                   // 3) live points to their new clusters, in order
+            Cluster& c = ncl[nold + labels[i]];
+            c.live.insert(c.live.end(), old.live.begin() + (size_t)i * T, old.live.begin() + (size_t)(i + 1) * T);
+            c.nlive++;
+        }
+        cl.swap(ncl);
+        logXpXq.swap(xx);
+        find_min();
+        for (auto& c : cl) { c.phantom.clear(); c.nphantom = 0; }   // 4) every phantom is re-assigned
+        for (int q = 0; q < nc_old; ++q)
+            for (int i = 0; i < before[q].nphantom; ++i) {
+                const double* pt = &before[q].phantom[(size_t)i * T];
+                const int j = identify_cluster(pt);
+                if (pt[l0] > cl[j].logLp) {
+                    cl[j].phantom.insert(cl[j].phantom.end(), pt, pt + T);
+                    cl[j].nphantom++;
+                }
+            }
+        // 5) volumes and evidences apportioned by the live + phantom counts
+        std::vector<double> logni(num), logni1(num);
+        for (int i = 0; i < num; ++i) {
+            logni[i] = std::log(cl[nold + i].nlive + cl[nold + i].nphantom + 0.0);
+            logni1[i] = std::log(cl[nold + i].nlive + cl[nold + i].nphantom + 1.0);
+        }
+        const double logn = logsumexp(logni.data(), logni.size()), logn1 = logaddexp(logn, 0.0);
+        for (int i = 0; i < num; ++i) {
+            Cluster& c = cl[nold + i];
+            c.logXp = old.logXp + logni[i] - logn;
+            c.logZXp = old.logZXp + logni[i] - logn;
+            c.logZp = old.logZp + logni[i] - logn;
+            c.logZp2 = old.logZp2 + logni[i] + logni1[i] - logn - logn1;
+            c.logZpXp = old.logZpXp + logni[i] + logni1[i] - logn - logn1;
+            for (int a = 0; a < nold; ++a) XX(nold + i, a) = XX(a, nold + i) = xpq[a] + logni[i] - logn;
+            for (int j = 0; j < num; ++j)
+                XX(nold + i, nold + j) = (i == j) ? xpp + logni[i] + logni1[i] - logn - logn1
+                                                  : xpp + logni[i] + logni[j] - logn - logn1;
+        }
+    }
+
+    // do_clustering, clustering.f90:253-324
+    bool do_clustering() {
+        bool found = false;
+        const int num_old = (int)cl.size();
+        int i = 0;
+        while (i < num_old) {
+            const int nl = cl[i].nlive;
+            if (nl > 2) {
+                std::vector<const double*> pts(nl);
+                for (int j = 0; j < nl; ++j) pts[j] = &cl[i].live[(size_t)j * T + h0];
+                int num = 1;
+                const std::vector<int> labels = NN_clustering(similarity_matrix(pts, D), nl, num);
+                if (num > 1) { found = true; add_cluster(i, labels, num); nsplits++; }
+                else ++i;
+            } else ++i;
+        }
+        return found;
+    }
+    long long nsplits = 0;
+
+    // ---- clusters, batched mode (the engine's schedule) ------------------------------------------
+    // The evidence stays global -- one nested-sampling run over the whole live set is exact whatever the shape of the
+    // posterior -- and the clusters only steer the proposals: at every update the live points are clustered from
+    // scratch (NN_clustering over all of them), the phantoms take the label of their nearest live point
+    // (identify_cluster), every cluster with more than nDims points gets the covariance / Cholesky factor of its
+    // own live + phantom points (the others keep the global one), a chain whitens its directions with the factor
+    // of its seed's cluster, and its babies inherit that label until the next update.
+    std::vector<int> lab, phlab;                  // label of every live slot / phantom record (all in cl[0])
+    std::vector<std::vector<double>> chols;       // Cholesky factor per label
+    int ncl_b = 1;
+    void cluster_update_batched() {
+        Cluster& c = cl[0];
+        const int n = c.nlive;
+        calculate_covmats();                      // the global covariance / factor
+        std::vector<const double*> pts(n);
+        for (int i = 0; i < n; ++i) pts[i] = &c.live[(size_t)i * T + h0];
+        int num = 1;
+        lab = NN_clustering(similarity_matrix(pts, D), n, num);
+        ncl_b = num;
+        if (num > 1) nsplits++;                   // updates that found more than one cluster
+        phlab.assign(c.nphantom, 0);
+        if (num > 1)
+            for (int i = 0; i < c.nphantom; ++i) {
+                const double* x = &c.phantom[(size_t)i * T + h0];
+                double best = HUGE_D;
+                int which = 0;
+                for (int j = 0; j < n; ++j) {
+                    const double d2 = dist2(x, pts[j], D);
+                    if (d2 < best) { best = d2; which = j; }   // ties: the lowest slot
+                }
+                phlab[i] = lab[which];
+            }
+        chols.assign(num, c.cholesky);
+        if (num == 1) return;
+        for (int p = 0; p < num; ++p) {
+            std::vector<const double*> mem;
+            for (int i = 0; i < n; ++i) if (lab[i] == p) mem.push_back(pts[i]);
+            for (int i = 0; i < c.nphantom; ++i) if (phlab[i] == p) mem.push_back(&c.phantom[(size_t)i * T + h0]);
+            const int N = (int)mem.size();
+            if (N <= D) continue;                 // too few points for a covariance: the global factor stays
+            std::vector<double> mean(D, 0.0), cov((size_t)D * D, 0.0), dv(D);
+            for (const double* x : mem) for (int k = 0; k < D; ++k) mean[k] += x[k];
+            for (int k = 0; k < D; ++k) mean[k] /= N;
+            for (const double* x : mem) {
+                for (int k = 0; k < D; ++k) dv[k] = x[k] - mean[k];
+                for (int b = 0; b < D; ++b) for (int a = 0; a < D; ++a) cov[a + (size_t)b * D] += dv[a] * dv[b];
+            }
+            for (double& v : cov) v /= N;
+            calc_cholesky(cov.data(), chols[p].data(), D);
         }
     }
 
@@ -776,12 +1038,12 @@ struct Run {
         find_min();
     }
 
-    void do_update() {
+    void do_update() {   // batched mode (nested_sampling.F90:321-368 in one piece: no cluster can die between the steps)
         logX_last_update = sum_logX();
-        if (S.batch_K > 0) clean_phantoms_stable(); else clean_phantoms();
+        clean_phantoms_stable();
         dump();
         nupdates++;
-        calculate_covmats();
+        if (S.do_clustering) cluster_update_batched(); else calculate_covmats();
     }
 
     // ---- reference-mode main loop, nested_sampling.F90:239-374 ----
@@ -817,7 +1079,19 @@ struct Run {
             ngen++;
             if (replace_point(babies, p)) failures = 0;
             else { failures++; nfail_total++; }
-            if (sum_logX() <= logX_last_update + std::log(S.compression_factor)) do_update();
+            const bool update = sum_logX() <= logX_last_update + std::log(S.compression_factor);   // :321
+            if (update) {
+                logX_last_update = sum_logX();
+                clean_phantoms();
+                dump();
+                nupdates++;
+            }
+            delete_cluster();                     // :339
+            if (cl.empty()) break;                // :346
+            if (update) {
+                if (S.do_clustering) do_clustering();   // :351-367
+                calculate_covmats();              // :368
+            }
         }
     }
 
@@ -851,19 +1125,25 @@ struct Run {
             // K chains seeded from the n-K survivors, all at contour Lstar
             int m = n - K;
             std::vector<double> newpts((size_t)K * T);
+            std::vector<int> newlab(K, 0);
+            const bool clustered = S.do_clustering && ncl_b > 1;
             for (int k = 0; k < K; ++k) {
                 uint64_t uid = (uint64_t)nchains + k;
                 double u = rng.uniform(TAG_SEED, uid, 0, 0);
                 int choice = (int)std::ceil(u * m);
                 if (choice < 1) choice = 1;
-                const double* seed = &c.live[(size_t)order[K + choice - 1] * T];
-                slice_sampling(Lstar, seed, c.cholesky.data(), uid, babies, nlike);
+                const int sslot = order[K + choice - 1];
+                const double* seed = &c.live[(size_t)sslot * T];
+                const int plab = clustered ? lab[sslot] : 0;
+                newlab[k] = plab;
+                slice_sampling(Lstar, seed, clustered ? chols[plab].data() : c.cholesky.data(), uid, babies, nlike);
                 for (int i = 0; i < R; ++i) babies[(size_t)i * T + b0] = Lstar;
                 for (int i = 0; i < R - 1; ++i) {
                     const double* pt = babies.data() + (size_t)i * T;
                     if (pt[l0] > Lstar) {
                         c.phantom.insert(c.phantom.end(), pt, pt + T);
                         c.nphantom++;
+                        if (S.do_clustering) phlab.push_back(plab);
                     }
                 }
                 const double* last = babies.data() + (size_t)(R - 1) * T;
@@ -872,6 +1152,7 @@ struct Run {
             }
             for (int k = 0; k < K; ++k)
                 std::copy(newpts.begin() + (size_t)k * T, newpts.begin() + (size_t)(k + 1) * T, c.live.begin() + (size_t)order[k] * T);
+            if (clustered) for (int k = 0; k < K; ++k) lab[order[k]] = newlab[k];
             nchains += K;
             ngen++;
             find_min();
@@ -909,6 +1190,8 @@ struct Run {
         // nprior > nlive: trim (nested_sampling.F90:201-203)
         while (cl[0].nlive > S.nlive) delete_outermost_point();
         if (S.batch_K > 0) run_batched(); else run_reference();
+        out->ncluster = S.batch_K > 0 ? ncl_b : (long long)cl.size();
+        out->nsplits = nsplits;
         final_killoff();
         dump();
         auto t1 = std::chrono::steady_clock::now();
@@ -1023,6 +1306,16 @@ int oracle_calculate_points(const oracle_settings* s, int like_kind, const doubl
     long long n = 0;
     for (int i = 0; i < npts; ++i) run.calculate_point(records + (size_t)i * run.T, n);
     return (int)n;
+}
+
+// NN_clustering (clustering.f90:15-97) of m points (row-major m x D cube coordinates); returns the number of clusters
+int oracle_nn_clustering(const double* points, int m, int D, int* labels_out) {
+    std::vector<const double*> pts(m);
+    for (int i = 0; i < m; ++i) pts[i] = points + (size_t)i * D;
+    int num = 1;
+    const std::vector<int> l = NN_clustering(similarity_matrix(pts, D), m, num);
+    std::copy(l.begin(), l.end(), labels_out);
+    return num;
 }
 
 void oracle_philox4x32_10(const unsigned* ctr, const unsigned* key, unsigned* out) {

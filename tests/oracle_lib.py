@@ -33,6 +33,7 @@ class OracleResult(C.Structure):
         ("ndead", C.c_longlong), ("nlike", C.c_longlong), ("nchains", C.c_longlong),
         ("ngenerations", C.c_longlong), ("nupdates", C.c_longlong), ("nfailures", C.c_longlong),
         ("nslices", C.c_longlong), ("nphantoms_final", C.c_longlong), ("seconds", C.c_double),
+        ("ncluster", C.c_longlong), ("nsplits", C.c_longlong),
     ]
 
 
@@ -184,3 +185,14 @@ def random_inverse_covmat(seed, D, sigma):
     L.oracle_random_inverse_covmat(C.c_uint(seed), D, C.c_double(sigma), inv.ctypes.data_as(C.POINTER(C.c_double)),
                                    C.byref(ld))
     return np.array(inv), ld.value
+
+
+def nn_clustering(points):
+    """NN_clustering (clustering.f90:15-97) of the rows of `points`; returns (labels, number of clusters)."""
+    L = lib()
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    m, D = pts.shape
+    labels = np.zeros(m, dtype=np.int32)
+    L.oracle_nn_clustering.restype = C.c_int
+    num = L.oracle_nn_clustering(_dptr(pts), m, D, labels.ctypes.data_as(C.POINTER(C.c_int)))
+    return labels, num
