@@ -158,6 +158,8 @@ typedef struct pc_run_info {
      * [3] phase U (phantom compaction + covariance), [4..6] one representative chain warp: direction
      * preparation left on the critical path, whitening, slice steps; [7] whole kernel */
     double phase_ms[8];
+    long long ncluster_max;     /* do_clustering: largest number of clusters an update found, and the number of */
+    long long ncluster_updates; /* updates that ran the clustering pass */
 } pc_run_info;
 
 /* Results of the most recent polychord_c_interface()/pc_run() in this process. */
@@ -225,6 +227,11 @@ void pc_format_e24(double value, char* out25);
 int pc_write_files(const char* base_dir, const char* file_root, int flags, int nDims, int nDerived, long long ndead,
                    const double* dead_rows, const double* dead_logw, int nlive, const double* live_rows, double logZ,
                    double logZerr, long long nlike, int num_repeats, double compression_factor, unsigned seed);
+
+/* NN_clustering (clustering.f90:15-97) of m points (row-major m x nDims cube coordinates) exactly as the engine's
+ * update runs it (device k-nearest-neighbour lists, host union-find); labels in order of first appearance.
+ * Returns the number of clusters. */
+int pc_cluster_points(const double* points, int m, int nDims, int* labels_out);
 
 /* Number of CUDA devices visible; <=0 means the engine cannot run (no CPU fallback exists). */
 int pc_device_count(void);

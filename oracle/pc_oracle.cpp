@@ -931,6 +931,11 @@ struct Run {
         for (int i = 0; i < n; ++i) pts[i] = &c.live[(size_t)i * T + h0];
         int num = 1;
         lab = NN_clustering(similarity_matrix(pts, D), n, num);
+        if (num > 256) {                          // the engine keeps 256 factors: further labels share the last one (global factor)
+            for (int& v : lab) v = std::min(v, 255);
+        }
+        const bool clamped = num > 256;
+        if (clamped) num = 256;
         ncl_b = num;
         if (num > 1) nsplits++;                   // updates that found more than one cluster
         phlab.assign(c.nphantom, 0);
@@ -952,7 +957,7 @@ struct Run {
             for (int i = 0; i < n; ++i) if (lab[i] == p) mem.push_back(pts[i]);
             for (int i = 0; i < c.nphantom; ++i) if (phlab[i] == p) mem.push_back(&c.phantom[(size_t)i * T + h0]);
             const int N = (int)mem.size();
-            if (N <= D) continue;                 // too few points for a covariance: the global factor stays
+            if (N <= D || (clamped && p == 255)) continue;   // too few points for a covariance: the global factor stays
             std::vector<double> mean(D, 0.0), cov((size_t)D * D, 0.0), dv(D);
             for (const double* x : mem) for (int k = 0; k < D; ++k) mean[k] += x[k];
             for (int k = 0; k < D; ++k) mean[k] /= N;

@@ -26,7 +26,7 @@ EXPORTS = [
     "pc_unit_prior", "pc_uniform_prior", "pc_set_option", "pc_get_option", "pc_set_stream", "pc_release_memory", "pc_mgpu_create", "pc_mgpu_attach", "pc_mgpu_destroy",
     "pc_last_run_info", "pc_run", "pc_run_ensemble", "pc_slice_chains", "pc_calculate_points",
     "pc_device_philox", "pc_device_uniforms", "pc_device_inv_normal_cdf", "pc_device_directions",
-    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort",
+    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points",
 ]
 
 
@@ -49,6 +49,7 @@ class RunInfo(C.Structure):
         ("warps_per_cta", C.c_int), ("ctas_per_run", C.c_int), ("kernel_launches", C.c_int),
         ("device_ms", C.c_double), ("wall_ms", C.c_double), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong),
         ("algorithmic_bytes", C.c_longlong), ("phase_ms", C.c_double * 8),
+        ("ncluster_max", C.c_longlong), ("ncluster_updates", C.c_longlong),
     ]
 
     def as_dict(self):
@@ -296,3 +297,16 @@ def write_files(base_dir, file_root, nDims, nDerived, dead_rows, dead_logw, live
     return L.pc_write_files(str(base_dir).encode(), str(file_root).encode(), fl, nDims, nDerived, dead_rows.shape[0],
                             _dptr(dead_rows), _dptr(dead_logw), live_rows.shape[0], _dptr(live_rows), float(logZ),
                             float(logZerr), int(nlike), int(num_repeats), float(compression_factor), int(seed))
+
+
+def cluster_points(points):
+    """pc_cluster_points: (labels, number of clusters) of the rows of `points`."""
+    L = lib()
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    m, D = pts.shape
+    labels = np.zeros(m, dtype=np.int32)
+    L.pc_cluster_points.restype = C.c_int
+    num = L.pc_cluster_points(_dptr(pts), m, D, labels.ctypes.data_as(C.POINTER(C.c_int)))
+    if num < 0:
+        raise RuntimeError(f"pc_cluster_points failed with status {num}")
+    return labels, num

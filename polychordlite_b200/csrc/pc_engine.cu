@@ -22,6 +22,7 @@
 #include "pc_probes.cuh"
 #include "pc_files.h"
 #include "pc_hostchain.cuh"
+#include "pc_cluster.cuh"
 #include "pc_shapes.h"
 
 namespace pc {
@@ -344,7 +345,8 @@ static void set_smem(const ShapeFns& fn, size_t smem) {
 struct HostRun {
     DevArr<DevRun> st;
     DevArr<double> live, live_snap, dead, logw, ph0, ph1, chol, cov, partial, nh, gsum;
-    DevArr<int> order;
+    DevArr<int> order, lab, phl0, phl1;
+    DevArr<double> cchol;
     DevArr<long long> pcount;
     RunBuf buf;
     DevRun host_st;
@@ -508,6 +510,8 @@ struct Engine {
         mark("layout+set_smem");
         KParams& k = L.kp;
         const int K = k.batch_K;
+        // do_clustering: one run on one GPU with a device likelihood; elsewhere the run stays one cluster (always valid)
+        k.clustering = (S.do_clustering && nruns == 1 && g_mgpu.world <= 1 && !host_like) ? 1 : 0;
         // CTAs per run: one warp per chain unless capped by residency
         int dev = 0, sms = 0, per_sm = 0;
         PC_CUDA(cudaGetDevice(&dev));
@@ -562,11 +566,18 @@ struct Engine {
             h.partial.alloc((size_t)G * k.partial_stride);
             h.pcount.alloc((size_t)cap_ph / U_TILE + 2); h.pcount.zero(stream);
             if (!k.nh_in_smem) h.nh.alloc((size_t)G * W * R * k.cp.LD);
+            if (k.clustering) {
+                h.lab.alloc(n); h.lab.zero(stream);
+                h.phl0.alloc(cap_ph); h.phl0.zero(stream);
+                h.phl1.alloc(cap_ph); h.phl1.zero(stream);
+                h.cchol.alloc((size_t)MAX_CLUSTERS * D * D);
+            }
             RunBuf& b = h.buf;
             std::memset(&b, 0, sizeof(b));
             b.st = h.st.p; b.live = h.live.p; b.live_snap = nullptr; b.ctl = nullptr; b.order = h.order.p; b.dead = h.dead.p; b.logw = h.logw.p;
             b.ph[0] = h.ph0.p; b.ph[1] = h.ph1.p; b.chol = h.chol.p; b.cov = h.cov.p; b.partial = h.partial.p;
             b.pcount = h.pcount.p; b.nh = h.nh.p; b.cap_dead = cap_dead; b.cap_ph = cap_ph; b.gsum = h.gsum.p;
+            b.lab = h.lab.p; b.phl[0] = h.phl0.p; b.phl[1] = h.phl1.p; b.cchol = h.cchol.p;
             if (sharded)  // continue the cross-GPU barrier count of earlier runs (the counters are monotonic)
                 PC_CUDA(cudaMemcpyAsync(&h.st.p->xepoch, &g_mgpu.epoch, sizeof(g_mgpu.epoch), cudaMemcpyHostToDevice, stream));
             b.seed = (unsigned)seeds[r];
@@ -693,6 +704,138 @@ struct Engine {
                             std::sqrt(std::fabs(var)), nlike_now, final_call);
     }
 
+    // ---- clustering at the update cadence (pc_cluster.cuh) -------------------------------------------------
+    long long ncluster_updates = 0, ncluster_max = 0;
+    std::vector<int> h_lab, h_knn;
+    DevArr<int> d_part, d_knn, d_ccount;
+
+    // NN_clustering (clustering.f90:15-97) over all live points, from scratch.  The recursion into the clusters found
+    // becomes a work list: every round the device computes the 10 nearest neighbours of every point WITHIN its
+    // current part, and each part that is not final yet is split into the connected components of its
+    // mutual-neighbour graph for n = 2, 3, ... (stopping at one component or at the first n that changes nothing).
+    // Parts that come back whole are final.  Labels are canonical: in order of first appearance over the slots
+    // (utils.F90:713-749 relabel), which is what the recursive formulation ends with.
+    int cluster_labels(std::vector<int>& lab_out) {
+        const KParams& k = L.kp;
+        return cluster_labels_of(runs[0].live.p, k.n, k.cp.D, k.cp.T, lab_out);
+    }
+    int cluster_labels_of(const double* d_live, int n, int D, int T, std::vector<int>& lab_out) {
+        std::vector<int> part(n, 0);
+        std::vector<char> final_part(1, 0);
+        int nparts = 1;
+        if (!d_part.p) { d_part.alloc(n); d_knn.alloc((size_t)n * KNN_K); }
+        h_knn.resize((size_t)n * KNN_K);
+        std::vector<int> uf(n), loc(n), canon(n), old(n), members;
+        auto find = [&](int a) { while (uf[a] != a) { uf[a] = uf[uf[a]]; a = uf[a]; } return a; };
+        for (int round = 0; round < 64; ++round) {
+            bool any = false;
+            for (int c = 0; c < nparts; ++c) any = any || !final_part[c];
+            if (!any) break;
+            d_part.upload(part.data(), n, stream);
+            const int W = 8;
+            pc_knn_kernel<<<(n + W - 1) / W, W * 32, (size_t)W * D * 8, stream>>>(d_live, T, D, n, d_part.p, d_knn.p);
+            PC_CUDA(cudaGetLastError());
+            d_knn.download(h_knn.data(), (size_t)n * KNN_K, stream);
+            PC_CUDA(cudaStreamSynchronize(stream));
+            launches += 1;
+            h2d += (long long)n * 4; d2h += (long long)n * KNN_K * 4;
+            const int nparts_now = nparts;
+            for (int c = 0; c < nparts_now; ++c) {
+                if (final_part[c]) continue;
+                members.clear();
+                for (int i = 0; i < n; ++i) if (part[i] == c) members.push_back(i);
+                const int m = (int)members.size();
+                if (m <= 2) { final_part[c] = 1; continue; }   // do_clustering: nlive > 2 (clustering.f90:289); two points are each other's neighbours
+                const int kk = std::min(m, KNN_K);
+                for (int a = 0; a < m; ++a) { loc[members[a]] = a; uf[a] = a; old[a] = a; }
+                // points grouped by the head of their own list (a point's nearest neighbour is itself unless it has a twin)
+                std::vector<std::vector<int>> byhead(m);
+                for (int a = 0; a < m; ++a) byhead[loc[h_knn[(size_t)members[a] * KNN_K]]].push_back(a);
+                int num = m;
+                bool split = false;
+                for (int nn = 2; nn <= kk; ++nn) {
+                    // the graph only gains edges with n: add those of list position nn-1 (and, the first time, position 0)
+                    for (int t = (nn == 2 ? 0 : nn - 1); t < nn; ++t)
+                        for (int a = 0; a < m; ++a) {
+                            const int v = h_knn[(size_t)members[a] * KNN_K + t];
+                            if (v < 0) continue;
+                            for (int b : byhead[loc[v]]) {   // neighbours(): the head of b's list appears in a's
+                                const int ra = find(a), rb = find(b);
+                                if (ra != rb) uf[std::max(ra, rb)] = std::min(ra, rb);
+                            }
+                        }
+                    // canonical labels of the components, in order of first appearance
+                    num = 0;
+                    std::vector<int> first(m, -1);
+                    for (int a = 0; a < m; ++a) {
+                        const int r0 = find(a);
+                        if (first[r0] < 0) first[r0] = num++;
+                        canon[a] = first[r0];
+                    }
+                    if (num == 1) break;
+                    bool same = true;
+                    for (int a = 0; a < m && same; ++a) same = canon[a] == old[a];
+                    if (same) { split = true; break; }
+                    for (int a = 0; a < m; ++a) old[a] = canon[a];
+                    if (nn == kk) split = true;
+                }
+                if (!split || num == 1) { final_part[c] = 1; continue; }
+                // component 0 keeps the part's number, the others become new parts; all of them are searched again
+                std::vector<int> newid(num, c);
+                for (int s2 = 1; s2 < num; ++s2) { newid[s2] = nparts++; final_part.push_back(0); }
+                for (int a = 0; a < m; ++a) part[members[a]] = newid[canon[a]];
+            }
+        }
+        std::vector<int> first(nparts, -1);
+        int num = 0;
+        lab_out.resize(n);
+        for (int i = 0; i < n; ++i) {
+            if (first[part[i]] < 0) first[part[i]] = num++;
+            lab_out[i] = first[part[i]];
+        }
+        return num;
+    }
+
+    // the update's clustering pass: labels of the live points, labels of the phantoms (identify_cluster), one
+    // covariance + Cholesky factor per cluster (calculate_covmats, run_time_info.f90:601-641)
+    void cluster_pass() {
+        const KParams& k = L.kp;
+        const int n = k.n, D = k.cp.D, T = k.cp.T;
+        HostRun& h = runs[0];
+        int num = cluster_labels(h_lab);
+        if (num > MAX_CLUSTERS) {   // further labels share the last one, which keeps the global factor
+            for (int& v : h_lab) v = std::min(v, MAX_CLUSTERS - 1);
+        }
+        const int ncl = std::min(num, MAX_CLUSTERS);
+        ++ncluster_updates;
+        ncluster_max = std::max<long long>(ncluster_max, num);
+        h.lab.upload(h_lab.data(), n, stream);
+        h2d += (long long)n * 4;
+        if (ncl > 1) {
+            const int cur = h.host_st.cur_pool;
+            const long long nph = h.host_st.nphantom;
+            const double* ph = cur == 0 ? h.ph0.p : h.ph1.p;
+            int* phl = cur == 0 ? h.phl0.p : h.phl1.p;
+            const int W = 8;
+            if (nph > 0) {
+                const int blocks = (int)std::min<long long>((nph + W - 1) / W, 148LL * 16);
+                pc_identify_kernel<<<blocks, W * 32, (size_t)W * D * 8, stream>>>(h.live.p, T, D, n, h.lab.p, ph, nph, phl);
+                PC_CUDA(cudaGetLastError());
+            }
+            if (!d_ccount.p) d_ccount.alloc(MAX_CLUSTERS);
+            const size_t smem = cluster_cov_smem(D, W);
+            PC_CUDA(cudaFuncSetAttribute(pc_cluster_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            pc_cluster_cov_kernel<<<ncl, W * 32, smem, stream>>>(h.live.p, h.lab.p, n, ph, phl, nph, T, D, h.gsum.p + 2, h.chol.p,
+                                                                h.cchol.p, d_ccount.p);
+            PC_CUDA(cudaGetLastError());
+            if (num > MAX_CLUSTERS)  // the shared last label keeps the global factor
+                PC_CUDA(cudaMemcpyAsync(h.cchol.p + (size_t)(MAX_CLUSTERS - 1) * D * D, h.chol.p, (size_t)D * D * 8, cudaMemcpyDeviceToDevice, stream));
+            launches += 2;
+        }
+        PC_CUDA(cudaMemcpyAsync(&h.st.p->ncl, &ncl, sizeof(int), cudaMemcpyHostToDevice, stream));
+        PC_CUDA(cudaStreamSynchronize(stream));
+    }
+
     void grow(int r, int status) {
         HostRun& h = runs[r];
         const KParams& k = L.kp;
@@ -708,6 +851,13 @@ struct Engine {
             DevArr<double>& b = cur == 0 ? h.ph1 : h.ph0;
             a.grow((size_t)nc * k.cp.T, (size_t)h.host_st.nphantom * k.cp.T, stream);
             b.alloc((size_t)nc * k.cp.T);
+            if (k.clustering) {
+                DevArr<int>& la = cur == 0 ? h.phl0 : h.phl1;
+                DevArr<int>& lb = cur == 0 ? h.phl1 : h.phl0;
+                la.grow((size_t)nc, (size_t)h.host_st.nphantom, stream);
+                lb.alloc((size_t)nc);
+                h.buf.phl[0] = h.phl0.p; h.buf.phl[1] = h.phl1.p;
+            }
             h.pcount.alloc((size_t)nc / U_TILE + 2);
             h.buf.pcount = h.pcount.p;
             h.buf.ph[0] = h.ph0.p; h.buf.ph[1] = h.ph1.p; h.buf.cap_ph = nc;
@@ -718,7 +868,7 @@ struct Engine {
         auto t0 = std::chrono::steady_clock::now();
         volatile HostCtl* ctl = nullptr;
         unsigned long long handled = 0;
-        const bool sync_dump = g_opt.sync_dump || std::getenv("PC_SYNC_DUMP") || host_like;  // a host-callback run returns to the host every generation anyway
+        const bool sync_dump = g_opt.sync_dump || std::getenv("PC_SYNC_DUMP") || host_like || L.kp.clustering;  // these runs return to the host at every update anyway
         if (host_like) host_generate_live_points();
         const bool want_files = g_files.enabled && nruns == 1;
         const bool dumping = (dumper != nullptr || want_files) && nruns == 1;
@@ -776,6 +926,12 @@ struct Engine {
                     dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, runs[r].live.p, stream,
                          runs[r].host_st.nlike);
                 if (stt == ST_HOSTCHAINS) host_chains();
+                if (stt == ST_CLUSTER) {  // the update left for the clustering pass; the dump of this update happens here too
+                    if (dumping)
+                        dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, runs[r].live.p, stream,
+                             runs[r].host_st.nlike);
+                    cluster_pass();
+                }
                 if (stt == ST_NEED_DEAD || stt == ST_NEED_PHANTOM) { grow(r, stt); regrow = true; }
                 if (stt != ST_DONE) all_done = false;
             }
@@ -810,6 +966,7 @@ struct Engine {
             o.logZ_raw = s.logZ; o.logZ2_raw = s.logZ2;
             o.ndead = s.ndead; o.nlike = s.nlike; o.nchains = s.nchains; o.ngenerations = s.ngen;
             o.nupdates = s.nupdates; o.nfailures = s.nfail; o.nslices = s.nslices; o.nphantoms_final = s.nphantom;
+            o.ncluster_max = ncluster_max; o.ncluster_updates = ncluster_updates;
             o.batch_K = k.batch_K; o.warps_per_cta = L.W; o.ctas_per_run = G; o.kernel_launches = launches;
             o.device_ms = device_ms;
             o.wall_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
@@ -1248,6 +1405,23 @@ int pc_device_cholesky(const double* a, int D, double* L_out) {
         fb.download(&f, 1, g_stream);
         PC_CUDA(cudaStreamSynchronize(g_stream));
         return f;
+    } catch (const std::exception& ex) {
+        return fail(-3, ex.what());
+    }
+}
+
+// NN_clustering of m points (row-major m x D) as the engine's update runs it: device neighbour lists + host union-find
+int pc_cluster_points(const double* points, int m, int D, int* labels_out) {
+    try {
+        device_check();
+        Engine e;
+        e.stream = g_stream;
+        DevArr<double> d((size_t)m * D);
+        d.upload(points, (size_t)m * D, g_stream);
+        std::vector<int> lab;
+        const int num = e.cluster_labels_of(d.p, m, D, D, lab);
+        std::copy(lab.begin(), lab.end(), labels_out);
+        return num;
     } catch (const std::exception& ex) {
         return fail(-3, ex.what());
     }

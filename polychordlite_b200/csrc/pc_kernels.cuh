@@ -25,11 +25,13 @@
 
 namespace pc {
 
-enum Status : int { ST_RUNNING = 0, ST_DONE = 1, ST_NEED_DEAD = 2, ST_NEED_PHANTOM = 3, ST_DUMP = 4, ST_HOSTCHAINS = 5, ST_ERROR = -1 };
+enum Status : int { ST_RUNNING = 0, ST_DONE = 1, ST_NEED_DEAD = 2, ST_NEED_PHANTOM = 3, ST_DUMP = 4, ST_HOSTCHAINS = 5, ST_CLUSTER = 6, ST_ERROR = -1 };
 
 constexpr double NEG_BIG = -1e300;  // log(0) stand-in that survives additions without NaN
 constexpr int COV_TPP = 10;         // 8x8 tiles of the moment matrix a warp accumulates per pass of phase U (2 registers each)
 constexpr int U_TILE = 256;         // records per phantom tile of phase U (= threads per CTA)
+constexpr int KNN_K = 10;           // clustering.f90:44: "10 degrees of separation"
+constexpr int MAX_CLUSTERS = 256;   // clusters with a factor of their own; further labels share the last one, which keeps the global factor
 constexpr int U_BATCH = 8;          // records a warp of phase U keeps in flight
 
 // Mutable per-run scalars (device global memory; the host reads them between launches).
@@ -57,6 +59,8 @@ struct DevRun {
     int chol_fallback;   // number of calc_cholesky identity fallbacks
     int order_valid;     // rb.order + order_off holds the live slots sorted by (logL, slot) as of the last phase S
     int order_off;       // 0 or n: which half of rb.order is current
+    int ncl;             // clusters found at the last update (1: the global factor is used)
+    int pad1;
     int host_resume;     // host-callback runs: the chains of the generation in flight were run by the host loop
     int pad0;
     // SM-clock cycle counters of the phases (thread 0 of CTA 0; chain phases: warp 0 of the first chain CTA)
@@ -94,6 +98,9 @@ struct RunBuf {
     double* gsum;      // [0] surviving phantoms of all ranks, [2..2+D) mean of live + phantom cube coordinates, [2+D..2+2D) pivot of the next update
     long long* pcount; // survivor count of each phantom tile (phase U)
     double* nh;        // global direction scratch (used when the directions do not fit in smem)
+    int* lab;          // clustering: label of every live slot
+    int* phl[2];       // clustering: label of every phantom record (compacted with the pools)
+    double* cchol;     // clustering: Cholesky factor per label, MAX_CLUSTERS x D x D
     long long cap_dead, cap_ph;
     unsigned int seed;
     int pad;
@@ -125,6 +132,7 @@ struct KParams {
     int chain_cta0;              // first CTA of a run's group that runs chains (1: CTA 0 only keeps the books)
     int paired;                  // 1: warps w >= W/2 prepare the chains of warp w - W/2 (a run alone on the device)
     int nh_in_smem, want_dump;
+    int clustering;              // 1: do_clustering -- the kernel leaves at every update for the clustering pass (pc_cluster.cuh)
     int host_like;               // 1: likelihood/prior are host callbacks -- the kernel leaves before the chain phase (pc_hostchain.cuh)
     int ntri, cov_passes, partial_stride;
     int off_like, off_warp, warp_bytes;  // shared-memory byte offsets

@@ -27,6 +27,7 @@ __device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st
             st->logZ = st->logZ2 = st->logZX = p.cp.logzero;  // run_time_info.f90:165-175
             st->logX = st->logXX = 0.0;
             st->logX_last_update = 0.0;
+            st->ncl = 1;
             st->init_need = p.host_like ? 0 : n;   // host-callback runs: the host evaluated and uploaded the live points
             if (!p.host_like) st->init_attempts = 0;
         }
@@ -392,6 +393,11 @@ __device__ inline void phase_UB(const KParams& p, const RunBuf& rb, DevRun* st, 
                     if (rem) { const int bit = __ffs(rem) - 1; rem &= rem - 1; rp[b2] = rbase + (size_t)bit * T; ++nb; }
                 }
                 double* out = dst + (size_t)(tbase + woff + kk) * T;
+                if (copy && p.clustering) {  // the phantom's cluster label moves with it
+#pragma unroll
+                    for (int b2 = 0; b2 < U_BATCH; ++b2)
+                        if (lane == b2 && b2 < nb) rb.phl[pool ^ 1][tbase + woff + kk + b2] = __ldcg(rb.phl[pool] + (rp[b2] - src) / T);
+                }
                 __syncwarp();
                 for (int j = 0; j < jmax; ++j) {
                     const int e = lane + 32 * j;
@@ -691,16 +697,19 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                 scatter_due = false;
             }
             long long t1 = clock64();
-            bool dump_exit = false;
+            bool dump_exit = false, cluster_exit = false;
             if (st->update_pending) {
                 if (!finish_update(p, rb, st, NG, smS.akey, s_chol) && tid == 0) st->status = ST_ERROR;
                 __syncthreads();
-                if (rb.ctl) dump_exit = publish_dump(p, rb, st);   // the kernel keeps running
+                if (p.clustering) cluster_exit = true;             // leave: the host runs the clustering pass (pc_cluster.cuh), dumps, relaunches
+                else if (rb.ctl) dump_exit = publish_dump(p, rb, st);   // the kernel keeps running
                 else if (p.want_dump) dump_exit = true;              // "sync_dump": leave, the host dumps and relaunches
             }
             long long t2 = clock64();
             bool evidence_due = false;
-            if (dump_exit) {
+            if (cluster_exit) {
+                if (tid == 0) st->status = ST_CLUSTER;
+            } else if (dump_exit) {
                 if (tid == 0) st->status = ST_DUMP;
             } else if (vload(&st->status) != ST_ERROR) {
                 evidence_due = phase_S1(p, rb, st, smS);
@@ -751,6 +760,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
         const long long ndead_base = vload(&st->ndead_base), nph_base = vload(&st->nph_base);
         const long long nchains_base = vload(&st->nchains_base);
         const int do_update = vload(&st->do_update);
+        const bool clustered = p.clustering && vload(&st->ncl) > 1;
         const int* order = rb.order + vload(&st->order_off);
         double* pool = rb.ph[vload(&st->cur_pool)];
         for (int e = tid; e < D * D; e += blockDim.x) s_chol[e] = __ldcg(rb.chol + e);
@@ -780,19 +790,21 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                 const int k = cl * xw + xr;                        // chain of the generation (dealt k % world)
                 const unsigned long long uid = (unsigned long long)(nchains_base + k);
                 const ChainScratch b = buf(pair_seq + j);
+                double u = uniform(rb.seed, TAG_SEED, uid, 0u, 0u);  // GenerateSeed, generate.F90:19-55
+                int choice = (int)ceil(u * (double)m);
+                choice = max(1, min(m, choice));
+                const int src = __ldcg(order + K + choice - 1);
+                const int plab = clustered ? min(__ldcg(rb.lab + src), MAX_CLUSTERS - 1) : 0;  // the seed's cluster
                 if (helper) {
                     long long th0 = clock64();
                     if (prep_uid != uid) { prep_chain(D, R, LD, rb.seed, uid, b); prep_white = false; }
-                    if (!prep_white) whiten_chain<(G * DPL + 7) / 8>(D, R, LD, s_chol, b);
+                    if (clustered) whiten_chain<(G * DPL + 7) / 8>(D, R, LD, rb.cchol + (size_t)plab * D * D, b);
+                    else if (!prep_white) whiten_chain<(G * DPL + 7) / 8>(D, R, LD, s_chol, b);
                     prep_uid = ~0ull;
                     if (lane == 0 && cta == c0 && pair == 0) st->cyc_prep += clock64() - th0;
                 }
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");  // hand-over of the buffer
                 if (!helper) {
-                    double u = uniform(rb.seed, TAG_SEED, uid, 0u, 0u);  // GenerateSeed, generate.F90:19-55
-                    int choice = (int)ceil(u * (double)m);
-                    choice = max(1, min(m, choice));
-                    const int src = __ldcg(order + K + choice - 1);
                     const int dslot = __ldcg(order + k);
                     double x[DPL];
 #pragma unroll
@@ -808,6 +820,10 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                                                       pool + (size_t)(nph_base + (long long)cl * (R - 1)) * T, last, nlike,
                                                       (cta == c0 && warp == 0) ? st->dbg : nullptr, false);
                     if (sharded) shard_publish(p, last, k, xpar);
+                    if (p.clustering) {  // the babies carry their seed's label until the next update
+                        for (int e = lane; e < R - 1; e += 32) rb.phl[vload(&st->cur_pool)][nph_base + (long long)cl * (R - 1) + e] = plab;
+                        if (lane == 0) rb.lab[dslot] = plab;
+                    }
                     if (ctimer) st->cyc_slice += clock64() - tc2;
                     if (!(lfin > Lstar)) ++nfail;
                 }
@@ -839,12 +855,18 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                     prep_white = false;
                 }
                 long long tc1 = clock64();
-                if (!prep_white) whiten_chain<(G * DPL + 7) / 8>(D, R, LD, s_chol, cs);
+                const int plab = clustered ? min(__ldcg(rb.lab + src), MAX_CLUSTERS - 1) : 0;  // the seed's cluster
+                if (clustered) whiten_chain<(G * DPL + 7) / 8>(D, R, LD, rb.cchol + (size_t)plab * D * D, cs);
+                else if (!prep_white) whiten_chain<(G * DPL + 7) / 8>(D, R, LD, s_chol, cs);
                 prep_uid = ~0ull;
                 long long tc2 = clock64();
                 double lfin = slice_chain<G, DPL, KIND>(p.cp, M, rb.seed, uid, x, Lstar, cs,
                                                   pool + (size_t)(nph_base + (long long)cl * (R - 1)) * T, last, nlike, nullptr, false);
                 if (sharded) shard_publish(p, last, k, xpar);
+                if (p.clustering) {
+                    for (int e = lane; e < R - 1; e += 32) rb.phl[vload(&st->cur_pool)][nph_base + (long long)cl * (R - 1) + e] = plab;
+                    if (lane == 0) rb.lab[dslot] = plab;
+                }
                 if (ctimer) {
                     long long tc3 = clock64();
                     st->cyc_prep += tc1 - tc0; st->cyc_white += tc2 - tc1; st->cyc_slice += tc3 - tc2;
@@ -901,8 +923,11 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
         } else if (will_chain) {
             prep_uid = (unsigned long long)(nchains_base + K + knext);
             prep_chain(D, R, LD, rb.seed, prep_uid, csn);
-            whiten_chain<(G * DPL + 7) / 8>(D, R, LD, s_chol, csn);
-            prep_white = true;
+            prep_white = false;
+            if (!p.clustering) {  // with clusters the factor depends on the chain's seed, which the next phase S decides
+                whiten_chain<(G * DPL + 7) / 8>(D, R, LD, s_chol, csn);
+                prep_white = true;
+            }
         }
     }
 }
