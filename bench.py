@@ -36,7 +36,8 @@ WORKLOADS = {
     # name: (nDims, nDerived, nlive, num_repeats, like, prior box)
     "gaussian20_nlive1000_R40": dict(nDims=20, nDerived=2, nlive=1000, num_repeats=40, like="gaussian", box=None),
     "gaussian20_nlive500_R40": dict(nDims=20, nDerived=2, nlive=500, num_repeats=40, like="gaussian", box=None),
-    "rastrigin10_nlive2000_R50": dict(nDims=10, nDerived=0, nlive=2000, num_repeats=50, like="rastrigin", box=5.12),
+    "rastrigin10_nlive2000_R50": dict(nDims=10, nDerived=0, nlive=2000, num_repeats=50, like="rastrigin", box=5.12,
+                                      clustering=True),
     "gaussian20_nlive8000_R40": dict(nDims=20, nDerived=2, nlive=8000, num_repeats=40, like="gaussian", box=None),
 }
 METRIC = "likelihood_evals_per_sec"
@@ -176,7 +177,7 @@ def run_reference(args):
 
     def one(seed):
         s = O.make_settings(w["nDims"], w["nDerived"], nlive=w["nlive"], num_repeats=w["num_repeats"], seed=seed,
-                            batch_K=0)
+                            batch_K=0, do_clustering=w.get("clustering", False))
         t0 = time.perf_counter()
         r, _ = O.run(s, like=w["like"], **kw)
         return r, time.perf_counter() - t0
@@ -242,6 +243,7 @@ def main():
 
     w = WORKLOADS[args.workload]
     D, P, n, R = w["nDims"], w["nDerived"], w["nlive"], w["num_repeats"]
+    clustering = bool(w.get("clustering", False))
     # N > 1 (weak scaling, BASELINE config 5's shape): ONE run with nlive*N live points sharded over the N GPUs --
     # every rank runs 1/N of each generation's chains, the new live points and the covariance statistics are
     # exchanged over NVLink inside the persistent kernel (polychordlite_b200/mgpu.py)
@@ -253,7 +255,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def settings(seed):
-        return capi.make_settings(D, P, nlive=n, num_repeats=R, seed=seed)
+        return capi.make_settings(D, P, nlive=n, num_repeats=R, seed=seed, do_clustering=clustering)
 
     if sharded:
         from polychordlite_b200 import mgpu
@@ -310,7 +312,7 @@ def main():
         # sharded run: every rank makes the call (like the ranks of an MPI run), rank 0 carries the dumper
         L.polychord_c_interface(C.cast(like_fn, C.c_void_p), C.cast(prior_fn, C.c_void_p),
                                 C.cast(dcb, C.c_void_p) if (rank == 0 or not sharded) else None,
-                                n, R, -1, -1, False, 0, 1e-3, -1e30, -1, 0.0,
+                                n, R, -1, -1, clustering, 0, 1e-3, -1e30, -1, 0.0,
                                 False, False, False, False, False, False, False, False, False, False, False,
                                 float(np.exp(-1)), True, D, P, b"chains", b"bench", 1, grade_frac, grade_dims, 0, None,
                                 None, seed, C.byref(comm))
@@ -345,7 +347,7 @@ def main():
         info = step_device(i + 1000 * rank * roff)
         info_dev = info
         wall += time.perf_counter() - t0
-        evals += info.nlike; dev_ms += info.device_ms; launches += info.kernel_launches
+        evals += info.nlike; dev_ms += info.device_ms + info.cluster_ms; launches += info.kernel_launches
         algo_bytes += info.algorithmic_bytes; logZs.append(info.logZ); ndead += info.ndead
     barrier()
     t_region = time.perf_counter() - t_region
@@ -400,7 +402,8 @@ def main():
             nruns = 3
             for sd in range(nruns):
                 t0 = time.perf_counter()
-                r, _ = O.run(O.make_settings(D, P, nlive=n, num_repeats=R, seed=sd, batch_K=0), like=w["like"], **kw)
+                r, _ = O.run(O.make_settings(D, P, nlive=n, num_repeats=R, seed=sd, batch_K=0, do_clustering=clustering),
+                             like=w["like"], **kw)
                 ct += time.perf_counter() - t0; ce += r.nlike
             cpu = {"value": ce / ct, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": f"{nruns} complete runs of the workload (seeds 0..{nruns - 1}), oracle reference schedule "
@@ -411,7 +414,7 @@ def main():
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload + (f"_x{world}_sharded" if sharded else ""), "nDims": D, "nDerived": P,
-                       "nlive": n, "num_repeats": R,
+                       "nlive": n, "num_repeats": R, "do_clustering": clustering,
                        "precision_criterion": 1e-3, "batch_K": int(info.batch_K), "ctas_per_run": int(info.ctas_per_run),
                        "warps_per_cta": int(info.warps_per_cta), "step": "one complete nested-sampling run",
                        "l2": "flushed (256 MiB memset) before every step",
@@ -421,7 +424,7 @@ def main():
                                      "covariance statistics exchanged over NVLink peer memory inside the persistent kernel")},
             "wall_time_to_logZ_s": dev_ms / args.steps * 1e-3, "wall_ms_per_step_host": 1e3 * wall_max / args.steps,
             "logZ_mean": float(np.mean(logZs)), "logZ_sem": float(np.std(logZs, ddof=1) / np.sqrt(len(logZs))) if len(logZs) > 1 else None,
-            "ndead_per_step": ndead / args.steps, "evals_per_step": (evals_all if sharded else evals) / args.steps,
+            "ncluster_max": int(info_dev.ncluster_max), "ndead_per_step": ndead / args.steps, "evals_per_step": (evals_all if sharded else evals) / args.steps,
             "e2e": {"value": e_evals_all / e_t_max, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
                     "d2h_bytes_per_step": d2h / args.steps, "api": "polychord_c_interface + dumper (host arrays)",
                     "ms_per_step": 1e3 * e_t_max / args.steps, "dumper_calls": sink["calls"]},

@@ -160,6 +160,7 @@ typedef struct pc_run_info {
     double phase_ms[8];
     long long ncluster_max;     /* do_clustering: largest number of clusters an update found, and the number of */
     long long ncluster_updates; /* updates that ran the clustering pass */
+    double cluster_ms;          /* wall time of the clustering passes (their kernels are not part of device_ms) */
 } pc_run_info;
 
 /* Results of the most recent polychord_c_interface()/pc_run() in this process. */

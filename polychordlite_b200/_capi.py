@@ -49,7 +49,7 @@ class RunInfo(C.Structure):
         ("warps_per_cta", C.c_int), ("ctas_per_run", C.c_int), ("kernel_launches", C.c_int),
         ("device_ms", C.c_double), ("wall_ms", C.c_double), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong),
         ("algorithmic_bytes", C.c_longlong), ("phase_ms", C.c_double * 8),
-        ("ncluster_max", C.c_longlong), ("ncluster_updates", C.c_longlong),
+        ("ncluster_max", C.c_longlong), ("ncluster_updates", C.c_longlong), ("cluster_ms", C.c_double),
     ]
 
     def as_dict(self):

@@ -35,86 +35,136 @@ __device__ __forceinline__ void warp_argmin(double& d, int& j) {
     }
 }
 
+// The cube coordinates of the live points, staged in shared memory with an odd row stride (conflict-free when the
+// lanes of a warp read the same coordinate of 32 consecutive points).  Falls back to global memory when the table
+// does not fit (tab == nullptr).
+__device__ __forceinline__ const double* stage_live_table(const double* live, int T, int D, int n, double* tab, int TS) {
+    if (!tab) return nullptr;
+    for (int e = threadIdx.x; e < n * D; e += blockDim.x) {
+        const int j = e / D, k = e - j * D;
+        tab[(size_t)j * TS + k] = live[(size_t)j * T + k];
+    }
+    __syncthreads();
+    return tab;
+}
+__host__ __device__ inline size_t live_table_bytes(int n, int D) { return (size_t)n * (D | 1) * 8; }
+
 // compute_knn restricted to a partition: for live slot i the KNN_K nearest slots j with part[j] == part[i]
 // (itself included), ordered by (distance, slot) -- the order compute_knn's insertion rule produces.
-// knn[i*KNN_K + t] = slot or -1.  One warp per point, one scan of the live points per neighbour.
-__global__ void pc_knn_kernel(const double* live, int T, int D, int n, const int* part, int* knn) {
+// knn[i*KNN_K + t] = slot or -1.  One warp per point: every lane keeps the KNN_K best of its share of the live
+// points in a sorted register list (one scan), then the 32 lists are merged head by head.
+// Dynamic shared memory: W x D doubles (the warps' own points), then the live table when use_tab.
+__global__ void pc_knn_kernel(const double* live, int T, int D, int n, const int* part, int* knn, int use_tab) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-    const int i = blockIdx.x * W + warp;
+    const int TS = D | 1;
     double* xi = (double*)smem + (size_t)warp * D;
-    if (i < n)
+    const double* tab = stage_live_table(live, T, D, n, use_tab ? (double*)smem + (size_t)W * D : nullptr, TS);
+    const double* base = tab ? tab : live;
+    const int stride = tab ? TS : T;
+    for (int i = blockIdx.x * W + warp; i < n; i += gridDim.x * W) {
+        __syncwarp();
         for (int k = lane; k < D; k += 32) xi[k] = live[(size_t)i * T + k];
-    __syncwarp();
-    if (i >= n) return;
-    const int pi = part[i];
-    double pd = -1.0;
-    int pj = -1;
-    for (int t = 0; t < KNN_K; ++t) {
-        double bd = INFINITY;
-        int bj = 0x7fffffff;
+        __syncwarp();
+        const int pi = part[i];
+        double bd[KNN_K];
+        int bj[KNN_K];
+#pragma unroll
+        for (int t = 0; t < KNN_K; ++t) { bd[t] = INFINITY; bj[t] = 0x7fffffff; }
         for (int j = lane; j < n; j += 32) {
             if (part[j] != pi) continue;
-            const double d = cube_dist2(xi, live + (size_t)j * T, D);
-            const bool after = d > pd || (d == pd && j > pj);           // not yet listed
-            if (after && (d < bd || (d == bd && j < bj))) { bd = d; bj = j; }
+            double cd = cube_dist2(xi, base + (size_t)j * stride, D);
+            int cj = j;
+            if (cd < bd[KNN_K - 1] || (cd == bd[KNN_K - 1] && cj < bj[KNN_K - 1])) {
+#pragma unroll
+                for (int t = 0; t < KNN_K; ++t) {   // insertion: the displaced entry is carried down the list
+                    const bool lt = cd < bd[t] || (cd == bd[t] && cj < bj[t]);
+                    const double td = bd[t];
+                    const int tj = bj[t];
+                    bd[t] = lt ? cd : td; bj[t] = lt ? cj : tj;
+                    cd = lt ? td : cd;   cj = lt ? tj : cj;
+                }
+            }
         }
-        warp_argmin(bd, bj);
-        if (lane == 0) knn[(size_t)i * KNN_K + t] = (bj == 0x7fffffff) ? -1 : bj;
-        if (bj == 0x7fffffff) {
-            if (lane == 0) for (int u = t + 1; u < KNN_K; ++u) knn[(size_t)i * KNN_K + u] = -1;
-            break;
+        for (int t = 0; t < KNN_K; ++t) {
+            double hd = bd[0];
+            int hj = bj[0];
+            const int mine = hj;
+            warp_argmin(hd, hj);
+            if (lane == 0) knn[(size_t)i * KNN_K + t] = (hj == 0x7fffffff) ? -1 : hj;
+            if (mine == hj && hj != 0x7fffffff) {   // slots are unique: exactly one lane holds the winner
+#pragma unroll
+                for (int u = 0; u + 1 < KNN_K; ++u) { bd[u] = bd[u + 1]; bj[u] = bj[u + 1]; }
+                bd[KNN_K - 1] = INFINITY; bj[KNN_K - 1] = 0x7fffffff;
+            }
         }
-        pd = bd; pj = bj;
     }
 }
 
 // identify_cluster (run_time_info.f90:913-949) for the phantoms: label of the nearest live point, ties to the
-// lowest slot.  One warp per phantom record.
+// lowest slot.  One warp per phantom record, four live points per lane in flight (independent accumulation chains;
+// each distance still adds its dimensions in order).  Dynamic shared memory as for pc_knn_kernel.
 __global__ void pc_identify_kernel(const double* live, int T, int D, int n, const int* lab, const double* ph,
-                                   long long nph, int* phl) {
+                                   long long nph, int* phl, int use_tab) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int TS = D | 1;
     double* x = (double*)smem + (size_t)warp * D;
+    const double* tab = stage_live_table(live, T, D, n, use_tab ? (double*)smem + (size_t)W * D : nullptr, TS);
+    const double* base = tab ? tab : live;
+    const int stride = tab ? TS : T;
     for (long long r = (long long)blockIdx.x * W + warp; r < nph; r += (long long)gridDim.x * W) {
         __syncwarp();
         for (int k = lane; k < D; k += 32) x[k] = ph[(size_t)r * T + k];
         __syncwarp();
         double bd = INFINITY;
         int bj = 0x7fffffff;
-        for (int j = lane; j < n; j += 32) {
-            const double d = cube_dist2(x, live + (size_t)j * T, D);
-            if (d < bd) { bd = d; bj = j; }   // j ascends within a lane: the first minimum is the lowest slot
+        for (int j0 = lane; j0 < n; j0 += 128) {
+            const double* q0 = base + (size_t)j0 * stride;
+            const double* q1 = base + (size_t)min(j0 + 32, n - 1) * stride;
+            const double* q2 = base + (size_t)min(j0 + 64, n - 1) * stride;
+            const double* q3 = base + (size_t)min(j0 + 96, n - 1) * stride;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            for (int k = 0; k < D; ++k) {
+                const double xk = x[k];
+                const double d0 = xk - q0[k], d1 = xk - q1[k], d2 = xk - q2[k], d3 = xk - q3[k];
+                s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
+            }
+            // j ascends within a lane: the first minimum is the lowest slot
+            if (s0 < bd) { bd = s0; bj = j0; }
+            if (j0 + 32 < n && s1 < bd) { bd = s1; bj = j0 + 32; }
+            if (j0 + 64 < n && s2 < bd) { bd = s2; bj = j0 + 64; }
+            if (j0 + 96 < n && s3 < bd) { bd = s3; bj = j0 + 96; }
         }
         warp_argmin(bd, bj);
         if (lane == 0) phl[r] = lab[bj];
     }
 }
 
-// calculate_covmats + calc_cholesky for ONE cluster per CTA: first and second moments of the cube coordinates of the
-// live points and phantoms labelled blockIdx.x about the pivot (the global mean), formed on the FP64 tensor cores
-// exactly as in phase U (pc_run_kernel.cuh), warps combined in warp order, then cov = S2/N - d d^T and its factor.
-// Clusters with N <= D points keep the global factor (no covariance can be formed from them).
-__global__ void __launch_bounds__(256) pc_cluster_cov_kernel(const double* live, const int* lab, int n, const double* ph,
-                                                             const int* phl, long long nph, int T, int D,
-                                                             const double* pivot, const double* chol_glob, double* cchol,
-                                                             int* ccount) {
+// calculate_covmats (run_time_info.f90:601-641) per cluster, first half: CTA (p, c) forms the moment matrix
+// M = sum z z^T, z = [x - pivot, 1], of the records of chunk c (live slots, then the phantom pool) labelled p, on
+// the FP64 tensor cores exactly as phase U does (pc_run_kernel.cuh), warps combined in warp order, and writes it
+// to cpart[(p * gridDim.y + c) * Dp8^2].
+__global__ void __launch_bounds__(256) pc_cluster_moments_kernel(const double* live, const int* lab, int n, const double* ph,
+                                                                 const int* phl, long long nph, int T, int D,
+                                                                 const double* pivot, double* cpart) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
-    const int p = blockIdx.x;
+    const int p = blockIdx.x, c = blockIdx.y;
     const int Dp8 = (D + 1 + 7) & ~7, SX = Dp8 + 4, nt = Dp8 >> 3, ntl = nt * (nt + 1) / 2;
     const int Dpad = (D + 1) & ~1;
     double* s_piv = (double*)smem;                                  // Dpad
     double* s_M = s_piv + Dpad;                                     // Dp8 x Dp8, accumulated over the passes
     double* s_x = s_M + (size_t)Dp8 * Dp8 + (size_t)warp * U_BATCH * SX;  // per warp: U_BATCH x SX staged rows
-    double* s_cov = s_M + (size_t)Dp8 * Dp8 + (size_t)W * U_BATCH * SX;   // D x D (+ D): the matrix, then its factor behind it
-    double* s_L = s_cov + (size_t)D * D + Dpad;
     for (int e = tid; e < D; e += blockDim.x) s_piv[e] = pivot[e];
     for (int e = tid; e < Dp8 * Dp8; e += blockDim.x) s_M[e] = 0.0;
     __syncthreads();
     const int fr = lane >> 2, fk = lane & 3;
     const int JD = (D + 31) >> 5;
     const long long total = (long long)n + nph;                     // records: live slots, then the phantom pool
+    long long chunk = (total + gridDim.y - 1) / gridDim.y;
+    chunk = (chunk + W * 32 - 1) / (W * 32) * (W * 32);
+    const long long r_begin = (long long)c * chunk, r_end = min(total, r_begin + chunk);
     const int passes = (ntl + COV_TPP - 1) / COV_TPP;
     for (int pass = 0; pass < passes; ++pass) {
         double c0[COV_TPP], c1[COV_TPP];
@@ -130,10 +180,10 @@ __global__ void __launch_bounds__(256) pc_cluster_cov_kernel(const double* live,
         }
         for (int e = lane; e < U_BATCH * SX; e += 32) s_x[e] = 0.0;
         __syncwarp();
-        for (long long base = (long long)warp * 32; base < total; base += (long long)W * 32) {
+        for (long long base = r_begin + (long long)warp * 32; base < r_end; base += (long long)W * 32) {
             const long long r = base + lane;
             bool mine = false;
-            if (r < total) mine = (r < n ? lab[r] : phl[r - n]) == p;
+            if (r < r_end) mine = (r < n ? lab[r] : phl[r - n]) == p;
             unsigned rem = __ballot_sync(FULL, mine);
             while (rem) {
                 const double* rp[U_BATCH];
@@ -185,7 +235,27 @@ __global__ void __launch_bounds__(256) pc_cluster_cov_kernel(const double* live,
             __syncthreads();
         }
     }
-    // M = sum z z^T of z = [x - pivot, 1]: S2 in the leading D x D block (upper triangle), S1 in column D, N at (D, D)
+    double* out = cpart + ((size_t)p * gridDim.y + c) * Dp8 * Dp8;
+    for (int e = tid; e < Dp8 * Dp8; e += blockDim.x) out[e] = s_M[e];
+}
+
+// second half: one CTA per cluster adds the chunks' matrices in chunk order, cov = S2/N - d d^T (S2 in the leading
+// D x D block, S1 in column D, N at (D, D)), calc_cholesky (utils.F90:621-649).  Clusters with N <= D points keep the
+// global factor (no covariance can be formed from them).
+__global__ void pc_cluster_factor_kernel(const double* cpart, int nchunks, int D, const double* chol_glob, double* cchol,
+                                         int* ccount) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, p = blockIdx.x;
+    const int Dp8 = (D + 1 + 7) & ~7;
+    double* s_M = (double*)smem;
+    double* s_cov = s_M + (size_t)Dp8 * Dp8;
+    double* s_L = s_cov + (size_t)D * D;
+    for (int e = tid; e < Dp8 * Dp8; e += blockDim.x) {
+        double s = 0.0;
+        for (int c = 0; c < nchunks; ++c) s += cpart[((size_t)p * nchunks + c) * Dp8 * Dp8 + e];
+        s_M[e] = s;
+    }
+    __syncthreads();
     const double N = s_M[D * Dp8 + D];
     if (tid == 0) ccount[p] = (int)N;
     if (!(N > (double)D)) {
@@ -198,14 +268,19 @@ __global__ void __launch_bounds__(256) pc_cluster_cov_kernel(const double* live,
         s_cov[idx] = s_M[lo * Dp8 + hi] / N - (s_M[a * Dp8 + D] / N) * (s_M[b * Dp8 + D] / N);
     }
     __syncthreads();
-    if (tid < 32) warp_cholesky(s_cov, s_L, D);   // utils.F90:621-649, with the sqrt(trace) * I fallback
+    if (tid < 32) warp_cholesky(s_cov, s_L, D);
     __syncthreads();
     for (int e = tid; e < D * D; e += blockDim.x) cchol[(size_t)p * D * D + e] = s_L[e];
 }
 
-__host__ __device__ inline size_t cluster_cov_smem(int D, int W) {
+constexpr int CLUSTER_CHUNKS = 16;
+__host__ __device__ inline size_t cluster_moments_smem(int D, int W) {
     const int Dp8 = (D + 1 + 7) & ~7, SX = Dp8 + 4, Dpad = (D + 1) & ~1;
-    return (size_t)(Dpad + Dp8 * Dp8 + W * U_BATCH * SX + D * D + Dpad + D * D) * 8;
+    return (size_t)(Dpad + Dp8 * Dp8 + W * U_BATCH * SX) * 8;
+}
+__host__ __device__ inline size_t cluster_factor_smem(int D) {
+    const int Dp8 = (D + 1 + 7) & ~7;
+    return (size_t)(Dp8 * Dp8 + 2 * D * D) * 8;
 }
 
 }  // namespace pc

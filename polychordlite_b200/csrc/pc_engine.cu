@@ -706,8 +706,10 @@ struct Engine {
 
     // ---- clustering at the update cadence (pc_cluster.cuh) -------------------------------------------------
     long long ncluster_updates = 0, ncluster_max = 0;
+    double cluster_ms = 0, cluster_label_ms = 0;   // wall time of the clustering passes / of their labelling part
     std::vector<int> h_lab, h_knn;
     DevArr<int> d_part, d_knn, d_ccount;
+    DevArr<double> d_cpart;
 
     // NN_clustering (clustering.f90:15-97) over all live points, from scratch.  The recursion into the clusters found
     // becomes a work list: every round the device computes the 10 nearest neighbours of every point WITHIN its
@@ -725,15 +727,19 @@ struct Engine {
         int nparts = 1;
         if (!d_part.p) { d_part.alloc(n); d_knn.alloc((size_t)n * KNN_K); }
         h_knn.resize((size_t)n * KNN_K);
-        std::vector<int> uf(n), loc(n), canon(n), old(n), members;
+        std::vector<int> uf(n), loc(n), canon(n), old(n), head(n), twin_next(n), firstseen(n), members;
+        members.reserve(n);
         auto find = [&](int a) { while (uf[a] != a) { uf[a] = uf[uf[a]]; a = uf[a]; } return a; };
         for (int round = 0; round < 64; ++round) {
             bool any = false;
             for (int c = 0; c < nparts; ++c) any = any || !final_part[c];
             if (!any) break;
             d_part.upload(part.data(), n, stream);
-            const int W = 8;
-            pc_knn_kernel<<<(n + W - 1) / W, W * 32, (size_t)W * D * 8, stream>>>(d_live, T, D, n, d_part.p, d_knn.p);
+            const int W = 16;
+            const bool tab = live_table_bytes(n, D) + (size_t)W * D * 8 <= 200 * 1024;   // the live table fits in shared memory
+            const size_t ksm = (size_t)W * D * 8 + (tab ? live_table_bytes(n, D) : 0);
+            PC_CUDA(cudaFuncSetAttribute(pc_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksm));
+            pc_knn_kernel<<<std::min((n + W - 1) / W, 148), W * 32, ksm, stream>>>(d_live, T, D, n, d_part.p, d_knn.p, tab ? 1 : 0);
             PC_CUDA(cudaGetLastError());
             d_knn.download(h_knn.data(), (size_t)n * KNN_K, stream);
             PC_CUDA(cudaStreamSynchronize(stream));
@@ -748,9 +754,22 @@ struct Engine {
                 if (m <= 2) { final_part[c] = 1; continue; }   // do_clustering: nlive > 2 (clustering.f90:289); two points are each other's neighbours
                 const int kk = std::min(m, KNN_K);
                 for (int a = 0; a < m; ++a) { loc[members[a]] = a; uf[a] = a; old[a] = a; }
-                // points grouped by the head of their own list (a point's nearest neighbour is itself unless it has a twin)
-                std::vector<std::vector<int>> byhead(m);
-                for (int a = 0; a < m; ++a) byhead[loc[h_knn[(size_t)members[a] * KNN_K]]].push_back(a);
+                // neighbours(): a ~ b when the HEAD of b's list appears in a's.  A point's nearest neighbour is itself
+                // unless it has an exact twin with a lower slot, so heads are almost always the points themselves;
+                // twins are chained behind their head (twin_next) and visited through it.
+                bool twins = false;
+                for (int a = 0; a < m; ++a) {
+                    head[a] = loc[h_knn[(size_t)members[a] * KNN_K]];
+                    twin_next[a] = -1;
+                    if (head[a] != a) twins = true;
+                }
+                if (twins)
+                    for (int a = m - 1; a >= 0; --a)
+                        if (head[a] != a) { twin_next[a] = twin_next[head[a]]; twin_next[head[a]] = a; }
+                auto join = [&](int a, int b) {
+                    const int ra = find(a), rb = find(b);
+                    if (ra != rb) uf[std::max(ra, rb)] = std::min(ra, rb);
+                };
                 int num = m;
                 bool split = false;
                 for (int nn = 2; nn <= kk; ++nn) {
@@ -759,18 +778,17 @@ struct Engine {
                         for (int a = 0; a < m; ++a) {
                             const int v = h_knn[(size_t)members[a] * KNN_K + t];
                             if (v < 0) continue;
-                            for (int b : byhead[loc[v]]) {   // neighbours(): the head of b's list appears in a's
-                                const int ra = find(a), rb = find(b);
-                                if (ra != rb) uf[std::max(ra, rb)] = std::min(ra, rb);
-                            }
+                            const int lv = loc[v];
+                            if (head[lv] == lv) join(a, lv);
+                            if (twins) for (int b = twin_next[lv]; b >= 0; b = twin_next[b]) join(a, b);
                         }
                     // canonical labels of the components, in order of first appearance
                     num = 0;
-                    std::vector<int> first(m, -1);
+                    for (int a = 0; a < m; ++a) firstseen[a] = -1;
                     for (int a = 0; a < m; ++a) {
                         const int r0 = find(a);
-                        if (first[r0] < 0) first[r0] = num++;
-                        canon[a] = first[r0];
+                        if (firstseen[r0] < 0) firstseen[r0] = num++;
+                        canon[a] = firstseen[r0];
                     }
                     if (num == 1) break;
                     bool same = true;
@@ -802,7 +820,9 @@ struct Engine {
         const KParams& k = L.kp;
         const int n = k.n, D = k.cp.D, T = k.cp.T;
         HostRun& h = runs[0];
+        const auto tc0 = std::chrono::steady_clock::now();
         int num = cluster_labels(h_lab);
+        cluster_label_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count();
         if (num > MAX_CLUSTERS) {   // further labels share the last one, which keeps the global factor
             for (int& v : h_lab) v = std::min(v, MAX_CLUSTERS - 1);
         }
@@ -818,15 +838,24 @@ struct Engine {
             int* phl = cur == 0 ? h.phl0.p : h.phl1.p;
             const int W = 8;
             if (nph > 0) {
-                const int blocks = (int)std::min<long long>((nph + W - 1) / W, 148LL * 16);
-                pc_identify_kernel<<<blocks, W * 32, (size_t)W * D * 8, stream>>>(h.live.p, T, D, n, h.lab.p, ph, nph, phl);
+                const int WI = 16;
+                const bool tab = live_table_bytes(n, D) + (size_t)WI * D * 8 <= 200 * 1024;
+                const size_t ism = (size_t)WI * D * 8 + (tab ? live_table_bytes(n, D) : 0);
+                const int blocks = (int)std::min<long long>((nph + WI - 1) / WI, tab ? 148LL : 148LL * 8);
+                PC_CUDA(cudaFuncSetAttribute(pc_identify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism));
+                pc_identify_kernel<<<blocks, WI * 32, ism, stream>>>(h.live.p, T, D, n, h.lab.p, ph, nph, phl, tab ? 1 : 0);
                 PC_CUDA(cudaGetLastError());
             }
             if (!d_ccount.p) d_ccount.alloc(MAX_CLUSTERS);
-            const size_t smem = cluster_cov_smem(D, W);
-            PC_CUDA(cudaFuncSetAttribute(pc_cluster_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            pc_cluster_cov_kernel<<<ncl, W * 32, smem, stream>>>(h.live.p, h.lab.p, n, ph, phl, nph, T, D, h.gsum.p + 2, h.chol.p,
-                                                                h.cchol.p, d_ccount.p);
+            const int Dp8 = (D + 1 + 7) & ~7;
+            if (d_cpart.n < (size_t)ncl * CLUSTER_CHUNKS * Dp8 * Dp8) d_cpart.alloc((size_t)MAX_CLUSTERS * CLUSTER_CHUNKS * Dp8 * Dp8);
+            const size_t msm = cluster_moments_smem(D, W), fsm = cluster_factor_smem(D);
+            PC_CUDA(cudaFuncSetAttribute(pc_cluster_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+            PC_CUDA(cudaFuncSetAttribute(pc_cluster_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+            pc_cluster_moments_kernel<<<dim3(ncl, CLUSTER_CHUNKS), W * 32, msm, stream>>>(h.live.p, h.lab.p, n, ph, phl, nph, T, D,
+                                                                                        h.gsum.p + 2, d_cpart.p);
+            PC_CUDA(cudaGetLastError());
+            pc_cluster_factor_kernel<<<ncl, 128, fsm, stream>>>(d_cpart.p, CLUSTER_CHUNKS, D, h.chol.p, h.cchol.p, d_ccount.p);
             PC_CUDA(cudaGetLastError());
             if (num > MAX_CLUSTERS)  // the shared last label keeps the global factor
                 PC_CUDA(cudaMemcpyAsync(h.cchol.p + (size_t)(MAX_CLUSTERS - 1) * D * D, h.chol.p, (size_t)D * D * 8, cudaMemcpyDeviceToDevice, stream));
@@ -834,6 +863,7 @@ struct Engine {
         }
         PC_CUDA(cudaMemcpyAsync(&h.st.p->ncl, &ncl, sizeof(int), cudaMemcpyHostToDevice, stream));
         PC_CUDA(cudaStreamSynchronize(stream));
+        cluster_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count();
     }
 
     void grow(int r, int status) {
@@ -966,7 +996,10 @@ struct Engine {
             o.logZ_raw = s.logZ; o.logZ2_raw = s.logZ2;
             o.ndead = s.ndead; o.nlike = s.nlike; o.nchains = s.nchains; o.ngenerations = s.ngen;
             o.nupdates = s.nupdates; o.nfailures = s.nfail; o.nslices = s.nslices; o.nphantoms_final = s.nphantom;
-            o.ncluster_max = ncluster_max; o.ncluster_updates = ncluster_updates;
+            o.ncluster_max = ncluster_max; o.ncluster_updates = ncluster_updates; o.cluster_ms = cluster_ms;
+            if (std::getenv("PC_DEBUG") && ncluster_updates)
+                std::fprintf(stderr, "[pc dbg cluster] %lld passes, %.3f ms in all, %.3f ms of it labelling (kNN kernel + union-find), up to %lld clusters\n",
+                             ncluster_updates, cluster_ms, cluster_label_ms, ncluster_max);
             o.batch_K = k.batch_K; o.warps_per_cta = L.W; o.ctas_per_run = G; o.kernel_launches = launches;
             o.device_ms = device_ms;
             o.wall_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
