@@ -582,9 +582,20 @@ __device__ inline void shard_scatter(const KParams& p, const RunBuf& rb, DevRun*
     const int K = st->K;
     const int* ord = rb.order + st->order_off;
     const double* in = p.sh.xin[p.sh.rank] + (size_t)(st->ngen & 1) * p.batch_K * T;
-    for (int e = tid; e < K * T; e += blockDim.x) {
-        const int k = e / T, c = e - k * T;
-        rb.live[(size_t)__ldcg(ord + k) * T + c] = __ldcg(in + e);
+    // four records per warp in flight (the copy is latency-bound: K x T doubles through one CTA)
+    const int lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
+    for (int k0 = warp * 4; k0 < K; k0 += W * 4) {
+        int slot[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) slot[j] = __ldcg(ord + min(k0 + j, K - 1));
+        for (int e = lane; e < T; e += 32) {
+            double v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = __ldcg(in + (size_t)min(k0 + j, K - 1) * T + e);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (k0 + j < K) rb.live[(size_t)slot[j] * T + e] = v[j];
+        }
     }
     __syncthreads();
 }
@@ -744,13 +755,13 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
         }
         const bool sharded = p.sh.world > 1;
         const int xw = sharded ? p.sh.world : 1, xr = sharded ? p.sh.rank : 0;
-        if (sharded && cta == 0) {  // the dying points move to the (replicated) dead list (run_time_info.f90:789-817)
+        if (sharded) {  // the dying points move to the (replicated) dead list (run_time_info.f90:789-817): one record per warp
             const int K_ = vload(&st->K);
             const long long nb = vload(&st->ndead_base);
             const int* ord = rb.order + vload(&st->order_off);
-            for (int e = tid; e < K_ * T; e += blockDim.x) {
-                const int k = e / T, c = e - k * T;
-                rb.dead[(size_t)(nb + k) * T + c] = __ldcg(rb.live + (size_t)__ldcg(ord + k) * T + c);
+            for (int k = gw; k < K_; k += GW) {
+                const int slot = __ldcg(ord + k);
+                for (int e = lane; e < T; e += 32) rb.dead[(size_t)(nb + k) * T + e] = __ldcg(rb.live + (size_t)slot * T + e);
             }
         }
 
