@@ -432,6 +432,44 @@ __device__ inline double slice_chain(const ChainParams& p, const Model<G, DPL, K
 #pragma unroll
     for (int k = 0; k < DPL; ++k) { wdt[k] = M.wid[k]; shf[k] = M.lo[k] - M.mu[k]; }
 
+    // Correlated Gaussian (utils.F90:1028-1048): along a chord the quadratic form is a quadratic in t,
+    //   (t nW + xs)^T A (t nW + xs) = c0 + 2 t c1 + t^2 c2,  c2 = nW.v, c1 = xs.v, c0 = xs.u  with v = A nW, u = A xs,
+    // so a slice step costs ONE matrix-vector product (v; u follows the accepted point: u += t v) and every trial
+    // point three fused multiply-adds.  The product is spread over the 32 lanes (rows lane, lane+32, ...) through
+    // the warp's scratch vectors.
+    double uA[DPL], vA[DPL];
+    double cq0 = 0.0, cq1 = 0.0, cq2 = 0.0;
+    double* sv0 = M.dvec - (size_t)grp * M.Dpad;   // the warp's scratch: input vector, then (behind it) the product
+    double* sv1 = sv0 + M.Dpad;
+    auto matvec = [&](const double (&in)[DPL], double (&out)[DPL]) {
+        __syncwarp();
+        if (grp == 0) {
+#pragma unroll
+            for (int k = 0; k < DPL; ++k)
+                if (M.valid(k)) sv0[M.dim(k)] = in[k];
+        }
+        __syncwarp();
+        for (int r = lane; r < D; r += 32) {
+            double a0 = 0.0, a1 = 0.0;
+            int cc = 0;
+            for (; cc + 1 < D; cc += 2) {
+                a0 = fma(M.invcov[r + (size_t)cc * D], sv0[cc], a0);
+                a1 = fma(M.invcov[r + (size_t)(cc + 1) * D], sv0[cc + 1], a1);
+            }
+            if (cc < D) a0 = fma(M.invcov[r + (size_t)cc * D], sv0[cc], a0);
+            sv1[r] = a0 + a1;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < DPL; ++k) out[k] = M.valid(k) ? sv1[M.dim(k)] : 0.0;
+    };
+    if constexpr (KIND == LIKE_CORR) {
+        double xs0[DPL];
+#pragma unroll
+        for (int k = 0; k < DPL; ++k) xs0[k] = fma(x[k], wdt[k], shf[k]);
+        matvec(xs0, uA);
+    }
+
     for (int i = 0; i < R; ++i) {
         const int c = cs.deck[i];
         const double* q = cs.nh + (size_t)c * LD;
@@ -454,6 +492,14 @@ __device__ inline double slice_chain(const ChainParams& p, const Model<G, DPL, K
                 nW[k] = nh[k] * wdt[k];
                 xs[k] = fma(x[k], wdt[k], shf[k]);
             }
+        }
+
+        if constexpr (KIND == LIKE_CORR) {
+            matvec(nW, vA);
+            double p2 = 0.0, p1 = 0.0, p0 = 0.0;
+#pragma unroll
+            for (int k = 0; k < DPL; ++k) { p2 = fma(nW[k], vA[k], p2); p1 = fma(xs[k], vA[k], p1); p0 = fma(xs[k], uA[k], p0); }
+            cq2 = M.group_sum(p2); cq1 = M.group_sum(p1); cq0 = M.group_sum(p0);
         }
 
         double y[DPL];
@@ -485,27 +531,8 @@ __device__ inline double slice_chain(const ChainParams& p, const Model<G, DPL, K
                     acc += M.valid(k) ? M.log_rast + th * th - 10.0 * cos(TwoPi * th) : 0.0;
                 }
                 logL = -M.group_sum(acc);
-            } else {  // utils.F90:1028-1048 log_gauss with a dense inverse covariance
-                double d[DPL], yk[DPL];
-                __syncwarp();
-#pragma unroll
-                for (int k = 0; k < DPL; ++k) {
-                    d[k] = fma(tt, nW[k], xs[k]);
-                    yk[k] = 0.0;
-                    if (M.valid(k)) M.dvec[M.dim(k)] = d[k];
-                }
-                __syncwarp();
-                for (int cc = 0; cc < D; ++cc) {
-                    const double dc = M.dvec[cc];
-                    const double* col = M.invcov + (size_t)cc * D;
-#pragma unroll
-                    for (int k = 0; k < DPL; ++k)
-                        if (M.valid(k)) yk[k] = fma(col[M.dim(k)], dc, yk[k]);
-                }
-                double acc = 0.0;
-#pragma unroll
-                for (int k = 0; k < DPL; ++k) acc += M.valid(k) ? d[k] * yk[k] : 0.0;
-                logL = M.corr_const - M.group_sum(acc) / 2.0;
+            } else {  // utils.F90:1028-1048 log_gauss with a dense inverse covariance: the chord quadratic
+                logL = fma(fma(tt, fma(tt, cq2, 2.0 * cq1), cq0), -0.5, M.corr_const);
             }
             return ((bal & gmask) == gmask) ? logL : logzero;  // outside the cube the likelihood is not called
         };
@@ -633,6 +660,10 @@ __device__ inline double slice_chain(const ChainParams& p, const Model<G, DPL, K
         }
 #pragma unroll
         for (int k = 0; k < DPL; ++k) x[k] = fma(t_acc, nh[k], x[k]);  // next start = this baby even if it failed (:88)
+        if constexpr (KIND == LIKE_CORR) {
+#pragma unroll
+            for (int k = 0; k < DPL; ++k) uA[k] = fma(t_acc, vA[k], uA[k]);
+        }
         logL_cur = lnew;
     }
     __syncwarp();
