@@ -344,7 +344,7 @@ static void set_smem(const ShapeFns& fn, size_t smem) {
 // ------------------------------------------------------------------------------------------
 struct HostRun {
     DevArr<DevRun> st;
-    DevArr<double> live, live_snap, dead, logw, ph0, ph1, chol, cov, partial, nh, gsum;
+    DevArr<double> live, live_snap, dead, logw, ph0, ph1, chol, cov, partial, nh, gsum, okey;
     DevArr<int> order, lab, phl0, phl1;
     DevArr<double> cchol;
     DevArr<long long> pcount;
@@ -557,6 +557,7 @@ struct Engine {
             h.st.alloc(1); h.st.zero(stream);
             h.live.alloc((size_t)n * T); h.live.zero(stream);
             h.order.alloc(2 * (size_t)n);
+            h.okey.alloc(2 * (size_t)n);
             h.dead.alloc((size_t)cap_dead * T);
             h.logw.alloc(cap_dead);
             h.ph0.alloc((size_t)cap_ph * T);
@@ -574,7 +575,7 @@ struct Engine {
             }
             RunBuf& b = h.buf;
             std::memset(&b, 0, sizeof(b));
-            b.st = h.st.p; b.live = h.live.p; b.live_snap = nullptr; b.ctl = nullptr; b.order = h.order.p; b.dead = h.dead.p; b.logw = h.logw.p;
+            b.st = h.st.p; b.live = h.live.p; b.live_snap = nullptr; b.ctl = nullptr; b.order = h.order.p; b.okey = h.okey.p; b.dead = h.dead.p; b.logw = h.logw.p;
             b.ph[0] = h.ph0.p; b.ph[1] = h.ph1.p; b.chol = h.chol.p; b.cov = h.cov.p; b.partial = h.partial.p;
             b.pcount = h.pcount.p; b.nh = h.nh.p; b.cap_dead = cap_dead; b.cap_ph = cap_ph; b.gsum = h.gsum.p;
             b.lab = h.lab.p; b.phl[0] = h.phl0.p; b.phl[1] = h.phl1.p; b.cchol = h.cchol.p;

@@ -89,6 +89,7 @@ struct RunBuf {
     double* live_snap; // n x T: copy of the live points at the last published dump
     HostCtl* ctl;      // mapped host memory, or null (no dumper)
     int* order;        // 2 x n: live slots sorted by (logL, slot), ping-pong (DevRun::order_off)
+    double* okey;      // 2 x n: the logL of those slots, same order and ping-pong
     double* dead;      // cap_dead x T
     double* logw;      // cap_dead
     double* ph[2];     // phantom pools (ping-pong), cap_ph x T each
@@ -145,6 +146,7 @@ struct KParams {
 // shared-memory layout of phase S (CTA 0)
 struct SmemS {
     double* sc;     // 64 doubles of reduction scratch
+    int* aval;      // n: slots of the survivors in order (merge path)
     double* akey;   // n: keys of the survivors in order (merge path) / np2: all keys (full sort)
     double* bkey;   // npB: keys of the new babies
     int* bval;      // npB (merge) / np2 (full sort: slot of every key)
@@ -154,18 +156,19 @@ __host__ __device__ inline int next_pow2(int v) { int p = 1; while (p < v) p <<=
 __host__ __device__ inline size_t smem_S_bytes(int n, int batch_K) {
     const int np2 = next_pow2(n), npB = next_pow2(batch_K);
     size_t full = (size_t)np2 * 12;
-    size_t merge = (size_t)n * 8 + (size_t)npB * 12;
+    size_t merge = (size_t)n * 8 + (size_t)npB * 12 + (size_t)((n + 1) & ~1) * 4;
     return 64 * 8 + (full > merge ? full : merge) + (size_t)((batch_K + 1) & ~1) * 8 + 16;
 }
 __device__ inline SmemS smem_S(unsigned char* base, int n, int batch_K) {
     SmemS m;
     const int np2 = next_pow2(n), npB = next_pow2(batch_K);
-    size_t full = (size_t)np2 * 12, merge = (size_t)n * 8 + (size_t)npB * 12;
+    size_t full = (size_t)np2 * 12, merge = (size_t)n * 8 + (size_t)npB * 12 + (size_t)((n + 1) & ~1) * 4;
     m.sc = (double*)base;
     m.akey = m.sc + 64;
     m.kkey = (double*)(base + 64 * 8 + (((full > merge ? full : merge) + 7) & ~(size_t)7));
     m.bkey = m.akey + n;           // merge layout
     m.bval = (int*)(m.bkey + npB);
+    m.aval = m.bval + npB;
     return m;
 }
 

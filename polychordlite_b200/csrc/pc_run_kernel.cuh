@@ -110,9 +110,14 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
     const bool merge = st->order_valid != 0 && Kp > 0 && Kp < n;
     const int* oldo = rb.order + st->order_off;
     int* newo = rb.order + (st->order_off ? 0 : n);
+    const double* oldk = rb.okey + st->order_off;
+    double* newk = rb.okey + (st->order_off ? 0 : n);
     const int m = n - Kp, npB = next_pow2(p.batch_K), np2 = next_pow2(n);
     if (merge) {
-        for (int i = tid; i < m; i += nthr) sm.akey[i] = __ldcg(rb.live + (size_t)__ldcg(oldo + Kp + i) * T + T - 1);
+        for (int i = tid; i < m; i += nthr) {  // the survivors: keys and slots as the previous phase S ordered them
+            sm.akey[i] = __ldcg(oldk + Kp + i);
+            sm.aval[i] = __ldcg(oldo + Kp + i);
+        }
         for (int j = tid; j < npB; j += nthr) {
             const int slot = j < Kp ? __ldcg(oldo + j) : 0x7fffffff;
             sm.bval[j] = slot;
@@ -160,7 +165,7 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
         // survivors before it ((key, slot) pairs are distinct, so the merged order is the sorted order)
         for (int i = tid; i < m; i += nthr) {
             const double ka = sm.akey[i];
-            const int va = __ldcg(oldo + Kp + i);
+            const int va = sm.aval[i];
             int lo = 0, hi = Kp;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
@@ -169,6 +174,7 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
             }
             const int rank = i + lo;
             newo[rank] = va;
+            newk[rank] = ka;
             if (rank < K) sm.kkey[rank] = ka;
         }
         for (int j = tid; j < Kp; j += nthr) {
@@ -179,11 +185,12 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
                 const int mid = (lo + hi) >> 1;
                 const double ka = sm.akey[mid];
                 bool less = ka < kb;
-                if (ka == kb) less = __ldcg(oldo + Kp + mid) < vb;
+                if (ka == kb) less = sm.aval[mid] < vb;
                 if (less) lo = mid + 1; else hi = mid;
             }
             const int rank = j + lo;
             newo[rank] = vb;
+            newk[rank] = kb;
             if (rank < K) sm.kkey[rank] = kb;
         }
         __syncthreads();
@@ -200,7 +207,7 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
             __syncthreads();
         }
         block_sort(skey, sval, np2);
-        for (int i = tid; i < n; i += nthr) newo[i] = sval[i];
+        for (int i = tid; i < n; i += nthr) { newo[i] = sval[i]; newk[i] = skey[i]; }
         if (!more) {  // final kill-off, nested_sampling.F90:381-384
             evidence_deaths(st, skey, n, n, rb.logw + ndead, sc);
             for (size_t e = tid; e < (size_t)n * T; e += nthr) {
