@@ -123,6 +123,11 @@ void pc_set_stream(void* cuda_stream);
  * of the host-callback path and polychord_c_interface reports status -3.  Language bindings whose callbacks cannot
  * unwind through C frames (ctypes, cgo, JNI) use it to turn a callback exception into a prompt return. */
 void pc_request_abort(void);
+/* Fast/slow parameter grades for the following pc_run()/probe calls (polychord_c_interface takes them from its own
+ * grade_dims / grade_frac arguments): grade g owns grade_dims[g] consecutive dimensions and contributes
+ * grade_repeats[g] slice steps per chain, drawn in the sub-space of the dimensions of grades >= g
+ * (chordal_sampling.f90:94-145).  The dims must sum to nDims, the repeats to num_repeats.  nGrade = 0 clears. */
+int pc_set_grades(int nGrade, const int* grade_dims, const int* grade_repeats);
 /* The engine keeps the device buffers of finished runs for the next run (cudaMalloc/cudaFree cost
  * milliseconds); this returns the cached blocks to the driver. */
 void pc_release_memory(void);

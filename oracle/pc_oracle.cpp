@@ -402,6 +402,8 @@ struct Cluster {
     std::vector<double> covmat, cholesky;  // column-major D x D
 };
 
+std::vector<int> g_grade_dims, g_grade_repeats;   // set by oracle_set_grades, read by every Run until cleared
+
 struct Run {
     oracle_settings S;
     Likelihood like;
@@ -409,6 +411,7 @@ struct Run {
     Rng rng;
     int D, P, T, R;
     int h0, p0, d0, b0, l0;
+    std::vector<int> grade_dims, grade_repeats;
 
     std::vector<double> sc_R, sc_L, sc_cube, sc_theta;  // scratch (no heap traffic in the hot loop)
     std::vector<Cluster> cl;
@@ -421,6 +424,12 @@ struct Run {
 
     void init_layout() {
         D = S.nDims; P = S.nDerived; T = 2 * D + P + 2; R = S.num_repeats;
+        // fast/slow grades (oracle_set_grades): R is the total over the grades
+        grade_dims = g_grade_dims; grade_repeats = g_grade_repeats;
+        if (grade_dims.empty() || std::accumulate(grade_dims.begin(), grade_dims.end(), 0) != D) {
+            grade_dims.assign(1, D); grade_repeats.assign(1, R);
+        }
+        R = std::accumulate(grade_repeats.begin(), grade_repeats.end(), 0);
         h0 = 0; p0 = D; d0 = 2 * D; b0 = 2 * D + P; l0 = b0 + 1;  // settings.f90:163-182 (zero-based)
         rng.seed = (uint32_t)S.seed;
     }
@@ -494,19 +503,36 @@ struct Run {
     }
 
     // ---- chordal_sampling.f90 ----
-    // generate_nhats for a single grade (grade_dims = [nDims]).
+    // generate_nhats, chordal_sampling.f90:94-145.  For every grade g: num_repeats(g) directions from random
+    // orthonormal bases of the sub-space of the dimensions of grades >= g (zero in the slower dimensions), then one
+    // shuffle of all columns but the first.  The Gaussian element (row r of the sub-space, column c) comes from
+    // stream (TAG_DIR, uid, a = c, b = r/2), lane r%2.
     void generate_nhats(uint64_t uid, std::vector<double>& nhats) {
         nhats.assign((size_t)D * R, 0.0);
-        std::vector<double> raw((size_t)D * R), basis((size_t)D * D);
-        int lower = 0;
-        // random_orthonormal_bases: full bases while upper_index < num_nhats, then one more, truncated
-        while (lower + D < R) {
-            random_orthonormal_basis(rng, TAG_DIR, uid, lower, D, basis.data());
-            std::copy(basis.begin(), basis.end(), raw.begin() + (size_t)lower * D);
-            lower += D;
+        std::vector<double> raw((size_t)D * R, 0.0);
+        int col0 = 0, off = 0;
+        for (size_t g = 0; g < grade_dims.size(); ++g) {
+            const int Dg = D - off, Rg = grade_repeats[g];
+            std::vector<double> basis((size_t)Dg * Dg);
+            auto put = [&](int col, int count) {
+                for (int i = 0; i < count; ++i)
+                    std::copy(basis.begin() + (size_t)i * Dg, basis.begin() + (size_t)(i + 1) * Dg,
+                              raw.begin() + (size_t)(col + i) * D + off);
+            };
+            int lower = 0;
+            // random_orthonormal_bases: full bases while upper_index < num_nhats, then one more, truncated
+            while (lower + Dg < Rg) {
+                random_orthonormal_basis(rng, TAG_DIR, uid, col0 + lower, Dg, basis.data());
+                put(col0 + lower, Dg);
+                lower += Dg;
+            }
+            if (Rg > 0) {
+                random_orthonormal_basis(rng, TAG_DIR, uid, col0 + lower, Dg, basis.data());
+                put(col0 + lower, Rg - lower);
+            }
+            col0 += Rg;
+            off += grade_dims[g];
         }
-        random_orthonormal_basis(rng, TAG_DIR, uid, lower, D, basis.data());
-        std::copy(basis.begin(), basis.begin() + (size_t)(R - lower) * D, raw.begin() + (size_t)lower * D);
         std::vector<int> deck(R);
         std::iota(deck.begin(), deck.end(), 0);
         shuffle_deck_tail(rng, uid, deck);
@@ -1311,6 +1337,13 @@ int oracle_calculate_points(const oracle_settings* s, int like_kind, const doubl
     long long n = 0;
     for (int i = 0; i < npts; ++i) run.calculate_point(records + (size_t)i * run.T, n);
     return (int)n;
+}
+
+// Fast/slow parameter grades for the following runs (settings%grade_dims, RTI%num_repeats per grade,
+// generate.F90:303-309); nGrade = 0 clears them.
+void oracle_set_grades(int nGrade, const int* grade_dims, const int* grade_repeats) {
+    g_grade_dims.assign(grade_dims, grade_dims + nGrade);
+    g_grade_repeats.assign(grade_repeats, grade_repeats + nGrade);
 }
 
 // NN_clustering (clustering.f90:15-97) of m points (row-major m x D cube coordinates); returns the number of clusters

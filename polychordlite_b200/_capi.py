@@ -4,12 +4,13 @@ Nothing here computes: every call goes into the CUDA library.  If the library is
 import fails loudly (there is no CPU fallback by design).
 """
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "lib" / "libchord.so"
+LIB_PATH = Path(os.environ.get("PC_LIBCHORD", PKG / "lib" / "libchord.so"))
 
 LL_CB = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int)
 PRIOR_CB = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int)
@@ -26,7 +27,7 @@ EXPORTS = [
     "pc_unit_prior", "pc_uniform_prior", "pc_set_option", "pc_get_option", "pc_set_stream", "pc_release_memory", "pc_mgpu_create", "pc_mgpu_attach", "pc_mgpu_destroy",
     "pc_last_run_info", "pc_run", "pc_run_ensemble", "pc_slice_chains", "pc_calculate_points",
     "pc_device_philox", "pc_device_uniforms", "pc_device_inv_normal_cdf", "pc_device_directions",
-    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points",
+    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points", "pc_set_grades",
 ]
 
 
@@ -310,3 +311,12 @@ def cluster_points(points):
     if num < 0:
         raise RuntimeError(f"pc_cluster_points failed with status {num}")
     return labels, num
+
+
+def set_grades(grade_dims=(), grade_repeats=()):
+    """pc_set_grades: fast/slow grades for the following runs / chain probes; no arguments clears them."""
+    n = len(grade_dims)
+    d = (C.c_int * max(n, 1))(*grade_dims)
+    r = (C.c_int * max(n, 1))(*grade_repeats)
+    if lib().pc_set_grades(n, d, r) != 0:
+        raise ValueError("pc_set_grades failed")

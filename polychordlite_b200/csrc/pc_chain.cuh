@@ -30,10 +30,16 @@ enum LikeKind : int { LIKE_GAUSSIAN = 0, LIKE_RASTRIGIN = 1, LIKE_CORR = 2 };
 
 constexpr int NU = 9;  // uniforms staged per slice step: u0 and the first 8 shrink draws (two shrink rounds)
 
+constexpr int MAX_GRADES = 8;
+
 // What the chain code needs from the run configuration.
 struct ChainParams {
     int D, P, T, R, LD;
     int like_kind;
+    // fast/slow parameter grades (settings%grade_dims; RTI%num_repeats per grade, generate.F90:303-309).
+    // ngrade <= 1: one grade of all D dimensions with R repeats.
+    int ngrade;
+    int gdims[MAX_GRADES], greps[MAX_GRADES];
     double logzero;
     double gauss_norm, Vn, log_rast, corr_const;
 };
@@ -226,25 +232,13 @@ struct Model {
 //   deck <- Fisher-Yates shuffle of columns 1..R-1 (chordal_sampling.f90:133-136, random_utils.F90:505-532)
 //   uni  <- slice uniforms: uni[i*NU + 0] = u0 of slice i, uni[i*NU + 1 + s] = shrink draw s
 // ------------------------------------------------------------------------------------------
-__device__ inline void prep_chain(int D, int R, int LD, unsigned seed, unsigned long long uid, const ChainScratch& cs) {
+__device__ inline void prep_chain(int D, int R, int LD, unsigned seed, unsigned long long uid, const ChainScratch& cs,
+                                  const ChainParams* gp = nullptr) {
     const int lane = threadIdx.x & 31;
     double* nh = cs.nh;
-    // (a) Gaussian deviates, two per Philox block (inv_normal_cdf = AS241, utils.F90:777-966)
-    const int H = (D + 1) >> 1;
-    for (int e = lane; e < R * H; e += 32) {
-        const int col = e / H, hp = e - col * H;
-        double u0, u1;
-        uniform2(seed, TAG_DIR, uid, (unsigned)col, (unsigned)hp, u0, u1);
-        double* vp = nh + (size_t)col * LD + 2 * hp;
-        vp[0] = inv_normal_cdf(u0);
-        if (2 * hp + 1 < D) vp[1] = inv_normal_cdf(u1);
-    }
-    for (int e = lane; e < R * (LD - D); e += 32) {  // zero padding of every column (entries D..LD-1)
-        const int col = e / (LD - D), r = D + e - col * (LD - D);
-        nh[(size_t)col * LD + r] = 0.0;
-    }
-    // (c) shuffle picks and (d) slice uniforms are independent of (a)/(b): issue them here so their
-    //     integer work overlaps the FP64 work above
+    const int ngrade = (gp && gp->ngrade > 1) ? gp->ngrade : 1;
+    // (c) shuffle picks and (d) slice uniforms are independent of the directions: issue them first so their
+    //     integer work overlaps the FP64 work below
     for (int i = lane; i < R; i += 32) {
         int j = 0;
         if (i >= 1) {
@@ -258,56 +252,80 @@ __device__ inline void prep_chain(int D, int R, int LD, unsigned seed, unsigned 
         const int i = e / NU, s = e - i * NU;
         cs.uni[e] = uniform(seed, TAG_SLICE, uid, (unsigned)i, (unsigned)s);
     }
-    __syncwarp();
-    // (b) Gram-Schmidt, B bases at a time on LB = 32/B lanes each.  Classical form: all projections of
-    //     vector i on q_0..q_{i-1} are taken from the raw vector, then subtracted together.
-    const int nb = (R + D - 1) / D;
-    const int B = nb >= 4 ? 4 : (nb >= 2 ? 2 : 1);
-    const int LB = 32 / B;
-    const int sl = lane % LB, bslot = lane / LB;
     const int Dpad = (D + 1) & ~1;
-    double* dots = cs.dots + (size_t)bslot * Dpad;
-    for (int b0 = 0; b0 < nb; b0 += B) {
-        const int basis = b0 + bslot;
-        const int col0 = basis * D;
-        const int m = (basis < nb) ? min(D, R - col0) : 0;    // vectors of my basis that are used
-        const int mmax = min(D, R - b0 * D);                  // trip count of the round (first basis is the longest)
-        for (int i = 0; i < mmax; ++i) {
-            const bool act = i < m;
-            double* vp = nh + (size_t)(col0 + i) * LD;
-            if (act) {
-                for (int jj = sl; jj < i; jj += LB) {
-                    const double* q = nh + (size_t)(col0 + jj) * LD;
-                    double d0 = 0.0, d1 = 0.0;
-                    int r = 0;
-                    for (; r + 1 < D; r += 2) { d0 += vp[r] * q[r]; d1 += vp[r + 1] * q[r + 1]; }
-                    if (r < D) d0 += vp[r] * q[r];
-                    dots[jj] = d0 + d1;
-                }
-            }
-            __syncwarp();
-            double acc = 0.0;
-            if (act) {
-                for (int r = sl; r < D; r += LB) {
-                    double t0 = vp[r], t1 = 0.0;
-                    int jj = 0;
-                    for (; jj + 1 < i; jj += 2) {
-                        t0 -= dots[jj] * nh[(size_t)(col0 + jj) * LD + r];
-                        t1 -= dots[jj + 1] * nh[(size_t)(col0 + jj + 1) * LD + r];
-                    }
-                    if (jj < i) t0 -= dots[jj] * nh[(size_t)(col0 + jj) * LD + r];
-                    const double t = t0 + t1;
-                    vp[r] = t;
-                    acc += t * t;
-                }
-            }
-            for (int o = LB >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-            if (act) {
-                const double inv = 1.0 / sqrt(acc);
-                for (int r = sl; r < D; r += LB) vp[r] *= inv;
-            }
-            __syncwarp();
+    // generate_nhats (chordal_sampling.f90:94-145): grade g contributes Rg columns (from column cbase) drawn from
+    // orthonormal bases of the sub-space of the dimensions roff..D-1 (the dimensions of grades >= g); the rows above
+    // roff and the padding rows D..LD-1 are zero
+    int cbase = 0, roff = 0;
+    for (int g = 0; g < ngrade; ++g) {
+        const int Dg = D - roff;
+        const int Rg = ngrade > 1 ? gp->greps[g] : R;
+        // (a) Gaussian deviates, two per Philox block (inv_normal_cdf = AS241, utils.F90:777-966)
+        const int H = (Dg + 1) >> 1;
+        for (int e = lane; e < Rg * H; e += 32) {
+            const int col = e / H, hp = e - col * H;
+            double u0, u1;
+            uniform2(seed, TAG_DIR, uid, (unsigned)(cbase + col), (unsigned)hp, u0, u1);
+            double* vp = nh + (size_t)(cbase + col) * LD + roff + 2 * hp;
+            vp[0] = inv_normal_cdf(u0);
+            if (2 * hp + 1 < Dg) vp[1] = inv_normal_cdf(u1);
         }
+        for (int e = lane; e < Rg * (LD - Dg); e += 32) {  // zeros: rows 0..roff-1 and D..LD-1 of every column
+            const int col = e / (LD - Dg), z = e - col * (LD - Dg);
+            nh[(size_t)(cbase + col) * LD + (z < roff ? z : D + z - roff)] = 0.0;
+        }
+        __syncwarp();
+        // (b) Gram-Schmidt, B bases at a time on LB = 32/B lanes each.  Classical form: all projections of
+        //     vector i on q_0..q_{i-1} are taken from the raw vector, then subtracted together.
+        const int nb = (Rg + Dg - 1) / Dg;
+        const int B = nb >= 4 ? 4 : (nb >= 2 ? 2 : 1);
+        const int LB = 32 / B;
+        const int sl = lane % LB, bslot = lane / LB;
+        double* dots = cs.dots + (size_t)bslot * Dpad;
+        for (int b0 = 0; b0 < nb; b0 += B) {
+            const int basis = b0 + bslot;
+            const int col0 = cbase + basis * Dg;
+            const int m = (basis < nb) ? min(Dg, Rg - basis * Dg) : 0;   // vectors of my basis that are used
+            const int mmax = min(Dg, Rg - b0 * Dg);                      // trip count of the round (first basis is the longest)
+            for (int i = 0; i < mmax; ++i) {
+                const bool act = i < m;
+                double* vp = nh + (size_t)(col0 + i) * LD + roff;
+                if (act) {
+                    for (int jj = sl; jj < i; jj += LB) {
+                        const double* q = nh + (size_t)(col0 + jj) * LD + roff;
+                        double d0 = 0.0, d1 = 0.0;
+                        int r = 0;
+                        for (; r + 1 < Dg; r += 2) { d0 += vp[r] * q[r]; d1 += vp[r + 1] * q[r + 1]; }
+                        if (r < Dg) d0 += vp[r] * q[r];
+                        dots[jj] = d0 + d1;
+                    }
+                }
+                __syncwarp();
+                double acc = 0.0;
+                if (act) {
+                    for (int r = sl; r < Dg; r += LB) {
+                        double t0 = vp[r], t1 = 0.0;
+                        int jj = 0;
+                        for (; jj + 1 < i; jj += 2) {
+                            t0 -= dots[jj] * nh[(size_t)(col0 + jj) * LD + roff + r];
+                            t1 -= dots[jj + 1] * nh[(size_t)(col0 + jj + 1) * LD + roff + r];
+                        }
+                        if (jj < i) t0 -= dots[jj] * nh[(size_t)(col0 + jj) * LD + roff + r];
+                        const double t = t0 + t1;
+                        vp[r] = t;
+                        acc += t * t;
+                    }
+                }
+                for (int o = LB >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+                if (act) {
+                    const double inv = 1.0 / sqrt(acc);
+                    for (int r = sl; r < Dg; r += LB) vp[r] *= inv;
+                }
+                __syncwarp();
+            }
+        }
+        cbase += Rg;
+        roff += ngrade > 1 ? gp->gdims[g] : D;
     }
     // (c) the shuffled deck.  The swaps run i = R-1 .. 1 (swap deck[i], deck[jd[i]]); the element that ends
     //     at position p is found by walking the swaps backwards from p.

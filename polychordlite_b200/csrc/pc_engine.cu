@@ -177,6 +177,7 @@ struct Options {
 };
 static Options g_opt;
 static volatile int g_abort = 0;                  // pc_request_abort(): a host callback asks the run in flight to stop
+static std::vector<int> g_grade_dims, g_grade_reps;   // fast/slow grades of the following runs (pc_set_grades)
 static pc_loglikelihood_t g_host_ll = nullptr;   // host-callback run in flight (PC_LIKE_HOST)
 static pc_prior_t g_host_prior = nullptr;
 static FileOpts g_files;    // output files of the run in flight (set by polychord_c_interface / pc_set_output)
@@ -291,6 +292,16 @@ static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const Dev
     k.host_like = ms.like_kind == PC_LIKE_HOST ? 1 : 0;
     const int npt = 32 / L.fn.G;
     k.cp.D = D; k.cp.P = P; k.cp.T = 2 * D + P + 2; k.cp.R = R;
+    k.cp.ngrade = 1;
+    if (g_grade_dims.size() > 1) {  // pc_set_grades: the dimensions and the repeats must add up to this run's
+        int sd = 0, sr = 0;
+        for (int v : g_grade_dims) sd += v;
+        for (int v : g_grade_reps) sr += v;
+        if (sd != D || sr != R || g_grade_dims.size() > MAX_GRADES)
+            throw std::invalid_argument("polychord_b200: grade_dims must sum to nDims, the repeats per grade to num_repeats (at most 8 grades)");
+        k.cp.ngrade = (int)g_grade_dims.size();
+        for (int g = 0; g < k.cp.ngrade; ++g) { k.cp.gdims[g] = g_grade_dims[g]; k.cp.greps[g] = g_grade_reps[g]; }
+    }
     k.cp.LD = (L.fn.G * L.fn.DPL) | 1;  // odd (bank-conflict free), zero-padded to the lanes' G*DPL dimensions
     k.cp.like_kind = ms.like_kind == PC_LIKE_HOST ? PC_LIKE_GAUSSIAN : ms.like_kind;
     k.cp.logzero = s.logzero;
@@ -427,7 +438,7 @@ struct Engine {
         const int D = k.cp.D, P = k.cp.P, K = runs[0].host_st.K;
         HcParams hp;
         std::memset(&hp, 0, sizeof(hp));
-        hp.D = D; hp.P = P; hp.T = k.cp.T; hp.R = k.cp.R; hp.LD = k.cp.LD; hp.n = k.n; hp.K = K;
+        hp.D = D; hp.P = P; hp.T = k.cp.T; hp.R = k.cp.R; hp.LD = k.cp.LD; hp.n = k.n; hp.K = K; hp.cp = k.cp;
         hp.logzero = S.logzero; hp.seed = runs[0].buf.seed; hp.rb = runs[0].buf;
         hp.scratch_bytes = chain_scratch_bytes(D, k.cp.R, k.cp.LD, true, LIKE_GAUSSIAN, 1);
         if (!hc_out) {
@@ -1086,6 +1097,12 @@ double pc_get_option(const char* name) {
 }
 void pc_set_stream(void* cuda_stream) { g_stream = (cudaStream_t)cuda_stream; }
 void pc_request_abort(void) { g_abort = 1; }
+int pc_set_grades(int nGrade, const int* grade_dims, const int* grade_repeats) {
+    if (nGrade < 0 || nGrade > MAX_GRADES) return -1;
+    g_grade_dims.assign(grade_dims, grade_dims + nGrade);
+    g_grade_reps.assign(grade_repeats, grade_repeats + nGrade);
+    return 0;
+}
 void pc_release_memory(void) { pool().trim(); }
 
 // ---- sharded run over the GPUs of one box ---------------------------------------------------------
@@ -1506,8 +1523,28 @@ void polychord_c_interface(pc_loglikelihood_t loglikelihood, pc_prior_t prior, p
         seed = (int)(std::chrono::high_resolution_clock::now().time_since_epoch().count() & 0x7fffffff);
     }
     s.seed = seed;
-    if (nGrade != 1 || (grade_dims && grade_dims[0] != nDims)) {
-        fail(-4, "fast/slow parameter grades (nGrade > 1) are not supported by the B200 engine yet");
+    // fast/slow grades: repeats per grade as generate.F90:303-309 sets them -- grade_frac > 1 everywhere: the
+    // fractions ARE the repeat counts; otherwise num_repeats for the slowest grade and in proportion to
+    // grade_frac for the others.  The reference also scales by the measured likelihood speed of each grade
+    // (time_speeds, generate.F90:330-455); this engine has no partial evaluations to time, so the speeds are equal.
+    struct GradesGuard { ~GradesGuard() { g_grade_dims.clear(); g_grade_reps.clear(); } } grades_guard;
+    if (nGrade > 1) {
+        if (nGrade > MAX_GRADES || !grade_dims || !grade_frac) { fail(-4, "at most 8 parameter grades are supported"); return; }
+        int sd = 0;
+        bool counts = true;
+        for (int g = 0; g < nGrade; ++g) { sd += grade_dims[g]; counts = counts && grade_frac[g] > 1.0; }
+        if (sd != nDims) { fail(-4, "grade_dims must sum to nDims"); return; }
+        g_grade_dims.assign(grade_dims, grade_dims + nGrade);
+        g_grade_reps.assign(nGrade, 0);
+        int total = 0;
+        for (int g = 0; g < nGrade; ++g) {
+            g_grade_reps[g] = counts ? (int)grade_frac[g]
+                                     : (g == 0 ? num_repeats : (int)std::lround(grade_frac[g] / grade_frac[0] * num_repeats));
+            total += g_grade_reps[g];
+        }
+        s.num_repeats = total;
+    } else if (grade_dims && grade_dims[0] != nDims) {
+        fail(-4, "grade_dims must sum to nDims");
         return;
     }
     if (n_nlives > 0) {

@@ -27,6 +27,7 @@ struct HcChain {
 // what the host returns: [theta D | phi P | logL]
 struct HcParams {
     int D, P, T, R, LD, n;
+    ChainParams cp;        // for the direction preparation (grades)
     int K;                 // chains of this generation
     double logzero;
     unsigned seed;
@@ -91,7 +92,7 @@ __global__ void hc_begin_kernel(const HcParams p) {
     double* x = p.x + (size_t)k * p.LD;
     for (int r = lane; r < p.LD; r += 32) x[r] = r < D ? p.rb.live[(size_t)src * T + r] : 0.0;
     const ChainScratch cs = hc_scratch(p, k);
-    prep_chain(D, p.R, p.LD, p.seed, uid, cs);
+    prep_chain(D, p.R, p.LD, p.seed, uid, cs, &p.cp);
     whiten_chain<16>(D, p.R, p.LD, p.rb.chol, cs);
     __syncwarp();
     HcChain c;

@@ -815,7 +815,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                 const int plab = clustered ? min(__ldcg(rb.lab + src), MAX_CLUSTERS - 1) : 0;  // the seed's cluster
                 if (helper) {
                     long long th0 = clock64();
-                    if (prep_uid != uid) { prep_chain(D, R, LD, rb.seed, uid, b); prep_white = false; }
+                    if (prep_uid != uid) { prep_chain(D, R, LD, rb.seed, uid, b, &p.cp); prep_white = false; }
                     if (clustered) whiten_chain<(G * DPL + 7) / 8>(D, R, LD, rb.cchol + (size_t)plab * D * D, b);
                     else if (!prep_white) whiten_chain<(G * DPL + 7) / 8>(D, R, LD, s_chol, b);
                     prep_uid = ~0ull;
@@ -869,7 +869,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                 double* last = sharded ? xin_mine + (size_t)k * T : rb.live + (size_t)dslot * T;
                 long long tc0 = clock64();
                 if (prep_uid != uid) {
-                    prep_chain(D, R, LD, rb.seed, uid, cs);
+                    prep_chain(D, R, LD, rb.seed, uid, cs, &p.cp);
                     prep_white = false;
                 }
                 long long tc1 = clock64();
@@ -935,12 +935,12 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
             have_wtarget = false;
             if (will_chain) {  // the Cholesky factor is about to change: whiten after the barrier
                 prep_uid = (unsigned long long)(nchains_base + K + knext);
-                prep_chain(D, R, LD, rb.seed, prep_uid, csn);
+                prep_chain(D, R, LD, rb.seed, prep_uid, csn, &p.cp);
                 prep_white = false;
             }
         } else if (will_chain) {
             prep_uid = (unsigned long long)(nchains_base + K + knext);
-            prep_chain(D, R, LD, rb.seed, prep_uid, csn);
+            prep_chain(D, R, LD, rb.seed, prep_uid, csn, &p.cp);
             prep_white = false;
             if (!p.clustering) {  // with clusters the factor depends on the chain's seed, which the next phase S decides
                 whiten_chain<(G * DPL + 7) / 8>(D, R, LD, s_chol, csn);
@@ -980,7 +980,7 @@ __global__ void __launch_bounds__(256, 1) pc_slice_chains_kernel(const __grid_co
         for (int j = 0; j < DPL; ++j) x[j] = M.valid(j) ? seed_points[(size_t)c * T + M.dim(j)] : 0.0;
         unsigned long long nl = 0;
         double* out = babies + (size_t)c * R * T;
-        prep_chain(D, R, LD, seed, uid[c], cs);
+        prep_chain(D, R, LD, seed, uid[c], cs, &p.cp);
         whiten_chain<(G * DPL + 7) / 8>(D, R, LD, s_chol, cs);
         slice_chain<G, DPL, KIND>(p.cp, M, seed, uid[c], x, logL[c], cs, out, out + (size_t)(R - 1) * T, nl);
         if (lane == 0) nlike_out[c] = (long long)nl;

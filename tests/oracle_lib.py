@@ -196,3 +196,9 @@ def nn_clustering(points):
     L.oracle_nn_clustering.restype = C.c_int
     num = L.oracle_nn_clustering(_dptr(pts), m, D, labels.ctypes.data_as(C.POINTER(C.c_int)))
     return labels, num
+
+
+def set_grades(grade_dims=(), grade_repeats=()):
+    """oracle_set_grades: fast/slow grades for the following runs / chain probes; no arguments clears them."""
+    n = len(grade_dims)
+    lib().oracle_set_grades(n, (C.c_int * max(n, 1))(*grade_dims), (C.c_int * max(n, 1))(*grade_repeats))

@@ -112,3 +112,33 @@ def test_walls_out_of_cube_points_are_never_accepted(gpu):
                                      np.arange(64, dtype=np.uint64), like_params=[0.0, 1.0])
     assert np.all(babies[:, :, :D] >= 0.0) and np.all(babies[:, :, :D] <= 1.0)
     assert np.all(babies[:, :, -1] > -1e30)
+
+
+@pytest.mark.parametrize("D,dims,reps", [(4, [1, 3], [20, 20]), (20, [5, 5, 10], [7, 40, 13]), (9, [8, 1], [3, 5])])
+def test_chains_with_parameter_grades_match_oracle(gpu, oracle, D, dims, reps):
+    """Fast/slow grades (chordal_sampling.f90:94-145): grade g draws its slice directions in the sub-space of the
+    dimensions of grades >= g.  Same babies, same nlike as the oracle; slow dimensions do not move in fast steps."""
+    R = sum(reps)
+    rng = np.random.default_rng(7)
+    so = oracle.make_settings(D, 0, nlive=10, num_repeats=R, seed=3)
+    sg = gpu.make_settings(D, 0, nlive=10, num_repeats=R, seed=3)
+    cubes = np.clip(0.5 + 0.05 * rng.standard_normal((16, D)), 1e-6, 1 - 1e-6)
+    chol = np.tril(rng.standard_normal((D, D)) * 0.01) + 0.05 * np.eye(D)
+    gpu.set_grades(dims, reps)
+    oracle.set_grades(dims, reps)
+    try:
+        rec, _ = oracle.calculate_points(so, cubes)
+        logL = rec[:, -1] - 2.0
+        uid = np.arange(16, dtype=np.uint64) + 100
+        babies, nlike = gpu.slice_chains(sg, rec, chol, logL, uid)
+        for c in range(16):
+            want, nl = oracle.slice_chain(so, rec[c], chol, float(logL[c]), int(uid[c]))
+            assert nl == nlike[c]
+            assert np.allclose(babies[c], want, rtol=0, atol=2e-8)
+        # a step of the fastest grade leaves the dimensions of the slower grades untouched
+        steps = np.diff(np.vstack([rec[0, :D], babies[0][:, :D]]), axis=0)
+        frozen = (np.abs(steps[:, :dims[0]]).max(axis=1) == 0).sum()
+        assert frozen >= sum(reps[1:]) - 1
+    finally:
+        gpu.set_grades()
+        oracle.set_grades()

@@ -1,0 +1,65 @@
+"""Randomised configurations, engine against oracle (batched schedule): shapes at the edges of every template
+instantiation (nDims 1..65), few live points, one slice per chain, every K from 1 to n-1, all three likelihoods,
+box priors, derived parameters, max_ndead, clustering on, fast/slow parameter grades.  Identical ndead / nlike / nupdates, logZ to rounding."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(rng, i):
+    D = int(rng.choice([1, 2, 3, 5, 8, 9, 16, 17, 20, 21, 32, 33, 40, 65]))
+    like = str(rng.choice(["gaussian", "rastrigin", "corr_gaussian"]))
+    if D > 40 and like == "rastrigin":
+        like = "gaussian"
+    P = int(rng.choice([0, 0, 1, 2, 3])) if like == "gaussian" else 0
+    n = int(rng.choice([4, 7, 16, 50, 120, 300]))
+    if D > 32:
+        n = max(n, 50)   # with far fewer live points than dimensions the covariance is rank-deficient and the Cholesky
+                         # fallback decision is rounding noise: no parity statement is possible there
+    R = int(rng.choice([1, 2, D, 2 * D + 1]))
+    R = min(R, 60)
+    grades = None
+    if D >= 3 and rng.random() < 0.3:   # fast/slow parameter grades
+        cut = sorted(rng.choice(np.arange(1, D), size=int(rng.integers(1, 3)), replace=False).tolist())
+        dims = np.diff([0] + cut + [D]).tolist()
+        reps = [int(rng.integers(1, 12)) for _ in dims]
+        grades, R = (dims, reps), sum(reps)
+    K = int(rng.integers(1, n))
+    kw = {}
+    lp = None
+    if like == "rastrigin":
+        kw = dict(prior_lo=[-5.12] * D, prior_hi=[5.12] * D)
+    elif like == "gaussian" and rng.random() < 0.5:
+        lo, hi = -rng.uniform(0.5, 2.0, D), rng.uniform(0.5, 2.0, D)
+        kw = dict(prior_lo=list(lo), prior_hi=list(hi))
+        lp = np.concatenate([rng.uniform(-0.2, 0.2, D), rng.uniform(0.05, 0.3, D)])
+    elif like == "corr_gaussian":
+        Q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+        sig = 0.1 * 0.1 ** (np.arange(D) / max(D - 1, 1))
+        invcov = (Q / sig ** 2) @ Q.T
+        invcov = 0.5 * (invcov + invcov.T)
+        lp = np.concatenate([np.full(D, 0.5), invcov.flatten(order="F"), [2 * np.log(sig).sum()]])
+    st = dict(nlive=n, num_repeats=R, seed=int(rng.integers(0, 1000)), do_clustering=bool(rng.random() < 0.3),
+              max_ndead=int(rng.choice([-1, -1, 3 * n])), precision_criterion=float(rng.choice([1e-3, 1e-2])))
+    return D, P, like, lp, kw, K, st, grades
+
+
+@pytest.mark.parametrize("i", range(32))
+def test_random_configuration_matches_oracle(gpu, oracle, i):
+    rng = np.random.default_rng(1000 + i)
+    D, P, like, lp, kw, K, st, grades = _case(rng, i)
+    gpu.set_option("batch_K", K)
+    if grades:
+        gpu.set_grades(*grades)
+        oracle.set_grades(*grades)
+    try:
+        gi, _ = gpu.run(gpu.make_settings(D, P, **st), like=like, like_params=lp, **kw)
+        oi, _ = oracle.run(oracle.make_settings(D, P, batch_K=K, **st), like=like, like_params=lp, **kw)
+    finally:
+        gpu.set_option("batch_K", 0)
+        gpu.set_grades()
+        oracle.set_grades()
+    desc = f"D={D} P={P} {like} K={K} {st} grades={grades}"
+    assert (gi.ndead, gi.nlike, gi.nupdates) == (oi.ndead, oi.nlike, oi.nupdates), desc
+    assert abs(gi.logZ - oi.logZ) < 1e-6 * max(1.0, abs(oi.logZ)), desc
