@@ -42,6 +42,12 @@ def _case(rng, i):
         lp = np.concatenate([np.full(D, 0.5), invcov.flatten(order="F"), [2 * np.log(sig).sum()]])
     st = dict(nlive=n, num_repeats=R, seed=int(rng.integers(0, 1000)), do_clustering=bool(rng.random() < 0.3),
               max_ndead=int(rng.choice([-1, -1, 3 * n])), precision_criterion=float(rng.choice([1e-3, 1e-2])))
+    if like == "rastrigin" and D > 24 and st["max_ndead"] < 0:
+        # engine and oracle add in different orders, so their coordinates differ by rounding; through 10 cos(2 pi theta)
+        # in 30+ dimensions and the covariance feedback that difference grows along a run (1e-9 in logL after ~1400
+        # deaths, measured) until an accept/reject decision flips.  Long high-dimensional Rastrigin runs are compared
+        # over their first 12 n deaths, where the two still agree to rounding.
+        st["max_ndead"] = 12 * n
     return D, P, like, lp, kw, K, st, grades
 
 
