@@ -15,7 +15,7 @@ LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libchord.so"
 
 NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", *os.environ.get("PC_EXTRA_NVCC", "").split(),
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "--threads", "8",
 ]
 

@@ -65,7 +65,11 @@ struct DevRun {
     int pad0;
     // SM-clock cycle counters of the phases (thread 0 of CTA 0; chain phases: warp 0 of the first chain CTA)
     long long cyc_wait, cyc_S, cyc_fin, cyc_U, cyc_prep, cyc_white, cyc_slice, cyc_total;
-    long long dbg[16];    // scratch cycle counters for profiling experiments (printed when PC_DEBUG is set)
+    // finer cycle counters, printed (in ms) when PC_DEBUG is set: [0] slice loop and [1] derived parameters of the
+    // representative chain warp; phase U of CTA 0: [2] pass A, [3] barrier, [4] pass B ([12] its set-up, [13] its tile
+    // loop, [15] the warps' combination), [5] closing barrier; phase S1: [6] keys, [7] termination test, [8] sort +
+    // merge, [9] publication; the first chain CTA: [10] wait at the generation barrier, [11] release -> first slice
+    long long dbg[16];
     unsigned int bar;    // group barrier, one arrival per CTA (monotonic)
     unsigned int wbar;   // chains-done barrier, one arrival per warp (monotonic)
 };

@@ -922,12 +922,6 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
             long long ua2 = clock64();
             phase_UB(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt);
             long long ua3 = clock64();
-#ifdef PC_EXPERIMENT_UB_TWICE
-            __syncthreads();
-            phase_UB(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt);
-            if (timer) st->dbg[12] += clock64() - ua3;
-            ua3 = clock64();
-#endif
             if (timer) { st->dbg[2] += ua1 - ua0; st->dbg[3] += ua2 - ua1; st->dbg[4] += ua3 - ua2; st->dbg[5] -= ua3; }
             if (cta == 0 && tid == 0) st->update_pending = 1;
             group_sync(&st->bar, NG);
