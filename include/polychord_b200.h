@@ -112,6 +112,7 @@ void pc_uniform_prior(double* cube, double* theta, int nDims); /* theta = lo + (
  *                     serialise kernel launches (the host cannot acknowledge a dump from inside the launch call).
  *   "no_pairing"      1: do not use helper warps for the direction preparation (a run alone on the device
  *                     normally pairs every chain warp with a helper warp)
+ *   "resume_interval" seconds between two rewrites of the resume file at updates (default 1; 0 = every update)
  *   "cap_dead0", "cap_ph0"  initial capacity (records) of the dead / phantom pools; 0 = automatic.
  *                     The pools grow on demand either way (the kernel exits, the host reallocates, relaunches).
  */
@@ -128,6 +129,13 @@ void pc_request_abort(void);
  * grade_repeats[g] slice steps per chain, drawn in the sub-space of the dimensions of grades >= g
  * (chordal_sampling.f90:94-145).  The dims must sum to nDims, the repeats to num_repeats.  nGrade = 0 clears. */
 int pc_set_grades(int nGrade, const int* grade_dims, const int* grade_repeats);
+/* Resume file for the following pc_run() calls (polychord_c_interface uses <base_dir>/<file_root>.resume with its
+ * write_resume / read_resume flags; replaces read_write.F90:219-476).  `path` must end in ".resume".  write: the run's
+ * state is saved between generations at the update cadence (at most once a second) and after the final kill-off;
+ * read: an existing file of the same run shape continues that run -- with its own seed, so an interrupted run and
+ * an uninterrupted one end bit-identical -- and a file of a different shape is a fatal error (read_write.F90:402-417).
+ * The file is this engine's own binary layout, not the reference's text dump.  NULL clears. */
+int pc_set_resume(const char* path, int write, int read);
 /* The engine keeps the device buffers of finished runs for the next run (cudaMalloc/cudaFree cost
  * milliseconds); this returns the cached blocks to the driver. */
 void pc_release_memory(void);

@@ -27,7 +27,7 @@ EXPORTS = [
     "pc_unit_prior", "pc_uniform_prior", "pc_set_option", "pc_get_option", "pc_set_stream", "pc_release_memory", "pc_mgpu_create", "pc_mgpu_attach", "pc_mgpu_destroy",
     "pc_last_run_info", "pc_run", "pc_run_ensemble", "pc_slice_chains", "pc_calculate_points",
     "pc_device_philox", "pc_device_uniforms", "pc_device_inv_normal_cdf", "pc_device_directions",
-    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points", "pc_set_grades",
+    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points", "pc_set_grades", "pc_set_resume",
 ]
 
 
@@ -122,20 +122,23 @@ def _prior_params(lo, hi):
     return np.concatenate([_arr(lo), _arr(hi)])
 
 
-def run(settings, like="gaussian", like_params=None, prior_lo=None, prior_hi=None, want_dump=False):
-    """One device run (pc_run).  Returns (RunInfo, dumps)."""
+def run(settings, like="gaussian", like_params=None, prior_lo=None, prior_hi=None, want_dump=False, abort_after_dumps=None):
+    """One device run (pc_run).  Returns (RunInfo, dumps).  abort_after_dumps: call pc_request_abort() from inside the
+    N-th dumper call (an interrupted run)."""
     L = lib()
     lp, pp = _arr(like_params), _prior_params(prior_lo, prior_hi)
     dumps = []
 
     def _dump(ndead, nlive, npars, live, dead, lw, logZ, logZerr):
+        if abort_after_dumps is not None and len(dumps) + 1 == abort_after_dumps:
+            L.pc_request_abort()
         dumps.append(dict(
             live=np.ctypeslib.as_array(live, shape=(max(nlive, 1), npars))[:nlive].copy(),
             dead=np.ctypeslib.as_array(dead, shape=(max(ndead, 1), npars))[:ndead].copy(),
             logweights=np.ctypeslib.as_array(lw, shape=(max(ndead, 1),))[:ndead].copy(),
             logZ=logZ, logZerr=logZerr))
 
-    dcb = DUMPER_CB(_dump) if want_dump else C.cast(None, DUMPER_CB)
+    dcb = DUMPER_CB(_dump) if (want_dump or abort_after_dumps) else C.cast(None, DUMPER_CB)
     info = RunInfo()
     rc = L.pc_run(C.byref(settings), LIKE_KINDS[like], _dptr(lp), 0 if lp is None else lp.size, _dptr(pp),
                   0 if pp is None else pp.size, dcb, C.byref(info))
@@ -320,3 +323,11 @@ def set_grades(grade_dims=(), grade_repeats=()):
     r = (C.c_int * max(n, 1))(*grade_repeats)
     if lib().pc_set_grades(n, d, r) != 0:
         raise ValueError("pc_set_grades failed")
+
+
+def set_resume(path=None, write=False, read=False):
+    """pc_set_resume: resume file of the following runs (path ending in .resume); no arguments clears it."""
+    L = lib()
+    L.pc_set_resume.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    if L.pc_set_resume(None if path is None else str(path).encode(), int(write), int(read)) != 0:
+        raise ValueError("pc_set_resume: the path must end in .resume")

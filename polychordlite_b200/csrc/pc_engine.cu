@@ -180,6 +180,12 @@ static volatile int g_abort = 0;                  // pc_request_abort(): a host 
 static std::vector<int> g_grade_dims, g_grade_reps;   // fast/slow grades of the following runs (pc_set_grades)
 static pc_loglikelihood_t g_host_ll = nullptr;   // host-callback run in flight (PC_LIKE_HOST)
 static pc_prior_t g_host_prior = nullptr;
+struct ResumeOpts {   // <base_dir>/<file_root>.resume
+    bool write = false, read = false;
+    std::string path;
+    double min_interval_s = 1.0;   // rewrites at updates are rate-limited; the one after the final kill-off always happens
+};
+static ResumeOpts g_resume;
 static FileOpts g_files;    // output files of the run in flight (set by polychord_c_interface / pc_set_output)
 static FileState g_fstate;
 static double g_dbg_dump[4];  // PC_DEBUG: ms spent in copies, row packing, weight normalisation, the user's dumper
@@ -366,6 +372,52 @@ struct HostRun {
     double lse_max = -std::numeric_limits<double>::infinity(), lse_sum = 0.0;  // running logsumexp of logw + logL
 };
 
+// Resume file.  The reference dumps its run_time_info as text (read_write.F90:219-476) so that the same program can
+// pick the run up again; nothing else reads that file, so this engine writes ITS OWN state in its own (binary) layout:
+// a header that pins the run's shape (the reference checks nDims / nDerived / grades the same way, :402-417), the
+// DevRun scalars, and every array a generation reads.  Written to <root>_temp.resume and renamed (read_write.F90:107).
+struct ResumeHeader {
+    char magic[8];
+    int version, sizeof_devrun;
+    int D, P, n, R, batch_K, like_kind, clustering, ngrade;
+    int gdims[MAX_GRADES], greps[MAX_GRADES];
+    unsigned seed;
+    int pad;
+    double logzero;
+};
+struct ResumeData {
+    ResumeHeader h;
+    DevRun st;
+    std::vector<double> live, okey, dead, logw, ph, chol, cov, gsum, cchol;
+    std::vector<int> order, lab, phl;
+};
+static const char RESUME_MAGIC[8] = {'P', 'C', 'B', '2', '0', '0', 'R', '1'};
+template <class V>
+static void put_vec(FILE* f, const std::vector<V>& v) {
+    const unsigned long long n = v.size();
+    std::fwrite(&n, sizeof(n), 1, f);
+    if (n) std::fwrite(v.data(), sizeof(V), n, f);
+}
+template <class V>
+static bool get_vec(FILE* f, std::vector<V>& v) {
+    unsigned long long n = 0;
+    if (std::fread(&n, sizeof(n), 1, f) != 1 || n > (1ull << 34)) return false;
+    v.resize(n);
+    return n == 0 || std::fread(v.data(), sizeof(V), n, f) == n;
+}
+static bool read_resume_file(const std::string& path, ResumeData& rd) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    bool ok = std::fread(&rd.h, sizeof(rd.h), 1, f) == 1 && std::memcmp(rd.h.magic, RESUME_MAGIC, 8) == 0 &&
+              rd.h.version == 1 && rd.h.sizeof_devrun == (int)sizeof(DevRun) && std::fread(&rd.st, sizeof(DevRun), 1, f) == 1;
+    ok = ok && get_vec(f, rd.live) && get_vec(f, rd.order) && get_vec(f, rd.okey) && get_vec(f, rd.dead) && get_vec(f, rd.logw) &&
+         get_vec(f, rd.ph) && get_vec(f, rd.chol) && get_vec(f, rd.cov) && get_vec(f, rd.gsum) && get_vec(f, rd.lab) &&
+         get_vec(f, rd.phl) && get_vec(f, rd.cchol);
+    std::fclose(f);
+    if (!ok) throw std::invalid_argument("polychord_b200: " + path + " is not a resume file of this engine version");
+    return true;
+}
+
 struct Engine {
     pc_settings S;
     ModelSpec ms;
@@ -376,6 +428,11 @@ struct Engine {
     std::vector<HostRun> runs;
     DevArr<RunBuf> d_bufs;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // resume (row f3)
+    bool resumed = false, resumed_finished = false;
+    ResumeData rd;
+    std::chrono::steady_clock::time_point resume_last;
+    bool resume_written = false;
     // host-callback runs (pc_hostchain.cuh)
     bool host_like = false;
     DevArr<unsigned char> hc_scratch;
@@ -523,6 +580,18 @@ struct Engine {
         const int K = k.batch_K;
         // do_clustering: one run on one GPU with a device likelihood; elsewhere the run stays one cluster (always valid)
         k.clustering = (S.do_clustering && nruns == 1 && g_mgpu.world <= 1 && !host_like) ? 1 : 0;
+        // read_resume: a file of this run's shape continues the run (nested_sampling.F90:175-183)
+        if (g_resume.read && nruns == 1 && g_mgpu.world <= 1 && read_resume_file(g_resume.path, rd)) {
+            const ResumeHeader& rh = rd.h;
+            bool same = rh.D == k.cp.D && rh.P == k.cp.P && rh.n == k.n && rh.R == k.cp.R && rh.batch_K == K &&
+                        rh.like_kind == ms.like_kind && rh.clustering == k.clustering && rh.ngrade == k.cp.ngrade;
+            for (int g = 0; same && g < k.cp.ngrade && k.cp.ngrade > 1; ++g)
+                same = rh.gdims[g] == k.cp.gdims[g] && rh.greps[g] == k.cp.greps[g];
+            if (!same)  // read_write.F90:402-417: a resume file of a different run is fatal
+                throw std::invalid_argument("polychord_b200: the resume file " + g_resume.path + " belongs to a run of a different shape "
+                                            "(nDims, nDerived, nlive, num_repeats, grades, likelihood kind, clustering or batch size)");
+            resumed = true;
+        }
         // CTAs per run: one warp per chain unless capped by residency
         int dev = 0, sms = 0, per_sm = 0;
         PC_CUDA(cudaGetDevice(&dev));
@@ -565,6 +634,10 @@ struct Engine {
             long long cap_ph = std::max<long long>(3LL * n * (R - 1) + (long long)K * (R - 1), n);
             if (g_opt.cap_dead0 > 0) cap_dead = std::max<long long>(g_opt.cap_dead0, 2LL * n + K);
             if (g_opt.cap_ph0 > 0) cap_ph = std::max<long long>(g_opt.cap_ph0, std::max<long long>((long long)K * (R - 1), n));
+            if (resumed) {  // room for what the file holds plus the next generation
+                cap_dead = std::max<long long>(cap_dead, rd.st.ndead + 2LL * n + K);
+                cap_ph = std::max<long long>(cap_ph, rd.st.nphantom + (long long)K * (R - 1) + n);
+            }
             h.st.alloc(1); h.st.zero(stream);
             h.live.alloc((size_t)n * T); h.live.zero(stream);
             h.order.alloc(2 * (size_t)n);
@@ -592,10 +665,36 @@ struct Engine {
             b.lab = h.lab.p; b.phl[0] = h.phl0.p; b.phl[1] = h.phl1.p; b.cchol = h.cchol.p;
             if (sharded)  // continue the cross-GPU barrier count of earlier runs (the counters are monotonic)
                 PC_CUDA(cudaMemcpyAsync(&h.st.p->xepoch, &g_mgpu.epoch, sizeof(g_mgpu.epoch), cudaMemcpyHostToDevice, stream));
-            b.seed = (unsigned)seeds[r];
+            b.seed = resumed ? rd.h.seed : (unsigned)seeds[r];   // a resumed run continues its own random stream
             hb[r] = b;
         }
         mark("allocs");
+        if (resumed) {  // the run continues from the state the file holds
+            HostRun& h = runs[0];
+            DevRun st0 = rd.st;
+            st0.status = ST_RUNNING;
+            st0.bar = 0; st0.wbar = 0;   // the barrier counters restart with the launch geometry of this process
+            if (rd.st.status == ST_DONE) resumed_finished = true;
+            h.st.upload(&st0, 1, stream);
+            h.host_st = rd.st;
+            h.live.upload(rd.live.data(), rd.live.size(), stream);
+            h.order.upload(rd.order.data(), rd.order.size(), stream);
+            h.okey.upload(rd.okey.data(), rd.okey.size(), stream);
+            if (!rd.dead.empty()) h.dead.upload(rd.dead.data(), rd.dead.size(), stream);
+            if (!rd.logw.empty()) h.logw.upload(rd.logw.data(), rd.logw.size(), stream);
+            DevArr<double>& pool = rd.st.cur_pool == 0 ? h.ph0 : h.ph1;
+            if (!rd.ph.empty()) pool.upload(rd.ph.data(), rd.ph.size(), stream);
+            h.chol.upload(rd.chol.data(), rd.chol.size(), stream);
+            h.cov.upload(rd.cov.data(), rd.cov.size(), stream);
+            h.gsum.upload(rd.gsum.data(), rd.gsum.size(), stream);
+            if (k.clustering) {
+                h.lab.upload(rd.lab.data(), rd.lab.size(), stream);
+                DevArr<int>& pl = rd.st.cur_pool == 0 ? h.phl0 : h.phl1;
+                if (!rd.phl.empty()) pl.upload(rd.phl.data(), rd.phl.size(), stream);
+                if (!rd.cchol.empty()) h.cchol.upload(rd.cchol.data(), rd.cchol.size(), stream);
+            }
+            h2d += (long long)(rd.live.size() + rd.dead.size() + rd.ph.size()) * 8;
+        }
         d_bufs.alloc(nruns);
         d_bufs.upload(hb.data(), nruns, stream);
         h2d += (long long)nruns * sizeof(RunBuf);
@@ -878,6 +977,54 @@ struct Engine {
         cluster_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count();
     }
 
+    // write_resume_file (read_write.F90:219-288): the state between two generations
+    void write_resume(bool final_call) {
+        if (!g_resume.write || nruns != 1 || g_mgpu.world > 1) return;
+        const auto now = std::chrono::steady_clock::now();
+        if (!final_call && resume_written && std::chrono::duration<double>(now - resume_last).count() < g_resume.min_interval_s) return;
+        const KParams& k = L.kp;
+        HostRun& h = runs[0];
+        const DevRun& st = h.host_st;
+        const int n = k.n, T = k.cp.T, D = k.cp.D;
+        ResumeData w;
+        std::memset(&w.h, 0, sizeof(w.h));
+        std::memcpy(w.h.magic, RESUME_MAGIC, 8);
+        w.h.version = 1; w.h.sizeof_devrun = (int)sizeof(DevRun);
+        w.h.D = D; w.h.P = k.cp.P; w.h.n = n; w.h.R = k.cp.R; w.h.batch_K = k.batch_K; w.h.like_kind = ms.like_kind;
+        w.h.clustering = k.clustering; w.h.ngrade = k.cp.ngrade;
+        for (int g = 0; g < MAX_GRADES; ++g) { w.h.gdims[g] = k.cp.gdims[g]; w.h.greps[g] = k.cp.greps[g]; }
+        w.h.seed = h.buf.seed; w.h.logzero = S.logzero;
+        w.st = st;
+        auto pull = [&](auto& vec, const auto& arr, size_t cnt) { vec.resize(cnt); if (cnt) arr.download(vec.data(), cnt, stream); };
+        pull(w.live, h.live, (size_t)n * T);
+        pull(w.order, h.order, 2 * (size_t)n);
+        pull(w.okey, h.okey, 2 * (size_t)n);
+        pull(w.dead, h.dead, (size_t)st.ndead * T);
+        pull(w.logw, h.logw, (size_t)st.ndead);
+        pull(w.ph, st.cur_pool == 0 ? h.ph0 : h.ph1, (size_t)st.nphantom * T);
+        pull(w.chol, h.chol, (size_t)D * D);
+        pull(w.cov, h.cov, (size_t)D * D);
+        pull(w.gsum, h.gsum, (size_t)2 * D + 4);
+        if (k.clustering) {
+            pull(w.lab, h.lab, (size_t)n);
+            pull(w.phl, st.cur_pool == 0 ? h.phl0 : h.phl1, (size_t)st.nphantom);
+            pull(w.cchol, h.cchol, (size_t)std::max(st.ncl, 1) * D * D);
+        }
+        PC_CUDA(cudaStreamSynchronize(stream));
+        d2h += (long long)(w.live.size() + w.dead.size() + w.ph.size()) * 8;
+        const std::string tmp = g_resume.path.substr(0, g_resume.path.size() - 7) + "_temp.resume";
+        FILE* f = std::fopen(tmp.c_str(), "wb");
+        if (!f) throw std::runtime_error("polychord_b200: cannot write " + tmp);
+        std::fwrite(&w.h, sizeof(w.h), 1, f);
+        std::fwrite(&w.st, sizeof(DevRun), 1, f);
+        put_vec(f, w.live); put_vec(f, w.order); put_vec(f, w.okey); put_vec(f, w.dead); put_vec(f, w.logw); put_vec(f, w.ph);
+        put_vec(f, w.chol); put_vec(f, w.cov); put_vec(f, w.gsum); put_vec(f, w.lab); put_vec(f, w.phl); put_vec(f, w.cchol);
+        std::fclose(f);
+        std::rename(tmp.c_str(), g_resume.path.c_str());
+        resume_written = true;
+        resume_last = std::chrono::steady_clock::now();
+    }
+
     void grow(int r, int status) {
         HostRun& h = runs[r];
         const KParams& k = L.kp;
@@ -910,8 +1057,8 @@ struct Engine {
         auto t0 = std::chrono::steady_clock::now();
         volatile HostCtl* ctl = nullptr;
         unsigned long long handled = 0;
-        const bool sync_dump = g_opt.sync_dump || std::getenv("PC_SYNC_DUMP") || host_like || L.kp.clustering;  // these runs return to the host at every update anyway
-        if (host_like) host_generate_live_points();
+        const bool sync_dump = g_opt.sync_dump || std::getenv("PC_SYNC_DUMP") || host_like || L.kp.clustering || g_resume.write;  // these runs return to the host at every update anyway
+        if (host_like && !resumed) host_generate_live_points();
         const bool want_files = g_files.enabled && nruns == 1;
         const bool dumping = (dumper != nullptr || want_files) && nruns == 1;
         if (dumping && !sync_dump) {  // asynchronous dumper hand-over
@@ -926,7 +1073,7 @@ struct Engine {
             h.buf.ctl = dctl;
             upload_bufs();
         }
-        L.kp.want_dump = dumping ? 1 : 0;
+        L.kp.want_dump = (dumping || (g_resume.write && nruns == 1)) ? 1 : 0;
         double dbg_service_ms = 0, dbg_launch_ms = 0, dbg_finish_ms = 0, dbg_final_ms = 0;
         auto now = [] { return std::chrono::steady_clock::now(); };
         auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
@@ -939,7 +1086,7 @@ struct Engine {
             ctl->ack_seq = handled;
             dbg_service_ms += ms_since(ts);
         };
-        for (;;) {
+        for (; !resumed_finished;) {
             if (ctl) {  // size the pinned staging now: (re)allocating pinned memory synchronises with the running kernel
                 g_pin_dead.need((size_t)runs[0].buf.cap_dead * (L.kp.cp.T + 1) * 8);
                 g_pin_live.need((size_t)L.kp.n * L.kp.cp.T * 8);
@@ -964,15 +1111,22 @@ struct Engine {
                 int stt = runs[r].host_st.status;
                 if (stt == ST_ERROR) throw std::runtime_error("polychord_b200: could not generate live points (likelihood <= logzero everywhere?)");
                 if (stt == ST_DUMP && ctl) throw std::runtime_error("polychord_b200: run aborted");
-                if (stt == ST_DUMP)  // sync_dump: the kernel left at the update, dump and relaunch
-                    dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, runs[r].live.p, stream,
-                         runs[r].host_st.nlike);
+                if (stt == ST_DUMP) {  // sync_dump: the kernel left at the update, dump and relaunch
+                    if (dumping)
+                        dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, runs[r].live.p, stream,
+                             runs[r].host_st.nlike);
+                    write_resume(false);
+                }
+                if (g_abort) throw std::runtime_error("polychord_b200: run aborted by a host callback (pc_request_abort)");
                 if (stt == ST_HOSTCHAINS) host_chains();
                 if (stt == ST_CLUSTER) {  // the update left for the clustering pass; the dump of this update happens here too
                     if (dumping)
                         dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, runs[r].live.p, stream,
                              runs[r].host_st.nlike);
                     cluster_pass();
+                    PC_CUDA(cudaMemcpyAsync(&runs[r].host_st.ncl, &runs[r].st.p->ncl, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                    PC_CUDA(cudaStreamSynchronize(stream));
+                    write_resume(false);
                 }
                 if (stt == ST_NEED_DEAD || stt == ST_NEED_PHANTOM) { grow(r, stt); regrow = true; }
                 if (stt != ST_DONE) all_done = false;
@@ -986,7 +1140,8 @@ struct Engine {
             for (int r = 0; r < nruns; ++r)
                 dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, nullptr, stream,
                      runs[r].host_st.nlike, true);
-        if (want_files) write_prior_info(g_files, L.kp.n, runs[0].host_st.init_attempts);
+        if (want_files && !resumed) write_prior_info(g_files, L.kp.n, runs[0].host_st.init_attempts);
+        if (!resumed_finished) write_resume(true);
         dbg_final_ms = ms_since(tfin);
         if (std::getenv("PC_DEBUG")) {
             std::fprintf(stderr, "[pc dbg dump] copies %.3f ms, rows %.3f ms, weights %.3f ms, user dumper %.3f ms\n", g_dbg_dump[0],
@@ -1077,6 +1232,7 @@ int pc_set_option(const char* name, double value) {
     else if (s == "sync_dump") g_opt.sync_dump = (int)value;
     else if (s == "cap_dead0") g_opt.cap_dead0 = (long long)value;
     else if (s == "cap_ph0") g_opt.cap_ph0 = (long long)value;
+    else if (s == "resume_interval") g_resume.min_interval_s = value;
     else return -1;
     return 0;
 }
@@ -1093,10 +1249,21 @@ double pc_get_option(const char* name) {
     if (s == "sync_dump") return g_opt.sync_dump;
     if (s == "cap_dead0") return (double)g_opt.cap_dead0;
     if (s == "cap_ph0") return (double)g_opt.cap_ph0;
+    if (s == "resume_interval") return g_resume.min_interval_s;
     return NAN;
 }
 void pc_set_stream(void* cuda_stream) { g_stream = (cudaStream_t)cuda_stream; }
 void pc_request_abort(void) { g_abort = 1; }
+int pc_set_resume(const char* path, int write, int read) {
+    g_resume.write = write != 0 && path;
+    g_resume.read = read != 0 && path;
+    g_resume.path = path ? path : "";
+    if (g_resume.path.size() < 8 || g_resume.path.substr(g_resume.path.size() - 7) != ".resume") {
+        g_resume.write = g_resume.read = false;
+        return path ? -1 : 0;
+    }
+    return 0;
+}
 int pc_set_grades(int nGrade, const int* grade_dims, const int* grade_repeats) {
     if (nGrade < 0 || nGrade > MAX_GRADES) return -1;
     g_grade_dims.assign(grade_dims, grade_dims + nGrade);
@@ -1227,6 +1394,7 @@ void pc_uniform_prior(double* cube, double* theta, int nDims) {
 static int run_common(const pc_settings* s, const ModelSpec& ms, int nruns, const int* seeds, pc_dumper_t dumper,
                       pc_run_info* out) {
     std::lock_guard<std::mutex> lk(g_mu);
+    g_abort = 0;
     auto t0 = std::chrono::steady_clock::now();
     Engine e;
     e.setup(*s, ms, nruns, seeds);
@@ -1509,7 +1677,7 @@ void polychord_c_interface(pc_loglikelihood_t loglikelihood, pc_prior_t prior, p
                            pc_bool synchronous, int nDims, int nDerived, char* base_dir, char* file_root, int nGrade,
                            double* grade_frac, int* grade_dims, int n_nlives, double* loglikes, int* nlives, int seed,
                            int* comm) {
-    (void)write_resume; (void)write_paramnames; (void)read_resume; (void)maximise; (void)synchronous; (void)grade_frac;
+    (void)write_paramnames; (void)maximise; (void)synchronous; (void)grade_frac;
     (void)loglikes; (void)nlives; (void)comm; (void)nfail; (void)do_clustering;
     std::memset(&g_last, 0, sizeof(g_last));
     g_abort = 0;
@@ -1591,6 +1759,10 @@ void polychord_c_interface(pc_loglikelihood_t loglikelihood, pc_prior_t prior, p
         std::fclose(probe);
         std::remove((fo.base_dir + "/.pc_probe").c_str());
     }
+    struct ResumeGuard {
+        ResumeGuard(bool w, bool r, const std::string& path) { g_resume.write = w; g_resume.read = r; g_resume.path = path; }
+        ~ResumeGuard() { g_resume.write = g_resume.read = false; }
+    } resume_guard(write_resume, read_resume, fo.base_dir + "/" + fo.file_root + ".resume");
     struct FilesGuard {  // exception-transparent: a throwing dumper must not leave the next run writing files
         FilesGuard(const FileOpts& o) { g_files = o; g_fstate = FileState(); }
         ~FilesGuard() { g_files.enabled = false; }
