@@ -141,6 +141,53 @@ __global__ void pc_identify_kernel(const double* live, int T, int D, int n, cons
     }
 }
 
+// The same for nDims <= DCAP <= 32 with the roles swapped: a LANE owns a phantom (its coordinates in registers, zero
+// beyond nDims) and the warp walks the live table together, so one broadcast read of a live coordinate serves 32
+// distances -- 2.5x less shared-memory traffic than the warp-per-phantom form, which is what bounds that kernel.
+// The table rows are padded to DCAP with zeros (a zero difference leaves the fused multiply-add chain unchanged, so
+// every distance is still the same number).  Dynamic shared memory: n x (DCAP | 1) doubles.
+template <int DCAP>
+__global__ void pc_identify_lanes_kernel(const double* live, int T, int D, int n, const int* lab, const double* ph,
+                                         long long nph, int* phl) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int TS = DCAP | 1;
+    double* tab = (double*)smem;
+    for (int e = threadIdx.x; e < n * DCAP; e += blockDim.x) {
+        const int j = e / DCAP, k = e - j * DCAP;
+        tab[(size_t)j * TS + k] = k < D ? live[(size_t)j * T + k] : 0.0;
+    }
+    __syncthreads();
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nph; r += (long long)gridDim.x * blockDim.x) {
+        double x[DCAP];
+#pragma unroll
+        for (int k = 0; k < DCAP; ++k) x[k] = k < D ? ph[(size_t)r * T + k] : 0.0;
+        double bd = INFINITY;
+        int bj = 0;
+        int j = 0;
+        for (; j + 4 <= n; j += 4) {   // four live points in flight
+            const double* q = tab + (size_t)j * TS;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int k = 0; k < DCAP; ++k) {
+                const double d0 = x[k] - q[k], d1 = x[k] - q[TS + k], d2 = x[k] - q[2 * TS + k], d3 = x[k] - q[3 * TS + k];
+                s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
+            }
+            if (s0 < bd) { bd = s0; bj = j; }          // slots ascend: the first minimum is the lowest slot
+            if (s1 < bd) { bd = s1; bj = j + 1; }
+            if (s2 < bd) { bd = s2; bj = j + 2; }
+            if (s3 < bd) { bd = s3; bj = j + 3; }
+        }
+        for (; j < n; ++j) {
+            const double* q = tab + (size_t)j * TS;
+            double s0 = 0.0;
+#pragma unroll
+            for (int k = 0; k < DCAP; ++k) { const double d0 = x[k] - q[k]; s0 = fma(d0, d0, s0); }
+            if (s0 < bd) { bd = s0; bj = j; }
+        }
+        phl[r] = lab[bj];
+    }
+}
+
 // calculate_covmats (run_time_info.f90:601-641) per cluster, first half: CTA (p, c) forms the moment matrix
 // M = sum z z^T, z = [x - pivot, 1], of the records of chunk c (live slots, then the phantom pool) labelled p, on
 // the FP64 tensor cores exactly as phase U does (pc_run_kernel.cuh), warps combined in warp order, and writes it

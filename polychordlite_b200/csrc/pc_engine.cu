@@ -950,11 +950,36 @@ struct Engine {
             const int W = 8;
             if (nph > 0) {
                 const int WI = 16;
-                const bool tab = live_table_bytes(n, D) + (size_t)WI * D * 8 <= 200 * 1024;
-                const size_t ism = (size_t)WI * D * 8 + (tab ? live_table_bytes(n, D) : 0);
-                const int blocks = (int)std::min<long long>((nph + WI - 1) / WI, tab ? 148LL : 148LL * 8);
-                PC_CUDA(cudaFuncSetAttribute(pc_identify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism));
-                pc_identify_kernel<<<blocks, WI * 32, ism, stream>>>(h.live.p, T, D, n, h.lab.p, ph, nph, phl, tab ? 1 : 0);
+                // register tile of the lane-per-phantom kernel: nDims rounded up to 2 (to 4 above 16); 0 = too wide
+                const int dcap = D <= 16 ? ((D + 1) & ~1) : (D <= 32 ? ((D + 3) & ~3) : 0);
+                const size_t lsm = dcap ? (size_t)n * (dcap | 1) * 8 : 0;
+                if (dcap && lsm <= 200 * 1024) {  // a lane per phantom, the live table in shared memory
+                    const int blocks = (int)std::min<long long>((nph + 255) / 256, 148LL);
+                    auto launch = [&](auto kern) {
+                        PC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+                        kern<<<blocks, 256, lsm, stream>>>(h.live.p, T, D, n, h.lab.p, ph, nph, phl);
+                    };
+                    switch (dcap) {
+                        case 2: launch(pc_identify_lanes_kernel<2>); break;
+                        case 4: launch(pc_identify_lanes_kernel<4>); break;
+                        case 6: launch(pc_identify_lanes_kernel<6>); break;
+                        case 8: launch(pc_identify_lanes_kernel<8>); break;
+                        case 10: launch(pc_identify_lanes_kernel<10>); break;
+                        case 12: launch(pc_identify_lanes_kernel<12>); break;
+                        case 14: launch(pc_identify_lanes_kernel<14>); break;
+                        case 16: launch(pc_identify_lanes_kernel<16>); break;
+                        case 20: launch(pc_identify_lanes_kernel<20>); break;
+                        case 24: launch(pc_identify_lanes_kernel<24>); break;
+                        case 28: launch(pc_identify_lanes_kernel<28>); break;
+                        default: launch(pc_identify_lanes_kernel<32>); break;
+                    }
+                } else {
+                    const bool tab = live_table_bytes(n, D) + (size_t)WI * D * 8 <= 200 * 1024;
+                    const size_t ism = (size_t)WI * D * 8 + (tab ? live_table_bytes(n, D) : 0);
+                    const int blocks = (int)std::min<long long>((nph + WI - 1) / WI, tab ? 148LL : 148LL * 8);
+                    PC_CUDA(cudaFuncSetAttribute(pc_identify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism));
+                    pc_identify_kernel<<<blocks, WI * 32, ism, stream>>>(h.live.p, T, D, n, h.lab.p, ph, nph, phl, tab ? 1 : 0);
+                }
                 PC_CUDA(cudaGetLastError());
             }
             if (!d_ccount.p) d_ccount.alloc(MAX_CLUSTERS);
