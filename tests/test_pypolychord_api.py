@@ -114,8 +114,11 @@ def test_legacy_run_polychord(gpu, tmp_path):
 
 @pytest.mark.gpu
 def test_unsupported_configuration_raises(gpu, tmp_path):
-    with pytest.raises(RuntimeError):
-        pypolychord.run(Gaussian(), nDims, base_dir=str(tmp_path), grade_dims=[1, 3], **KW)   # fast/slow grades
+    with pytest.raises(RuntimeError):   # dynamic nlive schedules are reported, not silently ignored
+        pypolychord.run(Gaussian(), nDims, base_dir=str(tmp_path), nlives={-10.0: 400}, **KW)
+    ns = pypolychord.run(Gaussian(mu=0.0, sigma=0.1), nDims, prior=UniformPrior(-1, 1), base_dir=str(tmp_path),
+                         grade_dims=[1, 3], seed=1, **KW)                                # fast/slow grades run
+    assert ns.info["nslices"] == 2 * KW["num_repeats"] * ns.info["nchains"]
 
 
 @pytest.mark.gpu
