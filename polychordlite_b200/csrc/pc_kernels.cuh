@@ -69,7 +69,7 @@ struct DevRun {
     // representative chain warp; phase U of CTA 0: [2] pass A, [3] barrier, [4] pass B ([12] its set-up, [13] its tile
     // loop, [15] the warps' combination), [5] closing barrier; phase S1: [6] keys, [7] termination test, [8] sort +
     // merge, [9] publication; the first chain CTA: [10] wait at the generation barrier, [11] release -> first slice
-    long long dbg[16];
+    long long dbg[20];
     unsigned int bar;    // group barrier, one arrival per CTA (monotonic)
     unsigned int wbar;   // chains-done barrier, one arrival per warp (monotonic)
 };
@@ -315,6 +315,36 @@ __device__ __forceinline__ void block_exscan_affine(double a, double b, double& 
     // exclusive = (warps before) then (lanes before)
     affine_combine(pa, pb, wa, wb);
     exa = pa; exb = pb; tota = ta; totb = tb;
+}
+
+// The same sort when every thread holds one element (np2 <= blockDim.x): the exchanges at distance < 32 are warp
+// shuffles, only the ones across warps go through shared memory (6 instead of 36 barrier-separated steps at 256).
+__device__ inline void block_sort_small(double* key, int* val, int np2) {
+    const int i = threadIdx.x;
+    double mk = i < np2 ? key[i] : INFINITY;
+    int mv = i < np2 ? val[i] : 0x7fffffff;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            double ok;
+            int ov;
+            if (j < 32) {
+                ok = __shfl_xor_sync(FULL, mk, j);
+                ov = __shfl_xor_sync(FULL, mv, j);
+            } else {
+                if (i < np2) { key[i] = mk; val[i] = mv; }
+                __syncthreads();
+                ok = i < np2 ? key[i ^ j] : INFINITY;
+                ov = i < np2 ? val[i ^ j] : 0x7fffffff;
+                __syncthreads();
+            }
+            const bool keep_min = ((i & k) == 0) == ((i & j) == 0);
+            const bool other_less = ok < mk || (ok == mk && ov < mv);
+            if (keep_min == other_less) { mk = ok; mv = ov; }
+        }
+    }
+    if (i < np2) { key[i] = mk; val[i] = mv; }
+    __syncthreads();
 }
 
 // bitonic sort of (key, val) ascending by key then val; np2 a power of two

@@ -160,7 +160,7 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
     }
     long long q2 = clock64();
     if (merge && more) {
-        block_sort(sm.bkey, sm.bval, npB);
+        if (npB <= (int)blockDim.x) block_sort_small(sm.bkey, sm.bval, npB); else block_sort(sm.bkey, sm.bval, npB);
         // rank of a survivor = its index + number of babies before it; rank of a baby = its index + number of
         // survivors before it ((key, slot) pairs are distinct, so the merged order is the sorted order)
         for (int i = tid; i < m; i += nthr) {
@@ -481,6 +481,7 @@ __device__ inline void phase_UB(const KParams& p, const RunBuf& rb, DevRun* st, 
 __device__ inline bool finish_update(const KParams& p, const RunBuf& rb, DevRun* st, int NG, double* s_cov, double* s_L) {
     const int tid = threadIdx.x, D = p.cp.D, ntri = p.ntri;
     const long long tot = st->ph_kept;
+    const long long f0 = clock64();
     __shared__ int s_ok;
     __shared__ double s_N;
     auto unpack = [](int idx, int& ai, int& bi) {
@@ -506,6 +507,7 @@ __device__ inline bool finish_update(const KParams& p, const RunBuf& rb, DevRun*
             for (int q = 0; q < p.sh.world; ++q) p.sh.xpart[q][(size_t)p.sh.rank * p.sh.xstride + 2 + e] = s;
         } else if (e < D) s_d[e] = s; else s_S2[e - D] = s;
     }
+    const long long f1 = clock64();
     double Nglob = (double)tot;  // surviving phantoms of all ranks
     if (p.sh.world > 1) {
         if (tid == 0)
@@ -547,11 +549,14 @@ __device__ inline bool finish_update(const KParams& p, const RunBuf& rb, DevRun*
         s_cov[bi + ai * D] = v;
     }
     __syncthreads();
+    const long long f2 = clock64();
     int fb = 0;
     if (tid < 32) fb = warp_cholesky(s_cov, s_L, D);  // calc_cholesky (utils.F90:621-649) in shared memory
     __syncthreads();
     for (int e = tid; e < D * D; e += blockDim.x) { rb.cov[e] = s_cov[e]; rb.chol[e] = s_L[e]; }
     if (tid == 0) {
+        const long long f3 = clock64();
+        st->dbg[16] += f1 - f0; st->dbg[17] += f2 - f1; st->dbg[18] += f3 - f2;
         rb.gsum[0] = Nglob;
         st->chol_fallback += fb;
         st->cov_N = N;
@@ -687,6 +692,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
     unsigned pair_seq = 0;  // paired mode: chains this warp pair has run since the launch (buffer parity)
     bool scatter_due = false;  // sharded run: the last babies of the generation are still in the incoming buffer
     bool s2_due = false;  // CTA 0: the evidence of the generation in flight is still to be accumulated
+    long long chol_epoch = -1;  // st->nupdates when this CTA last loaded the Cholesky factor into shared memory
 
     if (p.host_like && vload(&st->host_resume)) {
         // host-callback run: the host loop ran the chains of the generation in flight; finish the generation
@@ -781,8 +787,14 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
         const bool clustered = p.clustering && vload(&st->ncl) > 1;
         const int* order = rb.order + vload(&st->order_off);
         double* pool = rb.ph[vload(&st->cur_pool)];
-        for (int e = tid; e < D * D; e += blockDim.x) s_chol[e] = __ldcg(rb.chol + e);
-        __syncthreads();
+        {   // the Cholesky factor only changes at an update: reload it then (CTA 0 also uses the area as scratch)
+            const long long nup = vload(&st->nupdates);
+            if (cta == 0 || nup != chol_epoch) {
+                for (int e = tid; e < D * D; e += blockDim.x) s_chol[e] = __ldcg(rb.chol + e);
+                __syncthreads();
+                chol_epoch = nup;
+            }
+        }
         unsigned long long nlike = 0, nfail = 0;
         const int m = n - K;
         // sharded run: the last babies go to the incoming buffers (by generation parity) instead of the live slots
