@@ -60,9 +60,11 @@ void polychord_c_interface(
     double* grade_frac, int* grade_dims, int n_nlives, double* loglikes, int* nlives, int seed,
     int* comm);
 
-/* Replaces src/polychord/interfaces.F90:496-519 (decl. interfaces.h:47-56).  The .ini driver
- * path is outside the hot-path scope ("next" row f4): the symbol exists so
- * that the reference facade links, and reports "unsupported" through the error convention. */
+/* Replaces src/polychord/interfaces.F90:496-519 (decl. interfaces.h:47-56): settings, parameters and priors are read
+ * from the .ini file (src/polychord/ini.f90 format: "key = value" lines, "P : name | latex | speed | prior type |
+ * block | params", "D : name | latex"), setup_loglikelihood() is called once, then the run proceeds as through
+ * polychord_c_interface.  Prior types: uniform, log_uniform, power_uniform, gaussian, half_gaussian, exponential
+ * (priors.f90:40-174); the sorted / adaptive families and dynamic nlive schedules are reported as unsupported. */
 void polychord_c_interface_ini(pc_loglikelihood_t loglikelihood, void (*setup_loglikelihood)(void),
                                char* inifile, int* comm);
 

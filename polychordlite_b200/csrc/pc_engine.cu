@@ -21,6 +21,7 @@
 #include "../../include/polychord_b200.h"
 #include "pc_probes.cuh"
 #include "pc_files.h"
+#include "pc_ini.h"
 #include "pc_hostchain.cuh"
 #include "pc_cluster.cuh"
 #include "pc_shapes.h"
@@ -1809,10 +1810,53 @@ void polychord_c_interface(pc_loglikelihood_t loglikelihood, pc_prior_t prior, p
     }
 }
 
+static IniConfig g_ini;   // the .ini run in flight: its prior transform is reached through a plain C callback
+static void ini_prior_callback(double* cube, double* theta, int nDims) {
+    (void)nDims;
+    ini_prior_transform(g_ini, cube, theta);
+}
+static void ini_noop_dumper(int, int, int, double*, double*, double*, double, double) {}
+
+// Replaces interfaces.F90:496-519 + the generic run_polychord_ini path (:142-283): settings, parameters and priors
+// come from the file (ini.f90), setup_loglikelihood() is called once, then the run goes through
+// polychord_c_interface.  A likelihood pointer registered with a device form together with all-uniform priors runs
+// on the GPU; anything else takes the host-callback path with the file's prior transform.
 void polychord_c_interface_ini(pc_loglikelihood_t loglikelihood, void (*setup_loglikelihood)(void), char* inifile,
                                int* comm) {
-    (void)loglikelihood; (void)setup_loglikelihood; (void)inifile; (void)comm;
-    fail(-6, "polychord_c_interface_ini: the .ini driver path is outside the B200 engine's scope (SURVEY.md section 8 row f4)");
+    try {
+        g_ini = parse_ini(inifile ? std::string(inifile) : std::string());
+    } catch (const std::exception& ex) {
+        fail(-6, ex.what());
+        return;
+    }
+    if (setup_loglikelihood) setup_loglikelihood();
+    const int D = (int)g_ini.params.size(), P = (int)g_ini.derived.size();
+    bool all_uniform = true;
+    std::vector<double> box(2 * D);
+    for (int i = 0; i < D; ++i) {
+        all_uniform = all_uniform && g_ini.params[i].prior_type == 1;
+        box[i] = g_ini.params[i].params[0];
+        box[D + i] = g_ini.params[i].params[1];
+    }
+    if (all_uniform) pc_register_device_prior(ini_prior_callback, PC_PRIOR_UNIFORM, box.data(), 2 * D);
+    else prior_registry().erase((void*)ini_prior_callback);
+    if (g_ini.write_paramnames) {  // write_paramnames_file, read_write.F90:963-1011: "<name>   <latex>", derived names starred
+        FILE* f = std::fopen((g_ini.base_dir + "/" + g_ini.file_root + ".paramnames").c_str(), "w");
+        if (f) {
+            for (const auto& p : g_ini.params) std::fprintf(f, "%s   %s\n", p.name.c_str(), p.latex.c_str());
+            for (const auto& d : g_ini.derived) std::fprintf(f, "%s*   %s\n", d.first.c_str(), d.second.c_str());
+            std::fclose(f);
+        }
+    }
+    std::vector<char> base(g_ini.base_dir.begin(), g_ini.base_dir.end()), root(g_ini.file_root.begin(), g_ini.file_root.end());
+    base.push_back(0); root.push_back(0);
+    polychord_c_interface(loglikelihood, ini_prior_callback, ini_noop_dumper, g_ini.nlive, g_ini.num_repeats, g_ini.nprior,
+                          g_ini.nfail, g_ini.do_clustering, g_ini.feedback, g_ini.precision_criterion, g_ini.logzero,
+                          g_ini.max_ndead, g_ini.boost_posterior, g_ini.posteriors, g_ini.equals, g_ini.cluster_posteriors,
+                          g_ini.write_resume, false, g_ini.read_resume, g_ini.write_stats, g_ini.write_live, g_ini.write_dead,
+                          g_ini.write_prior, g_ini.maximise, g_ini.compression_factor, true, D, P, base.data(), root.data(),
+                          (int)g_ini.grade_dims.size(), g_ini.grade_frac.data(), g_ini.grade_dims.data(), 0, nullptr, nullptr,
+                          g_ini.seed, comm);
 }
 
 }  // extern "C"

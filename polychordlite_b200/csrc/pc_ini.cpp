@@ -1,0 +1,196 @@
+// pc_ini.cpp -- the .ini driver path behind polychord_c_interface_ini.
+//
+// Replaces src/polychord/ini.f90 (read_params :44-95, get_string :149-224, get_params :354-458, get_prior_params
+// :470-497) and the separable transforms of src/polychord/priors.f90 (uniform :40, gaussian :73, log_uniform :114,
+// power_uniform :140, half_gaussian :155, exponential :166).  Host-only.
+#include "pc_ini.h"
+
+#include <algorithm>
+#include <cmath>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+
+#include "pc_device.cuh"  // inv_normal_cdf (AS241), host-callable
+
+namespace pc {
+namespace {
+
+std::string trim(const std::string& s) {
+    const size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+    return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+}
+
+// get_string (ini.f90:149-224): lines containing a comment character anywhere are skipped, the key is what stands
+// before the first '=' or ':', the value what follows it; ith selects the ith match (1-based)
+struct IniFile {
+    std::vector<std::pair<std::string, std::string>> entries;
+    explicit IniFile(const std::string& path) {
+        std::ifstream f(path);
+        if (!f) throw std::invalid_argument("ini error: " + path + " does not exist");
+        std::string line;
+        while (std::getline(f, line)) {
+            if (line.find_first_of("#!") != std::string::npos) continue;
+            const size_t eq = line.find_first_of("=:");
+            if (eq == std::string::npos) continue;
+            entries.emplace_back(trim(line.substr(0, eq)), trim(line.substr(eq + 1)));
+        }
+    }
+    std::string get(const std::string& key, int ith = 1) const {
+        int c = 0;
+        for (const auto& e : entries)
+            if (e.first == key && ++c == ith) return e.second;
+        return std::string();
+    }
+    int get_int(const std::string& key, int dflt, bool required = false) const {
+        const std::string v = get(key);
+        if (v.empty()) {
+            if (required) throw std::invalid_argument("ini error: '" + key + "' is missing");
+            return dflt;
+        }
+        return std::stoi(v);
+    }
+    double get_double(const std::string& key, double dflt) const {
+        const std::string v = get(key);
+        return v.empty() ? dflt : std::stod(v);
+    }
+    bool get_logical(const std::string& key, bool dflt) const {  // Fortran list-directed logical: T / F / .true. / .false.
+        std::string v = get(key);
+        if (v.empty()) return dflt;
+        size_t i = 0;
+        if (v[0] == '.') i = 1;
+        const char c = i < v.size() ? v[i] : 'f';
+        return c == 'T' || c == 't';
+    }
+    std::vector<double> get_doubles(const std::string& key) const {
+        std::vector<double> out;
+        std::istringstream is(get(key));
+        double v;
+        while (is >> v) out.push_back(v);
+        return out;
+    }
+};
+
+std::vector<std::string> split_bar(const std::string& s) {
+    std::vector<std::string> out;
+    std::string cur;
+    for (char c : s) {
+        if (c == '|') { out.push_back(trim(cur)); cur.clear(); } else cur += c;
+    }
+    out.push_back(trim(cur));
+    return out;
+}
+
+int prior_type_from_string(const std::string& s) {  // priors.f90:620-668
+    static const char* names[] = {"", "uniform", "log_uniform", "power_uniform", "gaussian", "half_gaussian", "exponential",
+                                  "sorted_uniform", "sorted_gaussian", "sorted_half_gaussian", "sorted_exponential",
+                                  "adaptive_sorted_uniform", "adaptive_sorted_gaussian", "adaptive_sorted_half_gaussian",
+                                  "adaptive_sorted_exponential", "nn_adaptive_layer_gaussian"};
+    for (int i = 1; i < 16; ++i)
+        if (s == names[i]) return i;
+    return 0;
+}
+
+}  // namespace
+
+IniConfig parse_ini(const std::string& path) {
+    const IniFile f(path);
+    IniConfig c;
+    c.nlive = f.get_int("nlive", 0, true);                       // read_params, ini.f90:56-88
+    c.num_repeats = f.get_int("num_repeats", 0, true);
+    c.nprior = f.get_int("nprior", -1);
+    c.nfail = f.get_int("nfail", -1);
+    c.do_clustering = f.get_logical("do_clustering", false);
+    c.feedback = f.get_int("feedback", 1);
+    c.precision_criterion = f.get_double("precision_criterion", 1e-3);
+    c.logzero = f.get_double("logzero", -1e30);
+    c.max_ndead = f.get_int("max_ndead", -1);
+    c.boost_posterior = f.get_double("boost_posterior", 0.0);
+    c.posteriors = f.get_logical("posteriors", false);
+    c.equals = f.get_logical("equals", false);
+    c.cluster_posteriors = f.get_logical("cluster_posteriors", false);
+    c.write_resume = f.get_logical("write_resume", false);
+    c.write_paramnames = f.get_logical("write_paramnames", false);
+    c.read_resume = f.get_logical("read_resume", false);
+    c.write_stats = f.get_logical("write_stats", true);
+    c.write_live = f.get_logical("write_live", false);
+    c.write_dead = f.get_logical("write_dead", true);
+    c.write_prior = f.get_logical("write_prior", false);
+    c.maximise = f.get_logical("maximise", false);
+    c.compression_factor = f.get_double("compression_factor", std::exp(-1.0));
+    c.base_dir = f.get("base_dir").empty() ? "chains" : f.get("base_dir");
+    c.file_root = f.get("file_root").empty() ? "test" : f.get("file_root");
+    c.seed = f.get_int("seed", -1);
+    c.grade_frac = f.get_doubles("grade_frac");
+    if (c.grade_frac.empty()) c.grade_frac.assign(1, 1.0);
+    if (!f.get("nlives").empty() || !f.get("loglikes").empty())
+        throw std::invalid_argument("ini error: dynamic nlive schedules (nlives / loglikes) are not supported by the B200 engine");
+    // get_params, ini.f90:354-458:  P : name | latex | speed | prior type | prior block | prior params
+    for (int i = 1;; ++i) {
+        const std::string line = f.get("P", i);
+        if (line.empty()) break;
+        const std::vector<std::string> el = split_bar(line);
+        if (el.size() < 6) throw std::invalid_argument("ini error: parameter line needs 6 fields: " + line);
+        IniParam p;
+        p.name = el[0];
+        const size_t star = p.name.find('*');   // sub-clustering marker (ini.f90:376): accepted, not used
+        if (star != std::string::npos) p.name = p.name.substr(0, star);
+        p.latex = el[1];
+        p.speed = std::stoi(el[2]);
+        p.prior_type = prior_type_from_string(el[3]);
+        if (p.prior_type == 0) throw std::invalid_argument("get_priors error: Unknown prior type for parameter " + p.name);
+        if (p.prior_type > 6)
+            throw std::invalid_argument("ini error: prior type '" + el[3] + "' of parameter " + p.name +
+                                        " (sorted / adaptive families, priors.f90:242-488) is not supported by the B200 engine");
+        p.block = std::stoi(el[4]);
+        std::istringstream is(el[5]);
+        double v;
+        while (is >> v) p.params.push_back(v);
+        const size_t need = p.prior_type == 3 ? 3 : (p.prior_type == 6 ? 1 : 2);
+        if (p.params.size() < need) throw std::invalid_argument("ini error: too few prior parameters for " + p.name);
+        c.params.push_back(p);
+    }
+    if (c.params.empty()) throw std::invalid_argument("ini error: no parameters (P : ...) in " + path);
+    for (int i = 1;; ++i) {
+        const std::string line = f.get("D", i);
+        if (line.empty()) break;
+        const std::vector<std::string> el = split_bar(line);
+        c.derived.push_back({el[0], el.size() > 1 ? el[1] : el[0]});
+    }
+    // grades: the parameters' speeds, slowest first (create_priors, priors.f90:671-749, orders them so; this driver
+    // asks for them in that order)
+    for (size_t i = 1; i < c.params.size(); ++i)
+        if (c.params[i].speed < c.params[i - 1].speed)
+            throw std::invalid_argument("ini error: list the parameters in order of increasing speed (grade)");
+    for (size_t i = 0; i < c.params.size(); ++i) {
+        if (i == 0 || c.params[i].speed != c.params[i - 1].speed) c.grade_dims.push_back(0);
+        c.grade_dims.back() += 1;
+    }
+    if (c.grade_frac.size() != c.grade_dims.size()) {
+        if (c.grade_frac.size() == 1) c.grade_frac.assign(c.grade_dims.size(), c.grade_frac[0]);
+        else throw std::invalid_argument("ini error: grade_frac needs one entry per parameter speed");
+    }
+    return c;
+}
+
+void ini_prior_transform(const IniConfig& c, const double* cube, double* theta) {
+    for (size_t i = 0; i < c.params.size(); ++i) {
+        const IniParam& p = c.params[i];
+        const double u = cube[i];
+        const double* q = p.params.data();
+        switch (p.prior_type) {
+            case 1: theta[i] = q[0] + (q[1] - q[0]) * u; break;                       // uniform_htp, priors.f90:40-55
+            case 2: theta[i] = q[0] * std::pow(q[1] / q[0], u); break;                 // log_uniform_htp, :114-124
+            case 3: {                                                                  // power_uniform_htp, :140-153
+                const double a = std::pow(q[0], 1.0 / q[2]), b = std::pow(q[1], 1.0 / q[2]);
+                theta[i] = std::pow(a - u * std::fabs(a - b), q[2]);
+                break;
+            }
+            case 4: theta[i] = q[0] + q[1] * inv_normal_cdf(u); break;                 // gaussian_htp, :73-85
+            case 5: theta[i] = q[0] + q[1] * inv_normal_cdf(0.5 + 0.5 * u); break;     // half_gaussian_htp, :155-164
+            default: theta[i] = -std::log(1.0 - u) / q[0]; break;                      // exponential_htp, :166-174
+        }
+    }
+}
+
+}  // namespace pc
