@@ -139,14 +139,14 @@ IniConfig parse_ini(const std::string& path) {
         p.speed = std::stoi(el[2]);
         p.prior_type = prior_type_from_string(el[3]);
         if (p.prior_type == 0) throw std::invalid_argument("get_priors error: Unknown prior type for parameter " + p.name);
-        if (p.prior_type > 6)
+        if (p.prior_type > 10)
             throw std::invalid_argument("ini error: prior type '" + el[3] + "' of parameter " + p.name +
-                                        " (sorted / adaptive families, priors.f90:242-488) is not supported by the B200 engine");
+                                        " (adaptive families, priors.f90:300-488) is not supported by the B200 engine");
         p.block = std::stoi(el[4]);
         std::istringstream is(el[5]);
         double v;
         while (is >> v) p.params.push_back(v);
-        const size_t need = p.prior_type == 3 ? 3 : (p.prior_type == 6 ? 1 : 2);
+        const size_t need = p.prior_type == 3 ? 3 : ((p.prior_type == 6 || p.prior_type == 10) ? 1 : 2);
         if (p.params.size() < need) throw std::invalid_argument("ini error: too few prior parameters for " + p.name);
         c.params.push_back(p);
     }
@@ -173,23 +173,40 @@ IniConfig parse_ini(const std::string& path) {
     return c;
 }
 
-void ini_prior_transform(const IniConfig& c, const double* cube, double* theta) {
-    for (size_t i = 0; i < c.params.size(); ++i) {
-        const IniParam& p = c.params[i];
-        const double u = cube[i];
-        const double* q = p.params.data();
-        switch (p.prior_type) {
-            case 1: theta[i] = q[0] + (q[1] - q[0]) * u; break;                       // uniform_htp, priors.f90:40-55
-            case 2: theta[i] = q[0] * std::pow(q[1] / q[0], u); break;                 // log_uniform_htp, :114-124
-            case 3: {                                                                  // power_uniform_htp, :140-153
-                const double a = std::pow(q[0], 1.0 / q[2]), b = std::pow(q[1], 1.0 / q[2]);
-                theta[i] = std::pow(a - u * std::fabs(a - b), q[2]);
-                break;
-            }
-            case 4: theta[i] = q[0] + q[1] * inv_normal_cdf(u); break;                 // gaussian_htp, :73-85
-            case 5: theta[i] = q[0] + q[1] * inv_normal_cdf(0.5 + 0.5 * u); break;     // half_gaussian_htp, :155-164
-            default: theta[i] = -std::log(1.0 - u) / q[0]; break;                      // exponential_htp, :166-174
+static double separable_htp(int type, const double* q, double u) {
+    switch (type) {
+        case 1: return q[0] + (q[1] - q[0]) * u;                       // uniform_htp, priors.f90:40-55
+        case 2: return q[0] * std::pow(q[1] / q[0], u);                 // log_uniform_htp, :114-124
+        case 3: {                                                       // power_uniform_htp, :140-153
+            const double a = std::pow(q[0], 1.0 / q[2]), b = std::pow(q[1], 1.0 / q[2]);
+            return std::pow(a - u * std::fabs(a - b), q[2]);
         }
+        case 4: return q[0] + q[1] * inv_normal_cdf(u);                 // gaussian_htp, :73-85
+        case 5: return q[0] + q[1] * inv_normal_cdf(0.5 + 0.5 * u);     // half_gaussian_htp, :155-164
+        default: return -std::log(1.0 - u) / q[0];                      // exponential_htp, :166-174
+    }
+}
+
+void ini_prior_transform(const IniConfig& c, const double* cube, double* theta) {
+    const size_t n = c.params.size();
+    for (size_t i = 0; i < n;) {
+        const IniParam& p = c.params[i];
+        if (p.prior_type <= 6) {
+            theta[i] = separable_htp(p.prior_type, p.params.data(), cube[i]);
+            ++i;
+            continue;
+        }
+        // sorted families (priors.f90:242-298): the block's coordinates go through sort_hypercube (:190-200), which maps
+        // the unit cube onto its ordered corner, then through the separable transform of the same name
+        size_t j = i;
+        while (j < n && c.params[j].prior_type == p.prior_type && c.params[j].block == p.block) ++j;
+        const size_t m = j - i;
+        std::vector<double> srt(m);
+        srt[m - 1] = std::pow(cube[i + m - 1], 1.0 / (double)m);
+        for (size_t k = m - 1; k-- > 0;) srt[k] = std::pow(cube[i + k], 1.0 / (double)(k + 1)) * srt[k + 1];
+        static const int base_type[] = {1, 4, 5, 6};   // sorted_uniform, sorted_gaussian, sorted_half_gaussian, sorted_exponential
+        for (size_t k = 0; k < m; ++k) theta[i + k] = separable_htp(base_type[p.prior_type - 7], c.params[i + k].params.data(), srt[k]);
+        i = j;
     }
 }
 

@@ -93,5 +93,23 @@ def test_ini_errors(gpu, tmp_path):
     info = _ini_call(gpu, gpu.lib().pc_gaussian_loglikelihood, tmp_path / "missing.ini")
     assert info.status == -6
     bad = tmp_path / "bad.ini"
-    bad.write_text(HEADER.format(nlive=50, R=4, seed=1, base=tmp_path, root="bad") + "P : a | a | 1 | sorted_uniform | 1 | 0 1\n")
+    bad.write_text(HEADER.format(nlive=50, R=4, seed=1, base=tmp_path, root="bad") + "P : a | a | 1 | adaptive_sorted_uniform | 1 | 0 1\n")
     assert _ini_call(gpu, gpu.lib().pc_gaussian_loglikelihood, bad).status == -6
+
+
+def test_ini_sorted_uniform_prior(gpu, tmp_path):
+    """sorted_uniform (priors.f90:262-270): the block's parameters come out ordered; with a flat likelihood the
+    posterior is the prior of three ordered uniforms on [0, 2]: means 0.5, 1.0, 1.5."""
+    def like(theta_p, nd, phi_p, nder):
+        th = np.ctypeslib.as_array(theta_p, shape=(nd,))
+        assert th[0] <= th[1] <= th[2]
+        return 0.0
+    cb = gpu.LL_CB(like)
+    text = HEADER.format(nlive=60, R=6, seed=3, base=tmp_path, root="srt").replace("precision_criterion = 0.001", "precision_criterion = 0.001\nmax_ndead = 600")
+    text += "".join(f"P : t{i} | t_{i} | 1 | sorted_uniform | 1 | 0.0 2.0\n" for i in range(3))
+    ini = tmp_path / "srt.ini"
+    ini.write_text(text)
+    info = _ini_call(gpu, cb, ini)
+    assert info.status == 0
+    out = PolyChordOutput(str(tmp_path), "srt")
+    assert np.allclose(out.means, [0.5, 1.0, 1.5], atol=0.12) and abs(out.logZ) < 0.2   # Z = 1 for a flat likelihood of 1
