@@ -452,8 +452,8 @@ struct Engine {
         if (hc_in) cudaFreeHost(hc_in);
     }
 
-    // GenerateLivePoints (generate.F90:153-183) with host callbacks: attempt a draws cube = U(TAG_INIT, a, dim) --
-    // the same counter-addressed numbers the device path uses -- and is kept when logL > logzero.
+    // GenerateLivePoints (generate.F90:153-183) with host callbacks: attempt a draws cube = U(TAG_INIT, a, dim) on the
+    // device -- the same counter-addressed numbers the device path uses -- and is kept when logL > logzero.
     void host_generate_live_points() {
         const KParams& k = L.kp;
         const int D = k.cp.D, P = k.cp.P, T = k.cp.T, n = k.n;
@@ -463,23 +463,33 @@ struct Engine {
         int have = 0;
         long long a = 0, nl = 0;
         const unsigned seed = runs[0].buf.seed;
+        DevArr<double> d_cubes((size_t)n * D);
+        std::vector<double> cubes((size_t)n * D);
         while (have < n) {
             if (a > 1000LL * n + 1000000LL) throw std::runtime_error("polychord_b200: could not generate live points (likelihood <= logzero everywhere?)");
-            for (int d = 0; d < D; ++d) cube[d] = uniform(seed, TAG_INIT, (unsigned long long)a, (unsigned)d, 0u);
-            ++a;
-            std::vector<double> c2(cube);
-            std::fill(phi.begin(), phi.end(), 0.0);
-            g_host_prior(c2.data(), theta.data(), D);
-            const double logL = g_host_ll(theta.data(), D, phi.data(), P);
-            if (!(logL > S.logzero)) continue;
-            ++nl;
-            double* rec = &live[(size_t)have * T];
-            std::copy(cube.begin(), cube.end(), rec);
-            std::copy(theta.begin(), theta.end(), rec + D);
-            for (int i = 0; i < P; ++i) rec[2 * D + i] = phi[i];
-            rec[2 * D + P] = S.logzero;  // born from the prior
-            rec[2 * D + P + 1] = logL;
-            ++have;
+            const int count = n - have;   // as many attempts as points are still missing, drawn on the device
+            hc_init_cubes_kernel<<<(count * D + 255) / 256, 256, 0, stream>>>(seed, a, count, D, d_cubes.p);
+            PC_CUDA(cudaGetLastError());
+            d_cubes.download(cubes.data(), (size_t)count * D, stream);
+            PC_CUDA(cudaStreamSynchronize(stream));
+            launches += 1;
+            for (int t = 0; t < count; ++t) {
+                std::copy(cubes.begin() + (size_t)t * D, cubes.begin() + (size_t)(t + 1) * D, cube.begin());
+                std::vector<double> c2(cube);
+                std::fill(phi.begin(), phi.end(), 0.0);
+                g_host_prior(c2.data(), theta.data(), D);
+                const double logL = g_host_ll(theta.data(), D, phi.data(), P);
+                if (!(logL > S.logzero)) continue;
+                ++nl;
+                double* rec = &live[(size_t)have * T];
+                std::copy(cube.begin(), cube.end(), rec);
+                std::copy(theta.begin(), theta.end(), rec + D);
+                for (int i = 0; i < P; ++i) rec[2 * D + i] = phi[i];
+                rec[2 * D + P] = S.logzero;  // born from the prior
+                rec[2 * D + P + 1] = logL;
+                ++have;
+            }
+            a += count;
         }
         h0.nlike = nl;
         h0.init_attempts = a;

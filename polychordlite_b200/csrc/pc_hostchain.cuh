@@ -189,6 +189,15 @@ __global__ void hc_step_kernel(const HcParams p) {
     if (lane == 0) p.ch[k] = c;
 }
 
+// GenerateLivePoints (generate.F90:153-183) for host callbacks: the cube coordinates of attempts a0 .. a0+count-1,
+// cube[a][d] = U(TAG_INIT, a, d) -- the numbers the device path draws in init_phase -- for the host to evaluate
+__global__ void hc_init_cubes_kernel(unsigned seed, long long a0, int count, int D, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count * D) return;
+    const int a = i / D, d = i - a * D;
+    out[i] = uniform(seed, TAG_INIT, (unsigned long long)(a0 + a), (unsigned)d, 0u);
+}
+
 // end of the generation: the evaluation count of the host callbacks joins the run's counters
 __global__ void hc_finish_kernel(DevRun* st, long long nlike_add, int resume) {
     st->nlike += nlike_add;
