@@ -417,6 +417,11 @@ def main():
                    "sample": f"{nruns} complete runs of the workload (seeds 0..{nruns - 1}), oracle reference schedule "
                              f"(1 death/iteration), 1 host thread of {os.cpu_count()}; {ct:.1f} s of CPU work",
                    "wall_time_to_logZ_s": ct / nruns}
+        # arithmetic roofline (north star): whole-evaluation flops of the workload's likelihood (SURVEY.md section 8d:
+        # 11 D Gaussian, 10 D + D cos Rastrigin) against the device's MEASURED FP64 FMA throughput
+        fp64_peak = capi.measure_fp64_tflops()
+        flops_per_eval = {"gaussian": 11.0 * D, "rastrigin": 11.0 * D}[w["like"]]
+        fp64_ach = value / world * flops_per_eval / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -444,6 +449,9 @@ def main():
                          "peak_source": which, "kernel": "pc_run_kernel<4,5,0>",
                          "note": "latency-bound persistent kernel; one run occupies ctas_per_run of 148 SMs; "
                                  "see 'ensemble' for the GPU filled with independent replicas"},
+            "arithmetic_roofline": {"bound": "fp64_fma", "achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s per GPU",
+                                    "frac": fp64_ach / fp64_peak if fp64_peak else None, "flops_per_eval": flops_per_eval,
+                                    "peak_source": "measured here (pc_measure_fp64_tflops: FMA microbenchmark)"},
             "cpu_baseline": cpu, "clocks": clocks, "ensemble": ens, "region_wall_s": t_region,
         }
         print(json.dumps(line), flush=True)

@@ -250,6 +250,10 @@ int pc_write_files(const char* base_dir, const char* file_root, int flags, int n
  * Returns the number of clusters. */
 int pc_cluster_points(const double* points, int m, int nDims, int* labels_out);
 
+/* Measured FP64 fused-multiply-add throughput of the current device in TFLOP/s (a microbenchmark: eight independent
+ * FMA chains per thread, best of five launches).  bench.py quotes the run's arithmetic against it. */
+double pc_measure_fp64_tflops(void);
+
 /* Number of CUDA devices visible; <=0 means the engine cannot run (no CPU fallback exists). */
 int pc_device_count(void);
 const char* pc_version(void);

@@ -27,7 +27,7 @@ EXPORTS = [
     "pc_unit_prior", "pc_uniform_prior", "pc_set_option", "pc_get_option", "pc_set_stream", "pc_release_memory", "pc_mgpu_create", "pc_mgpu_attach", "pc_mgpu_destroy",
     "pc_last_run_info", "pc_run", "pc_run_ensemble", "pc_slice_chains", "pc_calculate_points",
     "pc_device_philox", "pc_device_uniforms", "pc_device_inv_normal_cdf", "pc_device_directions",
-    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points", "pc_set_grades", "pc_set_resume",
+    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points", "pc_set_grades", "pc_set_resume", "pc_measure_fp64_tflops",
 ]
 
 
@@ -331,3 +331,9 @@ def set_resume(path=None, write=False, read=False):
     L.pc_set_resume.argtypes = [C.c_char_p, C.c_int, C.c_int]
     if L.pc_set_resume(None if path is None else str(path).encode(), int(write), int(read)) != 0:
         raise ValueError("pc_set_resume: the path must end in .resume")
+
+
+def measure_fp64_tflops():
+    L = lib()
+    L.pc_measure_fp64_tflops.restype = C.c_double
+    return float(L.pc_measure_fp64_tflops())

@@ -1647,6 +1647,38 @@ int pc_device_evidence(double* state, const double* logLs, int count, int n_star
         return fail(-3, ex.what());
     }
 }
+// measured FP64 FMA throughput in TFLOP/s (best of five launches timed with CUDA events)
+double pc_measure_fp64_tflops(void) {
+    try {
+        device_check();
+        int dev = 0, sms = 0;
+        PC_CUDA(cudaGetDevice(&dev));
+        PC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int blocks = sms * 8, threads = 256, iters = 4096;
+        DevArr<double> out((size_t)blocks * threads);
+        cudaEvent_t e0, e1;
+        PC_CUDA(cudaEventCreate(&e0));
+        PC_CUDA(cudaEventCreate(&e1));
+        double best = 0.0;
+        for (int rep = 0; rep < 6; ++rep) {
+            PC_CUDA(cudaEventRecord(e0, g_stream));
+            pc_fp64_peak_kernel<<<blocks, threads, 0, g_stream>>>(out.p, iters, 0.999999, 1e-9);
+            PC_CUDA(cudaEventRecord(e1, g_stream));
+            PC_CUDA(cudaEventSynchronize(e1));
+            float ms = 0;
+            PC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            const double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+            if (rep > 0) best = std::max(best, tf);
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        return best;
+    } catch (const std::exception& ex) {
+        fail(-3, ex.what());
+        return 0.0;
+    }
+}
+
 int pc_device_cholesky(const double* a, int D, double* L_out) {
     try {
         device_check();

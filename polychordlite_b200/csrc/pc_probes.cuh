@@ -36,6 +36,16 @@ __global__ void pc_evidence_kernel(DevRun* st, const double* logLs, int count, i
     __syncthreads();
     evidence_deaths(st, skey, count, n_start, logw_out, sc);
 }
+// FP64 fused-multiply-add throughput of the device (the arithmetic roofline bench.py quotes the run against):
+// eight independent chains per thread, 2 flops per FMA
+__global__ void pc_fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
 __global__ void pc_cholesky_kernel(const double* a, double* L, int D, int* fb) {
     int f = warp_cholesky(a, L, D);
     if (threadIdx.x == 0) *fb = f;
