@@ -1216,7 +1216,7 @@ struct Engine {
             if (std::getenv("PC_DEBUG")) {
                 const int khz = std::max(1, sm_clock_khz());
                 std::fprintf(stderr, "[pc dbg ms]");
-                for (int i = 0; i < 20; ++i) std::fprintf(stderr, " %.3f", (double)s.dbg[i] / khz);
+                for (int i = 0; i < 24; ++i) std::fprintf(stderr, " %.3f", (double)s.dbg[i] / khz);
                 std::fprintf(stderr, "\n");
             }
             o.algorithmic_bytes = s.nslices * (8LL * k.cp.T + 8LL * k.cp.D) + s.nchains * 16LL * k.cp.T + s.ngen * 8LL * k.cp.D * k.cp.D;

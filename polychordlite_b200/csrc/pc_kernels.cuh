@@ -69,7 +69,11 @@ struct DevRun {
     // representative chain warp; phase U of CTA 0: [2] pass A, [3] barrier, [4] pass B ([12] its set-up, [13] its tile
     // loop, [15] the warps' combination), [5] closing barrier; phase S1: [6] keys, [7] termination test, [8] sort +
     // merge, [9] publication; the first chain CTA: [10] wait at the generation barrier, [11] release -> first slice
-    long long dbg[20];
+    long long dbg[24];
+    // what every warp needs at the start of a generation, in one 64-byte line (written by phase S1, read with one
+    // coalesced load per warp): [0] Lstar (bits), [1] ndead_base, [2] nph_base, [3] nchains_base, [4] ngen,
+    // [5] K | do_update << 32, [6] order_off | cur_pool << 32, [7] ncl | nupdates << 32
+    unsigned long long pub[8];
     unsigned int bar;    // group barrier, one arrival per CTA (monotonic)
     unsigned int wbar;   // chains-done barrier, one arrival per warp (monotonic)
 };

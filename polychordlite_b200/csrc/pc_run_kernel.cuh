@@ -240,6 +240,14 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
         st->nslices += (long long)K * p.cp.R;
         st->do_update = (lX_new <= st->logX_last_update + p.log_comp) ? 1 : 0;  // nested_sampling.F90:321
         st->status = ST_RUNNING;
+        st->pub[0] = (unsigned long long)__double_as_longlong(st->Lstar);
+        st->pub[1] = (unsigned long long)st->ndead_base;
+        st->pub[2] = (unsigned long long)st->nph_base;
+        st->pub[3] = (unsigned long long)st->nchains_base;
+        st->pub[4] = (unsigned long long)st->ngen;
+        st->pub[5] = (unsigned long long)(unsigned)st->K | ((unsigned long long)(unsigned)st->do_update << 32);
+        st->pub[6] = (unsigned long long)(unsigned)st->order_off | ((unsigned long long)(unsigned)st->cur_pool << 32);
+        st->pub[7] = (unsigned long long)(unsigned)st->ncl | ((unsigned long long)(unsigned)st->nupdates << 32);
         long long q4 = clock64();
         st->dbg[6] += q1 - q0; st->dbg[7] += q2 - q1; st->dbg[8] += q3 - q2; st->dbg[9] += q4 - q3;
     }
@@ -751,7 +759,11 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
         group_sync(&st->bar, NG);
         const long long tg1 = clock64();
         if (ctimer) st->dbg[10] += tg1 - tg0;
-        if (vload(&st->status) != ST_RUNNING) {
+        // the run's status and the generation's parameters: one load per lane, one latency
+        unsigned long long pw = 0;
+        if (lane < 8) pw = __ldcg(&st->pub[lane]);
+        else if (lane == 8) pw = (unsigned long long)(unsigned)vload(&st->status);
+        if ((int)__shfl_sync(FULL, pw, 8) != ST_RUNNING) {
             if (timer) st->cyc_total += clock64() - t_start;
             return;
         }
@@ -779,26 +791,31 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
         }
 
         // ---------------- phase C: chains, one warp each ----------------
-        const int K = vload(&st->K);
-        const double Lstar = vload(&st->Lstar);
-        const long long ndead_base = vload(&st->ndead_base), nph_base = vload(&st->nph_base);
-        const long long nchains_base = vload(&st->nchains_base);
-        const int do_update = vload(&st->do_update);
-        const bool clustered = p.clustering && vload(&st->ncl) > 1;
-        const int* order = rb.order + vload(&st->order_off);
-        double* pool = rb.ph[vload(&st->cur_pool)];
+        const unsigned long long w5 = __shfl_sync(FULL, pw, 5), w6 = __shfl_sync(FULL, pw, 6), w7 = __shfl_sync(FULL, pw, 7);
+        const int K = (int)(unsigned)w5;
+        const double Lstar = __longlong_as_double((long long)__shfl_sync(FULL, pw, 0));
+        const long long ndead_base = (long long)__shfl_sync(FULL, pw, 1), nph_base = (long long)__shfl_sync(FULL, pw, 2);
+        const long long nchains_base = (long long)__shfl_sync(FULL, pw, 3);
+        const long long ngen_now = (long long)__shfl_sync(FULL, pw, 4);
+        const int do_update = (int)(w5 >> 32);
+        const bool clustered = p.clustering && (int)(unsigned)w7 > 1;
+        const int cur_pool_now = (int)(w6 >> 32);
+        const int* order = rb.order + (int)(unsigned)w6;
+        double* pool = rb.ph[cur_pool_now];
         {   // the Cholesky factor only changes at an update: reload it then (CTA 0 also uses the area as scratch)
-            const long long nup = vload(&st->nupdates);
+            const long long nup = (long long)(w7 >> 32);
             if (cta == 0 || nup != chol_epoch) {
                 for (int e = tid; e < D * D; e += blockDim.x) s_chol[e] = __ldcg(rb.chol + e);
                 __syncthreads();
                 chol_epoch = nup;
             }
         }
+        const long long ts_a = clock64();
+        if (ctimer) st->dbg[19] += ts_a - tg1;   // release -> generation parameters and Cholesky factor in place
         unsigned long long nlike = 0, nfail = 0;
         const int m = n - K;
         // sharded run: the last babies go to the incoming buffers (by generation parity) instead of the live slots
-        const int xpar = (int)(vload(&st->ngen) & 1);
+        const int xpar = (int)(ngen_now & 1);
         double* xin_mine = sharded ? p.sh.xin[xr] + (size_t)xpar * p.batch_K * T : nullptr;
         int knext = -1;  // first chain this warp prepares for the next generation
         if (p.paired) {
@@ -825,6 +842,8 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                 choice = max(1, min(m, choice));
                 const int src = __ldcg(order + K + choice - 1);
                 const int plab = clustered ? min(__ldcg(rb.lab + src), MAX_CLUSTERS - 1) : 0;  // the seed's cluster
+                const long long ts_b = clock64();
+                if (ctimer && j == 0) st->dbg[20] += ts_b - ts_a;   // seed choice (Philox + order look-up)
                 if (helper) {
                     long long th0 = clock64();
                     if (prep_uid != uid) { prep_chain(D, R, LD, rb.seed, uid, b, &p.cp); prep_white = false; }
@@ -834,6 +853,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                     if (lane == 0 && cta == c0 && pair == 0) st->cyc_prep += clock64() - th0;
                 }
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");  // hand-over of the buffer
+                if (ctimer && j == 0) st->dbg[21] += clock64() - ts_b;   // wait for the helper's hand-over
                 if (!helper) {
                     const int dslot = __ldcg(order + k);
                     double x[DPL];
@@ -851,7 +871,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                                                       (cta == c0 && warp == 0) ? st->dbg : nullptr, false);
                     if (sharded) shard_publish(p, last, k, xpar);
                     if (p.clustering) {  // the babies carry their seed's label until the next update
-                        for (int e = lane; e < R - 1; e += 32) rb.phl[vload(&st->cur_pool)][nph_base + (long long)cl * (R - 1) + e] = plab;
+                        for (int e = lane; e < R - 1; e += 32) rb.phl[cur_pool_now][nph_base + (long long)cl * (R - 1) + e] = plab;
                         if (lane == 0) rb.lab[dslot] = plab;
                     }
                     if (ctimer) st->cyc_slice += clock64() - tc2;
@@ -894,7 +914,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                                                   pool + (size_t)(nph_base + (long long)cl * (R - 1)) * T, last, nlike, nullptr, false);
                 if (sharded) shard_publish(p, last, k, xpar);
                 if (p.clustering) {
-                    for (int e = lane; e < R - 1; e += 32) rb.phl[vload(&st->cur_pool)][nph_base + (long long)cl * (R - 1) + e] = plab;
+                    for (int e = lane; e < R - 1; e += 32) rb.phl[cur_pool_now][nph_base + (long long)cl * (R - 1) + e] = plab;
                     if (lane == 0) rb.lab[dslot] = plab;
                 }
                 if (ctimer) {
