@@ -245,6 +245,13 @@ int pc_write_files(const char* base_dir, const char* file_root, int flags, int n
                    const double* dead_rows, const double* dead_logw, int nlive, const double* live_rows, double logZ,
                    double logZerr, long long nlike, int num_repeats, double compression_factor, unsigned seed);
 
+/* Host-only (no device needed): hypercube_to_physical (priors.f90:494-556) of the parameter block of an .ini file in the
+ * reference's format (ini.f90:354-458), applied to one cube point: the separable families, their sorted forms, the
+ * adaptive sorted families and nn_adaptive_layer_gaussian (priors.f90:40-488).  This is the transform
+ * polychord_c_interface_ini runs with.  Returns 0; -6 when the file cannot be read or parsed (message on stderr), -7
+ * when nDims is not the file's parameter count. */
+int pc_ini_prior_transform(const char* inifile, const double* cube, double* theta, int nDims);
+
 /* NN_clustering (clustering.f90:15-97) of m points (row-major m x nDims cube coordinates) exactly as the engine's
  * update runs it (device k-nearest-neighbour lists, host union-find); labels in order of first appearance.
  * Returns the number of clusters. */

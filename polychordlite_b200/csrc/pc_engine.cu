@@ -1852,6 +1852,20 @@ void polychord_c_interface(pc_loglikelihood_t loglikelihood, pc_prior_t prior, p
     }
 }
 
+// Host-only: the prior transform of an .ini file's parameter block (hypercube_to_physical, priors.f90:494-556) applied
+// to one cube point.  Returns 0, -6 when the file cannot be read or parsed, -7 when nDims is not its parameter count.
+int pc_ini_prior_transform(const char* inifile, const double* cube, double* theta, int nDims) {
+    try {
+        const IniConfig c = parse_ini(inifile ? std::string(inifile) : std::string());
+        if ((int)c.params.size() != nDims) return -7;
+        ini_prior_transform(c, cube, theta);
+    } catch (const std::exception& ex) {
+        std::fprintf(stderr, "pc_ini_prior_transform: %s\n", ex.what());
+        return -6;
+    }
+    return 0;
+}
+
 static IniConfig g_ini;   // the .ini run in flight: its prior transform is reached through a plain C callback
 static void ini_prior_callback(double* cube, double* theta, int nDims) {
     (void)nDims;

@@ -2,7 +2,8 @@
 //
 // Replaces src/polychord/ini.f90 (read_params :44-95, get_string :149-224, get_params :354-458, get_prior_params
 // :470-497) and the separable transforms of src/polychord/priors.f90 (uniform :40, gaussian :73, log_uniform :114,
-// power_uniform :140, half_gaussian :155, exponential :166).  Host-only.
+// power_uniform :140, half_gaussian :155, exponential :166), their sorted forms (:242-360), the adaptive sorted
+// families (:367-461) and nn_adaptive_layer_gaussian (:469-488).  Host-only.
 #include "pc_ini.h"
 
 #include <algorithm>
@@ -139,14 +140,11 @@ IniConfig parse_ini(const std::string& path) {
         p.speed = std::stoi(el[2]);
         p.prior_type = prior_type_from_string(el[3]);
         if (p.prior_type == 0) throw std::invalid_argument("get_priors error: Unknown prior type for parameter " + p.name);
-        if (p.prior_type > 10)
-            throw std::invalid_argument("ini error: prior type '" + el[3] + "' of parameter " + p.name +
-                                        " (adaptive families, priors.f90:300-488) is not supported by the B200 engine");
         p.block = std::stoi(el[4]);
         std::istringstream is(el[5]);
         double v;
         while (is >> v) p.params.push_back(v);
-        const size_t need = p.prior_type == 3 ? 3 : ((p.prior_type == 6 || p.prior_type == 10) ? 1 : 2);
+        const size_t need = p.prior_type == 3 ? 3 : ((p.prior_type == 6 || p.prior_type == 10 || p.prior_type == 14) ? 1 : 2);
         if (p.params.size() < need) throw std::invalid_argument("ini error: too few prior parameters for " + p.name);
         c.params.push_back(p);
     }
@@ -187,8 +185,37 @@ static double separable_htp(int type, const double* q, double u) {
     }
 }
 
+// sort_hypercube (priors.f90:242-264): the unit cube onto its ordered corner, largest coordinate first
+static void sort_hypercube(const double* u, double* s, size_t m) {
+    if (m == 0) return;
+    s[m - 1] = std::pow(u[m - 1], 1.0 / (double)m);
+    for (size_t k = m - 1; k-- > 0;) s[k] = std::pow(u[k], 1.0 / (double)(k + 1)) * s[k + 1];
+}
+
+// adaptive_sorted_transform (priors.f90:367-385): the first coordinate, scaled to (0.5, m - 0.5), rounds to the number
+// nfunc of basis functions in use; only the next nfunc coordinates are sorted, the rest pass through.  The reference
+// indexes one past the block when the first coordinate is exactly 1; nfunc is clamped to m - 1 here.
+static void adaptive_sorted_transform(const double* cube, double* t, size_t m) {
+    for (size_t k = 0; k < m; ++k) t[k] = cube[k];
+    if (m == 0) return;
+    t[0] = 0.5 + cube[0] * (double)(m - 1);
+    const size_t nfunc = std::min((size_t)(t[0] + 0.5), m - 1);
+    sort_hypercube(cube + 1, t + 1, nfunc);
+}
+
+// adaptive_sorted_{uniform,gaussian,half_gaussian,exponential}_htp (priors.f90:389-461): the count coordinate is
+// returned as scaled (its own prior parameters are skipped: "parameters(3:)", "(2:)" for the exponential), the others
+// go through the separable transform of the same name
+static void adaptive_block(const IniConfig& c, size_t i, size_t m, int base, const double* cube, double* theta) {
+    std::vector<double> t(m);
+    adaptive_sorted_transform(cube, t.data(), m);
+    if (m) theta[0] = t[0];
+    for (size_t k = 1; k < m; ++k) theta[k] = separable_htp(base, c.params[i + k].params.data(), t[k]);
+}
+
 void ini_prior_transform(const IniConfig& c, const double* cube, double* theta) {
     const size_t n = c.params.size();
+    static const int base_type[] = {1, 4, 5, 6};   // uniform, gaussian, half_gaussian, exponential
     for (size_t i = 0; i < n;) {
         const IniParam& p = c.params[i];
         if (p.prior_type <= 6) {
@@ -196,16 +223,25 @@ void ini_prior_transform(const IniConfig& c, const double* cube, double* theta) 
             ++i;
             continue;
         }
-        // sorted families (priors.f90:242-298): the block's coordinates go through sort_hypercube (:190-200), which maps
-        // the unit cube onto its ordered corner, then through the separable transform of the same name
+        // block families: consecutive parameters of one type and one prior block (create_priors, priors.f90:671-749)
         size_t j = i;
         while (j < n && c.params[j].prior_type == p.prior_type && c.params[j].block == p.block) ++j;
         const size_t m = j - i;
-        std::vector<double> srt(m);
-        srt[m - 1] = std::pow(cube[i + m - 1], 1.0 / (double)m);
-        for (size_t k = m - 1; k-- > 0;) srt[k] = std::pow(cube[i + k], 1.0 / (double)(k + 1)) * srt[k + 1];
-        static const int base_type[] = {1, 4, 5, 6};   // sorted_uniform, sorted_gaussian, sorted_half_gaussian, sorted_exponential
-        for (size_t k = 0; k < m; ++k) theta[i + k] = separable_htp(base_type[p.prior_type - 7], c.params[i + k].params.data(), srt[k]);
+        if (p.prior_type <= 10) {
+            // sorted families (priors.f90:266-360): sort_hypercube, then the separable transform of the same name
+            std::vector<double> srt(m);
+            sort_hypercube(cube + i, srt.data(), m);
+            for (size_t k = 0; k < m; ++k)
+                theta[i + k] = separable_htp(base_type[p.prior_type - 7], c.params[i + k].params.data(), srt[k]);
+        } else if (p.prior_type <= 14) {
+            adaptive_block(c, i, m, base_type[p.prior_type - 11], cube + i, theta + i);
+        } else {
+            // nn_adaptive_layer_gaussian_htp (priors.f90:469-488): the first coordinate, scaled to (0.5, 2.5), is the
+            // number of hidden layers; one layer -> adaptive sorted half-Gaussian on the rest, else adaptive sorted
+            // Gaussian
+            theta[i] = 0.5 + 2.0 * cube[i];
+            if (m > 1) adaptive_block(c, i + 1, m - 1, theta[i] < 1.5 ? 5 : 4, cube + i + 1, theta + i + 1);
+        }
         i = j;
     }
 }

@@ -93,7 +93,7 @@ def test_ini_errors(gpu, tmp_path):
     info = _ini_call(gpu, gpu.lib().pc_gaussian_loglikelihood, tmp_path / "missing.ini")
     assert info.status == -6
     bad = tmp_path / "bad.ini"
-    bad.write_text(HEADER.format(nlive=50, R=4, seed=1, base=tmp_path, root="bad") + "P : a | a | 1 | adaptive_sorted_uniform | 1 | 0 1\n")
+    bad.write_text(HEADER.format(nlive=50, R=4, seed=1, base=tmp_path, root="bad") + "P : a | a | 1 | no_such_prior | 1 | 0 1\n")
     assert _ini_call(gpu, gpu.lib().pc_gaussian_loglikelihood, bad).status == -6
 
 
