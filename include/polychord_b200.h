@@ -245,6 +245,15 @@ int pc_write_files(const char* base_dir, const char* file_root, int flags, int n
                    const double* dead_rows, const double* dead_logw, int nlive, const double* live_rows, double logZ,
                    double logZerr, long long nlike, int num_repeats, double compression_factor, unsigned seed);
 
+/* boost_posterior (clean_phantoms, run_time_info.f90:820-877): when posteriors or equals is set and boost_posterior
+ * is not 0, every phantom the update removes becomes a posterior sample with probability boost_posterior /
+ * num_repeats (1 when boost_posterior < 0; generate.F90:311-316), carrying the weight of the death since the last
+ * update with the smallest logL above its own.  They are written to <root>.txt and <root>_equal_weights.txt with the
+ * dead points; this accessor returns those of the last run: rows[i] = [theta, phi, birth, logL] (npars = nDims +
+ * nDerived + 2), dead_index[i] = the dead point whose weight sample i carries, logw[i] = that weight + logL of the
+ * sample.  Returns the number of samples (fills up to cap), -1 when npars does not match the last run. */
+long long pc_last_boosted(double* rows, long long* dead_index, double* logw, long long cap, int npars);
+
 /* Host-only (no device needed): hypercube_to_physical (priors.f90:494-556) of the parameter block of an .ini file in the
  * reference's format (ini.f90:354-458), applied to one cube point: the separable families, their sorted forms, the
  * adaptive sorted families and nn_adaptive_layer_gaussian (priors.f90:40-488).  This is the transform

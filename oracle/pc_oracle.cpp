@@ -91,7 +91,7 @@ inline U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint
     return U4{{c0, c1, c2, c3}};
 }
 
-enum Tag : uint32_t { TAG_INIT = 1, TAG_SEED = 2, TAG_DIR = 3, TAG_SHUF = 4, TAG_SLICE = 5, TAG_POST = 6, TAG_LIKE = 7 };
+enum Tag : uint32_t { TAG_INIT = 1, TAG_SEED = 2, TAG_DIR = 3, TAG_SHUF = 4, TAG_SLICE = 5, TAG_POST = 6, TAG_LIKE = 7, TAG_BOOST = 8 };
 
 inline double u64_to_unit(uint64_t x) {
     // 52 random bits + 1/2 ulp offset: strictly inside (0,1), exactly representable.
@@ -395,6 +395,7 @@ struct Cluster {
     std::vector<double> live;     // T x nlive, point-major
     std::vector<double> phantom;  // T x nphantom
     std::vector<double> stack_l;  // pos_l of the posterior stack since the last update (deaths of this cluster)
+    std::vector<long long> stack_i;  // ... and the index of each of those deaths in Run::dead
     int nlive = 0, nphantom = 0;
     double logZp, logXp, logZXp, logZp2, logZpXp;
     double logLp;
@@ -403,6 +404,10 @@ struct Cluster {
 };
 
 std::vector<int> g_grade_dims, g_grade_repeats;   // set by oracle_set_grades, read by every Run until cleared
+// phantoms promoted to posterior samples by the last run (clean_phantoms, run_time_info.f90:820-877), read by
+// oracle_last_boosted: rows [theta, phi, birth, logL], the dead point whose weight each one carries, log-weight + logL
+std::vector<double> g_boost_rows, g_boost_logw;
+std::vector<long long> g_boost_dead;
 
 struct Run {
     oracle_settings S;
@@ -705,6 +710,7 @@ struct Run {
         find_min();
         push_dead(rec.data(), logw);
         c.stack_l.push_back(rec[l0]);
+        c.stack_i.push_back(ndead - 1);
     }
 
     int identify_cluster(const double* point) {
@@ -755,9 +761,36 @@ struct Run {
         return replaced;
     }
 
+    // RTI%thin_posterior, generate.F90:311-316
+    double thin_posterior() const {
+        if (!(S.posteriors || S.equals)) return 0.0;   // run_time_info.f90:858: only when posterior files are asked for
+        return S.boost_posterior < 0.0 ? 1.0 : S.boost_posterior / (double)R;
+    }
+    // The posterior conversion of a phantom that clean_phantoms removes (run_time_info.f90:846-868): with
+    // probability thin_posterior it becomes a posterior sample carrying the weight of the death of its cluster,
+    // since the last update, with the smallest logL above its own (minloc over the mask, :846-848).  The
+    // reference draws the Bernoulli trial from its sequential stream; here it is addressed by the bits of the
+    // phantom's logL, so that it does not depend on the order in which the phantoms are visited.  (The engine
+    // addresses it by the bits of ITS logL, equal to this one only to rounding: with thin_posterior < 1 the two
+    // promote different subsets of the same phantoms; tests compare the full lists, boost_posterior < 0.)
+    void boost(const Cluster& c, const double* pt) {
+        const double thin = thin_posterior();
+        if (!(thin > 0.0)) return;
+        uint64_t bits;
+        std::memcpy(&bits, &pt[l0], 8);
+        if (!(rng.uniform(TAG_BOOST, bits, 0, 0) < thin)) return;
+        long long best = -1;
+        double lbest = HUGE_D;
+        for (size_t j = 0; j < c.stack_l.size(); ++j)
+            if (c.stack_l[j] > pt[l0] && c.stack_l[j] < lbest) { lbest = c.stack_l[j]; best = c.stack_i[j]; }
+        if (best < 0) return;   // cannot happen: the caller found a death above this phantom
+        g_boost_rows.insert(g_boost_rows.end(), pt + p0, pt + T);
+        g_boost_dead.push_back(best);
+        g_boost_logw.push_back(logweights[(size_t)best] + pt[l0]);
+    }
+
     // clean_phantoms, run_time_info.f90:820-877: a phantom is dropped as soon as some death
-    // of its cluster since the last update has a larger logL.  (Posterior conversion: see
-    // DESIGN.md "next" row f1 -- the oracle only needs the deletion for the covariance.)
+    // of its cluster since the last update has a larger logL.
     void clean_phantoms() {
         for (auto& c : cl) {
             if (c.stack_l.empty()) continue;
@@ -765,6 +798,7 @@ struct Run {
             int i = 0;
             while (i < c.nphantom) {
                 if (lmax > c.phantom[(size_t)i * T + l0]) {
+                    boost(c, &c.phantom[(size_t)i * T]);
                     std::copy(c.phantom.begin() + (size_t)(c.nphantom - 1) * T, c.phantom.begin() + (size_t)c.nphantom * T,
                               c.phantom.begin() + (size_t)i * T);
                     c.nphantom--;
@@ -774,6 +808,7 @@ struct Run {
             }
             c.phantom.resize((size_t)c.nphantom * T);
             c.stack_l.clear();
+            c.stack_i.clear();
         }
     }
     // batched mode keeps the phantom pool in birth order (stable compaction) so that the
@@ -791,12 +826,15 @@ struct Run {
                                   c.phantom.begin() + (size_t)w * T);
                     if (lbl) phlab[w] = phlab[i];
                     ++w;
+                } else {
+                    boost(c, &c.phantom[(size_t)i * T]);
                 }
             }
             if (lbl) phlab.resize(w);
             c.nphantom = w;
             c.phantom.resize((size_t)w * T);
             c.stack_l.clear();
+            c.stack_i.clear();
         }
     }
 
@@ -1150,6 +1188,7 @@ struct Run {
                 double logw = update_evidence(0);
                 push_dead(r, logw);
                 c.stack_l.push_back(r[l0]);
+                c.stack_i.push_back(ndead - 1);
                 c.nlive--;
             }
             c.nlive = nlive_save;
@@ -1206,6 +1245,8 @@ struct Run {
                 c.logLp = r[l0];
                 double logw = update_evidence(0);
                 push_dead(r, logw);
+                c.stack_l.push_back(r[l0]);
+                c.stack_i.push_back(ndead - 1);
                 c.nlive--;
             }
             c.live.clear();
@@ -1216,6 +1257,7 @@ struct Run {
 
     void run(oracle_result* out) {
         auto t0 = std::chrono::steady_clock::now();
+        g_boost_rows.clear(); g_boost_dead.clear(); g_boost_logw.clear();
         init_layout();
         generate_live_points();
         // nprior > nlive: trim (nested_sampling.F90:201-203)
@@ -1224,6 +1266,11 @@ struct Run {
         out->ncluster = S.batch_K > 0 ? ncl_b : (long long)cl.size();
         out->nsplits = nsplits;
         final_killoff();
+        long long nph_end = 0;   // phantoms at the end of the sampling loop (what the engine reports too)
+        for (auto& c : cl) nph_end += c.nphantom;
+        if (thin_posterior() > 0.0) {   // update_posteriors, nested_sampling.F90:386: the last phantoms' conversion
+            if (S.batch_K > 0) clean_phantoms_stable(); else clean_phantoms();
+        }
         dump();
         auto t1 = std::chrono::steady_clock::now();
         double lz, var;
@@ -1232,9 +1279,7 @@ struct Run {
         out->logZ_raw = logZ; out->logZ2_raw = logZ2;
         out->ndead = ndead; out->nlike = nlike; out->nchains = nchains; out->ngenerations = ngen;
         out->nupdates = nupdates; out->nfailures = nfail_total; out->nslices = nslices;
-        long long nph = 0;
-        for (auto& c : cl) nph += c.nphantom;
-        out->nphantoms_final = nph;
+        out->nphantoms_final = nph_end;
         out->seconds = std::chrono::duration<double>(t1 - t0).count();
     }
 };
@@ -1337,6 +1382,19 @@ int oracle_calculate_points(const oracle_settings* s, int like_kind, const doubl
     long long n = 0;
     for (int i = 0; i < npts; ++i) run.calculate_point(records + (size_t)i * run.T, n);
     return (int)n;
+}
+
+// The phantoms the last oracle_run promoted to posterior samples (boost_posterior with posteriors or equals set):
+// rows[npars] = [theta, phi, birth, logL], dead_index = the dead point whose weight the sample carries,
+// logw = that weight + the sample's logL (unnormalised posterior log-weight).  Returns the count; fills up to cap.
+long long oracle_last_boosted(double* rows, long long* dead_index, double* logw, long long cap, int npars) {
+    const long long nb = (long long)g_boost_dead.size();
+    for (long long i = 0; i < std::min(nb, cap); ++i) {
+        std::copy(g_boost_rows.begin() + (size_t)i * npars, g_boost_rows.begin() + (size_t)(i + 1) * npars, rows + (size_t)i * npars);
+        dead_index[i] = g_boost_dead[(size_t)i];
+        logw[i] = g_boost_logw[(size_t)i];
+    }
+    return nb;
 }
 
 // Fast/slow parameter grades for the following runs (settings%grade_dims, RTI%num_repeats per grade,

@@ -27,7 +27,7 @@ EXPORTS = [
     "pc_unit_prior", "pc_uniform_prior", "pc_set_option", "pc_get_option", "pc_set_stream", "pc_release_memory", "pc_mgpu_create", "pc_mgpu_attach", "pc_mgpu_destroy",
     "pc_last_run_info", "pc_run", "pc_run_ensemble", "pc_slice_chains", "pc_calculate_points",
     "pc_device_philox", "pc_device_uniforms", "pc_device_inv_normal_cdf", "pc_device_directions",
-    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points", "pc_set_grades", "pc_set_resume", "pc_measure_fp64_tflops", "pc_ini_prior_transform",
+    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points", "pc_set_grades", "pc_set_resume", "pc_measure_fp64_tflops", "pc_ini_prior_transform", "pc_last_boosted",
 ]
 
 
@@ -145,6 +145,19 @@ def run(settings, like="gaussian", like_params=None, prior_lo=None, prior_hi=Non
     if rc != 0:
         raise RuntimeError(f"pc_run failed with status {rc}")
     return info, dumps
+
+
+def last_boosted(npars):
+    """Phantoms the last run promoted to posterior samples (boost_posterior): (rows[nb, npars], dead_index[nb], logw[nb])."""
+    L = lib()
+    L.pc_last_boosted.restype = C.c_longlong
+    L.pc_last_boosted.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double), C.c_longlong, C.c_int]
+    nb = L.pc_last_boosted(None, None, None, 0, npars)
+    if nb < 0:
+        raise ValueError("npars does not match the last run")
+    rows, idx, lw = np.zeros((max(nb, 1), npars)), np.zeros(max(nb, 1), dtype=np.int64), np.zeros(max(nb, 1))
+    L.pc_last_boosted(_dptr(rows), idx.ctypes.data_as(C.POINTER(C.c_longlong)), _dptr(lw), nb, npars)
+    return rows[:nb], idx[:nb], lw[:nb]
 
 
 def run_ensemble(settings, seeds, like="gaussian", like_params=None, prior_lo=None, prior_hi=None):

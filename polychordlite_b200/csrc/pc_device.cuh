@@ -10,7 +10,7 @@
 
 namespace pc {
 
-enum Tag : uint32_t { TAG_INIT = 1, TAG_SEED = 2, TAG_DIR = 3, TAG_SHUF = 4, TAG_SLICE = 5, TAG_POST = 6, TAG_LIKE = 7 };
+enum Tag : uint32_t { TAG_INIT = 1, TAG_SEED = 2, TAG_DIR = 3, TAG_SHUF = 4, TAG_SLICE = 5, TAG_POST = 6, TAG_LIKE = 7, TAG_BOOST = 8 };
 
 constexpr unsigned FULL = 0xffffffffu;
 

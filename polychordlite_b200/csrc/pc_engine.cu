@@ -98,6 +98,11 @@ static PinnedBuf g_pin_dead, g_pin_live;
 // than the copies.
 struct DumpMirror {
     std::vector<double> rows, logw, lw, live_rows;
+    // boost_posterior: phantoms promoted to posterior samples (clean_phantoms, run_time_info.f90:846-868), in the
+    // order (update, logL): rows [theta, phi, birth, logL], posterior log-weight (log w of its death + own logL), the
+    // dead point whose weight it carries, and the number of dead points at the update that removed it
+    std::vector<double> boost_rows, boost_logw;
+    std::vector<long long> boost_dead, boost_after;
 };
 static DumpMirror g_mirror;
 static int sm_clock_khz() {  // cudaDevAttrClockRate is a slow driver query (milliseconds): ask once per device
@@ -366,6 +371,9 @@ struct HostRun {
     DevArr<int> order, lab, phl0, phl1;
     DevArr<double> cchol;
     DevArr<long long> pcount;
+    DevArr<double> boost;
+    DevArr<unsigned long long> boost_win;
+    long long boost_mirrored = 0;   // rows of the device list already in the mirror
     RunBuf buf;
     DevRun host_st;
     // dumper mirror
@@ -389,8 +397,9 @@ struct ResumeHeader {
 struct ResumeData {
     ResumeHeader h;
     DevRun st;
-    std::vector<double> live, okey, dead, logw, ph, chol, cov, gsum, cchol;
+    std::vector<double> live, okey, dead, logw, ph, chol, cov, gsum, cchol, boost;
     std::vector<int> order, lab, phl;
+    std::vector<unsigned long long> boost_win;
 };
 static const char RESUME_MAGIC[8] = {'P', 'C', 'B', '2', '0', '0', 'R', '1'};
 template <class V>
@@ -413,7 +422,7 @@ static bool read_resume_file(const std::string& path, ResumeData& rd) {
               rd.h.version == 1 && rd.h.sizeof_devrun == (int)sizeof(DevRun) && std::fread(&rd.st, sizeof(DevRun), 1, f) == 1;
     ok = ok && get_vec(f, rd.live) && get_vec(f, rd.order) && get_vec(f, rd.okey) && get_vec(f, rd.dead) && get_vec(f, rd.logw) &&
          get_vec(f, rd.ph) && get_vec(f, rd.chol) && get_vec(f, rd.cov) && get_vec(f, rd.gsum) && get_vec(f, rd.lab) &&
-         get_vec(f, rd.phl) && get_vec(f, rd.cchol);
+         get_vec(f, rd.phl) && get_vec(f, rd.cchol) && get_vec(f, rd.boost) && get_vec(f, rd.boost_win);
     std::fclose(f);
     if (!ok) throw std::invalid_argument("polychord_b200: " + path + " is not a resume file of this engine version");
     return true;
@@ -591,6 +600,12 @@ struct Engine {
         const int K = k.batch_K;
         // do_clustering: one run on one GPU with a device likelihood; elsewhere the run stays one cluster (always valid)
         k.clustering = (S.do_clustering && nruns == 1 && g_mgpu.world <= 1 && !host_like) ? 1 : 0;
+        // boost_posterior: RTI%thin_posterior (generate.F90:311-316), in force when posterior samples are asked for
+        // (run_time_info.f90:858); one run on one GPU (the phantoms of a sharded run stay with their ranks)
+        k.boost_thin = 0.0;
+        if ((S.posteriors || S.equals) && S.boost_posterior != 0.0 && nruns == 1 && g_mgpu.world <= 1)
+            k.boost_thin = S.boost_posterior < 0.0 ? 1.0 : std::min(1.0, S.boost_posterior / (double)k.cp.R);
+        g_mirror.boost_logw.clear(); g_mirror.boost_rows.clear(); g_mirror.boost_dead.clear(); g_mirror.boost_after.clear();
         // read_resume: a file of this run's shape continues the run (nested_sampling.F90:175-183)
         if (g_resume.read && nruns == 1 && g_mgpu.world <= 1 && read_resume_file(g_resume.path, rd)) {
             const ResumeHeader& rh = rd.h;
@@ -649,6 +664,12 @@ struct Engine {
                 cap_dead = std::max<long long>(cap_dead, rd.st.ndead + 2LL * n + K);
                 cap_ph = std::max<long long>(cap_ph, rd.st.nphantom + (long long)K * (R - 1) + n);
             }
+            long long cap_boost = 0;
+            if (k.boost_thin > 0.0) {
+                cap_boost = 2 * cap_ph + (resumed ? (long long)rd.st.nboost : 0);
+                h.boost.alloc((size_t)cap_boost * (T - D));
+                h.boost_win.alloc((size_t)cap_boost);
+            }
             h.st.alloc(1); h.st.zero(stream);
             h.live.alloc((size_t)n * T); h.live.zero(stream);
             h.order.alloc(2 * (size_t)n);
@@ -674,6 +695,7 @@ struct Engine {
             b.ph[0] = h.ph0.p; b.ph[1] = h.ph1.p; b.chol = h.chol.p; b.cov = h.cov.p; b.partial = h.partial.p;
             b.pcount = h.pcount.p; b.nh = h.nh.p; b.cap_dead = cap_dead; b.cap_ph = cap_ph; b.gsum = h.gsum.p;
             b.lab = h.lab.p; b.phl[0] = h.phl0.p; b.phl[1] = h.phl1.p; b.cchol = h.cchol.p;
+            b.boost = h.boost.p; b.boost_win = h.boost_win.p; b.cap_boost = cap_boost;
             if (sharded)  // continue the cross-GPU barrier count of earlier runs (the counters are monotonic)
                 PC_CUDA(cudaMemcpyAsync(&h.st.p->xepoch, &g_mgpu.epoch, sizeof(g_mgpu.epoch), cudaMemcpyHostToDevice, stream));
             b.seed = resumed ? rd.h.seed : (unsigned)seeds[r];   // a resumed run continues its own random stream
@@ -698,6 +720,14 @@ struct Engine {
             h.chol.upload(rd.chol.data(), rd.chol.size(), stream);
             h.cov.upload(rd.cov.data(), rd.cov.size(), stream);
             h.gsum.upload(rd.gsum.data(), rd.gsum.size(), stream);
+            if (k.boost_thin > 0.0 && !rd.boost_win.empty() && rd.boost_win.size() == rd.st.nboost) {
+                h.boost.upload(rd.boost.data(), rd.boost.size(), stream);
+                h.boost_win.upload(rd.boost_win.data(), rd.boost_win.size(), stream);
+            } else if (rd.st.nboost) {   // the file was written without the samples (or the run no longer boosts)
+                const unsigned long long zero = 0;
+                PC_CUDA(cudaMemcpyAsync(&h.st.p->nboost, &zero, sizeof(zero), cudaMemcpyHostToDevice, stream));
+                h.host_st.nboost = 0;
+            }
             if (k.clustering) {
                 h.lab.upload(rd.lab.data(), rd.lab.size(), stream);
                 DevArr<int>& pl = rd.st.cur_pool == 0 ? h.phl0 : h.phl1;
@@ -821,9 +851,103 @@ struct Engine {
             dumper((int)ndead, nl, npars, live_rows.data(), ndead > 0 ? mr.rows.data() : dummy.data(), lw.data(), lz,
                    std::sqrt(var));
         lap(3);
-        if (g_files.enabled && r == 0)  // read_write.F90: the files are rewritten at every update and at the end
+        if (k.boost_thin > 0.0 && r == 0) collect_boosted(h, cs, ndead, final_call);
+        if (g_files.enabled && r == 0) {  // read_write.F90: the files are rewritten at every update and at the end
+            BoostedRows br;
+            br.n = (long long)mr.boost_logw.size(); br.rows = mr.boost_rows.data(); br.logw = mr.boost_logw.data();
+            br.after = mr.boost_after.data();
             write_run_files(g_files, g_fstate, D, P, ndead, mr.rows.data(), mr.logw.data(), nl, live_rows.data(), lz,
-                            std::sqrt(std::fabs(var)), nlike_now, final_call);
+                            std::sqrt(std::fabs(var)), nlike_now, final_call, br.n ? &br : nullptr);
+        }
+    }
+
+    // boost_posterior, host side.  The device list (rb.boost / rb.boost_win, filled by phase U) holds the promoted
+    // phantoms of the updates so far; at the final call the phantoms still in the pool go through the same rule
+    // against the deaths of the final kill-off (update_posteriors after the kill-off, nested_sampling.F90:381-386).
+    // Each sample takes the weight of the death, within its window, with the smallest logL above its own
+    // (run_time_info.f90:846-848; the dead points are in ascending logL, so that is a binary search).
+    // derived parameters of a phantom record (gaussian.f90:37-40; Model::finish_derived leaves them unset for phantoms)
+    void derived_of_phantom(double* rec) const {
+        const KParams& k = L.kp;
+        const int D = k.cp.D, P = k.cp.P;
+        const bool gauss = k.cp.like_kind == LIKE_GAUSSIAN && (int)h_mu.size() == D;
+        double r = 0.0;
+        if (gauss) {
+            double r2 = 0.0;
+            for (int d = 0; d < D; ++d) { const double dl = rec[D + d] - h_mu[(size_t)d]; r2 += dl * dl; }
+            r = std::sqrt(r2);
+        }
+        rec[2 * D] = r;
+        if (P >= 2) rec[2 * D + 1] = gauss ? std::log(std::pow(r, (double)D) * k.cp.Vn) : 0.0;
+        for (int i = 2; i < P; ++i) rec[2 * D + i] = 0.0;
+    }
+    std::vector<double> h_mu;   // host copy of the Gaussian's mean (the head of the device likelihood parameters)
+
+    void collect_boosted(HostRun& h, cudaStream_t cs, long long ndead, bool final_call) {
+        const KParams& k = L.kp;
+        const int T = k.cp.T, D = k.cp.D, np = T - D;
+        DumpMirror& mr = g_mirror;
+        struct Item { long long end, dead; double l, lw; std::vector<double> row; };
+        std::vector<Item> items;
+        auto dead_logL = [&](long long i) { return mr.rows[(size_t)i * np + np - 1]; };
+        auto place = [&](const double* row, long long first, long long end) {
+            first = std::max(0LL, std::min(first, ndead)); end = std::max(first, std::min(end, ndead));
+            const double l = row[np - 1];
+            long long lo = first, hi = end;   // first death of the window with logL > l
+            while (lo < hi) { const long long mid = (lo + hi) / 2; if (dead_logL(mid) > l) hi = mid; else lo = mid + 1; }
+            if (lo >= end) return;            // no death above it: the reference keeps such a phantom (:850-851)
+            Item it; it.end = end; it.dead = lo; it.l = l; it.lw = mr.logw[(size_t)lo] - dead_logL(lo) + l;
+            it.row.assign(row, row + np);
+            items.push_back(std::move(it));
+        };
+        const long long nb = std::min<long long>((long long)h.host_st.nboost, h.buf.cap_boost);
+        const long long fresh = nb - h.boost_mirrored;
+        if (fresh > 0) {
+            std::vector<double> rows((size_t)fresh * np);
+            std::vector<unsigned long long> win((size_t)fresh);
+            h.boost.download(rows.data(), rows.size(), cs, (size_t)h.boost_mirrored * np);
+            h.boost_win.download(win.data(), win.size(), cs, (size_t)h.boost_mirrored);
+            PC_CUDA(cudaStreamSynchronize(cs));
+            d2h += fresh * (np + 1) * 8;
+            for (long long i = 0; i < fresh; ++i)
+                place(&rows[(size_t)i * np], (long long)(win[(size_t)i] >> 32), (long long)(win[(size_t)i] & 0xffffffffull));
+            h.boost_mirrored = nb;
+        }
+        if (final_call && h.host_st.nphantom > 0 && ndead > 0) {
+            const long long nph = h.host_st.nphantom;
+            std::vector<double> pool((size_t)nph * T);
+            (h.host_st.cur_pool == 0 ? h.ph0 : h.ph1).download(pool.data(), pool.size(), cs);
+            PC_CUDA(cudaStreamSynchronize(cs));
+            d2h += nph * T * 8;
+            if (k.cp.P > 0 && !host_like && k.cp.like_kind == LIKE_GAUSSIAN && h_mu.empty()) {
+                h_mu.resize((size_t)D);
+                dm.like.download(h_mu.data(), (size_t)D, cs);
+                PC_CUDA(cudaStreamSynchronize(cs));
+            }
+            const double lmax = dead_logL(ndead - 1);
+            for (long long i = 0; i < nph; ++i) {
+                const double* rec = &pool[(size_t)i * T];
+                const double l = rec[T - 1];
+                if (!(lmax > l) || !(l > rec[T - 2])) continue;
+                uint64_t bits;
+                std::memcpy(&bits, &l, 8);
+                if (!(uniform(h.buf.seed, TAG_BOOST, bits, 0u, 0u) < k.boost_thin)) continue;
+                if (k.cp.P > 0 && !host_like) derived_of_phantom(&pool[(size_t)i * T]);
+                place(rec + D, h.host_st.ndead_upd, ndead);
+            }
+        }
+        // the device appends in no particular order: (update, logL, row) makes the list reproducible
+        std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) {
+            if (a.end != b.end) return a.end < b.end;
+            if (a.l != b.l) return a.l < b.l;
+            return a.row < b.row;
+        });
+        for (const Item& it : items) {
+            mr.boost_rows.insert(mr.boost_rows.end(), it.row.begin(), it.row.end());
+            mr.boost_logw.push_back(it.lw);
+            mr.boost_dead.push_back(it.dead);
+            mr.boost_after.push_back(it.end);
+        }
     }
 
     // ---- clustering at the update cadence (pc_cluster.cuh) -------------------------------------------------
@@ -1041,6 +1165,10 @@ struct Engine {
         pull(w.chol, h.chol, (size_t)D * D);
         pull(w.cov, h.cov, (size_t)D * D);
         pull(w.gsum, h.gsum, (size_t)2 * D + 4);
+        if (k.boost_thin > 0.0) {
+            pull(w.boost, h.boost, (size_t)st.nboost * (T - D));
+            pull(w.boost_win, h.boost_win, (size_t)st.nboost);
+        }
         if (k.clustering) {
             pull(w.lab, h.lab, (size_t)n);
             pull(w.phl, st.cur_pool == 0 ? h.phl0 : h.phl1, (size_t)st.nphantom);
@@ -1055,6 +1183,7 @@ struct Engine {
         std::fwrite(&w.st, sizeof(DevRun), 1, f);
         put_vec(f, w.live); put_vec(f, w.order); put_vec(f, w.okey); put_vec(f, w.dead); put_vec(f, w.logw); put_vec(f, w.ph);
         put_vec(f, w.chol); put_vec(f, w.cov); put_vec(f, w.gsum); put_vec(f, w.lab); put_vec(f, w.phl); put_vec(f, w.cchol);
+        put_vec(f, w.boost); put_vec(f, w.boost_win);
         std::fclose(f);
         std::rename(tmp.c_str(), g_resume.path.c_str());
         resume_written = true;
@@ -1064,7 +1193,12 @@ struct Engine {
     void grow(int r, int status) {
         HostRun& h = runs[r];
         const KParams& k = L.kp;
-        if (status == ST_NEED_DEAD) {
+        if (status == ST_NEED_BOOST) {
+            const long long nc = h.buf.cap_boost * 2 + h.buf.cap_ph, np = k.cp.T - k.cp.D;
+            h.boost.grow((size_t)nc * np, (size_t)h.host_st.nboost * np, stream);
+            h.boost_win.grow((size_t)nc, (size_t)h.host_st.nboost, stream);
+            h.buf.boost = h.boost.p; h.buf.boost_win = h.boost_win.p; h.buf.cap_boost = nc;
+        } else if (status == ST_NEED_DEAD) {
             long long nc = h.buf.cap_dead * 2 + k.n + k.batch_K;
             h.dead.grow((size_t)nc * k.cp.T, (size_t)h.host_st.ndead * k.cp.T, stream);
             h.logw.grow(nc, h.host_st.ndead, stream);
@@ -1093,10 +1227,11 @@ struct Engine {
         auto t0 = std::chrono::steady_clock::now();
         volatile HostCtl* ctl = nullptr;
         unsigned long long handled = 0;
-        const bool sync_dump = g_opt.sync_dump || std::getenv("PC_SYNC_DUMP") || host_like || L.kp.clustering || g_resume.write;  // these runs return to the host at every update anyway
+        const bool boosting = L.kp.boost_thin > 0.0;   // the promoted phantoms are collected at every update
+        const bool sync_dump = g_opt.sync_dump || std::getenv("PC_SYNC_DUMP") || host_like || L.kp.clustering || g_resume.write || boosting;  // these runs return to the host at every update anyway
         if (host_like && !resumed) host_generate_live_points();
         const bool want_files = g_files.enabled && nruns == 1;
-        const bool dumping = (dumper != nullptr || want_files) && nruns == 1;
+        const bool dumping = (dumper != nullptr || want_files || boosting) && nruns == 1;
         if (dumping && !sync_dump) {  // asynchronous dumper hand-over
             HostCtl* c = host_ctl();
             std::memset(c, 0, sizeof(*c));
@@ -1164,7 +1299,7 @@ struct Engine {
                     PC_CUDA(cudaStreamSynchronize(stream));
                     write_resume(false);
                 }
-                if (stt == ST_NEED_DEAD || stt == ST_NEED_PHANTOM) { grow(r, stt); regrow = true; }
+                if (stt == ST_NEED_DEAD || stt == ST_NEED_PHANTOM || stt == ST_NEED_BOOST) { grow(r, stt); regrow = true; }
                 if (stt != ST_DONE) all_done = false;
             }
             if (regrow) upload_bufs();
@@ -1727,7 +1862,7 @@ int pc_write_files(const char* base_dir, const char* file_root, int flags, int n
         o.posteriors = flags & 16; o.equals = flags & 32;
         o.num_repeats = num_repeats; o.compression_factor = compression_factor; o.seed = seed;
         FileState st;
-        return write_run_files(o, st, nDims, nDerived, ndead, dead_rows, dead_logw, nlive, live_rows, logZ, logZerr, nlike, true);
+        return write_run_files(o, st, nDims, nDerived, ndead, dead_rows, dead_logw, nlive, live_rows, logZ, logZerr, nlike, true, nullptr);
     } catch (const std::exception& ex) {
         return fail(-1, ex.what());
     }
@@ -1850,6 +1985,20 @@ void polychord_c_interface(pc_loglikelihood_t loglikelihood, pc_prior_t prior, p
                     info.logZ, info.logZerr, info.ndead, info.nlike, info.batch_K, info.kernel_launches, info.device_ms);
         std::fflush(stdout);
     }
+}
+
+// The phantoms the last run promoted to posterior samples (boost_posterior with posteriors or equals set), in the
+// order they are written to the posterior files.  Returns their number; fills up to cap entries.
+long long pc_last_boosted(double* rows, long long* dead_index, double* logw, long long cap, int npars) {
+    const DumpMirror& mr = g_mirror;
+    const long long nb = (long long)mr.boost_logw.size();
+    if (nb && (long long)mr.boost_rows.size() != nb * npars) return -1;
+    for (long long i = 0; i < std::min(nb, cap); ++i) {
+        std::copy(mr.boost_rows.begin() + (size_t)i * npars, mr.boost_rows.begin() + (size_t)(i + 1) * npars, rows + (size_t)i * npars);
+        dead_index[i] = mr.boost_dead[(size_t)i];
+        logw[i] = mr.boost_logw[(size_t)i];
+    }
+    return nb;
 }
 
 // Host-only: the prior transform of an .ini file's parameter block (hypercube_to_physical, priors.f90:494-556) applied

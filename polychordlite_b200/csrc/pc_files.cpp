@@ -82,7 +82,7 @@ void write_prior_info(const FileOpts& o, long long nprior, long long ndiscarded)
 
 int write_run_files(const FileOpts& o, FileState& st, int D, int P, long long ndead, const double* dead_rows,
                     const double* dead_logw, int nlive, const double* live_rows, double logZ, double logZerr,
-                    long long nlike, bool final_call) {
+                    long long nlike, bool final_call, const BoostedRows* boosted) {
     if (!o.enabled) return 0;
     const auto now = std::chrono::steady_clock::now();
     if (!final_call && st.written && std::chrono::duration<double>(now - st.last).count() < o.min_interval_s) return 0;
@@ -124,23 +124,34 @@ int write_run_files(const FileOpts& o, FileState& st, int D, int P, long long nd
     }
 
     // posterior weights: log w_i + log L_i relative to the largest one (maximum weight 1.0, read_write.F90:565-566)
-    double wmax = -std::numeric_limits<double>::infinity();
-    for (long long i = 0; i < ndead; ++i) wmax = std::max(wmax, dead_logw[i]);
-    long long nposterior = 0, nequals = 0;
+    // The posterior samples in file order: the dead points and, after the deaths of the update that removed them, the
+    // phantoms boost_posterior promoted (update_posteriors appends the stack update by update, run_time_info.f90:1036-1061)
+    struct PostRef { const double* row; double lw; uint64_t uid; };
+    std::vector<PostRef> post;
     if (o.posteriors || o.equals || o.write_stats) {
+        const long long nb = boosted ? boosted->n : 0;
+        post.reserve((size_t)(ndead + nb));
+        long long j = 0;
         for (long long i = 0; i < ndead; ++i) {
-            const double wgt = std::exp(dead_logw[i] - wmax);
-            if (wgt > 0.0) ++nposterior;
+            for (; j < nb && boosted->after[j] <= i; ++j)
+                post.push_back({boosted->rows + (size_t)j * npars, boosted->logw[j], (1ull << 40) + (uint64_t)j});
+            post.push_back({dead_rows + (size_t)i * npars, dead_logw[i], (uint64_t)i});
         }
+        for (; j < nb; ++j) post.push_back({boosted->rows + (size_t)j * npars, boosted->logw[j], (1ull << 40) + (uint64_t)j});
     }
+    double wmax = -std::numeric_limits<double>::infinity();
+    for (const PostRef& q : post) wmax = std::max(wmax, q.lw);
+    long long nposterior = 0, nequals = 0;
+    for (const PostRef& q : post)
+        if (std::exp(q.lw - wmax) > 0.0) ++nposterior;
     if (o.posteriors) {  // <root>.txt: weight, -2 logL, theta, phi (written to _temp, then renamed: read_write.F90:600-611)
         const std::string tmp = root + "_temp.txt";
         {
             Out w(tmp);
-            for (long long i = 0; i < ndead; ++i) {
-                const double wgt = std::exp(dead_logw[i] - wmax);
+            for (const PostRef& q : post) {
+                const double wgt = std::exp(q.lw - wmax);
                 if (!(wgt > 0.0)) continue;
-                const double* r = dead_rows + (size_t)i * npars;
+                const double* r = q.row;
                 w.num(wgt);
                 w.num(-2.0 * r[np + 1]);
                 for (int k = 0; k < np; ++k) w.num(r[k]);
@@ -155,17 +166,16 @@ int write_run_files(const FileOpts& o, FileState& st, int D, int P, long long nd
         // reference's incremental thinning in update_posteriors, run_time_info.f90:955-1066); the draw is
         // addressed by the point's index, so successive rewrites agree on the points they share
         const std::string tmp = root + "_equal_weights_temp.txt";
-        std::vector<long long> keep;
-        for (long long i = 0; i < ndead; ++i) {
-            const double u = uniform(o.seed, TAG_POST, (uint64_t)i, 0u, 0u);
-            if (u < std::exp(dead_logw[i] - wmax)) keep.push_back(i);
+        std::vector<const double*> keep;
+        for (const PostRef& q : post) {
+            const double u = uniform(o.seed, TAG_POST, q.uid, 0u, 0u);
+            if (u < std::exp(q.lw - wmax)) keep.push_back(q.row);
         }
         nequals = (long long)keep.size();
         if (o.equals) {
             {
                 Out w(tmp);
-                for (long long i : keep) {
-                    const double* r = dead_rows + (size_t)i * npars;
+                for (const double* r : keep) {
                     w.num(1.0);
                     w.num(-2.0 * r[np + 1]);
                     for (int k = 0; k < np; ++k) w.num(r[k]);
@@ -223,10 +233,10 @@ int write_run_files(const FileOpts& o, FileState& st, int D, int P, long long nd
             w.line("Dim No.       Mean        Sigma");
             std::vector<double> mu(np, 0.0), mu_old(np), logS(np, o.logzero);
             double logwsum = o.logzero;
-            for (long long i = 0; i < ndead; ++i) {
-                if (!(std::exp(dead_logw[i] - wmax) > 0.0)) continue;
-                const double* x = dead_rows + (size_t)i * npars;
-                const double lw = dead_logw[i];
+            for (const PostRef& q : post) {
+                if (!(std::exp(q.lw - wmax) > 0.0)) continue;
+                const double* x = q.row;
+                const double lw = q.lw;
                 mu_old = mu;
                 logwsum = host_logaddexp(logwsum, lw);
                 const double f = std::exp(lw - logwsum);

@@ -32,12 +32,20 @@ struct FileState {
 // value in Fortran E24.15E3 form, 24 characters, no terminator needed by callers (out must hold 25 bytes)
 void format_e24(double v, char* out);
 
+// boost_posterior: phantoms promoted to posterior samples; row i is written after dead row after[i] - 1
+struct BoostedRows {
+    long long n = 0;
+    const double* rows = nullptr;    // [theta(D), phi(P), birth, logL]
+    const double* logw = nullptr;    // unnormalised posterior log-weight
+    const long long* after = nullptr;
+};
+
 // Writes every requested file under base_dir.  dead_rows/live_rows: rows [theta(D), phi(P), birth, logL];
 // dead_logw[i] = log-weight + logL of dead point i (unnormalised posterior log-weight).
 // Returns the number of files written; throws std::runtime_error when a file cannot be opened.
 int write_run_files(const FileOpts& o, FileState& st, int D, int P, long long ndead, const double* dead_rows,
                     const double* dead_logw, int nlive, const double* live_rows, double logZ, double logZerr,
-                    long long nlike, bool final_call);
+                    long long nlike, bool final_call, const BoostedRows* boosted = nullptr);
 
 // generate.F90:274-279
 void write_prior_info(const FileOpts& o, long long nprior, long long ndiscarded);

@@ -25,7 +25,7 @@
 
 namespace pc {
 
-enum Status : int { ST_RUNNING = 0, ST_DONE = 1, ST_NEED_DEAD = 2, ST_NEED_PHANTOM = 3, ST_DUMP = 4, ST_HOSTCHAINS = 5, ST_CLUSTER = 6, ST_ERROR = -1 };
+enum Status : int { ST_RUNNING = 0, ST_DONE = 1, ST_NEED_DEAD = 2, ST_NEED_PHANTOM = 3, ST_DUMP = 4, ST_HOSTCHAINS = 5, ST_CLUSTER = 6, ST_NEED_BOOST = 7, ST_ERROR = -1 };
 
 constexpr double NEG_BIG = -1e300;  // log(0) stand-in that survives additions without NaN
 constexpr int COV_TPP = 10;         // 8x8 tiles of the moment matrix a warp accumulates per pass of phase U (2 registers each)
@@ -76,6 +76,11 @@ struct DevRun {
     unsigned long long pub[8];
     unsigned int bar;    // group barrier, one arrival per CTA (monotonic)
     unsigned int wbar;   // chains-done barrier, one arrival per warp (monotonic)
+    // boost_posterior (clean_phantoms, run_time_info.f90:820-877): phantoms promoted to posterior samples so far
+    // (rb.boost rows), and ndead at the last update -- the deaths after it are the posterior stack a removed
+    // phantom takes its weight from
+    unsigned long long nboost;
+    long long ndead_upd;
 };
 
 // Control block in mapped pinned host memory: the run kernel publishes a dump (run state + a snapshot of the
@@ -110,6 +115,9 @@ struct RunBuf {
     int* lab;          // clustering: label of every live slot
     int* phl[2];       // clustering: label of every phantom record (compacted with the pools)
     double* cchol;     // clustering: Cholesky factor per label, MAX_CLUSTERS x D x D
+    double* boost;     // boost_posterior: cap_boost x (D + P + 2) rows [theta, phi, birth, logL] of promoted phantoms
+    unsigned long long* boost_win;  // ... and the window of dead indices each was removed against: first << 32 | end
+    long long cap_boost;
     long long cap_dead, cap_ph;
     unsigned int seed;
     int pad;
@@ -146,6 +154,7 @@ struct KParams {
     int ntri, cov_passes, partial_stride;
     int off_like, off_warp, warp_bytes;  // shared-memory byte offsets
     double log_prec, log_comp;
+    double boost_thin;           // RTI%thin_posterior (generate.F90:311-316) when posterior files are written, else 0
     const double* like_params;   // gaussian: mu[D], 1/sigma[D]; corr: mu[D], invcov[D*D]
     const double* prior_params;  // lo[D], hi-lo[D]
     RunBuf* runs;

@@ -154,6 +154,11 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
         // sharded run: the decision must be the same on every rank, so it is taken on the phantoms of all ranks
         const long long nph_test = p.sh.world > 1 ? st->nph_glob : st->nphantom;
         if (nph_test + (long long)K * (p.cp.R - 1) > rb.cap_ph) { if (tid == 0) st->status = ST_NEED_PHANTOM; return false; }
+        // boost_posterior: room for every phantom the next update could promote
+        if (p.boost_thin > 0.0 && (long long)st->nboost + st->nphantom + (long long)K * (p.cp.R - 1) > rb.cap_boost) {
+            if (tid == 0) st->status = ST_NEED_BOOST;
+            return false;
+        }
     } else if (ndead + n > rb.cap_dead) {
         if (tid == 0) st->status = ST_NEED_DEAD;
         return false;
@@ -276,12 +281,51 @@ __device__ inline void phase_S2(const KParams& p, const RunBuf& rb, DevRun* st, 
 //   calc_cholesky.
 // Lane r of a warp owns dimension r, r+32, ... of S1 and COV_ACC entries of the packed triangle of S2.
 
+// boost_posterior (clean_phantoms, run_time_info.f90:846-868): a phantom that phase U removes becomes, with
+// probability thin_posterior, a posterior sample carrying the weight of the death since the last update with the
+// smallest logL above its own; the host looks that death up in the window stored with the row (the dead points are
+// in ascending logL).  The trial is addressed by the bits of the phantom's own logL, so it does not depend on the
+// order the phantoms are visited in (the reference draws it from its sequential stream; any fixed addressing gives
+// the same distribution, and the same run promotes the same phantoms every time).
+static __device__ __noinline__ void boost_harvest(const KParams& p, const RunBuf& rb, DevRun* st, const double* rec, unsigned long long win) {
+    const int D = p.cp.D, T = p.cp.T, np = T - D;
+    const double l = __ldcg(rec + T - 1);
+    if (!(l > __ldcg(rec + T - 2))) return;  // a baby at or below its birth contour (a failed slice) never was a phantom (run_time_info.f90:746-757)
+    if (!(uniform(rb.seed, TAG_BOOST, (uint64_t)__double_as_longlong(l), 0u, 0u) < p.boost_thin)) return;
+    const unsigned long long slot = atomicAdd(&st->nboost, 1ULL);
+    if ((long long)slot >= rb.cap_boost) return;  // phase S1 reserved room for every phantom: not reached
+    double* o = rb.boost + (size_t)slot * np;
+    for (int k = 0; k < np; ++k) o[k] = __ldcg(rec + D + k);  // theta, phi, birth contour, logL
+    // Device likelihoods leave a phantom's derived parameters unset (slice_chain only finishes the last baby);
+    // a posterior sample needs them: gaussian.f90:37-40, as Model::finish_derived.  Host-callback runs stored
+    // what the user's likelihood returned.
+    const int P = p.cp.P;
+    if (P > 0 && !p.host_like) {
+        const bool gauss = p.cp.like_kind == LIKE_GAUSSIAN;
+        double r = 0.0;
+        if (gauss) {
+            double r2 = 0.0;
+            for (int d = 0; d < D; ++d) {
+                const double dl = o[d] - __ldg(p.like_params + d);
+                r2 += dl * dl;
+            }
+            r = sqrt(r2);
+        }
+        o[D] = r;
+        if (P >= 2) o[D + 1] = gauss ? log(pow(r, (double)D) * p.cp.Vn) : 0.0;
+        for (int i = 2; i < P; ++i) o[D + i] = 0.0;
+    }
+    rb.boost_win[slot] = win;
+}
+
 __device__ inline void phase_UA(const KParams& p, const RunBuf& rb, DevRun* st, int cta, int NG) {
     const int tid = threadIdx.x, T = p.cp.T;
     const long long total = vload(&st->nphantom);
     const double Lstar = vload(&st->Lstar);
     const double* src = rb.ph[vload(&st->cur_pool)];
     const long long ntiles = (total + U_TILE - 1) / U_TILE;
+    const bool boosting = p.boost_thin > 0.0;
+    const unsigned long long bwin = boosting ? ((unsigned long long)vload(&st->ndead_upd) << 32) | (unsigned long long)vload(&st->ndead) : 0ull;
     // keys of up to four tiles in flight before the first count
     for (long long t0 = cta; t0 < ntiles; t0 += 4LL * NG) {
         bool keep[4];
@@ -289,6 +333,7 @@ __device__ inline void phase_UA(const KParams& p, const RunBuf& rb, DevRun* st, 
         for (int j = 0; j < 4; ++j) {
             const long long t = t0 + (long long)j * NG, rec = t * U_TILE + tid;
             keep[j] = t < ntiles && rec < total && !(Lstar > __ldcg(src + (size_t)rec * T + T - 1));
+            if (boosting && t < ntiles && rec < total && !keep[j]) boost_harvest(p, rb, st, src + (size_t)rec * T, bwin);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -573,6 +618,7 @@ __device__ inline bool finish_update(const KParams& p, const RunBuf& rb, DevRun*
         st->cur_pool ^= 1;
         st->nupdates += 1;
         st->logX_last_update = st->logX;
+        st->ndead_upd = st->ndead;
         st->update_pending = 0;
     }
     __syncthreads();

@@ -111,6 +111,18 @@ def run(settings, like="gaussian", like_params=None, prior_lo=None, prior_hi=Non
     return res, dumps
 
 
+def last_boosted(npars):
+    """Phantoms the last run() promoted to posterior samples: (rows[nb, npars], dead_index[nb], logw[nb])."""
+    L = lib()
+    L.oracle_last_boosted.restype = C.c_longlong
+    L.oracle_last_boosted.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double),
+                                      C.c_longlong, C.c_int]
+    nb = L.oracle_last_boosted(None, None, None, 0, npars)
+    rows, idx, lw = np.zeros((max(nb, 1), npars)), np.zeros(max(nb, 1), dtype=np.int64), np.zeros(max(nb, 1))
+    L.oracle_last_boosted(_dptr(rows), idx.ctypes.data_as(C.POINTER(C.c_longlong)), _dptr(lw), nb, npars)
+    return rows[:nb], idx[:nb], lw[:nb]
+
+
 def slice_chain(settings, seed_point, cholesky, logL, uid, like="gaussian", like_params=None, prior_lo=None,
                 prior_hi=None):
     L = lib()

@@ -8,7 +8,7 @@ ROOT = Path(__file__).resolve().parent.parent
 def declared_symbols():
     text = (ROOT / "include" / "polychord_b200.h").read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    names = re.findall(r"^\s*(?:const\s+)?(?:void|int|double|char\s*\*|const char\s*\*)\s+\**\s*((?:pc_|polychord_)\w+)\s*\(",
+    names = re.findall(r"^\s*(?:const\s+)?(?:void|int|long long|double|char\s*\*|const char\s*\*)\s+\**\s*((?:pc_|polychord_)\w+)\s*\(",
                        text, flags=re.M)
     return sorted(set(names))
 
