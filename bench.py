@@ -166,6 +166,18 @@ def dist_env():
     return rank, world, local
 
 
+def _reference_replica(job):
+    """One oracle run in a worker process (run_reference's all_cores leg); returns its likelihood evaluations."""
+    workload, seed = job
+    import oracle_lib as O
+    w = WORKLOADS[workload]
+    kw = dict(prior_lo=[-w["box"]] * w["nDims"], prior_hi=[w["box"]] * w["nDims"]) if w["box"] else {}
+    s = O.make_settings(w["nDims"], w["nDerived"], nlive=w["nlive"], num_repeats=w["num_repeats"], seed=seed,
+                        batch_K=0, do_clustering=w.get("clustering", False))
+    r, _ = O.run(s, like=w["like"], **kw)
+    return r.nlike
+
+
 def run_reference(args):
     """The reference's CPU path (restated: oracle, reference schedule batch_K=0), one thread."""
     rank, world, _ = dist_env()
@@ -189,6 +201,19 @@ def run_reference(args):
         r, t = one(i)
         tot_e += r.nlike; tot_t += t; lz.append(r.logZ)
     v = tot_e / tot_t
+    # every host core at once: independent runs of the same workload, one per core (an ensemble is the only way the
+    # single-threaded linear mode fills a box; the reference's MPI mode, which spreads ONE run over workers, needs
+    # an MPI library this image does not have)
+    ncores = os.cpu_count() or 1
+    all_cores = None
+    if ncores > 1 and not args.no_all_cores:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(ncores) as pool:
+            t0 = time.perf_counter()
+            res = pool.map(_reference_replica, [(args.workload, 2000 + i) for i in range(ncores)])
+            ta = time.perf_counter() - t0
+        all_cores = {"value": sum(res) / ta, "unit": UNIT, "cores": ncores, "seconds": ta,
+                     "sample": f"{ncores} independent runs of the workload, one per host core, started together"}
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -201,7 +226,7 @@ def run_reference(args):
                                    "cannot be built here (no gfortran/MPI) and its linear mode is single-threaded"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_time_to_logZ_s": tot_t / args.steps, "logZ_mean": sum(lz) / len(lz),
-        "host_cores": os.cpu_count(),
+        "host_cores": os.cpu_count(), "all_cores": all_cores,
     }
     print(json.dumps(line), flush=True)
 
@@ -212,6 +237,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-all-cores", action="store_true", help="reference arm: skip the one-run-per-core ensemble leg")
     ap.add_argument("--workload", default="gaussian20_nlive1000_R40", choices=sorted(WORKLOADS))
     ap.add_argument("--batch-fraction", type=float, default=None)
     ap.add_argument("--warps-per-cta", type=int, default=None)
