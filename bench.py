@@ -421,7 +421,7 @@ def main():
         achieved = (algo_bytes / (world if sharded else 1) / (dev_ms * 1e-3)) / 1e9
         # DRAM bytes of one launch of the run kernel from the committed `ncu --set full` capture of this workload
         traffic = None
-        prof = ROOT / "profiles" / "r01d_ncu_run_kernel.json"
+        prof = ROOT / "profiles" / "r01e_ncu_run_kernel.json"
         if prof.exists() and args.workload == "gaussian20_nlive1000_R40" and world == 1:
             try:
                 traffic = float(json.loads(prof.read_text())["dram_bytes_per_launch"])
@@ -470,7 +470,7 @@ def main():
             "gpu_launches": int(launches_all),
             "phase_ms_last_step": {k: round(v, 3) for k, v in info_dev.as_dict()["phase_ms"].items()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": "profiles/r01d_ncu_run_kernel.json (dram__bytes_read.sum + dram__bytes_write.sum, one launch = one run)" if traffic else None,
+                         "traffic": traffic, "traffic_source": "profiles/r01e_ncu_run_kernel.json (dram__bytes_read.sum + dram__bytes_write.sum, one launch = one run)" if traffic else None,
                          "algorithmic_bytes_per_launch": algo_bytes / args.steps / (world if sharded else 1),
                          "peak_source": which, "kernel": "pc_run_kernel<4,5,0>",
                          "note": "latency-bound persistent kernel; one run occupies ctas_per_run of 148 SMs; "
