@@ -144,3 +144,73 @@ def test_posterior_files_hold_the_boosted_samples(gpu, tmp_path):
         mean = (w[:, None] * post[:, 2:2 + D]).sum(0)
         sd = np.sqrt((w[:, None] * (post[:, 2:2 + D] - mean) ** 2).sum(0))
         assert np.all(np.abs(mean - 0.5) < 0.03) and np.all(np.abs(sd - 0.1) < 0.03)
+
+
+def test_interrupted_boosted_run_resumes_with_the_same_samples(gpu, tmp_path):
+    """The resume file carries the promoted phantoms: an interrupted run picked up from its file
+    ends with the list of the uninterrupted one, bit for bit."""
+    D, P = 6, 1
+    st = gpu.make_settings(D, P, nlive=200, num_repeats=12, seed=11, posteriors=True, boost_posterior=3.0)
+    ref, _ = gpu.run(st, want_dump=True)
+    r0, x0, w0 = gpu.last_boosted(D + P + 2)
+    path = tmp_path / "b.resume"
+    gpu.set_option("errors_return", 1)
+    try:
+        gpu.set_resume(path, write=True)
+        gpu.set_option("resume_interval", 0.0)
+        with pytest.raises(RuntimeError):
+            gpu.run(st, abort_after_dumps=5)
+        assert path.exists()
+        gpu.set_resume(path, read=True)
+        res, _ = gpu.run(st, want_dump=True)
+    finally:
+        gpu.set_resume()
+        gpu.set_option("resume_interval", 1.0)
+        gpu.set_option("errors_return", 0)
+    r1, x1, w1 = gpu.last_boosted(D + P + 2)
+    assert (res.ndead, res.nlike, res.logZ) == (ref.ndead, ref.nlike, ref.logZ)
+    assert len(x0) > ref.ndead // 2
+    assert np.array_equal(x0, x1) and np.array_equal(r0, r1) and np.array_equal(w0, w1)
+
+
+def test_host_callback_run_promotes_the_oracles_phantoms(gpu, oracle, tmp_path):
+    """Generic host callbacks (row f2): the phantoms carry the derived parameters the user's likelihood returned."""
+    D, P, n, R, K = 4, 1, 120, 8, 30
+    sig = 0.1
+
+    def callbacks(capi):
+        def ll(theta_p, nd, phi_p, nder):
+            th = np.ctypeslib.as_array(theta_p, shape=(nd,))
+            r2 = float(np.sum(th ** 2))
+            phi_p[0] = np.sqrt(r2)
+            return -D * (np.log(sig) + 0.5 * np.log(2 * np.pi)) - 0.5 * r2 / sig ** 2
+
+        def prior(cube_p, theta_p, nd):
+            for i in range(nd):
+                theta_p[i] = -1.0 + 2.0 * cube_p[i]
+        return capi.LL_CB(ll), capi.PRIOR_CB(prior)
+
+    ll, prior = callbacks(gpu)
+    L = gpu.lib()
+    L.polychord_c_interface.restype = None
+    L.polychord_c_interface.argtypes = pypolychord.polychord._ARGTYPES
+    gf, gd, comm = (C.c_double * 1)(1.0), (C.c_int * 1)(D), C.c_int(0)
+    gpu.set_option("batch_K", K)
+    try:
+        L.polychord_c_interface(C.cast(ll, C.c_void_p), C.cast(prior, C.c_void_p), None, n, R, -1, -1, False, 0, 1e-3,
+                                -1e30, -1, -1.0, True, False, False, False, False, False, False, False, False, False, False,
+                                float(np.exp(-1)), True, D, P, str(tmp_path).encode(), b"hc", 1, gf, gd, 0, None, None, 11,
+                                C.byref(comm))
+    finally:
+        gpu.set_option("batch_K", 0)
+    info = gpu.last_run_info()
+    assert info.status == 0
+    gr, gx, gw = _canon(*gpu.last_boosted(D + P + 2))
+    oll, oprior = callbacks(oracle)
+    oi, _ = oracle.run(oracle.make_settings(D, P, nlive=n, num_repeats=R, seed=11, batch_K=K, posteriors=True,
+                                            boost_posterior=-1.0), like="callback", ll_cb=oll, prior_cb=oprior)
+    orows, ox, ow = _canon(*oracle.last_boosted(D + P + 2))
+    assert (info.ndead, info.nlike) == (oi.ndead, oi.nlike)
+    assert len(gx) == len(ox) > 0 and np.array_equal(gx, ox)
+    assert np.allclose(gr, orows, rtol=0, atol=1e-6) and np.allclose(gw, ow, rtol=0, atol=1e-6)
+    assert np.all(gr[:, D] > 0)          # phi = |theta| came from the callback
