@@ -254,6 +254,17 @@ int pc_write_files(const char* base_dir, const char* file_root, int flags, int n
  * sample.  Returns the number of samples (fills up to cap), -1 when npars does not match the last run. */
 long long pc_last_boosted(double* rows, long long* dead_index, double* logw, long long cap, int npars);
 
+/* maximise (maximiser.F90, nelder_mead.f90): with the `maximise` flag polychord_c_interface ends by maximising the
+ * likelihood and the posterior with Nelder-Mead from the best nDims + 1 live points and writes <root>.maximum
+ * (write_max_file, read_write.F90:754-807).  The two entry points below are host-only (no device needed).
+ * pc_maximise: live_records = nlive records of 2*nDims + nDerived + 2 doubles [cube | theta | phi | birth | logL];
+ * point_out = one such record, the maximum found.  Returns 0, 1 when no simplex can be built, -1 on bad arguments.
+ * pc_prior_log_density: dXdtheta (maximiser.F90:172-202), the log prior density at a cube point from the
+ * finite-difference Jacobian of the prior transform. */
+int pc_maximise(pc_loglikelihood_t loglikelihood, pc_prior_t prior, int nDims, int nDerived, double logzero,
+                const double* live_records, int nlive, int posterior, double* point_out);
+double pc_prior_log_density(pc_prior_t prior, const double* cube, int nDims);
+
 /* Host-only (no device needed): hypercube_to_physical (priors.f90:494-556) of the parameter block of an .ini file in the
  * reference's format (ini.f90:354-458), applied to one cube point: the separable families, their sorted forms, the
  * adaptive sorted families and nn_adaptive_layer_gaussian (priors.f90:40-488).  This is the transform

@@ -22,6 +22,7 @@
 #include "pc_probes.cuh"
 #include "pc_files.h"
 #include "pc_ini.h"
+#include "pc_maximise.h"
 #include "pc_hostchain.cuh"
 #include "pc_cluster.cuh"
 #include "pc_shapes.h"
@@ -105,6 +106,10 @@ struct DumpMirror {
     std::vector<long long> boost_dead, boost_after;
 };
 static DumpMirror g_mirror;
+// `maximise`: the live points the sampling loop ended with (full records, cube coordinates included) -- the simplex
+// of the maximiser is built from them (maximiser.F90:117-135).  Filled by Engine::run when want is set.
+struct FinalLive { bool want = false; int n = 0; std::vector<double> recs; };
+static FinalLive g_final_live;
 static int sm_clock_khz() {  // cudaDevAttrClockRate is a slow driver query (milliseconds): ask once per device
     static std::map<int, int> cache;
     int dev = 0;
@@ -1306,6 +1311,15 @@ struct Engine {
             if (all_done) break;
         }
         if (g_mgpu.world > 1) g_mgpu.epoch = runs[0].host_st.xepoch;
+        if (g_final_live.want && nruns == 1 && runs[0].host_st.ndead >= L.kp.n) {
+            // the final kill-off appended the n live points, lowest logL first: they are the last n dead records
+            const size_t n = (size_t)L.kp.n, T = (size_t)L.kp.cp.T;
+            g_final_live.n = (int)n;
+            g_final_live.recs.resize(n * T);
+            runs[0].dead.download(g_final_live.recs.data(), n * T, stream, ((size_t)runs[0].host_st.ndead - n) * T);
+            PC_CUDA(cudaStreamSynchronize(stream));
+            d2h += (long long)(n * T * 8);
+        }
         auto tfin = now();
         if (dumping)  // the final call: every point is dead (nested_sampling.F90:392)
             for (int r = 0; r < nruns; ++r)
@@ -1868,6 +1882,50 @@ int pc_write_files(const char* base_dir, const char* file_root, int flags, int n
     }
 }
 
+// Host-only entry points of the maximiser (csrc/pc_maximise.cpp), see the header.
+int pc_maximise(pc_loglikelihood_t loglikelihood, pc_prior_t prior, int nDims, int nDerived, double logzero,
+                const double* live_records, int nlive, int posterior, double* point_out) {
+    if (!loglikelihood || !prior || !live_records || !point_out || nDims < 1 || nDerived < 0) return -1;
+    return do_maximisation(loglikelihood, prior, nDims, nDerived, logzero, live_records, nlive, posterior != 0, point_out) ? 0 : 1;
+}
+double pc_prior_log_density(pc_prior_t prior, const double* cube, int nDims) { return maximise_dXdtheta(prior, cube, nDims); }
+
+// maximise (maximiser.F90:31-77) after a run through polychord_c_interface: likelihood and posterior maxima from the
+// live points the run ended with, the posterior mean when posteriors are kept, <root>.maximum.
+static void run_maximiser(pc_loglikelihood_t ll, pc_prior_t prior, const pc_settings& s, const FileOpts& fo, const pc_run_info& info,
+                          int feedback) {
+    const int D = s.nDims, P = s.nDerived, T = 2 * D + P + 2;
+    if (!ll || !prior) throw std::invalid_argument("polychord_b200: maximise needs the loglikelihood and prior callbacks");
+    if (g_final_live.n < 1) throw std::runtime_error("polychord_b200: maximise: the run left no live points");
+    std::vector<double> mp(T, 0.0), pp(T, 0.0), mean(T, 0.0);
+    if (feedback >= 1) std::printf("-------------------------------------\nMaximising Likelihood\n");
+    const bool ok1 = do_maximisation(ll, prior, D, P, s.logzero, g_final_live.recs.data(), g_final_live.n, false, mp.data());
+    if (feedback >= 1) std::printf("-------------------------------------\nMaximising Posterior\n");
+    const bool ok2 = do_maximisation(ll, prior, D, P, s.logzero, g_final_live.recs.data(), g_final_live.n, true, pp.data());
+    if ((!ok1 || !ok2) && feedback >= 0) std::printf(" Could not construct simplex\n");
+    const double dx = maximise_dXdtheta(prior, pp.data(), D);
+    const bool with_mean = s.posteriors && info.ndead > 0;
+    if (with_mean) {  // mean (read_write.F90:912-934) over the weighted posterior the run ended with
+        const DumpMirror& mr = g_mirror;
+        const int npars = D + P + 2;
+        double logwsum = s.logzero;
+        std::vector<double> mu(D + P, 0.0);
+        auto add = [&](const double* x, double lw) {
+            const double m = std::max(logwsum, lw);
+            logwsum = m + std::log(std::exp(logwsum - m) + std::exp(lw - m));
+            const double f = std::exp(lw - logwsum);
+            for (int k = 0; k < D + P; ++k) mu[k] += f * (x[k] - mu[k]);
+        };
+        for (long long i = 0; i < info.ndead; ++i) add(&mr.rows[(size_t)i * npars], mr.logw[(size_t)i]);
+        for (size_t j = 0; j < mr.boost_logw.size(); ++j) add(&mr.boost_rows[j * npars], mr.boost_logw[j]);
+        std::copy(mu.begin(), mu.end(), mean.begin() + D);
+        std::vector<double> phi(std::max(P, 1), 0.0);
+        mean[T - 1] = ll(mean.data() + D, D, phi.data(), P);
+    }
+    write_max_file(fo.base_dir + "/" + fo.file_root + ".maximum", D, P, mp.data(), pp.data(), dx, with_mean ? mean.data() : nullptr);
+    std::fflush(stdout);
+}
+
 // ==========================================================================================
 // Drop-in boundary
 // ==========================================================================================
@@ -1880,7 +1938,7 @@ void polychord_c_interface(pc_loglikelihood_t loglikelihood, pc_prior_t prior, p
                            pc_bool synchronous, int nDims, int nDerived, char* base_dir, char* file_root, int nGrade,
                            double* grade_frac, int* grade_dims, int n_nlives, double* loglikes, int* nlives, int seed,
                            int* comm) {
-    (void)write_paramnames; (void)maximise; (void)synchronous; (void)grade_frac;
+    (void)write_paramnames; (void)synchronous; (void)grade_frac;
     (void)loglikes; (void)nlives; (void)comm; (void)nfail; (void)do_clustering;
     std::memset(&g_last, 0, sizeof(g_last));
     g_abort = 0;
@@ -1971,8 +2029,13 @@ void polychord_c_interface(pc_loglikelihood_t loglikelihood, pc_prior_t prior, p
         ~FilesGuard() { g_files.enabled = false; }
     } files_guard(fo);
     pc_run_info info;
+    struct FinalLiveGuard {
+        FinalLiveGuard(bool w) { g_final_live.want = w; g_final_live.n = 0; }
+        ~FinalLiveGuard() { g_final_live.want = false; g_final_live.recs.clear(); }
+    } final_live_guard(maximise);
     try {
         run_common(&s, ms, 1, &seed, dumper, &info);
+        if (maximise) run_maximiser(loglikelihood, prior, s, fo, info, feedback);
     } catch (const std::invalid_argument& ex) {
         fail(-2, ex.what());
         return;
