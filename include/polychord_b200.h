@@ -254,6 +254,14 @@ int pc_write_files(const char* base_dir, const char* file_root, int flags, int n
  * sample.  Returns the number of samples (fills up to cap), -1 when npars does not match the last run. */
 long long pc_last_boosted(double* rows, long long* dead_index, double* logw, long long cap, int npars);
 
+/* cube_samples (pypolychord.run, polychord.py:452, 576-579): the next run through polychord_c_interface starts from
+ * these live points instead of drawing them from the prior: npoints x nDims cube coordinates, row-major, copied.  They
+ * are evaluated through the run's own callbacks on the calling thread and enter with birth contour logzero.  The
+ * reference passes them through a resume file (_make_resume_file, polychord.py:650-789) and lets its dynamic-nlive
+ * mechanism absorb a count different from nlive; this engine wants exactly nlive of them.  One-shot; NULL or 0 clears.
+ * Returns 0, -1 on bad arguments; a mismatch with the run's shape is reported by the run. */
+int pc_set_initial_live(const double* cube_samples, int npoints, int nDims);
+
 /* maximise (maximiser.F90, nelder_mead.f90): with the `maximise` flag polychord_c_interface ends by maximising the
  * likelihood and the posterior with Nelder-Mead from the best nDims + 1 live points and writes <root>.maximum
  * (write_max_file, read_write.F90:754-807).  The two entry points below are host-only (no device needed).

@@ -406,6 +406,7 @@ struct Cluster {
 std::vector<int> g_grade_dims, g_grade_repeats;   // set by oracle_set_grades, read by every Run until cleared
 // phantoms promoted to posterior samples by the last run (clean_phantoms, run_time_info.f90:820-877), read by
 // oracle_last_boosted: rows [theta, phi, birth, logL], the dead point whose weight each one carries, log-weight + logL
+std::vector<double> g_init_cubes;   // oracle_set_initial_cubes: the next run's live points (cube_samples), one-shot
 std::vector<double> g_boost_rows, g_boost_logw;
 std::vector<long long> g_boost_dead;
 
@@ -1093,6 +1094,20 @@ struct Run {
         Cluster& c = cl[0];
         std::vector<double> pt(T);
         uint64_t attempt = 0;
+        if (!g_init_cubes.empty()) {   // cube_samples (polychord.py:650-789): the caller's live points, born from the prior
+            const int npts = (int)(g_init_cubes.size() / D);
+            for (int j = 0; j < npts; ++j) {
+                std::fill(pt.begin(), pt.end(), 0.0);
+                std::copy(g_init_cubes.begin() + (size_t)j * D, g_init_cubes.begin() + (size_t)(j + 1) * D, pt.begin() + h0);
+                calculate_point(pt.data(), nlike);
+                pt[b0] = S.logzero;
+                c.live.insert(c.live.end(), pt.begin(), pt.end());
+                c.nlive++;
+            }
+            g_init_cubes.clear();
+            find_min();
+            return;
+        }
         while (c.nlive < nprior) {
             std::fill(pt.begin(), pt.end(), 0.0);
             for (int k = 0; k < D; ++k) pt[h0 + k] = rng.uniform(TAG_INIT, attempt, (uint32_t)k, 0);
@@ -1382,6 +1397,11 @@ int oracle_calculate_points(const oracle_settings* s, int like_kind, const doubl
     long long n = 0;
     for (int i = 0; i < npts; ++i) run.calculate_point(records + (size_t)i * run.T, n);
     return (int)n;
+}
+
+// cube_samples: the live points the next oracle_run starts from (npoints x nDims cube coordinates), one-shot.
+void oracle_set_initial_cubes(const double* cubes, int npoints, int nDims) {
+    g_init_cubes.assign(cubes, cubes + (size_t)npoints * nDims);
 }
 
 // The phantoms the last oracle_run promoted to posterior samples (boost_posterior with posteriors or equals set):

@@ -27,7 +27,7 @@ EXPORTS = [
     "pc_unit_prior", "pc_uniform_prior", "pc_set_option", "pc_get_option", "pc_set_stream", "pc_release_memory", "pc_mgpu_create", "pc_mgpu_attach", "pc_mgpu_destroy",
     "pc_last_run_info", "pc_run", "pc_run_ensemble", "pc_slice_chains", "pc_calculate_points",
     "pc_device_philox", "pc_device_uniforms", "pc_device_inv_normal_cdf", "pc_device_directions",
-    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points", "pc_set_grades", "pc_set_resume", "pc_measure_fp64_tflops", "pc_ini_prior_transform", "pc_last_boosted", "pc_maximise", "pc_prior_log_density",
+    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points", "pc_set_grades", "pc_set_resume", "pc_measure_fp64_tflops", "pc_ini_prior_transform", "pc_last_boosted", "pc_maximise", "pc_prior_log_density", "pc_set_initial_live",
 ]
 
 
@@ -145,6 +145,18 @@ def run(settings, like="gaussian", like_params=None, prior_lo=None, prior_hi=Non
     if rc != 0:
         raise RuntimeError(f"pc_run failed with status {rc}")
     return info, dumps
+
+
+def set_initial_live(cube_samples=None):
+    """pc_set_initial_live: the next run through polychord_c_interface starts from these cube points (None clears)."""
+    L = lib()
+    L.pc_set_initial_live.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int]
+    if cube_samples is None:
+        L.pc_set_initial_live(None, 0, 0)
+        return
+    a = np.ascontiguousarray(cube_samples, dtype=np.float64)
+    if a.ndim != 2 or L.pc_set_initial_live(_dptr(a), a.shape[0], a.shape[1]) != 0:
+        raise ValueError("cube_samples must be a (npoints, nDims) array")
 
 
 def last_boosted(npars):

@@ -189,6 +189,12 @@ struct Options {
 static Options g_opt;
 static volatile int g_abort = 0;                  // pc_request_abort(): a host callback asks the run in flight to stop
 static std::vector<int> g_grade_dims, g_grade_reps;   // fast/slow grades of the following runs (pc_set_grades)
+// cube_samples (polychord.py:576-579, _make_resume_file :650-789): the caller's initial live points, cube coordinates,
+// consumed by the next run through polychord_c_interface (one-shot, pc_set_initial_live)
+static std::vector<double> g_init_cubes;
+static int g_init_n = 0, g_init_D = 0;
+static pc_loglikelihood_t g_init_ll = nullptr;    // the run's callbacks, to evaluate those points on the calling thread
+static pc_prior_t g_init_prior = nullptr;
 static pc_loglikelihood_t g_host_ll = nullptr;   // host-callback run in flight (PC_LIKE_HOST)
 static pc_prior_t g_host_prior = nullptr;
 struct ResumeOpts {   // <base_dir>/<file_root>.resume
@@ -307,6 +313,7 @@ static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const Dev
     if (s.nlive < 2) throw std::invalid_argument("polychord_b200: nlive must be >= 2");
     L.fn = pick_shape(D, ms.like_kind == PC_LIKE_HOST ? PC_LIKE_GAUSSIAN : ms.like_kind);
     k.host_like = ms.like_kind == PC_LIKE_HOST ? 1 : 0;
+    k.live_given = k.host_like;
     const int npt = 32 / L.fn.G;
     k.cp.D = D; k.cp.P = P; k.cp.T = 2 * D + P + 2; k.cp.R = R;
     k.cp.ngrade = 1;
@@ -450,6 +457,7 @@ struct Engine {
     bool resume_written = false;
     // host-callback runs (pc_hostchain.cuh)
     bool host_like = false;
+    bool given_live = false;   // the initial live points are the caller's cube_samples
     DevArr<unsigned char> hc_scratch;
     DevArr<double> hc_x;
     DevArr<HcChain> hc_ch;
@@ -468,6 +476,38 @@ struct Engine {
 
     // GenerateLivePoints (generate.F90:153-183) with host callbacks: attempt a draws cube = U(TAG_INIT, a, dim) on the
     // device -- the same counter-addressed numbers the device path uses -- and is kept when logL > logzero.
+    // cube_samples: the initial live points are the caller's (polychord.py:650-789 writes them into a resume file the
+    // Fortran then reads; here they are evaluated through the run's callbacks and uploaded).  Born from the prior
+    // (birth contour logzero); a point the likelihood excludes is fatal.
+    void host_given_live_points() {
+        const KParams& k = L.kp;
+        const int D = k.cp.D, P = k.cp.P, T = k.cp.T, n = k.n;
+        std::vector<double> live((size_t)n * T, 0.0), cube(D), theta(D), phi(std::max(P, 1));
+        for (int j = 0; j < n; ++j) {
+            double* rec = &live[(size_t)j * T];
+            std::copy(g_init_cubes.begin() + (size_t)j * D, g_init_cubes.begin() + (size_t)(j + 1) * D, rec);
+            for (int i = 0; i < D; ++i)
+                if (!(rec[i] >= 0.0 && rec[i] <= 1.0)) throw std::invalid_argument("polychord_b200: cube_samples must lie in the unit hypercube");
+            std::copy(rec, rec + D, cube.begin());
+            std::fill(phi.begin(), phi.end(), 0.0);
+            g_init_prior(cube.data(), theta.data(), D);
+            const double logL = g_init_ll(theta.data(), D, phi.data(), P);
+            if (!(logL > S.logzero)) throw std::invalid_argument("polychord_b200: a cube_samples point has loglikelihood <= logzero");
+            std::copy(theta.begin(), theta.end(), rec + D);
+            for (int i = 0; i < P; ++i) rec[2 * D + i] = phi[i];
+            rec[2 * D + P] = S.logzero;
+            rec[2 * D + P + 1] = logL;
+        }
+        DevRun h0;
+        std::memset(&h0, 0, sizeof(h0));
+        h0.nlike = n;
+        h0.init_attempts = n;
+        runs[0].live.upload(live.data(), live.size(), stream);
+        runs[0].st.upload(&h0, 1, stream);
+        h2d += (long long)live.size() * 8;
+        PC_CUDA(cudaStreamSynchronize(stream));
+    }
+
     void host_generate_live_points() {
         const KParams& k = L.kp;
         const int D = k.cp.D, P = k.cp.P, T = k.cp.T, n = k.n;
@@ -605,6 +645,16 @@ struct Engine {
         const int K = k.batch_K;
         // do_clustering: one run on one GPU with a device likelihood; elsewhere the run stays one cluster (always valid)
         k.clustering = (S.do_clustering && nruns == 1 && g_mgpu.world <= 1 && !host_like) ? 1 : 0;
+        given_live = false;
+        if (g_init_n > 0) {
+            if (nruns != 1 || g_mgpu.world > 1) throw std::invalid_argument("polychord_b200: cube_samples start one run on one GPU");
+            if (g_init_n != k.n || g_init_D != k.cp.D)
+                throw std::invalid_argument("polychord_b200: cube_samples must hold nlive points of nDims coordinates (a different "
+                                            "number would need the dynamic-nlive schedule, which this engine does not have)");
+            if (!g_init_ll || !g_init_prior) throw std::invalid_argument("polychord_b200: cube_samples need the run's callbacks");
+            given_live = true;
+            k.live_given = 1;
+        }
         // boost_posterior: RTI%thin_posterior (generate.F90:311-316), in force when posterior samples are asked for
         // (run_time_info.f90:858); one run on one GPU (the phantoms of a sharded run stay with their ranks)
         k.boost_thin = 0.0;
@@ -1234,7 +1284,8 @@ struct Engine {
         unsigned long long handled = 0;
         const bool boosting = L.kp.boost_thin > 0.0;   // the promoted phantoms are collected at every update
         const bool sync_dump = g_opt.sync_dump || std::getenv("PC_SYNC_DUMP") || host_like || L.kp.clustering || g_resume.write || boosting;  // these runs return to the host at every update anyway
-        if (host_like && !resumed) host_generate_live_points();
+        if (given_live && !resumed) host_given_live_points();
+        else if (host_like && !resumed) host_generate_live_points();
         const bool want_files = g_files.enabled && nruns == 1;
         const bool dumping = (dumper != nullptr || want_files || boosting) && nruns == 1;
         if (dumping && !sync_dump) {  // asynchronous dumper hand-over
@@ -1882,6 +1933,17 @@ int pc_write_files(const char* base_dir, const char* file_root, int flags, int n
     }
 }
 
+// cube_samples: the initial live points of the next run through polychord_c_interface (see the header)
+int pc_set_initial_live(const double* cube_samples, int npoints, int nDims) {
+    g_init_cubes.clear();
+    g_init_n = g_init_D = 0;
+    if (!cube_samples || npoints <= 0) return 0;
+    if (nDims < 1) return -1;
+    g_init_cubes.assign(cube_samples, cube_samples + (size_t)npoints * nDims);
+    g_init_n = npoints; g_init_D = nDims;
+    return 0;
+}
+
 // Host-only entry points of the maximiser (csrc/pc_maximise.cpp), see the header.
 int pc_maximise(pc_loglikelihood_t loglikelihood, pc_prior_t prior, int nDims, int nDerived, double logzero,
                 const double* live_records, int nlive, int posterior, double* point_out) {
@@ -2029,6 +2091,10 @@ void polychord_c_interface(pc_loglikelihood_t loglikelihood, pc_prior_t prior, p
         ~FilesGuard() { g_files.enabled = false; }
     } files_guard(fo);
     pc_run_info info;
+    struct InitLiveGuard {   // cube_samples are for this run only
+        InitLiveGuard(pc_loglikelihood_t l, pc_prior_t p) { g_init_ll = l; g_init_prior = p; }
+        ~InitLiveGuard() { g_init_ll = nullptr; g_init_prior = nullptr; g_init_n = 0; g_init_cubes.clear(); }
+    } init_live_guard(loglikelihood, prior);
     struct FinalLiveGuard {
         FinalLiveGuard(bool w) { g_final_live.want = w; g_final_live.n = 0; }
         ~FinalLiveGuard() { g_final_live.want = false; g_final_live.recs.clear(); }

@@ -151,6 +151,7 @@ struct KParams {
     int nh_in_smem, want_dump;
     int clustering;              // 1: do_clustering -- the kernel leaves at every update for the clustering pass (pc_cluster.cuh)
     int host_like;               // 1: likelihood/prior are host callbacks -- the kernel leaves before the chain phase (pc_hostchain.cuh)
+    int live_given;              // 1: the host uploaded the initial live points (host callbacks, or the caller's cube_samples)
     int ntri, cov_passes, partial_stride;
     int off_like, off_warp, warp_bytes;  // shared-memory byte offsets
     double log_prec, log_comp;

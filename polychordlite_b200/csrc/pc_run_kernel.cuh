@@ -28,8 +28,8 @@ __device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st
             st->logX = st->logXX = 0.0;
             st->logX_last_update = 0.0;
             st->ncl = 1;
-            st->init_need = p.host_like ? 0 : n;   // host-callback runs: the host evaluated and uploaded the live points
-            if (!p.host_like) st->init_attempts = 0;
+            st->init_need = p.live_given ? 0 : n;   // host-callback runs, cube_samples: the host evaluated and uploaded the live points
+            if (!p.live_given) st->init_attempts = 0;
         }
     }
     group_sync(&st->bar, NG);

@@ -57,7 +57,7 @@ def run(loglikelihood, nDims, **kwargs):
         'write_paramnames': False, 'read_resume': True, 'write_stats': True, 'write_live': True,
         'write_dead': True, 'write_prior': True, 'maximise': False, 'compression_factor': np.exp(-1),
         'synchronous': True, 'base_dir': 'chains', 'file_root': 'test', 'cluster_dir': 'clusters',
-        'grade_dims': [nDims], 'nlives': {}, 'seed': -1,
+        'grade_dims': [nDims], 'nlives': {}, 'seed': -1, 'cube_samples': None,
     }
     default_kwargs['grade_frac'] = ([1.0] * len(default_kwargs['grade_dims']) if 'grade_dims' not in kwargs
                                     else [1.0] * len(kwargs['grade_dims']))
@@ -155,6 +155,15 @@ def run(loglikelihood, nDims, **kwargs):
     # under Python report them as exceptions instead
     old_err = _capi.get_option("errors_return")
     _capi.set_option("errors_return", 1)
+    if kwargs.get('cube_samples') is not None:
+        # polychord.py:576-579: the run starts from the caller's live points.  The reference writes them into a resume
+        # file and lets the dynamic-nlive mechanism absorb a count other than nlive; this engine takes exactly nlive.
+        cs = np.asarray(kwargs['cube_samples'], dtype=np.float64)
+        if cs.ndim != 2 or cs.shape != (int(kwargs['nlive']), nDims):
+            _capi.set_option("errors_return", old_err)
+            raise ValueError("cube_samples must have shape (nlive, nDims): the B200 engine has no dynamic nlive to absorb "
+                             "a different number of starting points")
+        _capi.set_initial_live(cs)
     try:
         _call(L, like_fn, prior_fn, dcb, kwargs, nDims, nDerived, ngrade, grade_frac, grade_dims, nl, loglikes,
               nlives, comm)
@@ -202,6 +211,8 @@ def run_polychord(loglikelihood, nDims, nDerived, settings, prior=default_prior,
         'write_paramnames', 'read_resume', 'write_stats', 'write_live', 'write_dead', 'write_prior', 'maximise',
         'compression_factor', 'synchronous', 'base_dir', 'file_root', 'grade_dims', 'nlives', 'seed')}
     kw['grade_frac'] = settings.grade_frac
+    if getattr(settings, 'cube_samples', None) is not None:   # polychord.py:157-158
+        kw['cube_samples'] = settings.cube_samples
     lite = run(loglikelihood, nDims, nDerived=nDerived, prior=prior, dumper=dumper, _legacy_output=True, **kw)
     if settings.write_stats:  # polychord.py:218: PolyChordOutput(base_dir, file_root), parsed from <root>.stats
         out = PolyChordOutput(settings.base_dir, settings.file_root)

@@ -111,6 +111,15 @@ def run(settings, like="gaussian", like_params=None, prior_lo=None, prior_hi=Non
     return res, dumps
 
 
+def set_initial_cubes(cubes):
+    """cube_samples: the next run() starts from these live points."""
+    cubes = np.ascontiguousarray(cubes, dtype=np.float64)
+    L = lib()
+    L.oracle_set_initial_cubes.restype = None
+    L.oracle_set_initial_cubes.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int]
+    L.oracle_set_initial_cubes(_dptr(cubes), cubes.shape[0], cubes.shape[1])
+
+
 def last_boosted(npars):
     """Phantoms the last run() promoted to posterior samples: (rows[nb, npars], dead_index[nb], logw[nb])."""
     L = lib()
