@@ -406,6 +406,10 @@ struct Cluster {
 std::vector<int> g_grade_dims, g_grade_repeats;   // set by oracle_set_grades, read by every Run until cleared
 // phantoms promoted to posterior samples by the last run (clean_phantoms, run_time_info.f90:820-877), read by
 // oracle_last_boosted: rows [theta, phi, birth, logL], the dead point whose weight each one carries, log-weight + logL
+// dynamic nlive (settings%loglikes / settings%nlives, sorted by loglike: settings.f90:234-235), oracle_set_nlives;
+// read by the reference schedule of every Run until cleared
+std::vector<double> g_dyn_loglikes;
+std::vector<int> g_dyn_nlives;
 std::vector<double> g_init_cubes;   // oracle_set_initial_cubes: the next run's live points (cube_samples), one-shot
 std::vector<double> g_boost_rows, g_boost_logw;
 std::vector<long long> g_boost_dead;
@@ -744,7 +748,14 @@ struct Run {
         bool replaced = false;
         if (pt[l0] > logL) {
             if (identify_cluster(pt) == cluster_add) {
+                // run_time_info.f90:766-771: the target is that of the largest threshold below the contour
                 int nlive = S.nlive;
+                {
+                    int best = -1;
+                    for (size_t q = 0; q < g_dyn_loglikes.size(); ++q)
+                        if (logL > g_dyn_loglikes[q] && (best < 0 || g_dyn_loglikes[q] > g_dyn_loglikes[(size_t)best])) best = (int)q;
+                    if (best >= 0) nlive = g_dyn_nlives[(size_t)best];
+                }
                 if (total_live() >= std::max(nlive, 1)) {
                     delete_outermost_point();
                     replaced = true;
@@ -1397,6 +1408,13 @@ int oracle_calculate_points(const oracle_settings* s, int like_kind, const doubl
     long long n = 0;
     for (int i = 0; i < npts; ++i) run.calculate_point(records + (size_t)i * run.T, n);
     return (int)n;
+}
+
+// Dynamic nlive for the following runs in the reference schedule (batch_K = 0): above the contour loglikes[i] the
+// target number of live points is nlives[i] (run_time_info.f90:766-777); m = 0 clears.
+void oracle_set_nlives(const double* loglikes, const int* nlives, int m) {
+    g_dyn_loglikes.assign(loglikes, loglikes + m);
+    g_dyn_nlives.assign(nlives, nlives + m);
 }
 
 // cube_samples: the live points the next oracle_run starts from (npoints x nDims cube coordinates), one-shot.

@@ -111,6 +111,17 @@ def run(settings, like="gaussian", like_params=None, prior_lo=None, prior_hi=Non
     return res, dumps
 
 
+def set_nlives(schedule=None):
+    """Dynamic nlive of the following reference-schedule runs: {loglike threshold: nlive}; None or {} clears."""
+    L = lib()
+    L.oracle_set_nlives.restype = None
+    L.oracle_set_nlives.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
+    items = sorted((schedule or {}).items())
+    ll = (C.c_double * max(len(items), 1))(*[float(k) for k, _ in items])
+    nl = (C.c_int * max(len(items), 1))(*[int(v) for _, v in items])
+    L.oracle_set_nlives(ll, nl, len(items))
+
+
 def set_initial_cubes(cubes):
     """cube_samples: the next run() starts from these live points."""
     cubes = np.ascontiguousarray(cubes, dtype=np.float64)
