@@ -280,6 +280,15 @@ double pc_prior_log_density(pc_prior_t prior, const double* cube, int nDims);
  * when nDims is not the file's parameter count. */
 int pc_ini_prior_transform(const char* inifile, const double* cube, double* theta, int nDims);
 
+/* pc_write_files with the phantoms boost_posterior promoted (see pc_last_boosted): boosted_rows like dead_rows,
+ * boosted_logw[i] = log weight + logL, boosted_after[i] (ascending) = the number of dead rows that precede sample i in
+ * the posterior files -- the deaths up to the update that removed it (update_posteriors, run_time_info.f90:1036-1061). */
+int pc_write_files_boosted(const char* base_dir, const char* file_root, int flags, int nDims, int nDerived, long long ndead,
+                           const double* dead_rows, const double* dead_logw, int nlive, const double* live_rows, double logZ,
+                           double logZerr, long long nlike, int num_repeats, double compression_factor, unsigned seed,
+                           long long nboosted, const double* boosted_rows, const double* boosted_logw,
+                           const long long* boosted_after);
+
 /* NN_clustering (clustering.f90:15-97) of m points (row-major m x nDims cube coordinates) exactly as the engine's
  * update runs it (device k-nearest-neighbour lists, host union-find); labels in order of first appearance.
  * Returns the number of clusters. */

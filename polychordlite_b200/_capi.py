@@ -27,7 +27,7 @@ EXPORTS = [
     "pc_unit_prior", "pc_uniform_prior", "pc_set_option", "pc_get_option", "pc_set_stream", "pc_release_memory", "pc_mgpu_create", "pc_mgpu_attach", "pc_mgpu_destroy",
     "pc_last_run_info", "pc_run", "pc_run_ensemble", "pc_slice_chains", "pc_calculate_points",
     "pc_device_philox", "pc_device_uniforms", "pc_device_inv_normal_cdf", "pc_device_directions",
-    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points", "pc_set_grades", "pc_set_resume", "pc_measure_fp64_tflops", "pc_ini_prior_transform", "pc_last_boosted", "pc_maximise", "pc_prior_log_density", "pc_set_initial_live",
+    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points", "pc_set_grades", "pc_set_resume", "pc_measure_fp64_tflops", "pc_ini_prior_transform", "pc_last_boosted", "pc_maximise", "pc_prior_log_density", "pc_set_initial_live", "pc_write_files_boosted",
 ]
 
 
@@ -312,9 +312,29 @@ def format_e24(value):
 
 def write_files(base_dir, file_root, nDims, nDerived, dead_rows, dead_logw, live_rows, logZ, logZerr, nlike,
                 num_repeats, compression_factor=float(np.exp(-1)), seed=0, flags=("stats", "live", "dead", "posteriors",
-                                                                                  "equals")):
-    """pc_write_files: the engine's file writer driven with explicit arrays (no device needed)."""
+                                                                                  "equals"), boosted=None):
+    """pc_write_files: the engine's file writer driven with explicit arrays (no device needed).
+    boosted = (rows, logw, after): pc_write_files_boosted."""
     L = lib()
+    if boosted is not None:
+        brows = np.ascontiguousarray(boosted[0], dtype=np.float64).reshape(-1, nDims + nDerived + 2)
+        blogw = np.ascontiguousarray(boosted[1], dtype=np.float64)
+        bafter = np.ascontiguousarray(boosted[2], dtype=np.int64)
+        dead_rows = np.ascontiguousarray(dead_rows, dtype=np.float64).reshape(-1, nDims + nDerived + 2)
+        live_rows = np.ascontiguousarray(live_rows, dtype=np.float64).reshape(-1, nDims + nDerived + 2)
+        dead_logw = np.ascontiguousarray(dead_logw, dtype=np.float64)
+        L.pc_write_files_boosted.restype = C.c_int
+        L.pc_write_files_boosted.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_longlong,
+                                             C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double),
+                                             C.c_double, C.c_double, C.c_longlong, C.c_int, C.c_double, C.c_uint,
+                                             C.c_longlong, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                             C.POINTER(C.c_longlong)]
+        fl = sum(FILE_FLAGS[f] for f in flags)
+        return L.pc_write_files_boosted(str(base_dir).encode(), str(file_root).encode(), fl, nDims, nDerived,
+                                        dead_rows.shape[0], _dptr(dead_rows), _dptr(dead_logw), live_rows.shape[0],
+                                        _dptr(live_rows), float(logZ), float(logZerr), int(nlike), int(num_repeats),
+                                        float(compression_factor), int(seed), brows.shape[0], _dptr(brows), _dptr(blogw),
+                                        bafter.ctypes.data_as(C.POINTER(C.c_longlong)))
     dead_rows = np.ascontiguousarray(dead_rows, dtype=np.float64).reshape(-1, nDims + nDerived + 2)
     live_rows = np.ascontiguousarray(live_rows, dtype=np.float64).reshape(-1, nDims + nDerived + 2)
     dead_logw = np.ascontiguousarray(dead_logw, dtype=np.float64)

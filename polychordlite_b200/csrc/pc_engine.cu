@@ -1916,9 +1916,10 @@ int pc_cluster_points(const double* points, int m, int D, int* labels_out) {
 
 // ---- output files (host only; no device needed) -------------------------------------------------
 void pc_format_e24(double v, char* out25) { format_e24(v, out25); }
-int pc_write_files(const char* base_dir, const char* file_root, int flags, int nDims, int nDerived, long long ndead,
-                   const double* dead_rows, const double* dead_logw, int nlive, const double* live_rows, double logZ,
-                   double logZerr, long long nlike, int num_repeats, double compression_factor, unsigned seed) {
+static int write_files_common(const char* base_dir, const char* file_root, int flags, int nDims, int nDerived, long long ndead,
+                              const double* dead_rows, const double* dead_logw, int nlive, const double* live_rows, double logZ,
+                              double logZerr, long long nlike, int num_repeats, double compression_factor, unsigned seed,
+                              const BoostedRows* boosted) {
     try {
         FileOpts o;
         o.enabled = true;
@@ -1927,10 +1928,28 @@ int pc_write_files(const char* base_dir, const char* file_root, int flags, int n
         o.posteriors = flags & 16; o.equals = flags & 32;
         o.num_repeats = num_repeats; o.compression_factor = compression_factor; o.seed = seed;
         FileState st;
-        return write_run_files(o, st, nDims, nDerived, ndead, dead_rows, dead_logw, nlive, live_rows, logZ, logZerr, nlike, true, nullptr);
+        return write_run_files(o, st, nDims, nDerived, ndead, dead_rows, dead_logw, nlive, live_rows, logZ, logZerr, nlike, true, boosted);
     } catch (const std::exception& ex) {
         return fail(-1, ex.what());
     }
+}
+int pc_write_files(const char* base_dir, const char* file_root, int flags, int nDims, int nDerived, long long ndead,
+                   const double* dead_rows, const double* dead_logw, int nlive, const double* live_rows, double logZ,
+                   double logZerr, long long nlike, int num_repeats, double compression_factor, unsigned seed) {
+    return write_files_common(base_dir, file_root, flags, nDims, nDerived, ndead, dead_rows, dead_logw, nlive, live_rows, logZ,
+                              logZerr, nlike, num_repeats, compression_factor, seed, nullptr);
+}
+int pc_write_files_boosted(const char* base_dir, const char* file_root, int flags, int nDims, int nDerived, long long ndead,
+                           const double* dead_rows, const double* dead_logw, int nlive, const double* live_rows, double logZ,
+                           double logZerr, long long nlike, int num_repeats, double compression_factor, unsigned seed,
+                           long long nboosted, const double* boosted_rows, const double* boosted_logw,
+                           const long long* boosted_after) {
+    BoostedRows br;
+    br.n = nboosted; br.rows = boosted_rows; br.logw = boosted_logw; br.after = boosted_after;
+    for (long long i = 1; i < nboosted; ++i)
+        if (boosted_after[i] < boosted_after[i - 1]) return fail(-1, "pc_write_files_boosted: boosted_after must ascend");
+    return write_files_common(base_dir, file_root, flags, nDims, nDerived, ndead, dead_rows, dead_logw, nlive, live_rows, logZ,
+                              logZerr, nlike, num_repeats, compression_factor, seed, nboosted > 0 ? &br : nullptr);
 }
 
 // cube_samples: the initial live points of the next run through polychord_c_interface (see the header)

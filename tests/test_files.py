@@ -104,3 +104,52 @@ def test_missing_base_dir_is_an_error(tmp_path):
     finally:
         capi.set_option("errors_return", 0)
     assert rc < 0
+
+
+def test_posterior_files_with_boosted_samples(tmp_path):
+    """boost_posterior: the promoted phantoms are written with the dead points, update by update (pc_write_files_boosted;
+    update_posteriors, run_time_info.f90:1036-1061), and enter the weights' normalisation, the equally weighted file
+    and the stats file's posterior count and means."""
+    rng = np.random.default_rng(11)
+    D, P, ndead, nb = 2, 1, 120, 300
+    logL = np.sort(rng.uniform(-8, 0, ndead))
+    dead = np.column_stack([rng.normal(0.5, 0.1, (ndead, D)), rng.uniform(0, 1, (ndead, P)), logL - 0.5, logL])
+    dead_logw = -np.arange(ndead) / 30.0 + logL
+    after = np.sort(rng.integers(1, 5, nb) * 30)               # removed at the updates after 30, 60, 90, 120 deaths
+    bl = np.array([rng.uniform(logL[a - 30], logL[a - 1]) for a in after])
+    boosted = np.column_stack([rng.normal(0.5, 0.1, (nb, D)), rng.uniform(0, 1, (nb, P)), bl - 0.5, bl])
+    blogw = np.array([-(a - 15) / 30.0 for a in after]) + bl
+    blogw[7] = dead_logw.max() + 1.0                           # a promoted phantom may carry the largest weight
+    live = np.zeros((0, D + P + 2))
+    n = capi.write_files(tmp_path, "b", D, P, dead, dead_logw, live, logZ=-1.0, logZerr=0.1, nlike=5000, num_repeats=4,
+                         seed=3, flags=("stats", "posteriors", "equals"), boosted=(boosted, blogw, after))
+    assert n == 3
+    post = np.loadtxt(tmp_path / "b.txt")
+    assert post.shape == (ndead + nb, 2 + D + P)
+    allw = np.concatenate([dead_logw, blogw])
+    assert np.isclose(post[:, 0].max(), 1.0)
+    assert np.allclose(np.sort(post[:, 0]), np.sort(np.exp(allw - allw.max())), rtol=1e-12)
+    # order: the dead points of an update, then the phantoms it removed
+    is_dead = np.isin(np.round(post[:, 1], 9), np.round(-2 * logL, 9))
+    k = 0
+    for upd in (30, 60, 90, 120):
+        m = int(np.sum(after == upd))
+        assert is_dead[k:k + 30].all() and not is_dead[k + 30:k + 30 + m].any()
+        assert np.allclose(post[k:k + 30, 1], -2 * logL[upd - 30:upd], rtol=1e-13)
+        k += 30 + m
+    eq = np.loadtxt(tmp_path / "b_equal_weights.txt")
+    assert np.all(eq[:, 0] == 1.0)
+    assert abs(eq.shape[0] - post[:, 0].sum()) < 5 * np.sqrt(post[:, 0].sum())
+    stats = (tmp_path / "b.stats").read_text()
+    assert f"nposterior: {ndead + nb:8d}" in stats
+    # the same call without the samples writes the dead points only
+    capi.write_files(tmp_path, "p", D, P, dead, dead_logw, live, logZ=-1.0, logZerr=0.1, nlike=5000, num_repeats=4,
+                     seed=3, flags=("posteriors",))
+    assert np.loadtxt(tmp_path / "p.txt").shape[0] == ndead
+    # samples out of update order are refused
+    capi.set_option("errors_return", 1)
+    try:
+        assert capi.write_files(tmp_path, "x", D, P, dead, dead_logw, live, logZ=-1.0, logZerr=0.1, nlike=5000, num_repeats=4,
+                                seed=3, flags=("posteriors",), boosted=(boosted, blogw, after[::-1])) < 0
+    finally:
+        capi.set_option("errors_return", 0)
