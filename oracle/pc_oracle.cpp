@@ -1191,12 +1191,28 @@ struct Run {
     }
 
     // ---- batched-generation main loop (the GPU engine's schedule) ----
+    // Dynamic nlive in the batched schedule (the target for the engine's row a11): a generation kills the K lowest of
+    // its n live points with counts n, n-1, ... as always, then births B = target(L*) - (n - K) chains (none when the
+    // survivors already exceed the target, at most 2 batch_K), so the live count moves to max(n - K, target) --
+    // replace_point's rule (run_time_info.f90:766-777) taken a generation at a time.  Births k < min(B, K) take the
+    // vacated slots in death order, further births are appended, vacated slots left over are closed from the top down
+    // by moving the last record in.  With a constant target B = K: the schedule above, unchanged.
+    int target_nlive(double contour) const {
+        int nlive = S.nlive, best = -1;
+        for (size_t q = 0; q < g_dyn_loglikes.size(); ++q)
+            if (contour > g_dyn_loglikes[q] && (best < 0 || g_dyn_loglikes[q] > g_dyn_loglikes[(size_t)best])) best = (int)q;
+        if (best >= 0) nlive = g_dyn_nlives[(size_t)best];
+        return nlive;
+    }
+
     void run_batched() {
         Cluster& c = cl[0];
-        const int n = c.nlive;
-        std::vector<int> order(n);
+        std::vector<int> order;
         std::vector<double> babies, rec(T);
+        const bool dyn = !g_dyn_loglikes.empty() && !S.do_clustering;
         while (more_samples_needed()) {
+            const int n = c.nlive;
+            order.resize(n);
             int K = std::min(S.batch_K, n - 1);
             if (S.max_ndead > 0) K = (int)std::min<long long>(K, S.max_ndead - ndead);
             if (K < 1) break;
@@ -1218,12 +1234,13 @@ struct Run {
                 c.nlive--;
             }
             c.nlive = nlive_save;
-            // K chains seeded from the n-K survivors, all at contour Lstar
+            // B chains (B = K unless the live count is moving) seeded from the n-K survivors, all at contour Lstar
             int m = n - K;
-            std::vector<double> newpts((size_t)K * T);
-            std::vector<int> newlab(K, 0);
+            const int B = dyn ? std::max(0, std::min(std::max(target_nlive(Lstar), 1) - m, 2 * S.batch_K)) : K;
+            std::vector<double> newpts((size_t)std::max(B, 1) * T);
+            std::vector<int> newlab(std::max(B, 1), 0);
             const bool clustered = S.do_clustering && ncl_b > 1;
-            for (int k = 0; k < K; ++k) {
+            for (int k = 0; k < B; ++k) {
                 uint64_t uid = (uint64_t)nchains + k;
                 double u = rng.uniform(TAG_SEED, uid, 0, 0);
                 int choice = (int)std::ceil(u * m);
@@ -1246,10 +1263,24 @@ struct Run {
                 if (!(last[l0] > Lstar)) nfail_total++;
                 std::copy(last, last + T, newpts.begin() + (size_t)k * T);
             }
-            for (int k = 0; k < K; ++k)
+            for (int k = 0; k < std::min(B, K); ++k)
                 std::copy(newpts.begin() + (size_t)k * T, newpts.begin() + (size_t)(k + 1) * T, c.live.begin() + (size_t)order[k] * T);
             if (clustered) for (int k = 0; k < K; ++k) lab[order[k]] = newlab[k];
-            nchains += K;
+            if (B > K) {          // the live count grows: further births are appended
+                c.live.insert(c.live.end(), newpts.begin() + (size_t)K * T, newpts.begin() + (size_t)B * T);
+                c.nlive += B - K;
+            } else if (B < K) {   // it shrinks: close the vacated slots left over, highest slot first
+                std::vector<int> holes(order.begin() + B, order.begin() + K);
+                std::sort(holes.begin(), holes.end(), std::greater<int>());
+                for (int sl : holes) {
+                    const int lastp = c.nlive - 1;
+                    if (sl != lastp)
+                        std::copy(c.live.begin() + (size_t)lastp * T, c.live.begin() + (size_t)(lastp + 1) * T, c.live.begin() + (size_t)sl * T);
+                    c.nlive--;
+                }
+                c.live.resize((size_t)c.nlive * T);
+            }
+            nchains += B;
             ngen++;
             find_min();
             if (sum_logX() <= logX_last_update + std::log(S.compression_factor)) do_update();

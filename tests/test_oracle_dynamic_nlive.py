@@ -52,3 +52,25 @@ def test_no_schedule_is_the_plain_run(oracle, schedule):
     schedule({1e30: 10})                 # a threshold no contour reaches
     b, _ = oracle.run(s)
     assert (a.ndead, a.nlike, a.logZ) == (b.ndead, b.nlike, b.logZ)
+
+
+def test_batched_schedule_moves_the_live_count_a_generation_at_a_time(oracle, schedule):
+    """The engine's schedule with a moving target: max(n - K, target) after every
+    generation; unbiased evidence with an honest error bar; no schedule = the plain batched run."""
+    D = 4
+    plain, _ = oracle.run(oracle.make_settings(D, 0, nlive=100, num_repeats=8, seed=0, batch_K=25))
+    schedule({1e30: 10})
+    same, _ = oracle.run(oracle.make_settings(D, 0, nlive=100, num_repeats=8, seed=0, batch_K=25))
+    assert (plain.ndead, plain.nlike, plain.logZ) == (same.ndead, same.nlike, same.logZ)
+    schedule({-5.0: 300, 2.0: 50})
+    zs, errs = [], []
+    for seed in range(12):
+        res, dumps = oracle.run(oracle.make_settings(D, 0, nlive=100, num_repeats=8, seed=seed, batch_K=25), want_dump=True)
+        zs.append(res.logZ); errs.append(res.logZerr)
+        counts = [d["live"].shape[0] for d in dumps[:-1]]
+        assert counts[0] == 100 and max(counts) == 300 and counts[-1] == 50
+        for d in dumps[:-1]:
+            if d["live"][:, -1].min() <= -5.0:
+                assert d["live"].shape[0] == 100
+    assert abs(np.mean(zs)) < 4 * np.std(zs) / np.sqrt(len(zs)) + 0.05
+    assert 0.5 < np.std(zs) / np.mean(errs) < 2.0
