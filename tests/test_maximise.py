@@ -105,3 +105,44 @@ def test_no_simplex():
     rec = _live(_prior_unit)
     rec[:, -1] = LOGZERO
     assert _maximise(_prior_unit, rec, False)[0] == 1
+
+
+@pytest.mark.parametrize("dims,seed", [(2, 0), (5, 1), (8, 2)])
+def test_simplex_walk_on_random_quadratics(dims, seed):
+    """The C++ Nelder-Mead and the numpy restatement make the same moves (reflection / expansion / contraction /
+    shrink, the stopping rule with its single-precision exponent) on correlated quadratics in several dimensions."""
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((dims, dims))
+    H = A @ A.T / dims + 0.5 * np.eye(dims)
+    centre = rng.uniform(0.3, 0.7, dims)
+
+    def loglike(theta):
+        d = np.asarray(theta) - centre
+        return float(-0.5 * d @ H @ d / 0.01)
+
+    T = 2 * dims + 2
+    n = 4 * dims
+    rec = np.zeros((n, T))
+    rec[:, :dims] = rng.random((n, dims))
+    rec[:, dims:2 * dims] = rec[:, :dims]
+    rec[:, T - 1] = [loglike(c) for c in rec[:, :dims]]
+
+    def ll(theta_p, nd, phi_p, nder):
+        return loglike(np.ctypeslib.as_array(theta_p, shape=(nd,)))
+
+    def prior(cube_p, theta_p, nd):
+        for i in range(nd):
+            theta_p[i] = cube_p[i]
+    cll, cprior = _capi.LL_CB(ll), _capi.PRIOR_CB(prior)
+    L = _capi.lib()
+    L.pc_maximise.restype = C.c_int
+    L.pc_maximise.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), C.c_int, C.c_int,
+                              C.POINTER(C.c_double)]
+    out = np.zeros(T)
+    rc = L.pc_maximise(C.cast(cll, C.c_void_p), C.cast(cprior, C.c_void_p), dims, 0, LOGZERO,
+                       rec.ctypes.data_as(C.POINTER(C.c_double)), n, 0, out.ctypes.data_as(C.POINTER(C.c_double)))
+    assert rc == 0
+    want = mo.do_maximisation(loglike, _prior_unit, rec[:, :dims], rec[:, T - 1], LOGZERO, False)
+    np.testing.assert_allclose(out[:dims], want, rtol=0, atol=1e-9)
+    # where the walk stops: the values at the vertices agree to 1e-5, i.e. |x - centre| ~ sqrt(2e-5 * 0.01 / lambda_min)
+    assert out[T - 1] > -1e-4 and np.linalg.norm(out[:dims] - centre) < 2e-3
