@@ -28,7 +28,11 @@
 //   run_time_info.f90:683-709     live_logZ                      -> Run::live_logZ()
 //   run_time_info.f90:716-787     replace_point                  -> Run::replace_point()
 //   run_time_info.f90:789-817     delete_outermost_point         -> Run::delete_outermost_point()
-//   run_time_info.f90:820-877     clean_phantoms                 -> Run::clean_phantoms()
+//   run_time_info.f90:820-877     clean_phantoms                 -> Run::clean_phantoms(), clean_phantoms_stable()
+//   run_time_info.f90:846-868       its posterior conversion       -> Run::boost() (boost_posterior; oracle_last_boosted)
+//   run_time_info.f90:766-777     dynamic nlive in replace_point -> Run::replace_point(), Run::target_nlive() (oracle_set_nlives)
+//   generate.F90:311-316          thin_posterior                 -> Run::thin_posterior()
+//   pypolychord/polychord.py:650-789  cube_samples start         -> Run::generate_live_points() (oracle_set_initial_cubes)
 //   run_time_info.f90:883-909     find_min_loglikelihoods        -> Run::find_min()
 //   run_time_info.f90:913-949     identify_cluster               -> Run::identify_cluster()
 //   random_utils.F90:381-437      random_orthonormal_basis/bases -> random_orthonormal_basis()
