@@ -235,10 +235,10 @@ int pc_device_cholesky(const double* a, int D, double* L_out);
 /* ---- output files in the reference's formats (replaces src/polychord/read_write.F90:479-716, 809-961) ----
  * polychord_c_interface() writes them itself when its write_* / posteriors / equals flags are set:
  *   <root>.stats, <root>_dead.txt, <root>_dead-birth.txt, <root>_phys_live.txt, <root>_phys_live-birth.txt,
- *   <root>.txt (weighted posterior), <root>_equal_weights.txt, <root>.prior_info
+ *   <root>.txt (weighted posterior), <root>_equal_weights.txt, <root>.prior_info, <root>_prior.txt (the prior draws)
  * with every number in Fortran's E24.15E3 edit descriptor (utils.F90:19).  The two entry points below are host-only
  * (no device needed): the formatter, and the writer driven with explicit arrays.
- * flags: 1 stats, 2 live, 4 dead, 8 prior_info, 16 weighted posterior, 32 equally weighted posterior.
+ * flags: 1 stats, 2 live, 4 dead, 8 prior (_prior.txt; prior_info is written by the run), 16 weighted posterior, 32 equally weighted posterior.
  * dead_rows / live_rows: rows [theta(nDims), phi(nDerived), birth contour, logL]; dead_logw[i] = log weight + logL. */
 void pc_format_e24(double value, char* out25);
 int pc_write_files(const char* base_dir, const char* file_root, int flags, int nDims, int nDerived, long long ndead,

@@ -124,6 +124,26 @@ int write_run_files(const FileOpts& o, FileState& st, int D, int P, long long nd
     }
 
     // posterior weights: log w_i + log L_i relative to the largest one (maximum weight 1.0, read_write.F90:565-566)
+    if (o.write_prior) {
+        // write_prior_file (read_write.F90:721-752): the points drawn from the prior, rows [1, -2 logL, theta, phi].  The
+        // reference writes them once, right after GenerateLivePoints; here they are recognised by their birth contour
+        // (logzero) among the dead and the live points, so the file is complete at every rewrite.
+        Out w(root + "_prior.txt");
+        auto rows_of = [&](const double* rows, long long n) {
+            for (long long i = 0; i < n; ++i) {
+                const double* r = rows + (size_t)i * npars;
+                if (r[np] > o.logzero) continue;
+                w.num(1.0);
+                w.num(-2.0 * r[np + 1]);
+                for (int k = 0; k < np; ++k) w.num(r[k]);
+                w.nl();
+            }
+        };
+        rows_of(dead_rows, ndead);
+        rows_of(live_rows, nlive);
+        ++files;
+    }
+
     // The posterior samples in file order: the dead points and, after the deaths of the update that removed them, the
     // phantoms boost_posterior promoted (update_posteriors appends the stack update by update, run_time_info.f90:1036-1061)
     struct PostRef { const double* row; double lw; uint64_t uid; };

@@ -153,3 +153,24 @@ def test_posterior_files_with_boosted_samples(tmp_path):
                                 seed=3, flags=("posteriors",), boosted=(boosted, blogw, after[::-1])) < 0
     finally:
         capi.set_option("errors_return", 0)
+
+
+def test_prior_file(tmp_path):
+    """<root>_prior.txt (write_prior_file, read_write.F90:721-752): the points drawn from the prior, [1, -2 logL, theta,
+    phi], wherever they are by now (dead or still live)."""
+    rng = np.random.default_rng(5)
+    D, P = 3, 1
+
+    def rows(n, nprior):
+        logL = np.sort(rng.uniform(-9, 0, n))
+        birth = np.where(np.arange(n) < nprior, -1e30, logL - 0.3)
+        return np.column_stack([rng.uniform(0, 1, (n, D)), rng.uniform(0, 1, (n, P)), birth, logL])
+    dead, live = rows(80, 30), rows(40, 10)
+    n = capi.write_files(tmp_path, "pr", D, P, dead, dead[:, -1] - 1.0, live, logZ=-2.0, logZerr=0.2, nlike=999,
+                         num_repeats=6, flags=("prior",))
+    assert n == 1
+    pr = np.loadtxt(tmp_path / "pr_prior.txt")
+    assert pr.shape == (40, 2 + D + P) and np.all(pr[:, 0] == 1.0)
+    want = np.vstack([dead[:30], live[:10]])
+    assert np.allclose(pr[:, 1], -2 * want[:, -1], rtol=1e-14) and np.allclose(pr[:, 2:], want[:, :D + P], rtol=1e-14)
+    assert len((tmp_path / "pr_prior.txt").read_text().splitlines()[0]) == 24 * (2 + D + P)
