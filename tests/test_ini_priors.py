@@ -119,3 +119,31 @@ def test_errors(tmp_path):
     bad = tmp_path / "bad.ini"
     bad.write_text("nlive = 5\nnum_repeats = 2\nP : a | a | 1 | no_such_prior | 1 | 0 1\n")
     assert _transform(bad, np.zeros(1))[0] == -6
+
+
+def test_malformed_files_are_refused_not_crashed(tmp_path):
+    """Random damage to a valid file: the parser either still yields a transform (rc 0) or reports -6/-7."""
+    path, _, n = _ini(tmp_path, [(1, 2), (7, 3), (11, 4), (15, 3), (3, 1)])
+    good = path.read_text().splitlines()
+    rng = np.random.default_rng(23)
+    junk = ["P : x", "P : a | b | c | d | e | f", "P : a | a | 1 | uniform | 1 |", "P : a | a | x | gaussian | 1 | 0 1",
+            "nlive = many", "P : a | a | 1 | sorted_uniform | z | 0 1", "= = =", "P : a | a | 1 | power_uniform | 1 | 0 1",
+            "grade_frac = 0.5 0.5 0.5", "P : q | q | 0 | exponential | 9 | 2.0"]
+    seen = set()
+    for trial in range(60):
+        lines = list(good)
+        for _ in range(int(rng.integers(1, 4))):
+            k = int(rng.integers(0, len(lines) + 1))
+            if rng.random() < 0.5 and lines:
+                lines.pop(min(k, len(lines) - 1))
+            else:
+                lines.insert(k, junk[int(rng.integers(0, len(junk)))])
+        bad = tmp_path / f"bad{trial}.ini"
+        bad.write_text("\n".join(lines) + "\n")
+        for dims in (n, n + 1, n - 1):
+            rc, out = _transform(bad, rng.random(max(dims, 1)))
+            assert rc in (0, -6, -7)
+            seen.add(rc)
+            if rc == 0:
+                assert np.all(np.isfinite(out))
+    assert {-6, -7} <= seen
