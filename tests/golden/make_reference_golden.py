@@ -2,6 +2,7 @@
 (this container only; the fixture is what travels):
 
   priors     every class of /root/reference/pypolychord/priors.py evaluated on fixed cube points
+  settings   the attributes of /root/reference/pypolychord/settings.py's PolyChordSettings for two constructions
   stats      a <root>.stats file written by this repository's writer (pc_write_files, host-only, deterministic inputs)
              parsed by the reference's PolyChordOutput (/root/reference/pypolychord/output.py:57-99); the file's text is
              stored with the parsed fields, so the test can check both that the writer still produces these bytes and
@@ -54,6 +55,13 @@ def main():
         p = getattr(priors, name)(*args)
         out["priors"]["cases"].append({"class": name, "args": args, "theta": [np.asarray(p(c)).tolist() for c in cubes]})
     out["priors"]["forced_indentifiability_transform"] = [priors.forced_indentifiability_transform(c).tolist() for c in cubes]
+
+    settings = _load("settings")
+    out["settings"] = []
+    for nDims, nDerived, kw in ((4, 1, {}), (7, 0, {"nlive": 50, "grade_dims": [3, 4], "grade_frac": [1.0, 2.0], "seed": 3})):
+        st = settings.PolyChordSettings(nDims, nDerived, **kw)
+        out["settings"].append({"nDims": nDims, "nDerived": nDerived, "kwargs": kw,
+                                "attributes": {k: (float(v) if isinstance(v, np.floating) else v) for k, v in vars(st).items()}})
 
     from polychordlite_b200 import _capi
     D, P, dead, logw, live, kw = stats_inputs()

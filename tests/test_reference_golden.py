@@ -70,3 +70,10 @@ def test_stats_file_is_what_the_references_parser_read(tmp_path):
             assert list(got) == want, key
         else:
             assert got == want, key
+
+
+def test_settings_defaults_are_the_references():
+    for case in GOLD["settings"]:
+        st = pypolychord.PolyChordSettings(case["nDims"], case["nDerived"], **case["kwargs"])
+        got = {k: (float(v) if isinstance(v, np.floating) else v) for k, v in vars(st).items()}
+        assert got == case["attributes"]
