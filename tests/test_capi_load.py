@@ -89,3 +89,28 @@ def test_reference_facade_links_against_this_library(capi, tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     nm = subprocess.run(["nm", "-D", "--undefined-only", str(out)], capture_output=True, text=True).stdout
     assert "polychord_c_interface" in nm and "polychord_c_interface_ini" in nm
+
+
+def test_host_only_setters_validate_their_arguments(capi):
+    """pc_set_initial_live / pc_last_boosted / pc_maximise are callable without a device and check what they are given."""
+    import ctypes as C
+
+    import numpy as np
+    L = capi.lib()
+    L.pc_set_initial_live.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int]
+    a = np.zeros((3, 2))
+    assert L.pc_set_initial_live(a.ctypes.data_as(C.POINTER(C.c_double)), 3, 0) == -1
+    assert L.pc_set_initial_live(a.ctypes.data_as(C.POINTER(C.c_double)), 3, 2) == 0
+    assert L.pc_set_initial_live(None, 0, 0) == 0            # cleared again
+    capi.set_initial_live(None)
+    try:
+        capi.set_initial_live(np.zeros(4))
+        raise AssertionError("a 1-d array must be refused")
+    except ValueError:
+        pass
+    rows, idx, lw = capi.last_boosted(5)                     # no run yet in this process (or none that boosted)
+    assert len(idx) == len(lw) == rows.shape[0]
+    L.pc_maximise.restype = C.c_int
+    L.pc_maximise.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), C.c_int, C.c_int,
+                              C.POINTER(C.c_double)]
+    assert L.pc_maximise(None, None, 2, 0, -1e30, None, 0, 0, None) == -1
