@@ -63,9 +63,8 @@ void polychord_c_interface(
 /* Replaces src/polychord/interfaces.F90:496-519 (decl. interfaces.h:47-56): settings, parameters and priors are read
  * from the .ini file (src/polychord/ini.f90 format: "key = value" lines, "P : name | latex | speed | prior type |
  * block | params", "D : name | latex"), setup_loglikelihood() is called once, then the run proceeds as through
- * polychord_c_interface.  Prior types: uniform, log_uniform, power_uniform, gaussian, half_gaussian, exponential and
- * their sorted_* forms (priors.f90:40-298); the adaptive families and dynamic nlive schedules are reported as
- * unsupported. */
+ * polychord_c_interface.  All fifteen prior families of priors.f90:5-20 are read (separable, sorted, adaptive sorted,
+ * nn_adaptive_layer_gaussian; csrc/pc_ini.cpp). */
 void polychord_c_interface_ini(pc_loglikelihood_t loglikelihood, void (*setup_loglikelihood)(void),
                                char* inifile, int* comm);
 

@@ -13,6 +13,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libchord.so"
+SHIM_SRC = CSRC / "pypolychord_module.cpp"   # the CPython extension: a separate shared object linked against libchord.so
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -37,7 +38,7 @@ def build(force=False, verbose=False):
         return LIB
     LIBDIR.mkdir(exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    srcs = [str(p) for p in sources() if p.name != "_pypolychord.cpp"]
+    srcs = [str(p) for p in sources() if p.name != SHIM_SRC.name]
     cmd = [nvcc, *NVCC_FLAGS, "-I", str(PKG.parent / "include"), "-o", str(LIB), *srcs]
     if verbose:
         cmd.insert(1, "-Xptxas")
@@ -47,6 +48,27 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def shim_path():
+    import sysconfig
+    return PKG / "pypolychord" / ("_pypolychord" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_shim(force=False):
+    """The `_pypolychord` extension module (reference: pypolychord/_pypolychord.cpp, built by setup.py:114-123 with
+    -lchord): g++ against Python.h + numpy, linked to the in-tree libchord.so with an $ORIGIN rpath."""
+    import sysconfig
+    import numpy
+    out = shim_path()
+    if not force and out.exists() and out.stat().st_mtime > max(SHIM_SRC.stat().st_mtime, LIB.stat().st_mtime):
+        return out
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", str(SHIM_SRC),
+           "-I", sysconfig.get_paths()["include"], "-I", numpy.get_include(), "-L", str(LIBDIR), "-lchord",
+           "-Wl,-rpath,$ORIGIN/../lib", "-o", str(out)]   # Python's own symbols resolve against the interpreter at import
+    subprocess.run(cmd, check=True)
+    return out
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(LIB)
+    print(build_shim(force="--force" in sys.argv))

@@ -48,34 +48,44 @@ struct ChainParams {
 struct ChainScratch {
     double* nh;    // R columns, leading dimension LD (odd): raw orthonormal basis, then whitened unit directions
     double* wts;   // R: initial bracket width w = 3*|L q| of each column
-    double* uni;   // R x NU slice uniforms
-    double* dots;  // 4 x Dpad Gram-Schmidt projections
+    double* uni;   // R x NU slice uniforms (null in the dense layout: they go straight into the slice records)
+    double* dots;  // 4 x Dpad Gram-Schmidt projections; before that, the tail queue of the Gaussian deviates
     double* dvec;  // NPT x Dpad (correlated Gaussian only)
+    double* stage; // dense layout only: NPT x 2 x slb doubles, the point groups' slice-record buffers (pc_dense.cuh)
     int* deck;     // R: column used by slice i
     int* jd;       // R: Fisher-Yates picks
 };
 
-__host__ __device__ inline size_t chain_scratch_bytes(int D, int R, int LD, bool nh_in_smem, int like_kind, int npt) {
+// Gram-Schmidt projections (4 x Dpad) share their area with the tail queue of the Gaussian deviates (64 arguments + 64
+// element indices, prep_chain)
+__host__ __device__ constexpr int dots_doubles(int Dpad) { return 4 * Dpad > 96 ? 4 * Dpad : 96; }
+
+// slb > 0 selects the dense layout (pc_dense.cuh): slb doubles per slice record, no uniforms in shared memory
+__host__ __device__ inline size_t chain_scratch_bytes(int D, int R, int LD, bool nh_in_smem, int like_kind, int npt, int slb = 0) {
     const int Dpad = (D + 1) & ~1;
     size_t b = 0;
+    if (slb > 0) b += (size_t)npt * 2 * slb * 8;  // stage (first: 16-byte aligned for cp.async)
     if (nh_in_smem) b += (size_t)R * LD * 8;
     b += (size_t)R * 8;                 // wts
-    b += (size_t)R * NU * 8;            // uni
-    b += (size_t)4 * Dpad * 8;          // dots
+    if (slb == 0) b += (size_t)R * NU * 8;            // uni
+    b += (size_t)dots_doubles(Dpad) * 8;  // dots / tail queue
     if (like_kind == LIKE_CORR) b += (size_t)npt * Dpad * 8;
     b += (size_t)((2 * R + 1) & ~1) * 4;  // deck + jd
     return (b + 15) & ~(size_t)15;
 }
 
 __device__ __forceinline__ ChainScratch chain_scratch(unsigned char* base, int D, int R, int LD, bool nh_in_smem,
-                                                      int like_kind, int npt, double* nh_global) {
+                                                      int like_kind, int npt, double* nh_global, int slb = 0) {
     ChainScratch cs;
     const int Dpad = (D + 1) & ~1;
     double* d = (double*)base;
+    cs.stage = d;
+    if (slb > 0) d += (size_t)npt * 2 * slb;
     if (nh_in_smem) { cs.nh = d; d += (size_t)R * LD; } else cs.nh = nh_global;
     cs.wts = d; d += R;
-    cs.uni = d; d += (size_t)R * NU;
-    cs.dots = d; d += 4 * Dpad;
+    cs.uni = nullptr;
+    if (slb == 0) { cs.uni = d; d += (size_t)R * NU; }
+    cs.dots = d; d += dots_doubles(Dpad);
     cs.dvec = d;
     if (like_kind == LIKE_CORR) d += (size_t)npt * Dpad;
     cs.deck = (int*)d;
@@ -231,10 +241,21 @@ struct Model {
 //           random_utils.F90:381-437), column c at nh + c*LD
 //   deck <- Fisher-Yates shuffle of columns 1..R-1 (chordal_sampling.f90:133-136, random_utils.F90:505-532)
 //   uni  <- slice uniforms: uni[i*NU + 0] = u0 of slice i, uni[i*NU + 1 + s] = shrink draw s
+//           (skipped when cs.uni is null: the dense mode writes them straight into its global slice blocks)
+// Preparation is most of the warp instructions of a run (ncu, profiles/r01e: 2.3e4 per chain against 1.5e4 for
+// the 40 slice steps), so its two heavy parts are written for instruction count:
+//   * the Gaussian deviates evaluate AS241's central rational for every draw and queue the 15 % that fall in the
+//     tails; the queue is worked off 32 at a time, so the log / sqrt / second rational are paid per tail draw and not
+//     per warp-wide call;
+//   * Gram-Schmidt walks columns with pointers (no 64-bit index arithmetic per element) and, when the instantiation
+//     knows the padded dimension GD (rows D..GD-1 of every column are zero), runs its dot products fully unrolled.
+//     The order of every floating-point sum is the one of the generic loop: both give the same bits.
 // ------------------------------------------------------------------------------------------
+template <int GD = 0>
 __device__ inline void prep_chain(int D, int R, int LD, unsigned seed, unsigned long long uid, const ChainScratch& cs,
                                   const ChainParams* gp = nullptr) {
     const int lane = threadIdx.x & 31;
+    const unsigned below = (1u << lane) - 1u;
     double* nh = cs.nh;
     const int ngrade = (gp && gp->ngrade > 1) ? gp->ngrade : 1;
     // (c) shuffle picks and (d) slice uniforms are independent of the directions: issue them first so their
@@ -248,10 +269,11 @@ __device__ inline void prep_chain(int D, int R, int LD, unsigned seed, unsigned 
         }
         cs.jd[i] = j;
     }
-    for (int e = lane; e < R * NU; e += 32) {
-        const int i = e / NU, s = e - i * NU;
-        cs.uni[e] = uniform(seed, TAG_SLICE, uid, (unsigned)i, (unsigned)s);
-    }
+    if (cs.uni)
+        for (int e = lane; e < R * NU; e += 32) {
+            const int i = e / NU, s = e - i * NU;
+            cs.uni[e] = uniform(seed, TAG_SLICE, uid, (unsigned)i, (unsigned)s);
+        }
     const int Dpad = (D + 1) & ~1;
     // generate_nhats (chordal_sampling.f90:94-145): grade g contributes Rg columns (from column cbase) drawn from
     // orthonormal bases of the sub-space of the dimensions roff..D-1 (the dimensions of grades >= g); the rows above
@@ -261,18 +283,54 @@ __device__ inline void prep_chain(int D, int R, int LD, unsigned seed, unsigned 
         const int Dg = D - roff;
         const int Rg = ngrade > 1 ? gp->greps[g] : R;
         // (a) Gaussian deviates, two per Philox block (inv_normal_cdf = AS241, utils.F90:777-966)
-        const int H = (Dg + 1) >> 1;
-        for (int e = lane; e < Rg * H; e += 32) {
-            const int col = e / H, hp = e - col * H;
-            double u0, u1;
-            uniform2(seed, TAG_DIR, uid, (unsigned)(cbase + col), (unsigned)hp, u0, u1);
-            double* vp = nh + (size_t)(cbase + col) * LD + roff + 2 * hp;
-            vp[0] = inv_normal_cdf(u0);
-            if (2 * hp + 1 < Dg) vp[1] = inv_normal_cdf(u1);
+        {
+            const int H = (Dg + 1) >> 1, total = Rg * H;
+            double* qp = cs.dots;                    // tail queue: up to 64 arguments ...
+            int* qi = (int*)(cs.dots + 64);          // ... and the elements of nh they belong to
+            int qn = 0;
+            for (int e0 = 0; e0 < total; e0 += 32) {
+                const int e = e0 + lane;
+                const bool act = e < total;
+                const int col = act ? e / H : 0, hp = e - col * H;
+                double u0 = 0.5, u1 = 0.5;
+                if (act) uniform2(seed, TAG_DIR, uid, (unsigned)(cbase + col), (unsigned)hp, u0, u1);
+                const int slot = (cbase + col) * LD + roff + 2 * hp;
+                const bool has1 = act && (2 * hp + 1 < Dg);
+                double z0, z1;
+                const bool tl0 = !inv_normal_cdf_central(u0, z0) && act;
+                const bool tl1 = !inv_normal_cdf_central(u1, z1) && has1;
+                if (act && !tl0) nh[slot] = z0;
+                if (has1 && !tl1) nh[slot + 1] = z1;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const bool tl = half ? tl1 : tl0;
+                    const unsigned m = __ballot_sync(FULL, tl);
+                    if (m == 0u) continue;
+                    if (tl) {
+                        const int pos = qn + __popc(m & below);
+                        qp[pos] = half ? u1 : u0;
+                        qi[pos] = slot + half;
+                    }
+                    qn += __popc(m);
+                    __syncwarp();
+                    if (qn >= 32) {   // a full warp of tail draws
+                        nh[qi[lane]] = inv_normal_cdf_tail(qp[lane]);
+                        const int rest = qn - 32;
+                        double tp = 0.0;
+                        int ti = 0;
+                        if (lane < rest) { tp = qp[32 + lane]; ti = qi[32 + lane]; }
+                        __syncwarp();
+                        if (lane < rest) { qp[lane] = tp; qi[lane] = ti; }
+                        qn = rest;
+                        __syncwarp();
+                    }
+                }
+            }
+            if (lane < qn) nh[qi[lane]] = inv_normal_cdf_tail(qp[lane]);
         }
         for (int e = lane; e < Rg * (LD - Dg); e += 32) {  // zeros: rows 0..roff-1 and D..LD-1 of every column
             const int col = e / (LD - Dg), z = e - col * (LD - Dg);
-            nh[(size_t)(cbase + col) * LD + (z < roff ? z : D + z - roff)] = 0.0;
+            nh[(cbase + col) * LD + (z < roff ? z : D + z - roff)] = 0.0;
         }
         __syncwarp();
         // (b) Gram-Schmidt, B bases at a time on LB = 32/B lanes each.  Classical form: all projections of
@@ -281,22 +339,31 @@ __device__ inline void prep_chain(int D, int R, int LD, unsigned seed, unsigned 
         const int B = nb >= 4 ? 4 : (nb >= 2 ? 2 : 1);
         const int LB = 32 / B;
         const int sl = lane % LB, bslot = lane / LB;
-        double* dots = cs.dots + (size_t)bslot * Dpad;
+        double* dots = cs.dots + bslot * Dpad;
+        const bool unrolled = GD > 0 && roff == 0 && D <= GD && LD >= GD;   // padding rows are zero: sum over GD rows
         for (int b0 = 0; b0 < nb; b0 += B) {
             const int basis = b0 + bslot;
             const int col0 = cbase + basis * Dg;
             const int m = (basis < nb) ? min(Dg, Rg - basis * Dg) : 0;   // vectors of my basis that are used
             const int mmax = min(Dg, Rg - b0 * Dg);                      // trip count of the round (first basis is the longest)
+            double* const q0 = nh + col0 * LD + roff;                    // column 0 of my basis
             for (int i = 0; i < mmax; ++i) {
                 const bool act = i < m;
-                double* vp = nh + (size_t)(col0 + i) * LD + roff;
+                double* vp = q0 + i * LD;
                 if (act) {
                     for (int jj = sl; jj < i; jj += LB) {
-                        const double* q = nh + (size_t)(col0 + jj) * LD + roff;
+                        const double* q = q0 + jj * LD;
                         double d0 = 0.0, d1 = 0.0;
-                        int r = 0;
-                        for (; r + 1 < Dg; r += 2) { d0 += vp[r] * q[r]; d1 += vp[r + 1] * q[r + 1]; }
-                        if (r < Dg) d0 += vp[r] * q[r];
+                        if (unrolled) {
+#pragma unroll
+                            for (int r = 0; r < (GD > 0 ? GD : 1); ++r) {
+                                if (r & 1) d1 += vp[r] * q[r]; else d0 += vp[r] * q[r];
+                            }
+                        } else {
+                            int r = 0;
+                            for (; r + 1 < Dg; r += 2) { d0 += vp[r] * q[r]; d1 += vp[r + 1] * q[r + 1]; }
+                            if (r < Dg) d0 += vp[r] * q[r];
+                        }
                         dots[jj] = d0 + d1;
                     }
                 }
@@ -305,12 +372,14 @@ __device__ inline void prep_chain(int D, int R, int LD, unsigned seed, unsigned 
                 if (act) {
                     for (int r = sl; r < Dg; r += LB) {
                         double t0 = vp[r], t1 = 0.0;
+                        const double* qc = q0 + r;
+                        const double* dj = dots;
                         int jj = 0;
-                        for (; jj + 1 < i; jj += 2) {
-                            t0 -= dots[jj] * nh[(size_t)(col0 + jj) * LD + roff + r];
-                            t1 -= dots[jj + 1] * nh[(size_t)(col0 + jj + 1) * LD + roff + r];
+                        for (; jj + 1 < i; jj += 2, qc += 2 * LD, dj += 2) {
+                            t0 -= dj[0] * qc[0];
+                            t1 -= dj[1] * qc[LD];
                         }
-                        if (jj < i) t0 -= dots[jj] * nh[(size_t)(col0 + jj) * LD + roff + r];
+                        if (jj < i) t0 -= dj[0] * qc[0];
                         const double t = t0 + t1;
                         vp[r] = t;
                         acc += t * t;

@@ -53,28 +53,36 @@ __host__ __device__ __forceinline__ void uniform2(uint32_t seed, uint32_t tag, u
 
 // Inverse normal CDF, algorithm AS241 PPND16 (Wichura 1988) -- the algorithm the reference's
 // utils.F90:777-966 (inv_normal_cdf -> r8_normal_01_cdf_inverse) implements.  p in (0,1).
-__host__ __device__ inline double inv_normal_cdf(double p) {
-    double q = p - 0.5;
-    if (fabs(q) <= 0.425) {
-        double r = 0.180625 - q * q;
-        double num = 2.5090809287301226727e+3;
-        num = num * r + 3.3430575583588128105e+4;
-        num = num * r + 6.7265770927008700853e+4;
-        num = num * r + 4.5921953931549871457e+4;
-        num = num * r + 1.3731693765509461125e+4;
-        num = num * r + 1.9715909503065514427e+3;
-        num = num * r + 1.3314166789178437745e+2;
-        num = num * r + 3.3871328727963666080;
-        double den = 5.2264952788528545610e+3;
-        den = den * r + 2.8729085735721942674e+4;
-        den = den * r + 3.9307895800092710610e+4;
-        den = den * r + 2.1213794301586595867e+4;
-        den = den * r + 5.3941960214247511077e+3;
-        den = den * r + 6.8718700749205790830e+2;
-        den = den * r + 4.2313330701600911252e+1;
-        den = den * r + 1.0;
-        return q * num / den;
-    }
+__host__ __device__ inline double inv_normal_cdf(double p);
+
+// The two halves of inv_normal_cdf for warp code that wants them apart: in a warp of 32 deviates almost always SOME
+// lane is in a tail (15 % of the draws are), so the combined function pays for the log / sqrt / second rational on
+// every call.  prep_chain evaluates the central form for everybody and queues the tail arguments, which are then
+// worked off 32 at a time.  Same expressions, same results, as inv_normal_cdf above.
+__host__ __device__ __forceinline__ bool inv_normal_cdf_central(double p, double& out) {
+    const double q = p - 0.5;
+    const double r = 0.180625 - q * q;
+    double num = 2.5090809287301226727e+3;
+    num = num * r + 3.3430575583588128105e+4;
+    num = num * r + 6.7265770927008700853e+4;
+    num = num * r + 4.5921953931549871457e+4;
+    num = num * r + 1.3731693765509461125e+4;
+    num = num * r + 1.9715909503065514427e+3;
+    num = num * r + 1.3314166789178437745e+2;
+    num = num * r + 3.3871328727963666080;
+    double den = 5.2264952788528545610e+3;
+    den = den * r + 2.8729085735721942674e+4;
+    den = den * r + 3.9307895800092710610e+4;
+    den = den * r + 2.1213794301586595867e+4;
+    den = den * r + 5.3941960214247511077e+3;
+    den = den * r + 6.8718700749205790830e+2;
+    den = den * r + 4.2313330701600911252e+1;
+    den = den * r + 1.0;
+    out = q * num / den;
+    return fabs(q) <= 0.425;
+}
+__host__ __device__ inline double inv_normal_cdf_tail(double p) {   // |p - 0.5| > 0.425
+    const double q = p - 0.5;
     double r = (q < 0.0) ? p : 1.0 - p;
     r = sqrt(-log(r));
     double val;
@@ -118,6 +126,11 @@ __host__ __device__ inline double inv_normal_cdf(double p) {
         val = num / den;
     }
     return (q < 0.0) ? -val : val;
+}
+
+__host__ __device__ inline double inv_normal_cdf(double p) {
+    double v;
+    return inv_normal_cdf_central(p, v) ? v : inv_normal_cdf_tail(p);
 }
 
 // utils.F90:376-388

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../include/polychord_b200.h"
+#include "pc_errors.h"
 #include "pc_probes.cuh"
 #include "pc_files.h"
 #include "pc_ini.h"
@@ -33,7 +34,7 @@ namespace pc {
     do {                                                                                                \
         cudaError_t e_ = (call);                                                                        \
         if (e_ != cudaSuccess)                                                                          \
-            throw std::runtime_error(std::string("polychord_b200: CUDA error: ") + cudaGetErrorString(e_) + \
+            throw pc::RunError(std::string("polychord_b200: CUDA error: ") + cudaGetErrorString(e_) + \
                                      " at " + __FILE__ + ":" + std::to_string(__LINE__));              \
     } while (0)
 
@@ -60,7 +61,7 @@ struct DevicePool {
                 e = cudaMalloc(&p, bytes);
             }
             if (e != cudaSuccess)
-                throw std::runtime_error(std::string("polychord_b200: cudaMalloc failed: ") + cudaGetErrorString(e));
+                throw pc::RunError(std::string("polychord_b200: cudaMalloc failed: ") + cudaGetErrorString(e));
         }
         live_blocks[p] = {dev, bytes};
         return p;
@@ -175,7 +176,12 @@ struct DevArr {  // RAII device buffer (exception-transparent: callbacks may thr
 };
 
 struct Options {
-    double batch_fraction = 0.25;
+    // K lowest points die per generation: K = round(nlive * batch_fraction).  0 = automatic: 1/2 for a run that has
+    // the device to itself (its wall time is the number of generations: per unit of compression K = n/2 needs 2.4
+    // times fewer than K = n/4 for 1.25 times the variance), 1/4 for the runs of an ensemble (the device is full
+    // either way, so the smaller variance per likelihood evaluation wins).  DESIGN.md section 2.
+    double batch_fraction = 0.0;
+    int dense = 0;      // the dense chain phase (pc_dense.cuh): 0 = for ensembles, 1 = always (testing), -1 = never
     int batch_K = 0;
     int device = 0;
     int warps_per_cta = 8;
@@ -235,18 +241,18 @@ static void build_dev_model(const pc_settings& s, const ModelSpec& ms, DevModel&
         const auto& q = ms.like_params;
         if ((int)q.size() >= 2 * D) { mu.assign(q.begin(), q.begin() + D); sg.assign(q.begin() + D, q.begin() + 2 * D); }
         else if (q.size() == 2) { mu.assign(D, q[0]); sg.assign(D, q[1]); }
-        else if (!q.empty()) throw std::invalid_argument("polychord_b200: gaussian likelihood wants 0, 2 or 2*nDims params");
+        else if (!q.empty()) throw pc::ArgError("polychord_b200: gaussian likelihood wants 0, 2 or 2*nDims params");
         dm.gauss_norm = 0.0;
         for (int i = 0; i < D; ++i) dm.gauss_norm += std::log(sg[i]) + LOG_TWO_PI / 2.0;
         lp = mu;
         for (int i = 0; i < D; ++i) lp.push_back(1.0 / sg[i]);
     } else if (ms.like_kind == PC_LIKE_CORR_GAUSSIAN) {
         if ((int)ms.like_params.size() != D + D * D + 1)
-            throw std::invalid_argument("polychord_b200: correlated gaussian wants mu[D], invcov[D*D], logdet");
+            throw pc::ArgError("polychord_b200: correlated gaussian wants mu[D], invcov[D*D], logdet");
         lp.assign(ms.like_params.begin(), ms.like_params.begin() + D + D * D);
         dm.corr_const = -(D * LOG_TWO_PI + ms.like_params[D + D * D]) / 2.0;              // utils.F90:1040-1046
     } else if (ms.like_kind != PC_LIKE_RASTRIGIN) {
-        throw std::invalid_argument("polychord_b200: unknown device likelihood kind");
+        throw pc::ArgError("polychord_b200: unknown device likelihood kind");
     }
     if (lp.empty()) lp.push_back(0.0);
     dm.like.alloc(lp.size());
@@ -256,7 +262,7 @@ static void build_dev_model(const pc_settings& s, const ModelSpec& ms, DevModel&
     if ((int)ms.prior_params.size() == 2 * D)
         for (int i = 0; i < D; ++i) { pr[i] = ms.prior_params[i]; pr[D + i] = ms.prior_params[D + i] - ms.prior_params[i]; }
     else if (!ms.prior_params.empty())
-        throw std::invalid_argument("polychord_b200: uniform prior wants lo[D], hi[D]");
+        throw pc::ArgError("polychord_b200: uniform prior wants lo[D], hi[D]");
     dm.prior.alloc(pr.size());
     dm.prior.upload(pr.data(), pr.size(), st);
     PC_CUDA(cudaStreamSynchronize(st));
@@ -273,7 +279,7 @@ static int device_check() {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0)
-        throw std::runtime_error("polychord_b200: no CUDA device available -- this engine has no CPU fallback");
+        throw pc::RunError("polychord_b200: no CUDA device available -- this engine has no CPU fallback");
     PC_CUDA(cudaSetDevice(g_opt.device));
     return n;
 }
@@ -292,25 +298,40 @@ static ShapeFns pick_shape(int D, int kind) {
 #undef PC_SHAPE
 }
 
-static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const DevModel& dm, int W);
+static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const DevModel& dm, int W, bool alone, bool dense);
 
-// the largest warp count per CTA (<= the requested one) whose scratch fits in shared memory
-static Layout make_layout(const pc_settings& s, const ModelSpec& ms, const DevModel& dm, int W) {
+// points that die per generation (see Options::batch_fraction)
+static int batch_size(int nlive, bool alone) {
+    const double f = g_opt.batch_fraction > 0.0 ? g_opt.batch_fraction : (alone ? 0.5 : 0.25);
+    int K = g_opt.batch_K > 0 ? g_opt.batch_K : (int)std::lround(nlive * f);
+    return std::max(1, std::min(K, nlive - 1));
+}
+
+// the largest warp count per CTA (<= the requested one) whose scratch fits in shared memory; the dense chain phase
+// wants two CTAs per SM (half the shared memory each) and falls back to the warp-per-chain phase when even four warps
+// do not fit
+static Layout make_layout(const pc_settings& s, const ModelSpec& ms, const DevModel& dm, int W, bool alone = true, bool dense = false) {
+    if (dense) {
+        for (int w = W; w >= 4; --w) {
+            Layout L = make_layout_w(s, ms, dm, w, alone, true);
+            if (L.kp.nh_in_smem && L.smem <= 112 * 1024) return L;
+        }
+    }
     for (;; --W) {
-        Layout L = make_layout_w(s, ms, dm, W);
+        Layout L = make_layout_w(s, ms, dm, W, alone, false);
         if (L.smem <= 227 * 1024) return L;
-        if (W == 1) throw std::invalid_argument("polychord_b200: the run does not fit in shared memory (nlive too large for the in-kernel sort, or nDims*nDims too large)");
+        if (W == 1) throw pc::ArgError("polychord_b200: the run does not fit in shared memory (nlive too large for the in-kernel sort, or nDims*nDims too large)");
     }
 }
 
-static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const DevModel& dm, int W) {
+static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const DevModel& dm, int W, bool alone, bool dense) {
     Layout L;
     KParams& k = L.kp;
     std::memset(&k, 0, sizeof(k));
     const int D = s.nDims, P = s.nDerived, R = s.num_repeats;
-    if (D < 1 || D > 128) throw std::invalid_argument("polychord_b200: nDims must be in 1..128");
-    if (R < 1) throw std::invalid_argument("polychord_b200: num_repeats must be >= 1");  // settings.f90:216
-    if (s.nlive < 2) throw std::invalid_argument("polychord_b200: nlive must be >= 2");
+    if (D < 1 || D > 128) throw pc::ArgError("polychord_b200: nDims must be in 1..128");
+    if (R < 1) throw pc::ArgError("polychord_b200: num_repeats must be >= 1");  // settings.f90:216
+    if (s.nlive < 2) throw pc::ArgError("polychord_b200: nlive must be >= 2");
     L.fn = pick_shape(D, ms.like_kind == PC_LIKE_HOST ? PC_LIKE_GAUSSIAN : ms.like_kind);
     k.host_like = ms.like_kind == PC_LIKE_HOST ? 1 : 0;
     k.live_given = k.host_like;
@@ -322,7 +343,7 @@ static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const Dev
         for (int v : g_grade_dims) sd += v;
         for (int v : g_grade_reps) sr += v;
         if (sd != D || sr != R || g_grade_dims.size() > MAX_GRADES)
-            throw std::invalid_argument("polychord_b200: grade_dims must sum to nDims, the repeats per grade to num_repeats (at most 8 grades)");
+            throw pc::ArgError("polychord_b200: grade_dims must sum to nDims, the repeats per grade to num_repeats (at most 8 grades)");
         k.cp.ngrade = (int)g_grade_dims.size();
         for (int g = 0; g < k.cp.ngrade; ++g) { k.cp.gdims[g] = g_grade_dims[g]; k.cp.greps[g] = g_grade_reps[g]; }
     }
@@ -353,15 +374,16 @@ static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const Dev
     // phase U: pivot + a staged batch of augmented rows per warp; all warps' areas together hold the CTA's moment matrix
     const size_t cov_bytes = std::max((size_t)(Dpad + U_BATCH * (Dp8 + 4)) * 8,
                                       ((size_t)(Dpad + Dp8 * Dp8) * 8 + W - 1) / W);
-    int K = g_opt.batch_K > 0 ? g_opt.batch_K : (int)std::lround(s.nlive * g_opt.batch_fraction);
-    K = std::max(1, std::min(K, s.nlive - 1));
+    const int K = batch_size(s.nlive, alone);
     k.batch_K = K;
     const size_t sort_bytes = std::max(smem_S_bytes(s.nlive, K), (size_t)64 * 8 + (size_t)(D * D + Dpad) * 8);  // phase S, or the covariance (+ mean shift) in finish_update
-    const size_t budget = 200 * 1024;
-    const size_t with_nh = chain_scratch_bytes(D, R, k.cp.LD, true, ms.like_kind, npt);
-    const bool in_smem = !g_opt.nh_global && (off + (size_t)W * std::max(with_nh, cov_bytes) <= budget);
+    const size_t budget = dense ? 108 * 1024 : 200 * 1024;
+    const int slb = dense ? dense_slb(L.fn.G * L.fn.DPL) : 0;   // dense chain phase: slice records staged per point group
+    k.dense = dense ? 1 : 0;
+    const size_t with_nh = chain_scratch_bytes(D, R, k.cp.LD, true, ms.like_kind, npt, slb);
+    const bool in_smem = (!g_opt.nh_global || dense) && (off + (size_t)W * std::max(with_nh, cov_bytes) <= budget);
     k.nh_in_smem = in_smem ? 1 : 0;
-    size_t wb = std::max(chain_scratch_bytes(D, R, k.cp.LD, in_smem, ms.like_kind, npt), cov_bytes);
+    size_t wb = std::max(chain_scratch_bytes(D, R, k.cp.LD, in_smem, ms.like_kind, npt, slb), cov_bytes);
     wb = (wb + 15) & ~(size_t)15;
     k.warp_bytes = (int)wb;
     L.smem = off + std::max((size_t)W * wb, sort_bytes);
@@ -370,6 +392,10 @@ static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const Dev
 
 static void set_smem(const ShapeFns& fn, size_t smem) {
     PC_CUDA(cudaFuncSetAttribute(fn.run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (fn.run_dense) {
+        PC_CUDA(cudaFuncSetAttribute(fn.run_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PC_CUDA(cudaFuncSetAttribute(fn.slice_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     PC_CUDA(cudaFuncSetAttribute(fn.slice, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PC_CUDA(cudaFuncSetAttribute(fn.calc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 }
@@ -436,7 +462,7 @@ static bool read_resume_file(const std::string& path, ResumeData& rd) {
          get_vec(f, rd.ph) && get_vec(f, rd.chol) && get_vec(f, rd.cov) && get_vec(f, rd.gsum) && get_vec(f, rd.lab) &&
          get_vec(f, rd.phl) && get_vec(f, rd.cchol) && get_vec(f, rd.boost) && get_vec(f, rd.boost_win);
     std::fclose(f);
-    if (!ok) throw std::invalid_argument("polychord_b200: " + path + " is not a resume file of this engine version");
+    if (!ok) throw pc::ArgError("polychord_b200: " + path + " is not a resume file of this engine version");
     return true;
 }
 
@@ -487,12 +513,12 @@ struct Engine {
             double* rec = &live[(size_t)j * T];
             std::copy(g_init_cubes.begin() + (size_t)j * D, g_init_cubes.begin() + (size_t)(j + 1) * D, rec);
             for (int i = 0; i < D; ++i)
-                if (!(rec[i] >= 0.0 && rec[i] <= 1.0)) throw std::invalid_argument("polychord_b200: cube_samples must lie in the unit hypercube");
+                if (!(rec[i] >= 0.0 && rec[i] <= 1.0)) throw pc::ArgError("polychord_b200: cube_samples must lie in the unit hypercube");
             std::copy(rec, rec + D, cube.begin());
             std::fill(phi.begin(), phi.end(), 0.0);
             g_init_prior(cube.data(), theta.data(), D);
             const double logL = g_init_ll(theta.data(), D, phi.data(), P);
-            if (!(logL > S.logzero)) throw std::invalid_argument("polychord_b200: a cube_samples point has loglikelihood <= logzero");
+            if (!(logL > S.logzero)) throw pc::ArgError("polychord_b200: a cube_samples point has loglikelihood <= logzero");
             std::copy(theta.begin(), theta.end(), rec + D);
             for (int i = 0; i < P; ++i) rec[2 * D + i] = phi[i];
             rec[2 * D + P] = S.logzero;
@@ -520,7 +546,7 @@ struct Engine {
         DevArr<double> d_cubes((size_t)n * D);
         std::vector<double> cubes((size_t)n * D);
         while (have < n) {
-            if (a > 1000LL * n + 1000000LL) throw std::runtime_error("polychord_b200: could not generate live points (likelihood <= logzero everywhere?)");
+            if (a > 1000LL * n + 1000000LL) throw pc::RunError("polychord_b200: could not generate live points (likelihood <= logzero everywhere?)");
             const int count = n - have;   // as many attempts as points are still missing, drawn on the device
             hc_init_cubes_kernel<<<(count * D + 255) / 256, 256, 0, stream>>>(seed, a, count, D, d_cubes.p);
             PC_CUDA(cudaGetLastError());
@@ -604,7 +630,7 @@ struct Engine {
                 }
             }
             if (active == 0) break;
-            if (g_abort) throw std::runtime_error("polychord_b200: run aborted by a host callback (pc_request_abort)");
+            if (g_abort) throw pc::RunError("polychord_b200: run aborted by a host callback (pc_request_abort)");
             hc_step_kernel<<<blocks, W * 32, 0, stream>>>(hp);
             PC_CUDA(cudaGetLastError());
             ++hc_rounds;
@@ -629,15 +655,19 @@ struct Engine {
         S = s; ms = m; nruns = nruns_;
         stream = g_stream;
         if (S.nprior > 0 && S.nprior != S.nlive)
-            throw std::invalid_argument("polychord_b200: nprior != nlive is not supported by the device path yet");
+            throw pc::ArgError("polychord_b200: nprior != nlive is not supported by the device path yet");
         host_like = ms.like_kind == PC_LIKE_HOST;
         if (host_like && (nruns != 1 || g_mgpu.world > 1))
-            throw std::invalid_argument("polychord_b200: host-callback likelihoods run one run on one GPU");
-        if (host_like && (!g_host_ll || !g_host_prior)) throw std::invalid_argument("polychord_b200: host callbacks missing");
+            throw pc::ArgError("polychord_b200: host-callback likelihoods run one run on one GPU");
+        if (host_like && (!g_host_ll || !g_host_prior)) throw pc::ArgError("polychord_b200: host callbacks missing");
         build_dev_model(S, ms, dm, stream);
         mark("build_dev_model");
         int W = std::max(1, std::min(8, g_opt.warps_per_cta));
-        L = make_layout(S, ms, dm, W);
+        const bool alone = nruns == 1;
+        // the dense chain phase (a chain per point group) for runs that share the device; pc_dense.cuh
+        const bool want_dense = g_opt.dense >= 0 && (g_opt.dense > 0 || nruns > 1) && !host_like && g_mgpu.world <= 1 &&
+                                ms.like_kind != PC_LIKE_CORR_GAUSSIAN && g_grade_dims.size() <= 1;
+        L = make_layout(S, ms, dm, W, alone, want_dense);
         W = L.W;
         set_smem(L.fn, L.smem);
         mark("layout+set_smem");
@@ -647,11 +677,11 @@ struct Engine {
         k.clustering = (S.do_clustering && nruns == 1 && g_mgpu.world <= 1 && !host_like) ? 1 : 0;
         given_live = false;
         if (g_init_n > 0) {
-            if (nruns != 1 || g_mgpu.world > 1) throw std::invalid_argument("polychord_b200: cube_samples start one run on one GPU");
+            if (nruns != 1 || g_mgpu.world > 1) throw pc::ArgError("polychord_b200: cube_samples start one run on one GPU");
             if (g_init_n != k.n || g_init_D != k.cp.D)
-                throw std::invalid_argument("polychord_b200: cube_samples must hold nlive points of nDims coordinates (a different "
+                throw pc::ArgError("polychord_b200: cube_samples must hold nlive points of nDims coordinates (a different "
                                             "number would need the dynamic-nlive schedule, which this engine does not have)");
-            if (!g_init_ll || !g_init_prior) throw std::invalid_argument("polychord_b200: cube_samples need the run's callbacks");
+            if (!g_init_ll || !g_init_prior) throw pc::ArgError("polychord_b200: cube_samples need the run's callbacks");
             given_live = true;
             k.live_given = 1;
         }
@@ -662,14 +692,16 @@ struct Engine {
             k.boost_thin = S.boost_posterior < 0.0 ? 1.0 : std::min(1.0, S.boost_posterior / (double)k.cp.R);
         g_mirror.boost_logw.clear(); g_mirror.boost_rows.clear(); g_mirror.boost_dead.clear(); g_mirror.boost_after.clear();
         // read_resume: a file of this run's shape continues the run (nested_sampling.F90:175-183)
-        if (g_resume.read && nruns == 1 && g_mgpu.world <= 1 && read_resume_file(g_resume.path, rd)) {
+        // (the caller's cube_samples win over an existing file, as in the reference: polychord.py:576-579 overwrites the
+        // resume file with them)
+        if (g_resume.read && g_init_n == 0 && nruns == 1 && g_mgpu.world <= 1 && read_resume_file(g_resume.path, rd)) {
             const ResumeHeader& rh = rd.h;
             bool same = rh.D == k.cp.D && rh.P == k.cp.P && rh.n == k.n && rh.R == k.cp.R && rh.batch_K == K &&
                         rh.like_kind == ms.like_kind && rh.clustering == k.clustering && rh.ngrade == k.cp.ngrade;
             for (int g = 0; same && g < k.cp.ngrade && k.cp.ngrade > 1; ++g)
                 same = rh.gdims[g] == k.cp.gdims[g] && rh.greps[g] == k.cp.greps[g];
             if (!same)  // read_write.F90:402-417: a resume file of a different run is fatal
-                throw std::invalid_argument("polychord_b200: the resume file " + g_resume.path + " belongs to a run of a different shape "
+                throw pc::ArgError("polychord_b200: the resume file " + g_resume.path + " belongs to a run of a different shape "
                                             "(nDims, nDerived, nlive, num_repeats, grades, likelihood kind, clustering or batch size)");
             resumed = true;
         }
@@ -677,16 +709,16 @@ struct Engine {
         int dev = 0, sms = 0, per_sm = 0;
         PC_CUDA(cudaGetDevice(&dev));
         PC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        PC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&per_sm, L.fn.run, W * 32, L.smem, 0));
-        if (per_sm < 1) throw std::runtime_error("polychord_b200: run kernel does not fit on an SM");
+        PC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&per_sm, k.dense ? L.fn.run_dense : L.fn.run, W * 32, L.smem, 0));
+        if (per_sm < 1) throw pc::RunError("polychord_b200: run kernel does not fit on an SM");
         long long capacity = (long long)sms * per_sm;
         // A run alone on the device spreads its chains one per CTA (a chain warp then has an SM sub-partition
         // to itself) and leaves CTA 0 to the bookkeeping; an ensemble packs W chains per CTA.
         const bool sharded = g_mgpu.world > 1;
         if (sharded) {
-            if (nruns != 1) throw std::invalid_argument("polychord_b200: a sharded run cannot be part of an ensemble");
+            if (nruns != 1) throw pc::ArgError("polychord_b200: a sharded run cannot be part of an ensemble");
             if (g_mgpu.batch_K != K || g_mgpu.T != k.cp.T || g_mgpu.D != k.cp.D)
-                throw std::invalid_argument("polychord_b200: pc_mgpu_create was called with different settings than this run");
+                throw pc::ArgError("polychord_b200: pc_mgpu_create was called with different settings than this run");
             k.sh.rank = g_mgpu.rank; k.sh.world = g_mgpu.world; k.sh.xstride = (long long)mgpu_xstride(k.cp.D);
             for (int q = 0; q < g_mgpu.world; ++q) {
                 unsigned char* b = (unsigned char*)g_mgpu.peer[q];
@@ -696,12 +728,14 @@ struct Engine {
             }
         }
         G = (sharded ? (K + g_mgpu.world - 1) / g_mgpu.world : K) + 1;
+        if (k.dense) G = (K + W * (32 / L.fn.G) - 1) / (W * (32 / L.fn.G));   // W * 32/G chains per CTA and pass
         if (g_opt.max_ctas > 0) G = std::min(G, g_opt.max_ctas);
         G = (int)std::max(1LL, std::min<long long>(G, capacity / nruns));
-        if ((long long)G * nruns > capacity) throw std::invalid_argument("polychord_b200: too many concurrent runs for one launch");
+        if ((long long)G * nruns > capacity) throw pc::ArgError("polychord_b200: too many concurrent runs for one launch");
         k.ctas_per_run = G;
-        k.chain_cta0 = (G >= 8) ? 1 : 0;
+        k.chain_cta0 = (G >= 8 && !k.dense) ? 1 : 0;
         k.paired = (k.chain_cta0 == 1 && W >= 2 && (W % 2) == 0 && !g_opt.no_pairing) ? 1 : 0;
+        k.backoff = nruns > 1 ? 128 : 0;
         PC_CUDA(cudaEventCreate(&ev0));
         PC_CUDA(cudaEventCreate(&ev1));
         mark("occupancy+events");
@@ -737,7 +771,8 @@ struct Engine {
             h.gsum.alloc((size_t)2 * D + 4);
             h.partial.alloc((size_t)G * k.partial_stride);
             h.pcount.alloc((size_t)cap_ph / U_TILE + 2); h.pcount.zero(stream);
-            if (!k.nh_in_smem) h.nh.alloc((size_t)G * W * R * k.cp.LD);
+            if (k.dense) h.nh.alloc((size_t)G * W * (32 / L.fn.G) * R * dense_slb(L.fn.G * L.fn.DPL));   // slice records of the chains in flight
+            else if (!k.nh_in_smem) h.nh.alloc((size_t)G * W * R * k.cp.LD);
             if (k.clustering) {
                 h.lab.alloc(n); h.lab.zero(stream);
                 h.phl0.alloc(cap_ph); h.phl0.zero(stream);
@@ -811,7 +846,7 @@ struct Engine {
         KParams kp = L.kp;
         void* args[] = {&kp};
         PC_CUDA(cudaEventRecord(ev0, stream));
-        PC_CUDA(cudaLaunchCooperativeKernel(L.fn.run, dim3(G * nruns), dim3(L.W * 32), args, L.smem, stream));
+        PC_CUDA(cudaLaunchCooperativeKernel(kp.dense ? L.fn.run_dense : L.fn.run, dim3(G * nruns), dim3(L.W * 32), args, L.smem, stream));
         PC_CUDA(cudaEventRecord(ev1, stream));
     }
     void launch_finish() {
@@ -1233,7 +1268,7 @@ struct Engine {
         d2h += (long long)(w.live.size() + w.dead.size() + w.ph.size()) * 8;
         const std::string tmp = g_resume.path.substr(0, g_resume.path.size() - 7) + "_temp.resume";
         FILE* f = std::fopen(tmp.c_str(), "wb");
-        if (!f) throw std::runtime_error("polychord_b200: cannot write " + tmp);
+        if (!f) throw pc::RunError("polychord_b200: cannot write " + tmp);
         std::fwrite(&w.h, sizeof(w.h), 1, f);
         std::fwrite(&w.st, sizeof(DevRun), 1, f);
         put_vec(f, w.live); put_vec(f, w.order); put_vec(f, w.okey); put_vec(f, w.dead); put_vec(f, w.logw); put_vec(f, w.ph);
@@ -1336,15 +1371,15 @@ struct Engine {
             bool all_done = true, regrow = false;
             for (int r = 0; r < nruns; ++r) {
                 int stt = runs[r].host_st.status;
-                if (stt == ST_ERROR) throw std::runtime_error("polychord_b200: could not generate live points (likelihood <= logzero everywhere?)");
-                if (stt == ST_DUMP && ctl) throw std::runtime_error("polychord_b200: run aborted");
+                if (stt == ST_ERROR) throw pc::RunError("polychord_b200: could not generate live points (likelihood <= logzero everywhere?)");
+                if (stt == ST_DUMP && ctl) throw pc::RunError("polychord_b200: run aborted");
                 if (stt == ST_DUMP) {  // sync_dump: the kernel left at the update, dump and relaunch
                     if (dumping)
                         dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, runs[r].live.p, stream,
                              runs[r].host_st.nlike);
                     write_resume(false);
                 }
-                if (g_abort) throw std::runtime_error("polychord_b200: run aborted by a host callback (pc_request_abort)");
+                if (g_abort) throw pc::RunError("polychord_b200: run aborted by a host callback (pc_request_abort)");
                 if (stt == ST_HOSTCHAINS) host_chains();
                 if (stt == ST_CLUSTER) {  // the update left for the clustering pass; the dump of this update happens here too
                     if (dumping)
@@ -1443,6 +1478,10 @@ static int fail(int code, const std::string& msg) {
 
 using namespace pc;
 
+// the facade's defaults (csrc/pc_facade.cpp; c_interface.cpp:210-213): recognised by pointer identity
+void default_prior(double* cube, double* theta, int nDims);
+void default_dumper(int, int, int, double*, double*, double*, double, double);
+
 // ==========================================================================================
 // C ABI
 // ==========================================================================================
@@ -1459,6 +1498,7 @@ int pc_set_option(const char* name, double value) {
     std::string s(name);
     if (s == "batch_fraction") g_opt.batch_fraction = value;
     else if (s == "batch_K") g_opt.batch_K = (int)value;
+    else if (s == "dense") g_opt.dense = (int)value;
     else if (s == "device") g_opt.device = (int)value;
     else if (s == "warps_per_cta") g_opt.warps_per_cta = (int)value;
     else if (s == "max_ctas") g_opt.max_ctas = (int)value;
@@ -1476,6 +1516,7 @@ double pc_get_option(const char* name) {
     std::string s(name);
     if (s == "batch_fraction") return g_opt.batch_fraction;
     if (s == "batch_K") return g_opt.batch_K;
+    if (s == "dense") return g_opt.dense;
     if (s == "device") return g_opt.device;
     if (s == "warps_per_cta") return g_opt.warps_per_cta;
     if (s == "max_ctas") return g_opt.max_ctas;
@@ -1512,10 +1553,9 @@ void pc_release_memory(void) { pool().trim(); }
 int pc_mgpu_create(const pc_settings* s, int world, unsigned char* handle64) {
     try {
         device_check();
-        if (world < 2 || world > MAX_RANKS) throw std::invalid_argument("polychord_b200: world must be 2..8");
-        if (g_mgpu.local) throw std::invalid_argument("polychord_b200: pc_mgpu_create called twice (pc_mgpu_destroy first)");
-        int K = g_opt.batch_K > 0 ? g_opt.batch_K : (int)std::lround(s->nlive * g_opt.batch_fraction);
-        K = std::max(1, std::min(K, s->nlive - 1));
+        if (world < 2 || world > MAX_RANKS) throw pc::ArgError("polychord_b200: world must be 2..8");
+        if (g_mgpu.local) throw pc::ArgError("polychord_b200: pc_mgpu_create called twice (pc_mgpu_destroy first)");
+        const int K = batch_size(s->nlive, true);
         const int T = 2 * s->nDims + s->nDerived + 2;
         g_mgpu.bytes = mgpu_block_bytes(K, T, s->nDims, world);
         g_mgpu.batch_K = K; g_mgpu.T = T; g_mgpu.D = s->nDims; g_mgpu.world = 0; g_mgpu.epoch = 0;
@@ -1533,8 +1573,8 @@ int pc_mgpu_create(const pc_settings* s, int world, unsigned char* handle64) {
 }
 int pc_mgpu_attach(int rank, int world, const unsigned char* handles) {
     try {
-        if (!g_mgpu.local) throw std::invalid_argument("polychord_b200: pc_mgpu_attach before pc_mgpu_create");
-        if (rank < 0 || rank >= world || world > MAX_RANKS) throw std::invalid_argument("polychord_b200: bad rank/world");
+        if (!g_mgpu.local) throw pc::ArgError("polychord_b200: pc_mgpu_attach before pc_mgpu_create");
+        if (rank < 0 || rank >= world || world > MAX_RANKS) throw pc::ArgError("polychord_b200: bad rank/world");
         for (int q = 0; q < world; ++q) {
             if (q == rank) { g_mgpu.peer[q] = g_mgpu.local; continue; }
             cudaIpcMemHandle_t h;
@@ -1654,10 +1694,12 @@ int pc_run(const pc_settings* s, int like_kind, const double* like_params, int n
         if (prior_params) ms.prior_params.assign(prior_params, prior_params + n_prior_params);
         int seed = s->seed;
         return run_common(s, ms, 1, &seed, dumper, out);
-    } catch (const std::invalid_argument& ex) {
+    } catch (const ArgError& ex) {
         return fail(-2, ex.what());
-    } catch (const std::runtime_error& ex) {
+    } catch (const std::exception& ex) {   // these entry points are bound from C / ctypes: nothing may unwind through them
         return fail(-3, ex.what());
+    } catch (...) {
+        return fail(-3, "unknown exception");
     }
 }
 
@@ -1669,10 +1711,12 @@ int pc_run_ensemble(const pc_settings* s, int like_kind, const double* like_para
         if (like_params) ms.like_params.assign(like_params, like_params + n_like_params);
         if (prior_params) ms.prior_params.assign(prior_params, prior_params + n_prior_params);
         return run_common(s, ms, nruns, seeds, nullptr, out);
-    } catch (const std::invalid_argument& ex) {
+    } catch (const ArgError& ex) {
         return fail(-2, ex.what());
-    } catch (const std::runtime_error& ex) {
+    } catch (const std::exception& ex) {   // these entry points are bound from C / ctypes: nothing may unwind through them
         return fail(-3, ex.what());
+    } catch (...) {
+        return fail(-3, "unknown exception");
     }
 }
 
@@ -1689,7 +1733,8 @@ static void probe_setup(ProbeCtx& c, const pc_settings* s, int like_kind, const 
     if (lp) c.ms.like_params.assign(lp, lp + nlp);
     if (pp) c.ms.prior_params.assign(pp, pp + npp);
     build_dev_model(*s, c.ms, c.dm, g_stream);
-    c.L = make_layout(*s, c.ms, c.dm, std::max(1, std::min(8, g_opt.warps_per_cta)));
+    c.L = make_layout(*s, c.ms, c.dm, std::max(1, std::min(8, g_opt.warps_per_cta)), true,
+                      g_opt.dense > 0 && like_kind != PC_LIKE_CORR_GAUSSIAN && g_grade_dims.size() <= 1);
     set_smem(c.L.fn, c.L.smem);
 }
 
@@ -1714,7 +1759,11 @@ int pc_slice_chains(const pc_settings* s, int like_kind, const double* like_para
         d_babies.zero(st);
         int W = c.L.W;
         int blocks = std::min(1024, (nchains + W - 1) / W);
-        if (!k.nh_in_smem) d_nh.alloc((size_t)blocks * W * R * k.cp.LD);
+        const bool dense = k.dense != 0;
+        if (dense) {  // the dense chain phase: 32/G chains per warp, their slice records in global scratch
+            blocks = std::min(296, (nchains + W * (32 / c.L.fn.G) - 1) / (W * (32 / c.L.fn.G)));
+            d_nh.alloc((size_t)nchains * R * dense_slb(c.L.fn.G * c.L.fn.DPL));
+        } else if (!k.nh_in_smem) d_nh.alloc((size_t)blocks * W * R * k.cp.LD);
         KParams kp = k;
         unsigned seed = (unsigned)s->seed;
         const double *a_seed = d_seed.p, *a_chol = d_chol.p, *a_logL = d_logL.p;
@@ -1722,7 +1771,7 @@ int pc_slice_chains(const pc_settings* s, int like_kind, const double* like_para
         double *a_babies = d_babies.p, *a_nh = d_nh.p;
         long long* a_nlike = d_nlike.p;
         void* args[] = {&kp, &nchains, &a_seed, &a_chol, &a_logL, &a_uid, &seed, &a_babies, &a_nlike, &a_nh};
-        PC_CUDA(cudaLaunchKernel(c.L.fn.slice, dim3(blocks), dim3(W * 32), args, c.L.smem, st));
+        PC_CUDA(cudaLaunchKernel(dense ? c.L.fn.slice_dense : c.L.fn.slice, dim3(blocks), dim3(W * 32), args, c.L.smem, st));
         PC_CUDA(cudaGetLastError());
         d_babies.download(babies_out, (size_t)nchains * R * T, st);
         d_nlike.download(nlike_out, nchains, st);
@@ -1976,8 +2025,8 @@ double pc_prior_log_density(pc_prior_t prior, const double* cube, int nDims) { r
 static void run_maximiser(pc_loglikelihood_t ll, pc_prior_t prior, const pc_settings& s, const FileOpts& fo, const pc_run_info& info,
                           int feedback) {
     const int D = s.nDims, P = s.nDerived, T = 2 * D + P + 2;
-    if (!ll || !prior) throw std::invalid_argument("polychord_b200: maximise needs the loglikelihood and prior callbacks");
-    if (g_final_live.n < 1) throw std::runtime_error("polychord_b200: maximise: the run left no live points");
+    if (!ll || !prior) throw pc::ArgError("polychord_b200: maximise needs the loglikelihood and prior callbacks");
+    if (g_final_live.n < 1) throw pc::RunError("polychord_b200: maximise: the run left no live points");
     std::vector<double> mp(T, 0.0), pp(T, 0.0), mean(T, 0.0);
     if (feedback >= 1) std::printf("-------------------------------------\nMaximising Likelihood\n");
     const bool ok1 = do_maximisation(ll, prior, D, P, s.logzero, g_final_live.recs.data(), g_final_live.n, false, mp.data());
@@ -2023,6 +2072,7 @@ void polychord_c_interface(pc_loglikelihood_t loglikelihood, pc_prior_t prior, p
     (void)loglikes; (void)nlives; (void)comm; (void)nfail; (void)do_clustering;
     std::memset(&g_last, 0, sizeof(g_last));
     g_abort = 0;
+    if (dumper == default_dumper) dumper = nullptr;   // the facade's no-op: nothing to hand the dead points to
     pc_settings s;
     std::memset(&s, 0, sizeof(s));
     s.nDims = nDims; s.nDerived = nDerived; s.nlive = nlive; s.num_repeats = num_repeats; s.nprior = nprior; s.nfail = nfail;
@@ -2070,7 +2120,7 @@ void polychord_c_interface(pc_loglikelihood_t loglikelihood, pc_prior_t prior, p
     else if (loglikelihood == pc_rastrigin_loglikelihood) ms.like_kind = PC_LIKE_RASTRIGIN;
     else have_like = false;
     if (pi != prior_registry().end()) ms.prior_params = pi->second.params;
-    else if (prior == pc_unit_prior || prior == pc_uniform_prior) {}
+    else if (prior == pc_unit_prior || prior == pc_uniform_prior || prior == default_prior) {}
     else have_prior = false;
     struct HostGuard {  // callbacks may throw through the engine (e.g. a Python exception): always clear
         ~HostGuard() { g_host_ll = nullptr; g_host_prior = nullptr; }
@@ -2121,11 +2171,14 @@ void polychord_c_interface(pc_loglikelihood_t loglikelihood, pc_prior_t prior, p
     try {
         run_common(&s, ms, 1, &seed, dumper, &info);
         if (maximise) run_maximiser(loglikelihood, prior, s, fo, info, feedback);
-    } catch (const std::invalid_argument& ex) {
+    } catch (const ArgError& ex) {   // the engine's own failures only: a caller's exception passes through untouched
         fail(-2, ex.what());
         return;
-    } catch (const std::runtime_error& ex) {
+    } catch (const RunError& ex) {
         fail(-3, ex.what());
+        return;
+    } catch (const std::bad_alloc&) {
+        fail(-3, "out of host memory");
         return;
     }
     if (feedback >= 1) {

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <limits>
 #include <stdexcept>
+#include "pc_errors.h"
 #include <vector>
 
 #include "pc_device.cuh"  // the counter-based uniform stream (equally weighted posterior thinning)
@@ -50,7 +51,7 @@ struct Out {
     FILE* f;
     std::vector<char> big;  // stdio buffer of this file (must outlive the stream)
     explicit Out(const std::string& path) : f(std::fopen(path.c_str(), "w")), big(1 << 20) {
-        if (!f) throw std::runtime_error("polychord_b200: cannot open " + path + " for writing");
+        if (!f) throw pc::RunError("polychord_b200: cannot open " + path + " for writing");
         std::setvbuf(f, big.data(), _IOFBF, big.size());
     }
     Out(const Out&) = delete;
@@ -74,7 +75,7 @@ double host_logaddexp(double a, double b) {
 void write_prior_info(const FileOpts& o, long long nprior, long long ndiscarded) {
     if (!o.enabled || !o.write_prior) return;
     FILE* f = std::fopen((root_of(o) + ".prior_info").c_str(), "a");
-    if (!f) throw std::runtime_error("polychord_b200: cannot open " + root_of(o) + ".prior_info");
+    if (!f) throw pc::RunError("polychord_b200: cannot open " + root_of(o) + ".prior_info");
     std::fprintf(f, "nprior = %12lld\n", nprior);
     std::fprintf(f, "ndiscarded = %12lld\n", ndiscarded);
     std::fclose(f);

@@ -11,6 +11,7 @@
 #include <fstream>
 #include <sstream>
 #include <stdexcept>
+#include "pc_errors.h"
 
 #include "pc_device.cuh"  // inv_normal_cdf (AS241), host-callable
 
@@ -28,7 +29,7 @@ struct IniFile {
     std::vector<std::pair<std::string, std::string>> entries;
     explicit IniFile(const std::string& path) {
         std::ifstream f(path);
-        if (!f) throw std::invalid_argument("ini error: " + path + " does not exist");
+        if (!f) throw pc::ArgError("ini error: " + path + " does not exist");
         std::string line;
         while (std::getline(f, line)) {
             if (line.find_first_of("#!") != std::string::npos) continue;
@@ -46,7 +47,7 @@ struct IniFile {
     int get_int(const std::string& key, int dflt, bool required = false) const {
         const std::string v = get(key);
         if (v.empty()) {
-            if (required) throw std::invalid_argument("ini error: '" + key + "' is missing");
+            if (required) throw pc::ArgError("ini error: '" + key + "' is missing");
             return dflt;
         }
         return std::stoi(v);
@@ -125,13 +126,13 @@ IniConfig parse_ini(const std::string& path) {
     c.grade_frac = f.get_doubles("grade_frac");
     if (c.grade_frac.empty()) c.grade_frac.assign(1, 1.0);
     if (!f.get("nlives").empty() || !f.get("loglikes").empty())
-        throw std::invalid_argument("ini error: dynamic nlive schedules (nlives / loglikes) are not supported by the B200 engine");
+        throw pc::ArgError("ini error: dynamic nlive schedules (nlives / loglikes) are not supported by the B200 engine");
     // get_params, ini.f90:354-458:  P : name | latex | speed | prior type | prior block | prior params
     for (int i = 1;; ++i) {
         const std::string line = f.get("P", i);
         if (line.empty()) break;
         const std::vector<std::string> el = split_bar(line);
-        if (el.size() < 6) throw std::invalid_argument("ini error: parameter line needs 6 fields: " + line);
+        if (el.size() < 6) throw pc::ArgError("ini error: parameter line needs 6 fields: " + line);
         IniParam p;
         p.name = el[0];
         const size_t star = p.name.find('*');   // sub-clustering marker (ini.f90:376): accepted, not used
@@ -139,16 +140,16 @@ IniConfig parse_ini(const std::string& path) {
         p.latex = el[1];
         p.speed = std::stoi(el[2]);
         p.prior_type = prior_type_from_string(el[3]);
-        if (p.prior_type == 0) throw std::invalid_argument("get_priors error: Unknown prior type for parameter " + p.name);
+        if (p.prior_type == 0) throw pc::ArgError("get_priors error: Unknown prior type for parameter " + p.name);
         p.block = std::stoi(el[4]);
         std::istringstream is(el[5]);
         double v;
         while (is >> v) p.params.push_back(v);
         const size_t need = p.prior_type == 3 ? 3 : ((p.prior_type == 6 || p.prior_type == 10 || p.prior_type == 14) ? 1 : 2);
-        if (p.params.size() < need) throw std::invalid_argument("ini error: too few prior parameters for " + p.name);
+        if (p.params.size() < need) throw pc::ArgError("ini error: too few prior parameters for " + p.name);
         c.params.push_back(p);
     }
-    if (c.params.empty()) throw std::invalid_argument("ini error: no parameters (P : ...) in " + path);
+    if (c.params.empty()) throw pc::ArgError("ini error: no parameters (P : ...) in " + path);
     for (int i = 1;; ++i) {
         const std::string line = f.get("D", i);
         if (line.empty()) break;
@@ -159,14 +160,14 @@ IniConfig parse_ini(const std::string& path) {
     // asks for them in that order)
     for (size_t i = 1; i < c.params.size(); ++i)
         if (c.params[i].speed < c.params[i - 1].speed)
-            throw std::invalid_argument("ini error: list the parameters in order of increasing speed (grade)");
+            throw pc::ArgError("ini error: list the parameters in order of increasing speed (grade)");
     for (size_t i = 0; i < c.params.size(); ++i) {
         if (i == 0 || c.params[i].speed != c.params[i - 1].speed) c.grade_dims.push_back(0);
         c.grade_dims.back() += 1;
     }
     if (c.grade_frac.size() != c.grade_dims.size()) {
         if (c.grade_frac.size() == 1) c.grade_frac.assign(c.grade_dims.size(), c.grade_frac[0]);
-        else throw std::invalid_argument("ini error: grade_frac needs one entry per parameter speed");
+        else throw pc::ArgError("ini error: grade_frac needs one entry per parameter speed");
     }
     return c;
 }

@@ -22,6 +22,7 @@
 // (an ensemble) advance concurrently inside one launch.
 #pragma once
 #include "pc_chain.cuh"
+#include "pc_dense.cuh"
 
 namespace pc {
 
@@ -149,6 +150,8 @@ struct KParams {
     int chain_cta0;              // first CTA of a run's group that runs chains (1: CTA 0 only keeps the books)
     int paired;                  // 1: warps w >= W/2 prepare the chains of warp w - W/2 (a run alone on the device)
     int nh_in_smem, want_dump;
+    int dense;                   // 1: the dense chain phase (pc_dense.cuh): one chain per point group, rb.nh holds the slice records
+    int backoff;                 // ns a spinning thread sleeps between polls (ensembles: the SM is shared with other runs' warps); 0: spin
     int clustering;              // 1: do_clustering -- the kernel leaves at every update for the clustering pass (pc_cluster.cuh)
     int host_like;               // 1: likelihood/prior are host callbacks -- the kernel leaves before the chain phase (pc_hostchain.cuh)
     int live_given;              // 1: the host uploaded the initial live points (host callbacks, or the caller's cube_samples)
@@ -193,16 +196,18 @@ __device__ inline SmemS smem_S(unsigned char* base, int n, int batch_K) {
 // ------------------------------------------------------------------------------------------
 // group barrier (same fence / atomic / fence pattern cooperative groups uses for grid.sync)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void group_sync(unsigned int* bar, unsigned int G) {
+__device__ __forceinline__ void group_sync(unsigned int* bar, unsigned int G, int backoff = 0) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         unsigned int t = atomicAdd(bar, 1u);
         unsigned int target = (t / G + 1u) * G;
         unsigned int v;
-        do {
+        for (;;) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-        } while ((int)(v - target) < 0);
+            if ((int)(v - target) >= 0) break;
+            if (backoff) __nanosleep(backoff);   // an ensemble shares the SM: do not burn issue slots polling
+        }
         __threadfence();
     }
     __syncthreads();
@@ -238,12 +243,14 @@ __device__ __forceinline__ unsigned int warp_arrive(unsigned int* wbar, unsigned
     }
     return __shfl_sync(FULL, target, 0);
 }
-__device__ __forceinline__ void warp_wait(unsigned int* wbar, unsigned int target) {
+__device__ __forceinline__ void warp_wait(unsigned int* wbar, unsigned int target, int backoff = 0) {
     if ((threadIdx.x & 31) == 0) {
         unsigned int v;
-        do {
+        for (;;) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(wbar) : "memory");
-        } while ((int)(v - target) < 0);
+            if ((int)(v - target) >= 0) break;
+            if (backoff) __nanosleep(backoff);
+        }
         __threadfence();
     }
     __syncwarp();

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <numeric>
 #include <stdexcept>
+#include "pc_errors.h"
 
 #include "pc_files.h"
 
@@ -175,7 +176,7 @@ bool do_maximisation(pc_loglikelihood_t ll, pc_prior_t prior, int D, int P, doub
 void write_max_file(const std::string& path, int D, int P, const double* max_point, const double* max_post_point,
                     double dXdtheta, const double* mean_point) {
     FILE* f = std::fopen(path.c_str(), "w");
-    if (!f) throw std::runtime_error("polychord_b200: cannot write " + path);
+    if (!f) throw pc::RunError("polychord_b200: cannot write " + path);
     const int T = 2 * D + P + 2;
     char b[32];
     auto num = [&](double v) { format_e24(v, b); b[24] = 0; std::fputs(b, f); };

@@ -32,7 +32,7 @@ __device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st
             if (!p.live_given) st->init_attempts = 0;
         }
     }
-    group_sync(&st->bar, NG);
+    group_sync(&st->bar, NG, p.backoff);
     double* staging = rb.ph[1];
     for (;;) {
         const int need = vload(&st->init_need);
@@ -51,7 +51,7 @@ __device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st
             __syncwarp();
             if (j < need && M.sub == 0) M.finish_derived(rec, true);
         }
-        group_sync(&st->bar, NG);
+        group_sync(&st->bar, NG, p.backoff);
         if (cta == 0) {
             const int have = n - need;
             int run = 0;
@@ -74,7 +74,7 @@ __device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st
                 if (a0 > 1000LL * n + 1000000LL) { st->init_need = 0; st->status = ST_ERROR; }
             }
         }
-        group_sync(&st->bar, NG);
+        group_sync(&st->bar, NG, p.backoff);
     }
     if (cta == 0 && tid == 0) st->initialised = 1;
 }
@@ -705,10 +705,13 @@ __device__ inline bool publish_dump(const KParams& p, const RunBuf& rb, DevRun* 
 // so the counter-addressed direction/uniform preparation of a chain overlaps the bookkeeping of CTA 0
 // and the wait for the slowest chain.  Generations at the update cadence insert phase U (all CTAs)
 // between the arrival and the bookkeeping.
-template <int G, int DPL, int KIND>
-__global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ KParams p) {
+// MODE 0: a chain per warp (speculative rounds, helper warps; pc_chain.cuh) -- a run alone on the device.
+// MODE 1: a chain per point group (pc_dense.cuh) -- an ensemble that fills the device; two CTAs per SM (128 registers).
+template <int G, int DPL, int KIND, int MODE>
+__global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NPT = 32 / G;
+    constexpr int SLB = MODE == 1 ? dense_slb(G * DPL) : 0;
     const int NG = p.ctas_per_run;
     const int run = blockIdx.x / NG, cta = blockIdx.x % NG;
     const RunBuf rb = p.runs[run];
@@ -732,7 +735,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
     __syncthreads();
 
     const ChainScratch cs = chain_scratch(s_warp, D, R, LD, p.nh_in_smem != 0, p.cp.like_kind, NPT,
-                                          rb.nh ? rb.nh + (size_t)gw * R * LD : nullptr);
+                                          (MODE == 0 && rb.nh) ? rb.nh + (size_t)gw * R * LD : nullptr, SLB);
     Model<G, DPL, KIND> M;
     M.init(p.cp, s_like, p.prior_params, cs.dvec);
 
@@ -753,13 +756,13 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
         // (phase U at the update cadence) exactly where the chain phase would have left it
         if (vload(&st->do_update)) {
             phase_UA(p, rb, st, cta, NG);
-            group_sync(&st->bar, NG);
+            group_sync(&st->bar, NG, p.backoff);
             phase_UB(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt);
             if (cta == 0 && tid == 0) st->update_pending = 1;
         }
-        group_sync(&st->bar, NG);
+        group_sync(&st->bar, NG, p.backoff);
         if (cta == 0 && tid == 0) st->host_resume = 0;
-        group_sync(&st->bar, NG);
+        group_sync(&st->bar, NG, p.backoff);
     }
 
     const bool timer = (tid == 0) && (cta == 0);          // bookkeeping phases
@@ -768,7 +771,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
     for (;;) {
         if (cta == 0) {
             long long t0 = clock64();
-            if (have_wtarget) warp_wait(&st->wbar, wtarget);  // every chain of the previous generation is written
+            if (have_wtarget) warp_wait(&st->wbar, wtarget, p.backoff);  // every chain of the previous generation is written
             __syncthreads();
             if (scatter_due) {  // sharded run: every rank's last babies -> the replicated live array
                 shard_scatter(p, rb, st);
@@ -802,7 +805,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
             prep_uid = ~0ull;  // phase S overlays this CTA's chain scratch
         }
         const long long tg0 = clock64();
-        group_sync(&st->bar, NG);
+        group_sync(&st->bar, NG, p.backoff);
         const long long tg1 = clock64();
         if (ctimer) st->dbg[10] += tg1 - tg0;
         // the run's status and the generation's parameters: one load per lane, one latency
@@ -864,7 +867,60 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
         const int xpar = (int)(ngen_now & 1);
         double* xin_mine = sharded ? p.sh.xin[xr] + (size_t)xpar * p.batch_K * T : nullptr;
         int knext = -1;  // first chain this warp prepares for the next generation
-        if (p.paired) {
+        if constexpr (MODE == 1) {
+            // ---- dense chain phase (pc_dense.cuh): this warp's 32/G point groups run one chain each ----
+            if constexpr (KIND != LIKE_CORR) {
+                constexpr int GD = G * DPL;
+                const int grp = lane / G, sub = lane % G;
+                double* gblocks = rb.nh + (size_t)gw * NPT * R * SLB;   // the slice records of this warp's chains
+                for (int base = gw * NPT; base < K; base += GW * NPT) {
+                    // directions of the pass's chains, one chain at a time through the warp's shared-memory scratch
+                    for (int g = 0; g < NPT && base + g < K; ++g) {
+                        const unsigned long long uidg = (unsigned long long)(nchains_base + base + g);
+                        prep_chain<GD>(D, R, LD, rb.seed, uidg, cs, &p.cp);
+                        const double* Lf = s_chol;
+                        if (clustered) {  // the factor of the seed's cluster
+                            const double ug = uniform(rb.seed, TAG_SEED, uidg, 0u, 0u);
+                            const int cg = max(1, min(m, (int)ceil(ug * (double)m)));
+                            Lf = rb.cchol + (size_t)min(__ldcg(rb.lab + __ldcg(order + K + cg - 1)), MAX_CLUSTERS - 1) * D * D;
+                        }
+                        whiten_chain<(G * DPL + 7) / 8>(D, R, LD, Lf, cs);
+                        dense_store<GD>(R, LD, rb.seed, uidg, cs, gblocks + (size_t)g * R * SLB);
+                    }
+                    __syncwarp();
+                    const int k = base + grp;
+                    const bool active = k < K;
+                    const int kc = min(k, K - 1);
+                    const unsigned long long uid = (unsigned long long)(nchains_base + kc);
+                    const double u = uniform(rb.seed, TAG_SEED, uid, 0u, 0u);  // GenerateSeed, generate.F90:19-55
+                    const int choice = max(1, min(m, (int)ceil(u * (double)m)));
+                    const int src = __ldcg(order + K + choice - 1);
+                    const int dslot = __ldcg(order + kc);
+                    const int plab = clustered ? min(__ldcg(rb.lab + src), MAX_CLUSTERS - 1) : 0;
+                    double x[DPL];
+#pragma unroll
+                    for (int j = 0; j < DPL; ++j) x[j] = M.valid(j) ? __ldcg(rb.live + (size_t)src * T + M.dim(j)) : 0.0;
+                    // the dying point moves to the dead list before its slot is reused (run_time_info.f90:789-817)
+                    if (active)
+                        for (int e = sub; e < T; e += G)
+                            rb.dead[(size_t)(ndead_base + k) * T + e] = __ldcg(rb.live + (size_t)dslot * T + e);
+                    __syncwarp();
+                    double lfin = 0.0;
+                    slice_chains_dense<G, DPL, KIND>(p.cp, M, rb.seed, uid, active, x, Lstar, gblocks + (size_t)grp * R * SLB,
+                                                     cs.stage + (size_t)grp * 2 * SLB,
+                                                     pool + (size_t)(nph_base + (long long)kc * (R - 1)) * T,
+                                                     rb.live + (size_t)dslot * T, nlike, lfin);
+                    if (p.clustering && active) {  // the babies carry their seed's label until the next update
+                        for (int e = sub; e < R - 1; e += G) rb.phl[cur_pool_now][nph_base + (long long)k * (R - 1) + e] = plab;
+                        if (sub == 0) rb.lab[dslot] = plab;
+                    }
+                    if (active && sub == 0 && !(lfin > Lstar)) ++nfail;
+                }
+                // the per-group counts (on the groups' first lanes) -> lane 0
+                nlike = (unsigned long long)warp_sum_int((int)nlike);
+                nfail = (unsigned long long)warp_sum_int((int)nfail);
+            }
+        } else if (p.paired) {
             // Warps w < W/2 run chains, warp w + W/2 is the helper of warp w: it prepares (directions, deck,
             // uniforms, whitening) the pair's next chain into the other of the pair's two scratch buffers
             // while the chain warp is slicing, so preparation leaves the critical path.
@@ -892,7 +948,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                 if (ctimer && j == 0) st->dbg[20] += ts_b - ts_a;   // seed choice (Philox + order look-up)
                 if (helper) {
                     long long th0 = clock64();
-                    if (prep_uid != uid) { prep_chain(D, R, LD, rb.seed, uid, b, &p.cp); prep_white = false; }
+                    if (prep_uid != uid) { prep_chain<G * DPL>(D, R, LD, rb.seed, uid, b, &p.cp); prep_white = false; }
                     if (clustered) whiten_chain<(G * DPL + 7) / 8>(D, R, LD, rb.cchol + (size_t)plab * D * D, b);
                     else if (!prep_white) whiten_chain<(G * DPL + 7) / 8>(D, R, LD, s_chol, b);
                     prep_uid = ~0ull;
@@ -947,7 +1003,7 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                 double* last = sharded ? xin_mine + (size_t)k * T : rb.live + (size_t)dslot * T;
                 long long tc0 = clock64();
                 if (prep_uid != uid) {
-                    prep_chain(D, R, LD, rb.seed, uid, cs, &p.cp);
+                    prep_chain<G * DPL>(D, R, LD, rb.seed, uid, cs, &p.cp);
                     prep_white = false;
                 }
                 long long tc1 = clock64();
@@ -986,33 +1042,33 @@ __global__ void __launch_bounds__(256, 1) pc_run_kernel(const __grid_constant__ 
                                           : cs;
         if (do_update) {
             long long tu0 = clock64();
-            warp_wait(&st->wbar, wtarget);
+            warp_wait(&st->wbar, wtarget, p.backoff);
             long long tu1 = clock64();
             if (sharded) {  // the covariance is over the live points including this generation's babies
                 if (cta == 0) { __syncthreads(); shard_scatter(p, rb, st); }
                 scatter_due = false;
-                group_sync(&st->bar, NG);
+                group_sync(&st->bar, NG, p.backoff);
             }
             long long ua0 = clock64();
             phase_UA(p, rb, st, cta, NG);
             long long ua1 = clock64();
-            group_sync(&st->bar, NG);
+            group_sync(&st->bar, NG, p.backoff);
             long long ua2 = clock64();
             phase_UB(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt);
             long long ua3 = clock64();
             if (timer) { st->dbg[2] += ua1 - ua0; st->dbg[3] += ua2 - ua1; st->dbg[4] += ua3 - ua2; st->dbg[5] -= ua3; }
             if (cta == 0 && tid == 0) st->update_pending = 1;
-            group_sync(&st->bar, NG);
+            group_sync(&st->bar, NG, p.backoff);
             if (timer) { st->cyc_wait += tu1 - tu0; st->cyc_U += clock64() - tu1; st->dbg[5] += clock64(); }
             have_wtarget = false;
             if (will_chain) {  // the Cholesky factor is about to change: whiten after the barrier
                 prep_uid = (unsigned long long)(nchains_base + K + knext);
-                prep_chain(D, R, LD, rb.seed, prep_uid, csn, &p.cp);
+                prep_chain<G * DPL>(D, R, LD, rb.seed, prep_uid, csn, &p.cp);
                 prep_white = false;
             }
         } else if (will_chain) {
             prep_uid = (unsigned long long)(nchains_base + K + knext);
-            prep_chain(D, R, LD, rb.seed, prep_uid, csn, &p.cp);
+            prep_chain<G * DPL>(D, R, LD, rb.seed, prep_uid, csn, &p.cp);
             prep_white = false;
             if (!p.clustering) {  // with clusters the factor depends on the chain's seed, which the next phase S decides
                 whiten_chain<(G * DPL + 7) / 8>(D, R, LD, s_chol, csn);
@@ -1052,10 +1108,61 @@ __global__ void __launch_bounds__(256, 1) pc_slice_chains_kernel(const __grid_co
         for (int j = 0; j < DPL; ++j) x[j] = M.valid(j) ? seed_points[(size_t)c * T + M.dim(j)] : 0.0;
         unsigned long long nl = 0;
         double* out = babies + (size_t)c * R * T;
-        prep_chain(D, R, LD, seed, uid[c], cs, &p.cp);
+        prep_chain<G * DPL>(D, R, LD, seed, uid[c], cs, &p.cp);
         whiten_chain<(G * DPL + 7) / 8>(D, R, LD, s_chol, cs);
         slice_chain<G, DPL, KIND>(p.cp, M, seed, uid[c], x, logL[c], cs, out, out + (size_t)(R - 1) * T, nl);
         if (lane == 0) nlike_out[c] = (long long)nl;
+    }
+}
+
+// The same probe through the dense chain phase (pc_dense.cuh): a warp takes 32/G chains at a time, one per point group.
+// records: nchains x R x SLB doubles of global scratch for the slice records.
+template <int G, int DPL, int KIND>
+__global__ void __launch_bounds__(256, 2) pc_slice_chains_dense_kernel(const __grid_constant__ KParams p, int nchains,
+                                                                       const double* seed_points, const double* chol,
+                                                                       const double* logL, const unsigned long long* uid,
+                                                                       unsigned seed, double* babies, long long* nlike_out,
+                                                                       double* records) {
+    if constexpr (KIND != LIKE_CORR) {
+        extern __shared__ __align__(16) unsigned char smem[];
+        constexpr int NPT = 32 / G, GD = G * DPL, SLB = dense_slb(GD);
+        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
+        const int D = p.cp.D, T = p.cp.T, R = p.cp.R, LD = p.cp.LD;
+        double* s_chol = (double*)smem;
+        double* s_like = (double*)(smem + p.off_like);
+        unsigned char* s_warp = smem + p.off_warp + (size_t)warp * p.warp_bytes;
+        const int nlp = (p.cp.like_kind == LIKE_GAUSSIAN) ? 2 * D : 0;
+        for (int e = tid; e < nlp; e += blockDim.x) s_like[e] = p.like_params[e];
+        for (int e = tid; e < D * D; e += blockDim.x) s_chol[e] = chol[e];
+        __syncthreads();
+        const int gw = blockIdx.x * W + warp, grp = lane / G, sub = lane % G;
+        const ChainScratch cs = chain_scratch(s_warp, D, R, LD, true, p.cp.like_kind, NPT, nullptr, SLB);
+        Model<G, DPL, KIND> M;
+        M.init(p.cp, s_like, p.prior_params, cs.dvec);
+        for (int base = gw * NPT; base < nchains; base += gridDim.x * W * NPT) {
+            for (int g = 0; g < NPT && base + g < nchains; ++g) {
+                prep_chain<GD>(D, R, LD, seed, uid[base + g], cs, &p.cp);
+                whiten_chain<(G * DPL + 7) / 8>(D, R, LD, s_chol, cs);
+                dense_store<GD>(R, LD, seed, uid[base + g], cs, records + (size_t)(base + g) * R * SLB);
+            }
+            __syncwarp();
+            const int c = base + grp, cc = min(c, nchains - 1);
+            const bool active = c < nchains;
+            double x[DPL];
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) x[j] = M.valid(j) ? seed_points[(size_t)cc * T + M.dim(j)] : 0.0;
+            unsigned long long nl = 0;
+            double lfin = 0.0;
+            double* out = babies + (size_t)cc * R * T;
+            slice_chains_dense<G, DPL, KIND>(p.cp, M, seed, uid[cc], active, x, logL[cc], records + (size_t)cc * R * SLB,
+                                             cs.stage + (size_t)grp * 2 * SLB, out, out + (size_t)(R - 1) * T, nl, lfin);
+            if (active) {   // the chain probe returns every baby's derived parameters, as SliceSampling does
+                if (p.cp.P > 0)
+                    for (int i = sub; i < R - 1; i += G) M.finish_derived(out + (size_t)i * T, false);
+                if (sub == 0) nlike_out[c] = (long long)nl;
+            }
+            __syncwarp();
+        }
     }
 }
 

@@ -1,9 +1,11 @@
-// Instantiates the run kernel and the templated probes for G=8 lanes per point, DPL=8 dimensions per lane, likelihood kind 0.
+// Instantiates the run kernels and the templated probes for G=8 lanes per point, DPL=8 dimensions per lane, likelihood kind 0.
 #include "pc_run_kernel.cuh"
 #include "pc_shapes.h"
 namespace pc {
 ShapeFns shape_fns_8_8_0() {
-    return ShapeFns{(const void*)pc_run_kernel<8, 8, 0>, (const void*)pc_slice_chains_kernel<8, 8, 0>,
-                    (const void*)pc_calculate_points_kernel<8, 8, 0>, 8, 8, 0};
+    return ShapeFns{(const void*)pc_run_kernel<8, 8, 0, 0>, (const void*)pc_slice_chains_kernel<8, 8, 0>,
+                    (const void*)pc_calculate_points_kernel<8, 8, 0>,
+                    (const void*)pc_run_kernel<8, 8, 0, 1>, (const void*)pc_slice_chains_dense_kernel<8, 8, 0>,
+                    8, 8, 0};
 }
 }  // namespace pc

@@ -5,9 +5,11 @@
 #pragma once
 namespace pc {
 struct ShapeFns {
-    const void* run;     // pc_run_kernel<G, DPL, KIND>
+    const void* run;     // pc_run_kernel<G, DPL, KIND, 0>
     const void* slice;   // pc_slice_chains_kernel<G, DPL, KIND>
     const void* calc;    // pc_calculate_points_kernel<G, DPL, KIND>
+    const void* run_dense;    // pc_run_kernel<G, DPL, KIND, 1>: the dense chain phase (pc_dense.cuh); null for KIND 2
+    const void* slice_dense;  // pc_slice_chains_dense_kernel<G, DPL, KIND>; null for KIND 2
     int G, DPL, KIND;
 };
 ShapeFns shape_fns_4_2_0();

@@ -17,8 +17,17 @@ from pathlib import Path
 
 import numpy as np
 
+import os
+
 from .. import _capi
 from . import builtin as _builtin
+
+try:  # the CPython extension built by polychordlite_b200/_build.py (reference: pypolychord/_pypolychord.cpp)
+    from . import _pypolychord as _shim
+    if os.environ.get("PC_PY_BINDING") == "ctypes":
+        _shim = None
+except ImportError:  # not built: the same C ABI bound with ctypes
+    _shim = None
 from .output import NestedSamplesLite, PolyChordOutput, make_paramnames_file
 from .priors import UniformPrior
 
@@ -79,6 +88,116 @@ def run(loglikelihood, nDims, **kwargs):
 
     L = _capi.lib()
     nDerived = int(kwargs['nDerived'])
+    prior = kwargs['prior']
+    user_dumper = kwargs['dumper']
+    last = {}
+
+    def on_final_dump(dead, logweights, logZ, logZerr):
+        last.update(dead=dead.copy(), logweights=logweights.copy(), logZ=logZ, logZerr=logZerr)
+
+    # the reference convention for fatal configuration errors is a banner and exit(1) (abort.F90:19-29);
+    # under Python report them as exceptions instead
+    old_err = _capi.get_option("errors_return")
+    _capi.set_option("errors_return", 1)
+    try:
+        if kwargs.get('cube_samples') is not None:
+            # polychord.py:576-579: the run starts from the caller's live points; any number of them (the dynamic-nlive
+            # schedule absorbs the difference from nlive, as in the reference).  The points win over an existing resume file.
+            cs = np.asarray(kwargs['cube_samples'], dtype=np.float64)
+            if cs.ndim != 2 or cs.shape[1] != nDims or cs.shape[0] < 2:
+                raise ValueError("cube_samples must have shape (npoints, nDims)")
+            _capi.set_initial_live(cs)
+        if _shim is not None:
+            _run_through_shim(loglikelihood, prior, user_dumper, on_final_dump, kwargs, nDims, nDerived)
+        else:
+            _run_through_ctypes(L, loglikelihood, prior, user_dumper, on_final_dump, kwargs, nDims, nDerived)
+    finally:
+        _capi.set_option("errors_return", old_err)
+    info = _capi.last_run_info()
+    if info.status != 0 or not last:
+        raise RuntimeError(f"polychord_c_interface failed (status {info.status}); see the message on stderr")
+    lite = NestedSamplesLite(last['dead'], last['logweights'], last['logZ'], last['logZerr'], nDims, nDerived,
+                             info=info.as_dict())
+    if kwargs.get('_legacy_output'):
+        return lite
+    try:  # polychord.py:639-646: the chains as anesthetic reads them from the files the engine wrote
+        import anesthetic
+        if kwargs['write_dead']:
+            return anesthetic.read_chains(str(Path(kwargs['base_dir']) / kwargs['file_root']))
+    except ImportError:
+        pass
+    return lite
+
+
+class _CAddress:
+    """A callable with a device form, as the `_pypolychord` extension recognises it: `_pc_c_callback(nDims)` returns the
+    address of a C callback the engine knows (pc_register_device_likelihood / pc_register_device_prior)."""
+
+    def __init__(self, address_of):
+        self._address_of = address_of
+
+    def _pc_c_callback(self, nDims):
+        return self._address_of(nDims)
+
+    def __call__(self, *a):  # never called: the engine runs the device form
+        raise RuntimeError("device-resident callback called on the host")
+
+
+def _device_prior(prior, nDims, L):
+    """The C address of a prior with a device form (unit cube, UniformPrior), or None."""
+    if prior is default_prior:
+        return C.cast(L.pc_unit_prior, C.c_void_p).value
+    if isinstance(prior, UniformPrior) and getattr(prior, 'device_params', None) is not None:
+        fn = C.cast(L.pc_uniform_prior, _capi.PRIOR_CB)
+        pp = np.ascontiguousarray(prior.device_params(nDims), dtype=np.float64)
+        if L.pc_register_device_prior(fn, 0, pp.ctypes.data_as(C.POINTER(C.c_double)), pp.size) != 0:
+            raise RuntimeError("pc_register_device_prior failed")
+        return C.cast(fn, C.c_void_p).value
+    return None
+
+
+def _run_through_shim(loglikelihood, prior, user_dumper, on_final_dump, kwargs, nDims, nDerived):
+    """polychord.py:581-634: wrap the callables and hand the 34 positional arguments to `_pypolychord.run`.  A Python
+    exception raised inside a callback unwinds through the engine and is re-raised by the extension."""
+    L = _capi.lib()
+    if isinstance(loglikelihood, _builtin._DeviceLikelihood):
+        like = _CAddress(lambda nd: C.cast(loglikelihood.register(nd), C.c_void_p).value)
+    else:
+        def like(theta, phi):  # polychord.py:581-587 wrap_loglikelihood
+            res = loglikelihood(theta)
+            if isinstance(res, tuple):
+                logL, derived = res
+                if phi.size:
+                    phi[:] = derived
+            else:
+                logL = res
+            return float(logL)
+    addr = _device_prior(prior, nDims, L)
+    if addr is not None:
+        prior_cb = _CAddress(lambda nd: addr)
+    else:
+        def prior_cb(cube, theta):  # polychord.py:589-590 wrap_prior
+            theta[:] = prior(cube)
+
+    def dumper(live, dead, logweights, logZ, logZerr):
+        if live.shape[0] == 0:  # the final call: every point is dead (nested_sampling.F90:392)
+            on_final_dump(dead, logweights, logZ, logZerr)
+        user_dumper(live, dead, logweights, logZ, logZerr)
+
+    _shim.run(like, prior_cb, dumper, nDims, nDerived, int(kwargs['nlive']), int(kwargs['num_repeats']),
+              int(kwargs['nprior']), int(kwargs['nfail']), bool(kwargs['do_clustering']), int(kwargs['feedback']),
+              float(kwargs['precision_criterion']), float(kwargs['logzero']), int(kwargs['max_ndead']),
+              float(kwargs['boost_posterior']), bool(kwargs['posteriors']), bool(kwargs['equals']),
+              bool(kwargs['cluster_posteriors']), bool(kwargs['write_resume']), bool(kwargs['write_paramnames']),
+              bool(kwargs['read_resume']), bool(kwargs['write_stats']), bool(kwargs['write_live']),
+              bool(kwargs['write_dead']), bool(kwargs['write_prior']), bool(kwargs['maximise']),
+              float(kwargs['compression_factor']), bool(kwargs['synchronous']), str(kwargs['base_dir']),
+              str(kwargs['file_root']), [float(f) for f in kwargs['grade_frac']], kwargs['grade_dims'], kwargs['nlives'],
+              int(kwargs['seed']))
+
+
+def _run_through_ctypes(L, loglikelihood, prior, user_dumper, on_final_dump, kwargs, nDims, nDerived):
+    """The same call bound with ctypes (used when the `_pypolychord` extension has not been built)."""
     # ---- loglikelihood / prior -> device forms --------------------------------------------------
     pending = []   # exception raised inside a callback: ctypes cannot unwind through the C frames, so it is kept,
                    # the engine is asked to stop (pc_request_abort) and the exception is re-raised after the call
@@ -114,14 +233,9 @@ def run(loglikelihood, nDims, **kwargs):
             return float(logL)
         like_fn = _capi.LL_CB(_guard(_ll, float(kwargs['logzero'])))
         keep.append(like_fn)
-    prior = kwargs['prior']
-    if prior is default_prior:
-        prior_fn = C.cast(L.pc_unit_prior, _capi.PRIOR_CB)
-    elif isinstance(prior, UniformPrior) and getattr(prior, 'device_params', None) is not None:
-        prior_fn = C.cast(L.pc_uniform_prior, _capi.PRIOR_CB)
-        pp = np.ascontiguousarray(prior.device_params(nDims), dtype=np.float64)
-        if L.pc_register_device_prior(prior_fn, 0, pp.ctypes.data_as(C.POINTER(C.c_double)), pp.size) != 0:
-            raise RuntimeError("pc_register_device_prior failed")
+    addr = _device_prior(prior, nDims, L)
+    if addr is not None:
+        prior_fn = C.cast(addr, _capi.PRIOR_CB)
     else:
         # polychord.py:589-590 wrap_prior: theta[:] = prior(cube)
         def _prior(cube_p, theta_p, nd):
@@ -131,14 +245,10 @@ def run(loglikelihood, nDims, **kwargs):
         prior_fn = _capi.PRIOR_CB(_guard(_prior, None))
         keep.append(prior_fn)
 
-    # ---- dumper: the user's callable plus the in-memory result ------------------------------------
-    last = {}
-    user_dumper = kwargs['dumper']
-
     def _dumper(ndead, nlive, npars, live, dead, logweights, logZ, logZerr):
         lv, dd, lw = _view(live, (nlive, npars)), _view(dead, (ndead, npars)), _view(logweights, (ndead,))
         if nlive == 0:  # the final call: every point is dead (nested_sampling.F90:392)
-            last.update(dead=dd.copy(), logweights=lw.copy(), logZ=logZ, logZerr=logZerr)
+            on_final_dump(dd, lw, logZ, logZerr)
         user_dumper(lv, dd, lw, logZ, logZerr)
 
     dcb = _capi.DUMPER_CB(_guard(_dumper, None))
@@ -151,40 +261,10 @@ def run(loglikelihood, nDims, **kwargs):
     comm = C.c_int(0)
     L.polychord_c_interface.restype = None
     L.polychord_c_interface.argtypes = _ARGTYPES
-    # the reference convention for fatal configuration errors is a banner and exit(1) (abort.F90:19-29);
-    # under Python report them as exceptions instead
-    old_err = _capi.get_option("errors_return")
-    _capi.set_option("errors_return", 1)
-    if kwargs.get('cube_samples') is not None:
-        # polychord.py:576-579: the run starts from the caller's live points.  The reference writes them into a resume
-        # file and lets the dynamic-nlive mechanism absorb a count other than nlive; this engine takes exactly nlive.
-        cs = np.asarray(kwargs['cube_samples'], dtype=np.float64)
-        if cs.ndim != 2 or cs.shape != (int(kwargs['nlive']), nDims):
-            _capi.set_option("errors_return", old_err)
-            raise ValueError("cube_samples must have shape (nlive, nDims): the B200 engine has no dynamic nlive to absorb "
-                             "a different number of starting points")
-        _capi.set_initial_live(cs)
-    try:
-        _call(L, like_fn, prior_fn, dcb, kwargs, nDims, nDerived, ngrade, grade_frac, grade_dims, nl, loglikes,
-              nlives, comm)
-    finally:
-        _capi.set_option("errors_return", old_err)
+    _call(L, like_fn, prior_fn, dcb, kwargs, nDims, nDerived, ngrade, grade_frac, grade_dims, nl, loglikes,
+          nlives, comm)
     if pending:
         raise pending[0]
-    info = _capi.last_run_info()
-    if info.status != 0 or not last:
-        raise RuntimeError(f"polychord_c_interface failed (status {info.status}); see the message on stderr")
-    lite = NestedSamplesLite(last['dead'], last['logweights'], last['logZ'], last['logZerr'], nDims, nDerived,
-                             info=info.as_dict())
-    if kwargs.get('_legacy_output'):
-        return lite
-    try:  # polychord.py:639-646: the chains as anesthetic reads them from the files the engine wrote
-        import anesthetic
-        if kwargs['write_dead']:
-            return anesthetic.read_chains(str(Path(kwargs['base_dir']) / kwargs['file_root']))
-    except ImportError:
-        pass
-    return lite
 
 
 def _call(L, like_fn, prior_fn, dcb, kwargs, nDims, nDerived, ngrade, grade_frac, grade_dims, nl, loglikes, nlives,

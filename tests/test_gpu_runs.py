@@ -104,8 +104,14 @@ def test_ensemble_logZ_gaussian20_nlive1000_matches_analytic(gpu):
 def test_ensemble_member_equals_single_run(gpu):
     """A run inside an ensemble launch is bit-identical to the same seed run alone."""
     s = gpu.make_settings(8, 1, nlive=100, num_repeats=16, seed=5)
-    single, _ = gpu.run(s)
-    infos = gpu.run_ensemble(s, [3, 5, 9])
+    gpu.set_option("batch_K", 25)   # the automatic batch size differs between a run alone and an ensemble
+    gpu.set_option("dense", -1)     # same chain phase on both sides (tests/test_gpu_dense.py covers the dense one)
+    try:
+        single, _ = gpu.run(s)
+        infos = gpu.run_ensemble(s, [3, 5, 9])
+    finally:
+        gpu.set_option("batch_K", 0)
+        gpu.set_option("dense", 0)
     assert infos[1].logZ == single.logZ and infos[1].nlike == single.nlike and infos[1].ndead == single.ndead
     assert infos[0].logZ != infos[1].logZ
 
@@ -183,3 +189,73 @@ def test_reference_cpp_facade_drives_the_engine(gpu):
     logZ, logZerr, ndead, nlive_last, ndumps = r.stdout.split()[-5:]
     assert abs(float(logZ) - ANALYTIC["gaussian20_unit_cube"]["logZ"]) < 5 * float(logZerr)
     assert int(ndead) > 5000 and int(nlive_last) == 0 and int(ndumps) > 5
+
+
+def test_reference_cc_driver_linked_with_libchord_alone_runs(gpu, tmp_path):
+    """oracle/_ref/polychord_CC: the reference's src/drivers/polychord_CC.cpp + likelihoods/CC/CC_likelihood.cpp, compiled
+    unchanged and linked with -lchord only (oracle/Makefile) -- Settings, run_polychord and the engine all come from this
+    repository's library.  Its likelihood is a host callback, so this is the lock-step path end to end."""
+    import subprocess
+    from pathlib import Path
+    exe = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "polychord_CC"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/polychord_CC not built (needs the reference tree at build time)")
+    (tmp_path / "chains" / "clusters").mkdir(parents=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120, cwd=tmp_path)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "log(Z)" in r.stdout
+    live = np.loadtxt(tmp_path / "chains" / "test_phys_live.txt")   # settings.write_live = true (polychord_CC.cpp:24)
+    assert live.shape[1] == 3 + 1 + 1
+
+
+def test_reference_cpython_shim_linked_with_libchord_alone_runs(gpu, tmp_path):
+    """oracle/_ref/refshim/_pypolychord.so: the reference's pypolychord/_pypolychord.cpp compiled unchanged against our
+    library; a Python likelihood driven through it (34 positional arguments, polychord.py:600-634)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    d = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "refshim"
+    if not (d / "_pypolychord.so").exists():
+        pytest.skip("oracle/_ref/refshim not built (needs the reference tree at build time)")
+    (tmp_path / "chains").mkdir()
+    code = f"""
+import sys, numpy as np
+sys.path.insert(0, {str(d)!r})
+import _pypolychord
+out = {{}}
+def ll(theta, phi):
+    return float(-0.5 * np.sum((theta - 0.5) ** 2) / 0.01 - 4 * np.log(0.1 * np.sqrt(2 * np.pi)))
+def prior(cube, theta):
+    theta[:] = cube
+def dumper(live, dead, logweights, logZ, logZerr):
+    out.update(logZ=logZ, logZerr=logZerr, ndead=dead.shape[0], nlive=live.shape[0])
+_pypolychord.run(ll, prior, dumper, 4, 0, 100, 8, -1, -1, False, 0, 1e-3, -1e30, -1, 0.0, False, False, False, False, False,
+                 False, False, False, False, False, False, float(np.exp(-1)), True, {str(tmp_path / 'chains')!r}, "t", [1.0], [4], {{}}, 3)
+print(out["logZ"], out["logZerr"], out["ndead"], out["nlive"])
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    logZ, logZerr, ndead, nlive = r.stdout.split()[-4:]
+    assert abs(float(logZ)) < 5 * float(logZerr) + 0.05 and int(nlive) == 0 and int(ndead) > 500
+
+
+def test_own_cpython_shim_propagates_python_exceptions(gpu, tmp_path):
+    """polychordlite_b200/pypolychord/_pypolychord (csrc/pypolychord_module.cpp): an exception raised inside the Python
+    likelihood unwinds through the engine's frames and comes back as that exception (_pypolychord.cpp:219-224)."""
+    from polychordlite_b200 import pypolychord
+
+    calls = {"n": 0}
+
+    def ll(theta):
+        calls["n"] += 1
+        if calls["n"] > 500:
+            raise KeyError("boom")
+        return float(-0.5 * np.sum((theta - 0.5) ** 2) / 0.01)
+
+    with pytest.raises(KeyError, match="boom"):
+        pypolychord.run(ll, 3, nlive=50, num_repeats=6, base_dir=str(tmp_path), file_root="x", feedback=0, seed=1,
+                        read_resume=False, write_resume=False)
+    # the engine is usable afterwards
+    out = pypolychord.run(lambda t: float(-0.5 * np.sum((t - 0.5) ** 2) / 0.01), 3, nlive=50, num_repeats=6,
+                          base_dir=str(tmp_path), file_root="y", feedback=0, seed=1, read_resume=False, write_resume=False)
+    assert out is not None
