@@ -101,7 +101,10 @@ void pc_unit_prior(double* cube, double* theta, int nDims);    /* theta = cube (
 void pc_uniform_prior(double* cube, double* theta, int nDims); /* theta = lo + (hi-lo)*cube */
 
 /* Engine options (name/value); unknown names return -1.
- *   "batch_fraction"  K = max(1, round(nlive*value)) lowest points die per generation (default 0.25)
+ *   "batch_fraction"  K = max(1, round(nlive*value)) lowest points die per generation; 0 (default) = automatic: 1/2 for a
+ *                     run alone on the device (its wall time is the number of generations), 1/4 for the runs of an ensemble
+ *   "dense"           the dense chain phase (one chain per point group, csrc/pc_dense.cuh): 0 = ensembles only (default),
+ *                     1 = always, -1 = never
  *   "batch_K"         absolute K (overrides batch_fraction when > 0)
  *   "device"          CUDA device ordinal
  *   "warps_per_cta"   chain warps per CTA (default: chosen from the shared-memory budget)
@@ -131,6 +134,12 @@ void pc_request_abort(void);
  * grade_repeats[g] slice steps per chain, drawn in the sub-space of the dimensions of grades >= g
  * (chordal_sampling.f90:94-145).  The dims must sum to nDims, the repeats to num_repeats.  nGrade = 0 clears. */
 int pc_set_grades(int nGrade, const int* grade_dims, const int* grade_repeats);
+/* Dynamic nlive for the following pc_run() calls (polychord_c_interface takes it from its own loglikes / nlives
+ * arguments): above the contour loglikes[i] the run keeps nlives[i] live points (settings%loglikes / settings%nlives,
+ * run_time_info.f90:766-777); elsewhere settings.nlive.  In the batched schedule a generation that kills K of its n live
+ * points births target - (n - K) chains (none when the survivors already exceed the target, at most 2 batch_K).  At most
+ * 16 entries; m = 0 clears. */
+int pc_set_nlives(const double* loglikes, const int* nlives, int m);
 /* Resume file for the following pc_run() calls (polychord_c_interface uses <base_dir>/<file_root>.resume with its
  * write_resume / read_resume flags; replaces read_write.F90:219-476).  `path` must end in ".resume".  write: the run's
  * state is saved between generations at the update cadence (at most once a second) and after the final kill-off;

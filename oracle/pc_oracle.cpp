@@ -1209,84 +1209,129 @@ struct Run {
         return nlive;
     }
 
+    // One generation of the batched schedule: the K lowest of the n live points die (evidence with counts n, n-1, ...
+    // as the final kill-off nested_sampling.F90:381-384 applies it), B chains are seeded from the n-K survivors at the
+    // contour of the K-th lowest.  Births k < min(B, K) take the vacated slots in death order, further births are
+    // appended; a FAILED birth (last baby not above the contour: stale or non-deterministic likelihood) does not become
+    // a live point -- it goes to the dead list with log-weight logzero, as replace_point does (run_time_info.f90:
+    // 781-785) -- and counts towards nfail (nested_sampling.F90:315-319).  Slots left empty (vacated and not refilled,
+    // or reserved for a failed birth) are closed from the top down by moving the last record in.
+    // Returns the number of failed births.
+    int failures_in_a_row = 0;
+    int batched_generation(int K, int B, std::vector<double>& babies) {
+        Cluster& c = cl[0];
+        const int n = c.nlive;
+        std::vector<int> order(n);
+        // rank by (logL, slot)
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            return c.live[(size_t)a * T + l0] < c.live[(size_t)b * T + l0];
+        });
+        const double Lstar = c.live[(size_t)order[K - 1] * T + l0];
+        // K sequential deaths with n, n-1, ... live points (cf. nested_sampling.F90:381-384)
+        const int nlive_save = c.nlive;
+        for (int k = 0; k < K; ++k) {
+            const double* r = &c.live[(size_t)order[k] * T];
+            c.logLp = r[l0];
+            double logw = update_evidence(0);
+            push_dead(r, logw);
+            c.stack_l.push_back(r[l0]);
+            c.stack_i.push_back(ndead - 1);
+            c.nlive--;
+        }
+        c.nlive = nlive_save;
+        const int m = n - K;
+        std::vector<double> newpts((size_t)std::max(B, 1) * T);
+        std::vector<int> newlab(std::max(B, 1), 0);
+        std::vector<char> ok(std::max(B, 1), 0);
+        const bool clustered = S.do_clustering && ncl_b > 1;
+        int nfailed = 0;
+        for (int k = 0; k < B; ++k) {
+            uint64_t uid = (uint64_t)nchains + k;
+            double u = rng.uniform(TAG_SEED, uid, 0, 0);
+            int choice = (int)std::ceil(u * m);
+            if (choice < 1) choice = 1;
+            const int sslot = order[K + choice - 1];
+            const double* seed = &c.live[(size_t)sslot * T];
+            const int plab = clustered ? lab[sslot] : 0;
+            newlab[k] = plab;
+            slice_sampling(Lstar, seed, clustered ? chols[plab].data() : c.cholesky.data(), uid, babies, nlike);
+            for (int i = 0; i < R; ++i) babies[(size_t)i * T + b0] = Lstar;
+            for (int i = 0; i < R - 1; ++i) {
+                const double* pt = babies.data() + (size_t)i * T;
+                if (pt[l0] > Lstar) {
+                    c.phantom.insert(c.phantom.end(), pt, pt + T);
+                    c.nphantom++;
+                    if (S.do_clustering) phlab.push_back(plab);
+                }
+            }
+            const double* last = babies.data() + (size_t)(R - 1) * T;
+            ok[k] = last[l0] > Lstar;
+            std::copy(last, last + T, newpts.begin() + (size_t)k * T);
+        }
+        // failed births, in chain order
+        for (int k = 0; k < B; ++k) {
+            if (ok[k]) { failures_in_a_row = 0; continue; }
+            ++nfailed; ++nfail_total; ++failures_in_a_row;
+            push_dead(&newpts[(size_t)k * T], S.logzero);
+        }
+        // placement
+        const bool labelled = S.do_clustering && (int)lab.size() == n;
+        std::vector<int> holes;
+        for (int k = 0; k < K; ++k) {
+            if (k < B && ok[k]) {
+                std::copy(newpts.begin() + (size_t)k * T, newpts.begin() + (size_t)(k + 1) * T, c.live.begin() + (size_t)order[k] * T);
+                if (labelled) lab[order[k]] = newlab[k];
+            } else holes.push_back(order[k]);
+        }
+        for (int k = K; k < B; ++k) {   // the live count grows: further births are appended
+            if (!ok[k]) continue;
+            c.live.insert(c.live.end(), newpts.begin() + (size_t)k * T, newpts.begin() + (size_t)(k + 1) * T);
+            if (labelled) lab.push_back(newlab[k]);
+            c.nlive++;
+        }
+        std::sort(holes.begin(), holes.end(), std::greater<int>());
+        for (int sl : holes) {          // close the empty slots, highest first
+            const int lastp = c.nlive - 1;
+            if (sl != lastp) {
+                std::copy(c.live.begin() + (size_t)lastp * T, c.live.begin() + (size_t)(lastp + 1) * T, c.live.begin() + (size_t)sl * T);
+                if (labelled) lab[sl] = lab[lastp];
+            }
+            c.nlive--;
+        }
+        c.live.resize((size_t)c.nlive * T);
+        if (labelled) lab.resize(c.nlive);
+        nchains += B;
+        ngen++;
+        find_min();
+        return nfailed;
+    }
+
     void run_batched() {
         Cluster& c = cl[0];
-        std::vector<int> order;
-        std::vector<double> babies, rec(T);
-        const bool dyn = !g_dyn_loglikes.empty() && !S.do_clustering;
-        while (more_samples_needed()) {
+        std::vector<double> babies;
+        const int nfail = S.nfail <= 0 ? S.nlive : S.nfail;
+        // nprior > nlive: the trim of nested_sampling.F90:201-203 -- the excess points die one after the other, no
+        // births -- is a generation of its own
+        if (c.nlive > S.nlive) {
+            batched_generation(c.nlive - S.nlive, 0, babies);
+            ngen--;   // not a sampling generation
+        }
+        while (more_samples_needed() && failures_in_a_row <= nfail) {
             const int n = c.nlive;
-            order.resize(n);
             int K = std::min(S.batch_K, n - 1);
             if (S.max_ndead > 0) K = (int)std::min<long long>(K, S.max_ndead - ndead);
             if (K < 1) break;
-            // rank by (logL, slot)
+            // the live count moves towards its target above the contour (dynamic nlive, run_time_info.f90:766-777;
+            // constant: settings%nlive), at most 2 batch_K births a generation
+            std::vector<int> order(n);
             std::iota(order.begin(), order.end(), 0);
             std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
                 return c.live[(size_t)a * T + l0] < c.live[(size_t)b * T + l0];
             });
-            double Lstar = c.live[(size_t)order[K - 1] * T + l0];
-            // K sequential deaths with n, n-1, ... live points (cf. nested_sampling.F90:381-384)
-            int nlive_save = c.nlive;
-            for (int k = 0; k < K; ++k) {
-                const double* r = &c.live[(size_t)order[k] * T];
-                c.logLp = r[l0];
-                double logw = update_evidence(0);
-                push_dead(r, logw);
-                c.stack_l.push_back(r[l0]);
-                c.stack_i.push_back(ndead - 1);
-                c.nlive--;
-            }
-            c.nlive = nlive_save;
-            // B chains (B = K unless the live count is moving) seeded from the n-K survivors, all at contour Lstar
-            int m = n - K;
-            const int B = dyn ? std::max(0, std::min(std::max(target_nlive(Lstar), 1) - m, 2 * S.batch_K)) : K;
-            std::vector<double> newpts((size_t)std::max(B, 1) * T);
-            std::vector<int> newlab(std::max(B, 1), 0);
-            const bool clustered = S.do_clustering && ncl_b > 1;
-            for (int k = 0; k < B; ++k) {
-                uint64_t uid = (uint64_t)nchains + k;
-                double u = rng.uniform(TAG_SEED, uid, 0, 0);
-                int choice = (int)std::ceil(u * m);
-                if (choice < 1) choice = 1;
-                const int sslot = order[K + choice - 1];
-                const double* seed = &c.live[(size_t)sslot * T];
-                const int plab = clustered ? lab[sslot] : 0;
-                newlab[k] = plab;
-                slice_sampling(Lstar, seed, clustered ? chols[plab].data() : c.cholesky.data(), uid, babies, nlike);
-                for (int i = 0; i < R; ++i) babies[(size_t)i * T + b0] = Lstar;
-                for (int i = 0; i < R - 1; ++i) {
-                    const double* pt = babies.data() + (size_t)i * T;
-                    if (pt[l0] > Lstar) {
-                        c.phantom.insert(c.phantom.end(), pt, pt + T);
-                        c.nphantom++;
-                        if (S.do_clustering) phlab.push_back(plab);
-                    }
-                }
-                const double* last = babies.data() + (size_t)(R - 1) * T;
-                if (!(last[l0] > Lstar)) nfail_total++;
-                std::copy(last, last + T, newpts.begin() + (size_t)k * T);
-            }
-            for (int k = 0; k < std::min(B, K); ++k)
-                std::copy(newpts.begin() + (size_t)k * T, newpts.begin() + (size_t)(k + 1) * T, c.live.begin() + (size_t)order[k] * T);
-            if (clustered) for (int k = 0; k < K; ++k) lab[order[k]] = newlab[k];
-            if (B > K) {          // the live count grows: further births are appended
-                c.live.insert(c.live.end(), newpts.begin() + (size_t)K * T, newpts.begin() + (size_t)B * T);
-                c.nlive += B - K;
-            } else if (B < K) {   // it shrinks: close the vacated slots left over, highest slot first
-                std::vector<int> holes(order.begin() + B, order.begin() + K);
-                std::sort(holes.begin(), holes.end(), std::greater<int>());
-                for (int sl : holes) {
-                    const int lastp = c.nlive - 1;
-                    if (sl != lastp)
-                        std::copy(c.live.begin() + (size_t)lastp * T, c.live.begin() + (size_t)(lastp + 1) * T, c.live.begin() + (size_t)sl * T);
-                    c.nlive--;
-                }
-                c.live.resize((size_t)c.nlive * T);
-            }
-            nchains += B;
-            ngen++;
-            find_min();
+            const double Lstar = c.live[(size_t)order[K - 1] * T + l0];
+            const int B = std::max(0, std::min(std::max(target_nlive(Lstar), 1) - (n - K), 2 * S.batch_K));
+            batched_generation(K, B, babies);
             if (sum_logX() <= logX_last_update + std::log(S.compression_factor)) do_update();
         }
     }
@@ -1321,9 +1366,12 @@ struct Run {
         g_boost_rows.clear(); g_boost_dead.clear(); g_boost_logw.clear();
         init_layout();
         generate_live_points();
-        // nprior > nlive: trim (nested_sampling.F90:201-203)
-        while (cl[0].nlive > S.nlive) delete_outermost_point();
-        if (S.batch_K > 0) run_batched(); else run_reference();
+        if (S.batch_K > 0) run_batched();
+        else {
+            // nprior > nlive: trim (nested_sampling.F90:201-203)
+            while (cl[0].nlive > S.nlive) delete_outermost_point();
+            run_reference();
+        }
         out->ncluster = S.batch_K > 0 ? ncl_b : (long long)cl.size();
         out->nsplits = nsplits;
         final_killoff();

@@ -33,18 +33,43 @@ def stale():
     return any(p.stat().st_mtime > t for p in deps)
 
 
+def _deps(src):
+    """What an object file depends on: its source and, conservatively, every header of the engine."""
+    heads = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list((PKG.parent / "include").glob("*"))
+    if src.suffix == ".cpp":   # host-only units do not see the kernel headers
+        heads = [h for h in heads if h.suffix != ".cuh" or h.name == "pc_device.cuh"]
+    return [src] + heads
+
+
 def build(force=False, verbose=False):
+    """One object per translation unit under polychordlite_b200/build/ (only the stale ones are recompiled, eight at a
+    time), then one link.  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo for every unit."""
     if not force and not stale():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     LIBDIR.mkdir(exist_ok=True)
+    objdir = PKG / "build"
+    objdir.mkdir(exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    srcs = [str(p) for p in sources() if p.name != SHIM_SRC.name]
-    cmd = [nvcc, *NVCC_FLAGS, "-I", str(PKG.parent / "include"), "-o", str(LIB), *srcs]
+    flags = [f for f in NVCC_FLAGS if f not in ("-shared", "--threads", "8")]
+    srcs = [p for p in sources() if p.name != SHIM_SRC.name]
+    jobs = []
+    for src in srcs:
+        obj = objdir / (src.stem + ".o")
+        if force or not obj.exists() or any(d.stat().st_mtime > obj.stat().st_mtime for d in _deps(src)):
+            cmd = [nvcc, *flags, "-I", str(PKG.parent / "include"), "-c", str(src), "-o", str(obj)]
+            if verbose:
+                cmd[1:1] = ["-Xptxas", "-v"]
+            jobs.append(cmd)
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True)
+        print(f"{len(jobs)} of {len(srcs)} units to compile")
+    with ThreadPoolExecutor(max_workers=int(os.environ.get("PC_BUILD_JOBS", "8"))) as ex:
+        for r in ex.map(lambda c: subprocess.run(c, check=False), jobs):
+            if r.returncode != 0:
+                raise subprocess.CalledProcessError(r.returncode, r.args)
+    objs = [str(objdir / (p.stem + ".o")) for p in srcs]
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", str(LIB), *objs],
+                   check=True)
     return LIB
 
 

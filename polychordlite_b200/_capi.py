@@ -27,7 +27,7 @@ EXPORTS = [
     "pc_unit_prior", "pc_uniform_prior", "pc_set_option", "pc_get_option", "pc_set_stream", "pc_release_memory", "pc_mgpu_create", "pc_mgpu_attach", "pc_mgpu_destroy",
     "pc_last_run_info", "pc_run", "pc_run_ensemble", "pc_slice_chains", "pc_calculate_points",
     "pc_device_philox", "pc_device_uniforms", "pc_device_inv_normal_cdf", "pc_device_directions",
-    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points", "pc_set_grades", "pc_set_resume", "pc_measure_fp64_tflops", "pc_ini_prior_transform", "pc_last_boosted", "pc_maximise", "pc_prior_log_density", "pc_set_initial_live", "pc_write_files_boosted",
+    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points", "pc_set_grades", "pc_set_resume", "pc_measure_fp64_tflops", "pc_ini_prior_transform", "pc_last_boosted", "pc_maximise", "pc_prior_log_density", "pc_set_initial_live", "pc_write_files_boosted", "pc_set_nlives",
 ]
 
 
@@ -157,6 +157,17 @@ def set_initial_live(cube_samples=None):
     a = np.ascontiguousarray(cube_samples, dtype=np.float64)
     if a.ndim != 2 or L.pc_set_initial_live(_dptr(a), a.shape[0], a.shape[1]) != 0:
         raise ValueError("cube_samples must be a (npoints, nDims) array")
+
+
+def set_nlives(schedule=None):
+    """pc_set_nlives: dynamic nlive of the following pc_run() calls, {loglike threshold: nlive}; None or {} clears."""
+    L = lib()
+    L.pc_set_nlives.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
+    items = sorted((schedule or {}).items())
+    ll = (C.c_double * max(len(items), 1))(*[float(k) for k, _ in items])
+    nl = (C.c_int * max(len(items), 1))(*[int(v) for _, v in items])
+    if L.pc_set_nlives(ll, nl, len(items)) != 0:
+        raise ValueError("the nlives schedule holds at most 16 entries")
 
 
 def last_boosted(npars):

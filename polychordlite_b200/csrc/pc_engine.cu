@@ -195,6 +195,9 @@ struct Options {
 static Options g_opt;
 static volatile int g_abort = 0;                  // pc_request_abort(): a host callback asks the run in flight to stop
 static std::vector<int> g_grade_dims, g_grade_reps;   // fast/slow grades of the following runs (pc_set_grades)
+// dynamic nlive of the following runs (pc_set_nlives): above the contour loglikes[i] the run keeps nlives[i] live points
+static std::vector<double> g_dyn_loglikes;
+static std::vector<int> g_dyn_nlives;
 // cube_samples (polychord.py:576-579, _make_resume_file :650-789): the caller's initial live points, cube coordinates,
 // consumed by the next run through polychord_c_interface (one-shot, pc_set_initial_live)
 static std::vector<double> g_init_cubes;
@@ -352,6 +355,19 @@ static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const Dev
     k.cp.logzero = s.logzero;
     k.cp.gauss_norm = dm.gauss_norm; k.cp.Vn = dm.Vn; k.cp.log_rast = dm.log_rast; k.cp.corr_const = dm.corr_const;
     k.n = s.nlive;
+    k.nfail = s.nfail;
+    // live points the run starts with: nprior draws when nprior > nlive (generate.F90:142-153; the excess dies first,
+    // nested_sampling.F90:201-203), the caller's cube_samples when given (any number: the count then moves to nlive)
+    k.n0 = g_init_n > 0 ? g_init_n : std::max(s.nlive, s.nprior);
+    if (g_dyn_loglikes.size() > MAX_DYN) throw pc::ArgError("polychord_b200: at most 16 entries in the nlives schedule");
+    k.dyn_m = (int)g_dyn_loglikes.size();
+    k.nmax = std::max(k.n, k.n0);
+    for (int i = 0; i < k.dyn_m; ++i) {
+        if (g_dyn_nlives[i] < 1) throw pc::ArgError("polychord_b200: the nlives schedule must hold positive counts");
+        k.dyn_loglikes[i] = g_dyn_loglikes[i]; k.dyn_nlives[i] = g_dyn_nlives[i];
+        k.nmax = std::max(k.nmax, g_dyn_nlives[i]);
+    }
+    if (k.n0 < 2) throw pc::ArgError("polychord_b200: a run needs at least two live points");
     k.use_prec = s.precision_criterion > 0.0;
     k.max_ndead = s.max_ndead;
     k.log_prec = k.use_prec ? std::log(s.precision_criterion) : 0.0;
@@ -370,13 +386,14 @@ static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const Dev
     k.off_like = (int)off;
     off += (size_t)((nlp + 1) & ~1) * 8;
     off += 64 * sizeof(int);  // s_cnt
+    off = (off + 15) & ~(size_t)15;   // the per-warp areas start 16-byte aligned (cp.async staging of the dense chain phase)
     k.off_warp = (int)off;
     // phase U: pivot + a staged batch of augmented rows per warp; all warps' areas together hold the CTA's moment matrix
     const size_t cov_bytes = std::max((size_t)(Dpad + U_BATCH * (Dp8 + 4)) * 8,
                                       ((size_t)(Dpad + Dp8 * Dp8) * 8 + W - 1) / W);
     const int K = batch_size(s.nlive, alone);
     k.batch_K = K;
-    const size_t sort_bytes = std::max(smem_S_bytes(s.nlive, K), (size_t)64 * 8 + (size_t)(D * D + Dpad) * 8);  // phase S, or the covariance (+ mean shift) in finish_update
+    const size_t sort_bytes = std::max(smem_S_bytes(k.nmax, K), (size_t)64 * 8 + (size_t)(D * D + Dpad) * 8);  // phase S, or the covariance (+ mean shift) in finish_update
     const size_t budget = dense ? 108 * 1024 : 200 * 1024;
     const int slb = dense ? dense_slb(L.fn.G * L.fn.DPL) : 0;   // dense chain phase: slice records staged per point group
     k.dense = dense ? 1 : 0;
@@ -406,7 +423,7 @@ static void set_smem(const ShapeFns& fn, size_t smem) {
 struct HostRun {
     DevArr<DevRun> st;
     DevArr<double> live, live_snap, dead, logw, ph0, ph1, chol, cov, partial, nh, gsum, okey;
-    DevArr<int> order, lab, phl0, phl1;
+    DevArr<int> order, lab, phl0, phl1, cfail;
     DevArr<double> cchol;
     DevArr<long long> pcount;
     DevArr<double> boost;
@@ -426,7 +443,7 @@ struct HostRun {
 struct ResumeHeader {
     char magic[8];
     int version, sizeof_devrun;
-    int D, P, n, R, batch_K, like_kind, clustering, ngrade;
+    int D, P, n, nmax, R, batch_K, like_kind, clustering, ngrade;
     int gdims[MAX_GRADES], greps[MAX_GRADES];
     unsigned seed;
     int pad;
@@ -439,7 +456,7 @@ struct ResumeData {
     std::vector<int> order, lab, phl;
     std::vector<unsigned long long> boost_win;
 };
-static const char RESUME_MAGIC[8] = {'P', 'C', 'B', '2', '0', '0', 'R', '1'};
+static const char RESUME_MAGIC[8] = {'P', 'C', 'B', '2', '0', '0', 'R', '2'};
 template <class V>
 static void put_vec(FILE* f, const std::vector<V>& v) {
     const unsigned long long n = v.size();
@@ -507,7 +524,7 @@ struct Engine {
     // (birth contour logzero); a point the likelihood excludes is fatal.
     void host_given_live_points() {
         const KParams& k = L.kp;
-        const int D = k.cp.D, P = k.cp.P, T = k.cp.T, n = k.n;
+        const int D = k.cp.D, P = k.cp.P, T = k.cp.T, n = k.n0;
         std::vector<double> live((size_t)n * T, 0.0), cube(D), theta(D), phi(std::max(P, 1));
         for (int j = 0; j < n; ++j) {
             double* rec = &live[(size_t)j * T];
@@ -528,6 +545,7 @@ struct Engine {
         std::memset(&h0, 0, sizeof(h0));
         h0.nlike = n;
         h0.init_attempts = n;
+        h0.n = n;
         runs[0].live.upload(live.data(), live.size(), stream);
         runs[0].st.upload(&h0, 1, stream);
         h2d += (long long)live.size() * 8;
@@ -536,7 +554,7 @@ struct Engine {
 
     void host_generate_live_points() {
         const KParams& k = L.kp;
-        const int D = k.cp.D, P = k.cp.P, T = k.cp.T, n = k.n;
+        const int D = k.cp.D, P = k.cp.P, T = k.cp.T, n = k.n0;
         std::vector<double> live((size_t)n * T, 0.0), cube(D), theta(D), phi(std::max(P, 1));
         DevRun h0;
         std::memset(&h0, 0, sizeof(h0));
@@ -573,6 +591,7 @@ struct Engine {
         }
         h0.nlike = nl;
         h0.init_attempts = a;
+        h0.n = n;
         runs[0].live.upload(live.data(), live.size(), stream);
         runs[0].st.upload(&h0, 1, stream);
         h2d += (long long)live.size() * 8;
@@ -583,14 +602,14 @@ struct Engine {
     // and the calling thread makes the prior + likelihood calls (calculate_point, calculate.f90:6-50).
     void host_chains() {
         const KParams& k = L.kp;
-        const int D = k.cp.D, P = k.cp.P, K = runs[0].host_st.K;
+        const int D = k.cp.D, P = k.cp.P, K = runs[0].host_st.B, Kdead = runs[0].host_st.K;   // births (chains), deaths
         HcParams hp;
         std::memset(&hp, 0, sizeof(hp));
-        hp.D = D; hp.P = P; hp.T = k.cp.T; hp.R = k.cp.R; hp.LD = k.cp.LD; hp.n = k.n; hp.K = K; hp.cp = k.cp;
+        hp.D = D; hp.P = P; hp.T = k.cp.T; hp.R = k.cp.R; hp.LD = k.cp.LD; hp.n = runs[0].host_st.n_gen; hp.K = K; hp.Kdead = Kdead; hp.cp = k.cp;
         hp.logzero = S.logzero; hp.seed = runs[0].buf.seed; hp.rb = runs[0].buf;
         hp.scratch_bytes = chain_scratch_bytes(D, k.cp.R, k.cp.LD, true, LIKE_GAUSSIAN, 1);
         if (!hc_out) {
-            const size_t Kmax = (size_t)k.batch_K;
+            const size_t Kmax = (size_t)2 * k.batch_K;   // births of a generation (phase S1)
             hc_scratch.alloc(Kmax * hp.scratch_bytes);
             hc_x.alloc(Kmax * k.cp.LD);
             hc_ch.alloc(Kmax);
@@ -602,8 +621,8 @@ struct Engine {
         PC_CUDA(cudaHostGetDevicePointer((void**)&d_out, hc_out, 0));
         PC_CUDA(cudaHostGetDevicePointer((void**)&d_in, hc_in, 0));
         hp.out = d_out; hp.in = d_in;
-        const int W = 4, blocks = (K + W - 1) / W;
-        hc_begin_kernel<<<blocks, W * 32, 0, stream>>>(hp);
+        const int W = 4, blocks = std::max(1, (K + W - 1) / W);
+        hc_begin_kernel<<<std::max(1, (std::max(K, Kdead) + W - 1) / W), W * 32, 0, stream>>>(hp);
         PC_CUDA(cudaGetLastError());
         std::vector<double> cube(D), theta(D), phi(std::max(P, 1));
         long long nl = 0;
@@ -654,8 +673,6 @@ struct Engine {
         mark("device_check");
         S = s; ms = m; nruns = nruns_;
         stream = g_stream;
-        if (S.nprior > 0 && S.nprior != S.nlive)
-            throw pc::ArgError("polychord_b200: nprior != nlive is not supported by the device path yet");
         host_like = ms.like_kind == PC_LIKE_HOST;
         if (host_like && (nruns != 1 || g_mgpu.world > 1))
             throw pc::ArgError("polychord_b200: host-callback likelihoods run one run on one GPU");
@@ -678,9 +695,7 @@ struct Engine {
         given_live = false;
         if (g_init_n > 0) {
             if (nruns != 1 || g_mgpu.world > 1) throw pc::ArgError("polychord_b200: cube_samples start one run on one GPU");
-            if (g_init_n != k.n || g_init_D != k.cp.D)
-                throw pc::ArgError("polychord_b200: cube_samples must hold nlive points of nDims coordinates (a different "
-                                            "number would need the dynamic-nlive schedule, which this engine does not have)");
+            if (g_init_D != k.cp.D) throw pc::ArgError("polychord_b200: cube_samples must hold points of nDims coordinates");
             if (!g_init_ll || !g_init_prior) throw pc::ArgError("polychord_b200: cube_samples need the run's callbacks");
             given_live = true;
             k.live_given = 1;
@@ -696,7 +711,7 @@ struct Engine {
         // resume file with them)
         if (g_resume.read && g_init_n == 0 && nruns == 1 && g_mgpu.world <= 1 && read_resume_file(g_resume.path, rd)) {
             const ResumeHeader& rh = rd.h;
-            bool same = rh.D == k.cp.D && rh.P == k.cp.P && rh.n == k.n && rh.R == k.cp.R && rh.batch_K == K &&
+            bool same = rh.D == k.cp.D && rh.P == k.cp.P && rh.n == k.n && rh.nmax == k.nmax && rh.R == k.cp.R && rh.batch_K == K &&
                         rh.like_kind == ms.like_kind && rh.clustering == k.clustering && rh.ngrade == k.cp.ngrade;
             for (int g = 0; same && g < k.cp.ngrade && k.cp.ngrade > 1; ++g)
                 same = rh.gdims[g] == k.cp.gdims[g] && rh.greps[g] == k.cp.greps[g];
@@ -717,6 +732,8 @@ struct Engine {
         const bool sharded = g_mgpu.world > 1;
         if (sharded) {
             if (nruns != 1) throw pc::ArgError("polychord_b200: a sharded run cannot be part of an ensemble");
+            if (k.n0 != k.n || k.dyn_m > 0)
+                throw pc::ArgError("polychord_b200: a sharded run keeps its live count fixed (no nprior > nlive, nlives schedule or cube_samples of another length)");
             if (g_mgpu.batch_K != K || g_mgpu.T != k.cp.T || g_mgpu.D != k.cp.D)
                 throw pc::ArgError("polychord_b200: pc_mgpu_create was called with different settings than this run");
             k.sh.rank = g_mgpu.rank; k.sh.world = g_mgpu.world; k.sh.xstride = (long long)mgpu_xstride(k.cp.D);
@@ -740,18 +757,19 @@ struct Engine {
         PC_CUDA(cudaEventCreate(&ev1));
         mark("occupancy+events");
 
-        const int T = k.cp.T, D = k.cp.D, R = k.cp.R, n = k.n;
+        const int T = k.cp.T, D = k.cp.D, R = k.cp.R, n = k.nmax;   // capacities follow the largest live count the run can reach
         runs.resize(nruns);
         std::vector<RunBuf> hb(nruns);
         for (int r = 0; r < nruns; ++r) {
             HostRun& h = runs[r];
-            long long cap_dead = S.max_ndead > 0 ? (long long)S.max_ndead + 2LL * n + K : 40LL * n + K;
-            long long cap_ph = std::max<long long>(3LL * n * (R - 1) + (long long)K * (R - 1), n);
-            if (g_opt.cap_dead0 > 0) cap_dead = std::max<long long>(g_opt.cap_dead0, 2LL * n + K);
-            if (g_opt.cap_ph0 > 0) cap_ph = std::max<long long>(g_opt.cap_ph0, std::max<long long>((long long)K * (R - 1), n));
+            // a generation needs room for its K deaths, up to 2K births (failed ones go to the dead list) and the final kill-off
+            long long cap_dead = S.max_ndead > 0 ? (long long)S.max_ndead + 2LL * n + 3LL * K : 40LL * n + 3LL * K;
+            long long cap_ph = std::max<long long>(3LL * n * (R - 1) + 2LL * K * (R - 1), n);
+            if (g_opt.cap_dead0 > 0) cap_dead = std::max<long long>(g_opt.cap_dead0, 2LL * n + 3LL * K);
+            if (g_opt.cap_ph0 > 0) cap_ph = std::max<long long>(g_opt.cap_ph0, std::max<long long>(2LL * K * (R - 1), n));
             if (resumed) {  // room for what the file holds plus the next generation
-                cap_dead = std::max<long long>(cap_dead, rd.st.ndead + 2LL * n + K);
-                cap_ph = std::max<long long>(cap_ph, rd.st.nphantom + (long long)K * (R - 1) + n);
+                cap_dead = std::max<long long>(cap_dead, rd.st.ndead + 2LL * n + 3LL * K);
+                cap_ph = std::max<long long>(cap_ph, rd.st.nphantom + 2LL * K * (R - 1) + n);
             }
             long long cap_boost = 0;
             if (k.boost_thin > 0.0) {
@@ -769,6 +787,7 @@ struct Engine {
             h.ph1.alloc((size_t)cap_ph * T);
             h.chol.alloc((size_t)D * D); h.cov.alloc((size_t)D * D);
             h.gsum.alloc((size_t)2 * D + 4);
+            h.cfail.alloc((size_t)2 * K + 8); h.cfail.zero(stream);
             h.partial.alloc((size_t)G * k.partial_stride);
             h.pcount.alloc((size_t)cap_ph / U_TILE + 2); h.pcount.zero(stream);
             if (k.dense) h.nh.alloc((size_t)G * W * (32 / L.fn.G) * R * dense_slb(L.fn.G * L.fn.DPL));   // slice records of the chains in flight
@@ -786,6 +805,7 @@ struct Engine {
             b.pcount = h.pcount.p; b.nh = h.nh.p; b.cap_dead = cap_dead; b.cap_ph = cap_ph; b.gsum = h.gsum.p;
             b.lab = h.lab.p; b.phl[0] = h.phl0.p; b.phl[1] = h.phl1.p; b.cchol = h.cchol.p;
             b.boost = h.boost.p; b.boost_win = h.boost_win.p; b.cap_boost = cap_boost;
+            b.cfail = h.cfail.p;
             if (sharded)  // continue the cross-GPU barrier count of earlier runs (the counters are monotonic)
                 PC_CUDA(cudaMemcpyAsync(&h.st.p->xepoch, &g_mgpu.epoch, sizeof(g_mgpu.epoch), cudaMemcpyHostToDevice, stream));
             b.seed = resumed ? rd.h.seed : (unsigned)seeds[r];   // a resumed run continues its own random stream
@@ -866,10 +886,10 @@ struct Engine {
     // state: {ndead, logZ, logZ2}; live_src: device records of the live points to report (null: none);
     // cs: the stream the copies are enqueued on (the copy stream while the run kernel is still sampling)
     void dump(int r, pc_dumper_t dumper, long long ndead, double logZ_raw, double logZ2_raw, const double* live_src,
-              cudaStream_t cs, long long nlike_now = 0, bool final_call = false) {
+              int nlive_now, cudaStream_t cs, long long nlike_now = 0, bool final_call = false) {
         HostRun& h = runs[r];
         const KParams& k = L.kp;
-        const int T = k.cp.T, D = k.cp.D, P = k.cp.P, n = k.n, npars = D + P + 2;
+        const int T = k.cp.T, D = k.cp.D, P = k.cp.P, n = nlive_now, npars = D + P + 2;
         const long long fresh = ndead - h.mirrored;
         const int nl = live_src ? n : 0;
         auto td0 = std::chrono::steady_clock::now();
@@ -880,7 +900,7 @@ struct Engine {
         };
         // one batch of async copies into pinned staging, one synchronisation
         double* sd = fresh > 0 ? (double*)g_pin_dead.need((size_t)fresh * (T + 1) * 8) : nullptr;
-        double* sl = nl > 0 ? (double*)g_pin_live.need((size_t)n * T * 8) : nullptr;
+        double* sl = nl > 0 ? (double*)g_pin_live.need((size_t)k.nmax * T * 8) : nullptr;
         if (fresh > 0) {
             h.dead.download(sd, (size_t)fresh * T, cs, (size_t)h.mirrored * T);
             h.logw.download(sd + (size_t)fresh * T, fresh, cs, h.mirrored);
@@ -1055,7 +1075,7 @@ struct Engine {
     // (utils.F90:713-749 relabel), which is what the recursive formulation ends with.
     int cluster_labels(std::vector<int>& lab_out) {
         const KParams& k = L.kp;
-        return cluster_labels_of(runs[0].live.p, k.n, k.cp.D, k.cp.T, lab_out);
+        return cluster_labels_of(runs[0].live.p, runs[0].host_st.n, k.cp.D, k.cp.T, lab_out);
     }
     int cluster_labels_of(const double* d_live, int n, int D, int T, std::vector<int>& lab_out) {
         std::vector<int> part(n, 0);
@@ -1154,7 +1174,7 @@ struct Engine {
     // covariance + Cholesky factor per cluster (calculate_covmats, run_time_info.f90:601-641)
     void cluster_pass() {
         const KParams& k = L.kp;
-        const int n = k.n, D = k.cp.D, T = k.cp.T;
+        const int n = runs[0].host_st.n, D = k.cp.D, T = k.cp.T;
         HostRun& h = runs[0];
         const auto tc0 = std::chrono::steady_clock::now();
         int num = cluster_labels(h_lab);
@@ -1235,20 +1255,20 @@ struct Engine {
         const KParams& k = L.kp;
         HostRun& h = runs[0];
         const DevRun& st = h.host_st;
-        const int n = k.n, T = k.cp.T, D = k.cp.D;
+        const int n = st.n, T = k.cp.T, D = k.cp.D;
         ResumeData w;
         std::memset(&w.h, 0, sizeof(w.h));
         std::memcpy(w.h.magic, RESUME_MAGIC, 8);
         w.h.version = 1; w.h.sizeof_devrun = (int)sizeof(DevRun);
-        w.h.D = D; w.h.P = k.cp.P; w.h.n = n; w.h.R = k.cp.R; w.h.batch_K = k.batch_K; w.h.like_kind = ms.like_kind;
+        w.h.D = D; w.h.P = k.cp.P; w.h.n = k.n; w.h.nmax = k.nmax; w.h.R = k.cp.R; w.h.batch_K = k.batch_K; w.h.like_kind = ms.like_kind;
         w.h.clustering = k.clustering; w.h.ngrade = k.cp.ngrade;
         for (int g = 0; g < MAX_GRADES; ++g) { w.h.gdims[g] = k.cp.gdims[g]; w.h.greps[g] = k.cp.greps[g]; }
         w.h.seed = h.buf.seed; w.h.logzero = S.logzero;
         w.st = st;
         auto pull = [&](auto& vec, const auto& arr, size_t cnt) { vec.resize(cnt); if (cnt) arr.download(vec.data(), cnt, stream); };
         pull(w.live, h.live, (size_t)n * T);
-        pull(w.order, h.order, 2 * (size_t)n);
-        pull(w.okey, h.okey, 2 * (size_t)n);
+        pull(w.order, h.order, 2 * (size_t)k.nmax);
+        pull(w.okey, h.okey, 2 * (size_t)k.nmax);
         pull(w.dead, h.dead, (size_t)st.ndead * T);
         pull(w.logw, h.logw, (size_t)st.ndead);
         pull(w.ph, st.cur_pool == 0 ? h.ph0 : h.ph1, (size_t)st.nphantom * T);
@@ -1289,7 +1309,7 @@ struct Engine {
             h.boost_win.grow((size_t)nc, (size_t)h.host_st.nboost, stream);
             h.buf.boost = h.boost.p; h.buf.boost_win = h.boost_win.p; h.buf.cap_boost = nc;
         } else if (status == ST_NEED_DEAD) {
-            long long nc = h.buf.cap_dead * 2 + k.n + k.batch_K;
+            long long nc = h.buf.cap_dead * 2 + k.nmax + 3LL * k.batch_K;
             h.dead.grow((size_t)nc * k.cp.T, (size_t)h.host_st.ndead * k.cp.T, stream);
             h.logw.grow(nc, h.host_st.ndead, stream);
             h.buf.dead = h.dead.p; h.buf.logw = h.logw.p; h.buf.cap_dead = nc;
@@ -1328,7 +1348,7 @@ struct Engine {
             std::memset(c, 0, sizeof(*c));
             ctl = c;
             HostRun& h = runs[0];
-            h.live_snap.alloc((size_t)L.kp.n * L.kp.cp.T);
+            h.live_snap.alloc((size_t)L.kp.nmax * L.kp.cp.T);
             h.buf.live_snap = h.live_snap.p;
             HostCtl* dctl = nullptr;
             PC_CUDA(cudaHostGetDevicePointer((void**)&dctl, c, 0));
@@ -1343,7 +1363,7 @@ struct Engine {
             auto ts = now();
             const long long nd = ctl->ndead;
             const double lz = ctl->logZ, lz2 = ctl->logZ2;
-            dump(0, dumper, nd, lz, lz2, runs[0].live_snap.p, g_copy_stream, ctl->nlike);
+            dump(0, dumper, nd, lz, lz2, runs[0].live_snap.p, ctl->nlive, g_copy_stream, ctl->nlike);
             ++handled;
             ctl->ack_seq = handled;
             dbg_service_ms += ms_since(ts);
@@ -1351,7 +1371,7 @@ struct Engine {
         for (; !resumed_finished;) {
             if (ctl) {  // size the pinned staging now: (re)allocating pinned memory synchronises with the running kernel
                 g_pin_dead.need((size_t)runs[0].buf.cap_dead * (L.kp.cp.T + 1) * 8);
-                g_pin_live.need((size_t)L.kp.n * L.kp.cp.T * 8);
+                g_pin_live.need((size_t)L.kp.nmax * L.kp.cp.T * 8);
             }
             { auto tl = now(); launch_async(); dbg_launch_ms += ms_since(tl); }
             if (ctl) {
@@ -1375,16 +1395,16 @@ struct Engine {
                 if (stt == ST_DUMP && ctl) throw pc::RunError("polychord_b200: run aborted");
                 if (stt == ST_DUMP) {  // sync_dump: the kernel left at the update, dump and relaunch
                     if (dumping)
-                        dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, runs[r].live.p, stream,
-                             runs[r].host_st.nlike);
+                        dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, runs[r].live.p,
+                             runs[r].host_st.n, stream, runs[r].host_st.nlike);
                     write_resume(false);
                 }
                 if (g_abort) throw pc::RunError("polychord_b200: run aborted by a host callback (pc_request_abort)");
                 if (stt == ST_HOSTCHAINS) host_chains();
                 if (stt == ST_CLUSTER) {  // the update left for the clustering pass; the dump of this update happens here too
                     if (dumping)
-                        dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, runs[r].live.p, stream,
-                             runs[r].host_st.nlike);
+                        dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, runs[r].live.p,
+                             runs[r].host_st.n, stream, runs[r].host_st.nlike);
                     cluster_pass();
                     PC_CUDA(cudaMemcpyAsync(&runs[r].host_st.ncl, &runs[r].st.p->ncl, sizeof(int), cudaMemcpyDeviceToHost, stream));
                     PC_CUDA(cudaStreamSynchronize(stream));
@@ -1397,9 +1417,12 @@ struct Engine {
             if (all_done) break;
         }
         if (g_mgpu.world > 1) g_mgpu.epoch = runs[0].host_st.xepoch;
-        if (g_final_live.want && nruns == 1 && runs[0].host_st.ndead >= L.kp.n) {
+        for (int r = 0; r < nruns; ++r)   // nested_sampling.F90:407-409
+            if (runs[r].host_st.stop_nfail && S.feedback >= 0)
+                std::printf("Warning, unable to proceed after %6d: failed spawn events\n", runs[r].host_st.fail_run);
+        if (g_final_live.want && nruns == 1 && runs[0].host_st.ndead >= runs[0].host_st.n) {
             // the final kill-off appended the n live points, lowest logL first: they are the last n dead records
-            const size_t n = (size_t)L.kp.n, T = (size_t)L.kp.cp.T;
+            const size_t n = (size_t)runs[0].host_st.n, T = (size_t)L.kp.cp.T;
             g_final_live.n = (int)n;
             g_final_live.recs.resize(n * T);
             runs[0].dead.download(g_final_live.recs.data(), n * T, stream, ((size_t)runs[0].host_st.ndead - n) * T);
@@ -1409,9 +1432,9 @@ struct Engine {
         auto tfin = now();
         if (dumping)  // the final call: every point is dead (nested_sampling.F90:392)
             for (int r = 0; r < nruns; ++r)
-                dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, nullptr, stream,
+                dump(r, dumper, runs[r].host_st.ndead, runs[r].host_st.logZ, runs[r].host_st.logZ2, nullptr, 0, stream,
                      runs[r].host_st.nlike, true);
-        if (want_files && !resumed) write_prior_info(g_files, L.kp.n, runs[0].host_st.init_attempts);
+        if (want_files && !resumed) write_prior_info(g_files, L.kp.n0, runs[0].host_st.init_attempts);
         if (!resumed_finished) write_resume(true);
         dbg_final_ms = ms_since(tfin);
         if (std::getenv("PC_DEBUG")) {
@@ -1545,6 +1568,14 @@ int pc_set_grades(int nGrade, const int* grade_dims, const int* grade_repeats) {
     if (nGrade < 0 || nGrade > MAX_GRADES) return -1;
     g_grade_dims.assign(grade_dims, grade_dims + nGrade);
     g_grade_reps.assign(grade_repeats, grade_repeats + nGrade);
+    return 0;
+}
+int pc_set_nlives(const double* loglikes, const int* nlives, int m) {
+    g_dyn_loglikes.clear(); g_dyn_nlives.clear();
+    if (m <= 0 || !loglikes || !nlives) return 0;
+    if (m > MAX_DYN) return -1;
+    g_dyn_loglikes.assign(loglikes, loglikes + m);
+    g_dyn_nlives.assign(nlives, nlives + m);
     return 0;
 }
 void pc_release_memory(void) { pool().trim(); }
@@ -2068,8 +2099,7 @@ void polychord_c_interface(pc_loglikelihood_t loglikelihood, pc_prior_t prior, p
                            pc_bool synchronous, int nDims, int nDerived, char* base_dir, char* file_root, int nGrade,
                            double* grade_frac, int* grade_dims, int n_nlives, double* loglikes, int* nlives, int seed,
                            int* comm) {
-    (void)write_paramnames; (void)synchronous; (void)grade_frac;
-    (void)loglikes; (void)nlives; (void)comm; (void)nfail; (void)do_clustering;
+    (void)write_paramnames; (void)synchronous; (void)grade_frac; (void)comm;
     std::memset(&g_last, 0, sizeof(g_last));
     g_abort = 0;
     if (dumper == default_dumper) dumper = nullptr;   // the facade's no-op: nothing to hand the dead points to
@@ -2107,9 +2137,13 @@ void polychord_c_interface(pc_loglikelihood_t loglikelihood, pc_prior_t prior, p
         fail(-4, "grade_dims must sum to nDims");
         return;
     }
+    // dynamic nlive (settings%loglikes / settings%nlives, interfaces.F90:416-422): the batched form of replace_point's
+    // rule (run_time_info.f90:766-777), phase S1
+    struct DynGuard { ~DynGuard() { g_dyn_loglikes.clear(); g_dyn_nlives.clear(); } } dyn_guard;
     if (n_nlives > 0) {
-        fail(-4, "dynamic nlive schedules (nlives/loglikes) are not supported by the B200 engine yet");
-        return;
+        if (n_nlives > MAX_DYN || !loglikes || !nlives) { fail(-4, "the nlives schedule holds at most 16 entries"); return; }
+        g_dyn_loglikes.assign(loglikes, loglikes + n_nlives);
+        g_dyn_nlives.assign(nlives, nlives + n_nlives);
     }
     auto li = like_registry().find((void*)loglikelihood);
     auto pi = prior_registry().find((void*)prior);

@@ -28,7 +28,8 @@ struct HcChain {
 struct HcParams {
     int D, P, T, R, LD, n;
     ChainParams cp;        // for the direction preparation (grades)
-    int K;                 // chains of this generation
+    int K;                 // chains (births) of this generation
+    int Kdead;             // deaths of this generation (the live count moves when they differ)
     double logzero;
     unsigned seed;
     RunBuf rb;
@@ -78,17 +79,22 @@ __device__ inline void hc_start_slice(const HcParams& p, const ChainScratch& cs,
 __global__ void hc_begin_kernel(const HcParams p) {
     const int lane = threadIdx.x & 31, W = blockDim.x >> 5;
     const int k = blockIdx.x * W + (threadIdx.x >> 5);
-    if (k >= p.K) return;
     const DevRun* st = p.rb.st;
-    const int T = p.T, D = p.D, n = p.n, K = p.K;
+    const int T = p.T, D = p.D, n = st->n_gen, K = p.Kdead, B = p.K;
     const int* order = p.rb.order + st->order_off;
+    if (k >= B) {   // a death without a birth (the live count shrinks): only the move to the dead list
+        if (k < K)
+            for (int e = lane; e < T; e += 32) p.rb.dead[(size_t)(st->ndead_base + k) * T + e] = p.rb.live[(size_t)order[k] * T + e];
+        return;
+    }
     const unsigned long long uid = (unsigned long long)(st->nchains_base + k);
     const int m = n - K;
     const double u = uniform(p.seed, TAG_SEED, uid, 0u, 0u);
     int choice = (int)ceil(u * (double)m);
     choice = max(1, min(m, choice));
-    const int src = order[K + choice - 1], dslot = order[k];
-    for (int e = lane; e < T; e += 32) p.rb.dead[(size_t)(st->ndead_base + k) * T + e] = p.rb.live[(size_t)dslot * T + e];
+    const int src = order[K + choice - 1], dslot = k < K ? order[k] : n + (k - K);
+    if (k < K)
+        for (int e = lane; e < T; e += 32) p.rb.dead[(size_t)(st->ndead_base + k) * T + e] = p.rb.live[(size_t)dslot * T + e];
     double* x = p.x + (size_t)k * p.LD;
     for (int r = lane; r < p.LD; r += 32) x[r] = r < D ? p.rb.live[(size_t)src * T + r] : 0.0;
     const ChainScratch cs = hc_scratch(p, k);
@@ -178,8 +184,11 @@ __global__ void hc_step_kernel(const HcParams p) {
         for (int r = lane; r < P; r += 32) dst[2 * D + r] = in[D + r];
         if (lane == 0) { dst[2 * D + P] = Lstar; dst[2 * D + P + 1] = accepted ? l : logzero; }
         __syncwarp();
-        if (c.slice == R - 1 && lane == 0 && !(accepted && l > Lstar))   // a failed spawn (nested_sampling.F90:315-319)
-            atomicAdd((unsigned long long*)&p.rb.st->nfail, 1ull);
+        if (c.slice == R - 1 && lane == 0) {   // a failed spawn (nested_sampling.F90:315-319): settle_generation takes it out
+            const int failed = !(accepted && l > Lstar);
+            p.rb.cfail[k] = failed;
+            if (failed) { atomicAdd((unsigned long long*)&p.rb.st->nfail, 1ull); atomicAdd(&p.rb.st->nfail_gen, 1u); }
+        }
         c.slice += 1;
         if (c.slice == R) c.phase = HC_DONE;
         else hc_start_slice(p, cs, c);

@@ -34,6 +34,7 @@ constexpr int U_TILE = 256;         // records per phantom tile of phase U (= th
 constexpr int KNN_K = 10;           // clustering.f90:44: "10 degrees of separation"
 constexpr int MAX_CLUSTERS = 256;   // clusters with a factor of their own; further labels share the last one, which keeps the global factor
 constexpr int U_BATCH = 8;          // records a warp of phase U keeps in flight
+constexpr int MAX_DYN = 16;         // entries of a dynamic-nlive schedule
 
 // Mutable per-run scalars (device global memory; the host reads them between launches).
 struct DevRun {
@@ -63,7 +64,14 @@ struct DevRun {
     int ncl;             // clusters found at the last update (1: the global factor is used)
     int pad1;
     int host_resume;     // host-callback runs: the chains of the generation in flight were run by the host loop
-    int pad0;
+    int n;               // live points now (dynamic nlive, nprior, failed births: it moves; KParams::n is the target)
+    // the generation in flight: n_gen live points at its start, K of them die, B chains are born
+    int n_gen, B;
+    int holes_due;       // it leaves empty live slots (B != K): settle_generation closes them; failed births add to that
+    int trimmed;         // the nprior > nlive trim (nested_sampling.F90:201-203) has been done
+    int fail_run;        // failed births in a row (nested_sampling.F90:315-319)
+    int stop_nfail;      // ... exceeded nfail: the run ends with the reference's warning (:407-409)
+    unsigned int nfail_gen;  // failed births of the generation in flight (chain warps add, settle_generation clears)
     // SM-clock cycle counters of the phases (thread 0 of CTA 0; chain phases: warp 0 of the first chain CTA)
     long long cyc_wait, cyc_S, cyc_fin, cyc_U, cyc_prep, cyc_white, cyc_slice, cyc_total;
     // finer cycle counters, printed (in ms) when PC_DEBUG is set: [0] slice loop and [1] derived parameters of the
@@ -73,8 +81,8 @@ struct DevRun {
     long long dbg[24];
     // what every warp needs at the start of a generation, in one 64-byte line (written by phase S1, read with one
     // coalesced load per warp): [0] Lstar (bits), [1] ndead_base, [2] nph_base, [3] nchains_base, [4] ngen,
-    // [5] K | do_update << 32, [6] order_off | cur_pool << 32, [7] ncl | nupdates << 32
-    unsigned long long pub[8];
+    // [5] K | do_update << 32, [6] order_off | cur_pool << 32, [7] ncl | nupdates << 32, [8] n_gen | B << 32
+    unsigned long long pub[10];
     unsigned int bar;    // group barrier, one arrival per CTA (monotonic)
     unsigned int wbar;   // chains-done barrier, one arrival per warp (monotonic)
     // boost_posterior (clean_phantoms, run_time_info.f90:820-877): phantoms promoted to posterior samples so far
@@ -94,7 +102,7 @@ struct HostCtl {
     long long nlike;
     double logZ, logZ2;
     int abort;                     // host -> device: stop waiting (the dumper threw)
-    int pad;
+    int nlive;                     // live points in the snapshot
 };
 
 struct RunBuf {
@@ -120,6 +128,7 @@ struct RunBuf {
     unsigned long long* boost_win;  // ... and the window of dead indices each was removed against: first << 32 | end
     long long cap_boost;
     long long cap_dead, cap_ph;
+    int* cfail;        // per chain of the generation in flight: 1 when its last baby is not above the contour (a failed birth)
     unsigned int seed;
     int pad;
 };
@@ -144,7 +153,14 @@ struct Shard {
 struct KParams {
     ChainParams cp;              // D, P, T, R, LD, likelihood constants
     Shard sh;                    // sh.world <= 1: a run on one GPU
-    int n, batch_K;
+    int n, batch_K;              // target number of live points (settings%nlive); deaths per generation
+    int nmax, n0;                // capacity of the live arrays; live points the run starts with (nprior, cube_samples)
+    int nfail;                   // failed births in a row the run tolerates (settings%nfail; <= 0: nlive)
+    // dynamic nlive (settings%loglikes / settings%nlives, sorted by loglike: settings.f90:234-235): above the contour
+    // dyn_loglikes[i] the target is dyn_nlives[i] (run_time_info.f90:766-771)
+    int dyn_m;
+    int dyn_nlives[MAX_DYN];
+    double dyn_loglikes[MAX_DYN];
     int use_prec, max_ndead;
     int ctas_per_run, warps_per_cta;
     int chain_cta0;              // first CTA of a run's group that runs chains (1: CTA 0 only keeps the books)
@@ -164,30 +180,29 @@ struct KParams {
     RunBuf* runs;
 };
 
-// shared-memory layout of phase S (CTA 0)
+// shared-memory layout of phase S (CTA 0), over nmax live points and batches of up to kb births
 struct SmemS {
     double* sc;     // 64 doubles of reduction scratch
-    int* aval;      // n: slots of the survivors in order (merge path)
-    double* akey;   // n: keys of the survivors in order (merge path) / np2: all keys (full sort)
+    int* aval;      // nmax: slots of the survivors in order (merge path)
+    double* akey;   // nmax: keys of the survivors in order (merge path) / np2: all keys (full sort)
     double* bkey;   // npB: keys of the new babies
     int* bval;      // npB (merge) / np2 (full sort: slot of every key)
-    double* kkey;   // batch_K (+pad): the K lowest keys in order -> evidence
 };
 __host__ __device__ inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
-__host__ __device__ inline size_t smem_S_bytes(int n, int batch_K) {
-    const int np2 = next_pow2(n), npB = next_pow2(batch_K);
+__host__ __device__ inline size_t smem_S_bytes(int nmax, int batch_K) {
+    const int np2 = next_pow2(nmax), npB = next_pow2(batch_K);
     size_t full = (size_t)np2 * 12;
-    size_t merge = (size_t)n * 8 + (size_t)npB * 12 + (size_t)((n + 1) & ~1) * 4;
-    return 64 * 8 + (full > merge ? full : merge) + (size_t)((batch_K + 1) & ~1) * 8 + 16;
+    size_t merge = (size_t)nmax * 8 + (size_t)npB * 12 + (size_t)((nmax + 1) & ~1) * 4;
+    size_t settle = (size_t)nmax * 9 + 16 + (size_t)(2 * batch_K + 4) * 4;   // settle_generation: flags, fail flags, two slot lists
+    size_t most = full > merge ? full : merge;
+    return 64 * 8 + (most > settle ? most : settle) + 16;
 }
-__device__ inline SmemS smem_S(unsigned char* base, int n, int batch_K) {
+__device__ inline SmemS smem_S(unsigned char* base, int nmax, int batch_K) {
     SmemS m;
-    const int np2 = next_pow2(n), npB = next_pow2(batch_K);
-    size_t full = (size_t)np2 * 12, merge = (size_t)n * 8 + (size_t)npB * 12 + (size_t)((n + 1) & ~1) * 4;
+    const int npB = next_pow2(batch_K);
     m.sc = (double*)base;
     m.akey = m.sc + 64;
-    m.kkey = (double*)(base + 64 * 8 + (((full > merge ? full : merge) + 7) & ~(size_t)7));
-    m.bkey = m.akey + n;           // merge layout
+    m.bkey = m.akey + nmax;        // merge layout
     m.bval = (int*)(m.bkey + npB);
     m.aval = m.bval + npB;
     return m;
@@ -279,6 +294,28 @@ __device__ __forceinline__ double block_max(double v, double* sc) {
     __syncthreads();
     return t;
 }
+// exclusive prefix sum of ints; *total receives the block total
+__device__ __forceinline__ int block_exscan_int(int v, int* total, double* sc) {
+    int* si = (int*)sc;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) si[w] = inc;
+    __syncthreads();
+    int pre = 0, tot = 0;
+    for (int i = 0; i < nw; ++i) {
+        if (i < w) pre += si[i];
+        tot += si[i];
+    }
+    __syncthreads();
+    *total = tot;
+    return pre + inc - v;
+}
+
 // log( exp(init) + sum_threads exp(v) )
 __device__ __forceinline__ double block_lse(double v, double init, double* sc) {
     double m = fmax(block_max(v, sc), init);

@@ -15,7 +15,7 @@ __device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st
                                   int NG, double* sc) {
     constexpr int NPT = 32 / G;
     const int tid = threadIdx.x, W = blockDim.x >> 5, gw = cta * W + (tid >> 5), GW = NG * W;
-    const int D = p.cp.D, T = p.cp.T, n = p.n;
+    const int D = p.cp.D, T = p.cp.T, n = p.n0;   // nprior points when nprior > nlive (generate.F90:142-153), or the caller's cube_samples
     if (cta == 0) {
         for (int e = tid; e < D * D; e += blockDim.x) {
             double v = (e % D == e / D) ? 1.0 : 0.0;  // run_time_info.f90:193-194
@@ -28,6 +28,7 @@ __device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st
             st->logX = st->logXX = 0.0;
             st->logX_last_update = 0.0;
             st->ncl = 1;
+            st->n = n;
             st->init_need = p.live_given ? 0 : n;   // host-callback runs, cube_samples: the host evaluated and uploaded the live points
             if (!p.live_given) st->init_attempts = 0;
         }
@@ -81,10 +82,11 @@ __device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st
 
 // ---------------------------------------------------------------- phase S (CTA 0)
 // S1 (on the critical path of a generation): termination test (live_logZ, run_time_info.f90:683-709, against
-// precision_criterion, nested_sampling.F90:538), the order of the live points by (logL, slot), the K lowest die:
-// contour, bases, update decision.  The order is maintained incrementally: the n-K survivors of the previous
-// generation are still sorted, so only the K new babies are sorted (bitonic, shared memory) and the two lists
-// are merged by rank (binary searches).  The first generation sorts everything.
+// precision_criterion, nested_sampling.F90:538), the order of the n live points by (logL, slot), the K lowest die:
+// contour, number of births, bases, update decision.  The order is maintained incrementally: the n-K survivors of a
+// regular generation (K deaths, K successful births into the vacated slots) are still sorted, so only the K new babies
+// are sorted and the two lists are merged by rank (binary searches).  The first generation, and one that follows a
+// generation that moved live points (settle_generation), sorts everything.
 // S2 (off the critical path when CTA 0 only keeps the books): the evidence recurrences of the K deaths.
 // log X after `count` deaths from n_start live points: the same chunked sum evidence_deaths forms
 __device__ inline double logX_after(double lX, int count, int n_start, double* sc) {
@@ -100,19 +102,106 @@ __device__ inline double logX_after(double lX, int count, int n_start, double* s
     return lX;
 }
 
+// target number of live points above the contour (run_time_info.f90:766-771: the threshold with the largest loglike
+// below it; none: settings%nlive)
+__device__ inline int target_nlive(const KParams& p, double contour) {
+    int nlive = p.n, best = -1;
+    for (int q = 0; q < p.dyn_m; ++q)
+        if (contour > p.dyn_loglikes[q] && (best < 0 || p.dyn_loglikes[q] > p.dyn_loglikes[best])) best = q;
+    if (best >= 0) nlive = p.dyn_nlives[best];
+    return nlive;
+}
+
+// The generation just finished left empty live slots: vacated slots without a birth (B < K), or births that FAILED
+// (last baby not above the contour: a non-deterministic or plateau likelihood).  As replace_point (run_time_info.f90:
+// 781-785) a failed baby does not become a live point: it goes to the dead list with log-weight logzero, in chain
+// order, and counts towards nfail (nested_sampling.F90:315-319).  The empty slots are then closed from the top down by
+// moving the last record in -- in closed form: with n' = extent - holes, the occupied slots >= n' fill the holes < n',
+// the j-th lowest into the j-th lowest.  CTA 0; smem: the phase-S area.
+__device__ inline void settle_generation(const KParams& p, const RunBuf& rb, DevRun* st, unsigned char* smem_raw, bool clear_flags) {
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, W = nthr >> 5, T = p.cp.T;
+    const int K = st->K, B = st->B, n0 = st->n_gen;
+    const int ext = n0 + max(0, B - K);
+    const int* ord = rb.order + st->order_off;
+    double* sc = (double*)smem_raw;                             // 64 doubles
+    unsigned char* hole = smem_raw + 64 * 8;                    // ext flags
+    int* fail = (int*)(smem_raw + 64 * 8 + ((ext + 15) & ~15)); // B flags
+    int* list_h = fail + ((B + 3) & ~3);                        // holes below n', ascending
+    int* list_m = list_h + ext;                                 // occupied slots >= n', ascending
+    __shared__ int s_nf, s_run;
+    for (int k = tid; k < B; k += nthr) fail[k] = __ldcg(rb.cfail + k);
+    for (int e = tid; e < ext; e += nthr) hole[e] = 0;
+    if (tid == 0) { s_nf = 0; s_run = st->fail_run; }
+    __syncthreads();
+    // (a) failed births -> dead list, in chain order
+    const long long nd0 = st->ndead;
+    for (int k = 0; k < B; ++k) {
+        if (!fail[k]) { if (tid == 0) s_run = 0; continue; }   // uniform over the CTA
+        const int slot = k < K ? __ldcg(ord + k) : n0 + (k - K);
+        const int nf = s_nf;
+        __syncthreads();
+        for (int e = tid; e < T; e += nthr) rb.dead[(size_t)(nd0 + nf) * T + e] = __ldcg(rb.live + (size_t)slot * T + e);
+        if (tid == 0) { rb.logw[nd0 + nf] = p.cp.logzero; s_nf = nf + 1; s_run += 1; }
+        __syncthreads();
+    }
+    // (b) the empty slots
+    for (int k = tid; k < K; k += nthr)
+        if (k >= B || fail[k]) hole[__ldcg(ord + k)] = 1;
+    for (int k = K + tid; k < B; k += nthr)
+        if (fail[k]) hole[n0 + (k - K)] = 1;
+    __syncthreads();
+    int cnt = 0;
+    for (int e = tid; e < ext; e += nthr) cnt += hole[e];
+    int nh;
+    block_exscan_int(cnt, &nh, sc);
+    const int n1 = ext - nh;
+    // (c) ascending lists by contiguous chunks
+    {
+        const int chunk = (ext + nthr - 1) / nthr, e0 = tid * chunk, e1 = min(ext, e0 + chunk);
+        int ch = 0, cm = 0;
+        for (int e = e0; e < e1; ++e) { ch += (e < n1 && hole[e]); cm += (e >= n1 && !hole[e]); }
+        int th, tm;
+        int ph = block_exscan_int(ch, &th, sc);
+        int pm = block_exscan_int(cm, &tm, sc);
+        for (int e = e0; e < e1; ++e) {
+            if (e < n1 && hole[e]) list_h[ph++] = e;
+            if (e >= n1 && !hole[e]) list_m[pm++] = e;
+        }
+        __syncthreads();
+        // (d) the moves: distinct sources and destinations, one record per warp
+        for (int j = warp; j < th; j += W) {
+            const int src = list_m[j], dst = list_h[j];
+            for (int e = lane; e < T; e += 32) rb.live[(size_t)dst * T + e] = __ldcg(rb.live + (size_t)src * T + e);
+            if (p.clustering && lane == 0) rb.lab[dst] = __ldcg(rb.lab + src);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        st->n = n1;
+        st->ndead = nd0 + s_nf;
+        st->fail_run = s_run;
+        const int nfail = p.nfail > 0 ? p.nfail : p.n;
+        if (s_run > nfail) st->stop_nfail = 1;
+        st->order_valid = 0;
+        if (clear_flags) { st->holes_due = 0; st->nfail_gen = 0u; }
+    }
+    __syncthreads();
+}
+
 // returns true when the evidence of the K deaths is still to be accumulated (S2)
 __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, const SmemS& sm) {
-    const int tid = threadIdx.x, n = p.n, T = p.cp.T, nthr = blockDim.x;
+    const int tid = threadIdx.x, T = p.cp.T, nthr = blockDim.x;
+    const int n = st->n;
     double* sc = sm.sc;
     long long q0 = clock64();
     const long long ndead = st->ndead;
     const int Kp = st->K;
     const bool merge = st->order_valid != 0 && Kp > 0 && Kp < n;
     const int* oldo = rb.order + st->order_off;
-    int* newo = rb.order + (st->order_off ? 0 : n);
+    int* newo = rb.order + (st->order_off ? 0 : p.nmax);
     const double* oldk = rb.okey + st->order_off;
-    double* newk = rb.okey + (st->order_off ? 0 : n);
-    const int m = n - Kp, npB = next_pow2(p.batch_K), np2 = next_pow2(n);
+    double* newk = rb.okey + (st->order_off ? 0 : p.nmax);
+    const int m = n - Kp, npB = next_pow2(max(Kp, 1)), np2 = next_pow2(n);
     if (merge) {
         for (int i = tid; i < m; i += nthr) {  // the survivors: keys and slots as the previous phase S ordered them
             sm.akey[i] = __ldcg(oldk + Kp + i);
@@ -133,8 +222,12 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
     long long q1 = clock64();
     // every live key once, whichever layout: index i < m in akey, the rest in bkey (merge) / all in akey
     auto key_at = [&](int i) -> double { return merge ? (i < m ? sm.akey[i] : sm.bkey[i - m]) : sm.akey[i]; };
+    // nprior > nlive: the excess points die first, one after the other, without births (nested_sampling.F90:201-203)
+    const bool trim = !st->trimmed && n > p.n;
     bool more = true;
-    if (p.max_ndead == 0) more = false;
+    if (trim) more = true;
+    else if (st->stop_nfail) more = false;
+    else if (p.max_ndead == 0) more = false;
     else if (p.max_ndead > 0 && ndead >= p.max_ndead) more = false;
     else if (p.use_prec) {
         double mx = -INFINITY;
@@ -147,15 +240,18 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
         if (lz < p.log_prec + st->logZ) more = false;
     }
     int K = min(p.batch_K, n - 1);
-    if (p.max_ndead > 0) K = (int)min((long long)K, (long long)p.max_ndead - ndead);
+    if (trim) K = n - p.n;
+    else if (p.max_ndead > 0) K = (int)min((long long)K, (long long)p.max_ndead - ndead);
     if (K < 1) more = false;
+    const int Bmax = trim ? 0 : 2 * p.batch_K;   // births of this generation cannot exceed this
     if (more) {
-        if (ndead + K + n > rb.cap_dead) { if (tid == 0) st->status = ST_NEED_DEAD; return false; }
+        // room for the K deaths, the births that may fail, and the final kill-off
+        if (ndead + K + Bmax + p.nmax > rb.cap_dead) { if (tid == 0) st->status = ST_NEED_DEAD; return false; }
         // sharded run: the decision must be the same on every rank, so it is taken on the phantoms of all ranks
         const long long nph_test = p.sh.world > 1 ? st->nph_glob : st->nphantom;
-        if (nph_test + (long long)K * (p.cp.R - 1) > rb.cap_ph) { if (tid == 0) st->status = ST_NEED_PHANTOM; return false; }
+        if (nph_test + (long long)Bmax * (p.cp.R - 1) > rb.cap_ph) { if (tid == 0) st->status = ST_NEED_PHANTOM; return false; }
         // boost_posterior: room for every phantom the next update could promote
-        if (p.boost_thin > 0.0 && (long long)st->nboost + st->nphantom + (long long)K * (p.cp.R - 1) > rb.cap_boost) {
+        if (p.boost_thin > 0.0 && (long long)st->nboost + st->nphantom + (long long)Bmax * (p.cp.R - 1) > rb.cap_boost) {
             if (tid == 0) st->status = ST_NEED_BOOST;
             return false;
         }
@@ -165,7 +261,32 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
     }
     long long q2 = clock64();
     if (merge && more) {
-        if (npB <= (int)blockDim.x) block_sort_small(sm.bkey, sm.bval, npB); else block_sort(sm.bkey, sm.bval, npB);
+        // the babies in order.  Up to two per thread: each counts the babies before it (the keys are read as
+        // broadcasts, no barrier between the steps); more: bitonic sort in shared memory.
+        if (Kp <= 2 * nthr) {
+            double mk[2];
+            int mv[2], rk[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = tid + h * nthr;
+                mk[h] = j < Kp ? sm.bkey[j] : INFINITY;
+                mv[h] = j < Kp ? sm.bval[j] : 0x7fffffff;
+                rk[h] = 0;
+            }
+            for (int j = 0; j < Kp; ++j) {
+                const double kj = sm.bkey[j];
+                const int vj = sm.bval[j];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) rk[h] += (kj < mk[h] || (kj == mk[h] && vj < mv[h])) ? 1 : 0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (tid + h * nthr < Kp) { sm.bkey[rk[h]] = mk[h]; sm.bval[rk[h]] = mv[h]; }
+            __syncthreads();
+        } else {
+            block_sort(sm.bkey, sm.bval, npB);
+        }
         // rank of a survivor = its index + number of babies before it; rank of a baby = its index + number of
         // survivors before it ((key, slot) pairs are distinct, so the merged order is the sorted order)
         for (int i = tid; i < m; i += nthr) {
@@ -180,7 +301,6 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
             const int rank = i + lo;
             newo[rank] = va;
             newk[rank] = ka;
-            if (rank < K) sm.kkey[rank] = ka;
         }
         for (int j = tid; j < Kp; j += nthr) {
             const double kb = sm.bkey[j];
@@ -196,11 +316,10 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
             const int rank = j + lo;
             newo[rank] = vb;
             newk[rank] = kb;
-            if (rank < K) sm.kkey[rank] = kb;
         }
         __syncthreads();
     } else {
-        // full sort: first generation and the final kill-off (which needs every key in order)
+        // full sort: first generation, after live points moved, and the final kill-off (which needs every key in order)
         double* skey = sm.akey;
         int* sval = (int*)(sm.akey + np2);
         if (merge) {  // !more on the merge layout: rebuild the flat layout
@@ -213,37 +332,45 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
         }
         block_sort(skey, sval, np2);
         for (int i = tid; i < n; i += nthr) { newo[i] = sval[i]; newk[i] = skey[i]; }
+        __syncthreads();
         if (!more) {  // final kill-off, nested_sampling.F90:381-384
             evidence_deaths(st, skey, n, n, rb.logw + ndead, sc);
             for (size_t e = tid; e < (size_t)n * T; e += nthr) {
                 size_t i = e / T, c = e % T;
                 rb.dead[(size_t)(ndead + i) * T + c] = __ldcg(rb.live + (size_t)sval[i] * T + c);
             }
-            if (tid == 0) { st->ndead = ndead + n; st->K = 0; st->status = ST_DONE; }
+            if (tid == 0) { st->ndead = ndead + n; st->K = 0; st->B = 0; st->status = ST_DONE; }
             return false;
         }
-        __syncthreads();
-        for (int i = tid; i < K; i += nthr) sm.kkey[i] = skey[i];
-        __syncthreads();
     }
     long long q3 = clock64();
     const double lX_new = logX_after(st->logX, K, n, sc);
     if (tid == 0) {
+        const double Lstar = newk[K - 1];
+        // births: the live count moves towards its target above the contour, at most 2 batch_K a generation
+        // (constant target: B = K; the batched form of run_time_info.f90:766-777)
+        int B = trim ? 0 : max(0, min(max(target_nlive(p, Lstar), 1) - (n - K), 2 * p.batch_K));
+        if (p.sh.world > 1) B = K;   // a sharded run keeps the live count fixed
         st->K = K;
-        st->Lstar = sm.kkey[K - 1];
+        st->B = B;
+        st->n_gen = n;
+        st->trimmed = 1;
+        st->holes_due = (B != K) ? 1 : 0;
+        st->nfail_gen = 0u;
+        st->Lstar = Lstar;
         st->order_off = (int)(newo - rb.order);
         st->order_valid = 1;
         st->ndead_base = ndead;
         st->ndead = ndead + K;
         st->nph_base = st->nphantom;
-        const int Kloc = p.sh.world > 1 ? (K - p.sh.rank + p.sh.world - 1) / p.sh.world : K;  // chains of this rank
-        st->nphantom += (long long)Kloc * (p.cp.R - 1);
-        st->nph_glob += (long long)K * (p.cp.R - 1);
+        const int Bloc = p.sh.world > 1 ? (B - p.sh.rank + p.sh.world - 1) / p.sh.world : B;  // chains of this rank
+        st->nphantom += (long long)Bloc * (p.cp.R - 1);
+        st->nph_glob += (long long)B * (p.cp.R - 1);
         st->nchains_base = st->nchains;
-        st->nchains += K;
-        st->ngen += 1;
-        st->nslices += (long long)K * p.cp.R;
-        st->do_update = (lX_new <= st->logX_last_update + p.log_comp) ? 1 : 0;  // nested_sampling.F90:321
+        st->nchains += B;
+        if (!trim) st->ngen += 1;
+        st->nslices += (long long)B * p.cp.R;
+        st->do_update = (!trim && lX_new <= st->logX_last_update + p.log_comp) ? 1 : 0;  // nested_sampling.F90:321
         st->status = ST_RUNNING;
         st->pub[0] = (unsigned long long)__double_as_longlong(st->Lstar);
         st->pub[1] = (unsigned long long)st->ndead_base;
@@ -253,18 +380,18 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
         st->pub[5] = (unsigned long long)(unsigned)st->K | ((unsigned long long)(unsigned)st->do_update << 32);
         st->pub[6] = (unsigned long long)(unsigned)st->order_off | ((unsigned long long)(unsigned)st->cur_pool << 32);
         st->pub[7] = (unsigned long long)(unsigned)st->ncl | ((unsigned long long)(unsigned)st->nupdates << 32);
+        st->pub[8] = (unsigned long long)(unsigned)n | ((unsigned long long)(unsigned)B << 32);
         long long q4 = clock64();
         st->dbg[6] += q1 - q0; st->dbg[7] += q2 - q1; st->dbg[8] += q3 - q2; st->dbg[9] += q4 - q3;
     }
     return true;
 }
 
-// S2: update_evidence (run_time_info.f90:211-296) for the K deaths of the generation just published
+// S2: update_evidence (run_time_info.f90:211-296) for the K deaths of the generation just published; their keys are the
+// head of the order phase S1 wrote
 __device__ inline void phase_S2(const KParams& p, const RunBuf& rb, DevRun* st, const SmemS& sm) {
-    long long q0 = clock64();
     const int K = st->K;
-    evidence_deaths(st, sm.kkey, K, p.n, rb.logw + st->ndead_base, sm.sc);
-    
+    evidence_deaths(st, rb.okey + st->order_off, K, st->n_gen, rb.logw + st->ndead_base, sm.sc);
 }
 
 // ---------------------------------------------------------------- phase U
@@ -354,7 +481,7 @@ __device__ inline void phase_UA(const KParams& p, const RunBuf& rb, DevRun* st, 
 __device__ inline void phase_UB(const KParams& p, const RunBuf& rb, DevRun* st, int cta, int NG, unsigned char* smem_warp0,
                                 int warp_bytes, int* s_cnt) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
-    const int D = p.cp.D, T = p.cp.T, n = p.n;
+    const int D = p.cp.D, T = p.cp.T, n = vload(&st->n);
     const int Dpad = (D + 1) & ~1;
     const int Dp8 = (D + 1 + 7) & ~7, SX = Dp8 + 4;   // row stride of the staged batch: SX mod 16 in {4, 12}, conflict-free fragments
     const int nt = Dp8 >> 3, ntl = nt * (nt + 1) / 2;  // 8-wide dimension tiles, tiles of the upper triangle
@@ -584,7 +711,7 @@ __device__ inline bool finish_update(const KParams& p, const RunBuf& rb, DevRun*
         Nglob = s_N;
     }
     __syncthreads();
-    const double N = (double)p.n + Nglob;
+    const double N = (double)st->n + Nglob;
     for (int e = tid; e < D; e += blockDim.x) {
         const double d = s_d[e] / N;
         s_d[e] = d;
@@ -681,11 +808,12 @@ __device__ inline bool publish_dump(const KParams& p, const RunBuf& rb, DevRun* 
     }
     __syncthreads();
     if (s_abort) return true;
-    const size_t nd = (size_t)p.n * p.cp.T;
+    const size_t nd = (size_t)st->n * p.cp.T;
     for (size_t e = threadIdx.x; e < nd; e += blockDim.x) rb.live_snap[e] = __ldcg(rb.live + e);
     __syncthreads();
     if (threadIdx.x == 0) {
         ctl->ndead = st->ndead;
+        ctl->nlive = st->n;
         ctl->nlike = st->nlike;
         ctl->logZ = st->logZ;
         ctl->logZ2 = st->logZ2;
@@ -718,7 +846,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
     DevRun* st = rb.st;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
     const int gw = cta * W + warp, GW = NG * W;
-    const int D = p.cp.D, T = p.cp.T, n = p.n, R = p.cp.R, LD = p.cp.LD;
+    const int D = p.cp.D, T = p.cp.T, R = p.cp.R, LD = p.cp.LD;
     const int c0 = p.chain_cta0, Gc = NG - c0;
 
     double* s_chol = (double*)smem;
@@ -726,7 +854,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
     unsigned char* s_warp0 = smem + p.off_warp;
     unsigned char* s_warp = s_warp0 + (size_t)warp * p.warp_bytes;
     // CTA-wide scratch of phase S overlays the per-warp area
-    const SmemS smS = smem_S(s_warp0, n, p.batch_K);
+    const SmemS smS = smem_S(s_warp0, p.nmax, p.batch_K);
     double* sc = smS.sc;
     int* s_cnt = (int*)(smem + p.off_warp - 64 * (int)sizeof(int));
 
@@ -777,6 +905,8 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                 shard_scatter(p, rb, st);
                 scatter_due = false;
             }
+            // births that failed, slots left empty (B != K): the live set is made contiguous again before anything reads it
+            if (st->holes_due || vload(&st->nfail_gen)) { settle_generation(p, rb, st, s_warp0, true); __syncthreads(); }
             long long t1 = clock64();
             bool dump_exit = false, cluster_exit = false;
             if (st->update_pending) {
@@ -810,9 +940,9 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
         if (ctimer) st->dbg[10] += tg1 - tg0;
         // the run's status and the generation's parameters: one load per lane, one latency
         unsigned long long pw = 0;
-        if (lane < 8) pw = __ldcg(&st->pub[lane]);
-        else if (lane == 8) pw = (unsigned long long)(unsigned)vload(&st->status);
-        if ((int)__shfl_sync(FULL, pw, 8) != ST_RUNNING) {
+        if (lane < 9) pw = __ldcg(&st->pub[lane]);
+        else if (lane == 9) pw = (unsigned long long)(unsigned)vload(&st->status);
+        if ((int)__shfl_sync(FULL, pw, 9) != ST_RUNNING) {
             if (timer) st->cyc_total += clock64() - t_start;
             return;
         }
@@ -829,11 +959,14 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
         }
         const bool sharded = p.sh.world > 1;
         const int xw = sharded ? p.sh.world : 1, xr = sharded ? p.sh.rank : 0;
-        if (sharded) {  // the dying points move to the (replicated) dead list (run_time_info.f90:789-817): one record per warp
-            const int K_ = vload(&st->K);
-            const long long nb = vload(&st->ndead_base);
-            const int* ord = rb.order + vload(&st->order_off);
-            for (int k = gw; k < K_; k += GW) {
+        {   // The dying points move to the dead list (run_time_info.f90:789-817).  A chain copies the point whose slot its
+            // baby takes (before it writes there); the deaths without a chain of their own -- all of them in a sharded
+            // run, whose last babies arrive through the incoming buffers, and those beyond the B births when the live
+            // count shrinks -- are copied here, one record per warp.
+            const int K_ = (int)(unsigned)__shfl_sync(FULL, pw, 5), B_ = (int)(__shfl_sync(FULL, pw, 8) >> 32);
+            const long long nb = (long long)__shfl_sync(FULL, pw, 1);
+            const int* ord = rb.order + (int)(unsigned)__shfl_sync(FULL, pw, 6);
+            for (int k = (sharded ? 0 : B_) + gw; k < K_; k += GW) {
                 const int slot = __ldcg(ord + k);
                 for (int e = lane; e < T; e += 32) rb.dead[(size_t)(nb + k) * T + e] = __ldcg(rb.live + (size_t)slot * T + e);
             }
@@ -841,7 +974,9 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
 
         // ---------------- phase C: chains, one warp each ----------------
         const unsigned long long w5 = __shfl_sync(FULL, pw, 5), w6 = __shfl_sync(FULL, pw, 6), w7 = __shfl_sync(FULL, pw, 7);
-        const int K = (int)(unsigned)w5;
+        const int K = (int)(unsigned)w5;                       // deaths of the generation
+        const unsigned long long w8 = __shfl_sync(FULL, pw, 8);
+        const int n = (int)(unsigned)w8, B = (int)(w8 >> 32);  // live points at its start, births (chains)
         const double Lstar = __longlong_as_double((long long)__shfl_sync(FULL, pw, 0));
         const long long ndead_base = (long long)__shfl_sync(FULL, pw, 1), nph_base = (long long)__shfl_sync(FULL, pw, 2);
         const long long nchains_base = (long long)__shfl_sync(FULL, pw, 3);
@@ -873,9 +1008,9 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                 constexpr int GD = G * DPL;
                 const int grp = lane / G, sub = lane % G;
                 double* gblocks = rb.nh + (size_t)gw * NPT * R * SLB;   // the slice records of this warp's chains
-                for (int base = gw * NPT; base < K; base += GW * NPT) {
+                for (int base = gw * NPT; base < B; base += GW * NPT) {
                     // directions of the pass's chains, one chain at a time through the warp's shared-memory scratch
-                    for (int g = 0; g < NPT && base + g < K; ++g) {
+                    for (int g = 0; g < NPT && base + g < B; ++g) {
                         const unsigned long long uidg = (unsigned long long)(nchains_base + base + g);
                         prep_chain<GD>(D, R, LD, rb.seed, uidg, cs, &p.cp);
                         const double* Lf = s_chol;
@@ -889,19 +1024,19 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                     }
                     __syncwarp();
                     const int k = base + grp;
-                    const bool active = k < K;
-                    const int kc = min(k, K - 1);
+                    const bool active = k < B;
+                    const int kc = min(k, B - 1);
                     const unsigned long long uid = (unsigned long long)(nchains_base + kc);
                     const double u = uniform(rb.seed, TAG_SEED, uid, 0u, 0u);  // GenerateSeed, generate.F90:19-55
                     const int choice = max(1, min(m, (int)ceil(u * (double)m)));
                     const int src = __ldcg(order + K + choice - 1);
-                    const int dslot = __ldcg(order + kc);
+                    const int dslot = kc < K ? __ldcg(order + kc) : n + (kc - K);   // a vacated slot, or one appended (the live count grows)
                     const int plab = clustered ? min(__ldcg(rb.lab + src), MAX_CLUSTERS - 1) : 0;
                     double x[DPL];
 #pragma unroll
                     for (int j = 0; j < DPL; ++j) x[j] = M.valid(j) ? __ldcg(rb.live + (size_t)src * T + M.dim(j)) : 0.0;
                     // the dying point moves to the dead list before its slot is reused (run_time_info.f90:789-817)
-                    if (active)
+                    if (active && k < K)
                         for (int e = sub; e < T; e += G)
                             rb.dead[(size_t)(ndead_base + k) * T + e] = __ldcg(rb.live + (size_t)dslot * T + e);
                     __syncwarp();
@@ -914,7 +1049,11 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                         for (int e = sub; e < R - 1; e += G) rb.phl[cur_pool_now][nph_base + (long long)k * (R - 1) + e] = plab;
                         if (sub == 0) rb.lab[dslot] = plab;
                     }
-                    if (active && sub == 0 && !(lfin > Lstar)) ++nfail;
+                    if (active && sub == 0) {   // a failed birth: settle_generation takes it out of the live set
+                        const int failed = !(lfin > Lstar);
+                        rb.cfail[k] = failed;
+                        if (failed) { ++nfail; atomicAdd(&st->nfail_gen, 1u); }
+                    }
                 }
                 // the per-group counts (on the groups' first lanes) -> lane 0
                 nlike = (unsigned long long)warp_sum_int((int)nlike);
@@ -928,7 +1067,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
             const bool helper = warp >= HW;
             int nmine = 0;
             if (cta >= c0)
-                for (int li = pair; ((cta - c0) + Gc * li) * xw + xr < K; li += HW) ++nmine;
+                for (int li = pair; ((cta - c0) + Gc * li) * xw + xr < B; li += HW) ++nmine;
             auto buf = [&](unsigned sq) -> ChainScratch {
                 const int region = pair + HW * (int)(sq & 1u);
                 return chain_scratch(s_warp0 + (size_t)region * p.warp_bytes, D, R, LD, p.nh_in_smem != 0, p.cp.like_kind,
@@ -957,12 +1096,12 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");  // hand-over of the buffer
                 if (ctimer && j == 0) st->dbg[21] += clock64() - ts_b;   // wait for the helper's hand-over
                 if (!helper) {
-                    const int dslot = __ldcg(order + k);
+                    const int dslot = k < K ? __ldcg(order + k) : n + (k - K);   // a vacated slot, or one appended (the live count grows)
                     double x[DPL];
 #pragma unroll
                     for (int jj = 0; jj < DPL; ++jj) x[jj] = M.valid(jj) ? __ldcg(rb.live + (size_t)src * T + M.dim(jj)) : 0.0;
                     // the dying point moves to the dead list before its slot is reused (run_time_info.f90:789-817)
-                    if (!sharded)
+                    if (!sharded && k < K)
                         for (int e = lane; e < T; e += 32)
                             rb.dead[(size_t)(ndead_base + k) * T + e] = __ldcg(rb.live + (size_t)dslot * T + e);
                     double* last = sharded ? xin_mine + (size_t)k * T : rb.live + (size_t)dslot * T;
@@ -977,7 +1116,11 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                         if (lane == 0) rb.lab[dslot] = plab;
                     }
                     if (ctimer) st->cyc_slice += clock64() - tc2;
-                    if (!(lfin > Lstar)) ++nfail;
+                    if (lane == 0) {   // a failed birth: settle_generation takes it out of the live set
+                        const int failed = !(lfin > Lstar);
+                        if (!sharded) rb.cfail[k] = failed;
+                        if (failed) { ++nfail; if (!sharded) atomicAdd(&st->nfail_gen, 1u); }
+                    }
                 }
             }
             pair_seq += (unsigned)nmine;
@@ -986,18 +1129,18 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
             for (int li = warp;; li += W) {
                 const int cl = (cta - c0) + Gc * li;
                 const int k = cl * xw + xr;
-                if (k >= K) break;
+                if (k >= B) break;
                 const unsigned long long uid = (unsigned long long)(nchains_base + k);
                 double u = uniform(rb.seed, TAG_SEED, uid, 0u, 0u);  // GenerateSeed, generate.F90:19-55
                 int choice = (int)ceil(u * (double)m);
                 choice = max(1, min(m, choice));
                 const int src = __ldcg(order + K + choice - 1);
-                const int dslot = __ldcg(order + k);
+                const int dslot = k < K ? __ldcg(order + k) : n + (k - K);   // a vacated slot, or one appended (the live count grows)
                 double x[DPL];
 #pragma unroll
                 for (int j = 0; j < DPL; ++j) x[j] = M.valid(j) ? __ldcg(rb.live + (size_t)src * T + M.dim(j)) : 0.0;
                 // the dying point moves to the dead list before its slot is reused (run_time_info.f90:789-817)
-                if (!sharded)
+                if (!sharded && k < K)
                     for (int e = lane; e < T; e += 32)
                         rb.dead[(size_t)(ndead_base + k) * T + e] = __ldcg(rb.live + (size_t)dslot * T + e);
                 double* last = sharded ? xin_mine + (size_t)k * T : rb.live + (size_t)dslot * T;
@@ -1023,7 +1166,11 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                     long long tc3 = clock64();
                     st->cyc_prep += tc1 - tc0; st->cyc_white += tc2 - tc1; st->cyc_slice += tc3 - tc2;
                 }
-                if (!(lfin > Lstar)) ++nfail;
+                if (lane == 0) {   // a failed birth: settle_generation takes it out of the live set
+                    const int failed = !(lfin > Lstar);
+                    if (!sharded) rb.cfail[k] = failed;
+                    if (failed) { ++nfail; if (!sharded) atomicAdd(&st->nfail_gen, 1u); }
+                }
             }
             if (cta != 0 && ((cta - c0) + Gc * warp) * xw + xr < p.batch_K) knext = ((cta - c0) + Gc * warp) * xw + xr;
         }
@@ -1044,6 +1191,14 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
             long long tu0 = clock64();
             warp_wait(&st->wbar, wtarget, p.backoff);
             long long tu1 = clock64();
+            // failed births / empty slots: the live set is made contiguous before the covariance reads it (every warp
+            // sees the same flags after the barrier)
+            if (vload(&st->holes_due) || vload(&st->nfail_gen)) {
+                if (cta == 0) { __syncthreads(); settle_generation(p, rb, st, s_warp0, false); }
+                group_sync(&st->bar, NG, p.backoff);
+                // every warp of the run has read the flags by now: clear them (the next reader is CTA 0's next phase S)
+                if (cta == 0 && tid == 0) { st->holes_due = 0; st->nfail_gen = 0u; }
+            }
             if (sharded) {  // the covariance is over the live points including this generation's babies
                 if (cta == 0) { __syncthreads(); shard_scatter(p, rb, st); }
                 scatter_due = false;
@@ -1062,12 +1217,12 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
             if (timer) { st->cyc_wait += tu1 - tu0; st->cyc_U += clock64() - tu1; st->dbg[5] += clock64(); }
             have_wtarget = false;
             if (will_chain) {  // the Cholesky factor is about to change: whiten after the barrier
-                prep_uid = (unsigned long long)(nchains_base + K + knext);
+                prep_uid = (unsigned long long)(nchains_base + B + knext);
                 prep_chain<G * DPL>(D, R, LD, rb.seed, prep_uid, csn, &p.cp);
                 prep_white = false;
             }
         } else if (will_chain) {
-            prep_uid = (unsigned long long)(nchains_base + K + knext);
+            prep_uid = (unsigned long long)(nchains_base + B + knext);
             prep_chain<G * DPL>(D, R, LD, rb.seed, prep_uid, csn, &p.cp);
             prep_white = false;
             if (!p.clustering) {  // with clusters the factor depends on the chain's seed, which the next phase S decides

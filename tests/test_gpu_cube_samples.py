@@ -63,11 +63,32 @@ def test_device_run_from_given_live_points_matches_the_oracle(gpu, oracle):
     assert info2.status == 0 and not np.array_equal(np.sort(born2[:, :D], axis=0), np.sort(cubes, axis=0))
 
 
-def test_wrong_number_of_points_is_an_error(gpu):
+def test_another_number_of_points_is_absorbed_by_the_live_count(gpu, oracle):
+    """polychord.py:650-789 writes whatever points it is given into the resume file and the reference's dynamic-nlive rule
+    (run_time_info.f90:766-777) brings the count to nlive; here: the batched form of that rule (phase S1)."""
+    cubes = _cubes()[:60]
     L = gpu.lib()
-    gpu.set_initial_live(_cubes()[: N - 1])
+    gpu.set_initial_live(cubes)
     info = _c_interface(gpu, L.pc_gaussian_loglikelihood, L.pc_unit_prior, None, seed=5)
-    assert info.status == -2
+    assert info.status == 0
+    oracle.set_initial_cubes(cubes)
+    oi, _ = oracle.run(oracle.make_settings(D, P, nlive=N, num_repeats=R, seed=5, batch_K=K))
+    assert (info.ndead, info.nlike, info.nupdates, info.nchains) == (oi.ndead, oi.nlike, oi.nupdates, oi.nchains)
+    assert abs(info.logZ - oi.logZ) < 1e-7
+
+
+def test_cube_samples_win_over_a_stale_resume_file(gpu, tmp_path):
+    """pypolychord.run defaults to read_resume = write_resume = True: an earlier run's <root>.resume must not shadow the
+    caller's starting points (the reference overwrites the resume file with them, polychord.py:576-579)."""
+    from polychordlite_b200.pypolychord.builtin import Gaussian
+    kw = dict(nDerived=P, nlive=N, num_repeats=R, seed=2, feedback=0, base_dir=str(tmp_path), file_root="rs",
+              do_clustering=False, _legacy_output=True)
+    pypolychord.run(Gaussian(0.5, 0.1, nDerived=P), D, **kw)          # leaves rs.resume behind
+    assert (tmp_path / "rs.resume").exists()
+    cubes = _cubes(4)
+    out = pypolychord.run(Gaussian(0.5, 0.1, nDerived=P), D, cube_samples=cubes, **kw)
+    born = out.theta[out.logL_birth <= -1e29]
+    assert len(born) == N and np.array_equal(np.sort(born, axis=0), np.sort(cubes, axis=0))
 
 
 def test_pypolychord_keyword_with_a_python_likelihood(gpu, tmp_path):
@@ -82,6 +103,6 @@ def test_pypolychord_keyword_with_a_python_likelihood(gpu, tmp_path):
                           _legacy_output=True)
     born = out.theta[out.logL_birth <= -1e29]
     assert len(born) == N and np.array_equal(np.sort(born, axis=0), np.sort(cubes, axis=0))   # default prior: theta = cube
-    with pytest.raises(ValueError):
-        pypolychord.run(likelihood, D, nDerived=P, nlive=N, num_repeats=R, cube_samples=cubes[:10], feedback=0,
+    with pytest.raises(ValueError):   # points of another dimension
+        pypolychord.run(likelihood, D, nDerived=P, nlive=N, num_repeats=R, cube_samples=cubes[:, :D - 1], feedback=0,
                         base_dir=str(tmp_path), file_root="cs2", _legacy_output=True)
