@@ -185,6 +185,11 @@ typedef struct pc_run_info {
     long long ncluster_max;     /* do_clustering: largest number of clusters an update found, and the number of */
     long long ncluster_updates; /* updates that ran the clustering pass */
     double cluster_ms;          /* wall time of the clustering passes (their kernels are not part of device_ms) */
+    /* the run kernel that was dispatched: pc_run_kernel<G, DPL, KIND, MODE> -- G lanes per trial point, DPL dimensions
+     * per lane, likelihood kind, 0 = a chain per warp / 1 = the dense chain phase (a chain per point group) */
+    int kernel_G, kernel_DPL, kernel_kind, kernel_mode;
+    int nlive_final;            /* live points when the sampling loop ended (dynamic nlive) */
+    int pad_;
 } pc_run_info;
 
 /* Results of the most recent polychord_c_interface()/pc_run() in this process. */

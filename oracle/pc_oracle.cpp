@@ -1215,7 +1215,7 @@ struct Run {
     // appended; a FAILED birth (last baby not above the contour: stale or non-deterministic likelihood) does not become
     // a live point -- it goes to the dead list with log-weight logzero, as replace_point does (run_time_info.f90:
     // 781-785) -- and counts towards nfail (nested_sampling.F90:315-319).  Slots left empty (vacated and not refilled,
-    // or reserved for a failed birth) are closed from the top down by moving the last record in.
+    // or reserved for a failed birth) are closed by moving the records beyond the new count into them.
     // Returns the number of failed births.
     int failures_in_a_row = 0;
     int batched_generation(int K, int B, std::vector<double>& babies) {
@@ -1290,14 +1290,21 @@ struct Run {
             if (labelled) lab.push_back(newlab[k]);
             c.nlive++;
         }
-        std::sort(holes.begin(), holes.end(), std::greater<int>());
-        for (int sl : holes) {          // close the empty slots, highest first
-            const int lastp = c.nlive - 1;
-            if (sl != lastp) {
-                std::copy(c.live.begin() + (size_t)lastp * T, c.live.begin() + (size_t)(lastp + 1) * T, c.live.begin() + (size_t)sl * T);
-                if (labelled) lab[sl] = lab[lastp];
+        // close the empty slots: with n' = extent - holes live points left, the records at or above n' move into the
+        // empty slots below it, lowest into lowest (a rule every slot can apply by itself)
+        {
+            const int ext = c.nlive, n1 = ext - (int)holes.size();
+            std::vector<char> empty(ext, 0);
+            for (int sl : holes) empty[sl] = 1;
+            int src = n1;
+            for (int dst = 0; dst < n1; ++dst) {
+                if (!empty[dst]) continue;
+                while (empty[src]) ++src;
+                std::copy(c.live.begin() + (size_t)src * T, c.live.begin() + (size_t)(src + 1) * T, c.live.begin() + (size_t)dst * T);
+                if (labelled) lab[dst] = lab[src];
+                ++src;
             }
-            c.nlive--;
+            c.nlive = n1;
         }
         c.live.resize((size_t)c.nlive * T);
         if (labelled) lab.resize(c.nlive);

@@ -51,7 +51,14 @@ class RunInfo(C.Structure):
         ("device_ms", C.c_double), ("wall_ms", C.c_double), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong),
         ("algorithmic_bytes", C.c_longlong), ("phase_ms", C.c_double * 8),
         ("ncluster_max", C.c_longlong), ("ncluster_updates", C.c_longlong), ("cluster_ms", C.c_double),
+        ("kernel_G", C.c_int), ("kernel_DPL", C.c_int), ("kernel_kind", C.c_int), ("kernel_mode", C.c_int),
+        ("nlive_final", C.c_int), ("pad_", C.c_int),
     ]
+
+    @property
+    def kernel(self):
+        """Name of the run kernel that was dispatched (as ncu lists it)."""
+        return f"pc_run_kernel<{self.kernel_G},{self.kernel_DPL},{self.kernel_kind},{self.kernel_mode}>"
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}

@@ -337,8 +337,8 @@ __device__ inline void prep_chain(int D, int R, int LD, unsigned seed, unsigned 
         //     vector i on q_0..q_{i-1} are taken from the raw vector, then subtracted together.
         const int nb = (Rg + Dg - 1) / Dg;
         const int B = nb >= 4 ? 4 : (nb >= 2 ? 2 : 1);
-        const int LB = 32 / B;
-        const int sl = lane % LB, bslot = lane / LB;
+        const int lbs = B >= 4 ? 3 : (B >= 2 ? 4 : 5), LB = 1 << lbs;   // lanes per basis (a power of two: no integer division)
+        const int sl = lane & (LB - 1), bslot = lane >> lbs;
         double* dots = cs.dots + bslot * Dpad;
         const bool unrolled = GD > 0 && roff == 0 && D <= GD && LD >= GD;   // padding rows are zero: sum over GD rows
         for (int b0 = 0; b0 < nb; b0 += B) {

@@ -159,51 +159,46 @@ __device__ inline void slice_chains_dense(const ChainParams& p, const Model<G, D
         const bool run = phase != SP_DONE;
         if (run && sub == 0 && l > logzero) ++nlike;
         const bool inside = l >= Lstar && l > logzero;
-        bool fin = false;
-        double lnew = logzero;
-        if (run) {
-            auto next_draw = [&]() {  // baby = x0 + (u*(x0Rd + x0Ld) - x0Ld)*nhat (:247)
-                const int sidx = 1 + s_done;
-                const double u = sidx < NU ? stage[(slice & 1) * SLB + GD + 1 + sidx]
-                                           : slow_uniform(seed, uid, (unsigned)slice, (unsigned)sidx);
-                t = fma(u, wd, a);
-            };
-            auto begin_shrink = [&]() {
-                a = -dL; b = dR; wd = dR + dL;
-                phase = SP_SHRINK;
-                s_done = 0;
-                next_draw();
-            };
-            if (phase == SP_SHRINK) {  // (:240-266)
-                if (inside) { fin = true; lnew = l; }
-                else {
-                    const bool pos = __double2hiint(t) > 0;  // sign of (baby - x0).nhat picks the bound to move (:254-262)
-                    const double wpos = t - a, wneg = b - t;
-                    wd = pos ? wpos : wneg;
-                    a = pos ? a : t;
-                    b = pos ? t : b;
-                    s_done += 1;
-                    if (s_done >= 101) fin = true;   // "Non deterministic loglikelihood" (:268-271): kept with logL = logzero
-                    else next_draw();
-                }
-            } else if (phase == SP_R0) {
-                lR = l;
-                phase = SP_L0;
-                t = -dL;
-            } else if (phase == SP_L0) {
-                lL = l;
-                if (lR >= Lstar && lR > logzero) { phase = SP_OUT_R; istep = 1; dR = w; t = dR; }
-                else if (inside) { phase = SP_OUT_L; istep = 1; dL = w; t = -dL; }
-                else begin_shrink();
-            } else if (phase == SP_OUT_R) {  // R = x0 + nhat*w*i while inside (:223-227)
-                if (inside) { istep += 1; dR = w * (double)istep; t = dR; }
-                else if (lL >= Lstar && lL > logzero) { phase = SP_OUT_L; istep = 1; dL = w; t = -dL; }
-                else begin_shrink();
-            } else {  // SP_OUT_L (:232-236)
-                if (inside) { istep += 1; dL = w * (double)istep; t = -dL; }
-                else begin_shrink();
-            }
+        // slice_sample's state machine (:213-266), one step, written with selects: the groups of a warp sit in
+        // different phases, and divergent branches would make every round pay for all of them.
+        //   R0 -> L0 -> [step out right]* -> [step out left]* -> shrink ... -> accepted / given up
+        const bool in_R0 = phase == SP_R0, in_L0 = phase == SP_L0, in_OR = phase == SP_OUT_R, in_OL = phase == SP_OUT_L,
+                   in_SH = phase == SP_SHRINK;
+        lR = in_R0 ? l : lR;
+        lL = in_L0 ? l : lL;
+        const bool R_in = lR >= Lstar && lR > logzero, L_in = lL >= Lstar && lL > logzero;
+        // the right side keeps stepping out: entered from L0 when the right end was inside, continued while inside (:223-227)
+        const bool stepR = (in_L0 && R_in) || (in_OR && inside);
+        // the left side: entered when the right side is closed and the left end was inside, continued while inside (:232-236)
+        const bool stepL = !stepR && (((in_L0 || in_OR) && L_in) || (in_OL && inside));
+        const bool to_shrink = (in_L0 || in_OR || in_OL) && !stepR && !stepL;
+        const bool rejected = in_SH && !inside;
+        const bool fin_acc = in_SH && inside;
+        const int istep_n = ((in_OR && stepR) || (in_OL && stepL)) ? istep + 1 : 1;
+        const double wi = w * (double)istep_n;
+        if (stepR) { dR = wi; istep = istep_n; }
+        if (stepL) { dL = wi; istep = istep_n; }
+        // a rejected draw becomes the bound on its side: the sign of (baby - x0).nhat picks it (:254-262)
+        const bool pos = __double2hiint(t) > 0;
+        const double wpos = t - a, wneg = b - t;
+        if (rejected) {
+            wd = pos ? wpos : wneg;
+            a = pos ? a : t;
+            b = pos ? t : b;
+            s_done += 1;
         }
+        if (to_shrink) { a = -dL; b = dR; wd = dR + dL; s_done = 0; }
+        const bool gave_up = rejected && s_done >= 101;   // "Non deterministic loglikelihood" (:268-271): kept with logL = logzero
+        const bool draw = to_shrink || (rejected && !gave_up);
+        double u = 0.0;
+        if (draw) {  // baby = x0 + (u*(x0Rd + x0Ld) - x0Ld)*nhat (:247)
+            const int sidx = 1 + s_done;
+            u = sidx < NU ? stage[(slice & 1) * SLB + GD + 1 + sidx] : slow_uniform(seed, uid, (unsigned)slice, (unsigned)sidx);
+        }
+        t = in_R0 ? -dL : (stepR ? dR : (stepL ? -dL : (draw ? fma(u, wd, a) : t)));
+        phase = !run ? SP_DONE : in_R0 ? SP_L0 : stepR ? SP_OUT_R : stepL ? SP_OUT_L : SP_SHRINK;
+        const bool fin = run && (fin_acc || gave_up);
+        const double lnew = fin_acc ? l : logzero;
         if (__ballot_sync(FULL, fin)) {
             cp_async_wait_all();   // the next slice's record (issued at least three rounds ago)
             __syncwarp();

@@ -1462,6 +1462,8 @@ struct Engine {
                 std::fprintf(stderr, "[pc dbg cluster] %lld passes, %.3f ms in all, %.3f ms of it labelling (kNN kernel + union-find), up to %lld clusters\n",
                              ncluster_updates, cluster_ms, cluster_label_ms, ncluster_max);
             o.batch_K = k.batch_K; o.warps_per_cta = L.W; o.ctas_per_run = G; o.kernel_launches = launches;
+            o.kernel_G = L.fn.G; o.kernel_DPL = L.fn.DPL; o.kernel_kind = L.fn.KIND; o.kernel_mode = k.dense;
+            o.nlive_final = s.n;
             o.device_ms = device_ms;
             o.wall_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
             o.h2d_bytes = h2d; o.d2h_bytes = d2h;

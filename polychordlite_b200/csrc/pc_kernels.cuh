@@ -221,7 +221,7 @@ __device__ __forceinline__ void group_sync(unsigned int* bar, unsigned int G, in
         for (;;) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
             if ((int)(v - target) >= 0) break;
-            if (backoff) __nanosleep(backoff);   // an ensemble shares the SM: do not burn issue slots polling
+            if (backoff) { __nanosleep(backoff); if (backoff < 4096) backoff <<= 1; }   // an ensemble shares the SM: do not burn issue slots polling
         }
         __threadfence();
     }
@@ -264,7 +264,7 @@ __device__ __forceinline__ void warp_wait(unsigned int* wbar, unsigned int targe
         for (;;) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(wbar) : "memory");
             if ((int)(v - target) >= 0) break;
-            if (backoff) __nanosleep(backoff);
+            if (backoff) { __nanosleep(backoff); if (backoff < 4096) backoff <<= 1; }
         }
         __threadfence();
     }
@@ -470,18 +470,22 @@ __device__ inline int warp_cholesky(const double* a, double* L, int D) {
     for (int e = lane; e < D * D; e += 32) L[e] = 0.0;
     __syncwarp();
     int fallback = 0;
-    for (int i = 0; i < D; ++i) {
-        double s = 0.0;
-        for (int k = 0; k < i; ++k) s += L[i + k * D] * L[i + k * D];
-        double dii = a[i + i * D] - s;
-        if (dii <= 0.0) { fallback = 1; break; }
-        dii = sqrt(dii);
-        __syncwarp();
-        if (lane == 0) L[i + i * D] = dii;
-        for (int j = i + 1 + lane; j < D; j += 32) {
+    // Column i in one parallel step: lane l takes row j = i + l (+32, ...) and forms sum_k<i L[i,k] L[j,k] in the order
+    // of the reference's loops; lane 0's row is the diagonal itself, whose square root is handed round by a shuffle.
+    for (int i = 0; i < D && !fallback; ++i) {
+        double dii = 0.0;
+        for (int j0 = i; j0 < D; j0 += 32) {
+            const int j = j0 + lane;
             double t = 0.0;
-            for (int k = 0; k < i; ++k) t += L[i + k * D] * L[j + k * D];
-            L[j + i * D] = (a[i + j * D] - t) / dii;
+            if (j < D)
+                for (int k = 0; k < i; ++k) t += L[i + k * D] * L[j + k * D];
+            if (j0 == i) {
+                const double d = __shfl_sync(FULL, a[i + i * D] - t, 0);
+                if (d <= 0.0) { fallback = 1; break; }
+                dii = sqrt(d);
+                if (lane == 0) L[i + i * D] = dii;
+            }
+            if (j < D && j > i) L[j + i * D] = (a[i + j * D] - t) / dii;
         }
         __syncwarp();
     }

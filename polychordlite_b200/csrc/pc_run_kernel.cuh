@@ -85,7 +85,7 @@ __device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st
 // precision_criterion, nested_sampling.F90:538), the order of the n live points by (logL, slot), the K lowest die:
 // contour, number of births, bases, update decision.  The order is maintained incrementally: the n-K survivors of a
 // regular generation (K deaths, K successful births into the vacated slots) are still sorted, so only the K new babies
-// are sorted and the two lists are merged by rank (binary searches).  The first generation, and one that follows a
+// are sorted (bitonic) and the two lists are merged by rank (binary searches).  The first generation, and one that follows a
 // generation that moved live points (settle_generation), sorts everything.
 // S2 (off the critical path when CTA 0 only keeps the books): the evidence recurrences of the K deaths.
 // log X after `count` deaths from n_start live points: the same chunked sum evidence_deaths forms
@@ -115,9 +115,9 @@ __device__ inline int target_nlive(const KParams& p, double contour) {
 // The generation just finished left empty live slots: vacated slots without a birth (B < K), or births that FAILED
 // (last baby not above the contour: a non-deterministic or plateau likelihood).  As replace_point (run_time_info.f90:
 // 781-785) a failed baby does not become a live point: it goes to the dead list with log-weight logzero, in chain
-// order, and counts towards nfail (nested_sampling.F90:315-319).  The empty slots are then closed from the top down by
-// moving the last record in -- in closed form: with n' = extent - holes, the occupied slots >= n' fill the holes < n',
-// the j-th lowest into the j-th lowest.  CTA 0; smem: the phase-S area.
+// order, and counts towards nfail (nested_sampling.F90:315-319).  The empty slots are then closed: with n' = extent -
+// holes live points left, the occupied slots >= n' fill the holes < n', the j-th lowest into the j-th lowest (the rule
+// the oracle's batched_generation applies).  CTA 0; smem: the phase-S area.
 __device__ inline void settle_generation(const KParams& p, const RunBuf& rb, DevRun* st, unsigned char* smem_raw, bool clear_flags) {
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, W = nthr >> 5, T = p.cp.T;
     const int K = st->K, B = st->B, n0 = st->n_gen;
@@ -261,32 +261,8 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
     }
     long long q2 = clock64();
     if (merge && more) {
-        // the babies in order.  Up to two per thread: each counts the babies before it (the keys are read as
-        // broadcasts, no barrier between the steps); more: bitonic sort in shared memory.
-        if (Kp <= 2 * nthr) {
-            double mk[2];
-            int mv[2], rk[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int j = tid + h * nthr;
-                mk[h] = j < Kp ? sm.bkey[j] : INFINITY;
-                mv[h] = j < Kp ? sm.bval[j] : 0x7fffffff;
-                rk[h] = 0;
-            }
-            for (int j = 0; j < Kp; ++j) {
-                const double kj = sm.bkey[j];
-                const int vj = sm.bval[j];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) rk[h] += (kj < mk[h] || (kj == mk[h] && vj < mv[h])) ? 1 : 0;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-                if (tid + h * nthr < Kp) { sm.bkey[rk[h]] = mk[h]; sm.bval[rk[h]] = mv[h]; }
-            __syncthreads();
-        } else {
-            block_sort(sm.bkey, sm.bval, npB);
-        }
+        // the babies in order: bitonic, one element per thread with warp shuffles below distance 32 when they fit
+        if (npB <= (int)blockDim.x) block_sort_small(sm.bkey, sm.bval, npB); else block_sort(sm.bkey, sm.bval, npB);
         // rank of a survivor = its index + number of babies before it; rank of a baby = its index + number of
         // survivors before it ((key, slot) pairs are distinct, so the merged order is the sorted order)
         for (int i = tid; i < m; i += nthr) {
@@ -882,6 +858,13 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
     if (p.host_like && vload(&st->host_resume)) {
         // host-callback run: the host loop ran the chains of the generation in flight; finish the generation
         // (phase U at the update cadence) exactly where the chain phase would have left it
+        // (failed births / empty slots of that generation first: the covariance reads a contiguous live set)
+        if (vload(&st->holes_due) || vload(&st->nfail_gen)) {
+            if (cta == 0) { __syncthreads(); settle_generation(p, rb, st, s_warp0, false); }
+            group_sync(&st->bar, NG, p.backoff);
+            if (cta == 0 && tid == 0) { st->holes_due = 0; st->nfail_gen = 0u; }
+            group_sync(&st->bar, NG, p.backoff);
+        }
         if (vload(&st->do_update)) {
             phase_UA(p, rb, st, cta, NG);
             group_sync(&st->bar, NG, p.backoff);

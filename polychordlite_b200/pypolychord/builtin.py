@@ -54,6 +54,8 @@ class Gaussian(_DeviceLikelihood):
         self.mu, self.sigma = mu, sigma
 
     def device_params(self, nDims):
+        if np.ndim(self.mu) == 0 and np.ndim(self.sigma) == 0:
+            return np.array([float(self.mu), float(self.sigma)])   # the engine's dimension-free form: every dimension alike
         mu = np.broadcast_to(np.asarray(self.mu, dtype=float), (nDims,))
         sg = np.broadcast_to(np.asarray(self.sigma, dtype=float), (nDims,))
         return np.concatenate([mu, sg])

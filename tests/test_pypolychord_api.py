@@ -113,9 +113,16 @@ def test_legacy_run_polychord(gpu, tmp_path):
 
 
 @pytest.mark.gpu
-def test_unsupported_configuration_raises(gpu, tmp_path):
-    with pytest.raises(RuntimeError):   # dynamic nlive schedules are reported, not silently ignored
-        pypolychord.run(Gaussian(), nDims, base_dir=str(tmp_path), nlives={-10.0: 400}, **KW)
+def test_nlives_schedule_and_grades_run(gpu, tmp_path):
+    """The `nlives` keyword (polychord.py:452; dynamic nlive, run_time_info.f90:766-777) reaches the engine: above the
+    contour -10 the run keeps 400 live points, so the final kill-off adds 400 dead points and more points die in all."""
+    KW2 = {**KW, "_legacy_output": True}
+    plain = pypolychord.run(Gaussian(mu=0.0, sigma=0.1), nDims, prior=UniformPrior(-1, 1), base_dir=str(tmp_path), seed=1, **KW2)
+    dyn = pypolychord.run(Gaussian(mu=0.0, sigma=0.1), nDims, prior=UniformPrior(-1, 1), base_dir=str(tmp_path), seed=1,
+                          nlives={-10.0: 400}, **KW2)
+    assert dyn.ndead > plain.ndead + 200 and abs(dyn.logZ - plain.logZ) < 0.6
+    with pytest.raises(RuntimeError):   # more entries than the engine's schedule holds are reported, not silently dropped
+        pypolychord.run(Gaussian(), nDims, base_dir=str(tmp_path), nlives={-float(i): 100 + i for i in range(20)}, **KW)
     ns = pypolychord.run(Gaussian(mu=0.0, sigma=0.1), nDims, prior=UniformPrior(-1, 1), base_dir=str(tmp_path),
                          grade_dims=[1, 3], seed=1, **KW)                                # fast/slow grades run
     assert ns.info["nslices"] == 2 * KW["num_repeats"] * ns.info["nchains"]
