@@ -1284,17 +1284,20 @@ struct Run {
                 if (labelled) lab[order[k]] = newlab[k];
             } else holes.push_back(order[k]);
         }
-        for (int k = K; k < B; ++k) {   // the live count grows: further births are appended
-            if (!ok[k]) continue;
-            c.live.insert(c.live.end(), newpts.begin() + (size_t)k * T, newpts.begin() + (size_t)(k + 1) * T);
-            if (labelled) lab.push_back(newlab[k]);
-            c.nlive++;
+        // the live count grows: birth k >= K takes slot n + (k - K); a failed one leaves that slot empty
+        const int ext = n + std::max(0, B - K);
+        c.live.resize((size_t)ext * T);
+        if (labelled) lab.resize(ext);
+        for (int k = K; k < B; ++k) {
+            if (!ok[k]) { holes.push_back(n + (k - K)); continue; }
+            std::copy(newpts.begin() + (size_t)k * T, newpts.begin() + (size_t)(k + 1) * T, c.live.begin() + (size_t)(n + k - K) * T);
+            if (labelled) lab[n + k - K] = newlab[k];
         }
         // close the empty slots: with n' = extent - holes live points left, the records at or above n' move into the
         // empty slots below it, lowest into lowest (a rule every slot can apply by itself)
         {
-            const int ext = c.nlive, n1 = ext - (int)holes.size();
-            std::vector<char> empty(ext, 0);
+            const int n1 = ext - (int)holes.size();
+            std::vector<char> empty(ext + 1, 0);
             for (int sl : holes) empty[sl] = 1;
             int src = n1;
             for (int dst = 0; dst < n1; ++dst) {

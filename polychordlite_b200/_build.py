@@ -42,14 +42,15 @@ def _deps(src):
 
 
 def build(force=False, verbose=False):
-    """One object per translation unit under polychordlite_b200/build/ (only the stale ones are recompiled, eight at a
-    time), then one link.  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo for every unit."""
+    """One object per translation unit (only the stale ones are recompiled, eight at a time), then one link.  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo for every unit."""
     if not force and not stale():
         return LIB
     from concurrent.futures import ThreadPoolExecutor
     LIBDIR.mkdir(exist_ok=True)
-    objdir = PKG / "build"
-    objdir.mkdir(exist_ok=True)
+    # the objects are scratch: they live under gpurun_out/ (git-ignored, never shipped to the GPU box -- only the linked
+    # library travels), or wherever PC_BUILD_DIR says
+    objdir = Path(os.environ.get("PC_BUILD_DIR", str(PKG.parent / "gpurun_out" / ".objs")))
+    objdir.mkdir(parents=True, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     flags = [f for f in NVCC_FLAGS if f not in ("-shared", "--threads", "8")]
     srcs = [p for p in sources() if p.name != SHIM_SRC.name]

@@ -421,6 +421,15 @@ static __device__ __noinline__ void boost_harvest(const KParams& p, const RunBuf
     rb.boost_win[slot] = win;
 }
 
+// A pool record survives an update when no death since the last one lies above it (clean_phantoms, run_time_info.f90:
+// 842-851: the deaths' largest logL is the contour) -- and when it was a phantom in the first place: replace_point only
+// keeps babies strictly above their birth contour (run_time_info.f90:746-757); on a likelihood with plateaus a baby can
+// sit on the contour itself.  The chains write every baby into the pool; the others are dropped here.
+__device__ __forceinline__ bool phantom_kept(const double* rec, int T, double Lstar) {
+    const double l = __ldcg(rec + T - 1);
+    return !(Lstar > l) && l > __ldcg(rec + T - 2);
+}
+
 __device__ inline void phase_UA(const KParams& p, const RunBuf& rb, DevRun* st, int cta, int NG) {
     const int tid = threadIdx.x, T = p.cp.T;
     const long long total = vload(&st->nphantom);
@@ -435,7 +444,7 @@ __device__ inline void phase_UA(const KParams& p, const RunBuf& rb, DevRun* st, 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const long long t = t0 + (long long)j * NG, rec = t * U_TILE + tid;
-            keep[j] = t < ntiles && rec < total && !(Lstar > __ldcg(src + (size_t)rec * T + T - 1));
+            keep[j] = t < ntiles && rec < total && phantom_kept(src + (size_t)rec * T, T, Lstar);
             if (boosting && t < ntiles && rec < total && !keep[j]) boost_harvest(p, rb, st, src + (size_t)rec * T, bwin);
         }
 #pragma unroll
@@ -528,7 +537,7 @@ __device__ inline void phase_UB(const KParams& p, const RunBuf& rb, DevRun* st, 
             bool keep;
             if (is_ph) {
                 const long long tile = t * U_TILE, rec = tile + tid;
-                keep = rec < total && !(Lstar > __ldcg(src + (size_t)rec * T + T - 1));
+                keep = rec < total && phantom_kept(src + (size_t)rec * T, T, Lstar);
                 rbase = src + (size_t)(tile + warp * 32) * T;
             } else {
                 const int lrec = l0 + (int)(it - my_tiles) * U_TILE + tid;
