@@ -145,8 +145,10 @@ struct MgpuCtx {
 };
 static MgpuCtx g_mgpu;
 static size_t mgpu_xstride(int D) { return (size_t)((2 + D + D * (D + 1) / 2 + 1) & ~1); }
+static size_t mgpu_kr(int batch_K, int world) { return (size_t)(batch_K + world - 1) / world; }
+// [barrier][incoming last babies][statistics slots][sorted (logL, slot) runs of every rank's babies, 2 x world x kr pairs]
 static size_t mgpu_block_bytes(int batch_K, int T, int D, int world) {
-    return 256 + (size_t)2 * batch_K * T * 8 + (size_t)world * mgpu_xstride(D) * 8;
+    return 256 + (size_t)2 * batch_K * T * 8 + (size_t)world * mgpu_xstride(D) * 8 + (size_t)2 * world * mgpu_kr(batch_K, world) * 16;
 }
 
 template <class V>
@@ -737,11 +739,13 @@ struct Engine {
             if (g_mgpu.batch_K != K || g_mgpu.T != k.cp.T || g_mgpu.D != k.cp.D)
                 throw pc::ArgError("polychord_b200: pc_mgpu_create was called with different settings than this run");
             k.sh.rank = g_mgpu.rank; k.sh.world = g_mgpu.world; k.sh.xstride = (long long)mgpu_xstride(k.cp.D);
+            k.sh.kr = (int)mgpu_kr(K, g_mgpu.world);
             for (int q = 0; q < g_mgpu.world; ++q) {
                 unsigned char* b = (unsigned char*)g_mgpu.peer[q];
                 k.sh.xbar[q] = (unsigned int*)b;
                 k.sh.xin[q] = (double*)(b + 256);
                 k.sh.xpart[q] = (double*)(b + 256 + (size_t)2 * K * k.cp.T * 8);
+                k.sh.xrun[q] = k.sh.xpart[q] + (size_t)g_mgpu.world * mgpu_xstride(k.cp.D);
             }
         }
         G = (sharded ? (K + g_mgpu.world - 1) / g_mgpu.world : K) + 1;

@@ -142,12 +142,17 @@ struct RunBuf {
 //          all-reduced by storing them into every rank's slot and summing in rank order;
 //   xbar   one monotonic counter per rank: a barrier adds `world` to each of them.
 constexpr int MAX_RANKS = 8;
+//   xrun   the order of the new babies is built from per-rank pieces: every rank sorts the last babies of ITS chains
+//          (K / world of them) and stores the sorted (logL, slot) run into every rank's run buffer (2 x world x kr
+//          pairs, by generation parity); phase S merges the `world` runs by rank counting instead of sorting K keys.
 struct Shard {
     int rank, world;
     long long xstride;                 // doubles per rank slot in xpart
+    int kr, pad;                       // pairs per rank in xrun: ceil(batch_K / world)
     unsigned int* xbar[MAX_RANKS];
     double* xin[MAX_RANKS];
     double* xpart[MAX_RANKS];
+    double* xrun[MAX_RANKS];
 };
 
 struct KParams {
@@ -402,6 +407,49 @@ __device__ inline void block_sort_small(double* key, int* val, int np2) {
         }
     }
     if (i < np2) { key[i] = mk; val[i] = mv; }
+    __syncthreads();
+}
+
+// The same network with TWO elements per thread (np2 = 2 * blockDim.x): thread i holds elements i and i + blockDim.x, so
+// the exchange at distance blockDim.x is a compare-exchange of its own two registers, distances below 32 are warp
+// shuffles and only distances 32 .. blockDim.x / 2 go through shared memory.
+__device__ inline void block_sort_pair(double* key, int* val, int np2) {
+    const int i0 = threadIdx.x, H = blockDim.x;   // np2 == 2 * H
+    double mk[2] = {key[i0], key[i0 + H]};
+    int mv[2] = {val[i0], val[i0 + H]};
+    __syncthreads();
+    auto less = [](double ka, int va, double kb, int vb) { return ka < kb || (ka == kb && va < vb); };
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j == H) {   // partner = my other element (only at k == np2: ascending)
+                if (less(mk[1], mv[1], mk[0], mv[0])) {
+                    const double tk = mk[0]; mk[0] = mk[1]; mk[1] = tk;
+                    const int tv = mv[0]; mv[0] = mv[1]; mv[1] = tv;
+                }
+                continue;
+            }
+            double ok[2];
+            int ov[2];
+            if (j < 32) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) { ok[h] = __shfl_xor_sync(FULL, mk[h], j); ov[h] = __shfl_xor_sync(FULL, mv[h], j); }
+            } else {
+                key[i0] = mk[0]; key[i0 + H] = mk[1]; val[i0] = mv[0]; val[i0 + H] = mv[1];
+                __syncthreads();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) { ok[h] = key[(i0 + h * H) ^ j]; ov[h] = val[(i0 + h * H) ^ j]; }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = i0 + h * H;
+                const bool keep_min = ((i & k) == 0) == ((i & j) == 0);
+                const bool other_less = less(ok[h], ov[h], mk[h], mv[h]);
+                if (keep_min == other_less) { mk[h] = ok[h]; mv[h] = ov[h]; }
+            }
+        }
+    }
+    key[i0] = mk[0]; key[i0 + H] = mk[1]; val[i0] = mv[0]; val[i0 + H] = mv[1];
     __syncthreads();
 }
 

@@ -202,16 +202,54 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
     const double* oldk = rb.okey + st->order_off;
     double* newk = rb.okey + (st->order_off ? 0 : p.nmax);
     const int m = n - Kp, npB = next_pow2(max(Kp, 1)), np2 = next_pow2(n);
+    const bool runs = merge && p.sh.world > 1;   // sharded run: the babies arrive as `world` sorted runs (shard_close)
+    if (runs) {
+        // Merge the runs by rank counting: a baby's place among all babies is its place in its own run plus the number
+        // of smaller (logL, slot) pairs in each other run (binary searches; no sort, no barrier between the steps).
+        const int world = p.sh.world, kr = p.sh.kr;
+        const double* xr = p.sh.xrun[p.sh.rank] + (size_t)((int)(st->ngen & 1) * world) * kr * 2;
+        int off[MAX_RANKS + 1];
+        off[0] = 0;
+        for (int r = 0; r < world; ++r) off[r + 1] = off[r] + (Kp > r ? (Kp - r + world - 1) / world : 0);
+        for (int r = 0; r < world; ++r)
+            for (int j = tid; j < off[r + 1] - off[r]; j += nthr) {
+                sm.bkey[off[r] + j] = __ldcg(xr + ((size_t)r * kr + j) * 2);
+                sm.bval[off[r] + j] = (int)__ldcg(xr + ((size_t)r * kr + j) * 2 + 1);
+            }
+        __syncthreads();
+        for (int r = 0; r < world; ++r)
+            for (int j = tid; j < off[r + 1] - off[r]; j += nthr) {
+                const double kb = sm.bkey[off[r] + j];
+                const int vb = sm.bval[off[r] + j];
+                int rank = j;
+                for (int r2 = 0; r2 < world; ++r2) {
+                    if (r2 == r) continue;
+                    int lo = off[r2], hi = off[r2 + 1];
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        const double k2 = sm.bkey[mid];
+                        if (k2 < kb || (k2 == kb && sm.bval[mid] < vb)) lo = mid + 1; else hi = mid;
+                    }
+                    rank += lo - off[r2];
+                }
+                sm.akey[rank] = kb;   // (the survivors' area is still free)
+                sm.aval[rank] = vb;
+            }
+        __syncthreads();
+        for (int j = tid; j < Kp; j += nthr) { sm.bkey[j] = sm.akey[j]; sm.bval[j] = sm.aval[j]; }
+        __syncthreads();
+    }
     if (merge) {
         for (int i = tid; i < m; i += nthr) {  // the survivors: keys and slots as the previous phase S ordered them
             sm.akey[i] = __ldcg(oldk + Kp + i);
             sm.aval[i] = __ldcg(oldo + Kp + i);
         }
-        for (int j = tid; j < npB; j += nthr) {
-            const int slot = j < Kp ? __ldcg(oldo + j) : 0x7fffffff;
-            sm.bval[j] = slot;
-            sm.bkey[j] = j < Kp ? __ldcg(rb.live + (size_t)slot * T + T - 1) : INFINITY;
-        }
+        if (!runs)
+            for (int j = tid; j < npB; j += nthr) {
+                const int slot = j < Kp ? __ldcg(oldo + j) : 0x7fffffff;
+                sm.bval[j] = slot;
+                sm.bkey[j] = j < Kp ? __ldcg(rb.live + (size_t)slot * T + T - 1) : INFINITY;
+            }
     } else {
         for (int i = tid; i < np2; i += nthr) {
             sm.akey[i] = (i < n) ? __ldcg(rb.live + (size_t)i * T + T - 1) : INFINITY;
@@ -262,7 +300,11 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
     long long q2 = clock64();
     if (merge && more) {
         // the babies in order: bitonic, one element per thread with warp shuffles below distance 32 when they fit
-        if (npB <= (int)blockDim.x) block_sort_small(sm.bkey, sm.bval, npB); else block_sort(sm.bkey, sm.bval, npB);
+        // (a sharded run merged its sorted runs above)
+        if (runs) {}
+        else if (npB <= (int)blockDim.x) block_sort_small(sm.bkey, sm.bval, npB);
+        else if (npB == 2 * (int)blockDim.x) block_sort_pair(sm.bkey, sm.bval, npB);
+        else block_sort(sm.bkey, sm.bval, npB);
         // rank of a survivor = its index + number of babies before it; rank of a baby = its index + number of
         // survivors before it ((key, slot) pairs are distinct, so the merged order is the sorted order)
         for (int i = tid; i < m; i += nthr) {
@@ -749,33 +791,48 @@ __device__ inline void shard_publish(const KParams& p, const double* rec, int k,
     }
     __threadfence_system();
 }
-// CTA 0, after this rank's chains are done: cross-GPU barrier, then the K last babies of all ranks are copied
-// from the incoming buffer into the vacated live slots (the same on every rank).
-__device__ inline void shard_scatter(const KParams& p, const RunBuf& rb, DevRun* st) {
+// CTA 0, after this rank's chains are done: the last babies of this rank's chains (k = rank, rank + world, ...) are
+// sorted by (logL, slot) and the sorted run is stored into every rank's run buffer -- the order of all K babies is then
+// a merge of `world` runs, not a sort (phase_S1) -- then the cross-GPU barrier that closes the generation.
+// smem: the phase-S area.  Returns false when a peer did not arrive.
+__device__ inline bool shard_close(const KParams& p, const RunBuf& rb, DevRun* st, const SmemS& sm) {
     __shared__ int s_ok;
-    const int tid = threadIdx.x, T = p.cp.T;
-    if (tid == 0) s_ok = xgpu_barrier(p.sh, st) ? 1 : 0;
-    __syncthreads();
-    if (!s_ok) { if (tid == 0) st->status = ST_ERROR; __syncthreads(); return; }
-    const int K = st->K;
+    const int tid = threadIdx.x, nthr = blockDim.x, T = p.cp.T, world = p.sh.world, rank = p.sh.rank;
+    const int K = st->K, par = (int)(st->ngen & 1);
+    const int cnt = K > rank ? (K - rank + world - 1) / world : 0, np = next_pow2(max(cnt, 1));
     const int* ord = rb.order + st->order_off;
-    const double* in = p.sh.xin[p.sh.rank] + (size_t)(st->ngen & 1) * p.batch_K * T;
-    // four records per warp in flight (the copy is latency-bound: K x T doubles through one CTA)
-    const int lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
-    for (int k0 = warp * 4; k0 < K; k0 += W * 4) {
-        int slot[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) slot[j] = __ldcg(ord + min(k0 + j, K - 1));
-        for (int e = lane; e < T; e += 32) {
-            double v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = __ldcg(in + (size_t)min(k0 + j, K - 1) * T + e);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (k0 + j < K) rb.live[(size_t)slot[j] * T + e] = v[j];
-        }
+    const double* in = p.sh.xin[rank] + (size_t)par * p.batch_K * T;
+    for (int j = tid; j < np; j += nthr) {
+        const int k = rank + j * world;
+        sm.bkey[j] = j < cnt ? __ldcg(in + (size_t)k * T + T - 1) : INFINITY;
+        sm.bval[j] = j < cnt ? __ldcg(ord + k) : 0x7fffffff;
     }
     __syncthreads();
+    if (np <= nthr) block_sort_small(sm.bkey, sm.bval, np);
+    else if (np == 2 * nthr) block_sort_pair(sm.bkey, sm.bval, np);
+    else block_sort(sm.bkey, sm.bval, np);
+    for (int q = 0; q < world; ++q) {
+        double* run = p.sh.xrun[q] + ((size_t)(par * world + rank) * p.sh.kr) * 2;
+        for (int j = tid; j < cnt; j += nthr) { run[2 * j] = sm.bkey[j]; run[2 * j + 1] = (double)sm.bval[j]; }
+    }
+    __syncthreads();
+    if (tid == 0) s_ok = xgpu_barrier(p.sh, st) ? 1 : 0;   // publishes the stores above (system-scope fence inside)
+    __syncthreads();
+    if (!s_ok && tid == 0) st->status = ST_ERROR;
+    __syncthreads();
+    return s_ok != 0;
+}
+// Every warp of the run, after shard_close + a group barrier: the K last babies of all ranks are copied from this
+// rank's incoming buffer into the vacated live slots (the same on every rank), one record per warp.
+__device__ inline void shard_scatter(const KParams& p, const RunBuf& rb, DevRun* st, int gw, int GW) {
+    const int lane = threadIdx.x & 31, T = p.cp.T;
+    const int K = vload(&st->K);
+    const int* ord = rb.order + vload(&st->order_off);
+    const double* in = p.sh.xin[p.sh.rank] + (size_t)(vload(&st->ngen) & 1) * p.batch_K * T;
+    for (int k = gw; k < K; k += GW) {
+        const int slot = __ldcg(ord + k);
+        for (int e = lane; e < T; e += 32) rb.live[(size_t)slot * T + e] = __ldcg(in + (size_t)k * T + e);
+    }
 }
 
 // ---------------------------------------------------------------- dump hand-over (CTA 0)
@@ -860,7 +917,6 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
     unsigned int wtarget = 0;
     bool have_wtarget = false;
     unsigned pair_seq = 0;  // paired mode: chains this warp pair has run since the launch (buffer parity)
-    bool scatter_due = false;  // sharded run: the last babies of the generation are still in the incoming buffer
     bool s2_due = false;  // CTA 0: the evidence of the generation in flight is still to be accumulated
     long long chol_epoch = -1;  // st->nupdates when this CTA last loaded the Cholesky factor into shared memory
 
@@ -893,10 +949,6 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
             long long t0 = clock64();
             if (have_wtarget) warp_wait(&st->wbar, wtarget, p.backoff);  // every chain of the previous generation is written
             __syncthreads();
-            if (scatter_due) {  // sharded run: every rank's last babies -> the replicated live array
-                shard_scatter(p, rb, st);
-                scatter_due = false;
-            }
             // births that failed, slots left empty (B != K): the live set is made contiguous again before anything reads it
             if (st->holes_due || vload(&st->nfail_gen)) { settle_generation(p, rb, st, s_warp0, true); __syncthreads(); }
             long long t1 = clock64();
@@ -1172,7 +1224,18 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
         }
         wtarget = warp_arrive(&st->wbar, GW);
         have_wtarget = true;
-        scatter_due = sharded;
+        if (sharded) {
+            // Close the generation across the GPUs: this rank's chains are done -> CTA 0 sorts their last babies, stores
+            // the run with every rank and passes the cross-GPU barrier -> every warp copies its share of the K last babies
+            // from the incoming buffer into the live array.
+            warp_wait(&st->wbar, wtarget, p.backoff);
+            have_wtarget = false;
+            if (cta == 0) { __syncthreads(); shard_close(p, rb, st, smS); prep_uid = ~0ull; }
+            group_sync(&st->bar, NG, p.backoff);
+            if (vload(&st->status) == ST_ERROR) return;
+            shard_scatter(p, rb, st, gw, GW);
+            group_sync(&st->bar, NG, p.backoff);
+        }
         // the scratch the next generation's first chain of this warp (pair) will use
         const bool will_chain = knext >= 0;
         const ChainScratch csn = p.paired ? chain_scratch(s_warp0 + (size_t)((warp % (W >> 1)) + (W >> 1) * (int)(pair_seq & 1u)) * p.warp_bytes,
@@ -1190,11 +1253,6 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                 group_sync(&st->bar, NG, p.backoff);
                 // every warp of the run has read the flags by now: clear them (the next reader is CTA 0's next phase S)
                 if (cta == 0 && tid == 0) { st->holes_due = 0; st->nfail_gen = 0u; }
-            }
-            if (sharded) {  // the covariance is over the live points including this generation's babies
-                if (cta == 0) { __syncthreads(); shard_scatter(p, rb, st); }
-                scatter_due = false;
-                group_sync(&st->bar, NG, p.backoff);
             }
             long long ua0 = clock64();
             phase_UA(p, rb, st, cta, NG);

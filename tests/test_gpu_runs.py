@@ -29,6 +29,8 @@ def both(gpu, oracle, like="gaussian", extra=None, **kw):
     dict(nDims=4, nDerived=1, nlive=64, num_repeats=8, seed=0, batch_K=16),
     dict(nDims=20, nDerived=2, nlive=200, num_repeats=40, seed=1, batch_K=50),
     dict(nDims=20, nDerived=2, nlive=1000, num_repeats=40, seed=2, batch_K=250),   # BASELINE config 2
+    dict(nDims=20, nDerived=2, nlive=1000, num_repeats=40, seed=5, batch_K=500),   # ... at the engine's default batch (n/2: two babies per thread in phase S)
+    dict(nDims=5, nDerived=0, nlive=700, num_repeats=10, seed=6, batch_K=300),     # a batch between the two register sorts
     dict(nDims=6, nDerived=0, nlive=100, num_repeats=12, seed=3, batch_K=99),      # K = nlive-1
     dict(nDims=6, nDerived=0, nlive=100, num_repeats=12, seed=3, batch_K=1),       # one death per generation
     dict(nDims=3, nDerived=0, nlive=50, num_repeats=1, seed=4, batch_K=10),        # no phantoms at all
