@@ -902,17 +902,21 @@ struct Engine {
             g_dbg_dump[slot] += std::chrono::duration<double, std::milli>(t - td0).count();
             td0 = t;
         };
-        // one batch of async copies into pinned staging, one synchronisation
-        double* sd = fresh > 0 ? (double*)g_pin_dead.need((size_t)fresh * (T + 1) * 8) : nullptr;
-        double* sl = nl > 0 ? (double*)g_pin_live.need((size_t)k.nmax * T * 8) : nullptr;
+        // one batch of async copies into pinned staging, one synchronisation.  The dumper's rows are [theta, phi, birth,
+        // logL] = columns D .. T-1 of a record (nested_sampling.F90:569-584): only those cross the bus (a strided copy;
+        // the cube coordinates stay on the device)
+        double* sd = fresh > 0 ? (double*)g_pin_dead.need((size_t)fresh * (npars + 1) * 8) : nullptr;
+        double* sl = nl > 0 ? (double*)g_pin_live.need((size_t)k.nmax * npars * 8) : nullptr;
         if (fresh > 0) {
-            h.dead.download(sd, (size_t)fresh * T, cs, (size_t)h.mirrored * T);
-            h.logw.download(sd + (size_t)fresh * T, fresh, cs, h.mirrored);
-            d2h += fresh * (T + 1) * 8;
+            PC_CUDA(cudaMemcpy2DAsync(sd, (size_t)npars * 8, h.dead.p + (size_t)h.mirrored * T + D, (size_t)T * 8, (size_t)npars * 8,
+                                      (size_t)fresh, cudaMemcpyDeviceToHost, cs));
+            h.logw.download(sd + (size_t)fresh * npars, fresh, cs, h.mirrored);
+            d2h += fresh * (npars + 1) * 8;
         }
         if (nl > 0) {
-            PC_CUDA(cudaMemcpyAsync(sl, live_src, (size_t)n * T * 8, cudaMemcpyDeviceToHost, cs));
-            d2h += (long long)n * T * 8;
+            PC_CUDA(cudaMemcpy2DAsync(sl, (size_t)npars * 8, live_src + D, (size_t)T * 8, (size_t)npars * 8, (size_t)n,
+                                      cudaMemcpyDeviceToHost, cs));
+            d2h += (long long)n * npars * 8;
         }
         PC_CUDA(cudaStreamSynchronize(cs));
         lap(0);
@@ -920,15 +924,11 @@ struct Engine {
         if (mr.rows.size() < (size_t)ndead * npars) mr.rows.resize(std::max((size_t)ndead * npars, mr.rows.size() * 2));
         if (mr.logw.size() < (size_t)ndead) { mr.logw.resize(std::max((size_t)ndead, mr.logw.size() * 2)); mr.lw.resize(mr.logw.size()); }
         if (fresh > 0) {
-            const double* lwp = sd + (size_t)fresh * T;
+            const double* lwp = sd + (size_t)fresh * npars;
+            std::memcpy(&mr.rows[(size_t)h.mirrored * npars], sd, (size_t)fresh * npars * sizeof(double));
             double mx = h.lse_max;
             for (long long i = 0; i < fresh; ++i) {
-                const double* s = sd + (size_t)i * T;
-                double* o = &mr.rows[(size_t)(h.mirrored + i) * npars];
-                std::memcpy(o, s + D, (size_t)(D + P) * sizeof(double));  // theta, phi
-                o[D + P] = s[2 * D + P];
-                o[D + P + 1] = s[2 * D + P + 1];
-                const double v = lwp[i] + s[T - 1];
+                const double v = lwp[i] + sd[(size_t)i * npars + npars - 1];
                 mr.logw[h.mirrored + i] = v;
                 mx = std::max(mx, v);
             }
@@ -941,13 +941,7 @@ struct Engine {
         }
         if (mr.live_rows.size() < (size_t)std::max(nl, 1) * npars) mr.live_rows.resize((size_t)std::max(nl, 1) * npars);
         std::vector<double>& live_rows = mr.live_rows;
-        for (int i = 0; i < nl; ++i) {
-            const double* s = sl + (size_t)i * T;
-            double* o = &live_rows[(size_t)i * npars];
-            std::memcpy(o, s + D, (size_t)(D + P) * sizeof(double));
-            o[D + P] = s[2 * D + P];
-            o[D + P + 1] = s[2 * D + P + 1];
-        }
+        if (nl > 0) std::memcpy(live_rows.data(), sl, (size_t)nl * npars * sizeof(double));
         lap(1);
         std::vector<double>& lw = mr.lw;
         if (lw.empty()) lw.resize(1);
