@@ -117,6 +117,8 @@ void pc_uniform_prior(double* cube, double* theta, int nDims); /* theta = lo + (
  *                     serialise kernel launches (the host cannot acknowledge a dump from inside the launch call).
  *   "no_pairing"      1: do not use helper warps for the direction preparation (a run alone on the device
  *                     normally pairs every chain warp with a helper warp)
+ *   "no_phase_d"      1: keep the order of the live points on one CTA (phase S); normally every CTA of a run
+ *                     ranks its share of the live points after a regular generation (phase D)
  *   "resume_interval" seconds between two rewrites of the resume file at updates (default 1; 0 = every update)
  *   "cap_dead0", "cap_ph0"  initial capacity (records) of the dead / phantom pools; 0 = automatic.
  *                     The pools grow on demand either way (the kernel exits, the host reallocates, relaunches).

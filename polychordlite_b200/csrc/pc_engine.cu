@@ -191,6 +191,7 @@ struct Options {
     int errors_return = 0;
     int nh_global = 0;  // force the direction scratch into global memory (testing)
     int no_pairing = 0; // keep the helper-warp preparation off (testing)
+    int no_phase_d = 0; // order the live points on CTA 0 only (testing: phase D off)
     int sync_dump = 0;  // the kernel exits at every update for the dumper instead of handing dumps over while running
     long long cap_dead0 = 0, cap_ph0 = 0;  // initial pool capacities in records (0 = automatic)
 };
@@ -406,6 +407,17 @@ static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const Dev
     wb = (wb + 15) & ~(size_t)15;
     k.warp_bytes = (int)wb;
     L.smem = off + std::max((size_t)W * wb, sort_bytes);
+    // phase D (pc_run_kernel.cuh): every CTA stages the nmax live keys behind its per-warp areas; when they do not fit,
+    // CTA 0's phase S keeps ordering the live points
+    k.off_dkeys = 0;
+    {
+        const size_t d_off = (off + (size_t)W * wb + 15) & ~(size_t)15;
+        const size_t d_end = d_off + ((size_t)k.nmax + 2 * W + 2) * 8;
+        if (!g_opt.no_phase_d && d_end <= (dense ? (size_t)112 * 1024 : (size_t)227 * 1024)) {
+            k.off_dkeys = (int)d_off;
+            L.smem = std::max(L.smem, d_end);
+        }
+    }
     return L;
 }
 
@@ -424,7 +436,7 @@ static void set_smem(const ShapeFns& fn, size_t smem) {
 // ------------------------------------------------------------------------------------------
 struct HostRun {
     DevArr<DevRun> st;
-    DevArr<double> live, live_snap, dead, logw, ph0, ph1, chol, cov, partial, nh, gsum, okey;
+    DevArr<double> live, live_snap, dead, logw, ph0, ph1, chol, cov, partial, nh, gsum, okey, bkey, dpart;
     DevArr<int> order, lab, phl0, phl1, cfail;
     DevArr<double> cchol;
     DevArr<long long> pcount;
@@ -792,6 +804,8 @@ struct Engine {
             h.chol.alloc((size_t)D * D); h.cov.alloc((size_t)D * D);
             h.gsum.alloc((size_t)2 * D + 4);
             h.cfail.alloc((size_t)2 * K + 8); h.cfail.zero(stream);
+            h.bkey.alloc((size_t)2 * K + 8); h.bkey.zero(stream);
+            h.dpart.alloc((size_t)2 * G + 8); h.dpart.zero(stream);
             h.partial.alloc((size_t)G * k.partial_stride);
             h.pcount.alloc((size_t)cap_ph / U_TILE + 2); h.pcount.zero(stream);
             if (k.dense) h.nh.alloc((size_t)G * W * (32 / L.fn.G) * R * dense_slb(L.fn.G * L.fn.DPL));   // slice records of the chains in flight
@@ -809,7 +823,7 @@ struct Engine {
             b.pcount = h.pcount.p; b.nh = h.nh.p; b.cap_dead = cap_dead; b.cap_ph = cap_ph; b.gsum = h.gsum.p;
             b.lab = h.lab.p; b.phl[0] = h.phl0.p; b.phl[1] = h.phl1.p; b.cchol = h.cchol.p;
             b.boost = h.boost.p; b.boost_win = h.boost_win.p; b.cap_boost = cap_boost;
-            b.cfail = h.cfail.p;
+            b.cfail = h.cfail.p; b.bkey = h.bkey.p; b.dpart = h.dpart.p;
             if (sharded)  // continue the cross-GPU barrier count of earlier runs (the counters are monotonic)
                 PC_CUDA(cudaMemcpyAsync(&h.st.p->xepoch, &g_mgpu.epoch, sizeof(g_mgpu.epoch), cudaMemcpyHostToDevice, stream));
             b.seed = resumed ? rd.h.seed : (unsigned)seeds[r];   // a resumed run continues its own random stream
@@ -1528,6 +1542,7 @@ int pc_set_option(const char* name, double value) {
     else if (s == "errors_return") g_opt.errors_return = (int)value;
     else if (s == "nh_global") g_opt.nh_global = (int)value;
     else if (s == "no_pairing") g_opt.no_pairing = (int)value;
+    else if (s == "no_phase_d") g_opt.no_phase_d = (int)value;
     else if (s == "sync_dump") g_opt.sync_dump = (int)value;
     else if (s == "cap_dead0") g_opt.cap_dead0 = (long long)value;
     else if (s == "cap_ph0") g_opt.cap_ph0 = (long long)value;
@@ -1546,6 +1561,7 @@ double pc_get_option(const char* name) {
     if (s == "errors_return") return g_opt.errors_return;
     if (s == "nh_global") return g_opt.nh_global;
     if (s == "no_pairing") return g_opt.no_pairing;
+    if (s == "no_phase_d") return g_opt.no_phase_d;
     if (s == "sync_dump") return g_opt.sync_dump;
     if (s == "cap_dead0") return (double)g_opt.cap_dead0;
     if (s == "cap_ph0") return (double)g_opt.cap_ph0;

@@ -81,10 +81,13 @@ struct DevRun {
     long long dbg[24];
     // what every warp needs at the start of a generation, in one 64-byte line (written by phase S1, read with one
     // coalesced load per warp): [0] Lstar (bits), [1] ndead_base, [2] nph_base, [3] nchains_base, [4] ngen,
-    // [5] K | do_update << 32, [6] order_off | cur_pool << 32, [7] ncl | nupdates << 32, [8] n_gen | B << 32
-    unsigned long long pub[10];
+    // [5] K | do_update << 32, [6] order_off | cur_pool << 32, [7] ncl | nupdates << 32, [8] n_gen | B << 32,
+    // [9] nfail at the start of the generation (a generation whose chains leave it unchanged had no failed birth)
+    unsigned long long pub[12];
     unsigned int bar;    // group barrier, one arrival per CTA (monotonic)
     unsigned int wbar;   // chains-done barrier, one arrival per warp (monotonic)
+    unsigned int dbar;   // phase D done, one arrival per ranking CTA (monotonic); only CTA 0 waits for it
+    unsigned int pad2;
     // boost_posterior (clean_phantoms, run_time_info.f90:820-877): phantoms promoted to posterior samples so far
     // (rb.boost rows), and ndead at the last update -- the deaths after it are the posterior stack a removed
     // phantom takes its weight from
@@ -129,6 +132,8 @@ struct RunBuf {
     long long cap_boost;
     long long cap_dead, cap_ph;
     int* cfail;        // per chain of the generation in flight: 1 when its last baby is not above the contour (a failed birth)
+    double* bkey;      // per chain of the generation in flight: logL of its last baby (phase D ranks the babies from here)
+    double* dpart;     // per CTA: (max, sum of exp(logL - max)) over the live points the CTA ranked in phase D (termination test)
     unsigned int seed;
     int pad;
 };
@@ -142,13 +147,12 @@ struct RunBuf {
 //          all-reduced by storing them into every rank's slot and summing in rank order;
 //   xbar   one monotonic counter per rank: a barrier adds `world` to each of them.
 constexpr int MAX_RANKS = 8;
-//   xrun   the order of the new babies is built from per-rank pieces: every rank sorts the last babies of ITS chains
-//          (K / world of them) and stores the sorted (logL, slot) run into every rank's run buffer (2 x world x kr
-//          pairs, by generation parity); phase S merges the `world` runs by rank counting instead of sorting K keys.
+//   xrun   the logL of the last baby of every chain, stored by the chain into every rank's key buffer (2 x batch_K
+//          doubles, by generation parity): phase D ranks the babies from there on every rank.
 struct Shard {
     int rank, world;
     long long xstride;                 // doubles per rank slot in xpart
-    int kr, pad;                       // pairs per rank in xrun: ceil(batch_K / world)
+    int kr, pad;                       // ceil(batch_K / world) (sizes the key buffers)
     unsigned int* xbar[MAX_RANKS];
     double* xin[MAX_RANKS];
     double* xpart[MAX_RANKS];
@@ -178,6 +182,7 @@ struct KParams {
     int live_given;              // 1: the host uploaded the initial live points (host callbacks, or the caller's cube_samples)
     int ntri, cov_passes, partial_stride;
     int off_like, off_warp, warp_bytes;  // shared-memory byte offsets
+    int off_dkeys;               // phase D's key area behind the per-warp areas (nmax + 2 * warps + 2 doubles); 0: phase S orders the live points on CTA 0
     double log_prec, log_comp;
     double boost_thin;           // RTI%thin_posterior (generate.F90:311-316) when posterior files are written, else 0
     const double* like_params;   // gaussian: mu[D], 1/sigma[D]; corr: mu[D], invcov[D*D]
@@ -478,6 +483,8 @@ __device__ inline void block_sort(double* key, int* val, int np2) {
 // X and XX are prefix sums, ZX a first-order linear recurrence (affine scan), Z and Z2
 // log-sum-exp reductions.  skey: ascending logL of the dying points (shared memory).
 // ------------------------------------------------------------------------------------------
+// KEYS_GLOBAL: skey is global memory other CTAs wrote (phase D): read past L1.
+template <bool KEYS_GLOBAL = false>
 __device__ inline void evidence_deaths(DevRun* st, const double* skey, int count, int n_start, double* logw_out,
                                        double* sc) {
     const double LOG2 = 0.69314718055994530942;
@@ -492,7 +499,7 @@ __device__ inline void evidence_deaths(DevRun* st, const double* skey, int count
         double totx, totxx;
         double lXb = lX + block_exscan_sum(dx, &totx, sc);
         double lXXb = lXX + block_exscan_sum(dxx, &totxx, sc);
-        double L = act ? skey[j] : 0.0;
+        double L = act ? (KEYS_GLOBAL ? __ldcg(skey + j) : skey[j]) : 0.0;
         double a = dx, b = act ? lXXb + L + l0n - l1 - l2 : NEG_BIG;
         double exa, exb, tota, totb;
         block_exscan_affine(a, b, exa, exb, tota, totb, sc);

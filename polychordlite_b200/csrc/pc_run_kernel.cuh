@@ -188,8 +188,10 @@ __device__ inline void settle_generation(const KParams& p, const RunBuf& rb, Dev
     __syncthreads();
 }
 
-// returns true when the evidence of the K deaths is still to be accumulated (S2)
-__device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, const SmemS& sm) {
+// returns true when the evidence of the K deaths is still to be accumulated (S2).
+// merged: phase D (all CTAs) already wrote the new order into the other half of rb.order / rb.okey and left the CTAs'
+// (max, sum exp) partials of the termination test in rb.dpart[0 .. 2 nparts).
+__device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, const SmemS& sm, bool merged, int nparts) {
     const int tid = threadIdx.x, T = p.cp.T, nthr = blockDim.x;
     const int n = st->n;
     double* sc = sm.sc;
@@ -202,54 +204,19 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
     const double* oldk = rb.okey + st->order_off;
     double* newk = rb.okey + (st->order_off ? 0 : p.nmax);
     const int m = n - Kp, npB = next_pow2(max(Kp, 1)), np2 = next_pow2(n);
-    const bool runs = merge && p.sh.world > 1;   // sharded run: the babies arrive as `world` sorted runs (shard_close)
-    if (runs) {
-        // Merge the runs by rank counting: a baby's place among all babies is its place in its own run plus the number
-        // of smaller (logL, slot) pairs in each other run (binary searches; no sort, no barrier between the steps).
-        const int world = p.sh.world, kr = p.sh.kr;
-        const double* xr = p.sh.xrun[p.sh.rank] + (size_t)((int)(st->ngen & 1) * world) * kr * 2;
-        int off[MAX_RANKS + 1];
-        off[0] = 0;
-        for (int r = 0; r < world; ++r) off[r + 1] = off[r] + (Kp > r ? (Kp - r + world - 1) / world : 0);
-        for (int r = 0; r < world; ++r)
-            for (int j = tid; j < off[r + 1] - off[r]; j += nthr) {
-                sm.bkey[off[r] + j] = __ldcg(xr + ((size_t)r * kr + j) * 2);
-                sm.bval[off[r] + j] = (int)__ldcg(xr + ((size_t)r * kr + j) * 2 + 1);
-            }
-        __syncthreads();
-        for (int r = 0; r < world; ++r)
-            for (int j = tid; j < off[r + 1] - off[r]; j += nthr) {
-                const double kb = sm.bkey[off[r] + j];
-                const int vb = sm.bval[off[r] + j];
-                int rank = j;
-                for (int r2 = 0; r2 < world; ++r2) {
-                    if (r2 == r) continue;
-                    int lo = off[r2], hi = off[r2 + 1];
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        const double k2 = sm.bkey[mid];
-                        if (k2 < kb || (k2 == kb && sm.bval[mid] < vb)) lo = mid + 1; else hi = mid;
-                    }
-                    rank += lo - off[r2];
-                }
-                sm.akey[rank] = kb;   // (the survivors' area is still free)
-                sm.aval[rank] = vb;
-            }
-        __syncthreads();
-        for (int j = tid; j < Kp; j += nthr) { sm.bkey[j] = sm.akey[j]; sm.bval[j] = sm.aval[j]; }
-        __syncthreads();
-    }
+    if (merged) {
+        // nothing to load: the order is in place
+    } else
     if (merge) {
         for (int i = tid; i < m; i += nthr) {  // the survivors: keys and slots as the previous phase S ordered them
             sm.akey[i] = __ldcg(oldk + Kp + i);
             sm.aval[i] = __ldcg(oldo + Kp + i);
         }
-        if (!runs)
-            for (int j = tid; j < npB; j += nthr) {
-                const int slot = j < Kp ? __ldcg(oldo + j) : 0x7fffffff;
-                sm.bval[j] = slot;
-                sm.bkey[j] = j < Kp ? __ldcg(rb.live + (size_t)slot * T + T - 1) : INFINITY;
-            }
+        for (int j = tid; j < npB; j += nthr) {
+            const int slot = j < Kp ? __ldcg(oldo + j) : 0x7fffffff;
+            sm.bval[j] = slot;
+            sm.bkey[j] = j < Kp ? __ldcg(rb.live + (size_t)slot * T + T - 1) : INFINITY;
+        }
     } else {
         for (int i = tid; i < np2; i += nthr) {
             sm.akey[i] = (i < n) ? __ldcg(rb.live + (size_t)i * T + T - 1) : INFINITY;
@@ -268,12 +235,21 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
     else if (p.max_ndead == 0) more = false;
     else if (p.max_ndead > 0 && ndead >= p.max_ndead) more = false;
     else if (p.use_prec) {
-        double mx = -INFINITY;
-        for (int i = tid; i < n; i += nthr) mx = fmax(mx, key_at(i));
-        mx = block_max(mx, sc);
-        double s = 0.0;
-        for (int i = tid; i < n; i += nthr) s += exp(key_at(i) - mx);
-        s = block_sum(s, sc);
+        double mx = -INFINITY, s = 0.0;
+        if (merged) {   // the CTAs' partials, combined in CTA order
+            double pm = -INFINITY, ps = 0.0;
+            for (int c = tid; c < nparts; c += nthr) {   // (nparts <= blockDim.x in every launch geometry; the loop keeps it general)
+                const double cm = __ldcg(rb.dpart + 2 * c), csum = __ldcg(rb.dpart + 2 * c + 1);
+                if (cm > pm) { ps = ps * exp(pm - cm) + csum; pm = cm; } else if (csum > 0.0) ps += csum * exp(cm - pm);
+            }
+            mx = block_max(pm, sc);
+            s = block_sum(ps > 0.0 ? ps * exp(pm - mx) : 0.0, sc);
+        } else {
+            for (int i = tid; i < n; i += nthr) mx = fmax(mx, key_at(i));
+            mx = block_max(mx, sc);
+            for (int i = tid; i < n; i += nthr) s += exp(key_at(i) - mx);
+            s = block_sum(s, sc);
+        }
         double lz = mx + log(s) - log((double)n) + st->logX;
         if (lz < p.log_prec + st->logZ) more = false;
     }
@@ -298,11 +274,11 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
         return false;
     }
     long long q2 = clock64();
-    if (merge && more) {
+    if (merged && more) {
+        // phase D ordered the live points
+    } else if (merge && more) {
         // the babies in order: bitonic, one element per thread with warp shuffles below distance 32 when they fit
-        // (a sharded run merged its sorted runs above)
-        if (runs) {}
-        else if (npB <= (int)blockDim.x) block_sort_small(sm.bkey, sm.bval, npB);
+        if (npB <= (int)blockDim.x) block_sort_small(sm.bkey, sm.bval, npB);
         else if (npB == 2 * (int)blockDim.x) block_sort_pair(sm.bkey, sm.bval, npB);
         else block_sort(sm.bkey, sm.bval, npB);
         // rank of a survivor = its index + number of babies before it; rank of a baby = its index + number of
@@ -364,7 +340,7 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
     long long q3 = clock64();
     const double lX_new = logX_after(st->logX, K, n, sc);
     if (tid == 0) {
-        const double Lstar = newk[K - 1];
+        const double Lstar = __ldcg(newk + K - 1);   // (phase D's CTAs may have written it)
         // births: the live count moves towards its target above the contour, at most 2 batch_K a generation
         // (constant target: B = K; the batched form of run_time_info.f90:766-777)
         int B = trim ? 0 : max(0, min(max(target_nlive(p, Lstar), 1) - (n - K), 2 * p.batch_K));
@@ -399,6 +375,7 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
         st->pub[6] = (unsigned long long)(unsigned)st->order_off | ((unsigned long long)(unsigned)st->cur_pool << 32);
         st->pub[7] = (unsigned long long)(unsigned)st->ncl | ((unsigned long long)(unsigned)st->nupdates << 32);
         st->pub[8] = (unsigned long long)(unsigned)n | ((unsigned long long)(unsigned)B << 32);
+        st->pub[9] = (unsigned long long)st->nfail;
         long long q4 = clock64();
         st->dbg[6] += q1 - q0; st->dbg[7] += q2 - q1; st->dbg[8] += q3 - q2; st->dbg[9] += q4 - q3;
     }
@@ -409,7 +386,83 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
 // head of the order phase S1 wrote
 __device__ inline void phase_S2(const KParams& p, const RunBuf& rb, DevRun* st, const SmemS& sm) {
     const int K = st->K;
-    evidence_deaths(st, rb.okey + st->order_off, K, st->n_gen, rb.logw + st->ndead_base, sm.sc);
+    evidence_deaths<true>(st, rb.okey + st->order_off, K, st->n_gen, rb.logw + st->ndead_base, sm.sc);
+}
+
+// ---------------------------------------------------------------- phase D (every CTA that runs chains)
+// The order of the live points after a REGULAR generation -- K deaths, K successful births into the vacated slots -- built by
+// all warps of the run instead of CTA 0 (find_min / the sorted live set of nested_sampling.F90:262-303, kept incrementally):
+// the n-K survivors keep their relative order, so the rank of a survivor is its index plus the number of babies below it,
+// and the rank of a baby is the number of babies below it plus the number of survivors below it.  Every CTA stages the K baby
+// keys (bkeys: written by the chains, logL of their last babies; baby j sits in slot oldo[j]) and the n-K survivor keys in
+// shared memory; a warp takes one live point at a time, its lanes count the babies below it (ties by slot, as everywhere),
+// a binary search counts the survivors below a baby, and lane 0 writes (slot, key) to its place in the other half of
+// rb.order / rb.okey.  Nothing is sorted and nothing depends on another point's rank: the phase is one pass, spread over
+// cta_rel = 0 .. nctas-1.  Beside it every CTA leaves (max, sum exp(logL - max)) of the points it ranked in rb.dpart for the
+// termination test (live_logZ, run_time_info.f90:683-709).
+__device__ inline void phase_D(const KParams& p, const RunBuf& rb, DevRun* st, const double* bkeys, int cta_rel, int nctas,
+                               double* s_keys) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5, nthr = blockDim.x;
+    const int K = vload(&st->K), n = vload(&st->n_gen), m = n - K;
+    const int off = vload(&st->order_off);
+    const int* oldo = rb.order + off;
+    const double* oldk = rb.okey + off;
+    int* newo = rb.order + (off ? 0 : p.nmax);
+    double* newk = rb.okey + (off ? 0 : p.nmax);
+    double* sb = s_keys;          // K baby keys
+    double* ss = s_keys + K;      // m survivor keys, ascending
+    double* sp = s_keys + n;      // 2 W: the warps' partials
+    for (int j = tid; j < K; j += nthr) sb[j] = __ldcg(bkeys + j);
+    for (int i = tid; i < m; i += nthr) ss[i] = __ldcg(oldk + K + i);
+    __syncthreads();
+    double pm = -INFINITY, ps = 0.0;   // lane 0: running max and sum of exp(key - max) over the warp's points
+    for (int e = cta_rel * W + warp; e < n; e += nctas * W) {
+        const bool baby = e >= m;
+        const int idx = baby ? e - m : e;
+        const double key = baby ? sb[idx] : ss[idx];
+        const int slot = __ldcg(oldo + (baby ? idx : K + idx));
+        int cnt = 0;
+        for (int j = lane; j < K; j += 32) {
+            const double kb = sb[j];
+            bool less = kb < key;
+            if (kb == key) less = __ldcg(oldo + j) < slot;   // (a baby is not below itself: equal slots)
+            cnt += less ? 1 : 0;
+        }
+        cnt = __reduce_add_sync(FULL, cnt);
+        int rank = cnt + idx;
+        if (baby) {   // survivors below it: first survivor that is not
+            int lo = 0, hi = m;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (ss[mid] < key) lo = mid + 1; else hi = mid;
+            }
+            while (lo < m && ss[lo] == key && __ldcg(oldo + K + lo) < slot) ++lo;
+            rank = cnt + lo;
+        }
+        if (lane == 0) {
+            newo[rank] = slot;
+            newk[rank] = key;
+            if (key > pm) { ps = ps * exp(pm - key) + 1.0; pm = key; } else ps += exp(key - pm);
+        }
+    }
+    if (lane == 0) { sp[2 * warp] = pm; sp[2 * warp + 1] = ps; }
+    __syncthreads();
+    if (tid == 0) {   // the warps' partials in warp order
+        double cm = -INFINITY, cs = 0.0;
+        for (int w = 0; w < W; ++w) {
+            const double wm = sp[2 * w], ws = sp[2 * w + 1];
+            if (ws > 0.0) {
+                if (wm > cm) { cs = cs * exp(cm - wm) + ws; cm = wm; } else cs += ws * exp(wm - cm);
+            }
+        }
+        rb.dpart[2 * cta_rel] = cm;
+        rb.dpart[2 * cta_rel + 1] = cs;
+        // arrive (CTA 0 waits for every ranking CTA before phase S1 reads the order; nobody else waits: the CTAs go
+        // on to prepare their next chains)
+        __threadfence();
+        atomicAdd(&st->dbar, 1u);
+    }
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------- phase U
@@ -780,43 +833,27 @@ __device__ inline bool finish_update(const KParams& p, const RunBuf& rb, DevRun*
 }
 
 // ---------------------------------------------------------------- sharded run: last-baby exchange
-// A chain warp stores its last baby (already in this rank's incoming buffer) into every peer's incoming buffer.
-__device__ inline void shard_publish(const KParams& p, const double* rec, int k, int parity) {
+// A chain warp stores its last baby (already in this rank's incoming buffer) into every peer's incoming buffer, and the
+// baby's logL into every rank's key buffer (phase D ranks the babies of all ranks from there, on every rank).
+__device__ inline void shard_publish(const KParams& p, const double* rec, int k, int parity, double lfin) {
     const int lane = threadIdx.x & 31, T = p.cp.T;
     __syncwarp();
     for (int q = 0; q < p.sh.world; ++q) {
-        if (q == p.sh.rank) continue;
-        double* dst = p.sh.xin[q] + ((size_t)parity * p.batch_K + k) * T;
-        for (int e = lane; e < T; e += 32) dst[e] = __ldcg(rec + e);
+        if (q != p.sh.rank) {
+            double* dst = p.sh.xin[q] + ((size_t)parity * p.batch_K + k) * T;
+            for (int e = lane; e < T; e += 32) dst[e] = __ldcg(rec + e);
+        }
+        if (lane == 0) p.sh.xrun[q][(size_t)parity * p.batch_K + k] = lfin;
     }
     __threadfence_system();
 }
-// CTA 0, after this rank's chains are done: the last babies of this rank's chains (k = rank, rank + world, ...) are
-// sorted by (logL, slot) and the sorted run is stored into every rank's run buffer -- the order of all K babies is then
-// a merge of `world` runs, not a sort (phase_S1) -- then the cross-GPU barrier that closes the generation.
-// smem: the phase-S area.  Returns false when a peer did not arrive.
-__device__ inline bool shard_close(const KParams& p, const RunBuf& rb, DevRun* st, const SmemS& sm) {
+// CTA 0, after this rank's chains are done: the cross-GPU barrier that closes the generation (every rank's last babies and
+// keys have arrived here when it returns).  Returns false when a peer did not arrive.
+__device__ inline bool shard_close(const KParams& p, DevRun* st) {
     __shared__ int s_ok;
-    const int tid = threadIdx.x, nthr = blockDim.x, T = p.cp.T, world = p.sh.world, rank = p.sh.rank;
-    const int K = st->K, par = (int)(st->ngen & 1);
-    const int cnt = K > rank ? (K - rank + world - 1) / world : 0, np = next_pow2(max(cnt, 1));
-    const int* ord = rb.order + st->order_off;
-    const double* in = p.sh.xin[rank] + (size_t)par * p.batch_K * T;
-    for (int j = tid; j < np; j += nthr) {
-        const int k = rank + j * world;
-        sm.bkey[j] = j < cnt ? __ldcg(in + (size_t)k * T + T - 1) : INFINITY;
-        sm.bval[j] = j < cnt ? __ldcg(ord + k) : 0x7fffffff;
-    }
+    const int tid = threadIdx.x;
     __syncthreads();
-    if (np <= nthr) block_sort_small(sm.bkey, sm.bval, np);
-    else if (np == 2 * nthr) block_sort_pair(sm.bkey, sm.bval, np);
-    else block_sort(sm.bkey, sm.bval, np);
-    for (int q = 0; q < world; ++q) {
-        double* run = p.sh.xrun[q] + ((size_t)(par * world + rank) * p.sh.kr) * 2;
-        for (int j = tid; j < cnt; j += nthr) { run[2 * j] = sm.bkey[j]; run[2 * j + 1] = (double)sm.bval[j]; }
-    }
-    __syncthreads();
-    if (tid == 0) s_ok = xgpu_barrier(p.sh, st) ? 1 : 0;   // publishes the stores above (system-scope fence inside)
+    if (tid == 0) s_ok = xgpu_barrier(p.sh, st) ? 1 : 0;   // (system-scope fence inside)
     __syncthreads();
     if (!s_ok && tid == 0) st->status = ST_ERROR;
     __syncthreads();
@@ -914,8 +951,6 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
     // chain whose directions currently sit in this warp's scratch (~0 = none), and whether they are whitened
     unsigned long long prep_uid = ~0ull;
     bool prep_white = false;
-    unsigned int wtarget = 0;
-    bool have_wtarget = false;
     unsigned pair_seq = 0;  // paired mode: chains this warp pair has run since the launch (buffer parity)
     bool s2_due = false;  // CTA 0: the evidence of the generation in flight is still to be accumulated
     long long chol_epoch = -1;  // st->nupdates when this CTA last loaded the Cholesky factor into shared memory
@@ -944,21 +979,41 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
     const bool timer = (tid == 0) && (cta == 0);          // bookkeeping phases
     const bool ctimer = (tid == 0) && (cta == c0);         // chain phases of one representative warp
     const long long t_start = clock64();
+    unsigned int dtarget = vload(&st->dbar);   // CTA 0: arrivals phase D has to show (no phase D is in flight at a launch)
+    bool d_done = false;   // phase D ordered the live points of the generation just finished (the same on every CTA of the run)
     for (;;) {
+        bool dump_exit = false, cluster_exit = false;
         if (cta == 0) {
-            long long t0 = clock64();
-            if (have_wtarget) warp_wait(&st->wbar, wtarget, p.backoff);  // every chain of the previous generation is written
+            // (every chain of the previous generation is written: all warps waited for that at the end of the last pass)
+            long long t1 = clock64();
             __syncthreads();
             // births that failed, slots left empty (B != K): the live set is made contiguous again before anything reads it
             if (st->holes_due || vload(&st->nfail_gen)) { settle_generation(p, rb, st, s_warp0, true); __syncthreads(); }
-            long long t1 = clock64();
-            bool dump_exit = false, cluster_exit = false;
             if (st->update_pending) {
                 if (!finish_update(p, rb, st, NG, smS.akey, s_chol) && tid == 0) st->status = ST_ERROR;
                 __syncthreads();
                 if (p.clustering) cluster_exit = true;             // leave: the host runs the clustering pass (pc_cluster.cuh), dumps, relaunches
                 else if (rb.ctl) dump_exit = publish_dump(p, rb, st);   // the kernel keeps running
                 else if (p.want_dump) dump_exit = true;              // "sync_dump": leave, the host dumps and relaunches
+            }
+            if (timer) st->cyc_fin += clock64() - t1;
+        }
+        if (cta == 0) {
+            if (d_done) {   // phase D complete on every ranking CTA: phase S1 reads the order they left
+                const long long tb0 = clock64();
+                dtarget += (unsigned)(NG - c0);
+                if (tid == 0) {
+                    unsigned int v;
+                    int backoff = p.backoff;
+                    for (;;) {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&st->dbar) : "memory");
+                        if ((int)(v - dtarget) >= 0) break;
+                        if (backoff) { __nanosleep(backoff); if (backoff < 4096) backoff <<= 1; }
+                    }
+                    __threadfence();
+                }
+                __syncthreads();
+                if (timer) st->dbg[23] += clock64() - tb0;
             }
             long long t2 = clock64();
             bool evidence_due = false;
@@ -967,26 +1022,24 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
             } else if (dump_exit) {
                 if (tid == 0) st->status = ST_DUMP;
             } else if (vload(&st->status) != ST_ERROR) {
-                evidence_due = phase_S1(p, rb, st, smS);
+                evidence_due = phase_S1(p, rb, st, smS, d_done, NG - c0);
                 if (evidence_due && c0 == 0) { __syncthreads(); phase_S2(p, rb, st, smS); evidence_due = false; }
             }
             s2_due = evidence_due;
             __syncthreads();
-            if (timer) {
-                long long t3 = clock64();
-                st->cyc_wait += t1 - t0; st->cyc_fin += t2 - t1; st->cyc_S += t3 - t2; 
-            }
+            if (timer) st->cyc_S += clock64() - t2;
             prep_uid = ~0ull;  // phase S overlays this CTA's chain scratch
         }
+        d_done = false;
         const long long tg0 = clock64();
         group_sync(&st->bar, NG, p.backoff);
         const long long tg1 = clock64();
         if (ctimer) st->dbg[10] += tg1 - tg0;
         // the run's status and the generation's parameters: one load per lane, one latency
         unsigned long long pw = 0;
-        if (lane < 9) pw = __ldcg(&st->pub[lane]);
-        else if (lane == 9) pw = (unsigned long long)(unsigned)vload(&st->status);
-        if ((int)__shfl_sync(FULL, pw, 9) != ST_RUNNING) {
+        if (lane < 10) pw = __ldcg(&st->pub[lane]);
+        else if (lane == 10) pw = (unsigned long long)(unsigned)vload(&st->status);
+        if ((int)__shfl_sync(FULL, pw, 10) != ST_RUNNING) {
             if (timer) st->cyc_total += clock64() - t_start;
             return;
         }
@@ -1096,6 +1149,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                     if (active && sub == 0) {   // a failed birth: settle_generation takes it out of the live set
                         const int failed = !(lfin > Lstar);
                         rb.cfail[k] = failed;
+                        rb.bkey[k] = lfin;   // phase D ranks the babies from here
                         if (failed) { ++nfail; atomicAdd(&st->nfail_gen, 1u); }
                     }
                 }
@@ -1154,7 +1208,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                     double lfin = slice_chain<G, DPL, KIND>(p.cp, M, rb.seed, uid, x, Lstar, b,
                                                       pool + (size_t)(nph_base + (long long)cl * (R - 1)) * T, last, nlike,
                                                       (cta == c0 && warp == 0) ? st->dbg : nullptr, false);
-                    if (sharded) shard_publish(p, last, k, xpar);
+                    if (sharded) shard_publish(p, last, k, xpar, lfin);
                     if (p.clustering) {  // the babies carry their seed's label until the next update
                         for (int e = lane; e < R - 1; e += 32) rb.phl[cur_pool_now][nph_base + (long long)cl * (R - 1) + e] = plab;
                         if (lane == 0) rb.lab[dslot] = plab;
@@ -1162,7 +1216,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                     if (ctimer) st->cyc_slice += clock64() - tc2;
                     if (lane == 0) {   // a failed birth: settle_generation takes it out of the live set
                         const int failed = !(lfin > Lstar);
-                        if (!sharded) rb.cfail[k] = failed;
+                        if (!sharded) { rb.cfail[k] = failed; rb.bkey[k] = lfin; }
                         if (failed) { ++nfail; if (!sharded) atomicAdd(&st->nfail_gen, 1u); }
                     }
                 }
@@ -1201,7 +1255,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                 long long tc2 = clock64();
                 double lfin = slice_chain<G, DPL, KIND>(p.cp, M, rb.seed, uid, x, Lstar, cs,
                                                   pool + (size_t)(nph_base + (long long)cl * (R - 1)) * T, last, nlike, nullptr, false);
-                if (sharded) shard_publish(p, last, k, xpar);
+                if (sharded) shard_publish(p, last, k, xpar, lfin);
                 if (p.clustering) {
                     for (int e = lane; e < R - 1; e += 32) rb.phl[cur_pool_now][nph_base + (long long)cl * (R - 1) + e] = plab;
                     if (lane == 0) rb.lab[dslot] = plab;
@@ -1212,7 +1266,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                 }
                 if (lane == 0) {   // a failed birth: settle_generation takes it out of the live set
                     const int failed = !(lfin > Lstar);
-                    if (!sharded) rb.cfail[k] = failed;
+                    if (!sharded) { rb.cfail[k] = failed; rb.bkey[k] = lfin; }
                     if (failed) { ++nfail; if (!sharded) atomicAdd(&st->nfail_gen, 1u); }
                 }
             }
@@ -1222,30 +1276,46 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
             if (nlike) atomicAdd((unsigned long long*)&st->nlike, nlike);
             if (nfail) atomicAdd((unsigned long long*)&st->nfail, nfail);
         }
-        wtarget = warp_arrive(&st->wbar, GW);
-        have_wtarget = true;
-        if (sharded) {
-            // Close the generation across the GPUs: this rank's chains are done -> CTA 0 sorts their last babies, stores
-            // the run with every rank and passes the cross-GPU barrier -> every warp copies its share of the K last babies
-            // from the incoming buffer into the live array.
-            warp_wait(&st->wbar, wtarget, p.backoff);
-            have_wtarget = false;
-            if (cta == 0) { __syncthreads(); shard_close(p, rb, st, smS); prep_uid = ~0ull; }
-            group_sync(&st->bar, NG, p.backoff);
-            if (vload(&st->status) == ST_ERROR) return;
-            shard_scatter(p, rb, st, gw, GW);
-            group_sync(&st->bar, NG, p.backoff);
-        }
+        const unsigned int wtarget = warp_arrive(&st->wbar, GW);
         // the scratch the next generation's first chain of this warp (pair) will use
         const bool will_chain = knext >= 0;
         const ChainScratch csn = p.paired ? chain_scratch(s_warp0 + (size_t)((warp % (W >> 1)) + (W >> 1) * (int)(pair_seq & 1u)) * p.warp_bytes,
                                                           D, R, LD, p.nh_in_smem != 0, p.cp.like_kind, NPT,
                                                           rb.nh ? rb.nh + ((size_t)cta * W + (warp % (W >> 1)) + (W >> 1) * (int)(pair_seq & 1u)) * R * LD : nullptr)
                                           : cs;
+        // Directions of this warp's first chain of the NEXT generation (counter-addressed: they do not depend on its
+        // outcome).  A helper warp prepares them while the chains of this generation are still slicing; a warp that ran
+        // chains itself does it behind phase D, beside CTA 0's bookkeeping.  Phase U stages its batches in the per-warp
+        // scratch, so an update generation prepares afterwards, and whitens once the new factor is there.
+        auto prep_next = [&]() {
+            prep_uid = (unsigned long long)(nchains_base + B + knext);
+            prep_chain<G * DPL>(D, R, LD, rb.seed, prep_uid, csn, &p.cp);
+            prep_white = false;
+            if (!do_update && !p.clustering) {  // with clusters the factor depends on the chain's seed, which the next phase S decides
+                whiten_chain<(G * DPL + 7) / 8>(D, R, LD, s_chol, csn);
+                prep_white = true;
+            }
+        };
+        const bool prep_early = will_chain && p.paired && !do_update;
+        if (prep_early) prep_next();
+        // every chain of the generation is written
+        const long long tw0 = clock64();
+        warp_wait(&st->wbar, wtarget, p.backoff);
+        const long long tw1 = clock64();
+        if (timer) st->cyc_wait += tw1 - tw0;
+        if (sharded) {
+            // Close the generation across the GPUs: this rank's chains are done -> CTA 0 passes the cross-GPU barrier (every
+            // rank's last babies and keys have arrived) -> every warp copies its share of the K last babies from the incoming
+            // buffer into the live array.
+            if (cta == 0) shard_close(p, st);
+            group_sync(&st->bar, NG, p.backoff);
+            if (vload(&st->status) == ST_ERROR) return;
+            shard_scatter(p, rb, st, gw, GW);
+            if (timer) st->dbg[14] += clock64() - tw1;
+        }
         if (do_update) {
-            long long tu0 = clock64();
-            warp_wait(&st->wbar, wtarget, p.backoff);
             long long tu1 = clock64();
+            if (sharded) group_sync(&st->bar, NG, p.backoff);   // the covariance reads the scattered live points
             // failed births / empty slots: the live set is made contiguous before the covariance reads it (every warp
             // sees the same flags after the barrier)
             if (vload(&st->holes_due) || vload(&st->nfail_gen)) {
@@ -1264,22 +1334,20 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
             if (timer) { st->dbg[2] += ua1 - ua0; st->dbg[3] += ua2 - ua1; st->dbg[4] += ua3 - ua2; st->dbg[5] -= ua3; }
             if (cta == 0 && tid == 0) st->update_pending = 1;
             group_sync(&st->bar, NG, p.backoff);
-            if (timer) { st->cyc_wait += tu1 - tu0; st->cyc_U += clock64() - tu1; st->dbg[5] += clock64(); }
-            have_wtarget = false;
-            if (will_chain) {  // the Cholesky factor is about to change: whiten after the barrier
-                prep_uid = (unsigned long long)(nchains_base + B + knext);
-                prep_chain<G * DPL>(D, R, LD, rb.seed, prep_uid, csn, &p.cp);
-                prep_white = false;
-            }
-        } else if (will_chain) {
-            prep_uid = (unsigned long long)(nchains_base + B + knext);
-            prep_chain<G * DPL>(D, R, LD, rb.seed, prep_uid, csn, &p.cp);
-            prep_white = false;
-            if (!p.clustering) {  // with clusters the factor depends on the chain's seed, which the next phase S decides
-                whiten_chain<(G * DPL + 7) / 8>(D, R, LD, s_chol, csn);
-                prep_white = true;
-            }
+            if (timer) { st->cyc_U += clock64() - tu1; st->dbg[5] += clock64(); }
         }
+        // Phase D: a regular generation (as many births as deaths, none failed -- the failure count is where phase S1
+        // published it) leaves the survivors in order: every chain CTA ranks its share of the live points.  The
+        // decision reads only what every CTA of the run sees alike.
+        d_done = p.off_dkeys != 0 && B == K && K > 0 && K < n &&
+                 (sharded || (unsigned long long)vload(&st->nfail) == __shfl_sync(FULL, pw, 9));
+        if (d_done && cta >= c0) {
+            const long long td0 = clock64();
+            phase_D(p, rb, st, sharded ? p.sh.xrun[xr] + (size_t)xpar * p.batch_K : rb.bkey, cta - c0, NG - c0,
+                    (double*)(smem + p.off_dkeys));
+            if (ctimer) st->dbg[22] += clock64() - td0;
+        }
+        if (will_chain && !prep_early) prep_next();
     }
 }
 
