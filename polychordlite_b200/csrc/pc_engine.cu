@@ -440,6 +440,7 @@ struct HostRun {
     DevArr<int> order, lab, phl0, phl1, cfail;
     DevArr<double> cchol;
     DevArr<long long> pcount;
+    DevArr<unsigned int> pmask;
     DevArr<double> boost;
     DevArr<unsigned long long> boost_win;
     long long boost_mirrored = 0;   // rows of the device list already in the mirror
@@ -808,6 +809,7 @@ struct Engine {
             h.dpart.alloc((size_t)2 * G + 8); h.dpart.zero(stream);
             h.partial.alloc((size_t)G * k.partial_stride);
             h.pcount.alloc((size_t)cap_ph / U_TILE + 2); h.pcount.zero(stream);
+            h.pmask.alloc((size_t)cap_ph / 32 + 8); h.pmask.zero(stream);
             if (k.dense) h.nh.alloc((size_t)G * W * (32 / L.fn.G) * R * dense_slb(L.fn.G * L.fn.DPL));   // slice records of the chains in flight
             else if (!k.nh_in_smem) h.nh.alloc((size_t)G * W * R * k.cp.LD);
             if (k.clustering) {
@@ -820,7 +822,7 @@ struct Engine {
             std::memset(&b, 0, sizeof(b));
             b.st = h.st.p; b.live = h.live.p; b.live_snap = nullptr; b.ctl = nullptr; b.order = h.order.p; b.okey = h.okey.p; b.dead = h.dead.p; b.logw = h.logw.p;
             b.ph[0] = h.ph0.p; b.ph[1] = h.ph1.p; b.chol = h.chol.p; b.cov = h.cov.p; b.partial = h.partial.p;
-            b.pcount = h.pcount.p; b.nh = h.nh.p; b.cap_dead = cap_dead; b.cap_ph = cap_ph; b.gsum = h.gsum.p;
+            b.pcount = h.pcount.p; b.pmask = h.pmask.p; b.nh = h.nh.p; b.cap_dead = cap_dead; b.cap_ph = cap_ph; b.gsum = h.gsum.p;
             b.lab = h.lab.p; b.phl[0] = h.phl0.p; b.phl[1] = h.phl1.p; b.cchol = h.cchol.p;
             b.boost = h.boost.p; b.boost_win = h.boost_win.p; b.cap_boost = cap_boost;
             b.cfail = h.cfail.p; b.bkey = h.bkey.p; b.dpart = h.dpart.p;
@@ -1341,6 +1343,8 @@ struct Engine {
             }
             h.pcount.alloc((size_t)nc / U_TILE + 2);
             h.buf.pcount = h.pcount.p;
+            h.pmask.alloc((size_t)nc / 32 + 8);
+            h.buf.pmask = h.pmask.p;
             h.buf.ph[0] = h.ph0.p; h.buf.ph[1] = h.ph1.p; h.buf.cap_ph = nc;
         }
     }
@@ -1978,16 +1982,26 @@ double pc_measure_fp64_tflops(void) {
 int pc_device_cholesky(const double* a, int D, double* L_out) {
     try {
         device_check();
-        DevArr<double> da((size_t)D * D), dl((size_t)D * D);
-        DevArr<int> fb(1);
+        DevArr<double> da((size_t)D * D), dl((size_t)D * D), dl2((size_t)D * D);
+        DevArr<int> fb(2);
         da.upload(a, (size_t)D * D, g_stream);
-        pc_cholesky_kernel<<<1, 32, 0, g_stream>>>(da.p, dl.p, D, fb.p);
+        // both factorisations of the engine: the one-warp form (per-cluster factors) and the CTA-wide form (the run
+        // kernel's update); they must agree to rounding, the result returned is the run kernel's
+        pc_cholesky_kernel<<<1, 32, 0, g_stream>>>(da.p, dl.p, D, fb.p, 0);
         PC_CUDA(cudaGetLastError());
-        int f = 0;
-        dl.download(L_out, (size_t)D * D, g_stream);
-        fb.download(&f, 1, g_stream);
+        pc_cholesky_kernel<<<1, 256, 0, g_stream>>>(da.p, dl2.p, D, fb.p + 1, 1);
+        PC_CUDA(cudaGetLastError());
+        int f[2] = {0, 0};
+        std::vector<double> Lw((size_t)D * D);
+        dl.download(Lw.data(), (size_t)D * D, g_stream);
+        dl2.download(L_out, (size_t)D * D, g_stream);
+        fb.download(f, 2, g_stream);
         PC_CUDA(cudaStreamSynchronize(g_stream));
-        return f;
+        if (f[0] != f[1]) throw pc::RunError("polychord_b200: the two Cholesky kernels disagree on the fallback");
+        for (size_t e = 0; e < (size_t)D * D; ++e)
+            if (std::fabs(Lw[e] - L_out[e]) > 1e-11 * (1.0 + std::fabs(Lw[e])))
+                throw pc::RunError("polychord_b200: the two Cholesky kernels disagree");
+        return f[1];
     } catch (const std::exception& ex) {
         return fail(-3, ex.what());
     }

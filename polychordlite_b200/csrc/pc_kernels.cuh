@@ -30,7 +30,7 @@ enum Status : int { ST_RUNNING = 0, ST_DONE = 1, ST_NEED_DEAD = 2, ST_NEED_PHANT
 
 constexpr double NEG_BIG = -1e300;  // log(0) stand-in that survives additions without NaN
 constexpr int COV_TPP = 10;         // 8x8 tiles of the moment matrix a warp accumulates per pass of phase U (2 registers each)
-constexpr int U_TILE = 256;         // records per phantom tile of phase U (= threads per CTA)
+constexpr int U_TILE = 32;          // sizes the per-tile arrays of phase U: a tile is at least one warp's 32 records
 constexpr int KNN_K = 10;           // clustering.f90:44: "10 degrees of separation"
 constexpr int MAX_CLUSTERS = 256;   // clusters with a factor of their own; further labels share the last one, which keeps the global factor
 constexpr int U_BATCH = 8;          // records a warp of phase U keeps in flight
@@ -122,7 +122,8 @@ struct RunBuf {
     double* cov;       // D x D column-major
     double* partial;   // per CTA: [0]=count, [1..D]=sum x, then ntri covariance partials
     double* gsum;      // [0] surviving phantoms of all ranks, [2..2+D) mean of live + phantom cube coordinates, [2+D..2+2D) pivot of the next update
-    long long* pcount; // survivor count of each phantom tile (phase U)
+    long long* pcount; // survivor count of each phantom tile (phase U; a tile is one record per thread of a CTA)
+    unsigned int* pmask; // keep mask of each 32-record segment of the phantom pool (phase U, pass A -> pass B)
     double* nh;        // global direction scratch (used when the directions do not fit in smem)
     int* lab;          // clustering: label of every live slot
     int* phl[2];       // clustering: label of every phantom record (compacted with the pools)
@@ -552,6 +553,38 @@ __device__ inline int warp_cholesky(const double* a, double* L, int D) {
         __syncwarp();
         for (int k = lane; k < D; k += 32) L[k + k * D] = sqrt(tr);
         __syncwarp();
+    }
+    return fallback;
+}
+
+// The same factorisation by a whole CTA, right-looking: with r = 1/sqrt(a_ii) column i of L is a(:, i) * r and the trailing
+// lower triangle takes a(j, k) -= (a(j, i) r)(a(k, i) r), both read from the matrix as the previous column left it, so a
+// column costs ONE barrier (and no dependent dot product per entry).  Every thread keeps its entries' (row, column) pairs.
+// a: symmetric, column-major, DESTROYED (the caller keeps its own copy of the covariance); L: zeros above the diagonal.
+// Same fallback as warp_cholesky (utils.F90:621-649: a non-positive pivot -> sqrt(trace) * identity).
+__device__ inline int block_cholesky(double* a, double* L, int D) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    double tr = 0.0;
+    for (int k = 0; k < D; ++k) tr += a[k + k * D];   // (every thread: the fallback's trace, before a is touched)
+    __syncthreads();
+    int fallback = 0;
+    for (int i = 0; i < D; ++i) {
+        const double d = a[i + i * D];   // the same value on every thread
+        if (d <= 0.0) { fallback = 1; break; }
+        const double r = rsqrt(d);
+        for (int e = tid; e < D * D; e += nthr) {
+            const int k = e / D, j = e - k * D;   // entry (j, k), column-major
+            if (k == i) L[e] = j > i ? a[j + i * D] * r : (j == i ? d * r : 0.0);
+            else if (k > i && j >= k) a[e] = fma(-(a[j + i * D] * r), a[k + i * D] * r, a[e]);
+        }
+        __syncthreads();
+    }
+    if (fallback) {
+        __syncthreads();
+        for (int e = tid; e < D * D; e += nthr) L[e] = 0.0;
+        __syncthreads();
+        for (int k = tid; k < D; k += nthr) L[k + k * D] = sqrt(tr);
+        __syncthreads();
     }
     return fallback;
 }

@@ -46,8 +46,10 @@ __global__ void pc_fp64_peak_kernel(double* out, int iters, double a, double b) 
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
-__global__ void pc_cholesky_kernel(const double* a, double* L, int D, int* fb) {
-    int f = warp_cholesky(a, L, D);
+// which = 0: the one-warp factorisation (clustering: one factor per cluster), launched with 32 threads;
+// which = 1: the CTA-wide one of the run kernel's update (a is overwritten), launched with 256 threads
+__global__ void pc_cholesky_kernel(double* a, double* L, int D, int* fb, int which) {
+    int f = which ? block_cholesky(a, L, D) : warp_cholesky(a, L, D);
     if (threadIdx.x == 0) *fb = f;
 }
 

@@ -188,9 +188,89 @@ __device__ inline void settle_generation(const KParams& p, const RunBuf& rb, Dev
     __syncthreads();
 }
 
+// What phase S1 decides for the next generation, written by one thread: contour, deaths and births, bases of the dead /
+// phantom / chain counters, the update decision, and the 64-byte line every warp reads at the release.
+__device__ inline void publish_generation(const KParams& p, const RunBuf& rb, DevRun* st, int n, int K, bool trim,
+                                          long long ndead, const int* newo, const double* newk, double lX_new) {
+    const double Lstar = __ldcg(newk + K - 1);   // (phase D's CTAs may have written it)
+    // births: the live count moves towards its target above the contour, at most 2 batch_K a generation
+    // (constant target: B = K; the batched form of run_time_info.f90:766-777)
+    int B = trim ? 0 : max(0, min(max(target_nlive(p, Lstar), 1) - (n - K), 2 * p.batch_K));
+    if (p.sh.world > 1) B = K;   // a sharded run keeps the live count fixed
+    const long long nph = st->nphantom, nch = st->nchains, ngen = st->ngen + (trim ? 0 : 1);
+    const int order_off = (int)(newo - rb.order);
+    const int do_update = (!trim && lX_new <= st->logX_last_update + p.log_comp) ? 1 : 0;  // nested_sampling.F90:321
+    st->K = K;
+    st->B = B;
+    st->n_gen = n;
+    st->trimmed = 1;
+    st->holes_due = (B != K) ? 1 : 0;
+    st->nfail_gen = 0u;
+    st->Lstar = Lstar;
+    st->order_off = order_off;
+    st->order_valid = 1;
+    st->ndead_base = ndead;
+    st->ndead = ndead + K;
+    st->nph_base = nph;
+    const int Bloc = p.sh.world > 1 ? (B - p.sh.rank + p.sh.world - 1) / p.sh.world : B;  // chains of this rank
+    st->nphantom = nph + (long long)Bloc * (p.cp.R - 1);
+    st->nph_glob += (long long)B * (p.cp.R - 1);
+    st->nchains_base = nch;
+    st->nchains = nch + B;
+    st->ngen = ngen;
+    st->nslices += (long long)B * p.cp.R;
+    st->do_update = do_update;
+    st->status = ST_RUNNING;
+    st->pub[0] = (unsigned long long)__double_as_longlong(Lstar);
+    st->pub[1] = (unsigned long long)ndead;
+    st->pub[2] = (unsigned long long)nph;
+    st->pub[3] = (unsigned long long)nch;
+    st->pub[4] = (unsigned long long)ngen;
+    st->pub[5] = (unsigned long long)(unsigned)K | ((unsigned long long)(unsigned)do_update << 32);
+    st->pub[6] = (unsigned long long)(unsigned)order_off | ((unsigned long long)(unsigned)st->cur_pool << 32);
+    st->pub[7] = (unsigned long long)(unsigned)st->ncl | ((unsigned long long)(unsigned)st->nupdates << 32);
+    st->pub[8] = (unsigned long long)(unsigned)n | ((unsigned long long)(unsigned)B << 32);
+    st->pub[9] = (unsigned long long)st->nfail;
+}
+
+// Phase S1 after phase D in the common case -- the run goes on, nothing has to grow -- on ONE warp of CTA 0, without a
+// block-wide barrier: the termination test from the CTAs' partial sums (they are taken about M0, the largest survivor key),
+// the capacity tests, the publication.  Returns false when anything else is due (termination and the final kill-off, a
+// pool that has to grow, the nprior trim, nfail): phase_S1 then decides from the same inputs.
+__device__ inline bool phase_S1_fast(const KParams& p, const RunBuf& rb, DevRun* st, int nparts) {
+    const int lane = threadIdx.x & 31;
+    const int n = st->n;
+    const long long ndead = st->ndead;
+    if (st->stop_nfail || (!st->trimmed && n > p.n) || p.max_ndead == 0 || (p.max_ndead > 0 && ndead >= p.max_ndead)) return false;
+    int K = min(p.batch_K, n - 1);
+    if (p.max_ndead > 0) K = (int)min((long long)K, (long long)p.max_ndead - ndead);
+    if (K < 1) return false;
+    int* newo = rb.order + (st->order_off ? 0 : p.nmax);
+    const double* oldk = rb.okey + st->order_off;
+    double* newk = rb.okey + (st->order_off ? 0 : p.nmax);
+    if (p.use_prec) {
+        const double M0 = __ldcg(oldk + n - 1);   // phase D's reference point: the largest survivor key
+        double s = 0.0;
+        for (int c = lane; c < nparts; c += 32) s += __ldcg(rb.dpart + c);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        const double lz = M0 + log(s) - log((double)n) + st->logX;   // live_logZ, run_time_info.f90:683-709
+        if (!(lz >= p.log_prec + st->logZ)) return false;              // precision reached (or not a number): the full path ends the run
+    }
+    const int Bmax = 2 * p.batch_K;
+    if (ndead + K + Bmax + p.nmax > rb.cap_dead) return false;
+    const long long nph_test = p.sh.world > 1 ? st->nph_glob : st->nphantom;
+    if (nph_test + (long long)Bmax * (p.cp.R - 1) > rb.cap_ph) return false;
+    if (p.boost_thin > 0.0 && (long long)st->nboost + st->nphantom + (long long)Bmax * (p.cp.R - 1) > rb.cap_boost) return false;
+    // log X after the K deaths: sum_j log((n - j) / (n - j + 1)) telescopes
+    const double lX_new = st->logX + (log((double)(n - K + 1)) - log((double)(n + 1)));
+    if (lane == 0) publish_generation(p, rb, st, n, K, false, ndead, newo, newk, lX_new);
+    return true;
+}
+
 // returns true when the evidence of the K deaths is still to be accumulated (S2).
 // merged: phase D (all CTAs) already wrote the new order into the other half of rb.order / rb.okey and left the CTAs'
-// (max, sum exp) partials of the termination test in rb.dpart[0 .. 2 nparts).
+// partial sums of the termination test in rb.dpart[0 .. nparts).
 __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, const SmemS& sm, bool merged, int nparts) {
     const int tid = threadIdx.x, T = p.cp.T, nthr = blockDim.x;
     const int n = st->n;
@@ -236,14 +316,10 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
     else if (p.max_ndead > 0 && ndead >= p.max_ndead) more = false;
     else if (p.use_prec) {
         double mx = -INFINITY, s = 0.0;
-        if (merged) {   // the CTAs' partials, combined in CTA order
-            double pm = -INFINITY, ps = 0.0;
-            for (int c = tid; c < nparts; c += nthr) {   // (nparts <= blockDim.x in every launch geometry; the loop keeps it general)
-                const double cm = __ldcg(rb.dpart + 2 * c), csum = __ldcg(rb.dpart + 2 * c + 1);
-                if (cm > pm) { ps = ps * exp(pm - cm) + csum; pm = cm; } else if (csum > 0.0) ps += csum * exp(cm - pm);
-            }
-            mx = block_max(pm, sc);
-            s = block_sum(ps > 0.0 ? ps * exp(pm - mx) : 0.0, sc);
+        if (merged) {   // the CTAs' partial sums of exp(logL - M0), M0 the largest survivor key (phase D)
+            mx = __ldcg(oldk + n - 1);
+            for (int c = tid; c < nparts; c += nthr) s += __ldcg(rb.dpart + c);
+            s = block_sum(s, sc);
         } else {
             for (int i = tid; i < n; i += nthr) mx = fmax(mx, key_at(i));
             mx = block_max(mx, sc);
@@ -340,42 +416,7 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
     long long q3 = clock64();
     const double lX_new = logX_after(st->logX, K, n, sc);
     if (tid == 0) {
-        const double Lstar = __ldcg(newk + K - 1);   // (phase D's CTAs may have written it)
-        // births: the live count moves towards its target above the contour, at most 2 batch_K a generation
-        // (constant target: B = K; the batched form of run_time_info.f90:766-777)
-        int B = trim ? 0 : max(0, min(max(target_nlive(p, Lstar), 1) - (n - K), 2 * p.batch_K));
-        if (p.sh.world > 1) B = K;   // a sharded run keeps the live count fixed
-        st->K = K;
-        st->B = B;
-        st->n_gen = n;
-        st->trimmed = 1;
-        st->holes_due = (B != K) ? 1 : 0;
-        st->nfail_gen = 0u;
-        st->Lstar = Lstar;
-        st->order_off = (int)(newo - rb.order);
-        st->order_valid = 1;
-        st->ndead_base = ndead;
-        st->ndead = ndead + K;
-        st->nph_base = st->nphantom;
-        const int Bloc = p.sh.world > 1 ? (B - p.sh.rank + p.sh.world - 1) / p.sh.world : B;  // chains of this rank
-        st->nphantom += (long long)Bloc * (p.cp.R - 1);
-        st->nph_glob += (long long)B * (p.cp.R - 1);
-        st->nchains_base = st->nchains;
-        st->nchains += B;
-        if (!trim) st->ngen += 1;
-        st->nslices += (long long)B * p.cp.R;
-        st->do_update = (!trim && lX_new <= st->logX_last_update + p.log_comp) ? 1 : 0;  // nested_sampling.F90:321
-        st->status = ST_RUNNING;
-        st->pub[0] = (unsigned long long)__double_as_longlong(st->Lstar);
-        st->pub[1] = (unsigned long long)st->ndead_base;
-        st->pub[2] = (unsigned long long)st->nph_base;
-        st->pub[3] = (unsigned long long)st->nchains_base;
-        st->pub[4] = (unsigned long long)st->ngen;
-        st->pub[5] = (unsigned long long)(unsigned)st->K | ((unsigned long long)(unsigned)st->do_update << 32);
-        st->pub[6] = (unsigned long long)(unsigned)st->order_off | ((unsigned long long)(unsigned)st->cur_pool << 32);
-        st->pub[7] = (unsigned long long)(unsigned)st->ncl | ((unsigned long long)(unsigned)st->nupdates << 32);
-        st->pub[8] = (unsigned long long)(unsigned)n | ((unsigned long long)(unsigned)B << 32);
-        st->pub[9] = (unsigned long long)st->nfail;
+        publish_generation(p, rb, st, n, K, trim, ndead, newo, newk, lX_new);
         long long q4 = clock64();
         st->dbg[6] += q1 - q0; st->dbg[7] += q2 - q1; st->dbg[8] += q3 - q2; st->dbg[9] += q4 - q3;
     }
@@ -398,8 +439,8 @@ __device__ inline void phase_S2(const KParams& p, const RunBuf& rb, DevRun* st, 
 // shared memory; a warp takes one live point at a time, its lanes count the babies below it (ties by slot, as everywhere),
 // a binary search counts the survivors below a baby, and lane 0 writes (slot, key) to its place in the other half of
 // rb.order / rb.okey.  Nothing is sorted and nothing depends on another point's rank: the phase is one pass, spread over
-// cta_rel = 0 .. nctas-1.  Beside it every CTA leaves (max, sum exp(logL - max)) of the points it ranked in rb.dpart for the
-// termination test (live_logZ, run_time_info.f90:683-709).
+// cta_rel = 0 .. nctas-1.  Beside it every CTA leaves the sum of exp(logL - M0) over the points it ranked (M0: the largest
+// survivor key) in rb.dpart for the termination test (live_logZ, run_time_info.f90:683-709).
 __device__ inline void phase_D(const KParams& p, const RunBuf& rb, DevRun* st, const double* bkeys, int cta_rel, int nctas,
                                double* s_keys) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5, nthr = blockDim.x;
@@ -415,7 +456,8 @@ __device__ inline void phase_D(const KParams& p, const RunBuf& rb, DevRun* st, c
     for (int j = tid; j < K; j += nthr) sb[j] = __ldcg(bkeys + j);
     for (int i = tid; i < m; i += nthr) ss[i] = __ldcg(oldk + K + i);
     __syncthreads();
-    double pm = -INFINITY, ps = 0.0;   // lane 0: running max and sum of exp(key - max) over the warp's points
+    const double M0 = ss[m - 1];   // the largest survivor key: reference point of the termination sums (the same on every CTA)
+    double ps = 0.0;               // lane 0: sum of exp(key - M0) over the warp's points
     for (int e = cta_rel * W + warp; e < n; e += nctas * W) {
         const bool baby = e >= m;
         const int idx = baby ? e - m : e;
@@ -442,21 +484,15 @@ __device__ inline void phase_D(const KParams& p, const RunBuf& rb, DevRun* st, c
         if (lane == 0) {
             newo[rank] = slot;
             newk[rank] = key;
-            if (key > pm) { ps = ps * exp(pm - key) + 1.0; pm = key; } else ps += exp(key - pm);
+            ps += exp(key - M0);
         }
     }
-    if (lane == 0) { sp[2 * warp] = pm; sp[2 * warp + 1] = ps; }
+    if (lane == 0) sp[warp] = ps;
     __syncthreads();
     if (tid == 0) {   // the warps' partials in warp order
-        double cm = -INFINITY, cs = 0.0;
-        for (int w = 0; w < W; ++w) {
-            const double wm = sp[2 * w], ws = sp[2 * w + 1];
-            if (ws > 0.0) {
-                if (wm > cm) { cs = cs * exp(cm - wm) + ws; cm = wm; } else cs += ws * exp(wm - cm);
-            }
-        }
-        rb.dpart[2 * cta_rel] = cm;
-        rb.dpart[2 * cta_rel + 1] = cs;
+        double cs = 0.0;
+        for (int w = 0; w < W; ++w) cs += sp[w];
+        rb.dpart[cta_rel] = cs;
         // arrive (CTA 0 waits for every ranking CTA before phase S1 reads the order; nobody else waits: the CTAs go
         // on to prepare their next chains)
         __threadfence();
@@ -526,19 +562,20 @@ __device__ __forceinline__ bool phantom_kept(const double* rec, int T, double Ls
 }
 
 __device__ inline void phase_UA(const KParams& p, const RunBuf& rb, DevRun* st, int cta, int NG) {
-    const int tid = threadIdx.x, T = p.cp.T;
+    const int tid = threadIdx.x, lane = tid & 31, T = p.cp.T, UT = blockDim.x, W = UT >> 5;   // a tile: one record per thread
     const long long total = vload(&st->nphantom);
     const double Lstar = vload(&st->Lstar);
     const double* src = rb.ph[vload(&st->cur_pool)];
-    const long long ntiles = (total + U_TILE - 1) / U_TILE;
+    const long long ntiles = (total + UT - 1) / UT;
     const bool boosting = p.boost_thin > 0.0;
     const unsigned long long bwin = boosting ? ((unsigned long long)vload(&st->ndead_upd) << 32) | (unsigned long long)vload(&st->ndead) : 0ull;
-    // keys of up to four tiles in flight before the first count
+    // keys of up to four tiles in flight before the first count.  Beside the tile's count, every 32-record segment
+    // leaves its keep mask: pass B takes its records and its place inside the tile from the masks, without a barrier.
     for (long long t0 = cta; t0 < ntiles; t0 += 4LL * NG) {
         bool keep[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const long long t = t0 + (long long)j * NG, rec = t * U_TILE + tid;
+            const long long t = t0 + (long long)j * NG, rec = t * UT + tid;
             keep[j] = t < ntiles && rec < total && phantom_kept(src + (size_t)rec * T, T, Lstar);
             if (boosting && t < ntiles && rec < total && !keep[j]) boost_harvest(p, rb, st, src + (size_t)rec * T, bwin);
         }
@@ -546,6 +583,8 @@ __device__ inline void phase_UA(const KParams& p, const RunBuf& rb, DevRun* st, 
         for (int j = 0; j < 4; ++j) {
             const long long t = t0 + (long long)j * NG;
             if (t < ntiles) {  // uniform over the CTA
+                const unsigned bal = __ballot_sync(FULL, keep[j]);
+                if (lane == 0) rb.pmask[t * W + (tid >> 5)] = bal;
                 const int c = __syncthreads_count(keep[j]);
                 if (tid == 0) rb.pcount[t] = c;
             }
@@ -570,7 +609,7 @@ __device__ inline void phase_UB(const KParams& p, const RunBuf& rb, DevRun* st, 
     const int pool = vload(&st->cur_pool);
     const double* __restrict__ src = rb.ph[pool];
     double* __restrict__ dst = rb.ph[pool ^ 1];
-    const long long ntiles = (total + U_TILE - 1) / U_TILE;
+    const long long ntiles = (total + blockDim.x - 1) / blockDim.x;   // tiles of one record per thread (phase_UA)
     const int lchunk = (n + NG - 1) / NG, l0 = min(n, cta * lchunk), l1 = min(n, l0 + lchunk);
     // per warp: [0..Dpad) pivot (warp 0's copy is used) | U_BATCH x SX staged rows.  After a pass the whole per-warp
     // area (behind the pivot) is reused as the CTA's Dp8 x Dp8 matrix the warps add their tiles to, in warp order.
@@ -578,10 +617,11 @@ __device__ inline void phase_UB(const KParams& p, const RunBuf& rb, DevRun* st, 
     double* s_x = (double*)(smem_warp0 + (size_t)warp * warp_bytes) + Dpad;
     double* s_M = (double*)smem_warp0 + Dpad;
     long long* s_base = (long long*)(s_cnt + 16);  // [0] survivors in the tiles before this CTA's first tile, [1] all survivors
+    const int UT = blockDim.x;   // records per tile (phase_UA)
     const bool tmr = (cta == 0 && tid == 0);
     const long long z0 = clock64();
     __syncthreads();
-    // survivors before tile `upto` (exclusive) starting from tile `from`: one warp, coalesced
+    // survivors before tile `upto` (exclusive) starting from tile `from`: one warp, coalesced; every lane gets the sum
     auto count_range = [&](long long from, long long upto) -> long long {
         long long c = 0;
         for (long long g = from + lane; g < upto; g += 32) c += __ldcg(rb.pcount + g);
@@ -616,37 +656,53 @@ __device__ inline void phase_UB(const KParams& p, const RunBuf& rb, DevRun* st, 
         for (int e = lane; e < U_BATCH * SX; e += 32) s_x[e] = 0.0;  // the padding columns stay zero
         __syncwarp();
         // The CTA's work items: its phantom tiles (t = cta, cta + NG, ...), then its share of the live points cut
-        // into pseudo-tiles of U_TILE records (never copied).  A warp takes the kept records of its 32-record
-        // segment in batches of U_BATCH: all loads of a batch are issued before the first use.  Pass 0 copies
-        // the phantom records to their place in the other pool (stable compaction).
+        // into pseudo-tiles of UT records (never copied).  A warp takes the kept records of its 32-record segment
+        // (the mask pass A left) in batches of U_BATCH: all loads of a batch are issued before the first use.  Pass 0
+        // copies the phantom records to their place in the other pool (stable compaction): the tile's offset is the
+        // prefix of the tile counts, the segment's place inside the tile the population of the masks before it.  The
+        // warps of a CTA run through their items independently; the next item's masks and counts are fetched while the
+        // current one is worked on.
         long long tbase = base;
         const long long z1 = clock64();
         if (tmr) st->dbg[12] += z1 - z0;
         const long long my_tiles = (ntiles > cta) ? (ntiles - cta + NG - 1) / NG : 0;
         const int my_live = (p.sh.rank == 0) ? (l1 - l0) : 0;  // the live points are replicated: rank 0 counts them
-        const long long my_items = my_tiles + (my_live + U_TILE - 1) / U_TILE;
+        const long long my_items = my_tiles + (my_live + UT - 1) / UT;
+        // masks of the tile's segments (lane w holds segment w's) and, per lane, its share of the counts of the tiles
+        // between this tile and the CTA's next one
+        auto fetch = [&](long long t, unsigned& mk, long long& cr) {
+            mk = (lane < W && t < ntiles) ? __ldcg(rb.pmask + t * W + lane) : 0u;
+            cr = 0;
+            if (pass == 0)
+                for (long long g = t + lane; g < min(t + NG, ntiles); g += 32) cr += __ldcg(rb.pcount + g);
+        };
+        unsigned mk_n = 0;
+        long long cr_n = 0;
+        if (my_tiles > 0) fetch(cta, mk_n, cr_n);
         for (long long it = 0; it < my_items; ++it) {
             const bool is_ph = it < my_tiles;
             const long long t = cta + it * NG;
             const double* __restrict__ rbase;   // record 0 of this warp's segment
-            bool keep;
-            if (is_ph) {
-                const long long tile = t * U_TILE, rec = tile + tid;
-                keep = rec < total && phantom_kept(src + (size_t)rec * T, T, Lstar);
-                rbase = src + (size_t)(tile + warp * 32) * T;
-            } else {
-                const int lrec = l0 + (int)(it - my_tiles) * U_TILE + tid;
-                keep = lrec < l1;
-                rbase = rb.live + (size_t)(l0 + (int)(it - my_tiles) * U_TILE + warp * 32) * T;
-            }
-            const unsigned bal = __ballot_sync(FULL, keep);
+            unsigned bal;
             int woff = 0;
+            long long tnext = 0;
             const bool copy = is_ph && pass == 0;
-            if (copy) {  // survivor number woff+kk of the tile goes to tbase+woff+kk
-                __syncthreads();
-                if (lane == 0) s_cnt[warp] = __popc(bal);
-                __syncthreads();
-                for (int w = 0; w < warp; ++w) woff += s_cnt[w];
+            if (is_ph) {
+                const unsigned mk = mk_n;
+                long long cr = cr_n;
+                if (it + 1 < my_tiles) fetch(t + NG, mk_n, cr_n);   // in flight while this tile is worked on
+                bal = __shfl_sync(FULL, mk, warp);
+                woff = __reduce_add_sync(FULL, lane < warp ? __popc(mk) : 0);
+                if (copy) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) cr += __shfl_xor_sync(FULL, cr, o);
+                    tnext = tbase + cr;
+                }
+                rbase = src + (size_t)(t * UT + warp * 32) * T;
+            } else {
+                const int lrec = l0 + (int)(it - my_tiles) * UT + tid;
+                bal = __ballot_sync(FULL, lrec < l1);
+                rbase = rb.live + (size_t)(l0 + (int)(it - my_tiles) * UT + warp * 32) * T;
             }
             const int jmax = copy ? JT : JD;
             unsigned rem = bal;
@@ -690,16 +746,7 @@ __device__ inline void phase_UB(const KParams& p, const RunBuf& rb, DevRun* st, 
                 }
                 kk += nb;
             }
-            // offset of this CTA's next phantom tile
-            if (copy && t + NG < ntiles) {
-                __syncthreads();
-                if (warp == 0) {
-                    const long long c = count_range(t, t + NG);
-                    if (lane == 0) s_base[0] = tbase + c;
-                }
-                __syncthreads();
-                tbase = s_base[0];
-            }
+            if (copy) tbase = tnext;   // offset of this CTA's next phantom tile
         }
         const long long z3 = clock64();
         if (tmr) st->dbg[13] += z3 - z1;
@@ -810,10 +857,10 @@ __device__ inline bool finish_update(const KParams& p, const RunBuf& rb, DevRun*
     }
     __syncthreads();
     const long long f2 = clock64();
-    int fb = 0;
-    if (tid < 32) fb = warp_cholesky(s_cov, s_L, D);  // calc_cholesky (utils.F90:621-649) in shared memory
+    for (int e = tid; e < D * D; e += blockDim.x) rb.cov[e] = s_cov[e];
     __syncthreads();
-    for (int e = tid; e < D * D; e += blockDim.x) { rb.cov[e] = s_cov[e]; rb.chol[e] = s_L[e]; }
+    const int fb = block_cholesky(s_cov, s_L, D);  // calc_cholesky (utils.F90:621-649) in shared memory, by the whole CTA
+    for (int e = tid; e < D * D; e += blockDim.x) rb.chol[e] = s_L[e];
     if (tid == 0) {
         const long long f3 = clock64();
         st->dbg[16] += f1 - f0; st->dbg[17] += f2 - f1; st->dbg[18] += f3 - f2;
@@ -1022,7 +1069,15 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
             } else if (dump_exit) {
                 if (tid == 0) st->status = ST_DUMP;
             } else if (vload(&st->status) != ST_ERROR) {
-                evidence_due = phase_S1(p, rb, st, smS, d_done, NG - c0);
+                // after phase D the common case is decided by one warp; everything else by the full phase S1
+                bool fast = false;
+                if (d_done) {
+                    __shared__ int s_fast;
+                    if (warp == 0) { const bool f = phase_S1_fast(p, rb, st, NG - c0); if (lane == 0) s_fast = f ? 1 : 0; }
+                    __syncthreads();
+                    fast = s_fast != 0;
+                }
+                evidence_due = fast ? true : phase_S1(p, rb, st, smS, d_done, NG - c0);
                 if (evidence_due && c0 == 0) { __syncthreads(); phase_S2(p, rb, st, smS); evidence_due = false; }
             }
             s2_due = evidence_due;
