@@ -119,6 +119,9 @@ void pc_uniform_prior(double* cube, double* theta, int nDims); /* theta = lo + (
  *                     normally pairs every chain warp with a helper warp)
  *   "no_phase_d"      1: keep the order of the live points on one CTA (phase S); normally every CTA of a run
  *                     ranks its share of the live points after a regular generation (phase D)
+ *   "resume_text"     1: <root>.resume is written in the reference's text layout (read_write.F90:219-288) instead of the
+ *                     engine's binary one.  Reading accepts both layouts whatever this option says (and the files
+ *                     pypolychord writes for cube_samples, polychord.py:650-789).
  *   "resume_interval" seconds between two rewrites of the resume file at updates (default 1; 0 = every update)
  *   "cap_dead0", "cap_ph0"  initial capacity (records) of the dead / phantom pools; 0 = automatic.
  *                     The pools grow on demand either way (the kernel exits, the host reallocates, relaunches).
@@ -256,6 +259,14 @@ int pc_device_cholesky(const double* a, int D, double* L_out);
  * flags: 1 stats, 2 live, 4 dead, 8 prior (_prior.txt; prior_info is written by the run), 16 weighted posterior, 32 equally weighted posterior.
  * dead_rows / live_rows: rows [theta(nDims), phi(nDerived), birth contour, logL]; dead_logw[i] = log weight + logL. */
 void pc_format_e24(double value, char* out25);
+
+/* Host-only: parse a resume file in the reference's TEXT layout (src/polychord/read_write.F90:219-288 writes it,
+ * :384-476 reads it; pypolychord/polychord.py:650-789 writes it for cube_samples).  ints[8] = {nDims, nDerived, ndead,
+ * ncluster, ncluster_dead, live points, phantoms, likelihood calls}; reals[6] = {logZ, logZ2, log sum_p X_p, last
+ * update volume, lowest and highest live logL}.  A non-empty out_path re-writes what was read in the same layout (one
+ * active cluster only).  Returns 0; -2 for a malformed file, -3 for another failure (the message goes to stderr;
+ * a probe never exits the process). */
+int pc_resume_text_probe(const char* path, long long* ints, double* reals, const char* out_path);
 int pc_write_files(const char* base_dir, const char* file_root, int flags, int nDims, int nDerived, long long ndead,
                    const double* dead_rows, const double* dead_logw, int nlive, const double* live_rows, double logZ,
                    double logZerr, long long nlike, int num_repeats, double compression_factor, unsigned seed);

@@ -27,7 +27,7 @@ EXPORTS = [
     "pc_unit_prior", "pc_uniform_prior", "pc_set_option", "pc_get_option", "pc_set_stream", "pc_release_memory", "pc_mgpu_create", "pc_mgpu_attach", "pc_mgpu_destroy",
     "pc_last_run_info", "pc_run", "pc_run_ensemble", "pc_slice_chains", "pc_calculate_points",
     "pc_device_philox", "pc_device_uniforms", "pc_device_inv_normal_cdf", "pc_device_directions",
-    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points", "pc_set_grades", "pc_set_resume", "pc_measure_fp64_tflops", "pc_ini_prior_transform", "pc_last_boosted", "pc_maximise", "pc_prior_log_density", "pc_set_initial_live", "pc_write_files_boosted", "pc_set_nlives",
+    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points", "pc_set_grades", "pc_set_resume", "pc_measure_fp64_tflops", "pc_ini_prior_transform", "pc_last_boosted", "pc_maximise", "pc_prior_log_density", "pc_set_initial_live", "pc_write_files_boosted", "pc_set_nlives", "pc_resume_text_probe",
 ]
 
 
@@ -326,6 +326,21 @@ def format_e24(value):
     L.pc_format_e24.restype = None
     L.pc_format_e24(float(value), buf)
     return buf.value.decode()
+
+
+def resume_text_probe(path, out_path=None):
+    """pc_resume_text_probe: parse a resume file in the reference's text layout (host only); optionally re-write it."""
+    L = lib()
+    L.pc_resume_text_probe.argtypes = [C.c_char_p, C.POINTER(C.c_longlong), C.POINTER(C.c_double), C.c_char_p]
+    L.pc_resume_text_probe.restype = C.c_int
+    ints = (C.c_longlong * 8)()
+    reals = (C.c_double * 6)()
+    rc = L.pc_resume_text_probe(str(path).encode(), ints, reals, str(out_path).encode() if out_path else None)
+    if rc != 0:
+        raise ValueError(f"pc_resume_text_probe: status {rc} (malformed resume file; the message is on stderr)")
+    keys_i = ["nDims", "nDerived", "ndead", "ncluster", "ncluster_dead", "nlive", "nphantom", "nlike"]
+    keys_r = ["logZ", "logZ2", "logX", "logX_last_update", "logL_min", "logL_max"]
+    return {**{k: int(v) for k, v in zip(keys_i, ints)}, **{k: float(v) for k, v in zip(keys_r, reals)}}
 
 
 def write_files(base_dir, file_root, nDims, nDerived, dead_rows, dead_logw, live_rows, logZ, logZerr, nlike,

@@ -22,6 +22,7 @@
 #include "pc_errors.h"
 #include "pc_probes.cuh"
 #include "pc_files.h"
+#include "pc_resume_text.h"
 #include "pc_ini.h"
 #include "pc_maximise.h"
 #include "pc_hostchain.cuh"
@@ -192,6 +193,7 @@ struct Options {
     int nh_global = 0;  // force the direction scratch into global memory (testing)
     int no_pairing = 0; // keep the helper-warp preparation off (testing)
     int no_phase_d = 0; // order the live points on CTA 0 only (testing: phase D off)
+    int resume_text = 0; // write_resume writes the reference's text layout (read_write.F90:219-288) instead of the engine's binary one
     int sync_dump = 0;  // the kernel exits at every update for the dumper instead of handing dumps over while running
     long long cap_dead0 = 0, cap_ph0 = 0;  // initial pool capacities in records (0 = automatic)
 };
@@ -724,7 +726,10 @@ struct Engine {
         // read_resume: a file of this run's shape continues the run (nested_sampling.F90:175-183)
         // (the caller's cube_samples win over an existing file, as in the reference: polychord.py:576-579 overwrites the
         // resume file with them)
-        if (g_resume.read && g_init_n == 0 && nruns == 1 && g_mgpu.world <= 1 && read_resume_file(g_resume.path, rd)) {
+        if (g_resume.read && g_init_n == 0 && nruns == 1 && g_mgpu.world <= 1 && pc::is_reference_resume(g_resume.path)) {
+            import_reference_resume(g_resume.path, (unsigned)seeds[0]);   // the reference's text layout (or pypolychord's)
+            resumed = true;
+        } else if (g_resume.read && g_init_n == 0 && nruns == 1 && g_mgpu.world <= 1 && read_resume_file(g_resume.path, rd)) {
             const ResumeHeader& rh = rd.h;
             bool same = rh.D == k.cp.D && rh.P == k.cp.P && rh.n == k.n && rh.nmax == k.nmax && rh.R == k.cp.R && rh.batch_K == K &&
                         rh.like_kind == ms.like_kind && rh.clustering == k.clustering && rh.ngrade == k.cp.ngrade;
@@ -1261,6 +1266,112 @@ struct Engine {
         cluster_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count();
     }
 
+    // read_resume_file (read_write.F90:384-476) for a file in the reference's text layout -- written by the reference, by
+    // pypolychord's _make_resume_file (polychord.py:650-789: a run started from the caller's live points) or by this
+    // engine with the option "resume_text".  The file's state becomes the ResumeData the binary reader would have
+    // produced, and the run continues in this engine's schedule.  nDims, nDerived and the grades must match (fatal
+    // otherwise, :402-417).  Several clusters are taken as one (pc_resume_text.h).  The file carries no chain counter:
+    // the chains are numbered from the dead count on, so a continuation is a valid run but not the bits of the
+    // uninterrupted one (the binary layout gives that).
+    void import_reference_resume(const std::string& path, unsigned seed) {
+        const KParams& k = L.kp;
+        pc::RefResume r;
+        pc::read_reference_resume(path, r);
+        const int D = k.cp.D, P = k.cp.P, T = k.cp.T;
+        if (r.nDims != D) throw pc::ArgError("polychord_b200: resume error: nDims does not match");
+        if (r.nDerived != P) throw pc::ArgError("polychord_b200: resume error: nDerived does not match");
+        const int ngrade = std::max(1, k.cp.ngrade);
+        if ((int)r.grade_dims.size() != ngrade) throw pc::ArgError("polychord_b200: resume error: number of grades does not match");
+        for (int g = 0; g < ngrade; ++g)
+            if (r.grade_dims[g] != (k.cp.ngrade > 1 ? k.cp.gdims[g] : D)) throw pc::ArgError("polychord_b200: resume error: Grades do not match");
+        long long n = 0, nph = 0;
+        for (int c = 0; c < r.ncluster; ++c) { n += r.nlive[c]; nph += r.nphantom[c]; }
+        if (n < 2) throw pc::ArgError("polychord_b200: the resume file holds fewer than two live points (the run it describes has finished)");
+        if (n > k.nmax) throw pc::ArgError("polychord_b200: the resume file holds more live points than this run's nlive / nprior allow");
+        auto lse = [](const std::vector<double>& v) {
+            double m = -INFINITY;
+            for (double x : v) m = std::max(m, x);
+            if (!std::isfinite(m)) return m;
+            double s2 = 0.0;
+            for (double x : v) s2 += std::exp(x - m);
+            return m + std::log(s2);
+        };
+        std::memset(&rd.h, 0, sizeof(rd.h));
+        std::memcpy(rd.h.magic, RESUME_MAGIC, 8);
+        rd.h.version = 1; rd.h.sizeof_devrun = (int)sizeof(DevRun);
+        rd.h.D = D; rd.h.P = P; rd.h.n = k.n; rd.h.nmax = k.nmax; rd.h.R = k.cp.R; rd.h.batch_K = k.batch_K; rd.h.like_kind = ms.like_kind;
+        rd.h.clustering = k.clustering; rd.h.ngrade = k.cp.ngrade;
+        for (int g = 0; g < MAX_GRADES; ++g) { rd.h.gdims[g] = k.cp.gdims[g]; rd.h.greps[g] = k.cp.greps[g]; }
+        rd.h.seed = seed; rd.h.logzero = S.logzero;
+        DevRun& st = rd.st;
+        std::memset(&st, 0, sizeof(st));
+        st.logZ = r.logZ; st.logZ2 = r.logZ2;
+        st.logX = lse(r.logXp); st.logZX = lse(r.logZXp); st.logXX = lse(r.logXpXq);
+        st.logX_last_update = r.logX_last_update;
+        st.ndead = r.ndead; st.ndead_upd = r.ndead;
+        st.nlike = 0;
+        for (long long v : r.nlike) st.nlike += v;
+        st.nchains = r.ndead;
+        st.nphantom = nph; st.nph_glob = nph; st.ph_kept = nph;
+        st.status = ST_RUNNING; st.initialised = 1; st.order_valid = 0; st.ncl = 1; st.n = (int)n; st.trimmed = 1;
+        rd.live = r.live;
+        rd.order.assign(2 * (size_t)k.nmax, 0);
+        rd.okey.assign(2 * (size_t)k.nmax, 0.0);
+        rd.dead = r.dead; rd.logw = r.logweights; rd.ph = r.phantom;
+        rd.chol.assign(r.cholesky.begin(), r.cholesky.begin() + (size_t)D * D);   // the first cluster's factor until the next update
+        rd.cov.assign(r.covmat.begin(), r.covmat.begin() + (size_t)D * D);
+        rd.gsum.assign((size_t)2 * D + 4, 0.0);
+        rd.gsum[0] = (double)nph;
+        for (int e = 0; e < D; ++e) rd.gsum[2 + e] = rd.gsum[2 + D + e] = 0.5;   // pivot of the first covariance: the cube centre (init_phase)
+        rd.lab.clear(); rd.phl.clear(); rd.cchol.clear(); rd.boost.clear(); rd.boost_win.clear();
+        if (k.clustering) {
+            rd.lab.assign((size_t)n, 0); rd.phl.assign((size_t)nph, 0);
+            rd.cchol = rd.chol;
+        }
+        if ((long long)rd.live.size() != n * T || (long long)rd.dead.size() != r.ndead * T || (long long)rd.ph.size() != nph * T)
+            throw pc::ArgError("polychord_b200: the resume file's point arrays do not have the run's record length");
+    }
+
+    // write_resume_file (read_write.F90:219-288) in the reference's text layout: this engine's state as ONE cluster (its
+    // evidence is global), every dead point in the global posterior list
+    void export_reference_resume(const std::string& path, const ResumeData& w) {
+        const KParams& k = L.kp;
+        const DevRun& st = w.st;
+        const int D = k.cp.D, P = k.cp.P, T = k.cp.T;
+        const int n = st.status == ST_DONE ? 0 : st.n;   // after the final kill-off every live point is in the dead list (nested_sampling.F90:381-384)
+        pc::RefResume r;
+        r.nDims = D; r.nDerived = P; r.ndead = st.ndead; r.ncluster = 1; r.ncluster_dead = 0;
+        if (k.cp.ngrade > 1) {
+            for (int g = 0; g < k.cp.ngrade; ++g) { r.grade_dims.push_back(k.cp.gdims[g]); r.num_repeats.push_back(k.cp.greps[g]); r.nlike.push_back(g == 0 ? st.nlike : 0); }
+        } else { r.grade_dims = {D}; r.num_repeats = {k.cp.R}; r.nlike = {st.nlike}; }
+        r.nlive = {n}; r.nphantom = {(int)st.nphantom};
+        r.logZ = st.logZ; r.logZ2 = st.logZ2; r.thin_posterior = k.boost_thin;
+        double lmin = INFINITY;
+        for (int i = 0; i < n; ++i) lmin = std::min(lmin, w.live[(size_t)i * T + T - 1]);
+        r.logLp = {lmin}; r.logXp = {st.logX}; r.logX_last_update = st.logX_last_update;
+        r.logZXp = {st.logZX}; r.logZp = {st.logZ}; r.logZp2 = {st.logZ2}; r.logZpXp = {st.logZX}; r.logXpXq = {st.logXX};
+        r.covmat = w.cov; r.cholesky = w.chol;
+        r.live.assign(w.live.begin(), w.live.begin() + (size_t)n * T); r.dead = w.dead; r.logweights = w.logw; r.phantom = w.ph;
+        // the dead points as global posterior points [logX, logL, log-weight, logZ, theta, derived] (settings.f90:189-204;
+        // the reference's writers use the weight, logL and the parameters: read_write.F90:556-560)
+        const int npost = 4 + D + P;
+        r.nposterior_global = st.ndead;
+        r.posterior_global.resize((size_t)st.ndead * npost);
+        double mlw = S.logzero;
+        for (long long i = 0; i < st.ndead; ++i) {
+            const double* rec = &w.dead[(size_t)i * T];
+            double* o = &r.posterior_global[(size_t)i * npost];
+            o[0] = w.logw[i] + std::log((double)k.n + 1.0);
+            o[1] = rec[T - 1];
+            o[2] = w.logw[i];
+            o[3] = st.logZ;
+            std::memcpy(o + 4, rec + D, (size_t)(D + P) * sizeof(double));
+            mlw = std::max(mlw, w.logw[i] + rec[T - 1]);
+        }
+        r.maxlogweight = {mlw};
+        pc::write_reference_resume(path, r);
+    }
+
     // write_resume_file (read_write.F90:219-288): the state between two generations
     void write_resume(bool final_call) {
         if (!g_resume.write || nruns != 1 || g_mgpu.world > 1) return;
@@ -1301,6 +1412,13 @@ struct Engine {
         PC_CUDA(cudaStreamSynchronize(stream));
         d2h += (long long)(w.live.size() + w.dead.size() + w.ph.size()) * 8;
         const std::string tmp = g_resume.path.substr(0, g_resume.path.size() - 7) + "_temp.resume";
+        if (g_opt.resume_text) {
+            export_reference_resume(tmp, w);
+            std::rename(tmp.c_str(), g_resume.path.c_str());
+            resume_written = true;
+            resume_last = std::chrono::steady_clock::now();
+            return;
+        }
         FILE* f = std::fopen(tmp.c_str(), "wb");
         if (!f) throw pc::RunError("polychord_b200: cannot write " + tmp);
         std::fwrite(&w.h, sizeof(w.h), 1, f);
@@ -1547,6 +1665,7 @@ int pc_set_option(const char* name, double value) {
     else if (s == "nh_global") g_opt.nh_global = (int)value;
     else if (s == "no_pairing") g_opt.no_pairing = (int)value;
     else if (s == "no_phase_d") g_opt.no_phase_d = (int)value;
+    else if (s == "resume_text") g_opt.resume_text = (int)value;
     else if (s == "sync_dump") g_opt.sync_dump = (int)value;
     else if (s == "cap_dead0") g_opt.cap_dead0 = (long long)value;
     else if (s == "cap_ph0") g_opt.cap_ph0 = (long long)value;
@@ -1566,6 +1685,7 @@ double pc_get_option(const char* name) {
     if (s == "nh_global") return g_opt.nh_global;
     if (s == "no_pairing") return g_opt.no_pairing;
     if (s == "no_phase_d") return g_opt.no_phase_d;
+    if (s == "resume_text") return g_opt.resume_text;
     if (s == "sync_dump") return g_opt.sync_dump;
     if (s == "cap_dead0") return (double)g_opt.cap_dead0;
     if (s == "cap_ph0") return (double)g_opt.cap_ph0;
@@ -2026,6 +2146,36 @@ int pc_cluster_points(const double* points, int m, int D, int* labels_out) {
 
 // ---- output files (host only; no device needed) -------------------------------------------------
 void pc_format_e24(double v, char* out25) { format_e24(v, out25); }
+
+// Host-only: parse a resume file in the reference's text layout (pc_resume_text.h).  ints[8] = {nDims, nDerived, ndead,
+// ncluster, ncluster_dead, live points of all clusters, phantoms of all clusters, likelihood calls}; reals[6] = {logZ,
+// logZ2, log sum X_p, last update volume, lowest live logL, highest live logL}.  When out_path is given and the file
+// holds one active cluster, what was read is written back in the same layout (the writer used for "resume_text").
+int pc_resume_text_probe(const char* path, long long* ints, double* reals, const char* out_path) {
+    try {
+        pc::RefResume r;
+        pc::read_reference_resume(path, r);
+        long long n = 0, nph = 0, nl = 0;
+        for (int v : r.nlive) n += v;
+        for (int v : r.nphantom) nph += v;
+        for (long long v : r.nlike) nl += v;
+        const long long T = 2LL * r.nDims + r.nDerived + 2;
+        double lo = INFINITY, hi = -INFINITY, mx = -INFINITY, sx = 0.0;
+        for (long long i = 0; i < n; ++i) { lo = std::min(lo, r.live[(size_t)i * T + T - 1]); hi = std::max(hi, r.live[(size_t)i * T + T - 1]); }
+        for (double x : r.logXp) mx = std::max(mx, x);
+        for (double x : r.logXp) sx += std::exp(x - mx);
+        if (ints) { ints[0] = r.nDims; ints[1] = r.nDerived; ints[2] = r.ndead; ints[3] = r.ncluster; ints[4] = r.ncluster_dead; ints[5] = n; ints[6] = nph; ints[7] = nl; }
+        if (reals) { reals[0] = r.logZ; reals[1] = r.logZ2; reals[2] = mx + std::log(sx); reals[3] = r.logX_last_update; reals[4] = lo; reals[5] = hi; }
+        if (out_path && *out_path) pc::write_reference_resume(out_path, r);
+        return 0;
+    } catch (const pc::ArgError& ex) {   // (a probe: a malformed file is reported, never fatal)
+        std::fprintf(stderr, " polychord_b200: %s\n", ex.what());
+        return -2;
+    } catch (const std::exception& ex) {
+        std::fprintf(stderr, " polychord_b200: %s\n", ex.what());
+        return -3;
+    }
+}
 static int write_files_common(const char* base_dir, const char* file_root, int flags, int nDims, int nDerived, long long ndead,
                               const double* dead_rows, const double* dead_logw, int nlive, const double* live_rows, double logZ,
                               double logZerr, long long nlike, int num_repeats, double compression_factor, unsigned seed,

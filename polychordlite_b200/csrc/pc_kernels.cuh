@@ -481,40 +481,78 @@ __device__ inline void block_sort(double* key, int* val, int np2) {
 // ------------------------------------------------------------------------------------------
 // Evidence recurrences for `count` consecutive deaths with live counts n_start, n_start-1, ...
 // (run_time_info.f90:211-296 applied as in the final kill-off nested_sampling.F90:381-384).
-// X and XX are prefix sums, ZX a first-order linear recurrence (affine scan), Z and Z2
-// log-sum-exp reductions.  skey: ascending logL of the dying points (shared memory).
+// With n_j = n_start - j the death j does
+//     Z  <- Z  (+) X L / (n+1)                          Z2 <- Z2 (+) 2 ZX L / (n+1) (+) 2 XX L^2 / ((n+1)(n+2))
+//     ZX <- ZX n/(n+1) (+) XX L n / ((n+1)(n+2))        X  <- X n/(n+1)             XX <- XX n/(n+2)
+// in log space ((+) = logaddexp).  X and XX are products that telescope, ZX is a first-order linear recurrence
+// (a composition of affine maps x -> logaddexp(x + a, b)), Z and Z2 are log-sum-exp reductions.  Two levels: a thread
+// owns a CONTIGUOUS run of deaths and walks it sequentially (one new logarithm per death: log(n_j + 1) and
+// log(n_j + 2) are the previous death's log(n_j) and log(n_j + 1)); its start values of X and XX come in closed form,
+// its start value of ZX from ONE block-wide scan of the threads' composed maps.  The work of a death no longer
+// scales with block-wide barriers (16 rounds of five scans each for 4096 deaths before; one scan now).
+// skey: ascending logL of the dying points.  KEYS_GLOBAL: skey is global memory other CTAs wrote (phase D): read past L1.
 // ------------------------------------------------------------------------------------------
-// KEYS_GLOBAL: skey is global memory other CTAs wrote (phase D): read past L1.
 template <bool KEYS_GLOBAL = false>
 __device__ inline void evidence_deaths(DevRun* st, const double* skey, int count, int n_start, double* logw_out,
                                        double* sc) {
     const double LOG2 = 0.69314718055994530942;
-    double lX = st->logX, lXX = st->logXX, lZX = st->logZX, lZ = st->logZ, lZ2 = st->logZ2;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const double lX0 = st->logX, lXX0 = st->logXX, lZX0 = st->logZX, lZ0 = st->logZ, lZ20 = st->logZ2;
     __syncthreads();
-    for (int base = 0; base < count; base += blockDim.x) {
-        int j = base + threadIdx.x;
-        bool act = j < count;
-        double nj = (double)(n_start - (act ? j : 0));
-        double l0n = log(nj), l1 = log(nj + 1.0), l2 = log(nj + 2.0);
-        double dx = act ? l0n - l1 : 0.0, dxx = act ? l0n - l2 : 0.0;
-        double totx, totxx;
-        double lXb = lX + block_exscan_sum(dx, &totx, sc);
-        double lXXb = lXX + block_exscan_sum(dxx, &totxx, sc);
-        double L = act ? (KEYS_GLOBAL ? __ldcg(skey + j) : skey[j]) : 0.0;
-        double a = dx, b = act ? lXXb + L + l0n - l1 - l2 : NEG_BIG;
-        double exa, exb, tota, totb;
-        block_exscan_affine(a, b, exa, exb, tota, totb, sc);
-        double ZXb = logaddexp(lZX + exa, exb);
-        double tZ = act ? lXb + L - l1 : NEG_BIG;
-        double tZ2 = act ? logaddexp(LOG2 + ZXb + L - l1, LOG2 + lXXb + 2.0 * L - l1 - l2) : NEG_BIG;
-        if (act) logw_out[j] = lXb - l1;
-        lZ = block_lse(tZ, lZ, sc);
-        lZ2 = block_lse(tZ2, lZ2, sc);
-        lZX = logaddexp(lZX + tota, totb);
-        lX += totx;
-        lXX += totxx;
+    const int c = (count + nthr - 1) / nthr;
+    const int j0 = min(count, tid * c), j1 = min(count, j0 + c);
+    auto keyat = [&](int j) -> double { return KEYS_GLOBAL ? __ldcg(skey + j) : skey[j]; };
+    // X and XX before death j0 (products of n/(n+1), n/(n+2) over the deaths before it, telescoped)
+    const double nA = (double)(n_start - j0), nB = (double)n_start;
+    const double lgA1 = log(nA + 1.0), lgA2 = log(nA + 2.0), lgB1 = log(nB + 1.0), lgB2 = log(nB + 2.0);
+    const double lXs = lX0 + (lgA1 - lgB1), lXXs = lXX0 + ((lgA1 + lgA2) - (lgB1 + lgB2));
+    // pass 1: the thread's composed ZX map
+    double ma = 0.0, mb = NEG_BIG;
+    {
+        double l1 = lgA1, l2 = lgA2, lXXb = lXXs;
+        for (int j = j0; j < j1; ++j) {
+            const double l0n = log((double)(n_start - j));
+            const double a = l0n - l1, b = lXXb + keyat(j) + l0n - l1 - l2;
+            // (ma, mb) earlier, (a, b) later
+            mb = logaddexp(mb + a, b);
+            ma = ma + a;
+            lXXb += l0n - l2;
+            l2 = l1; l1 = l0n;
+        }
     }
-    if (threadIdx.x == 0) { st->logX = lX; st->logXX = lXX; st->logZX = lZX; st->logZ = lZ; st->logZ2 = lZ2; }
+    double exa, exb, tota, totb;
+    block_exscan_affine(ma, mb, exa, exb, tota, totb, sc);
+    // pass 2: the thread's deaths from its start state
+    double zm = NEG_BIG, zs = 0.0, z2m = NEG_BIG, z2s = 0.0;   // running (max, sum of exp(. - max)) of the Z and Z2 terms
+    {
+        double l1 = lgA1, l2 = lgA2, lXb = lXs, lXXb = lXXs, ZXb = logaddexp(lZX0 + exa, exb);
+        auto push = [](double& m, double& s2, double t) {
+            if (t > m) { s2 = s2 * exp(m - t) + 1.0; m = t; } else s2 += exp(t - m);
+        };
+        for (int j = j0; j < j1; ++j) {
+            const double l0n = log((double)(n_start - j));
+            const double L = keyat(j);
+            logw_out[j] = lXb - l1;
+            push(zm, zs, lXb + L - l1);
+            push(z2m, z2s, logaddexp(LOG2 + ZXb + L - l1, LOG2 + lXXb + 2.0 * L - l1 - l2));
+            ZXb = logaddexp(ZXb + (l0n - l1), lXXb + L + l0n - l1 - l2);
+            lXb += l0n - l1;
+            lXXb += l0n - l2;
+            l2 = l1; l1 = l0n;
+        }
+    }
+    // Z and Z2: log-sum-exp over the threads' partials and the start values
+    const double gm = fmax(block_max(zm, sc), lZ0), gm2 = fmax(block_max(z2m, sc), lZ20);
+    const double sZ = block_sum(zs > 0.0 ? zs * exp(zm - gm) : 0.0, sc) + exp(lZ0 - gm);
+    const double sZ2 = block_sum(z2s > 0.0 ? z2s * exp(z2m - gm2) : 0.0, sc) + exp(lZ20 - gm2);
+    if (tid == 0) {
+        const double nE = (double)(n_start - count);
+        st->logX = lX0 + (log(nE + 1.0) - lgB1);
+        st->logXX = lXX0 + ((log(nE + 1.0) + log(nE + 2.0)) - (lgB1 + lgB2));
+        st->logZX = logaddexp(lZX0 + tota, totb);
+        st->logZ = gm + log(sZ);
+        st->logZ2 = gm2 + log(sZ2);
+    }
     __syncthreads();
 }
 

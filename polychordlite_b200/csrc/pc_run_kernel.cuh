@@ -88,18 +88,10 @@ __device__ inline void init_phase(const KParams& p, const RunBuf& rb, DevRun* st
 // are sorted (bitonic) and the two lists are merged by rank (binary searches).  The first generation, and one that follows a
 // generation that moved live points (settle_generation), sorts everything.
 // S2 (off the critical path when CTA 0 only keeps the books): the evidence recurrences of the K deaths.
-// log X after `count` deaths from n_start live points: the same chunked sum evidence_deaths forms
-__device__ inline double logX_after(double lX, int count, int n_start, double* sc) {
-    for (int base = 0; base < count; base += blockDim.x) {
-        const int j = base + threadIdx.x;
-        const bool act = j < count;
-        const double nj = (double)(n_start - (act ? j : 0));
-        const double dx = act ? log(nj) - log(nj + 1.0) : 0.0;
-        double totx;
-        block_exscan_sum(dx, &totx, sc);
-        lX += totx;
-    }
-    return lX;
+// log X after `count` deaths from n_start live points: prod (n_j / (n_j + 1)) telescopes; the same expression evidence_deaths
+// leaves in DevRun::logX
+__device__ inline double logX_after(double lX, int count, int n_start) {
+    return lX + (log((double)(n_start - count) + 1.0) - log((double)n_start + 1.0));
 }
 
 // target number of live points above the contour (run_time_info.f90:766-771: the threshold with the largest loglike
@@ -263,7 +255,7 @@ __device__ inline bool phase_S1_fast(const KParams& p, const RunBuf& rb, DevRun*
     if (nph_test + (long long)Bmax * (p.cp.R - 1) > rb.cap_ph) return false;
     if (p.boost_thin > 0.0 && (long long)st->nboost + st->nphantom + (long long)Bmax * (p.cp.R - 1) > rb.cap_boost) return false;
     // log X after the K deaths: sum_j log((n - j) / (n - j + 1)) telescopes
-    const double lX_new = st->logX + (log((double)(n - K + 1)) - log((double)(n + 1)));
+    const double lX_new = logX_after(st->logX, K, n);
     if (lane == 0) publish_generation(p, rb, st, n, K, false, ndead, newo, newk, lX_new);
     return true;
 }
@@ -414,7 +406,7 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
         }
     }
     long long q3 = clock64();
-    const double lX_new = logX_after(st->logX, K, n, sc);
+    const double lX_new = logX_after(st->logX, K, n);
     if (tid == 0) {
         publish_generation(p, rb, st, n, K, trim, ndead, newo, newk, lX_new);
         long long q4 = clock64();
@@ -453,38 +445,78 @@ __device__ inline void phase_D(const KParams& p, const RunBuf& rb, DevRun* st, c
     double* sb = s_keys;          // K baby keys
     double* ss = s_keys + K;      // m survivor keys, ascending
     double* sp = s_keys + n;      // 2 W: the warps' partials
-    for (int j = tid; j < K; j += nthr) sb[j] = __ldcg(bkeys + j);
-    for (int i = tid; i < m; i += nthr) ss[i] = __ldcg(oldk + K + i);
+    // (bkeys[0 .. K) and oldk[K .. n) land in sb[0 .. K), ss[0 .. m) = s_keys[0 .. n): one sweep, eight loads in flight per thread)
+    for (int j0 = tid; j0 < n; j0 += 8 * nthr) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u * nthr;
+            v[u] = j < K ? __ldcg(bkeys + j) : (j < n ? __ldcg(oldk + j) : 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u * nthr;
+            if (j < n) s_keys[j] = v[u];
+        }
+    }
     __syncthreads();
     const double M0 = ss[m - 1];   // the largest survivor key: reference point of the termination sums (the same on every CTA)
     double ps = 0.0;               // lane 0: sum of exp(key - M0) over the warp's points
-    for (int e = cta_rel * W + warp; e < n; e += nctas * W) {
-        const bool baby = e >= m;
-        const int idx = baby ? e - m : e;
-        const double key = baby ? sb[idx] : ss[idx];
-        const int slot = __ldcg(oldo + (baby ? idx : K + idx));
-        int cnt = 0;
+    // a warp ranks up to NQ points per pass over the baby keys (one shared-memory read serves NQ comparisons)
+    constexpr int NQ = 4;
+    const int first = cta_rel * W + warp, stride = nctas * W;
+    for (int e0 = first; e0 < n; e0 += NQ * stride) {
+        double key[NQ];
+        int idx[NQ], slot[NQ], cnt[NQ];
+        bool baby[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int e = e0 + q * stride;
+            const bool act = e < n;
+            baby[q] = act && e >= m;
+            idx[q] = baby[q] ? e - m : (act ? e : -1);
+            key[q] = !act ? -INFINITY : (baby[q] ? sb[idx[q]] : ss[idx[q]]);   // nothing is below -inf: an idle entry counts nothing
+            slot[q] = act ? __ldcg(oldo + (baby[q] ? idx[q] : K + idx[q])) : 0;
+            cnt[q] = 0;
+        }
+        int eqc[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) eqc[q] = 0;
+#pragma unroll 4
         for (int j = lane; j < K; j += 32) {
             const double kb = sb[j];
-            bool less = kb < key;
-            if (kb == key) less = __ldcg(oldo + j) < slot;   // (a baby is not below itself: equal slots)
-            cnt += less ? 1 : 0;
-        }
-        cnt = __reduce_add_sync(FULL, cnt);
-        int rank = cnt + idx;
-        if (baby) {   // survivors below it: first survivor that is not
-            int lo = 0, hi = m;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (ss[mid] < key) lo = mid + 1; else hi = mid;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                cnt[q] += kb < key[q] ? 1 : 0;
+                eqc[q] += kb == key[q] ? 1 : 0;
             }
-            while (lo < m && ss[lo] == key && __ldcg(oldo + K + lo) < slot) ++lo;
-            rank = cnt + lo;
         }
-        if (lane == 0) {
-            newo[rank] = slot;
-            newk[rank] = key;
-            ps += exp(key - M0);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {   // equal keys (rare; a baby always meets itself): the slot decides
+            if (idx[q] < 0) continue;
+            if (__reduce_add_sync(FULL, eqc[q]) > (baby[q] ? 1 : 0))
+                for (int j = lane; j < K; j += 32)
+                    if (sb[j] == key[q] && !(baby[q] && j == idx[q])) cnt[q] += __ldcg(oldo + j) < slot[q] ? 1 : 0;
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            if (idx[q] < 0) continue;   // uniform over the warp
+            const int below = __reduce_add_sync(FULL, cnt[q]);
+            int rank = below + idx[q];
+            if (baby[q]) {   // survivors below it: first survivor that is not
+                int lo = 0, hi = m;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (ss[mid] < key[q]) lo = mid + 1; else hi = mid;
+                }
+                while (lo < m && ss[lo] == key[q] && __ldcg(oldo + K + lo) < slot[q]) ++lo;
+                rank = below + lo;
+            }
+            if (lane == 0) {
+                newo[rank] = slot[q];
+                newk[rank] = key[q];
+                ps += exp(key[q] - M0);
+            }
         }
     }
     if (lane == 0) sp[warp] = ps;
@@ -598,7 +630,7 @@ __device__ inline void phase_UA(const KParams& p, const RunBuf& rb, DevRun* st, 
 // the m8n8k4 FP64 tensor-core MMA) in shared memory and multiplies the 8x8 tiles of the upper triangle of M,
 // COV_TPP tiles per pass over the data (one pass up to D = 31).
 __device__ inline void phase_UB(const KParams& p, const RunBuf& rb, DevRun* st, int cta, int NG, unsigned char* smem_warp0,
-                                int warp_bytes, int* s_cnt) {
+                                int warp_bytes, int* s_cnt, long long* tim) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
     const int D = p.cp.D, T = p.cp.T, n = vload(&st->n);
     const int Dpad = (D + 1) & ~1;
@@ -664,7 +696,7 @@ __device__ inline void phase_UB(const KParams& p, const RunBuf& rb, DevRun* st, 
         // current one is worked on.
         long long tbase = base;
         const long long z1 = clock64();
-        if (tmr) st->dbg[12] += z1 - z0;
+        if (tmr) tim[12] += z1 - z0;
         const long long my_tiles = (ntiles > cta) ? (ntiles - cta + NG - 1) / NG : 0;
         const int my_live = (p.sh.rank == 0) ? (l1 - l0) : 0;  // the live points are replicated: rank 0 counts them
         const long long my_items = my_tiles + (my_live + UT - 1) / UT;
@@ -749,7 +781,7 @@ __device__ inline void phase_UB(const KParams& p, const RunBuf& rb, DevRun* st, 
             if (copy) tbase = tnext;   // offset of this CTA's next phantom tile
         }
         const long long z3 = clock64();
-        if (tmr) st->dbg[13] += z3 - z1;
+        if (tmr) tim[13] += z3 - z1;
         // the warps add their tiles to the CTA's matrix in warp order (deterministic), then the pass's entries go
         // to this CTA's partial: [0] count, [1..1+D) S1, then the packed triangle of S2 (entry (a <= b) at b(b+1)/2 + a)
         __syncthreads();
@@ -780,12 +812,12 @@ __device__ inline void phase_UB(const KParams& p, const RunBuf& rb, DevRun* st, 
             else outp[1 + D + b2 * (b2 + 1) / 2 + a2] = v;
         }
         __syncthreads();
-        if (tmr) st->dbg[15] += clock64() - z3;
+        if (tmr) tim[15] += clock64() - z3;
     }
 }
 
 // ---------------------------------------------------------------- update finalisation (CTA 0)
-__device__ inline bool finish_update(const KParams& p, const RunBuf& rb, DevRun* st, int NG, double* s_cov, double* s_L) {
+__device__ inline bool finish_update(const KParams& p, const RunBuf& rb, DevRun* st, int NG, double* s_cov, double* s_L, long long* tim) {
     const int tid = threadIdx.x, D = p.cp.D, ntri = p.ntri;
     const long long tot = st->ph_kept;
     const long long f0 = clock64();
@@ -863,7 +895,7 @@ __device__ inline bool finish_update(const KParams& p, const RunBuf& rb, DevRun*
     for (int e = tid; e < D * D; e += blockDim.x) rb.chol[e] = s_L[e];
     if (tid == 0) {
         const long long f3 = clock64();
-        st->dbg[16] += f1 - f0; st->dbg[17] += f2 - f1; st->dbg[18] += f3 - f2;
+        tim[16] += f1 - f0; tim[17] += f2 - f1; tim[18] += f3 - f2;
         rb.gsum[0] = Nglob;
         st->chol_fallback += fb;
         st->cov_N = N;
@@ -986,7 +1018,20 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
 
     const int nlp = (p.cp.like_kind == LIKE_GAUSSIAN) ? 2 * D : (p.cp.like_kind == LIKE_CORR ? D + D * D : 0);
     for (int e = tid; e < nlp; e += blockDim.x) s_like[e] = p.like_params[e];
+    // Cycle counters of the phases live in shared memory while the kernel runs (a counter in global memory costs the
+    // counting thread an L2 round trip per update -- on CTA 0 that is the critical path of every generation) and are
+    // added to DevRun when the kernel leaves: [0 .. 24) = DevRun::dbg, then cyc_wait, cyc_S, cyc_fin, cyc_U, cyc_prep,
+    // cyc_white, cyc_slice, cyc_total.  Single writer per counter and CTA.
+    __shared__ long long tim[32];
+    if (tid < 32) tim[tid] = 0;
     __syncthreads();
+    auto flush_timers = [&]() {
+        __syncthreads();
+        if (tid < 32 && (cta == 0 || cta == c0) && tim[tid] != 0) {
+            long long* dst = tid < 24 ? &st->dbg[tid] : (&st->cyc_wait + (tid - 24));
+            atomicAdd((unsigned long long*)dst, (unsigned long long)tim[tid]);
+        }
+    };
 
     const ChainScratch cs = chain_scratch(s_warp, D, R, LD, p.nh_in_smem != 0, p.cp.like_kind, NPT,
                                           (MODE == 0 && rb.nh) ? rb.nh + (size_t)gw * R * LD : nullptr, SLB);
@@ -1015,7 +1060,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
         if (vload(&st->do_update)) {
             phase_UA(p, rb, st, cta, NG);
             group_sync(&st->bar, NG, p.backoff);
-            phase_UB(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt);
+            phase_UB(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt, tim);
             if (cta == 0 && tid == 0) st->update_pending = 1;
         }
         group_sync(&st->bar, NG, p.backoff);
@@ -1037,13 +1082,13 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
             // births that failed, slots left empty (B != K): the live set is made contiguous again before anything reads it
             if (st->holes_due || vload(&st->nfail_gen)) { settle_generation(p, rb, st, s_warp0, true); __syncthreads(); }
             if (st->update_pending) {
-                if (!finish_update(p, rb, st, NG, smS.akey, s_chol) && tid == 0) st->status = ST_ERROR;
+                if (!finish_update(p, rb, st, NG, smS.akey, s_chol, tim) && tid == 0) st->status = ST_ERROR;
                 __syncthreads();
                 if (p.clustering) cluster_exit = true;             // leave: the host runs the clustering pass (pc_cluster.cuh), dumps, relaunches
                 else if (rb.ctl) dump_exit = publish_dump(p, rb, st);   // the kernel keeps running
                 else if (p.want_dump) dump_exit = true;              // "sync_dump": leave, the host dumps and relaunches
             }
-            if (timer) st->cyc_fin += clock64() - t1;
+            if (timer) tim[26] += clock64() - t1;
         }
         if (cta == 0) {
             if (d_done) {   // phase D complete on every ranking CTA: phase S1 reads the order they left
@@ -1060,7 +1105,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                     __threadfence();
                 }
                 __syncthreads();
-                if (timer) st->dbg[23] += clock64() - tb0;
+                if (timer) tim[23] += clock64() - tb0;
             }
             long long t2 = clock64();
             bool evidence_due = false;
@@ -1073,8 +1118,14 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                 bool fast = false;
                 if (d_done) {
                     __shared__ int s_fast;
-                    if (warp == 0) { const bool f = phase_S1_fast(p, rb, st, NG - c0); if (lane == 0) s_fast = f ? 1 : 0; }
+                    if (warp == 0) {
+                        const long long tf0 = clock64();
+                        const bool f = phase_S1_fast(p, rb, st, NG - c0);
+                        if (lane == 0) { s_fast = f ? 1 : 0; tim[6] += clock64() - tf0; tim[7] += tf0 - t2; tim[8] -= clock64(); tim[9] -= clock64(); }
+                    }
+                    if (tid == 32) tim[14] += clock64() - t2;   // (probe) warp 1 reaches the barrier
                     __syncthreads();
+                    if (timer) tim[9] += clock64();              // (probe) with tim[8]: S1-fast end -> past the barrier
                     fast = s_fast != 0;
                 }
                 evidence_due = fast ? true : phase_S1(p, rb, st, smS, d_done, NG - c0);
@@ -1082,20 +1133,21 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
             }
             s2_due = evidence_due;
             __syncthreads();
-            if (timer) st->cyc_S += clock64() - t2;
+            if (timer) { tim[25] += clock64() - t2; if (d_done) tim[8] += clock64(); }
             prep_uid = ~0ull;  // phase S overlays this CTA's chain scratch
         }
         d_done = false;
         const long long tg0 = clock64();
         group_sync(&st->bar, NG, p.backoff);
         const long long tg1 = clock64();
-        if (ctimer) st->dbg[10] += tg1 - tg0;
+        if (ctimer) tim[10] += tg1 - tg0;
         // the run's status and the generation's parameters: one load per lane, one latency
         unsigned long long pw = 0;
         if (lane < 10) pw = __ldcg(&st->pub[lane]);
         else if (lane == 10) pw = (unsigned long long)(unsigned)vload(&st->status);
         if ((int)__shfl_sync(FULL, pw, 10) != ST_RUNNING) {
-            if (timer) st->cyc_total += clock64() - t_start;
+            if (timer) tim[31] += clock64() - t_start;
+            flush_timers();
             return;
         }
         if (cta == 0 && s2_due) {  // the chains are running: the evidence bookkeeping is off their critical path
@@ -1107,6 +1159,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                 __syncthreads();
                 if (tid == 0) st->status = ST_HOSTCHAINS;
             }
+            flush_timers();
             return;
         }
         const bool sharded = p.sh.world > 1;
@@ -1147,7 +1200,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
             }
         }
         const long long ts_a = clock64();
-        if (ctimer) st->dbg[19] += ts_a - tg1;   // release -> generation parameters and Cholesky factor in place
+        if (ctimer) tim[19] += ts_a - tg1;   // release -> generation parameters and Cholesky factor in place
         unsigned long long nlike = 0, nfail = 0;
         const int m = n - K;
         // sharded run: the last babies go to the incoming buffers (by generation parity) instead of the live slots
@@ -1237,17 +1290,17 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                 const int src = __ldcg(order + K + choice - 1);
                 const int plab = clustered ? min(__ldcg(rb.lab + src), MAX_CLUSTERS - 1) : 0;  // the seed's cluster
                 const long long ts_b = clock64();
-                if (ctimer && j == 0) st->dbg[20] += ts_b - ts_a;   // seed choice (Philox + order look-up)
+                if (ctimer && j == 0) tim[20] += ts_b - ts_a;   // seed choice (Philox + order look-up)
                 if (helper) {
                     long long th0 = clock64();
                     if (prep_uid != uid) { prep_chain<G * DPL>(D, R, LD, rb.seed, uid, b, &p.cp); prep_white = false; }
                     if (clustered) whiten_chain<(G * DPL + 7) / 8>(D, R, LD, rb.cchol + (size_t)plab * D * D, b);
                     else if (!prep_white) whiten_chain<(G * DPL + 7) / 8>(D, R, LD, s_chol, b);
                     prep_uid = ~0ull;
-                    if (lane == 0 && cta == c0 && pair == 0) st->cyc_prep += clock64() - th0;
+                    if (lane == 0 && cta == c0 && pair == 0) tim[28] += clock64() - th0;
                 }
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");  // hand-over of the buffer
-                if (ctimer && j == 0) st->dbg[21] += clock64() - ts_b;   // wait for the helper's hand-over
+                if (ctimer && j == 0) tim[21] += clock64() - ts_b;   // wait for the helper's hand-over
                 if (!helper) {
                     const int dslot = k < K ? __ldcg(order + k) : n + (k - K);   // a vacated slot, or one appended (the live count grows)
                     double x[DPL];
@@ -1259,16 +1312,16 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                             rb.dead[(size_t)(ndead_base + k) * T + e] = __ldcg(rb.live + (size_t)dslot * T + e);
                     double* last = sharded ? xin_mine + (size_t)k * T : rb.live + (size_t)dslot * T;
                     long long tc2 = clock64();
-                    if (ctimer && j == 0) st->dbg[11] += tc2 - tg1;
+                    if (ctimer && j == 0) tim[11] += tc2 - tg1;
                     double lfin = slice_chain<G, DPL, KIND>(p.cp, M, rb.seed, uid, x, Lstar, b,
                                                       pool + (size_t)(nph_base + (long long)cl * (R - 1)) * T, last, nlike,
-                                                      (cta == c0 && warp == 0) ? st->dbg : nullptr, false);
+                                                      (cta == c0 && warp == 0) ? tim : nullptr, false);
                     if (sharded) shard_publish(p, last, k, xpar, lfin);
                     if (p.clustering) {  // the babies carry their seed's label until the next update
                         for (int e = lane; e < R - 1; e += 32) rb.phl[cur_pool_now][nph_base + (long long)cl * (R - 1) + e] = plab;
                         if (lane == 0) rb.lab[dslot] = plab;
                     }
-                    if (ctimer) st->cyc_slice += clock64() - tc2;
+                    if (ctimer) tim[30] += clock64() - tc2;
                     if (lane == 0) {   // a failed birth: settle_generation takes it out of the live set
                         const int failed = !(lfin > Lstar);
                         if (!sharded) { rb.cfail[k] = failed; rb.bkey[k] = lfin; }
@@ -1317,7 +1370,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                 }
                 if (ctimer) {
                     long long tc3 = clock64();
-                    st->cyc_prep += tc1 - tc0; st->cyc_white += tc2 - tc1; st->cyc_slice += tc3 - tc2;
+                    tim[28] += tc1 - tc0; tim[29] += tc2 - tc1; tim[30] += tc3 - tc2;
                 }
                 if (lane == 0) {   // a failed birth: settle_generation takes it out of the live set
                     const int failed = !(lfin > Lstar);
@@ -1357,7 +1410,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
         const long long tw0 = clock64();
         warp_wait(&st->wbar, wtarget, p.backoff);
         const long long tw1 = clock64();
-        if (timer) st->cyc_wait += tw1 - tw0;
+        if (timer) tim[24] += tw1 - tw0;
         if (sharded) {
             // Close the generation across the GPUs: this rank's chains are done -> CTA 0 passes the cross-GPU barrier (every
             // rank's last babies and keys have arrived) -> every warp copies its share of the K last babies from the incoming
@@ -1366,7 +1419,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
             group_sync(&st->bar, NG, p.backoff);
             if (vload(&st->status) == ST_ERROR) return;
             shard_scatter(p, rb, st, gw, GW);
-            if (timer) st->dbg[14] += clock64() - tw1;
+            if (timer) tim[14] += clock64() - tw1;
         }
         if (do_update) {
             long long tu1 = clock64();
@@ -1384,12 +1437,12 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
             long long ua1 = clock64();
             group_sync(&st->bar, NG, p.backoff);
             long long ua2 = clock64();
-            phase_UB(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt);
+            phase_UB(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt, tim);
             long long ua3 = clock64();
-            if (timer) { st->dbg[2] += ua1 - ua0; st->dbg[3] += ua2 - ua1; st->dbg[4] += ua3 - ua2; st->dbg[5] -= ua3; }
+            if (timer) { tim[2] += ua1 - ua0; tim[3] += ua2 - ua1; tim[4] += ua3 - ua2; tim[5] -= ua3; }
             if (cta == 0 && tid == 0) st->update_pending = 1;
             group_sync(&st->bar, NG, p.backoff);
-            if (timer) { st->cyc_U += clock64() - tu1; st->dbg[5] += clock64(); }
+            if (timer) { tim[27] += clock64() - tu1; tim[5] += clock64(); }
         }
         // Phase D: a regular generation (as many births as deaths, none failed -- the failure count is where phase S1
         // published it) leaves the survivors in order: every chain CTA ranks its share of the live points.  The
@@ -1400,7 +1453,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
             const long long td0 = clock64();
             phase_D(p, rb, st, sharded ? p.sh.xrun[xr] + (size_t)xpar * p.batch_K : rb.bkey, cta - c0, NG - c0,
                     (double*)(smem + p.off_dkeys));
-            if (ctimer) st->dbg[22] += clock64() - td0;
+            if (ctimer) tim[22] += clock64() - td0;
         }
         if (will_chain && !prep_early) prep_next();
     }
