@@ -260,6 +260,17 @@ int pc_device_cholesky(const double* a, int D, double* L_out);
  * dead_rows / live_rows: rows [theta(nDims), phi(nDerived), birth contour, logL]; dead_logw[i] = log weight + logL. */
 void pc_format_e24(double value, char* out25);
 
+/* Clusters of the last run with do_clustering.  The clusters persist as in the
+ * reference -- at every update each one is searched for sub-clusters and split (clustering.f90:253-324,
+ * run_time_info.f90:303-505), one without live points is deleted (:507-598) -- and every death is attributed to the
+ * cluster of the dying point.  pc_last_clusters returns their number: the clusters alive at the end of sampling first
+ * (label order), then the deleted ones; rows = {log<Z_p>, log<Z_p^2>} per cluster, uid = its identity (0: the initial
+ * cluster, a split creates new identities).  pc_last_dead_clusters: the identity every dead point's cluster had at its
+ * death.  pc_last_cluster_tree: for every identity the one it was split from (-1: none). */
+int pc_last_clusters(int* nactive, double* rows, int* uid);
+long long pc_last_dead_clusters(int* out, long long cap);
+int pc_last_cluster_tree(int* parent_out);
+
 /* Host-only: parse a resume file in the reference's TEXT layout (src/polychord/read_write.F90:219-288 writes it,
  * :384-476 reads it; pypolychord/polychord.py:650-789 writes it for cube_samples).  ints[8] = {nDims, nDerived, ndead,
  * ncluster, ncluster_dead, live points, phantoms, likelihood calls}; reals[6] = {logZ, logZ2, log sum_p X_p, last

@@ -416,6 +416,11 @@ std::vector<double> g_dyn_loglikes;
 std::vector<int> g_dyn_nlives;
 std::vector<double> g_init_cubes;   // oracle_set_initial_cubes: the next run's live points (cube_samples), one-shot
 std::vector<double> g_boost_rows, g_boost_logw;
+// evidence clusters of the last batched run with clustering: per cluster {logZp, logZp2, logXp at the end of sampling}, the
+// clusters alive at the end first (in label order), then the deleted ones in order of deletion (oracle_last_clusters)
+std::vector<double> g_last_clusters;
+int g_last_nactive = 0;
+std::vector<int> g_last_dead_cluster, g_last_uid_parent, g_last_cluster_uid;   // identities: per dead point, per identity its parent, per listed cluster
 std::vector<long long> g_boost_dead;
 
 struct Run {
@@ -646,9 +651,12 @@ struct Run {
     }
     double& XX(int p, int q) { return logXpXq[(size_t)p * cl.size() + q]; }
 
-    // update_evidence, run_time_info.f90:211-296
-    double update_evidence(int p) {
-        Cluster& c = cl[p];
+    // update_evidence, run_time_info.f90:211-296, on a set of clusters C with the cross-moment matrix M (the reference
+    // schedule: the clusters that hold the points; the batched schedule with clustering: the evidence clusters `ev`)
+    double update_evidence_in(std::vector<Cluster>& C, std::vector<double>& M, int p) {
+        Cluster& c = C[p];
+        const int nc = (int)C.size();
+        auto X2 = [&](int a, int b) -> double& { return M[(size_t)a * nc + b]; };
         const double log2 = std::log(2.0);
         double logL = c.logLp;
         double lognp = std::log(c.nlive + 0.0), lognp1 = std::log(c.nlive + 1.0), lognp2 = std::log(c.nlive + 2.0);
@@ -656,22 +664,23 @@ struct Run {
         logincexp(logZ, c.logXp + logL - lognp1);
         logincexp(c.logZp, c.logXp + logL - lognp1);
         c.logXp = c.logXp + lognp - lognp1;
-        logincexp(logZ2, log2 + c.logZXp + logL - lognp1, log2 + XX(p, p) + 2 * logL - lognp1 - lognp2);
+        logincexp(logZ2, log2 + c.logZXp + logL - lognp1, log2 + X2(p, p) + 2 * logL - lognp1 - lognp2);
         c.logZXp = c.logZXp + lognp - lognp1;
-        logincexp(c.logZXp, XX(p, p) + logL + lognp - lognp1 - lognp2);
-        for (int q = 0; q < (int)cl.size(); ++q)
-            if (q != p) logincexp(cl[q].logZXp, XX(p, q) + logL - lognp1);
-        logincexp(c.logZp2, log2 + c.logZpXp + logL - lognp1, log2 + XX(p, p) + 2 * logL - lognp1 - lognp2);
+        logincexp(c.logZXp, X2(p, p) + logL + lognp - lognp1 - lognp2);
+        for (int q = 0; q < nc; ++q)
+            if (q != p) logincexp(C[q].logZXp, X2(p, q) + logL - lognp1);
+        logincexp(c.logZp2, log2 + c.logZpXp + logL - lognp1, log2 + X2(p, p) + 2 * logL - lognp1 - lognp2);
         c.logZpXp = c.logZpXp + lognp - lognp1;
-        logincexp(c.logZpXp, XX(p, p) + logL + lognp - lognp1 - lognp2);
-        XX(p, p) = XX(p, p) + lognp - lognp2;
-        for (int q = 0; q < (int)cl.size(); ++q)
+        logincexp(c.logZpXp, X2(p, p) + logL + lognp - lognp1 - lognp2);
+        X2(p, p) = X2(p, p) + lognp - lognp2;
+        for (int q = 0; q < nc; ++q)
             if (q != p) {
-                XX(p, q) += lognp - lognp1;
-                XX(q, p) += lognp - lognp1;
+                X2(p, q) += lognp - lognp1;
+                X2(q, p) += lognp - lognp1;
             }
         return logweight;
     }
+    double update_evidence(int p) { return update_evidence_in(cl, logXpXq, p); }
 
     void find_min() {
         for (auto& c : cl) {
@@ -692,6 +701,7 @@ struct Run {
     }
     double sum_logX() {
         std::vector<double> v;
+        if (pce()) { for (auto& c : ev) v.push_back(c.logXp); return logsumexp(v.data(), v.size()); }
         for (auto& c : cl) v.push_back(c.logXp);
         return logsumexp(v.data(), v.size());
     }
@@ -994,65 +1004,239 @@ struct Run {
     long long nsplits = 0;
 
     // ---- clusters, batched mode (the engine's schedule) ------------------------------------------
-    // The evidence stays global -- one nested-sampling run over the whole live set is exact whatever the shape of the
-    // posterior -- and the clusters only steer the proposals: at every update the live points are clustered from
-    // scratch (NN_clustering over all of them), the phantoms take the label of their nearest live point
-    // (identify_cluster), every cluster with more than nDims points gets the covariance / Cholesky factor of its
-    // own live + phantom points (the others keep the global one), a chain whitens its directions with the factor
-    // of its seed's cluster, and its babies inherit that label until the next update.
+    // The points stay in cl[0] (one live array, one phantom pool), lab[slot] / phlab[i] carry the cluster of every live
+    // point / phantom, and the evidence is kept PER CLUSTER in `ev` exactly as the reference keeps it
+    // (run_time_info.f90:211-296 update_evidence, :303-505 add_cluster, :507-598 delete_cluster):
+    //   * a generation's K deaths go through update_evidence in death order, each in the cluster of the dying point with
+    //     that cluster's live count (which falls as its points die);
+    //   * a cluster left without live points is deleted (its local evidence joins the dead clusters');
+    //   * the seed of a chain is drawn as GenerateSeed draws it (generate.F90:19-55): a cluster in proportion to its
+    //     volume, then one of its surviving points (in rank order); the babies join the seed's cluster;
+    //   * at every update every cluster is searched for sub-clusters (do_clustering, clustering.f90:253-324:
+    //     NN_clustering on its own live points) and split by add_cluster -- volumes and evidences apportioned by the
+    //     live + phantom counts of the pieces -- where a phantom belongs to the cluster of its nearest live point
+    //     (identify_cluster); every cluster with more than nDims points gets the covariance / Cholesky factor of its own
+    //     live + phantom points (the others keep the global one).
+    // One difference of bookkeeping, none of substance: the phantoms' labels are recomputed from the nearest live point
+    // at every update (the reference re-assigns them when a cluster splits and drops the ones of a deleted cluster; in
+    // between it never reads them).
     std::vector<int> lab, phlab;                  // label of every live slot / phantom record (all in cl[0])
-    std::vector<std::vector<double>> chols;       // Cholesky factor per label
-    int ncl_b = 1;
+    std::vector<Cluster> ev;                      // the evidence clusters (scalar fields, nlive, cholesky)
+    std::vector<double> evXX;                     // their cross moments log<X_p X_q>, ev.size() squared
+    int ncl_b = 1, ncl_max_b = 1;
+    std::vector<int> ev_uid;                      // persistent identity of every evidence cluster (a split creates new ones)
+    std::vector<int> uid_parent;                  // ... and the cluster it was split from (-1: the initial cluster)
+    std::vector<int> dead_cluster;                // for every dead point: the identity of its cluster at its death
+    std::vector<int> dead_uid;                    // identities of the deleted clusters, in order of deletion
+    // do_clustering = 1: the evidence stays GLOBAL (one nested-sampling run over the whole live set: exact whatever the
+    //   shape of the posterior) and every death is ATTRIBUTED to the cluster of the dying point -- local evidence
+    //   Z_p = sum over its deaths of w L with the global weight w = X/(n+1), and its second moment by the same
+    //   recurrences as the global one (run_time_info.f90:211-296 with the global X): this is what the engine does.
+    // do_clustering = 2: every cluster keeps its own volume as well, as the reference does (local volumes shrink with the
+    //   cluster's own deaths, seeds are drawn by volume).  Kept for the record: the estimator is biased high -- also in
+    //   the reference schedule -- see scripts/r02_cluster_bias.py and DESIGN.md section 5.4.
+    bool pce() const { return S.batch_K > 0 && S.do_clustering == 2; }
+    bool attr() const { return S.batch_K > 0 && S.do_clustering == 1; }
+    bool evc() const { return S.batch_K > 0 && S.do_clustering != 0; }
+    // a death in evidence cluster p under the global accounting (attr): the global update_evidence gave log-weight logw
+    // with n live points before the death; Z_p, <Z_p^2> and <Z_p X> follow the global recurrences restricted to p
+    void attribute_death(int p, double logL, int n_before, double XX_before) {
+        const double log2 = std::log(2.0);
+        const double lognp = std::log(n_before + 0.0), lognp1 = std::log(n_before + 1.0), lognp2 = std::log(n_before + 2.0);
+        Cluster& c = ev[p];
+        const double X_before = cl[0].logXp - (lognp - lognp1);   // (the global update already shrank it)
+        logincexp(c.logZp, X_before + logL - lognp1);
+        logincexp(c.logZp2, log2 + c.logZpXp + logL - lognp1, log2 + XX_before + 2 * logL - lognp1 - lognp2);
+        for (auto& q : ev) q.logZpXp += lognp - lognp1;          // X shrinks for every cluster's <Z_q X>
+        logincexp(c.logZpXp, XX_before + logL + lognp - lognp1 - lognp2);
+    }
+    void init_ev() {
+        ev.assign(1, Cluster());
+        Cluster& c = ev[0];
+        c.logZp = c.logZXp = c.logZp2 = c.logZpXp = S.logzero;
+        c.logXp = 0.0;
+        c.logLp = S.logzero;
+        c.nlive = cl[0].nlive;
+        c.cholesky = cl[0].cholesky;
+        c.covmat = cl[0].covmat;
+        evXX.assign(1, 0.0);
+        lab.assign(cl[0].nlive, 0);
+        phlab.clear();
+        ev_uid.assign(1, 0);
+        uid_parent.assign(1, -1);
+        dead_cluster.clear();
+        dead_uid.clear();
+    }
+    // delete_cluster for every evidence cluster without live points (lowest index first, as minloc picks them)
+    void delete_empty_ev() {
+        for (;;) {
+            int p = -1;
+            for (int q = 0; q < (int)ev.size(); ++q) if (ev[q].nlive == 0) { p = q; break; }
+            if (p < 0 || ev.size() == 1) return;
+            const int nc = (int)ev.size();
+            logZp_dead.push_back(ev[p].logZp);
+            logZp2_dead.push_back(ev[p].logZp2);
+            dead_uid.push_back(ev_uid[p]);
+            ++ncluster_dead;
+            std::vector<double> xx((size_t)(nc - 1) * (nc - 1));
+            for (int a2 = 0, ia = 0; a2 < nc; ++a2) {
+                if (a2 == p) continue;
+                for (int b2 = 0, ib = 0; b2 < nc; ++b2) {
+                    if (b2 == p) continue;
+                    xx[(size_t)ia * (nc - 1) + ib] = evXX[(size_t)a2 * nc + b2];
+                    ++ib;
+                }
+                ++ia;
+            }
+            ev.erase(ev.begin() + p);
+            ev_uid.erase(ev_uid.begin() + p);
+            evXX.swap(xx);
+            for (int& v : lab) if (v > p) --v;     // (no live point carries p any more)
+            for (int& v : phlab) if (v > p) --v; else if (v == p) v = 0;   // recomputed at the next update anyway
+        }
+    }
+    // add_cluster (run_time_info.f90:303-505) on the evidence clusters: cluster p splits into `num` pieces, appended
+    // behind the surviving clusters; piece[j] is the piece of the j-th live point of p (in slot order), nn[i] the live
+    // slot nearest to phantom i
+    void add_cluster_ev(int p, const std::vector<int>& members, const std::vector<int>& piece, int num, const std::vector<int>& nn) {
+        const int nc_old = (int)ev.size(), nold = nc_old - 1, nc = nold + num;
+        const Cluster old = ev[p];
+        std::vector<int> keep;
+        for (int q = 0; q < nc_old; ++q) if (q != p) keep.push_back(q);
+        std::vector<double> xpq(nold);
+        for (int a2 = 0; a2 < nold; ++a2) xpq[a2] = evXX[(size_t)p * nc_old + keep[a2]];
+        const double xpp = evXX[(size_t)p * nc_old + p];
+        std::vector<double> xx((size_t)nc * nc, 0.0);
+        for (int a2 = 0; a2 < nold; ++a2)
+            for (int b2 = 0; b2 < nold; ++b2) xx[(size_t)a2 * nc + b2] = evXX[(size_t)keep[a2] * nc_old + keep[b2]];
+        std::vector<Cluster> nev;
+        std::vector<int> nuid;
+        for (int q : keep) { nev.push_back(ev[q]); nuid.push_back(ev_uid[q]); }
+        for (int i = 0; i < num; ++i) { nuid.push_back((int)uid_parent.size()); uid_parent.push_back(ev_uid[p]); }
+        ev_uid.swap(nuid);
+        for (int i = 0; i < num; ++i) {
+            Cluster c = old;           // (cholesky / covmat: the parent's until the update recomputes them)
+            c.nlive = 0;
+            c.logLp = S.logzero;
+            nev.push_back(c);
+        }
+        // the labels: clusters behind p move up, the points of p go to their pieces
+        for (int& v : lab) if (v > p) --v;
+        for (size_t j = 0; j < members.size(); ++j) {
+            lab[members[j]] = nold + piece[j];
+            nev[nold + piece[j]].nlive++;
+        }
+        ev.swap(nev);
+        evXX.swap(xx);
+        auto X2 = [&](int a2, int b2) -> double& { return evXX[(size_t)a2 * nc + b2]; };
+        // live + phantom counts of the pieces (every phantom identified afresh: the cluster of its nearest live point)
+        std::vector<int> nph(num, 0);
+        for (int s2 : nn) if (lab[s2] >= nold) nph[lab[s2] - nold]++;
+        std::vector<double> logni(num), logni1(num);
+        for (int i = 0; i < num; ++i) {
+            logni[i] = std::log(ev[nold + i].nlive + nph[i] + 0.0);
+            logni1[i] = std::log(ev[nold + i].nlive + nph[i] + 1.0);
+        }
+        const double logn = logsumexp(logni.data(), logni.size()), logn1 = logaddexp(logn, 0.0);
+        if (!pce()) {   // attributed evidences: Z_p splits by the counts, the volume is global (nothing of it splits)
+            for (int i = 0; i < num; ++i) {
+                Cluster& c = ev[nold + i];
+                c.logZp = old.logZp + logni[i] - logn;
+                c.logZp2 = old.logZp2 + logni[i] + logni1[i] - logn - logn1;
+                c.logZpXp = old.logZpXp + logni[i] - logn;
+            }
+            return;
+        }
+        for (int i = 0; i < num; ++i) {
+            Cluster& c = ev[nold + i];
+            c.logXp = old.logXp + logni[i] - logn;
+            c.logZXp = old.logZXp + logni[i] - logn;
+            c.logZp = old.logZp + logni[i] - logn;
+            c.logZp2 = old.logZp2 + logni[i] + logni1[i] - logn - logn1;
+            c.logZpXp = old.logZpXp + logni[i] + logni1[i] - logn - logn1;
+            for (int a2 = 0; a2 < nold; ++a2) X2(nold + i, a2) = X2(a2, nold + i) = xpq[a2] + logni[i] - logn;
+            for (int j = 0; j < num; ++j)
+                X2(nold + i, nold + j) = (i == j) ? xpp + logni[i] + logni1[i] - logn - logn1
+                                                  : xpp + logni[i] + logni[j] - logn - logn1;
+        }
+    }
     void cluster_update_batched() {
         Cluster& c = cl[0];
         const int n = c.nlive;
-        calculate_covmats();                      // the global covariance / factor
+        calculate_covmats();                      // the global covariance / factor (clusters of few points use it)
         std::vector<const double*> pts(n);
         for (int i = 0; i < n; ++i) pts[i] = &c.live[(size_t)i * T + h0];
-        int num = 1;
-        lab = NN_clustering(similarity_matrix(pts, D), n, num);
-        if (num > 256) {                          // the engine keeps 256 factors: further labels share the last one (global factor)
-            for (int& v : lab) v = std::min(v, 255);
-        }
-        const bool clamped = num > 256;
-        if (clamped) num = 256;
-        ncl_b = num;
-        if (num > 1) nsplits++;                   // updates that found more than one cluster
-        phlab.assign(c.nphantom, 0);
-        if (num > 1)
-            for (int i = 0; i < c.nphantom; ++i) {
-                const double* x = &c.phantom[(size_t)i * T + h0];
-                double best = HUGE_D;
-                int which = 0;
-                for (int j = 0; j < n; ++j) {
-                    const double d2 = dist2(x, pts[j], D);
-                    if (d2 < best) { best = d2; which = j; }   // ties: the lowest slot
-                }
-                phlab[i] = lab[which];
+        // identify_cluster for every phantom: the nearest live point (ties: the lowest slot)
+        std::vector<int> nn(c.nphantom, 0);
+        for (int i = 0; i < c.nphantom; ++i) {
+            const double* x = &c.phantom[(size_t)i * T + h0];
+            double best = HUGE_D;
+            for (int j = 0; j < n; ++j) {
+                const double d2 = dist2(x, pts[j], D);
+                if (d2 < best) { best = d2; nn[i] = j; }
             }
-        chols.assign(num, c.cholesky);
-        if (num == 1) return;
-        for (int p = 0; p < num; ++p) {
+        }
+        // do_clustering (clustering.f90:253-324): every cluster is searched for sub-clusters; a cluster that splits
+        // leaves its place to the next one (the loop index stays), its pieces go to the end.  At most 256 clusters
+        // (the engine keeps that many factors): a split that would exceed them is not made.
+        // (The reference's loop index also reaches the first of the appended pieces; NN_clustering returns a piece only
+        // after searching it again and finding one cluster, so that visit never splits anything: the old clusters are
+        // the ones examined here.)
+        bool found = false;
+        int i = 0;
+        for (int remaining = (int)ev.size(); remaining > 0; --remaining) {
+            std::vector<int> members;
+            for (int s2 = 0; s2 < n; ++s2) if (lab[s2] == i) members.push_back(s2);
+            const int nl = (int)members.size();
+            int num = 1;
+            std::vector<int> piece;
+            if (nl > 2) {
+                std::vector<const double*> mp(nl);
+                for (int j = 0; j < nl; ++j) mp[j] = pts[members[j]];
+                piece = NN_clustering(similarity_matrix(mp, D), nl, num);
+            }
+            if (num > 1 && (int)ev.size() - 1 + num <= 256) { found = true; add_cluster_ev(i, members, piece, num, nn); }
+            else ++i;
+        }
+        if (found) nsplits++;                     // updates that split a cluster
+        ncl_b = (int)ev.size();
+        ncl_max_b = std::max(ncl_max_b, ncl_b);
+        phlab.resize(c.nphantom);
+        for (int k = 0; k < c.nphantom; ++k) phlab[k] = lab[nn[k]];
+        // per-cluster covariance and factor
+        for (int p = 0; p < ncl_b; ++p) {
+            ev[p].cholesky = c.cholesky;
+            ev[p].covmat = c.covmat;
+            if (ncl_b == 1) continue;
             std::vector<const double*> mem;
-            for (int i = 0; i < n; ++i) if (lab[i] == p) mem.push_back(pts[i]);
-            for (int i = 0; i < c.nphantom; ++i) if (phlab[i] == p) mem.push_back(&c.phantom[(size_t)i * T + h0]);
+            for (int s2 = 0; s2 < n; ++s2) if (lab[s2] == p) mem.push_back(pts[s2]);
+            for (int k = 0; k < c.nphantom; ++k) if (phlab[k] == p) mem.push_back(&c.phantom[(size_t)k * T + h0]);
             const int N = (int)mem.size();
-            if (N <= D || (clamped && p == 255)) continue;   // too few points for a covariance: the global factor stays
+            if (N <= D) continue;                 // too few points for a covariance: the global factor stays
             std::vector<double> mean(D, 0.0), cov((size_t)D * D, 0.0), dv(D);
             for (const double* x : mem) for (int k = 0; k < D; ++k) mean[k] += x[k];
             for (int k = 0; k < D; ++k) mean[k] /= N;
             for (const double* x : mem) {
                 for (int k = 0; k < D; ++k) dv[k] = x[k] - mean[k];
-                for (int b = 0; b < D; ++b) for (int a = 0; a < D; ++a) cov[a + (size_t)b * D] += dv[a] * dv[b];
+                for (int b2 = 0; b2 < D; ++b2) for (int a2 = 0; a2 < D; ++a2) cov[a2 + (size_t)b2 * D] += dv[a2] * dv[b2];
             }
             for (double& v : cov) v /= N;
-            calc_cholesky(cov.data(), chols[p].data(), D);
+            ev[p].covmat = cov;
+            calc_cholesky(cov.data(), ev[p].cholesky.data(), D);
         }
     }
 
     double live_logZ() {
         double r = S.logzero;
         std::vector<double> ll;
+        if (pce()) {   // per evidence cluster: mean likelihood of its live points times its volume
+            for (int p = 0; p < (int)ev.size(); ++p) {
+                ll.clear();
+                for (int s2 = 0; s2 < cl[0].nlive; ++s2) if (lab[s2] == p) ll.push_back(cl[0].live[(size_t)s2 * T + l0]);
+                if (!ll.empty()) logincexp(r, logsumexp(ll.data(), ll.size()) - std::log((double)ll.size()) + ev[p].logXp);
+            }
+            return r;
+        }
         for (auto& c : cl) {
             if (c.nlive > 0) {
                 ll.resize(c.nlive);
@@ -1230,10 +1414,25 @@ struct Run {
         const double Lstar = c.live[(size_t)order[K - 1] * T + l0];
         // K sequential deaths with n, n-1, ... live points (cf. nested_sampling.F90:381-384)
         const int nlive_save = c.nlive;
+        const bool per_cluster = pce(), labelled_ev = evc();
         for (int k = 0; k < K; ++k) {
             const double* r = &c.live[(size_t)order[k] * T];
-            c.logLp = r[l0];
-            double logw = update_evidence(0);
+            double logw;
+            if (per_cluster) {   // the death belongs to the cluster of the dying point
+                const int pc = lab[order[k]];
+                ev[pc].logLp = r[l0];
+                logw = update_evidence_in(ev, evXX, pc);
+                ev[pc].nlive--;
+            } else {
+                c.logLp = r[l0];
+                const double xx0 = XX(0, 0);
+                logw = update_evidence(0);
+                if (labelled_ev) {
+                    attribute_death(lab[order[k]], r[l0], c.nlive, xx0);
+                    ev[lab[order[k]]].nlive--;
+                }
+            }
+            if (labelled_ev) dead_cluster.push_back(ev_uid[lab[order[k]]]);
             push_dead(r, logw);
             c.stack_l.push_back(r[l0]);
             c.stack_i.push_back(ndead - 1);
@@ -1241,21 +1440,49 @@ struct Run {
         }
         c.nlive = nlive_save;
         const int m = n - K;
+        // survivors of every evidence cluster in rank order (GenerateSeed picks among them), and the clusters' shares
+        std::vector<std::vector<int>> members;
+        std::vector<double> cdf;
+        if (labelled_ev) delete_empty_ev();   // a cluster that lost its last live point is deleted (delete_cluster); no survivor carries its label
+        if (per_cluster) {
+            members.assign(ev.size(), {});
+            for (int i = K; i < n; ++i) members[lab[order[i]]].push_back(order[i]);
+            if (ev.size() > 1) {
+                const double lse = sum_logX();
+                std::vector<double> probs(ev.size());
+                double norm = 0.0;
+                for (size_t q = 0; q < ev.size(); ++q) { probs[q] = std::exp(ev[q].logXp - lse); norm += probs[q]; }
+                double acc = 0.0;
+                for (size_t q = 0; q < ev.size(); ++q) { acc += probs[q] / norm; cdf.push_back(acc); }
+            }
+        }
         std::vector<double> newpts((size_t)std::max(B, 1) * T);
         std::vector<int> newlab(std::max(B, 1), 0);
         std::vector<char> ok(std::max(B, 1), 0);
-        const bool clustered = S.do_clustering && ncl_b > 1;
+        const bool clustered = per_cluster && ev.size() > 1, factors = labelled_ev && ev.size() > 1;
         int nfailed = 0;
         for (int k = 0; k < B; ++k) {
             uint64_t uid = (uint64_t)nchains + k;
             double u = rng.uniform(TAG_SEED, uid, 0, 0);
-            int choice = (int)std::ceil(u * m);
-            if (choice < 1) choice = 1;
-            const int sslot = order[K + choice - 1];
+            int sslot, plab = 0;
+            if (clustered) {   // GenerateSeed, generate.F90:19-55: a cluster by volume, then one of its live points
+                const double rnd = rng.uniform(TAG_SEED, uid, 1, 0);
+                plab = (int)ev.size() - 1;
+                for (size_t q = 0; q < ev.size(); ++q) if (rnd < cdf[q]) { plab = (int)q; break; }
+                const int mp = (int)members[plab].size();
+                int choice = (int)std::ceil(u * mp);
+                if (choice < 1) choice = 1;
+                if (choice > mp) choice = mp;
+                sslot = members[plab][choice - 1];
+            } else {
+                int choice = (int)std::ceil(u * m);
+                if (choice < 1) choice = 1;
+                sslot = order[K + choice - 1];
+                if (labelled_ev) plab = lab[sslot];
+            }
             const double* seed = &c.live[(size_t)sslot * T];
-            const int plab = clustered ? lab[sslot] : 0;
             newlab[k] = plab;
-            slice_sampling(Lstar, seed, clustered ? chols[plab].data() : c.cholesky.data(), uid, babies, nlike);
+            slice_sampling(Lstar, seed, factors ? ev[plab].cholesky.data() : c.cholesky.data(), uid, babies, nlike);
             for (int i = 0; i < R; ++i) babies[(size_t)i * T + b0] = Lstar;
             for (int i = 0; i < R - 1; ++i) {
                 const double* pt = babies.data() + (size_t)i * T;
@@ -1282,6 +1509,7 @@ struct Run {
             if (k < B && ok[k]) {
                 std::copy(newpts.begin() + (size_t)k * T, newpts.begin() + (size_t)(k + 1) * T, c.live.begin() + (size_t)order[k] * T);
                 if (labelled) lab[order[k]] = newlab[k];
+                if (labelled_ev) ev[newlab[k]].nlive++;
             } else holes.push_back(order[k]);
         }
         // the live count grows: birth k >= K takes slot n + (k - K); a failed one leaves that slot empty
@@ -1292,6 +1520,7 @@ struct Run {
             if (!ok[k]) { holes.push_back(n + (k - K)); continue; }
             std::copy(newpts.begin() + (size_t)k * T, newpts.begin() + (size_t)(k + 1) * T, c.live.begin() + (size_t)(n + k - K) * T);
             if (labelled) lab[n + k - K] = newlab[k];
+            if (labelled_ev) ev[newlab[k]].nlive++;
         }
         // close the empty slots: with n' = extent - holes live points left, the records at or above n' move into the
         // empty slots below it, lowest into lowest (a rule every slot can apply by itself)
@@ -1358,8 +1587,19 @@ struct Run {
             });
             for (int k = 0; k < n; ++k) {
                 const double* r = &c.live[(size_t)order[k] * T];
-                c.logLp = r[l0];
-                double logw = update_evidence(0);
+                double logw;
+                if (pce()) {
+                    const int pc = lab[order[k]];
+                    ev[pc].logLp = r[l0];
+                    logw = update_evidence_in(ev, evXX, pc);
+                    ev[pc].nlive--;
+                } else {
+                    c.logLp = r[l0];
+                    const double xx0 = XX(0, 0);
+                    logw = update_evidence(0);
+                    if (evc()) { attribute_death(lab[order[k]], r[l0], c.nlive, xx0); ev[lab[order[k]]].nlive--; }
+                }
+                if (evc()) dead_cluster.push_back(ev_uid[lab[order[k]]]);
                 push_dead(r, logw);
                 c.stack_l.push_back(r[l0]);
                 c.stack_i.push_back(ndead - 1);
@@ -1376,15 +1616,30 @@ struct Run {
         g_boost_rows.clear(); g_boost_dead.clear(); g_boost_logw.clear();
         init_layout();
         generate_live_points();
+        if (evc()) init_ev();
         if (S.batch_K > 0) run_batched();
         else {
             // nprior > nlive: trim (nested_sampling.F90:201-203)
             while (cl[0].nlive > S.nlive) delete_outermost_point();
             run_reference();
         }
-        out->ncluster = S.batch_K > 0 ? ncl_b : (long long)cl.size();
+        out->ncluster = S.batch_K > 0 ? ncl_max_b : (long long)cl.size();
         out->nsplits = nsplits;
+        std::vector<double> logX_end;
+        if (evc()) for (auto& c : ev) logX_end.push_back(pce() ? c.logXp : cl[0].logXp + std::log(std::max(c.nlive, 1) / (double)std::max(cl[0].nlive, 1)));
         final_killoff();
+        g_last_clusters.clear();
+        g_last_nactive = 0;
+        g_last_dead_cluster.clear(); g_last_uid_parent.clear(); g_last_cluster_uid.clear();
+        if (evc()) {
+            g_last_dead_cluster = dead_cluster;
+            g_last_uid_parent = uid_parent;
+            g_last_cluster_uid = ev_uid;
+            g_last_cluster_uid.insert(g_last_cluster_uid.end(), dead_uid.begin(), dead_uid.end());
+            g_last_nactive = (int)ev.size();
+            for (size_t q = 0; q < ev.size(); ++q) { g_last_clusters.push_back(ev[q].logZp); g_last_clusters.push_back(ev[q].logZp2); g_last_clusters.push_back(logX_end[q]); }
+            for (size_t q = 0; q < logZp_dead.size(); ++q) { g_last_clusters.push_back(logZp_dead[q]); g_last_clusters.push_back(logZp2_dead[q]); g_last_clusters.push_back(S.logzero); }
+        }
         long long nph_end = 0;   // phantoms at the end of the sampling loop (what the engine reports too)
         for (auto& c : cl) nph_end += c.nphantom;
         if (thin_posterior() > 0.0) {   // update_posteriors, nested_sampling.F90:386: the last phantoms' conversion
@@ -1505,6 +1760,25 @@ int oracle_calculate_points(const oracle_settings* s, int like_kind, const doubl
 
 // Dynamic nlive for the following runs in the reference schedule (batch_K = 0): above the contour loglikes[i] the
 // target number of live points is nlives[i] (run_time_info.f90:766-777); m = 0 clears.
+// evidence clusters of the last batched run with clustering: returns their number (active first, then deleted),
+// *nactive the active ones; out (when not null, 3 doubles per cluster): logZp, logZp2, logXp at the end of sampling
+// identity of the cluster every dead point of the last batched run with clustering died in (0: the initial cluster; a
+// split creates new identities), and for every identity the one it was split from (-1: none).  Return the counts.
+long long oracle_last_dead_clusters(int* out, long long cap) {
+    if (out) std::copy(g_last_dead_cluster.begin(), g_last_dead_cluster.begin() + std::min<long long>(cap, (long long)g_last_dead_cluster.size()), out);
+    return (long long)g_last_dead_cluster.size();
+}
+int oracle_last_cluster_tree(int* parent_out, int* uid_of_cluster_out) {
+    if (parent_out) std::copy(g_last_uid_parent.begin(), g_last_uid_parent.end(), parent_out);
+    if (uid_of_cluster_out) std::copy(g_last_cluster_uid.begin(), g_last_cluster_uid.end(), uid_of_cluster_out);
+    return (int)g_last_uid_parent.size();
+}
+int oracle_last_clusters(int* nactive, double* out) {
+    if (nactive) *nactive = g_last_nactive;
+    if (out) std::copy(g_last_clusters.begin(), g_last_clusters.end(), out);
+    return (int)(g_last_clusters.size() / 3);
+}
+
 void oracle_set_nlives(const double* loglikes, const int* nlives, int m) {
     g_dyn_loglikes.assign(loglikes, loglikes + m);
     g_dyn_nlives.assign(nlives, nlives + m);

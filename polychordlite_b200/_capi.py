@@ -27,7 +27,7 @@ EXPORTS = [
     "pc_unit_prior", "pc_uniform_prior", "pc_set_option", "pc_get_option", "pc_set_stream", "pc_release_memory", "pc_mgpu_create", "pc_mgpu_attach", "pc_mgpu_destroy",
     "pc_last_run_info", "pc_run", "pc_run_ensemble", "pc_slice_chains", "pc_calculate_points",
     "pc_device_philox", "pc_device_uniforms", "pc_device_inv_normal_cdf", "pc_device_directions",
-    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points", "pc_set_grades", "pc_set_resume", "pc_measure_fp64_tflops", "pc_ini_prior_transform", "pc_last_boosted", "pc_maximise", "pc_prior_log_density", "pc_set_initial_live", "pc_write_files_boosted", "pc_set_nlives", "pc_resume_text_probe",
+    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points", "pc_set_grades", "pc_set_resume", "pc_measure_fp64_tflops", "pc_ini_prior_transform", "pc_last_boosted", "pc_maximise", "pc_prior_log_density", "pc_set_initial_live", "pc_write_files_boosted", "pc_set_nlives", "pc_resume_text_probe", "pc_last_clusters", "pc_last_dead_clusters", "pc_last_cluster_tree",
 ]
 
 
@@ -326,6 +326,35 @@ def format_e24(value):
     L.pc_format_e24.restype = None
     L.pc_format_e24(float(value), buf)
     return buf.value.decode()
+
+
+def last_clusters():
+    """Clusters of the last run with do_clustering: (nactive, rows[ncl, 2] of log<Z_p>, log<Z_p^2>, uid[ncl])."""
+    L = lib()
+    L.pc_last_clusters.restype = C.c_int
+    L.pc_last_clusters.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    nact = C.c_int(0)
+    n = L.pc_last_clusters(C.byref(nact), None, None)
+    rows = np.zeros((max(n, 1), 2))
+    uid = np.zeros(max(n, 1), dtype=np.int32)
+    L.pc_last_clusters(C.byref(nact), _dptr(rows), uid.ctypes.data_as(C.POINTER(C.c_int)))
+    return int(nact.value), rows[:n], uid[:n]
+
+
+def last_dead_clusters():
+    """(identity of the cluster each dead point of the last clustered run died in, parent of every identity)."""
+    L = lib()
+    L.pc_last_dead_clusters.restype = C.c_longlong
+    L.pc_last_dead_clusters.argtypes = [C.POINTER(C.c_int), C.c_longlong]
+    n = L.pc_last_dead_clusters(None, 0)
+    out = np.zeros(max(n, 1), dtype=np.int32)
+    L.pc_last_dead_clusters(out.ctypes.data_as(C.POINTER(C.c_int)), n)
+    L.pc_last_cluster_tree.restype = C.c_int
+    L.pc_last_cluster_tree.argtypes = [C.POINTER(C.c_int)]
+    m = L.pc_last_cluster_tree(None)
+    par = np.zeros(max(m, 1), dtype=np.int32)
+    L.pc_last_cluster_tree(par.ctypes.data_as(C.POINTER(C.c_int)))
+    return out[:n], par[:m]
 
 
 def resume_text_probe(path, out_path=None):

@@ -145,6 +145,14 @@ struct MgpuCtx {
     unsigned long long epoch = 0;  // cross-GPU barriers passed so far (the counters are never reset)
 };
 static MgpuCtx g_mgpu;
+// clusters of the last run with do_clustering (pc_last_clusters): per cluster {log<Z_p>, log<Z_p^2>} and its identity, the
+// clusters alive at the end of sampling first, then the deleted ones; per identity its parent; per dead point its cluster
+struct ClusterReport {
+    int nactive = 0;
+    std::vector<double> rows;
+    std::vector<int> uid, parent, point_uid;
+};
+static ClusterReport g_cluster_report;
 static size_t mgpu_xstride(int D) { return (size_t)((2 + D + D * (D + 1) / 2 + 1) & ~1); }
 static size_t mgpu_kr(int batch_K, int world) { return (size_t)(batch_K + world - 1) / world; }
 // [barrier][incoming last babies][statistics slots][sorted (logL, slot) runs of every rank's babies, 2 x world x kr pairs]
@@ -439,7 +447,7 @@ static void set_smem(const ShapeFns& fn, size_t smem) {
 struct HostRun {
     DevArr<DevRun> st;
     DevArr<double> live, live_snap, dead, logw, ph0, ph1, chol, cov, partial, nh, gsum, okey, bkey, dpart;
-    DevArr<int> order, lab, phl0, phl1, cfail;
+    DevArr<int> order, lab, phl0, phl1, cfail, deadlab, deadn;
     DevArr<double> cchol;
     DevArr<long long> pcount;
     DevArr<unsigned int> pmask;
@@ -818,6 +826,8 @@ struct Engine {
             if (k.dense) h.nh.alloc((size_t)G * W * (32 / L.fn.G) * R * dense_slb(L.fn.G * L.fn.DPL));   // slice records of the chains in flight
             else if (!k.nh_in_smem) h.nh.alloc((size_t)G * W * R * k.cp.LD);
             if (k.clustering) {
+                h.deadlab.alloc(cap_dead); h.deadlab.zero(stream);
+                h.deadn.alloc(cap_dead); h.deadn.zero(stream);
                 h.lab.alloc(n); h.lab.zero(stream);
                 h.phl0.alloc(cap_ph); h.phl0.zero(stream);
                 h.phl1.alloc(cap_ph); h.phl1.zero(stream);
@@ -830,7 +840,7 @@ struct Engine {
             b.pcount = h.pcount.p; b.pmask = h.pmask.p; b.nh = h.nh.p; b.cap_dead = cap_dead; b.cap_ph = cap_ph; b.gsum = h.gsum.p;
             b.lab = h.lab.p; b.phl[0] = h.phl0.p; b.phl[1] = h.phl1.p; b.cchol = h.cchol.p;
             b.boost = h.boost.p; b.boost_win = h.boost_win.p; b.cap_boost = cap_boost;
-            b.cfail = h.cfail.p; b.bkey = h.bkey.p; b.dpart = h.dpart.p;
+            b.cfail = h.cfail.p; b.bkey = h.bkey.p; b.dpart = h.dpart.p; b.deadlab = h.deadlab.p; b.deadn = h.deadn.p;
             if (sharded)  // continue the cross-GPU barrier count of earlier runs (the counters are monotonic)
                 PC_CUDA(cudaMemcpyAsync(&h.st.p->xepoch, &g_mgpu.epoch, sizeof(g_mgpu.epoch), cudaMemcpyHostToDevice, stream));
             b.seed = resumed ? rd.h.seed : (unsigned)seeds[r];   // a resumed run continues its own random stream
@@ -1097,10 +1107,26 @@ struct Engine {
         return cluster_labels_of(runs[0].live.p, runs[0].host_st.n, k.cp.D, k.cp.T, lab_out);
     }
     int cluster_labels_of(const double* d_live, int n, int D, int T, std::vector<int>& lab_out) {
-        std::vector<int> part(n, 0);
-        std::vector<char> final_part(1, 0);
-        int nparts = 1;
-        if (!d_part.p) { d_part.alloc(n); d_knn.alloc((size_t)n * KNN_K); }
+        std::vector<int> part(n, 0), origin;
+        const int nparts = refine_partition(d_live, n, D, T, part, 1, origin);
+        std::vector<int> first(nparts, -1);
+        int num = 0;
+        lab_out.resize(n);
+        for (int i = 0; i < n; ++i) {
+            if (first[part[i]] < 0) first[part[i]] = num++;
+            lab_out[i] = first[part[i]];
+        }
+        return num;
+    }
+    // The recursion itself, from ANY starting partition (do_clustering, clustering.f90:253-324, searches every existing
+    // cluster for sub-clusters): part[i] in [0, nparts0) on entry; on return the parts are final, their number is
+    // returned and origin[part] names the starting part each one descends from (a part only ever splits).
+    int refine_partition(const double* d_live, int n, int D, int T, std::vector<int>& part, int nparts0, std::vector<int>& origin) {
+        std::vector<char> final_part((size_t)nparts0, 0);
+        int nparts = nparts0;
+        origin.resize(nparts0);
+        for (int c = 0; c < nparts0; ++c) origin[c] = c;
+        if (d_part.n < (size_t)n) { d_part.alloc(n); d_knn.alloc((size_t)n * KNN_K); }
         h_knn.resize((size_t)n * KNN_K);
         std::vector<int> uf(n), loc(n), canon(n), old(n), head(n), twin_next(n), firstseen(n), members;
         members.reserve(n);
@@ -1175,33 +1201,152 @@ struct Engine {
                 if (!split || num == 1) { final_part[c] = 1; continue; }
                 // component 0 keeps the part's number, the others become new parts; all of them are searched again
                 std::vector<int> newid(num, c);
-                for (int s2 = 1; s2 < num; ++s2) { newid[s2] = nparts++; final_part.push_back(0); }
+                for (int s2 = 1; s2 < num; ++s2) { newid[s2] = nparts++; final_part.push_back(0); origin.push_back(origin[c]); }
                 for (int a = 0; a < m; ++a) part[members[a]] = newid[canon[a]];
             }
         }
-        std::vector<int> first(nparts, -1);
-        int num = 0;
-        lab_out.resize(n);
-        for (int i = 0; i < n; ++i) {
-            if (first[part[i]] < 0) first[part[i]] = num++;
-            lab_out[i] = first[part[i]];
-        }
-        return num;
+        return nparts;
     }
 
-    // the update's clustering pass: labels of the live points, labels of the phantoms (identify_cluster), one
-    // covariance + Cholesky factor per cluster (calculate_covmats, run_time_info.f90:601-641)
+    // ---- clusters with an identity ----------------------------------------
+    // The evidence of a run is GLOBAL (one nested-sampling run over the whole live set is exact whatever the shape of
+    // the posterior; keeping a volume per cluster as run_time_info.f90:211-296 does is measurably biased, DESIGN.md
+    // section 5.4), and the clusters are the reference's in every other respect: they persist -- at an update every
+    // cluster is searched for sub-clusters and SPLIT (do_clustering, clustering.f90:253-324; add_cluster,
+    // run_time_info.f90:303-505), a cluster without live points is DELETED (delete_cluster, :507-598) -- and every death
+    // is attributed to the cluster of the dying point: local evidence Z_p = sum of w L over its deaths with the global
+    // weight w = X / (n + 1), second moment <Z_p^2> by the global recurrences restricted to the cluster; a split hands
+    // the pieces the parent's evidence in proportion to their live + phantom counts (as add_cluster does).
+    struct ClusterBook {
+        std::vector<int> uid_of_index;     // device label -> identity (the device labels only change in a clustering pass)
+        std::vector<int> parent;           // per identity: the cluster it was split from (-1: the initial one)
+        std::vector<double> Zp, Zp2, ZpXn; // per identity: log<Z_p>, log<Z_p^2>, log<Z_p X> - log<X>
+        std::vector<int> dead_order;       // identities of the deleted clusters, in order of deletion
+        std::vector<int> point_uid;        // per dead point: the identity of its cluster at its death
+        long long processed = 0;           // dead points attributed so far
+        double logXX = 0.0;                // global log<X^2> before the next death to attribute
+        int new_uid(int par, double lz) {
+            parent.push_back(par); Zp.push_back(lz); Zp2.push_back(lz); ZpXn.push_back(lz);
+            return (int)parent.size() - 1;
+        }
+    };
+    ClusterBook book;
+    void book_init(long long ndead0, int ncl0, double logXX0) {
+        book = ClusterBook();
+        for (int c = 0; c < std::max(1, ncl0); ++c) book.uid_of_index.push_back(book.new_uid(-1, S.logzero));
+        book.processed = ndead0;
+        book.point_uid.assign((size_t)ndead0, 0);
+        book.logXX = logXX0;
+    }
+    static double lae(double a, double b) { return a > b ? a + std::log1p(std::exp(b - a)) : b + std::log1p(std::exp(a - b)); }
+    // the deaths [book.processed, ndead): update_evidence's local part for the cluster of each (run_time_info.f90:211-296)
+    void attribute_deaths(long long ndead) {
+        HostRun& h = runs[0];
+        const int T = L.kp.cp.T;
+        const long long d0 = book.processed, cnt = ndead - d0;
+        if (cnt <= 0) return;
+        std::vector<int> lab((size_t)cnt), nn((size_t)cnt);
+        std::vector<double> lw((size_t)cnt), ll((size_t)cnt);
+        h.deadlab.download(lab.data(), (size_t)cnt, stream, (size_t)d0);
+        h.deadn.download(nn.data(), (size_t)cnt, stream, (size_t)d0);
+        h.logw.download(lw.data(), (size_t)cnt, stream, (size_t)d0);
+        PC_CUDA(cudaMemcpy2DAsync(ll.data(), 8, h.dead.p + (size_t)d0 * T + T - 1, (size_t)T * 8, 8, (size_t)cnt, cudaMemcpyDeviceToHost, stream));
+        PC_CUDA(cudaStreamSynchronize(stream));
+        d2h += cnt * 24;
+        const double log2 = std::log(2.0);
+        book.point_uid.resize((size_t)ndead);
+        for (long long i = 0; i < cnt; ++i) {
+            const int lbl = std::max(0, std::min(lab[i], (int)book.uid_of_index.size() - 1));
+            const int u = book.uid_of_index[lbl];
+            book.point_uid[(size_t)(d0 + i)] = u;
+            const int n = nn[i];
+            if (n <= 0) continue;   // a failed birth: no weight
+            const double L0 = ll[i], lognp = std::log((double)n), lognp1 = std::log(n + 1.0), lognp2 = std::log(n + 2.0);
+            const double X_before = lw[i] + lognp1, X_after = X_before + lognp - lognp1, XX = book.logXX;
+            const double ZpX_before = book.ZpXn[u] + X_before;
+            book.Zp[u] = lae(book.Zp[u], X_before + L0 - lognp1);
+            book.Zp2[u] = lae(book.Zp2[u], lae(log2 + ZpX_before + L0 - lognp1, log2 + XX + 2 * L0 - lognp1 - lognp2));
+            // <Z_p X> shrinks with X for every cluster (that is the normalisation); the dying point's cluster gains a term
+            book.ZpXn[u] = lae(book.ZpXn[u], XX + L0 + lognp - lognp1 - lognp2 - X_after);
+            book.logXX = XX + lognp - lognp2;
+        }
+        book.processed = ndead;
+    }
+    // what pc_last_clusters reports: the clusters alive at the end (label order) then the deleted ones (order of deletion)
+    void publish_clusters() {
+        g_cluster_report.rows.clear(); g_cluster_report.uid.clear();
+        g_cluster_report.nactive = (int)book.uid_of_index.size();
+        g_cluster_report.parent = book.parent;
+        g_cluster_report.point_uid = book.point_uid;
+        auto put = [&](int u) {
+            g_cluster_report.rows.push_back(book.Zp[u]); g_cluster_report.rows.push_back(book.Zp2[u]);
+            g_cluster_report.uid.push_back(u);
+        };
+        for (int u : book.uid_of_index) put(u);
+        for (int u : book.dead_order) put(u);
+    }
+
+    // the update's clustering pass: the new deaths are attributed, empty clusters deleted, every cluster searched for
+    // sub-clusters and split; then the labels of the phantoms (identify_cluster) and one covariance + Cholesky factor per
+    // cluster (calculate_covmats, run_time_info.f90:601-641)
     void cluster_pass() {
         const KParams& k = L.kp;
         const int n = runs[0].host_st.n, D = k.cp.D, T = k.cp.T;
         HostRun& h = runs[0];
         const auto tc0 = std::chrono::steady_clock::now();
-        int num = cluster_labels(h_lab);
-        cluster_label_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count();
-        if (num > MAX_CLUSTERS) {   // further labels share the last one, which keeps the global factor
-            for (int& v : h_lab) v = std::min(v, MAX_CLUSTERS - 1);
+        h_lab.resize(n);
+        h.lab.download(h_lab.data(), n, stream);
+        PC_CUDA(cudaStreamSynchronize(stream));
+        d2h += (long long)n * 4;
+        attribute_deaths(h.host_st.ndead);
+        // delete_cluster: labels without a live point leave, the others keep their order
+        int ncl0 = (int)book.uid_of_index.size();
+        {
+            std::vector<int> cnt(ncl0, 0), remap(ncl0, -1);
+            for (int i = 0; i < n; ++i) { h_lab[i] = std::max(0, std::min(h_lab[i], ncl0 - 1)); cnt[h_lab[i]]++; }
+            std::vector<int> keep;
+            for (int c = 0; c < ncl0; ++c) {
+                if (cnt[c] > 0 || (keep.empty() && c == ncl0 - 1)) { remap[c] = (int)keep.size(); keep.push_back(book.uid_of_index[c]); }
+                else book.dead_order.push_back(book.uid_of_index[c]);
+            }
+            for (int i = 0; i < n; ++i) h_lab[i] = remap[h_lab[i]];
+            book.uid_of_index.swap(keep);
+            ncl0 = (int)book.uid_of_index.size();
         }
-        const int ncl = std::min(num, MAX_CLUSTERS);
+        // do_clustering: the recursion from the current clusters; then the new labels -- the clusters that stay whole first,
+        // in their order, the pieces of the split ones behind them (add_cluster appends), pieces in order of first
+        // appearance over the slots (relabel).  At most MAX_CLUSTERS clusters: a split that would exceed them is not made.
+        std::vector<int> part = h_lab, origin;
+        const int nparts = refine_partition(h.live.p, n, D, T, part, ncl0, origin);
+        cluster_label_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count();
+        struct Split { int parent_uid; std::vector<int> child_label; };
+        std::vector<Split> splits;
+        {
+            std::vector<int> npieces(ncl0, 0), piece_no(nparts, -1);
+            for (int i = 0; i < n; ++i)
+                if (piece_no[part[i]] < 0) piece_no[part[i]] = npieces[origin[part[i]]]++;
+            std::vector<char> split(ncl0, 0);
+            int total = ncl0;
+            for (int c = 0; c < ncl0; ++c)
+                if (npieces[c] > 1 && total - 1 + npieces[c] <= MAX_CLUSTERS) { split[c] = 1; total += npieces[c] - 1; }
+            std::vector<int> newlabel(ncl0, -1), base(ncl0, -1), uid_new;
+            int next = 0;
+            for (int c = 0; c < ncl0; ++c) if (!split[c]) { newlabel[c] = next++; uid_new.push_back(book.uid_of_index[c]); }
+            for (int c = 0; c < ncl0; ++c)
+                if (split[c]) {
+                    base[c] = next;
+                    Split sp; sp.parent_uid = book.uid_of_index[c];
+                    for (int j = 0; j < npieces[c]; ++j) { sp.child_label.push_back(next++); uid_new.push_back(book.new_uid(sp.parent_uid, S.logzero)); }
+                    splits.push_back(sp);
+                }
+            for (int i = 0; i < n; ++i) {
+                const int c = origin[part[i]];
+                h_lab[i] = split[c] ? base[c] + piece_no[part[i]] : newlabel[c];
+            }
+            book.uid_of_index.swap(uid_new);
+        }
+        const int num = (int)book.uid_of_index.size();
+        const int ncl = num;
         ++ncluster_updates;
         ncluster_max = std::max<long long>(ncluster_max, num);
         h.lab.upload(h_lab.data(), n, stream);
@@ -1257,9 +1402,26 @@ struct Engine {
             PC_CUDA(cudaGetLastError());
             pc_cluster_factor_kernel<<<ncl, 128, fsm, stream>>>(d_cpart.p, CLUSTER_CHUNKS, D, h.chol.p, h.cchol.p, d_ccount.p);
             PC_CUDA(cudaGetLastError());
-            if (num > MAX_CLUSTERS)  // the shared last label keeps the global factor
-                PC_CUDA(cudaMemcpyAsync(h.cchol.p + (size_t)(MAX_CLUSTERS - 1) * D * D, h.chol.p, (size_t)D * D * 8, cudaMemcpyDeviceToDevice, stream));
             launches += 2;
+            if (!splits.empty()) {   // add_cluster step 5: the pieces share the parent's evidence by their live + phantom counts
+                std::vector<int> cc(ncl);
+                d_ccount.download(cc.data(), ncl, stream);
+                PC_CUDA(cudaStreamSynchronize(stream));
+                for (const Split& sp : splits) {
+                    const int m = (int)sp.child_label.size();
+                    std::vector<double> logni(m), logni1(m);
+                    double tot = 0.0;
+                    for (int j = 0; j < m; ++j) { const double c = (double)cc[sp.child_label[j]]; logni[j] = std::log(c); logni1[j] = std::log(c + 1.0); tot += c; }
+                    const double logn = std::log(tot), logn1 = std::log(tot + 1.0);
+                    const int pu = sp.parent_uid;
+                    for (int j = 0; j < m; ++j) {
+                        const int u = book.uid_of_index[sp.child_label[j]];
+                        book.Zp[u] = book.Zp[pu] + logni[j] - logn;
+                        book.Zp2[u] = book.Zp2[pu] + logni[j] + logni1[j] - logn - logn1;
+                        book.ZpXn[u] = book.ZpXn[pu] + logni[j] - logn;
+                    }
+                }
+            }
         }
         PC_CUDA(cudaMemcpyAsync(&h.st.p->ncl, &ncl, sizeof(int), cudaMemcpyHostToDevice, stream));
         PC_CUDA(cudaStreamSynchronize(stream));
@@ -1444,6 +1606,11 @@ struct Engine {
             long long nc = h.buf.cap_dead * 2 + k.nmax + 3LL * k.batch_K;
             h.dead.grow((size_t)nc * k.cp.T, (size_t)h.host_st.ndead * k.cp.T, stream);
             h.logw.grow(nc, h.host_st.ndead, stream);
+            if (k.clustering) {
+                h.deadlab.grow(nc, h.host_st.ndead, stream);
+                h.deadn.grow(nc, h.host_st.ndead, stream);
+                h.buf.deadlab = h.deadlab.p; h.buf.deadn = h.deadn.p;
+            }
             h.buf.dead = h.dead.p; h.buf.logw = h.logw.p; h.buf.cap_dead = nc;
         } else {
             long long nc = h.buf.cap_ph * 2;
@@ -1502,6 +1669,8 @@ struct Engine {
             ctl->ack_seq = handled;
             dbg_service_ms += ms_since(ts);
         };
+        if (L.kp.clustering) book_init(resumed ? runs[0].host_st.ndead : 0, resumed ? runs[0].host_st.ncl : 1, resumed ? runs[0].host_st.logXX : 0.0);
+        else g_cluster_report = ClusterReport();
         for (; !resumed_finished;) {
             if (ctl) {  // size the pinned staging now: (re)allocating pinned memory synchronises with the running kernel
                 g_pin_dead.need((size_t)runs[0].buf.cap_dead * (L.kp.cp.T + 1) * 8);
@@ -1551,6 +1720,23 @@ struct Engine {
             if (all_done) break;
         }
         if (g_mgpu.world > 1) g_mgpu.epoch = runs[0].host_st.xepoch;
+        if (L.kp.clustering && !resumed_finished) {
+            // the deaths since the last pass and the final kill-off; clusters that emptied during sampling count as deleted
+            HostRun& h = runs[0];
+            const int n = h.host_st.n, ncl0 = (int)book.uid_of_index.size();
+            h_lab.resize(n);
+            h.lab.download(h_lab.data(), n, stream);
+            PC_CUDA(cudaStreamSynchronize(stream));
+            attribute_deaths(h.host_st.ndead);
+            std::vector<int> cnt(ncl0, 0), keep;
+            for (int i = 0; i < n; ++i) cnt[std::max(0, std::min(h_lab[i], ncl0 - 1))]++;
+            for (int c = 0; c < ncl0; ++c) {
+                if (cnt[c] > 0 || (keep.empty() && c == ncl0 - 1)) keep.push_back(book.uid_of_index[c]);
+                else book.dead_order.push_back(book.uid_of_index[c]);
+            }
+            book.uid_of_index.swap(keep);
+            publish_clusters();
+        }
         for (int r = 0; r < nruns; ++r)   // nested_sampling.F90:407-409
             if (runs[r].host_st.stop_nfail && S.feedback >= 0)
                 std::printf("Warning, unable to proceed after %6d: failed spawn events\n", runs[r].host_st.fail_run);
@@ -2146,6 +2332,26 @@ int pc_cluster_points(const double* points, int m, int D, int* labels_out) {
 
 // ---- output files (host only; no device needed) -------------------------------------------------
 void pc_format_e24(double v, char* out25) { format_e24(v, out25); }
+
+// Clusters of the last run with do_clustering.  Returns their number (the clusters alive at the end of sampling first, in
+// label order, then the deleted ones) and *nactive; rows (2 doubles per cluster: log<Z_p>, log<Z_p^2> -- attributed local
+// evidences) and uid (the cluster's identity) when not null.
+int pc_last_clusters(int* nactive, double* rows, int* uid) {
+    if (nactive) *nactive = g_cluster_report.nactive;
+    if (rows) std::copy(g_cluster_report.rows.begin(), g_cluster_report.rows.end(), rows);
+    if (uid) std::copy(g_cluster_report.uid.begin(), g_cluster_report.uid.end(), uid);
+    return (int)g_cluster_report.uid.size();
+}
+// ... the identity every dead point's cluster had at its death (up to cap entries; returns the number of dead points), and
+// for every identity the one it was split from (-1: the initial cluster; returns the number of identities)
+long long pc_last_dead_clusters(int* out, long long cap) {
+    if (out) std::copy(g_cluster_report.point_uid.begin(), g_cluster_report.point_uid.begin() + std::min<long long>(cap, (long long)g_cluster_report.point_uid.size()), out);
+    return (long long)g_cluster_report.point_uid.size();
+}
+int pc_last_cluster_tree(int* parent_out) {
+    if (parent_out) std::copy(g_cluster_report.parent.begin(), g_cluster_report.parent.end(), parent_out);
+    return (int)g_cluster_report.parent.size();
+}
 
 // Host-only: parse a resume file in the reference's text layout (pc_resume_text.h).  ints[8] = {nDims, nDerived, ndead,
 // ncluster, ncluster_dead, live points of all clusters, phantoms of all clusters, likelihood calls}; reals[6] = {logZ,

@@ -132,6 +132,8 @@ struct RunBuf {
     unsigned long long* boost_win;  // ... and the window of dead indices each was removed against: first << 32 | end
     long long cap_boost;
     long long cap_dead, cap_ph;
+    int* deadlab;      // clustering: cluster label every dead point carried when it died (attributed local evidences); else null
+    int* deadn;        // clustering: live points before each death (the n of its update_evidence); else null
     int* cfail;        // per chain of the generation in flight: 1 when its last baby is not above the contour (a failed birth)
     double* bkey;      // per chain of the generation in flight: logL of its last baby (phase D ranks the babies from here)
     double* dpart;     // per CTA: (max, sum of exp(logL - max)) over the live points the CTA ranked in phase D (termination test)
@@ -494,7 +496,7 @@ __device__ inline void block_sort(double* key, int* val, int np2) {
 // ------------------------------------------------------------------------------------------
 template <bool KEYS_GLOBAL = false>
 __device__ inline void evidence_deaths(DevRun* st, const double* skey, int count, int n_start, double* logw_out,
-                                       double* sc) {
+                                       double* sc, int* n_out = nullptr) {
     const double LOG2 = 0.69314718055994530942;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const double lX0 = st->logX, lXX0 = st->logXX, lZX0 = st->logZX, lZ0 = st->logZ, lZ20 = st->logZ2;
@@ -533,6 +535,7 @@ __device__ inline void evidence_deaths(DevRun* st, const double* skey, int count
             const double l0n = log((double)(n_start - j));
             const double L = keyat(j);
             logw_out[j] = lXb - l1;
+            if (n_out) n_out[j] = n_start - j;
             push(zm, zs, lXb + L - l1);
             push(z2m, z2s, logaddexp(LOG2 + ZXb + L - l1, LOG2 + lXXb + 2.0 * L - l1 - l2));
             ZXb = logaddexp(ZXb + (l0n - l1), lXXb + L + l0n - l1 - l2);

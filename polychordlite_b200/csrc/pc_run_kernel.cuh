@@ -133,7 +133,10 @@ __device__ inline void settle_generation(const KParams& p, const RunBuf& rb, Dev
         const int nf = s_nf;
         __syncthreads();
         for (int e = tid; e < T; e += nthr) rb.dead[(size_t)(nd0 + nf) * T + e] = __ldcg(rb.live + (size_t)slot * T + e);
-        if (tid == 0) { rb.logw[nd0 + nf] = p.cp.logzero; s_nf = nf + 1; s_run += 1; }
+        if (tid == 0) {
+            rb.logw[nd0 + nf] = p.cp.logzero; s_nf = nf + 1; s_run += 1;
+            if (rb.deadlab) { rb.deadlab[nd0 + nf] = __ldcg(rb.lab + slot); rb.deadn[nd0 + nf] = 0; }   // (a failed birth carries no weight)
+        }
         __syncthreads();
     }
     // (b) the empty slots
@@ -396,11 +399,13 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
         for (int i = tid; i < n; i += nthr) { newo[i] = sval[i]; newk[i] = skey[i]; }
         __syncthreads();
         if (!more) {  // final kill-off, nested_sampling.F90:381-384
-            evidence_deaths(st, skey, n, n, rb.logw + ndead, sc);
+            evidence_deaths(st, skey, n, n, rb.logw + ndead, sc, rb.deadn ? rb.deadn + ndead : nullptr);
             for (size_t e = tid; e < (size_t)n * T; e += nthr) {
                 size_t i = e / T, c = e % T;
                 rb.dead[(size_t)(ndead + i) * T + c] = __ldcg(rb.live + (size_t)sval[i] * T + c);
             }
+            if (rb.deadlab)
+                for (int i = tid; i < n; i += nthr) rb.deadlab[ndead + i] = __ldcg(rb.lab + sval[i]);
             if (tid == 0) { st->ndead = ndead + n; st->K = 0; st->B = 0; st->status = ST_DONE; }
             return false;
         }
@@ -419,7 +424,8 @@ __device__ inline bool phase_S1(const KParams& p, const RunBuf& rb, DevRun* st, 
 // head of the order phase S1 wrote
 __device__ inline void phase_S2(const KParams& p, const RunBuf& rb, DevRun* st, const SmemS& sm) {
     const int K = st->K;
-    evidence_deaths<true>(st, rb.okey + st->order_off, K, st->n_gen, rb.logw + st->ndead_base, sm.sc);
+    evidence_deaths<true>(st, rb.okey + st->order_off, K, st->n_gen, rb.logw + st->ndead_base, sm.sc,
+                          rb.deadn ? rb.deadn + st->ndead_base : nullptr);
 }
 
 // ---------------------------------------------------------------- phase D (every CTA that runs chains)
@@ -1174,6 +1180,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
             for (int k = (sharded ? 0 : B_) + gw; k < K_; k += GW) {
                 const int slot = __ldcg(ord + k);
                 for (int e = lane; e < T; e += 32) rb.dead[(size_t)(nb + k) * T + e] = __ldcg(rb.live + (size_t)slot * T + e);
+                if (rb.deadlab && lane == 0) rb.deadlab[nb + k] = __ldcg(rb.lab + slot);
             }
         }
 
@@ -1241,9 +1248,11 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
 #pragma unroll
                     for (int j = 0; j < DPL; ++j) x[j] = M.valid(j) ? __ldcg(rb.live + (size_t)src * T + M.dim(j)) : 0.0;
                     // the dying point moves to the dead list before its slot is reused (run_time_info.f90:789-817)
-                    if (active && k < K)
+                    if (active && k < K) {
                         for (int e = sub; e < T; e += G)
                             rb.dead[(size_t)(ndead_base + k) * T + e] = __ldcg(rb.live + (size_t)dslot * T + e);
+                        if (rb.deadlab && sub == 0) rb.deadlab[ndead_base + k] = __ldcg(rb.lab + dslot);
+                    }
                     __syncwarp();
                     double lfin = 0.0;
                     slice_chains_dense<G, DPL, KIND>(p.cp, M, rb.seed, uid, active, x, Lstar, gblocks + (size_t)grp * R * SLB,
@@ -1307,9 +1316,11 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
 #pragma unroll
                     for (int jj = 0; jj < DPL; ++jj) x[jj] = M.valid(jj) ? __ldcg(rb.live + (size_t)src * T + M.dim(jj)) : 0.0;
                     // the dying point moves to the dead list before its slot is reused (run_time_info.f90:789-817)
-                    if (!sharded && k < K)
+                    if (!sharded && k < K) {
                         for (int e = lane; e < T; e += 32)
                             rb.dead[(size_t)(ndead_base + k) * T + e] = __ldcg(rb.live + (size_t)dslot * T + e);
+                        if (rb.deadlab && lane == 0) rb.deadlab[ndead_base + k] = __ldcg(rb.lab + dslot);
+                    }
                     double* last = sharded ? xin_mine + (size_t)k * T : rb.live + (size_t)dslot * T;
                     long long tc2 = clock64();
                     if (ctimer && j == 0) tim[11] += tc2 - tg1;
@@ -1346,9 +1357,11 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
 #pragma unroll
                 for (int j = 0; j < DPL; ++j) x[j] = M.valid(j) ? __ldcg(rb.live + (size_t)src * T + M.dim(j)) : 0.0;
                 // the dying point moves to the dead list before its slot is reused (run_time_info.f90:789-817)
-                if (!sharded && k < K)
+                if (!sharded && k < K) {
                     for (int e = lane; e < T; e += 32)
                         rb.dead[(size_t)(ndead_base + k) * T + e] = __ldcg(rb.live + (size_t)dslot * T + e);
+                    if (rb.deadlab && lane == 0) rb.deadlab[ndead_base + k] = __ldcg(rb.lab + dslot);
+                }
                 double* last = sharded ? xin_mine + (size_t)k * T : rb.live + (size_t)dslot * T;
                 long long tc0 = clock64();
                 if (prep_uid != uid) {

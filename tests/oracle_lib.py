@@ -131,6 +131,38 @@ def set_initial_cubes(cubes):
     L.oracle_set_initial_cubes(_dptr(cubes), cubes.shape[0], cubes.shape[1])
 
 
+def last_clusters():
+    """Evidence clusters of the last batched run with clustering: (nactive, array[ncl, 3] of logZp, logZp2, logXp at the
+    end of sampling); the clusters alive at the end come first, then the deleted ones in order of deletion."""
+    L = lib()
+    L.oracle_last_clusters.restype = C.c_int
+    L.oracle_last_clusters.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    nact = C.c_int(0)
+    n = L.oracle_last_clusters(C.byref(nact), None)
+    out = np.zeros((max(n, 1), 3))
+    L.oracle_last_clusters(C.byref(nact), _dptr(out))
+    return int(nact.value), out[:n]
+
+
+def last_dead_clusters():
+    """(identity of the cluster each dead point of the last clustered batched run died in, parent of every identity,
+    identity of every cluster last_clusters() lists)."""
+    L = lib()
+    L.oracle_last_dead_clusters.restype = C.c_longlong
+    L.oracle_last_dead_clusters.argtypes = [C.POINTER(C.c_int), C.c_longlong]
+    n = L.oracle_last_dead_clusters(None, 0)
+    out = np.zeros(max(n, 1), dtype=np.int32)
+    L.oracle_last_dead_clusters(out.ctypes.data_as(C.POINTER(C.c_int)), n)
+    L.oracle_last_cluster_tree.restype = C.c_int
+    L.oracle_last_cluster_tree.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    m = L.oracle_last_cluster_tree(None, None)
+    par = np.zeros(max(m, 1), dtype=np.int32)
+    ncl = L.oracle_last_clusters(None, None)
+    cu = np.zeros(max(ncl, 1), dtype=np.int32)
+    L.oracle_last_cluster_tree(par.ctypes.data_as(C.POINTER(C.c_int)), cu.ctypes.data_as(C.POINTER(C.c_int)))
+    return out[:n], par[:m], cu[:ncl]
+
+
 def last_boosted(npars):
     """Phantoms the last run() promoted to posterior samples: (rows[nb, npars], dead_index[nb], logw[nb])."""
     L = lib()

@@ -1,7 +1,8 @@
-"""do_clustering on the device (csrc/pc_cluster.cuh): at every update the live
-points are clustered (device k-nearest neighbours + host union-find = the reference's NN_clustering), the phantoms
-take the label of their nearest live point, every cluster gets its own covariance / Cholesky factor and a chain
-whitens with the factor of its seed's cluster.  Checked against the oracle's batched schedule with clustering on
+"""do_clustering on the device (csrc/pc_cluster.cuh): at every update every cluster
+is searched for sub-clusters (device k-nearest neighbours + host union-find = the reference's NN_clustering) and split,
+a cluster without live points is deleted, the phantoms take the label of their nearest live point, every cluster gets
+its own covariance / Cholesky factor and a chain whitens with the factor of its seed's cluster; every death is
+attributed to the cluster of the dying point (local evidences).  Checked against the oracle's batched schedule with clustering on
 (same labels => same factors => same chains: identical ndead / nlike, logZ to rounding) and against the analytic
 Rastrigin evidence."""
 import numpy as np
@@ -52,6 +53,21 @@ def test_clustered_rastrigin_run_matches_oracle(gpu, oracle, seed):
     assert gi.ncluster_updates == gi.nupdates
     assert (gi.ndead, gi.nlike, gi.nupdates) == (oi.ndead, oi.nlike, oi.nupdates)
     assert abs(gi.logZ - oi.logZ) < 1e-7
+    assert gi.ncluster_max == oi.ncluster
+    # the clusters themselves: the same identities alive and deleted, the same dead points in each, the same local
+    # evidences log<Z_p> and second moments log<Z_p^2>; the local evidences add up to the global one
+    g_act, g_rows, g_uid = gpu.last_clusters()
+    o_act, o_rows = oracle.last_clusters()
+    o_dead, o_par, o_uid = oracle.last_dead_clusters()
+    g_dead, g_par = gpu.last_dead_clusters()
+    assert g_act == o_act and np.array_equal(g_uid[:g_act], o_uid[:o_act])
+    assert sorted(g_uid[g_act:]) == sorted(o_uid[o_act:]) and len(g_uid) == len(set(g_uid))
+    assert np.array_equal(g_par, o_par) and np.array_equal(g_dead, o_dead)
+    go, oo = np.argsort(g_uid), np.argsort(o_uid)
+    assert np.allclose(g_rows[go], o_rows[oo][:, :2], rtol=0, atol=1e-7)
+    lz = g_rows[:, 0]
+    assert abs(lz.max() + np.log(np.exp(lz - lz.max()).sum()) - gi.logZ_raw) < 1e-9
+    assert np.all(g_rows[:, 1] >= 2 * g_rows[:, 0] - 1e-9)          # <Z_p^2> >= <Z_p>^2
 
 
 def test_unimodal_run_with_clustering_on_matches_oracle(gpu, oracle):
