@@ -1459,7 +1459,9 @@ struct Run {
         std::vector<double> newpts((size_t)std::max(B, 1) * T);
         std::vector<int> newlab(std::max(B, 1), 0);
         std::vector<char> ok(std::max(B, 1), 0);
-        const bool clustered = per_cluster && ev.size() > 1, factors = labelled_ev && ev.size() > 1;
+        // (a chain whitens with its seed's cluster's factor -- also when deletions have left a single cluster: that cluster
+        // keeps the factor of its own points until the next update)
+        const bool clustered = per_cluster && ev.size() > 1, factors = labelled_ev;
         int nfailed = 0;
         for (int k = 0; k < B; ++k) {
             uint64_t uid = (uint64_t)nchains + k;

@@ -151,6 +151,8 @@ struct ClusterReport {
     int nactive = 0;
     std::vector<double> rows;
     std::vector<int> uid, parent, point_uid;
+    std::vector<double> frac;   // per identity: log share of its parent's evidence it received at the split
+    std::vector<double> zp, zp2; // rows, one column each (what the file writer takes)
 };
 static ClusterReport g_cluster_report;
 static size_t mgpu_xstride(int D) { return (size_t)((2 + D + D * (D + 1) / 2 + 1) & ~1); }
@@ -995,8 +997,17 @@ struct Engine {
             BoostedRows br;
             br.n = (long long)mr.boost_logw.size(); br.rows = mr.boost_rows.data(); br.logw = mr.boost_logw.data();
             br.after = mr.boost_after.data();
+            ClusterRows cr;
+            const ClusterReport& rep = g_cluster_report;
+            if (k.clustering && !rep.uid.empty() && (long long)rep.point_uid.size() >= (final_call ? ndead : 0)) {
+                cr.n = (int)rep.uid.size(); cr.nactive = rep.nactive; cr.logZp = rep.zp.data(); cr.logZp2 = rep.zp2.data();
+                cr.uid = rep.uid.data(); cr.nuid = (int)rep.parent.size(); cr.parent = rep.parent.data(); cr.frac = rep.frac.data();
+                // the cluster files need every dead point's cluster: they are written with the final files
+                cr.point_uid = (long long)rep.point_uid.size() >= ndead ? rep.point_uid.data() : nullptr;
+                cr.cluster_posteriors = S.cluster_posteriors != 0;
+            }
             write_run_files(g_files, g_fstate, D, P, ndead, mr.rows.data(), mr.logw.data(), nl, live_rows.data(), lz,
-                            std::sqrt(std::fabs(var)), nlike_now, final_call, br.n ? &br : nullptr);
+                            std::sqrt(std::fabs(var)), nlike_now, final_call, br.n ? &br : nullptr, cr.n ? &cr : nullptr);
         }
     }
 
@@ -1221,12 +1232,13 @@ struct Engine {
         std::vector<int> uid_of_index;     // device label -> identity (the device labels only change in a clustering pass)
         std::vector<int> parent;           // per identity: the cluster it was split from (-1: the initial one)
         std::vector<double> Zp, Zp2, ZpXn; // per identity: log<Z_p>, log<Z_p^2>, log<Z_p X> - log<X>
+        std::vector<double> frac;          // per identity: log(n_i / n), its share of the parent's evidence at the split (0: none)
         std::vector<int> dead_order;       // identities of the deleted clusters, in order of deletion
         std::vector<int> point_uid;        // per dead point: the identity of its cluster at its death
         long long processed = 0;           // dead points attributed so far
         double logXX = 0.0;                // global log<X^2> before the next death to attribute
         int new_uid(int par, double lz) {
-            parent.push_back(par); Zp.push_back(lz); Zp2.push_back(lz); ZpXn.push_back(lz);
+            parent.push_back(par); Zp.push_back(lz); Zp2.push_back(lz); ZpXn.push_back(lz); frac.push_back(0.0);
             return (int)parent.size() - 1;
         }
     };
@@ -1278,8 +1290,11 @@ struct Engine {
         g_cluster_report.nactive = (int)book.uid_of_index.size();
         g_cluster_report.parent = book.parent;
         g_cluster_report.point_uid = book.point_uid;
+        g_cluster_report.frac = book.frac;
+        g_cluster_report.zp.clear(); g_cluster_report.zp2.clear();
         auto put = [&](int u) {
             g_cluster_report.rows.push_back(book.Zp[u]); g_cluster_report.rows.push_back(book.Zp2[u]);
+            g_cluster_report.zp.push_back(book.Zp[u]); g_cluster_report.zp2.push_back(book.Zp2[u]);
             g_cluster_report.uid.push_back(u);
         };
         for (int u : book.uid_of_index) put(u);
@@ -1419,12 +1434,14 @@ struct Engine {
                         book.Zp[u] = book.Zp[pu] + logni[j] - logn;
                         book.Zp2[u] = book.Zp2[pu] + logni[j] + logni1[j] - logn - logn1;
                         book.ZpXn[u] = book.ZpXn[pu] + logni[j] - logn;
+                        book.frac[u] = logni[j] - logn;
                     }
                 }
             }
         }
         PC_CUDA(cudaMemcpyAsync(&h.st.p->ncl, &ncl, sizeof(int), cudaMemcpyHostToDevice, stream));
         PC_CUDA(cudaStreamSynchronize(stream));
+        publish_clusters();
         cluster_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count();
     }
 

@@ -7,6 +7,8 @@
 #include <cstring>
 #include <limits>
 #include <stdexcept>
+#include <sys/stat.h>
+#include <algorithm>
 #include "pc_errors.h"
 #include <vector>
 
@@ -81,9 +83,17 @@ void write_prior_info(const FileOpts& o, long long nprior, long long ndiscarded)
     std::fclose(f);
 }
 
+// log of the sum of the local evidences (= the global log<Z>: every death belongs to exactly one cluster)
+static double logZ_raw_of(const ClusterRows* c) {
+    double m = -std::numeric_limits<double>::infinity(), s2 = 0.0;
+    for (int i = 0; i < c->n; ++i) m = std::max(m, c->logZp[i]);
+    for (int i = 0; i < c->n; ++i) s2 += std::exp(c->logZp[i] - m);
+    return m + std::log(s2);
+}
+
 int write_run_files(const FileOpts& o, FileState& st, int D, int P, long long ndead, const double* dead_rows,
                     const double* dead_logw, int nlive, const double* live_rows, double logZ, double logZerr,
-                    long long nlike, bool final_call, const BoostedRows* boosted) {
+                    long long nlike, bool final_call, const BoostedRows* boosted, const ClusterRows* clusters) {
     if (!o.enabled) return 0;
     const auto now = std::chrono::steady_clock::now();
     if (!final_call && st.written && std::chrono::duration<double>(now - st.last).count() < o.min_interval_s) return 0;
@@ -208,6 +218,65 @@ int write_run_files(const FileOpts& o, FileState& st, int D, int P, long long nd
         }
     }
 
+    // cluster posteriors (read_write.F90:527-607): file i belongs to the cluster with the i-th largest local evidence; its
+    // points are the dead points of the cluster and of its ancestors (scaled by the shares the pieces received)
+    if (clusters && clusters->cluster_posteriors && clusters->n > 0 && clusters->point_uid && (o.posteriors || o.equals)) {
+        const std::string cdir = o.base_dir + "/clusters";
+        ::mkdir(cdir.c_str(), 0777);
+        std::vector<int> ordering(clusters->n);
+        for (int c = 0; c < clusters->n; ++c) ordering[c] = c;
+        std::stable_sort(ordering.begin(), ordering.end(), [&](int x, int y) { return clusters->logZp[x] > clusters->logZp[y]; });
+        std::vector<double> scale((size_t)clusters->nuid);
+        for (int i = 0; i < clusters->n; ++i) {
+            const int c = ordering[i];
+            // log share of every identity's points in this cluster: 0 for itself, the product of the shares down the line
+            // of descent for an ancestor, nothing for anybody else
+            std::fill(scale.begin(), scale.end(), -std::numeric_limits<double>::infinity());
+            double acc = 0.0;
+            for (int u = clusters->uid[c]; u >= 0 && u < clusters->nuid; u = clusters->parent[u]) {
+                scale[u] = acc;
+                acc += clusters->frac[u];
+            }
+            double cmax = -std::numeric_limits<double>::infinity();
+            for (long long k = 0; k < ndead; ++k) {
+                const int u = clusters->point_uid[k];
+                if (u >= 0 && u < clusters->nuid && std::isfinite(scale[u])) cmax = std::max(cmax, dead_logw[k] + scale[u]);
+            }
+            const std::string base = cdir + "/" + o.file_root + "_" + std::to_string(i + 1);
+            const double rel = std::exp(clusters->logZp[c] - logZ_raw_of(clusters));   // exp(logZp - logZ): the cluster's share of the evidence
+            if (o.posteriors) {
+                Out w(base + ".txt");
+                for (long long k = 0; k < ndead; ++k) {
+                    const int u = clusters->point_uid[k];
+                    if (u < 0 || u >= clusters->nuid || !std::isfinite(scale[u])) continue;
+                    const double wgt = std::exp(dead_logw[k] + scale[u] - cmax) * rel;
+                    if (!(wgt > 0.0)) continue;
+                    const double* r = dead_rows + (size_t)k * npars;
+                    w.num(wgt);
+                    w.num(-2.0 * r[np + 1]);
+                    for (int q = 0; q < np; ++q) w.num(r[q]);
+                    w.nl();
+                }
+                ++files;
+            }
+            if (o.equals) {
+                Out w(base + "_equal_weights.txt");
+                for (long long k = 0; k < ndead; ++k) {
+                    const int u = clusters->point_uid[k];
+                    if (u < 0 || u >= clusters->nuid || !std::isfinite(scale[u])) continue;
+                    const double uu = uniform(o.seed, TAG_POST, (uint64_t)k, 1u + (unsigned)c, 0u);
+                    if (!(uu < std::exp(dead_logw[k] + scale[u] - cmax))) continue;
+                    const double* r = dead_rows + (size_t)k * npars;
+                    w.num(rel);
+                    w.num(-2.0 * r[np + 1]);
+                    for (int q = 0; q < np; ++q) w.num(r[q]);
+                    w.nl();
+                }
+                ++files;
+            }
+        }
+    }
+
     if (o.write_stats) {  // write_stats_file, read_write.F90:809-910 (one cluster: evidence is kept globally)
         Out w(root + ".stats");
         char a[25], b[25];
@@ -226,14 +295,30 @@ int write_run_files(const FileOpts& o, FileState& st, int D, int P, long long nd
         w.line("Local evidences:");
         w.line("----------------");
         w.line("");
-        if (nlive > 0) std::fprintf(w.f, "log(Z_1)     = %s +/- %s (Still Active)\n", a, b);
+        int ncl_active = nlive > 0 ? 1 : 0, ncl_total = 1;
+        if (clusters && clusters->n > 0) {
+            // calculate_logZ_estimate (run_time_info.f90:652-678) per cluster; label "log(Z_p)" padded as read_write.F90:861-871
+            ncl_active = nlive > 0 ? clusters->nactive : 0;
+            ncl_total = clusters->n;
+            for (int c = 0; c < clusters->n; ++c) {
+                const double lz = std::max(-std::numeric_limits<double>::max(), 2 * clusters->logZp[c] - 0.5 * clusters->logZp2[c]);
+                const double var = clusters->logZp2[c] - 2 * clusters->logZp[c];
+                char lbl[32];
+                std::snprintf(lbl, sizeof(lbl), "log(Z_%d)", c + 1);
+                const int digits = (int)std::strlen(lbl) - 7;
+                format_e24(lz, a); format_e24(std::sqrt(std::fabs(var)), b);
+                std::fprintf(w.f, "%s%*s= %s +/- %s%s\n", lbl, std::max(0, 6 - digits), "", a, b,
+                             (nlive > 0 && c < clusters->nactive) ? " (Still Active)" : "");
+            }
+            format_e24(logZ, a); format_e24(logZerr, b);
+        } else if (nlive > 0) std::fprintf(w.f, "log(Z_1)     = %s +/- %s (Still Active)\n", a, b);
         else std::fprintf(w.f, "log(Z_1)     = %s +/- %s\n", a, b);
         w.line("");
         w.line("");
         w.line("Run-time information:");
         w.line("---------------------");
         w.line("");
-        std::fprintf(w.f, " ncluster:   %8d /%8d\n", nlive > 0 ? 1 : 0, 1);
+        std::fprintf(w.f, " ncluster:   %8d /%8d\n", ncl_active, ncl_total);
         std::fprintf(w.f, " nposterior: %8lld\n", nposterior);
         std::fprintf(w.f, " nequals:    %8lld\n", nequals);
         std::fprintf(w.f, " ndead:      %8lld\n", ndead);

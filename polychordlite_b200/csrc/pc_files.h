@@ -40,12 +40,31 @@ struct BoostedRows {
     const long long* after = nullptr;
 };
 
+// Clusters of a run with do_clustering: the "Local evidences" table of <root>.stats
+// (read_write.F90:858-872) and, with cluster_posteriors, the files clusters/<root>_<i>.txt and
+// clusters/<root>_<i>_equal_weights.txt (read_write.F90:527-607).  Clusters are listed active first, then deleted;
+// frac[u] is the share log(n_i / n) of its parent's evidence identity u received when it was split off (0 for the initial
+// cluster): a cluster's posterior holds its own dead points and, scaled by those shares, the ones of its ancestors (the
+// reference copies the parent's posterior to every piece with the weights reduced in that proportion,
+// run_time_info.f90:433-441, 497-503).
+struct ClusterRows {
+    int n = 0, nactive = 0;
+    const double* logZp = nullptr;   // n
+    const double* logZp2 = nullptr;  // n
+    const int* uid = nullptr;        // n: identity of every listed cluster
+    int nuid = 0;
+    const int* parent = nullptr;     // nuid: identity a cluster was split from (-1: none)
+    const double* frac = nullptr;    // nuid
+    const int* point_uid = nullptr;  // per dead point: identity of its cluster at its death
+    bool cluster_posteriors = false;
+};
+
 // Writes every requested file under base_dir.  dead_rows/live_rows: rows [theta(D), phi(P), birth, logL];
 // dead_logw[i] = log-weight + logL of dead point i (unnormalised posterior log-weight).
 // Returns the number of files written; throws std::runtime_error when a file cannot be opened.
 int write_run_files(const FileOpts& o, FileState& st, int D, int P, long long ndead, const double* dead_rows,
                     const double* dead_logw, int nlive, const double* live_rows, double logZ, double logZerr,
-                    long long nlike, bool final_call, const BoostedRows* boosted = nullptr);
+                    long long nlike, bool final_call, const BoostedRows* boosted = nullptr, const ClusterRows* clusters = nullptr);
 
 // generate.F90:274-279
 void write_prior_info(const FileOpts& o, long long nprior, long long ndiscarded);

@@ -14,9 +14,10 @@ def _case(rng, i):
         like = "gaussian"
     P = int(rng.choice([0, 0, 1, 2, 3])) if like == "gaussian" else 0
     n = int(rng.choice([4, 7, 16, 50, 120, 300]))
-    if D > 32:
+    if D >= 32:
         n = max(n, 50)   # with far fewer live points than dimensions the covariance is rank-deficient and the Cholesky
-                         # fallback decision is rounding noise: no parity statement is possible there
+                         # fallback decision is rounding noise: no parity statement is possible there (with clustering on
+                         # the same holds for the factor of a cluster that has just over nDims points)
     R = int(rng.choice([1, 2, D, 2 * D + 1]))
     R = min(R, 60)
     grades = None
