@@ -118,3 +118,26 @@ def test_clustering_off_and_on_agree_statistically(oracle):
          for c in (False, True) for s in range(10)]
     off, on = np.array(a[:10]), np.array(a[10:])
     assert abs(off.mean() - on.mean()) < 4 * np.sqrt(off.var(ddof=1) / 10 + on.var(ddof=1) / 10) + 0.05
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_batched_clusters_keep_their_identity_and_their_evidences_add_up(oracle, mode):
+    """The batched schedule with clustering (the engine's): clusters persist (split at updates, deleted when empty), every
+    death belongs to one cluster, and the local evidences add up to the global one -- with the evidence kept globally and
+    the deaths attributed (mode 1, the engine's) and with per-cluster volumes as the reference keeps them (mode 2)."""
+    s = oracle.make_settings(2, 0, nlive=300, num_repeats=6, seed=4, do_clustering=mode, batch_K=75)
+    r, _ = oracle.run(s, like="rastrigin", prior_lo=[-5.12] * 2, prior_hi=[5.12] * 2)
+    nact, rows = oracle.last_clusters()
+    dead, parent, uid = oracle.last_dead_clusters()
+    assert r.ncluster > 1 and len(rows) == len(uid) > nact >= 1
+    lz = rows[:, 0]
+    assert abs(lz.max() + np.log(np.exp(lz - lz.max()).sum()) - r.logZ_raw) < 1e-9
+    assert np.all(rows[:, 1] >= 2 * rows[:, 0] - 1e-9)                       # <Z_p^2> >= <Z_p>^2
+    assert len(dead) == r.ndead and dead.min() >= 0 and dead.max() < len(parent)
+    assert parent[0] == -1 and np.all(parent[1:] >= 0) and np.all(parent[1:] < np.arange(1, len(parent)))   # a tree, parents first
+    assert len(set(uid)) == len(uid)
+    # a cluster that was split is neither alive nor deleted at the end: its evidence went to its pieces
+    assert not (set(parent[1:]) & set(uid))
+    # every listed cluster that has dead points of its own has a finite local evidence
+    own = set(dead)
+    assert all(np.isfinite(rows[i, 0]) and rows[i, 0] > -1e29 for i, u in enumerate(uid) if u in own)
