@@ -76,7 +76,7 @@ def flops_per_eval(w):
 
 def committed_traffic(tag):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this workload."""
-    for name in (f"r02_ncu_{tag}.json",):
+    for name in (f"r02_ncu_{tag}.json", f"r02_ncu_{tag}_single.json"):
         p = ROOT / "profiles" / name
         if p.exists():
             try:

@@ -749,6 +749,7 @@ struct Engine {
                 throw pc::ArgError("polychord_b200: the resume file " + g_resume.path + " belongs to a run of a different shape "
                                             "(nDims, nDerived, nlive, num_repeats, grades, likelihood kind, clustering or batch size)");
             resumed = true;
+            g_files.seed = rh.seed;   // the continuation is the file's run: the equal-weights thinning follows its seed too
         }
         // CTAs per run: one warp per chain unless capped by residency
         int dev = 0, sms = 0, per_sm = 0;
@@ -2539,6 +2540,8 @@ void polychord_c_interface(pc_loglikelihood_t loglikelihood, pc_prior_t prior, p
     } else if (grade_dims && grade_dims[0] != nDims) {
         fail(-4, "grade_dims must sum to nDims");
         return;
+    } else if (nGrade == 1 && grade_frac && grade_frac[0] > 1.0) {
+        s.num_repeats = (int)grade_frac[0];   // generate.F90:304-309: every grade_frac > 1 -- the fractions are the repeat counts
     }
     // dynamic nlive (settings%loglikes / settings%nlives, interfaces.F90:416-422): the batched form of replace_point's
     // rule (run_time_info.f90:766-777), phase S1
@@ -2578,7 +2581,7 @@ void polychord_c_interface(pc_loglikelihood_t loglikelihood, pc_prior_t prior, p
     fo.enabled = write_stats || write_live || write_dead || write_prior || posteriors || equals;
     fo.base_dir = base_dir ? std::string(base_dir) : std::string(".");   // read up to the first NUL only (utils.F90:787-801)
     fo.file_root = file_root ? std::string(file_root) : std::string("test");
-    fo.compression_factor = compression_factor; fo.num_repeats = num_repeats; fo.seed = (unsigned)seed; fo.logzero = logzero;
+    fo.compression_factor = compression_factor; fo.num_repeats = s.num_repeats; fo.seed = (unsigned)seed; fo.logzero = logzero;
     if (fo.enabled) {
         FILE* probe = std::fopen((fo.base_dir + "/.pc_probe").c_str(), "w");
         if (!probe) {
