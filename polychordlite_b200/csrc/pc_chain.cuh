@@ -54,11 +54,13 @@ struct ChainScratch {
     double* stage; // dense layout only: NPT x 2 x slb doubles, the point groups' slice-record buffers (pc_dense.cuh)
     int* deck;     // R: column used by slice i
     int* jd;       // R: Fisher-Yates picks
+    bool nh_smem;  // nh lives in shared memory (else in global memory: bases are orthogonalised in a staging area)
 };
 
 // Gram-Schmidt projections (4 x Dpad) share their area with the tail queue of the Gaussian deviates (64 arguments + 64
-// element indices, prep_chain)
-__host__ __device__ constexpr int dots_doubles(int Dpad) { return 4 * Dpad > 96 ? 4 * Dpad : 96; }
+// element indices, prep_chain); the block form of Gram-Schmidt (more than 32 dimensions) keeps the 8-column panel's
+// projections on all earlier vectors there: 8 x Dpad
+__host__ __device__ constexpr int dots_doubles(int Dpad) { return Dpad > 32 ? 8 * Dpad : (4 * Dpad > 96 ? 4 * Dpad : 96); }
 
 // slb > 0 selects the dense layout (pc_dense.cuh): slb doubles per slice record, no uniforms in shared memory
 __host__ __device__ inline size_t chain_scratch_bytes(int D, int R, int LD, bool nh_in_smem, int like_kind, int npt, int slb = 0) {
@@ -90,6 +92,7 @@ __device__ __forceinline__ ChainScratch chain_scratch(unsigned char* base, int D
     if (like_kind == LIKE_CORR) d += (size_t)npt * Dpad;
     cs.deck = (int*)d;
     cs.jd = cs.deck + R;
+    cs.nh_smem = nh_in_smem;
     return cs;
 }
 
@@ -236,6 +239,130 @@ struct Model {
 };
 
 // ------------------------------------------------------------------------------------------
+// gram_schmidt_block: Gram-Schmidt of ONE basis (random_utils.F90:381-403) on the FP64 tensor cores, for bases of more
+// than 32 dimensions.  q0: column 0 of the basis (column c at q0 + c*LDQ, Dg rows), m <= Dg vectors are wanted.
+//
+// The columns are taken in panels of eight.  Against the vectors of the earlier panels a panel is orthogonalised with
+// two small matrix products, W = Qprev^T V (all projections taken from the raw panel, as the classical form does) and
+// V -= Qprev W: m8n8k4 DMMAs whose fragments come straight from the columns; inside the panel the eight vectors follow
+// the classical form one after the other with the rows dealt over the lanes and the finished panel vectors in
+// registers.  The vector-at-a-time form above costs two shared-memory loads per multiply-add and, with one basis left
+// over (R = 5 D: four bases side by side, then one on a quarter of the lanes), most of its lanes: measured 54 % of
+// all warp samples of the 50-dimensional BASELINE run (profiles/r02b_summary.md).
+// wbuf: 8 * (Dg rounded up to 8) doubles.  MAXMT >= ceil(Dg / 8).
+// ------------------------------------------------------------------------------------------
+template <int MAXMT>
+__device__ __noinline__ void gram_schmidt_block(double* q0, int LDQ, int Dg, int m, double* wbuf) {
+    constexpr int MAXRPL = (MAXMT * 8 + 31) / 32;
+    const int lane = threadIdx.x & 31, fr = lane >> 2, fk = lane & 3;
+    const int MT = (Dg + 7) >> 3, KT = (Dg + 3) >> 2;
+    for (int p0 = 0; p0 < m; p0 += 8) {
+        const int pw = min(8, m - p0);
+        if (p0 > 0) {
+            const int NT = p0 >> 3;  // 8-vector tiles of the earlier panels
+            {   // W[j][c] = q_j . v_{p0+c}: A = Qprev^T (row = earlier vector, k = dimension), B = the panel (k = dimension, col = vector)
+                double a0[MAXMT], a1[MAXMT];
+#pragma unroll
+                for (int t = 0; t < MAXMT; ++t) a0[t] = a1[t] = 0.0;
+                const bool bcol = fr < pw;
+                const double* vb = q0 + (size_t)(p0 + (bcol ? fr : 0)) * LDQ;
+                for (int kt = 0; kt < KT; ++kt) {
+                    const int k = 4 * kt + fk;
+                    const bool kin = k < Dg;
+                    const double b = (kin && bcol) ? vb[k] : 0.0;
+#pragma unroll
+                    for (int t = 0; t < MAXMT; ++t)
+                        if (t < NT) {
+                            const double a = kin ? q0[(size_t)(8 * t + fr) * LDQ + k] : 0.0;
+                            dmma884(a0[t], a1[t], a, b);
+                        }
+                }
+#pragma unroll
+                for (int t = 0; t < MAXMT; ++t)
+                    if (t < NT) {  // this lane holds W[8t + fr][2 fk + {0, 1}]
+                        wbuf[(8 * t + fr) * 8 + 2 * fk] = a0[t];
+                        wbuf[(8 * t + fr) * 8 + 2 * fk + 1] = a1[t];
+                    }
+            }
+            __syncwarp();
+            {   // V -= Qprev W: A = Qprev (row = dimension, k = earlier vector), B = -W, C = the panel (row = dimension, col = vector)
+                double c0[MAXMT], c1[MAXMT];
+                const int ca = p0 + 2 * fk;
+                const bool h0 = 2 * fk < pw, h1 = 2 * fk + 1 < pw;
+#pragma unroll
+                for (int mt = 0; mt < MAXMT; ++mt) {
+                    const int r = 8 * mt + fr;
+                    c0[mt] = (mt < MT && r < Dg && h0) ? q0[(size_t)ca * LDQ + r] : 0.0;
+                    c1[mt] = (mt < MT && r < Dg && h1) ? q0[(size_t)(ca + 1) * LDQ + r] : 0.0;
+                }
+                for (int kt = 0; kt < 2 * NT; ++kt) {
+                    const int j = 4 * kt + fk;
+                    const double b = -wbuf[j * 8 + fr];
+                    const double* qj = q0 + (size_t)j * LDQ;
+#pragma unroll
+                    for (int mt = 0; mt < MAXMT; ++mt)
+                        if (mt < MT) {
+                            const int r = 8 * mt + fr;
+                            const double a = r < Dg ? qj[r] : 0.0;
+                            dmma884(c0[mt], c1[mt], a, b);
+                        }
+                }
+#pragma unroll
+                for (int mt = 0; mt < MAXMT; ++mt) {
+                    const int r = 8 * mt + fr;
+                    if (mt < MT && r < Dg) {
+                        if (h0) q0[(size_t)ca * LDQ + r] = c0[mt];
+                        if (h1) q0[(size_t)(ca + 1) * LDQ + r] = c1[mt];
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // inside the panel: rows lane, lane + 32, ... of a vector on this lane, the finished vectors of the panel in registers
+        double P[8][MAXRPL];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < pw) {  // warp-uniform
+                double* col = q0 + (size_t)(p0 + i) * LDQ;
+                double v[MAXRPL];
+#pragma unroll
+                for (int r = 0; r < MAXRPL; ++r) v[r] = (lane + 32 * r < Dg) ? col[lane + 32 * r] : 0.0;
+                double d[8];
+#pragma unroll
+                for (int j = 0; j < i; ++j) {
+                    double sdot = 0.0;
+#pragma unroll
+                    for (int r = 0; r < MAXRPL; ++r) sdot = fma(P[j][r], v[r], sdot);
+                    d[j] = sdot;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int j = 0; j < i; ++j) d[j] += __shfl_xor_sync(FULL, d[j], o);
+                }
+#pragma unroll
+                for (int j = 0; j < i; ++j) {
+#pragma unroll
+                    for (int r = 0; r < MAXRPL; ++r) v[r] = fma(-d[j], P[j][r], v[r]);
+                }
+                double nrm = 0.0;
+#pragma unroll
+                for (int r = 0; r < MAXRPL; ++r) nrm = fma(v[r], v[r], nrm);
+                nrm = warp_sum(nrm);
+                const double inv = 1.0 / sqrt(nrm);
+#pragma unroll
+                for (int r = 0; r < MAXRPL; ++r) {
+                    v[r] *= inv;
+                    P[i][r] = v[r];
+                    if (lane + 32 * r < Dg) col[lane + 32 * r] = v[r];
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // prep_chain: everything of a chain that depends only on (seed, uid).
 //   nh   <- ceil(R/D) Haar-random orthonormal bases (Gram-Schmidt on Gaussian vectors,
 //           random_utils.F90:381-437), column c at nh + c*LD
@@ -269,11 +396,19 @@ __device__ inline void prep_chain(int D, int R, int LD, unsigned seed, unsigned 
         }
         cs.jd[i] = j;
     }
-    if (cs.uni)
+    // bases of more than 32 dimensions take the block form of Gram-Schmidt (gram_schmidt_block); when the directions
+    // live in global memory a basis is drawn and orthogonalised in a staging area of shared memory -- the room of the
+    // widths and the slice uniforms, which are only written afterwards -- and copied out once
+    constexpr bool HAS_BLOCK = (GD == 0 || GD > 32);
+    constexpr int BLOCK_MT = GD > 0 ? (GD + 7) / 8 : 16;
+    const bool can_stage = HAS_BLOCK && D > 32 && !cs.nh_smem && cs.uni != nullptr;
+    auto draw_uniforms = [&]() {
         for (int e = lane; e < R * NU; e += 32) {
             const int i = e / NU, s = e - i * NU;
             cs.uni[e] = uniform(seed, TAG_SLICE, uid, (unsigned)i, (unsigned)s);
         }
+    };
+    if (cs.uni && !can_stage) draw_uniforms();
     const int Dpad = (D + 1) & ~1;
     // generate_nhats (chordal_sampling.f90:94-145): grade g contributes Rg columns (from column cbase) drawn from
     // orthonormal bases of the sub-space of the dimensions roff..D-1 (the dimensions of grades >= g); the rows above
@@ -282,25 +417,26 @@ __device__ inline void prep_chain(int D, int R, int LD, unsigned seed, unsigned 
     for (int g = 0; g < ngrade; ++g) {
         const int Dg = D - roff;
         const int Rg = ngrade > 1 ? gp->greps[g] : R;
-        // (a) Gaussian deviates, two per Philox block (inv_normal_cdf = AS241, utils.F90:777-966)
-        {
-            const int H = (Dg + 1) >> 1, total = Rg * H;
+        // (a) Gaussian deviates, two per Philox block (inv_normal_cdf = AS241, utils.F90:777-966): columns
+        //     cfirst .. cfirst + ncols - 1 of this grade, element (column c, row r of the sub-space) at dst[c*ldd + r]
+        auto fill_gauss = [&](int cfirst, int ncols, double* dst, int ldd) {
+            const int H = (Dg + 1) >> 1, total = ncols * H;
             double* qp = cs.dots;                    // tail queue: up to 64 arguments ...
-            int* qi = (int*)(cs.dots + 64);          // ... and the elements of nh they belong to
+            int* qi = (int*)(cs.dots + 64);          // ... and the elements of dst they belong to
             int qn = 0;
             for (int e0 = 0; e0 < total; e0 += 32) {
                 const int e = e0 + lane;
                 const bool act = e < total;
                 const int col = act ? e / H : 0, hp = e - col * H;
                 double u0 = 0.5, u1 = 0.5;
-                if (act) uniform2(seed, TAG_DIR, uid, (unsigned)(cbase + col), (unsigned)hp, u0, u1);
-                const int slot = (cbase + col) * LD + roff + 2 * hp;
+                if (act) uniform2(seed, TAG_DIR, uid, (unsigned)(cbase + cfirst + col), (unsigned)hp, u0, u1);
+                const int slot = col * ldd + 2 * hp;
                 const bool has1 = act && (2 * hp + 1 < Dg);
                 double z0, z1;
                 const bool tl0 = !inv_normal_cdf_central(u0, z0) && act;
                 const bool tl1 = !inv_normal_cdf_central(u1, z1) && has1;
-                if (act && !tl0) nh[slot] = z0;
-                if (has1 && !tl1) nh[slot + 1] = z1;
+                if (act && !tl0) dst[slot] = z0;
+                if (has1 && !tl1) dst[slot + 1] = z1;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const bool tl = half ? tl1 : tl0;
@@ -314,7 +450,7 @@ __device__ inline void prep_chain(int D, int R, int LD, unsigned seed, unsigned 
                     qn += __popc(m);
                     __syncwarp();
                     if (qn >= 32) {   // a full warp of tail draws
-                        nh[qi[lane]] = inv_normal_cdf_tail(qp[lane]);
+                        dst[qi[lane]] = inv_normal_cdf_tail(qp[lane]);
                         const int rest = qn - 32;
                         double tp = 0.0;
                         int ti = 0;
@@ -326,8 +462,11 @@ __device__ inline void prep_chain(int D, int R, int LD, unsigned seed, unsigned 
                     }
                 }
             }
-            if (lane < qn) nh[qi[lane]] = inv_normal_cdf_tail(qp[lane]);
-        }
+            if (lane < qn) dst[qi[lane]] = inv_normal_cdf_tail(qp[lane]);
+        };
+        const bool block = HAS_BLOCK && Dg > 32;
+        const bool staged = block && can_stage && (long long)Dg * Dg <= (long long)R * (1 + NU);
+        if (!staged) fill_gauss(0, Rg, nh + (size_t)cbase * LD + roff, LD);
         for (int e = lane; e < Rg * (LD - Dg); e += 32) {  // zeros: rows 0..roff-1 and D..LD-1 of every column
             const int col = e / (LD - Dg), z = e - col * (LD - Dg);
             nh[(cbase + col) * LD + (z < roff ? z : D + z - roff)] = 0.0;
@@ -336,6 +475,30 @@ __device__ inline void prep_chain(int D, int R, int LD, unsigned seed, unsigned 
         // (b) Gram-Schmidt, B bases at a time on LB = 32/B lanes each.  Classical form: all projections of
         //     vector i on q_0..q_{i-1} are taken from the raw vector, then subtracted together.
         const int nb = (Rg + Dg - 1) / Dg;
+        if constexpr (HAS_BLOCK) {
+            if (block) {   // one basis at a time on the whole warp
+                for (int basis = 0; basis < nb; ++basis) {
+                    const int m = min(Dg, Rg - basis * Dg);
+                    double* qcols = nh + (size_t)(cbase + basis * Dg) * LD + roff;   // where the basis belongs
+                    if (staged) {
+                        double* sq = cs.wts;   // [wts | uni): R * (1 + NU) doubles
+                        fill_gauss(basis * Dg, m, sq, Dg);
+                        __syncwarp();
+                        gram_schmidt_block<BLOCK_MT>(sq, Dg, Dg, m, cs.dots);
+                        for (int e = lane; e < m * Dg; e += 32) {
+                            const int c = e / Dg, r = e - c * Dg;
+                            qcols[(size_t)c * LD + r] = sq[e];
+                        }
+                        __syncwarp();
+                    } else {
+                        gram_schmidt_block<BLOCK_MT>(qcols, LD, Dg, m, cs.dots);
+                    }
+                }
+                cbase += Rg;
+                roff += ngrade > 1 ? gp->gdims[g] : D;
+                continue;
+            }
+        }
         const int B = nb >= 4 ? 4 : (nb >= 2 ? 2 : 1);
         const int lbs = B >= 4 ? 3 : (B >= 2 ? 4 : 5), LB = 1 << lbs;   // lanes per basis (a power of two: no integer division)
         const int sl = lane & (LB - 1), bslot = lane >> lbs;
@@ -396,6 +559,7 @@ __device__ inline void prep_chain(int D, int R, int LD, unsigned seed, unsigned 
         cbase += Rg;
         roff += ngrade > 1 ? gp->gdims[g] : D;
     }
+    if (cs.uni && can_stage) draw_uniforms();   // (the staging area is free again)
     // (c) the shuffled deck.  The swaps run i = R-1 .. 1 (swap deck[i], deck[jd[i]]); the element that ends
     //     at position p is found by walking the swaps backwards from p.
     for (int p = lane; p < R; p += 32) {

@@ -31,6 +31,22 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// Per-dimension constants of the prior and the likelihood for the slice loop, one CTA-wide table in shared memory:
+// [lo | wid | mu | isig], GD entries each, zero beyond D (Model::init's padding rule).  The loop needs them once per
+// slice (chord form) and once per baby (theta); held in registers they pushed the loop over the 128 registers of two
+// CTAs per SM, and the spills went to local memory behind an L1 that the shared-memory carve-out leaves almost empty
+// (profiles/r02a: 10 % of the ensemble's warp samples sat on the reload in front of the baby's store).
+template <int GD>
+__device__ inline void dense_table_fill(double* tab, int D, int like_kind, const double* s_like, const double* prior_params) {
+    for (int e = threadIdx.x; e < GD; e += blockDim.x) {
+        const bool v = e < D;
+        tab[e] = v ? prior_params[e] : 0.0;
+        tab[GD + e] = v ? prior_params[D + e] : 0.0;
+        tab[2 * GD + e] = (v && like_kind != LIKE_RASTRIGIN) ? s_like[e] : 0.0;
+        tab[3 * GD + e] = (v && like_kind == LIKE_GAUSSIAN) ? s_like[D + e] : 0.0;
+    }
+}
+
 // The prepared chain in cs (whitened unit directions, widths, deck) -> its global block, in slice order; the slice
 // uniforms are drawn straight into the records (prep_chain was called with cs.uni == nullptr).  One warp.
 template <int GD>
@@ -60,7 +76,7 @@ template <int G, int DPL, int KIND>
 __device__ inline void slice_chains_dense(const ChainParams& p, const Model<G, DPL, KIND>& M, unsigned seed,
                                           unsigned long long uid, bool active, double (&x)[DPL], double Lstar,
                                           const double* gblock, double* stage, double* ph_base, double* last_dst,
-                                          unsigned long long& nlike, double& lfin) {
+                                          unsigned long long& nlike, double& lfin, const double* tab) {
     static_assert(KIND != LIKE_CORR, "the dense chain phase has no correlated-Gaussian form (one matrix-vector product per slice and group)");
     constexpr int GD = G * DPL, SLB = dense_slb(GD);
     constexpr int LOG2G = (G == 1) ? 0 : (G == 2) ? 1 : (G == 4) ? 2 : (G == 8) ? 3 : (G == 16) ? 4 : 5;
@@ -68,9 +84,7 @@ __device__ inline void slice_chains_dense(const ChainParams& p, const Model<G, D
     const int lane = threadIdx.x & 31, grp = lane >> LOG2G, sub = lane & (G - 1);
     const unsigned gmask = Model<G, DPL, KIND>::GMASK << (grp << LOG2G);
     const double logzero = p.logzero;
-    double wdt[DPL], shf[DPL];
-#pragma unroll
-    for (int k = 0; k < DPL; ++k) { wdt[k] = M.wid[k]; shf[k] = M.lo[k] - M.mu[k]; }
+    const double* t_lo = tab + sub;   // this lane's entries: lo at [k*G], wid at [GD + k*G], mu at [2GD + k*G], 1/sigma at [3GD + k*G]
 
     int slice = 0, phase = active ? SP_R0 : SP_DONE, istep = 0, s_done = 0;
     double w = 0.0, dL = 0.0, dR = 0.0, a = 0.0, b = 0.0, wd = 0.0, t = 0.0, lR = 0.0, lL = 0.0;
@@ -95,14 +109,16 @@ __device__ inline void slice_chains_dense(const ChainParams& p, const Model<G, D
         if constexpr (KIND == LIKE_GAUSSIAN) {
 #pragma unroll
             for (int k = 0; k < DPL; ++k) {  // z = (theta - mu)/sigma = t*nW + xs
-                nW[k] = nh[k] * wdt[k] * M.isig[k];
-                xs[k] = fma(x[k], wdt[k], shf[k]) * M.isig[k];
+                const double wk = t_lo[GD + k * G], ik = t_lo[3 * GD + k * G];
+                nW[k] = nh[k] * wk * ik;
+                xs[k] = fma(x[k], wk, t_lo[k * G] - t_lo[2 * GD + k * G]) * ik;
             }
         } else {
 #pragma unroll
             for (int k = 0; k < DPL; ++k) {  // theta - mu = t*nW + xs
-                nW[k] = nh[k] * wdt[k];
-                xs[k] = fma(x[k], wdt[k], shf[k]);
+                const double wk = t_lo[GD + k * G];
+                nW[k] = nh[k] * wk;
+                xs[k] = fma(x[k], wk, t_lo[k * G] - t_lo[2 * GD + k * G]);
             }
         }
         phase = SP_R0;
@@ -209,7 +225,7 @@ __device__ inline void slice_chains_dense(const ChainParams& p, const Model<G, D
                 for (int k = 0; k < DPL; ++k)
                     if (M.valid(k)) {
                         dst[M.dim(k)] = y[k];
-                        dst[D + M.dim(k)] = incube ? fma(wdt[k], y[k], M.lo[k]) : 0.0;
+                        dst[D + M.dim(k)] = incube ? fma(t_lo[GD + k * G], y[k], t_lo[k * G]) : 0.0;
                     }
                 if (sub == 0) {
                     dst[2 * D + p.P] = Lstar;

@@ -1043,6 +1043,12 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                                           (MODE == 0 && rb.nh) ? rb.nh + (size_t)gw * R * LD : nullptr, SLB);
     Model<G, DPL, KIND> M;
     M.init(p.cp, s_like, p.prior_params, cs.dvec);
+    __shared__ double s_tab[MODE == 1 ? 4 * G * DPL : 1];   // dense chain phase: per-dimension constants (pc_dense.cuh)
+    if constexpr (MODE == 1) {
+        __syncthreads();
+        dense_table_fill<G * DPL>(s_tab, D, p.cp.like_kind, s_like, p.prior_params);
+        __syncthreads();
+    }
 
     if (!vload(&st->initialised)) init_phase<G, DPL, KIND>(p, rb, st, M, cta, NG, sc);
 
@@ -1258,7 +1264,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                     slice_chains_dense<G, DPL, KIND>(p.cp, M, rb.seed, uid, active, x, Lstar, gblocks + (size_t)grp * R * SLB,
                                                      cs.stage + (size_t)grp * 2 * SLB,
                                                      pool + (size_t)(nph_base + (long long)kc * (R - 1)) * T,
-                                                     rb.live + (size_t)dslot * T, nlike, lfin);
+                                                     rb.live + (size_t)dslot * T, nlike, lfin, s_tab);
                     if (p.clustering && active) {  // the babies carry their seed's label until the next update
                         for (int e = sub; e < R - 1; e += G) rb.phl[cur_pool_now][nph_base + (long long)k * (R - 1) + e] = plab;
                         if (sub == 0) rb.lab[dslot] = plab;
@@ -1533,6 +1539,9 @@ __global__ void __launch_bounds__(256, 2) pc_slice_chains_dense_kernel(const __g
         const ChainScratch cs = chain_scratch(s_warp, D, R, LD, true, p.cp.like_kind, NPT, nullptr, SLB);
         Model<G, DPL, KIND> M;
         M.init(p.cp, s_like, p.prior_params, cs.dvec);
+        __shared__ double s_tab[4 * G * DPL];
+        dense_table_fill<GD>(s_tab, D, p.cp.like_kind, s_like, p.prior_params);
+        __syncthreads();
         for (int base = gw * NPT; base < nchains; base += gridDim.x * W * NPT) {
             for (int g = 0; g < NPT && base + g < nchains; ++g) {
                 prep_chain<GD>(D, R, LD, seed, uid[base + g], cs, &p.cp);
@@ -1549,7 +1558,7 @@ __global__ void __launch_bounds__(256, 2) pc_slice_chains_dense_kernel(const __g
             double lfin = 0.0;
             double* out = babies + (size_t)cc * R * T;
             slice_chains_dense<G, DPL, KIND>(p.cp, M, seed, uid[cc], active, x, logL[cc], records + (size_t)cc * R * SLB,
-                                             cs.stage + (size_t)grp * 2 * SLB, out, out + (size_t)(R - 1) * T, nl, lfin);
+                                             cs.stage + (size_t)grp * 2 * SLB, out, out + (size_t)(R - 1) * T, nl, lfin, s_tab);
             if (active) {   // the chain probe returns every baby's derived parameters, as SliceSampling does
                 if (p.cp.P > 0)
                     for (int i = sub; i < R - 1; i += G) M.finish_derived(out + (size_t)i * T, false);
