@@ -203,6 +203,7 @@ struct Options {
     int nh_global = 0;  // force the direction scratch into global memory (testing)
     int no_pairing = 0; // keep the helper-warp preparation off (testing)
     int no_phase_d = 0; // order the live points on CTA 0 only (testing: phase D off)
+    int no_bulk = 0;    // phase U streams its records through registers (testing: the bulk-copy ring off)
     int resume_text = 0; // write_resume writes the reference's text layout (read_write.F90:219-288) instead of the engine's binary one
     int sync_dump = 0;  // the kernel exits at every update for the dumper instead of handing dumps over while running
     long long cap_dead0 = 0, cap_ph0 = 0;  // initial pool capacities in records (0 = automatic)
@@ -417,6 +418,9 @@ static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const Dev
     k.nh_in_smem = in_smem ? 1 : 0;
     size_t wb = std::max(chain_scratch_bytes(D, R, k.cp.LD, in_smem, ms.like_kind, npt, slb), cov_bytes);
     wb = (wb + 15) & ~(size_t)15;
+    // phase U's record stream (bulk copies into a per-warp ring of 2 * U_BATCH records behind the staged rows): taken when
+    // the ring fits into the per-warp area as it is
+    k.u_bulk = (!g_opt.no_bulk && (size_t)(Dpad + U_BATCH * (Dp8 + 4) + 2 * U_BATCH * k.cp.T) * 8 <= wb) ? 1 : 0;
     k.warp_bytes = (int)wb;
     L.smem = off + std::max((size_t)W * wb, sort_bytes);
     // phase D (pc_run_kernel.cuh): every CTA stages the nmax live keys behind its per-warp areas; when they do not fit,
@@ -1869,6 +1873,7 @@ int pc_set_option(const char* name, double value) {
     else if (s == "nh_global") g_opt.nh_global = (int)value;
     else if (s == "no_pairing") g_opt.no_pairing = (int)value;
     else if (s == "no_phase_d") g_opt.no_phase_d = (int)value;
+    else if (s == "no_bulk") g_opt.no_bulk = (int)value;
     else if (s == "resume_text") g_opt.resume_text = (int)value;
     else if (s == "sync_dump") g_opt.sync_dump = (int)value;
     else if (s == "cap_dead0") g_opt.cap_dead0 = (long long)value;
@@ -1889,6 +1894,7 @@ double pc_get_option(const char* name) {
     if (s == "nh_global") return g_opt.nh_global;
     if (s == "no_pairing") return g_opt.no_pairing;
     if (s == "no_phase_d") return g_opt.no_phase_d;
+    if (s == "no_bulk") return g_opt.no_bulk;
     if (s == "resume_text") return g_opt.resume_text;
     if (s == "sync_dump") return g_opt.sync_dump;
     if (s == "cap_dead0") return (double)g_opt.cap_dead0;

@@ -186,6 +186,7 @@ struct KParams {
     int ntri, cov_passes, partial_stride;
     int off_like, off_warp, warp_bytes;  // shared-memory byte offsets
     int off_dkeys;               // phase D's key area behind the per-warp areas (nmax + 2 * warps + 2 doubles); 0: phase S orders the live points on CTA 0
+    int u_bulk;                  // phase U: the per-warp areas hold the staging ring of the bulk-copy record stream (2 * U_BATCH records behind the staged rows)
     double log_prec, log_comp;
     double boost_thin;           // RTI%thin_posterior (generate.F90:311-316) when posterior files are written, else 0
     const double* like_params;   // gaussian: mu[D], 1/sigma[D]; corr: mu[D], invcov[D*D]
@@ -629,5 +630,41 @@ __device__ inline int block_cholesky(double* a, double* L, int D) {
     }
     return fallback;
 }
+
+
+// ---------------------------------------------------------------- bulk copies (TMA, 1-D) and their mbarriers
+// Phase U streams whole records global -> shared -> global.  A record is contiguous, so it moves as ONE bulk copy
+// (cp.async.bulk, the non-tensor form of the TMA engine; SASS UBLKCP): no registers hold data in flight, a warp keeps
+// two batches of records on the way, and completion is counted in bytes on an mbarrier.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    while (!mbar_test(bar, parity)) {}
+}
+// global -> shared, completion as bytes on `bar`; 16-byte aligned addresses, size a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global (bulk group of the issuing thread)
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 }  // namespace pc

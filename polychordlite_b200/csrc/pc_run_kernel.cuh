@@ -635,8 +635,13 @@ __device__ inline void phase_UA(const KParams& p, const RunBuf& rb, DevRun* st, 
 // D x D block, S1 in column D and the record count at (D, D).  A warp stages U_BATCH = 8 records (two k-steps of
 // the m8n8k4 FP64 tensor-core MMA) in shared memory and multiplies the 8x8 tiles of the upper triangle of M,
 // COV_TPP tiles per pass over the data (one pass up to D = 31).
+// Record stream.  With an even record length (16-byte aligned records) a kept record moves global -> shared as one
+// bulk copy (TMA, cp.async.bulk) into the warp's staging ring -- two batches of U_BATCH records, the next batch on its
+// way while this one is multiplied -- and, in pass 0, from there to its place in the other pool as one bulk store; the
+// data never sits in registers, and the warp's mbarriers (mbar: two per warp, parity bits in `mpar`) count the bytes.
+// Odd record lengths (an odd number of derived parameters) take the register path.
 __device__ inline void phase_UB(const KParams& p, const RunBuf& rb, DevRun* st, int cta, int NG, unsigned char* smem_warp0,
-                                int warp_bytes, int* s_cnt, long long* tim) {
+                                int warp_bytes, int* s_cnt, long long* tim, unsigned long long* mbar, unsigned& mpar) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
     const int D = p.cp.D, T = p.cp.T, n = vload(&st->n);
     const int Dpad = (D + 1) & ~1;
@@ -677,6 +682,7 @@ __device__ inline void phase_UB(const KParams& p, const RunBuf& rb, DevRun* st, 
     const long long base = s_base[0];
     if (cta == 0 && tid == 0) st->ph_kept = s_base[1];
     const int JT = (T + 31) >> 5, JD = (D + 31) >> 5;  // 32-wide column chunks of a record / of its cube coordinates
+    const bool bulk = (T & 1) == 0 && p.u_bulk != 0;   // 16-byte aligned records and room for the staging ring
     const int fr = lane >> 2, fk = lane & 3;           // fragment row (dimension within a tile) and k index (record within a k-step)
     double* outp = rb.partial + (size_t)cta * p.partial_stride;
     for (int pass = 0; pass < p.cov_passes; ++pass) {
@@ -717,74 +723,147 @@ __device__ inline void phase_UB(const KParams& p, const RunBuf& rb, DevRun* st, 
         unsigned mk_n = 0;
         long long cr_n = 0;
         if (my_tiles > 0) fetch(cta, mk_n, cr_n);
-        for (long long it = 0; it < my_items; ++it) {
-            const bool is_ph = it < my_tiles;
-            const long long t = cta + it * NG;
-            const double* __restrict__ rbase;   // record 0 of this warp's segment
-            unsigned bal;
-            int woff = 0;
-            long long tnext = 0;
-            const bool copy = is_ph && pass == 0;
-            if (is_ph) {
-                const unsigned mk = mk_n;
-                long long cr = cr_n;
-                if (it + 1 < my_tiles) fetch(t + NG, mk_n, cr_n);   // in flight while this tile is worked on
-                bal = __shfl_sync(FULL, mk, warp);
-                woff = __reduce_add_sync(FULL, lane < warp ? __popc(mk) : 0);
-                if (copy) {
+        // The batches of this warp, in order: an item's kept records (the mask pass A left, or the live pseudo-tile's
+        // extent) in groups of U_BATCH.  next_batch() walks items and masks; a batch is (first record of the segment,
+        // mask of its records, count, copy?, place in the other pool).
+        struct UBatch { const double* rbase; unsigned bm; int nb; bool copy; long long place; };
+        long long it = 0, tnext = 0;
+        unsigned rem = 0;
+        int kk = 0, woff = 0;
+        bool it_copy = false, it_open = false;
+        const double* it_rbase = src;
+        auto next_batch = [&](UBatch& b) -> bool {
+            while (rem == 0) {
+                if (it_open && it_copy) tbase = tnext;   // offset of this CTA's next phantom tile
+                it_open = false;
+                if (it >= my_items) return false;
+                const bool is_ph = it < my_tiles;
+                const long long t = cta + it * NG;
+                it_copy = is_ph && pass == 0;
+                woff = 0;
+                if (is_ph) {
+                    const unsigned mk = mk_n;
+                    long long cr = cr_n;
+                    if (it + 1 < my_tiles) fetch(t + NG, mk_n, cr_n);   // in flight while this tile is worked on
+                    rem = __shfl_sync(FULL, mk, warp);
+                    woff = __reduce_add_sync(FULL, lane < warp ? __popc(mk) : 0);
+                    if (it_copy) {
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) cr += __shfl_xor_sync(FULL, cr, o);
-                    tnext = tbase + cr;
+                        for (int o = 16; o > 0; o >>= 1) cr += __shfl_xor_sync(FULL, cr, o);
+                        tnext = tbase + cr;
+                    }
+                    it_rbase = src + (size_t)(t * UT + warp * 32) * T;
+                } else {
+                    const int lrec = l0 + (int)(it - my_tiles) * UT + tid;
+                    rem = __ballot_sync(FULL, lrec < l1);
+                    it_rbase = rb.live + (size_t)(l0 + (int)(it - my_tiles) * UT + warp * 32) * T;
                 }
-                rbase = src + (size_t)(t * UT + warp * 32) * T;
-            } else {
-                const int lrec = l0 + (int)(it - my_tiles) * UT + tid;
-                bal = __ballot_sync(FULL, lrec < l1);
-                rbase = rb.live + (size_t)(l0 + (int)(it - my_tiles) * UT + warp * 32) * T;
+                kk = 0;
+                it_open = true;
+                ++it;
             }
-            const int jmax = copy ? JT : JD;
-            unsigned rem = bal;
-            int kk = 0;
-            while (rem) {
+            unsigned bm = 0;
+            int nb = 0;
+#pragma unroll
+            for (int b2 = 0; b2 < U_BATCH; ++b2)
+                if (rem) { bm |= rem & (0u - rem); rem &= rem - 1; ++nb; }
+            b.rbase = it_rbase; b.bm = bm; b.nb = nb; b.copy = it_copy; b.place = tbase + woff + kk;
+            kk += nb;
+            return true;
+        };
+        // the DMMAs of a staged batch
+        auto multiply = [&]() {
+#pragma unroll
+            for (int ks = 0; ks < U_BATCH / 4; ++ks) {
+                const double* row = s_x + (4 * ks + fk) * SX + fr;
+#pragma unroll
+                for (int q = 0; q < COV_TPP; ++q)
+                    if (tl[q] >= 0) dmma884(c0[q], c1[q], row[(tl[q] >> 8) << 3], row[(tl[q] & 0xff) << 3]);
+            }
+        };
+        auto move_labels = [&](const UBatch& b) {   // the phantom's cluster label moves with it
+            if (b.copy && p.clustering && lane < b.nb) {
+                const int bit = __fns(b.bm, 0, lane + 1);
+                rb.phl[pool ^ 1][b.place + lane] = __ldcg(rb.phl[pool] + ((b.rbase - src) / T + bit));
+            }
+        };
+        if (bulk) {
+            double* s_stage = s_x + U_BATCH * SX;   // 2 x U_BATCH x T doubles behind the staged rows
+            unsigned long long* bar = mbar + 2 * warp;
+            fence_proxy_async();   // the area was last written through the generic proxy (moment matrix of the pass before)
+            auto issue = [&](const UBatch& b, int buf) {
+                const unsigned bytes = (unsigned)((((b.copy ? T : D) + 1) & ~1) * 8);
+                bulk_wait_read0();   // this lane's store out of the slot it is about to refill (issued a batch ago) has read it
+                if (lane == 0) mbar_expect_tx(bar + buf, bytes * (unsigned)b.nb);
+                __syncwarp();
+                if (lane < b.nb) {
+                    const int bit = __fns(b.bm, 0, lane + 1);
+                    bulk_g2s(s_stage + ((size_t)buf * U_BATCH + lane) * T, b.rbase + (size_t)bit * T, bytes, bar + buf);
+                }
+            };
+            UBatch cur, nxt;
+            bool have = next_batch(cur);
+            int buf = 0;
+            if (have) issue(cur, 0);
+            while (have) {
+                const bool have_n = next_batch(nxt);
+                if (have_n) issue(nxt, buf ^ 1);
+                mbar_wait(bar + buf, (mpar >> buf) & 1u);
+                mpar ^= 1u << buf;
+                const double* sb = s_stage + (size_t)buf * U_BATCH * T;
+                if (cur.copy) {   // stable compaction: the record goes to its place in the other pool as it lies in the ring
+                    if (lane < cur.nb) bulk_s2g(dst + (size_t)(cur.place + lane) * T, sb + (size_t)lane * T, (unsigned)(T * 8));
+                    bulk_commit();
+                    move_labels(cur);
+                }
+                for (int j = 0; j < JD; ++j) {
+                    const int e = lane + 32 * j;
+                    const double pv = e < D ? s_piv[e] : 0.0;
+#pragma unroll
+                    for (int b2 = 0; b2 < U_BATCH; ++b2)   // rows beyond the batch are zero; column D carries the 1 of the augmented row
+                        if (e <= D) s_x[b2 * SX + e] = b2 < cur.nb ? (e < D ? sb[b2 * T + e] - pv : 1.0) : 0.0;
+                }
+                if ((D & 31) == 0 && lane < U_BATCH) s_x[lane * SX + D] = lane < cur.nb ? 1.0 : 0.0;
+                __syncwarp();
+                multiply();
+                __syncwarp();
+                cur = nxt;
+                have = have_n;
+                buf ^= 1;
+            }
+            bulk_wait0();          // this lane's stores are complete ...
+            fence_proxy_async();   // ... and ordered before what follows in the generic proxy (the barrier's release)
+        } else {
+            UBatch b;
+            while (next_batch(b)) {
                 const double* rp[U_BATCH];
-                int nb = 0;
+                unsigned m2 = b.bm;
 #pragma unroll
                 for (int b2 = 0; b2 < U_BATCH; ++b2) {
-                    rp[b2] = rbase;
-                    if (rem) { const int bit = __ffs(rem) - 1; rem &= rem - 1; rp[b2] = rbase + (size_t)bit * T; ++nb; }
+                    rp[b2] = b.rbase;
+                    if (m2) { rp[b2] = b.rbase + (size_t)(__ffs(m2) - 1) * T; m2 &= m2 - 1; }
                 }
-                double* out = dst + (size_t)(tbase + woff + kk) * T;
-                if (copy && p.clustering) {  // the phantom's cluster label moves with it
-#pragma unroll
-                    for (int b2 = 0; b2 < U_BATCH; ++b2)
-                        if (lane == b2 && b2 < nb) rb.phl[pool ^ 1][tbase + woff + kk + b2] = __ldcg(rb.phl[pool] + (rp[b2] - src) / T);
-                }
+                double* out = dst + (size_t)b.place * T;
+                move_labels(b);
                 __syncwarp();
+                const int jmax = b.copy ? JT : JD;
                 for (int j = 0; j < jmax; ++j) {
                     const int e = lane + 32 * j;
                     double v[U_BATCH];
 #pragma unroll
-                    for (int b2 = 0; b2 < U_BATCH; ++b2) v[b2] = (b2 < nb && e < T) ? __ldcg(rp[b2] + e) : 0.0;
+                    for (int b2 = 0; b2 < U_BATCH; ++b2) v[b2] = (b2 < b.nb && e < T) ? __ldcg(rp[b2] + e) : 0.0;
                     const double pv = e < D ? s_piv[e] : 0.0;
 #pragma unroll
                     for (int b2 = 0; b2 < U_BATCH; ++b2) {
-                        if (copy && b2 < nb && e < T) out[(size_t)b2 * T + e] = v[b2];
+                        if (b.copy && b2 < b.nb && e < T) out[(size_t)b2 * T + e] = v[b2];
                         // rows beyond the batch are zero; column D carries the 1 of the augmented row
-                        if (e <= D) s_x[b2 * SX + e] = b2 < nb ? (e < D ? v[b2] - pv : 1.0) : 0.0;
+                        if (e <= D) s_x[b2 * SX + e] = b2 < b.nb ? (e < D ? v[b2] - pv : 1.0) : 0.0;
                     }
                 }
-                if ((D & 31) == 0 && lane < U_BATCH) s_x[lane * SX + D] = lane < nb ? 1.0 : 0.0;  // column D starts a chunk the loop above did not reach
+                if ((D & 31) == 0 && lane < U_BATCH) s_x[lane * SX + D] = lane < b.nb ? 1.0 : 0.0;  // column D starts a chunk the loop above did not reach
                 __syncwarp();
-#pragma unroll
-                for (int ks = 0; ks < U_BATCH / 4; ++ks) {
-                    const double* row = s_x + (4 * ks + fk) * SX + fr;
-#pragma unroll
-                    for (int q = 0; q < COV_TPP; ++q)
-                        if (tl[q] >= 0) dmma884(c0[q], c1[q], row[(tl[q] >> 8) << 3], row[(tl[q] & 0xff) << 3]);
-                }
-                kk += nb;
+                multiply();
             }
-            if (copy) tbase = tnext;   // offset of this CTA's next phantom tile
         }
         const long long z3 = clock64();
         if (tmr) tim[13] += z3 - z1;
@@ -1030,6 +1109,11 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
     // cyc_white, cyc_slice, cyc_total.  Single writer per counter and CTA.
     __shared__ long long tim[32];
     if (tid < 32) tim[tid] = 0;
+    // phase U's record stream: two mbarriers per warp (one per batch of the staging ring), their parities on the warp
+    __shared__ __align__(8) unsigned long long s_mbar[16];
+    unsigned mbar_parity = 0;
+    if (tid < 16) mbar_init(&s_mbar[tid], 1);
+    mbar_fence_init();
     __syncthreads();
     auto flush_timers = [&]() {
         __syncthreads();
@@ -1072,7 +1156,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
         if (vload(&st->do_update)) {
             phase_UA(p, rb, st, cta, NG);
             group_sync(&st->bar, NG, p.backoff);
-            phase_UB(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt, tim);
+            phase_UB(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt, tim, s_mbar, mbar_parity);
             if (cta == 0 && tid == 0) st->update_pending = 1;
         }
         group_sync(&st->bar, NG, p.backoff);
@@ -1456,7 +1540,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
             long long ua1 = clock64();
             group_sync(&st->bar, NG, p.backoff);
             long long ua2 = clock64();
-            phase_UB(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt, tim);
+            phase_UB(p, rb, st, cta, NG, s_warp0, p.warp_bytes, s_cnt, tim, s_mbar, mbar_parity);
             long long ua3 = clock64();
             if (timer) { tim[2] += ua1 - ua0; tim[3] += ua2 - ua1; tim[4] += ua3 - ua2; tim[5] -= ua3; }
             if (cta == 0 && tid == 0) st->update_pending = 1;
