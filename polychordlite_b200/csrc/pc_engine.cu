@@ -1671,7 +1671,7 @@ struct Engine {
             std::memset(c, 0, sizeof(*c));
             ctl = c;
             HostRun& h = runs[0];
-            h.live_snap.alloc((size_t)L.kp.nmax * L.kp.cp.T);
+            h.live_snap.alloc((size_t)2 * L.kp.nmax * L.kp.cp.T);   // two halves, by dump parity
             h.buf.live_snap = h.live_snap.p;
             HostCtl* dctl = nullptr;
             PC_CUDA(cudaHostGetDevicePointer((void**)&dctl, c, 0));
@@ -1686,7 +1686,7 @@ struct Engine {
             auto ts = now();
             const long long nd = ctl->ndead;
             const double lz = ctl->logZ, lz2 = ctl->logZ2;
-            dump(0, dumper, nd, lz, lz2, runs[0].live_snap.p, ctl->nlive, g_copy_stream, ctl->nlike);
+            dump(0, dumper, nd, lz, lz2, runs[0].live_snap.p + (size_t)((handled + 1) & 1) * L.kp.nmax * L.kp.cp.T, ctl->nlive, g_copy_stream, ctl->nlike);
             ++handled;
             ctl->ack_seq = handled;
             dbg_service_ms += ms_since(ts);

@@ -62,7 +62,7 @@ struct DevRun {
     int order_valid;     // rb.order + order_off holds the live slots sorted by (logL, slot) as of the last phase S
     int order_off;       // 0 or n: which half of rb.order is current
     int ncl;             // clusters found at the last update (1: the global factor is used)
-    int pad1;
+    int dump_pub;        // asynchronous dumper hand-over: dumps published so far (the snapshot of dump s lies in half s & 1 of live_snap)
     int host_resume;     // host-callback runs: the chains of the generation in flight were run by the host loop
     int n;               // live points now (dynamic nlive, nprior, failed births: it moves; KParams::n is the target)
     // the generation in flight: n_gen live points at its start, K of them die, B chains are born
@@ -87,7 +87,7 @@ struct DevRun {
     unsigned int bar;    // group barrier, one arrival per CTA (monotonic)
     unsigned int wbar;   // chains-done barrier, one arrival per warp (monotonic)
     unsigned int dbar;   // phase D done, one arrival per ranking CTA (monotonic); only CTA 0 waits for it
-    unsigned int pad2;
+    unsigned int snap_arr; // ... CTAs that have written their share of the next dump's live snapshot (monotonic)
     // boost_posterior (clean_phantoms, run_time_info.f90:820-877): phantoms promoted to posterior samples so far
     // (rb.boost rows), and ndead at the last update -- the deaths after it are the posterior stack a removed
     // phantom takes its weight from
@@ -111,7 +111,7 @@ struct HostCtl {
 struct RunBuf {
     DevRun* st;
     double* live;      // n x T records
-    double* live_snap; // n x T: copy of the live points at the last published dump
+    double* live_snap; // 2 x nmax x T: the live points at the published dumps, by dump parity (every CTA writes its share)
     HostCtl* ctl;      // mapped host memory, or null (no dumper)
     int* order;        // 2 x n: live slots sorted by (logL, slot), ping-pong (DevRun::order_off)
     double* okey;      // 2 x n: the logL of those slots, same order and ping-pong

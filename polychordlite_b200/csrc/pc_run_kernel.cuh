@@ -1040,7 +1040,22 @@ __device__ inline void shard_scatter(const KParams& p, const RunBuf& rb, DevRun*
 // dump (nested_sampling.F90:546-590) is called at every update (:335).  The kernel does not stop for it: it
 // waits until the host has consumed the previous dump, snapshots the live points, publishes the state through
 // the mapped control block and goes on.  Returns true when the host asked to abort.
-__device__ inline bool publish_dump(const KParams& p, const RunBuf& rb, DevRun* st) {
+// The live snapshot of the next dump: every CTA of the run copies its share after the update's last barrier, while CTA 0
+// finishes the covariance -- the copy (n x T doubles) used to sit on CTA 0 alone, on the critical path of every update.
+// Two halves by dump parity: the half being written belongs to the dump before the last, which the host has acknowledged
+// (publish_dump waits for the acknowledgement of dump s-1 before it publishes dump s).
+__device__ inline void snapshot_share(const KParams& p, const RunBuf& rb, DevRun* st, int cta, int NG) {
+    const size_t nd = (size_t)vload(&st->n) * p.cp.T;
+    double* snap = rb.live_snap + (size_t)((vload(&st->dump_pub) + 1) & 1) * p.nmax * p.cp.T;
+    const size_t chunk = (nd + NG - 1) / NG, e0 = min(nd, (size_t)cta * chunk), e1 = min(nd, e0 + chunk);
+    for (size_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) snap[e] = __ldcg(rb.live + e);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        atomicAdd(&st->snap_arr, 1u);
+    }
+}
+__device__ inline bool publish_dump(const KParams& p, const RunBuf& rb, DevRun* st, int NG) {
     __shared__ int s_abort;
     volatile HostCtl* ctl = rb.ctl;
     if (threadIdx.x == 0) {
@@ -1051,10 +1066,11 @@ __device__ inline bool publish_dump(const KParams& p, const RunBuf& rb, DevRun* 
     }
     __syncthreads();
     if (s_abort) return true;
-    const size_t nd = (size_t)st->n * p.cp.T;
-    for (size_t e = threadIdx.x; e < nd; e += blockDim.x) rb.live_snap[e] = __ldcg(rb.live + e);
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {   // every CTA of the run has written its share of the snapshot (snapshot_share)
+        const unsigned want = (unsigned)(st->dump_pub + 1) * (unsigned)NG;
+        unsigned v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&st->snap_arr) : "memory"); } while ((int)(v - want) < 0);
+        st->dump_pub = st->dump_pub + 1;
         ctl->ndead = st->ndead;
         ctl->nlive = st->n;
         ctl->nlike = st->nlike;
@@ -1181,7 +1197,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
                 if (!finish_update(p, rb, st, NG, smS.akey, s_chol, tim) && tid == 0) st->status = ST_ERROR;
                 __syncthreads();
                 if (p.clustering) cluster_exit = true;             // leave: the host runs the clustering pass (pc_cluster.cuh), dumps, relaunches
-                else if (rb.ctl) dump_exit = publish_dump(p, rb, st);   // the kernel keeps running
+                else if (rb.ctl) dump_exit = publish_dump(p, rb, st, NG);   // the kernel keeps running
                 else if (p.want_dump) dump_exit = true;              // "sync_dump": leave, the host dumps and relaunches
             }
             if (timer) tim[26] += clock64() - t1;
@@ -1546,6 +1562,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) pc_run_kernel(const __
             if (cta == 0 && tid == 0) st->update_pending = 1;
             group_sync(&st->bar, NG, p.backoff);
             if (timer) { tim[27] += clock64() - tu1; tim[5] += clock64(); }
+            if (rb.ctl && !p.clustering) snapshot_share(p, rb, st, cta, NG);   // (the same condition as publish_dump's)
         }
         // Phase D: a regular generation (as many births as deaths, none failed -- the failure count is where phase S1
         // published it) leaves the survivors in order: every chain CTA ranks its share of the live points.  The

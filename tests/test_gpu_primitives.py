@@ -37,7 +37,7 @@ def test_inv_normal_cdf(gpu, oracle):
     assert np.allclose(got, want, rtol=1e-14, atol=1e-15)
 
 
-@pytest.mark.parametrize("D,R", [(4, 20), (20, 40), (10, 50), (50, 250), (33, 40), (7, 3), (1, 5)])
+@pytest.mark.parametrize("D,R", [(4, 20), (20, 40), (10, 50), (50, 250), (33, 40), (7, 3), (1, 5), (64, 70), (100, 120), (128, 130)])
 def test_directions_match_oracle(gpu, oracle, D, R):
     """chordal_sampling.f90:94-145.  The engine projects with lane-parallel classical Gram-Schmidt,
     the oracle (like random_utils.F90:393-396) with the modified form: same basis up to
