@@ -363,8 +363,12 @@ def main():
     if sharded:
         from polychordlite_b200 import mgpu
         alone = None
-        if rank == 0:
-            alone, _ = capi.run(settings(424242), like=w["like"], **box)
+        if rank == 0:   # (the same batch size as the sharded run: the automatic one follows the number of devices)
+            capi.set_option("batch_K", capi.auto_batch_size(n, world))
+            try:
+                alone, _ = capi.run(settings(424242), like=w["like"], **box)
+            finally:
+                capi.set_option("batch_K", 0)
         dist.barrier()
         mgpu.attach(settings(0))
         both, _ = capi.run(settings(424242), like=w["like"], **box)
@@ -587,7 +591,7 @@ def main():
                                      "independent replica runs per rank (no data-path collective)" if not sharded else
                                      f"ONE run, nlive={n} sharded over {world} GPUs: chains dealt k % world, last babies and "
                                      "covariance statistics exchanged over NVLink peer memory inside the persistent kernel")},
-            "schedule": {"batch_K": K, "rule": "engine default: K = nlive/2 for a run alone on the device, nlive/4 inside an ensemble",
+            "schedule": {"batch_K": K, "rule": "engine default: about nlive/2 for a run alone on the device -- a whole number of waves of chains ((SMs-1)*4 per device) where that stays within [0.5, 0.6] nlive, else nlive/2 -- and nlive/4 inside an ensemble",
                          "logX_variance_per_unit_compression_vs_one_death_at_a_time": var_ratio,
                          "note": "the reported logZerr carries this factor (the evidence recurrences are applied death by death)"},
             "wall_time_to_logZ_s": dev_ms / args.steps * 1e-3, "wall_ms_per_step_host": 1e3 * wall_max / args.steps,

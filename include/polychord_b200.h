@@ -335,6 +335,12 @@ int pc_cluster_points(const double* points, int m, int nDims, int* labels_out);
  * FMA chains per thread, best of five launches).  bench.py quotes the run's arithmetic against it. */
 double pc_measure_fp64_tflops(void);
 
+/* The batch size (deaths per generation) the engine picks by itself for a run of nlive live points alone on the device,
+ * or sharded over `world` devices (about nlive/2, a whole number of waves of chains where that
+ * stays below 0.6 nlive); the options batch_K / batch_fraction override it.  Needs a CUDA device (the wave is a
+ * function of its SM count). */
+int pc_auto_batch_size(int nlive, int world);
+
 /* Number of CUDA devices visible; <=0 means the engine cannot run (no CPU fallback exists). */
 int pc_device_count(void);
 const char* pc_version(void);

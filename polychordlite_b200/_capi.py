@@ -27,7 +27,7 @@ EXPORTS = [
     "pc_unit_prior", "pc_uniform_prior", "pc_set_option", "pc_get_option", "pc_set_stream", "pc_release_memory", "pc_mgpu_create", "pc_mgpu_attach", "pc_mgpu_destroy",
     "pc_last_run_info", "pc_run", "pc_run_ensemble", "pc_slice_chains", "pc_calculate_points",
     "pc_device_philox", "pc_device_uniforms", "pc_device_inv_normal_cdf", "pc_device_directions",
-    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points", "pc_set_grades", "pc_set_resume", "pc_measure_fp64_tflops", "pc_ini_prior_transform", "pc_last_boosted", "pc_maximise", "pc_prior_log_density", "pc_set_initial_live", "pc_write_files_boosted", "pc_set_nlives", "pc_resume_text_probe", "pc_last_clusters", "pc_last_dead_clusters", "pc_last_cluster_tree",
+    "pc_device_evidence", "pc_device_cholesky", "pc_device_count", "pc_version", "pc_format_e24", "pc_write_files", "pc_request_abort", "pc_cluster_points", "pc_set_grades", "pc_set_resume", "pc_measure_fp64_tflops", "pc_ini_prior_transform", "pc_last_boosted", "pc_maximise", "pc_prior_log_density", "pc_set_initial_live", "pc_write_files_boosted", "pc_set_nlives", "pc_resume_text_probe", "pc_last_clusters", "pc_last_dead_clusters", "pc_last_cluster_tree", "pc_auto_batch_size",
 ]
 
 
@@ -438,6 +438,14 @@ def set_resume(path=None, write=False, read=False):
     L.pc_set_resume.argtypes = [C.c_char_p, C.c_int, C.c_int]
     if L.pc_set_resume(None if path is None else str(path).encode(), int(write), int(read)) != 0:
         raise ValueError("pc_set_resume: the path must end in .resume")
+
+
+def auto_batch_size(nlive, world=1):
+    """pc_auto_batch_size: the deaths per generation the engine picks for a run alone on the device / sharded over `world`."""
+    L = lib()
+    L.pc_auto_batch_size.restype = C.c_int
+    L.pc_auto_batch_size.argtypes = [C.c_int, C.c_int]
+    return int(L.pc_auto_batch_size(int(nlive), int(world)))
 
 
 def measure_fp64_tflops():

@@ -189,10 +189,10 @@ struct DevArr {  // RAII device buffer (exception-transparent: callbacks may thr
 };
 
 struct Options {
-    // K lowest points die per generation: K = round(nlive * batch_fraction).  0 = automatic: 1/2 for a run that has
-    // the device to itself (its wall time is the number of generations: per unit of compression K = n/2 needs 2.4
-    // times fewer than K = n/4 for 1.25 times the variance), 1/4 for the runs of an ensemble (the device is full
-    // either way, so the smaller variance per likelihood evaluation wins).  DESIGN.md section 2.
+    // K lowest points die per generation: K = round(nlive * batch_fraction).  0 = automatic (batch_size()): about 1/2 for
+    // a run that has the device to itself (its wall time is the number of generations: per unit of compression K = n/2
+    // needs 2.4 times fewer than K = n/4 for 1.25 times the variance), 1/4 for the runs of an ensemble (the device is
+    // full either way, so the smaller variance per likelihood evaluation wins).  DESIGN.md section 2.
     double batch_fraction = 0.0;
     int dense = 0;      // the dense chain phase (pc_dense.cuh): 0 = for ensembles, 1 = always (testing), -1 = never
     int batch_K = 0;
@@ -204,6 +204,7 @@ struct Options {
     int no_pairing = 0; // keep the helper-warp preparation off (testing)
     int no_phase_d = 0; // order the live points on CTA 0 only (testing: phase D off)
     int no_bulk = 0;    // phase U streams its records through registers (testing: the bulk-copy ring off)
+    int no_wave_batch = 0;  // automatic batch size: plain nlive/2 for a run alone (the wave rule of batch_size() off)
     int resume_text = 0; // write_resume writes the reference's text layout (read_write.F90:219-288) instead of the engine's binary one
     int sync_dump = 0;  // the kernel exits at every update for the dumper instead of handing dumps over while running
     long long cap_dead0 = 0, cap_ph0 = 0;  // initial pool capacities in records (0 = automatic)
@@ -319,10 +320,28 @@ static ShapeFns pick_shape(int D, int kind) {
 
 static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const DevModel& dm, int W, bool alone, bool dense);
 
-// points that die per generation (see Options::batch_fraction)
-static int batch_size(int nlive, bool alone) {
-    const double f = g_opt.batch_fraction > 0.0 ? g_opt.batch_fraction : (alone ? 0.5 : 0.25);
-    int K = g_opt.batch_K > 0 ? g_opt.batch_K : (int)std::lround(nlive * f);
+// points that die per generation (see Options::batch_fraction).  A run alone on the device (or sharded over `world`
+// devices) takes about half the live points per generation -- the critical path of a run is its generation count -- and,
+// where that fits, a whole number of WAVES of chains: one wave is a chain warp and its helper on every SM sub-partition
+// of every chain CTA ((SMs - 1) * 4 chains per device), and a generation of 500 chains costs the device as much time as
+// one of 588.  So K = m * wave for the smallest m with K >= nlive/2, if that keeps K <= 0.6 nlive (variance per unit of
+// log-compression 1.61 against 1.44 at nlive/2; the error bar carries it), else nlive/2.  `half_only`: the launch turned
+// out not to have the paired geometry (fewer than 8 warps per CTA fit), plain nlive/2.
+static bool g_half_only = false;
+static int wave_chains(int world) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return std::max(1, (sms - 1) * 4) * std::max(1, world);
+}
+static int batch_size(int nlive, bool alone, int world = 1) {
+    if (g_opt.batch_K > 0) return std::max(1, std::min(g_opt.batch_K, nlive - 1));
+    if (g_opt.batch_fraction > 0.0) return std::max(1, std::min((int)std::lround(nlive * g_opt.batch_fraction), nlive - 1));
+    int K = (int)std::lround(nlive * (alone ? 0.5 : 0.25));
+    if (alone && !g_half_only && !g_opt.no_wave_batch) {
+        const long long wave = wave_chains(world);
+        const long long m = (K + wave - 1) / wave;
+        if (m * wave <= (long long)(0.6 * nlive)) K = (int)(m * wave);
+    }
     return std::max(1, std::min(K, nlive - 1));
 }
 
@@ -336,9 +355,14 @@ static Layout make_layout(const pc_settings& s, const ModelSpec& ms, const DevMo
             if (L.kp.nh_in_smem && L.smem <= 112 * 1024) return L;
         }
     }
+    struct HalfGuard { ~HalfGuard() { g_half_only = false; } } half_guard;
     for (;; --W) {
         Layout L = make_layout_w(s, ms, dm, W, alone, false);
-        if (L.smem <= 227 * 1024) return L;
+        if (L.smem <= 227 * 1024) {
+            // the wave rule of batch_size() assumes the paired geometry (an even number of warps per CTA): without it, nlive/2
+            if (alone && !g_half_only && !g_mgpu.local && (L.W % 2) != 0) { g_half_only = true; L = make_layout_w(s, ms, dm, W, alone, false); }
+            return L;
+        }
         if (W == 1) throw pc::ArgError("polychord_b200: the run does not fit in shared memory (nlive too large for the in-kernel sort, or nDims*nDims too large)");
     }
 }
@@ -407,7 +431,7 @@ static Layout make_layout_w(const pc_settings& s, const ModelSpec& ms, const Dev
     // phase U: pivot + a staged batch of augmented rows per warp; all warps' areas together hold the CTA's moment matrix
     const size_t cov_bytes = std::max((size_t)(Dpad + U_BATCH * (Dp8 + 4)) * 8,
                                       ((size_t)(Dpad + Dp8 * Dp8) * 8 + W - 1) / W);
-    const int K = batch_size(s.nlive, alone);
+    const int K = (g_mgpu.local && alone) ? g_mgpu.batch_K : batch_size(s.nlive, alone);   // a sharded run: what pc_mgpu_create fixed
     k.batch_K = K;
     const size_t sort_bytes = std::max(smem_S_bytes(k.nmax, K), (size_t)64 * 8 + (size_t)(D * D + Dpad) * 8);  // phase S, or the covariance (+ mean shift) in finish_update
     const size_t budget = dense ? 108 * 1024 : 200 * 1024;
@@ -1874,6 +1898,7 @@ int pc_set_option(const char* name, double value) {
     else if (s == "no_pairing") g_opt.no_pairing = (int)value;
     else if (s == "no_phase_d") g_opt.no_phase_d = (int)value;
     else if (s == "no_bulk") g_opt.no_bulk = (int)value;
+    else if (s == "no_wave_batch") g_opt.no_wave_batch = (int)value;
     else if (s == "resume_text") g_opt.resume_text = (int)value;
     else if (s == "sync_dump") g_opt.sync_dump = (int)value;
     else if (s == "cap_dead0") g_opt.cap_dead0 = (long long)value;
@@ -1895,6 +1920,7 @@ double pc_get_option(const char* name) {
     if (s == "no_pairing") return g_opt.no_pairing;
     if (s == "no_phase_d") return g_opt.no_phase_d;
     if (s == "no_bulk") return g_opt.no_bulk;
+    if (s == "no_wave_batch") return g_opt.no_wave_batch;
     if (s == "resume_text") return g_opt.resume_text;
     if (s == "sync_dump") return g_opt.sync_dump;
     if (s == "cap_dead0") return (double)g_opt.cap_dead0;
@@ -1929,6 +1955,14 @@ int pc_set_nlives(const double* loglikes, const int* nlives, int m) {
     return 0;
 }
 void pc_release_memory(void) { pool().trim(); }
+int pc_auto_batch_size(int nlive, int world) {
+    try {
+        device_check();
+        return batch_size(nlive, true, std::max(1, world));
+    } catch (const std::exception&) {
+        return -1;
+    }
+}
 
 // ---- sharded run over the GPUs of one box ---------------------------------------------------------
 int pc_mgpu_create(const pc_settings* s, int world, unsigned char* handle64) {
@@ -1936,7 +1970,7 @@ int pc_mgpu_create(const pc_settings* s, int world, unsigned char* handle64) {
         device_check();
         if (world < 2 || world > MAX_RANKS) throw pc::ArgError("polychord_b200: world must be 2..8");
         if (g_mgpu.local) throw pc::ArgError("polychord_b200: pc_mgpu_create called twice (pc_mgpu_destroy first)");
-        const int K = batch_size(s->nlive, true);
+        const int K = batch_size(s->nlive, true, world);
         const int T = 2 * s->nDims + s->nDerived + 2;
         g_mgpu.bytes = mgpu_block_bytes(K, T, s->nDims, world);
         g_mgpu.batch_K = K; g_mgpu.T = T; g_mgpu.D = s->nDims; g_mgpu.world = 0; g_mgpu.epoch = 0;

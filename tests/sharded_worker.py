@@ -22,7 +22,9 @@ res = dict(rank=rank, logZ=info.logZ, ndead=int(info.ndead), nlike_local=int(inf
            nupdates=int(info.nupdates), ngen=int(info.ngenerations), device_ms=info.device_ms,
            dead_sum=float(dumps[-1]["dead"].sum()), ndumps=len(dumps))
 if rank == 0:
+    capi.set_option("batch_K", int(info.batch_K))   # the automatic batch size follows the number of devices
     single, sd = capi.run(s, want_dump=True)
+    capi.set_option("batch_K", 0)
     res.update(single_logZ=single.logZ, single_ndead=int(single.ndead), single_nlike=int(single.nlike),
                single_ms=single.device_ms, single_dead_sum=float(sd[-1]["dead"].sum()),
                max_dead_diff=float(np.abs(sd[-1]["dead"] - dumps[-1]["dead"]).max())

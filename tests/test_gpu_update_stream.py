@@ -44,3 +44,22 @@ def test_odd_record_length_takes_the_register_stream_and_matches_oracle(gpu, ora
     oi, _ = oracle.run(oracle.make_settings(batch_K=30, **kw))
     assert (gi.ndead, gi.nlike, gi.nupdates) == (oi.ndead, oi.nlike, oi.nupdates)
     assert abs(gi.logZ - oi.logZ) < 1e-7
+
+
+def test_automatic_batch_size_is_whole_waves_of_chains(gpu):
+    """a run alone on the device takes m waves of (SMs - 1) * 4 chains per generation when that lies in
+    [0.5, 0.6] nlive, else nlive / 2; a sharded run counts the waves of all its devices; an explicit batch_K wins."""
+    import torch
+    wave = (torch.cuda.get_device_properties(0).multi_processor_count - 1) * 4
+    for n in (200, 500, 1000, 2000, 8000):
+        K = gpu.auto_batch_size(n, 1)
+        m = -(-(n // 2) // wave)
+        assert K == (m * wave if m * wave <= 0.6 * n else round(n / 2)), (n, K)
+    assert gpu.auto_batch_size(8000, 8) == gpu.auto_batch_size(1000, 1) * 8 or gpu.auto_batch_size(1000, 1) == 500
+    info, _ = gpu.run(gpu.make_settings(20, 2, nlive=1000, num_repeats=40, seed=2))
+    assert info.batch_K == gpu.auto_batch_size(1000, 1)
+    gpu.set_option("batch_K", 123)
+    try:
+        assert gpu.auto_batch_size(1000, 1) == 123
+    finally:
+        gpu.set_option("batch_K", 0)
