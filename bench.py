@@ -312,7 +312,7 @@ def main():
     ap.add_argument("--workload", default="gaussian20_nlive1000_R40", choices=sorted(WORKLOADS))
     ap.add_argument("--batch-fraction", type=float, default=None)
     ap.add_argument("--warps-per-cta", type=int, default=None)
-    ap.add_argument("--ensemble", type=int, default=72, help="replicas for the ensemble-throughput figure (0=skip)")
+    ap.add_argument("--ensemble", type=int, default=74, help="replicas for the ensemble-throughput figure (0=skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the block of the other BASELINE configurations")
     ap.add_argument("--replicas", action="store_true",

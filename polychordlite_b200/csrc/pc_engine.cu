@@ -881,8 +881,30 @@ struct Engine {
         if (resumed) {  // the run continues from the state the file holds
             HostRun& h = runs[0];
             DevRun st0 = rd.st;
+            {   // the file's counters index device arrays sized from THIS run's settings: a damaged or foreign file that
+                // passed the shape header must not reach the kernel (the reference's reader trusts its text file; here
+                // the state is binary and drives pointers)
+                const long long nl = st0.n, nd = st0.ndead, np = st0.nphantom, nmaxl = k.nmax;
+                const bool counts = nl >= 1 && nl <= nmaxl && nd >= 0 && np >= 0 && (st0.cur_pool == 0 || st0.cur_pool == 1) &&
+                                    (st0.order_off == 0 || st0.order_off == k.nmax) && st0.K >= 0 && st0.K <= k.nmax &&
+                                    st0.ncl >= 0 && st0.ncl <= MAX_CLUSTERS && st0.nchains >= 0 && st0.ngen >= 0;
+                const bool sizes = counts && (long long)rd.live.size() <= nmaxl * T && (long long)rd.live.size() >= nl * T &&
+                                   rd.order.size() == 2 * (size_t)k.nmax && rd.okey.size() == 2 * (size_t)k.nmax &&
+                                   (long long)rd.dead.size() == nd * T && (rd.logw.empty() || (long long)rd.logw.size() == nd) &&
+                                   (long long)rd.ph.size() == np * T && rd.chol.size() == (size_t)D * D && rd.cov.size() == (size_t)D * D &&
+                                   rd.gsum.size() == (size_t)2 * D + 4 && (rd.lab.empty() || (long long)rd.lab.size() <= nmaxl) &&
+                                   (rd.phl.empty() || (long long)rd.phl.size() == np) &&
+                                   (rd.cchol.empty() || rd.cchol.size() <= (size_t)MAX_CLUSTERS * D * D) &&
+                                   nd <= (long long)h.dead.n / T && np <= (long long)(st0.cur_pool == 0 ? h.ph0.n : h.ph1.n) / T;
+                bool order_ok = sizes;
+                for (long long e = 0; order_ok && st0.order_valid && e < nl; ++e) { const int o = rd.order[(size_t)st0.order_off + e]; order_ok = o >= 0 && o < k.nmax; }   // (the other half is scratch)
+                for (size_t e = 0; order_ok && e < rd.lab.size(); ++e) order_ok = rd.lab[e] >= 0 && rd.lab[e] < MAX_CLUSTERS;
+                if (!order_ok)
+                    throw pc::ArgError("polychord_b200: the resume file " + g_resume.path + " is damaged (its counters or array sizes do not fit the run it describes)");
+            }
             st0.status = ST_RUNNING;
             st0.bar = 0; st0.wbar = 0;   // the barrier counters restart with the launch geometry of this process
+            st0.dump_pub = 0; st0.snap_arr = 0u;   // ... and the dumper hand-over with this process's control block
             if (rd.st.status == ST_DONE) resumed_finished = true;
             h.st.upload(&st0, 1, stream);
             h.host_st = rd.st;
@@ -1634,7 +1656,11 @@ struct Engine {
         put_vec(f, w.live); put_vec(f, w.order); put_vec(f, w.okey); put_vec(f, w.dead); put_vec(f, w.logw); put_vec(f, w.ph);
         put_vec(f, w.chol); put_vec(f, w.cov); put_vec(f, w.gsum); put_vec(f, w.lab); put_vec(f, w.phl); put_vec(f, w.cchol);
         put_vec(f, w.boost); put_vec(f, w.boost_win);
-        std::fclose(f);
+        const bool wrote = std::ferror(f) == 0;
+        if (std::fclose(f) != 0 || !wrote) {   // a short write (disk full): the last good file stays in place
+            std::remove(tmp.c_str());
+            throw pc::RunError("polychord_b200: writing " + tmp + " failed");
+        }
         std::rename(tmp.c_str(), g_resume.path.c_str());
         resume_written = true;
         resume_last = std::chrono::steady_clock::now();

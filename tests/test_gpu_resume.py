@@ -87,3 +87,30 @@ def test_python_api_resumes_a_host_callback_run(gpu, tmp_path):
     res = pypolychord.run(like, 3, file_root="leg", write_resume=True, read_resume=True, **kw)
     assert res.equals(ref) and res.logZ == ref.logZ
 
+
+
+def test_damaged_resume_file_is_refused(gpu, tmp_path):
+    """A file that passes the shape header but whose counters do not fit its arrays must not reach the kernel."""
+    import struct
+    st = gpu.make_settings(6, 0, nlive=200, num_repeats=12, seed=11)
+    path = tmp_path / "r.resume"
+    gpu.set_option("errors_return", 1)
+    try:
+        gpu.set_resume(path, write=True)
+        gpu.set_option("resume_interval", 0.0)
+        with pytest.raises(RuntimeError):
+            gpu.run(st, abort_after_dumps=3)
+        raw = bytearray(path.read_bytes())
+        header = 136                                       # sizeof(ResumeHeader) (csrc/pc_engine.cu: 124 bytes of ints, padded, one double)
+        ndead_at = header + 8 * 8                          # DevRun: eight doubles, then ndead
+        (ndead,) = struct.unpack_from("<q", raw, ndead_at)
+        assert 0 < ndead < 10 ** 6
+        struct.pack_into("<q", raw, ndead_at, ndead + 12345)
+        path.write_bytes(bytes(raw))
+        gpu.set_resume(path, read=True)
+        with pytest.raises(RuntimeError):
+            gpu.run(st)
+    finally:
+        gpu.set_resume()
+        gpu.set_option("resume_interval", 1.0)
+        gpu.set_option("errors_return", 0)
