@@ -145,45 +145,69 @@ __global__ void pc_identify_kernel(const double* live, int T, int D, int n, cons
 // beyond nDims) and the warp walks the live table together, so one broadcast read of a live coordinate serves 32
 // distances -- 2.5x less shared-memory traffic than the warp-per-phantom form, which is what bounds that kernel.
 // The table rows are padded to DCAP with zeros (a zero difference leaves the fused multiply-add chain unchanged, so
-// every distance is still the same number).  Dynamic shared memory: n x (DCAP | 1) doubles.
+// every distance is still the same number).
+//
+// The scan is bound by the FP64 pipe (a subtraction and a fused multiply-add per dimension and live point), so it is
+// run behind a filter that costs half of that: with |x - q|^2 = |x|^2 + |q|^2 - 2 x.q, the value s = |q|^2 - 2 x.q (one
+// fused multiply-add per dimension, |q|^2 kept in the table) orders the live points as the distance does, up to its
+// rounding error.  Only a live point whose s is within FILTER_TOL of the best distance found so far (minus |x|^2) can
+// be the nearest one or tie with it; for those -- a few per phantom -- the distance itself is formed in the reference
+// order and compared exactly, lowest slot first.  The label is therefore the one of the unfiltered scan, bit for bit.
+// FILTER_TOL: cube coordinates lie in [0, 1], so |s|'s terms are below 2 and its rounding error below
+// (DCAP + 2) * 3 DCAP * 2^-53 < 4e-13 for DCAP = 32.  Dynamic shared memory: n x TS doubles, TS = (DCAP + 1) | 1.
+constexpr double FILTER_TOL = 1e-11;
 template <int DCAP>
 __global__ void pc_identify_lanes_kernel(const double* live, int T, int D, int n, const int* lab, const double* ph,
                                          long long nph, int* phl) {
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int TS = DCAP | 1;
+    constexpr int TS = (DCAP + 1) | 1;
     double* tab = (double*)smem;
     for (int e = threadIdx.x; e < n * DCAP; e += blockDim.x) {
         const int j = e / DCAP, k = e - j * DCAP;
         tab[(size_t)j * TS + k] = k < D ? live[(size_t)j * T + k] : 0.0;
     }
     __syncthreads();
-    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nph; r += (long long)gridDim.x * blockDim.x) {
-        double x[DCAP];
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {   // |q|^2 behind the coordinates
+        const double* q = tab + (size_t)j * TS;
+        double qn = 0.0;
 #pragma unroll
-        for (int k = 0; k < DCAP; ++k) x[k] = k < D ? ph[(size_t)r * T + k] : 0.0;
-        double bd = INFINITY;
+        for (int k = 0; k < DCAP; ++k) qn = fma(q[k], q[k], qn);
+        tab[(size_t)j * TS + DCAP] = qn;
+    }
+    __syncthreads();
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nph; r += (long long)gridDim.x * blockDim.x) {
+        double x[DCAP], m2x[DCAP];
+        double xn = 0.0;
+#pragma unroll
+        for (int k = 0; k < DCAP; ++k) {
+            x[k] = k < D ? ph[(size_t)r * T + k] : 0.0;
+            m2x[k] = -2.0 * x[k];
+            xn = fma(x[k], x[k], xn);
+        }
+        double bd = INFINITY, lim = INFINITY;   // best distance so far; lim = bd - |x|^2 + FILTER_TOL in the filter's terms
         int bj = 0;
+        auto exact = [&](int j) {   // the distance in the reference order (calculate.f90:94-109 / identify_cluster); strict <: lowest slot wins ties
+            const double* q = tab + (size_t)j * TS;
+            double sd = 0.0;
+#pragma unroll
+            for (int k = 0; k < DCAP; ++k) { const double d0 = x[k] - q[k]; sd = fma(d0, d0, sd); }
+            if (sd < bd) { bd = sd; bj = j; lim = bd - xn + FILTER_TOL; }
+        };
         int j = 0;
         for (; j + 4 <= n; j += 4) {   // four live points in flight
             const double* q = tab + (size_t)j * TS;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            double s0 = q[DCAP], s1 = q[TS + DCAP], s2 = q[2 * TS + DCAP], s3 = q[3 * TS + DCAP];
 #pragma unroll
             for (int k = 0; k < DCAP; ++k) {
-                const double d0 = x[k] - q[k], d1 = x[k] - q[TS + k], d2 = x[k] - q[2 * TS + k], d3 = x[k] - q[3 * TS + k];
-                s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
+                s0 = fma(m2x[k], q[k], s0); s1 = fma(m2x[k], q[TS + k], s1);
+                s2 = fma(m2x[k], q[2 * TS + k], s2); s3 = fma(m2x[k], q[3 * TS + k], s3);
             }
-            if (s0 < bd) { bd = s0; bj = j; }          // slots ascend: the first minimum is the lowest slot
-            if (s1 < bd) { bd = s1; bj = j + 1; }
-            if (s2 < bd) { bd = s2; bj = j + 2; }
-            if (s3 < bd) { bd = s3; bj = j + 3; }
+            if (s0 <= lim) exact(j);          // slots ascend: the first minimum is the lowest slot
+            if (s1 <= lim) exact(j + 1);
+            if (s2 <= lim) exact(j + 2);
+            if (s3 <= lim) exact(j + 3);
         }
-        for (; j < n; ++j) {
-            const double* q = tab + (size_t)j * TS;
-            double s0 = 0.0;
-#pragma unroll
-            for (int k = 0; k < DCAP; ++k) { const double d0 = x[k] - q[k]; s0 = fma(d0, d0, s0); }
-            if (s0 < bd) { bd = s0; bj = j; }
-        }
+        for (; j < n; ++j) exact(j);
         phl[r] = lab[bj];
     }
 }

@@ -1190,7 +1190,7 @@ struct Engine {
         for (int c = 0; c < nparts0; ++c) origin[c] = c;
         if (d_part.n < (size_t)n) { d_part.alloc(n); d_knn.alloc((size_t)n * KNN_K); }
         h_knn.resize((size_t)n * KNN_K);
-        std::vector<int> uf(n), loc(n), canon(n), old(n), head(n), twin_next(n), firstseen(n), members;
+        std::vector<int> uf(n), loc(n), canon(n), old(n), head(n), twin_next(n), firstseen(n), members, bucket, bucket_off;
         members.reserve(n);
         auto find = [&](int a) { while (uf[a] != a) { uf[a] = uf[uf[a]]; a = uf[a]; } return a; };
         for (int round = 0; round < 64; ++round) {
@@ -1209,10 +1209,18 @@ struct Engine {
             launches += 1;
             h2d += (long long)n * 4; d2h += (long long)n * KNN_K * 4;
             const int nparts_now = nparts;
+            // the points of every part, in slot order (one counting pass instead of a scan of all points per part)
+            bucket_off.assign((size_t)nparts_now + 1, 0);
+            for (int i = 0; i < n; ++i) bucket_off[part[i] + 1]++;
+            for (int c = 0; c < nparts_now; ++c) bucket_off[c + 1] += bucket_off[c];
+            bucket.resize(n);
+            {
+                std::vector<int> fill(bucket_off.begin(), bucket_off.end() - 1);
+                for (int i = 0; i < n; ++i) bucket[fill[part[i]]++] = i;
+            }
             for (int c = 0; c < nparts_now; ++c) {
                 if (final_part[c]) continue;
-                members.clear();
-                for (int i = 0; i < n; ++i) if (part[i] == c) members.push_back(i);
+                members.assign(bucket.begin() + bucket_off[c], bucket.begin() + bucket_off[c + 1]);
                 const int m = (int)members.size();
                 if (m <= 2) { final_part[c] = 1; continue; }   // do_clustering: nlive > 2 (clustering.f90:289); two points are each other's neighbours
                 const int kk = std::min(m, KNN_K);
@@ -1427,7 +1435,7 @@ struct Engine {
                 const int WI = 16;
                 // register tile of the lane-per-phantom kernel: nDims rounded up to 2 (to 4 above 16); 0 = too wide
                 const int dcap = D <= 16 ? ((D + 1) & ~1) : (D <= 32 ? ((D + 3) & ~3) : 0);
-                const size_t lsm = dcap ? (size_t)n * (dcap | 1) * 8 : 0;
+                const size_t lsm = dcap ? (size_t)n * ((dcap + 1) | 1) * 8 : 0;   // coordinates + |q|^2, odd row stride
                 if (dcap && lsm <= 200 * 1024) {  // a lane per phantom, the live table in shared memory
                     const int blocks = (int)std::min<long long>((nph + 255) / 256, 148LL);
                     auto launch = [&](auto kern) {
