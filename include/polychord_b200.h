@@ -101,8 +101,11 @@ void pc_unit_prior(double* cube, double* theta, int nDims);    /* theta = cube (
 void pc_uniform_prior(double* cube, double* theta, int nDims); /* theta = lo + (hi-lo)*cube */
 
 /* Engine options (name/value); unknown names return -1.
- *   "batch_fraction"  K = max(1, round(nlive*value)) lowest points die per generation; 0 (default) = automatic: 1/2 for a
- *                     run alone on the device (its wall time is the number of generations), 1/4 for the runs of an ensemble
+ *   "batch_fraction"  K = max(1, round(nlive*value)) lowest points die per generation; 0 (default) = automatic
+ *                     (pc_auto_batch_size): about 1/2 for a run alone on the device (its wall time is the number of
+ *                     generations), in whole waves of chains where that stays within [0.5, 0.6] nlive; 1/4 for the runs
+ *                     of an ensemble
+ *   "no_wave_batch"   1: the automatic batch of a run alone on the device is plain nlive/2
  *   "dense"           the dense chain phase (one chain per point group, csrc/pc_dense.cuh): 0 = ensembles only (default),
  *                     1 = always, -1 = never
  *   "batch_K"         absolute K (overrides batch_fraction when > 0)
@@ -119,6 +122,8 @@ void pc_uniform_prior(double* cube, double* theta, int nDims); /* theta = lo + (
  *                     normally pairs every chain warp with a helper warp)
  *   "no_phase_d"      1: keep the order of the live points on one CTA (phase S); normally every CTA of a run
  *                     ranks its share of the live points after a regular generation (phase D)
+ *   "no_bulk"         1: phase U streams the phantom records through registers; normally records of an even length
+ *                     move by bulk copies (cp.async.bulk) through a shared-memory ring (same results bit for bit)
  *   "resume_text"     1: <root>.resume is written in the reference's text layout (read_write.F90:219-288) instead of the
  *                     engine's binary one.  Reading accepts both layouts whatever this option says (and the files
  *                     pypolychord writes for cube_samples, polychord.py:650-789).
