@@ -225,7 +225,7 @@ __device__ inline void slice_chains_dense(const ChainParams& p, const Model<G, D
                 for (int k = 0; k < DPL; ++k)
                     if (M.valid(k)) {
                         dst[M.dim(k)] = y[k];
-                        dst[D + M.dim(k)] = incube ? fma(t_lo[GD + k * G], y[k], t_lo[k * G]) : 0.0;
+                        if (slice == R - 1 || !p.ph_narrow) dst[D + M.dim(k)] = incube ? fma(t_lo[GD + k * G], y[k], t_lo[k * G]) : 0.0;
                     }
                 if (sub == 0) {
                     dst[2 * D + p.P] = Lstar;

@@ -791,14 +791,21 @@ __device__ inline void phase_UB(const KParams& p, const RunBuf& rb, DevRun* st, 
             double* s_stage = s_x + U_BATCH * SX;   // 2 x U_BATCH x T doubles behind the staged rows
             unsigned long long* bar = mbar + 2 * warp;
             fence_proxy_async();   // the area was last written through the generic proxy (moment matrix of the pass before)
+            // what moves: the cube coordinates (rounded up to 16 bytes); in the compaction pass the whole record, or -- narrow
+            // phantoms (ChainParams::ph_narrow) -- the cube coordinates and the record's last 16 bytes, [birth, logL]
+            const unsigned cube_bytes = (unsigned)(((D + 1) & ~1) * 8);
+            const bool narrow = p.cp.ph_narrow != 0 && cube_bytes + 16u < (unsigned)(T * 8);
             auto issue = [&](const UBatch& b, int buf) {
-                const unsigned bytes = (unsigned)((((b.copy ? T : D) + 1) & ~1) * 8);
+                const unsigned bytes = (b.copy && !narrow) ? (unsigned)(T * 8) : cube_bytes;
                 bulk_wait_read0();   // this lane's store out of the slot it is about to refill (issued a batch ago) has read it
-                if (lane == 0) mbar_expect_tx(bar + buf, bytes * (unsigned)b.nb);
+                if (lane == 0) mbar_expect_tx(bar + buf, (bytes + ((b.copy && narrow) ? 16u : 0u)) * (unsigned)b.nb);
                 __syncwarp();
                 if (lane < b.nb) {
                     const int bit = __fns(b.bm, 0, lane + 1);
-                    bulk_g2s(s_stage + ((size_t)buf * U_BATCH + lane) * T, b.rbase + (size_t)bit * T, bytes, bar + buf);
+                    double* slot = s_stage + ((size_t)buf * U_BATCH + lane) * T;
+                    const double* rec = b.rbase + (size_t)bit * T;
+                    bulk_g2s(slot, rec, bytes, bar + buf);
+                    if (b.copy && narrow) bulk_g2s(slot + (T - 2), rec + (T - 2), 16u, bar + buf);
                 }
             };
             UBatch cur, nxt;
@@ -812,7 +819,16 @@ __device__ inline void phase_UB(const KParams& p, const RunBuf& rb, DevRun* st, 
                 mpar ^= 1u << buf;
                 const double* sb = s_stage + (size_t)buf * U_BATCH * T;
                 if (cur.copy) {   // stable compaction: the record goes to its place in the other pool as it lies in the ring
-                    if (lane < cur.nb) bulk_s2g(dst + (size_t)(cur.place + lane) * T, sb + (size_t)lane * T, (unsigned)(T * 8));
+                    if (lane < cur.nb) {
+                        double* out = dst + (size_t)(cur.place + lane) * T;
+                        const double* slot = sb + (size_t)lane * T;
+                        if (narrow) {
+                            bulk_s2g(out, slot, cube_bytes);
+                            bulk_s2g(out + (T - 2), slot + (T - 2), 16u);
+                        } else {
+                            bulk_s2g(out, slot, (unsigned)(T * 8));
+                        }
+                    }
                     bulk_commit();
                     move_labels(cur);
                 }
