@@ -124,6 +124,8 @@ void pc_uniform_prior(double* cube, double* theta, int nDims); /* theta = lo + (
  *                     ranks its share of the live points after a regular generation (phase D)
  *   "no_bulk"         1: phase U streams the phantom records through registers; normally records of an even length
  *                     move by bulk copies (cp.async.bulk) through a shared-memory ring (same results bit for bit)
+ *   "no_narrow"       1: the runs of an ensemble store and carry a phantom's theta although nothing reads it (normally
+ *                     they skip those columns: less DRAM traffic, same results)
  *   "resume_text"     1: <root>.resume is written in the reference's text layout (read_write.F90:219-288) instead of the
  *                     engine's binary one.  Reading accepts both layouts whatever this option says (and the files
  *                     pypolychord writes for cube_samples, polychord.py:650-789).

@@ -63,3 +63,19 @@ def test_automatic_batch_size_is_whole_waves_of_chains(gpu):
         assert gpu.auto_batch_size(1000, 1) == 123
     finally:
         gpu.set_option("batch_K", 0)
+
+
+def test_narrow_phantom_traffic_changes_nothing_in_an_ensemble(gpu):
+    """ChainParams::ph_narrow (ensembles): the chains do not store a phantom's theta and phase U does not carry it along.
+    Nothing reads it, so every run of the ensemble ends with the same numbers as with full records."""
+    s = gpu.make_settings(20, 2, nlive=300, num_repeats=40)
+    seeds = list(range(6))
+    a = gpu.run_ensemble(s, seeds)
+    gpu.set_option("no_narrow", 1)
+    try:
+        b = gpu.run_ensemble(s, seeds)
+    finally:
+        gpu.set_option("no_narrow", 0)
+    for x, y in zip(a, b):
+        assert (x.ndead, x.nlike, x.nupdates) == (y.ndead, y.nlike, y.nupdates)
+        assert x.logZ == y.logZ and x.logZerr == y.logZerr
