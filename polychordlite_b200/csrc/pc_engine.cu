@@ -108,6 +108,25 @@ struct DumpMirror {
     std::vector<long long> boost_dead, boost_after;
 };
 static DumpMirror g_mirror;
+// The mirror's rows, page-locked in place (cudaHostRegister) while an asynchronous dumper hand-over is in use: the new dead
+// rows of a dump then land in the mirror by DMA instead of in a staging buffer that the host copies from (at nlive 8000
+// the copy was a third of the host's work per dump, and the host's work per dump is what bounds the sharded runs end to
+// end).  Sized before the launch (registering, like allocating pinned memory, synchronises with a running kernel).
+struct MirrorPin {
+    void* p = nullptr;
+    size_t bytes = 0;
+    void drop() { if (p) cudaHostUnregister(p); p = nullptr; bytes = 0; }
+    // rows: capacity wanted (doubles); keeps the contents
+    void reserve(std::vector<double>& v, size_t doubles) {
+        if (v.size() >= doubles && p == (void*)v.data() && bytes >= doubles * sizeof(double)) return;
+        drop();
+        if (v.size() < doubles) v.resize(std::max(doubles, v.size() * 2));
+        if (cudaHostRegister(v.data(), v.size() * sizeof(double), cudaHostRegisterDefault) == cudaSuccess) { p = v.data(); bytes = v.size() * sizeof(double); }
+        else cudaGetLastError();   // not fatal: the staged path stays
+    }
+    bool covers(const std::vector<double>& v, size_t doubles) const { return p && p == (const void*)v.data() && v.size() >= doubles && bytes >= doubles * sizeof(double); }
+};
+static MirrorPin g_mirror_pin;
 // `maximise`: the live points the sampling loop ended with (full records, cube coordinates included) -- the simplex
 // of the maximiser is built from them (maximiser.F90:117-135).  Filled by Engine::run when want is set.
 struct FinalLive { bool want = false; int n = 0; std::vector<double> recs; };
@@ -996,10 +1015,13 @@ struct Engine {
         // one batch of async copies into pinned staging, one synchronisation.  The dumper's rows are [theta, phi, birth,
         // logL] = columns D .. T-1 of a record (nested_sampling.F90:569-584): only those cross the bus (a strided copy;
         // the cube coordinates stay on the device)
+        DumpMirror& mr = g_mirror;
+        const bool direct = fresh > 0 && g_mirror_pin.covers(mr.rows, (size_t)ndead * npars);   // the rows go straight into the (page-locked) mirror
         double* sd = fresh > 0 ? (double*)g_pin_dead.need((size_t)fresh * (npars + 1) * 8) : nullptr;
         double* sl = nl > 0 ? (double*)g_pin_live.need((size_t)k.nmax * npars * 8) : nullptr;
         if (fresh > 0) {
-            PC_CUDA(cudaMemcpy2DAsync(sd, (size_t)npars * 8, h.dead.p + (size_t)h.mirrored * T + D, (size_t)T * 8, (size_t)npars * 8,
+            double* rows_dst = direct ? &mr.rows[(size_t)h.mirrored * npars] : sd;
+            PC_CUDA(cudaMemcpy2DAsync(rows_dst, (size_t)npars * 8, h.dead.p + (size_t)h.mirrored * T + D, (size_t)T * 8, (size_t)npars * 8,
                                       (size_t)fresh, cudaMemcpyDeviceToHost, cs));
             h.logw.download(sd + (size_t)fresh * npars, fresh, cs, h.mirrored);
             d2h += fresh * (npars + 1) * 8;
@@ -1011,15 +1033,18 @@ struct Engine {
         }
         PC_CUDA(cudaStreamSynchronize(cs));
         lap(0);
-        DumpMirror& mr = g_mirror;
-        if (mr.rows.size() < (size_t)ndead * npars) mr.rows.resize(std::max((size_t)ndead * npars, mr.rows.size() * 2));
+        if (mr.rows.size() < (size_t)ndead * npars) {   // (not reached with a page-locked mirror: that one was sized before the launch)
+            g_mirror_pin.drop();
+            mr.rows.resize(std::max((size_t)ndead * npars, mr.rows.size() * 2));
+        }
         if (mr.logw.size() < (size_t)ndead) { mr.logw.resize(std::max((size_t)ndead, mr.logw.size() * 2)); mr.lw.resize(mr.logw.size()); }
         if (fresh > 0) {
             const double* lwp = sd + (size_t)fresh * npars;
-            std::memcpy(&mr.rows[(size_t)h.mirrored * npars], sd, (size_t)fresh * npars * sizeof(double));
+            if (!direct) std::memcpy(&mr.rows[(size_t)h.mirrored * npars], sd, (size_t)fresh * npars * sizeof(double));
+            const double* fr = &mr.rows[(size_t)h.mirrored * npars];
             double mx = h.lse_max;
             for (long long i = 0; i < fresh; ++i) {
-                const double v = lwp[i] + sd[(size_t)i * npars + npars - 1];
+                const double v = lwp[i] + fr[(size_t)i * npars + npars - 1];
                 mr.logw[h.mirrored + i] = v;
                 mx = std::max(mx, v);
             }
@@ -1030,9 +1055,8 @@ struct Engine {
             h.lse_max = mx; h.lse_sum = sum;
             h.mirrored = ndead;
         }
-        if (mr.live_rows.size() < (size_t)std::max(nl, 1) * npars) mr.live_rows.resize((size_t)std::max(nl, 1) * npars);
-        std::vector<double>& live_rows = mr.live_rows;
-        if (nl > 0) std::memcpy(live_rows.data(), sl, (size_t)nl * npars * sizeof(double));
+        if (mr.live_rows.size() < (size_t)npars) mr.live_rows.resize((size_t)npars);
+        const double* live_rows = nl > 0 ? sl : mr.live_rows.data();   // the dumper reads the live rows where the copy engine left them
         lap(1);
         std::vector<double>& lw = mr.lw;
         if (lw.empty()) lw.resize(1);
@@ -1047,7 +1071,7 @@ struct Engine {
         std::vector<double> dummy(npars, 0.0);
         lap(2);
         if (dumper)
-            dumper((int)ndead, nl, npars, live_rows.data(), ndead > 0 ? mr.rows.data() : dummy.data(), lw.data(), lz,
+            dumper((int)ndead, nl, npars, const_cast<double*>(live_rows), ndead > 0 ? mr.rows.data() : dummy.data(), lw.data(), lz,
                    std::sqrt(var));
         lap(3);
         if (k.boost_thin > 0.0 && r == 0) collect_boosted(h, cs, ndead, final_call);
@@ -1064,7 +1088,7 @@ struct Engine {
                 cr.point_uid = (long long)rep.point_uid.size() >= ndead ? rep.point_uid.data() : nullptr;
                 cr.cluster_posteriors = S.cluster_posteriors != 0;
             }
-            write_run_files(g_files, g_fstate, D, P, ndead, mr.rows.data(), mr.logw.data(), nl, live_rows.data(), lz,
+            write_run_files(g_files, g_fstate, D, P, ndead, mr.rows.data(), mr.logw.data(), nl, live_rows, lz,
                             std::sqrt(std::fabs(var)), nlike_now, final_call, br.n ? &br : nullptr, cr.n ? &cr : nullptr);
         }
     }
@@ -1762,6 +1786,7 @@ struct Engine {
             if (ctl) {  // size the pinned staging now: (re)allocating pinned memory synchronises with the running kernel
                 g_pin_dead.need((size_t)runs[0].buf.cap_dead * (L.kp.cp.T + 1) * 8);
                 g_pin_live.need((size_t)L.kp.nmax * L.kp.cp.T * 8);
+                g_mirror_pin.reserve(g_mirror.rows, (size_t)runs[0].buf.cap_dead * (L.kp.cp.T - L.kp.cp.D));
             }
             { auto tl = now(); launch_async(); dbg_launch_ms += ms_since(tl); }
             if (ctl) {
