@@ -59,6 +59,12 @@ __global__ void pc_knn_kernel(const double* live, int T, int D, int n, const int
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int TS = D | 1;
     double* xi = (double*)smem + (size_t)warp * D;
+    {   // a negative part marks a point whose part is final (its list is not wanted): a CTA without work leaves before it
+        // stages the live table -- the later rounds of a clustering pass only look at the pieces of the round before
+        bool any = false;
+        for (int i = blockIdx.x * W + warp; i < n; i += gridDim.x * W) any = any || part[i] >= 0;
+        if (!__syncthreads_or(any ? 1 : 0)) return;
+    }
     const double* tab = stage_live_table(live, T, D, n, use_tab ? (double*)smem + (size_t)W * D : nullptr, TS);
     const double* base = tab ? tab : live;
     const int stride = tab ? TS : T;
@@ -67,6 +73,7 @@ __global__ void pc_knn_kernel(const double* live, int T, int D, int n, const int
         for (int k = lane; k < D; k += 32) xi[k] = live[(size_t)i * T + k];
         __syncwarp();
         const int pi = part[i];
+        if (pi < 0) continue;
         double bd[KNN_K];
         int bj[KNN_K];
 #pragma unroll

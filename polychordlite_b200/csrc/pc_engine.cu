@@ -1221,14 +1221,16 @@ struct Engine {
         for (int c = 0; c < nparts0; ++c) origin[c] = c;
         if (d_part.n < (size_t)n) { d_part.alloc(n); d_knn.alloc((size_t)n * KNN_K); }
         h_knn.resize((size_t)n * KNN_K);
-        std::vector<int> uf(n), loc(n), canon(n), old(n), head(n), twin_next(n), firstseen(n), members, bucket, bucket_off;
+        std::vector<int> uf(n), loc(n), canon(n), old(n), head(n), twin_next(n), firstseen(n), members, bucket, bucket_off, part_dev;
         members.reserve(n);
         auto find = [&](int a) { while (uf[a] != a) { uf[a] = uf[uf[a]]; a = uf[a]; } return a; };
         for (int round = 0; round < 64; ++round) {
             bool any = false;
             for (int c = 0; c < nparts; ++c) any = any || !final_part[c];
             if (!any) break;
-            d_part.upload(part.data(), n, stream);
+            part_dev.resize(n);   // final parts are marked: the kernel skips their points
+            for (int i = 0; i < n; ++i) part_dev[i] = final_part[part[i]] ? -1 : part[i];
+            d_part.upload(part_dev.data(), n, stream);
             const int W = 16;
             const bool tab = live_table_bytes(n, D) + (size_t)W * D * 8 <= 200 * 1024;   // the live table fits in shared memory
             const size_t ksm = (size_t)W * D * 8 + (tab ? live_table_bytes(n, D) : 0);
