@@ -1000,7 +1000,7 @@ struct Engine {
     // state: {ndead, logZ, logZ2}; live_src: device records of the live points to report (null: none);
     // cs: the stream the copies are enqueued on (the copy stream while the run kernel is still sampling)
     void dump(int r, pc_dumper_t dumper, long long ndead, double logZ_raw, double logZ2_raw, const double* live_src,
-              int nlive_now, cudaStream_t cs, long long nlike_now = 0, bool final_call = false) {
+              int nlive_now, cudaStream_t cs, long long nlike_now = 0, bool final_call = false, bool live_packed = false) {
         HostRun& h = runs[r];
         const KParams& k = L.kp;
         const int T = k.cp.T, D = k.cp.D, P = k.cp.P, n = nlive_now, npars = D + P + 2;
@@ -1026,7 +1026,10 @@ struct Engine {
             h.logw.download(sd + (size_t)fresh * npars, fresh, cs, h.mirrored);
             d2h += fresh * (npars + 1) * 8;
         }
-        if (nl > 0) {
+        if (nl > 0 && live_packed) {   // the kernel's snapshot: the reported columns only, one piece
+            PC_CUDA(cudaMemcpyAsync(sl, live_src, (size_t)n * npars * 8, cudaMemcpyDeviceToHost, cs));
+            d2h += (long long)n * npars * 8;
+        } else if (nl > 0) {
             PC_CUDA(cudaMemcpy2DAsync(sl, (size_t)npars * 8, live_src + D, (size_t)T * 8, (size_t)npars * 8, (size_t)n,
                                       cudaMemcpyDeviceToHost, cs));
             d2h += (long long)n * npars * 8;
@@ -1777,7 +1780,8 @@ struct Engine {
             auto ts = now();
             const long long nd = ctl->ndead;
             const double lz = ctl->logZ, lz2 = ctl->logZ2;
-            dump(0, dumper, nd, lz, lz2, runs[0].live_snap.p + (size_t)((handled + 1) & 1) * L.kp.nmax * L.kp.cp.T, ctl->nlive, g_copy_stream, ctl->nlike);
+            dump(0, dumper, nd, lz, lz2, runs[0].live_snap.p + (size_t)((handled + 1) & 1) * L.kp.nmax * (L.kp.cp.T - L.kp.cp.D), ctl->nlive,
+                 g_copy_stream, ctl->nlike, false, true);
             ++handled;
             ctl->ack_seq = handled;
             dbg_service_ms += ms_since(ts);

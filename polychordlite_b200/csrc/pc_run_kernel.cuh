@@ -1061,10 +1061,15 @@ __device__ inline void shard_scatter(const KParams& p, const RunBuf& rb, DevRun*
 // Two halves by dump parity: the half being written belongs to the dump before the last, which the host has acknowledged
 // (publish_dump waits for the acknowledgement of dump s-1 before it publishes dump s).
 __device__ inline void snapshot_share(const KParams& p, const RunBuf& rb, DevRun* st, int cta, int NG) {
-    const size_t nd = (size_t)vload(&st->n) * p.cp.T;
-    double* snap = rb.live_snap + (size_t)((vload(&st->dump_pub) + 1) & 1) * p.nmax * p.cp.T;
+    // (only the columns the dumper reports, [theta, phi, birth, logL], packed: the host copies them in one piece)
+    const int T = p.cp.T, D = p.cp.D, np = T - D;
+    const size_t nd = (size_t)vload(&st->n) * np;
+    double* snap = rb.live_snap + (size_t)((vload(&st->dump_pub) + 1) & 1) * p.nmax * np;
     const size_t chunk = (nd + NG - 1) / NG, e0 = min(nd, (size_t)cta * chunk), e1 = min(nd, e0 + chunk);
-    for (size_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) snap[e] = __ldcg(rb.live + e);
+    for (size_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const size_t row = e / np;
+        snap[e] = __ldcg(rb.live + row * T + D + (e - row * np));
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();
